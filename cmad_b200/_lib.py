@@ -1,0 +1,127 @@
+"""ctypes binding of ``libcmad_b200.so`` (the C-ABI in ``include/cmad_b200.h``).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc,
+sm_100a).  There is no CPU fallback: if the library is missing or fails to
+load, importing any compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "lib", "libcmad_b200.so")
+INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
+
+SOURCES = ["api.cu", "mp_update.cu", "elastic_update.cu", "mp_sens.cu", "fe_block.cu"]
+
+# ---- enums (mirror include/cmad_b200.h) ---------------------------------
+OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(5)
+MODEL_SMALL_ELASTIC_PLASTIC, MODEL_ELASTIC = 0, 1
+YIELD_J2, YIELD_HILL, YIELD_HOSFORD = 0, 1, 2
+ELASTIC_PAIRS = [("E", "nu"), ("E", "mu"), ("E", "kappa"), ("E", "lambda"), ("kappa", "mu"),
+                 ("kappa", "nu"), ("kappa", "lambda"), ("lambda", "mu"), ("lambda", "nu"),
+                 ("mu", "nu")]
+HARD_VOCE, HARD_LINEAR = 1, 2
+(P_EL0, P_EL1, P_Y, P_VOCE_S, P_VOCE_D, P_LIN_K, P_HILL_F, P_HILL_G, P_HILL_H, P_HILL_L,
+ P_HILL_M, P_HILL_N, P_HOSFORD_A, P_Q00) = range(14)
+NUM_PARAM_IDS = P_Q00 + 9
+MAX_ACTIVE = 16
+NEWTON_TRACED, NEWTON_IMPERATIVE = 0, 1
+
+
+class Material(C.Structure):
+    _fields_ = [("model", C.c_int32), ("yield_", C.c_int32), ("elastic_pair", C.c_int32),
+                ("hardening_mask", C.c_int32), ("elastic", C.c_double * 2), ("Y", C.c_double),
+                ("voce_S", C.c_double), ("voce_D", C.c_double), ("linear_K", C.c_double),
+                ("hill", C.c_double * 6), ("hosford_a", C.c_double), ("Q", C.c_double * 9),
+                ("yield_tol", C.c_double)]
+
+
+class Newton(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("max_iters", C.c_int32), ("ls_max_evals", C.c_int32),
+                ("reserved", C.c_int32), ("abs_tol", C.c_double), ("rel_tol", C.c_double),
+                ("ls_c1", C.c_double), ("ls_bmin", C.c_double), ("ls_bmax", C.c_double)]
+
+
+class MpBuffers(C.Structure):
+    _fields_ = [("n", C.c_int64), ("ld", C.c_int64), ("strain_comps", C.c_int32),
+                ("reserved", C.c_int32), ("xi_prev", C.c_void_p), ("strain", C.c_void_p), ("xi_init", C.c_void_p),
+                ("xi", C.c_void_p), ("sigma", C.c_void_p), ("dsig_deps", C.c_void_p),
+                ("dxi_deps", C.c_void_p), ("dC_dp", C.c_void_p), ("dC_dxi", C.c_void_p),
+                ("dC_dxi_prev", C.c_void_p), ("iters", C.c_void_p), ("flags", C.c_void_p),
+                ("cnorm", C.c_void_p), ("C", C.c_void_p)]
+
+
+class CmadxError(RuntimeError):
+    pass
+
+
+def nvcc_command(out: str = LIB_PATH) -> list[str]:
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
+            "-std=c++17", "-Xcompiler", "-fPIC", "-I" + INCLUDE, "-shared", "-o", out] + srcs
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into ``cmad_b200/lib/libcmad_b200.so``."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "cmad_b200.h")]
+    newest = max(os.path.getmtime(s) for s in srcs)
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
+        return LIB_PATH
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    cmd = nvcc_command()
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the shared library; raise loudly if it is absent (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CmadxError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  cmad_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.cmadx_version.restype = C.c_int
+    L.cmadx_error_string.restype = C.c_char_p
+    L.cmadx_error_string.argtypes = [C.c_int]
+    L.cmadx_last_cuda_error.restype = C.c_char_p
+    L.cmadx_launch_count.restype = C.c_int64
+    L.cmadx_lame.argtypes = [C.POINTER(Material), C.POINTER(C.c_double)]
+    mp_args = [C.POINTER(Material), C.POINTER(Newton), C.POINTER(C.c_int32), C.c_int32,
+               C.POINTER(MpBuffers)]
+    L.cmadx_mp_update.argtypes = mp_args + [C.c_void_p]
+    L.cmadx_mp_update_host.argtypes = mp_args + [C.c_int, C.c_int64]
+    L.cmadx_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_void_p]
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = "cmadx call") -> None:
+    if rc != OK:
+        L = lib()
+        msg = L.cmadx_error_string(rc).decode()
+        if rc == ECUDA:
+            msg += " (" + L.cmadx_last_cuda_error().decode() + ")"
+        if rc == EINVAL:
+            raise ValueError(f"{what}: {msg}")
+        if rc == EUNSUPPORTED:
+            raise NotImplementedError(f"{what}: {msg}")
+        raise CmadxError(f"{what}: {msg}")
+
+
+def exported_symbols() -> list[str]:
+    """Function names declared in include/cmad_b200.h (for the load test)."""
+    import re
+    text = open(os.path.join(INCLUDE, "cmad_b200.h")).read()
+    return sorted(set(re.findall(r"\b(cmadx_[a-z0-9_]+)\s*\(", text)))

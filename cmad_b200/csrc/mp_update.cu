@@ -1,0 +1,301 @@
+// K1 - batched material-point constitutive update (sm_100a).
+//
+// One thread per point.  Inputs/outputs are component-major (SoA) so every
+// load/store of a warp is one fully coalesced 256-byte transaction; the local
+// 7x7 system, its LU factors and all derivative blocks stay in registers.  The
+// Newton loop exits warp-wide by ballot.  Outputs are written with streaming
+// stores (write-once data, keep L2 for the inputs of the next launch).
+//
+// Replaces, for a batch of points (reference file:line):
+//   cmad/models/nonlinear_solver.py:88-174 (make_newton_solve + IFT rule) or
+//   :14-85 (newton_solve), cmad/models/model.py:121-166 (AD Jacobians),
+//   cmad/parameters/parameters.py:368-377 (active-column selection).
+#include "mp_update.cuh"
+
+namespace cmadx {
+
+namespace {
+
+CMADX_DEV void st(double* p, int64_t c, int64_t ld, int64_t i, double v) {
+    __stcs(p + c * ld + i, v);
+}
+
+// 6x6 maps between global and material symmetric-tensor components for a
+// rotation Q (cmad/models/small_elastic_plastic.py:44-62, 318-319):
+//   T[c][b] = d(Q^T e Q)_c / d e_b ,  S[a][c] = d(Q s Q^T)_a / d s_c
+CMADX_DEV void rot_maps(const double* Q, double (&T)[6][6], double (&S)[6][6]) {
+    const int ci[6] = {0, 0, 0, 1, 1, 2}, cj[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            const int i = ci[c], j = cj[c], k = ci[b], l = cj[b];
+            double t = Q[3 * k + i] * Q[3 * l + j];
+            double s = Q[3 * i + k] * Q[3 * j + l];
+            if (k != l) { t += Q[3 * l + i] * Q[3 * k + j]; s += Q[3 * i + l] * Q[3 * j + k]; }
+            T[c][b] = t;
+            S[c][b] = s;
+        }
+}
+
+template <int YK, bool ROT>
+__global__ void __launch_bounds__(MP_BLOCK)
+mp_update_kernel(const __grid_constant__ MpArgs A) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < A.b.n;
+    const int64_t ld = A.b.ld;
+    const DevMat& m = A.m;
+
+    double xp[7], x[7], e[6];
+    if (live) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) xp[c] = __ldg(A.b.xi_prev + c * ld + i);
+        if (A.b.strain_comps == 6) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) e[c] = __ldg(A.b.strain + c * ld + i);
+        } else {
+            double g[9];
+#pragma unroll
+            for (int c = 0; c < 9; ++c) g[c] = __ldg(A.b.strain + c * ld + i);
+            e[0] = g[0]; e[3] = g[4]; e[5] = g[8];
+            e[1] = 0.5 * (g[1] + g[3]); e[2] = 0.5 * (g[2] + g[6]); e[4] = 0.5 * (g[5] + g[7]);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) xp[c] = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) e[c] = 0.0;
+    }
+    double em[6];
+    if (ROT) {
+        double T[6][6], S[6][6];
+        rot_maps(m.Q, T, S);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) s = fma(T[c][b], e[b], s);
+            em[c] = s;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) em[c] = e[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 7; ++c) x[c] = xp[c];
+    if (live && A.b.xi_init) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) x[c] = __ldg(A.b.xi_init + c * ld + i);
+    }
+
+    SepPoint<YK> pt;
+    double Cres[7];
+    const NewtonResult nr = local_newton<SepPoint<YK>, 7>(m, A.nw, pt, x, xp, em, live, Cres);
+    if (!live) return;
+    if (A.b.C) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) st(A.b.C, c, ld, i, Cres[c]);
+    }
+
+    // ---------------------------------------------------------------- outputs
+    if (A.b.iters) A.b.iters[i] = nr.iters;
+    if (A.b.flags) A.b.flags[i] = nr.flag_entry | ((pt.plastic ? 1 : 0) << 1);
+    if (A.b.cnorm) A.b.cnorm[i] = nr.cnorm;
+    if (A.b.xi) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) st(A.b.xi, c, ld, i, x[c]);
+    }
+    double ee[6], sig[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) ee[a] = em[a] - x[a];
+    {
+        const double ltr = m.lam * (ee[0] + ee[3] + ee[5]);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) sig[a] = is_diag(a) ? fma(m.two_mu, ee[a], ltr) : m.two_mu * ee[a];
+    }
+    if (A.b.sigma) {
+        if (ROT) {
+            double T[6][6], S[6][6];
+            rot_maps(m.Q, T, S);
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                double s = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) s = fma(S[a][c], sig[c], s);
+                st(A.b.sigma, a, ld, i, s);
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) st(A.b.sigma, a, ld, i, sig[a]);
+        }
+    }
+    const double dg = x[6] - xp[6];
+    const bool pl = pt.plastic;
+
+    // dC/dxi_prev: plastic rows a<6: -I and +n in the alpha column; yield row 0
+    if (A.b.dC_dxi_prev) {
+#pragma unroll
+        for (int r = 0; r < 7; ++r)
+#pragma unroll
+            for (int c = 0; c < 7; ++c) {
+                double v = (r == c) ? -1.0 : 0.0;
+                if (pl) {
+                    if (r == 6) v = 0.0;
+                    else if (c == 6) v = pt.n[r];
+                }
+                st(A.b.dC_dxi_prev, r * 7 + c, ld, i, v);
+            }
+    }
+
+    // dC/dp at (x*, x_prev): elastic branch -> 0 (C_e holds no parameters)
+    if (A.b.dC_dp && A.n_active > 0) {
+        const int na = A.n_active;
+        double Mee[6];      // (dn/dsigma : ee)_a
+        double nee = 0.0;   // n : ee
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) s = fma(pt.yf.M(a, b), ee[b], s);
+            Mee[a] = s;
+            nee = fma(mult(a) * pt.n[a], ee[a], nee);
+        }
+        const double imu = 1.0 / m.mu;
+        for (int c = 0; c < na; ++c) {
+            const int pid = A.pid[c];
+            double col[7] = {0, 0, 0, 0, 0, 0, 0};
+            if (pl) {
+                if (pid == CMADX_P_EL0 || pid == CMADX_P_EL1) {
+                    // only mu matters: all three surfaces are pressure-insensitive
+                    const double dmu = m.dmu[pid - CMADX_P_EL0];
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) col[a] = -2.0 * dg * Mee[a] * dmu;
+                    col[6] = (nee - pt.f) * imu * dmu;
+                } else if (pid == CMADX_P_Y) {
+                    col[6] = -m.inv_two_mu;
+                } else if (pid == CMADX_P_VOCE_S) {
+                    col[6] = -(1.0 - pt.eD) * m.inv_two_mu;
+                } else if (pid == CMADX_P_VOCE_D) {
+                    col[6] = -m.S * x[6] * pt.eD * m.inv_two_mu;
+                } else if (pid == CMADX_P_LIN_K) {
+                    col[6] = -x[6] * m.inv_two_mu;
+                } else {
+                    double dphi, dn[6];
+                    if (pt.yf.dparam(m, pid, sig, dphi, dn)) {
+#pragma unroll
+                        for (int a = 0; a < 6; ++a) col[a] = -dg * dn[a];
+                        col[6] = dphi * m.inv_two_mu;
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 7; ++r) st(A.b.dC_dp, (int64_t)r * na + c, ld, i, col[r]);
+        }
+    }
+
+    const bool want_ift = A.b.dsig_deps || A.b.dxi_deps;
+    if (!want_ift && !A.b.dC_dxi) return;
+
+    RegLU<7> lu;
+    pt.jacobian(m, dg, lu.a);
+    if (A.b.dC_dxi) {
+#pragma unroll
+        for (int r = 0; r < 7; ++r)
+#pragma unroll
+            for (int c = 0; c < 7; ++c) st(A.b.dC_dxi, r * 7 + c, ld, i, lu.a[r][c]);
+    }
+    if (!want_ift) return;
+
+    // IFT (nonlinear_solver.py:158-171).  In material axes dC/de = -(A[:, :6] - E),
+    // E = [I6; 0], so dx/de = E - A^{-1}E and d sigma/de = Cel . (A^{-1})[0:6,0:6].
+    if (__any_sync(__activemask(), pl)) lu.factor();
+    if (!ROT) {
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            double X[7];
+#pragma unroll
+            for (int r = 0; r < 7; ++r) X[r] = (r == b) ? 1.0 : 0.0;
+            if (pl) lu.solve(X);
+            if (A.b.dxi_deps) {
+#pragma unroll
+                for (int r = 0; r < 7; ++r) st(A.b.dxi_deps, r * 6 + b, ld, i, ((r == b) ? 1.0 : 0.0) - X[r]);
+            }
+            if (A.b.dsig_deps) {
+                const double ltr = m.lam * (X[0] + X[3] + X[5]);
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+                    st(A.b.dsig_deps, a * 6 + b, ld, i, is_diag(a) ? fma(m.two_mu, X[a], ltr) : m.two_mu * X[a]);
+            }
+        }
+    } else {
+        double Dm[6][6], Xm[7][6];
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            double X[7];
+#pragma unroll
+            for (int r = 0; r < 7; ++r) X[r] = (r == b) ? 1.0 : 0.0;
+            if (pl) lu.solve(X);
+            const double ltr = m.lam * (X[0] + X[3] + X[5]);
+#pragma unroll
+            for (int a = 0; a < 6; ++a) Dm[a][b] = is_diag(a) ? fma(m.two_mu, X[a], ltr) : m.two_mu * X[a];
+#pragma unroll
+            for (int r = 0; r < 7; ++r) Xm[r][b] = ((r == b) ? 1.0 : 0.0) - X[r];
+        }
+        double T[6][6], S[6][6];
+        rot_maps(m.Q, T, S);
+        if (A.b.dxi_deps) {
+#pragma unroll
+            for (int r = 0; r < 7; ++r)
+#pragma unroll
+                for (int b = 0; b < 6; ++b) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) s = fma(Xm[r][c], T[c][b], s);
+                    st(A.b.dxi_deps, r * 6 + b, ld, i, s);
+                }
+        }
+        if (A.b.dsig_deps) {
+            double DT[6][6];
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int b = 0; b < 6; ++b) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) s = fma(Dm[a][c], T[c][b], s);
+                    DT[a][b] = s;
+                }
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int b = 0; b < 6; ++b) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) s = fma(S[a][c], DT[c][b], s);
+                    st(A.b.dsig_deps, a * 6 + b, ld, i, s);
+                }
+        }
+    }
+}
+
+template <int YK>
+cudaError_t launch_yk(const MpArgs& A, cudaStream_t stream) {
+    const int64_t nblk = (A.b.n + MP_BLOCK - 1) / MP_BLOCK;
+    if (nblk == 0) return cudaSuccess;
+    if (A.m.rot) mp_update_kernel<YK, true><<<(unsigned)nblk, MP_BLOCK, 0, stream>>>(A);
+    else mp_update_kernel<YK, false><<<(unsigned)nblk, MP_BLOCK, 0, stream>>>(A);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_mp_update_sep(const MpArgs& A, cudaStream_t stream) {
+    switch (A.m.yield) {
+    case CMADX_YIELD_J2: return launch_yk<CMADX_YIELD_J2>(A, stream);
+    case CMADX_YIELD_HILL: return launch_yk<CMADX_YIELD_HILL>(A, stream);
+    case CMADX_YIELD_HOSFORD: return launch_yk<CMADX_YIELD_HOSFORD>(A, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace cmadx

@@ -1,0 +1,24 @@
+// Shared launch-argument structs of the material-point kernels.
+#pragma once
+#include "point_solver.cuh"
+
+namespace cmadx {
+
+constexpr int MP_BLOCK = 128;
+
+struct MpArgs {
+    DevMat m;
+    DevNewton nw;
+    int n_active;
+    int pid[CMADX_MAX_ACTIVE];
+    cmadx_mp_buffers_t b;
+};
+
+// host-side: validate + convert the C-ABI structs (defined in api.cu)
+int make_dev_mat(const cmadx_material_t* mat, DevMat* out);
+int make_dev_newton(const cmadx_newton_t* nw, DevNewton* out);
+
+cudaError_t launch_mp_update_sep(const MpArgs& A, cudaStream_t stream);
+cudaError_t launch_mp_update_elastic(const MpArgs& A, cudaStream_t stream);
+
+}  // namespace cmadx

@@ -1,0 +1,492 @@
+// Per-material-point device routines of the constitutive update: residual,
+// hand-derived Jacobian, register-resident 7x7 LU with partial pivoting, the
+// reference-identical local Newton (traced + imperative flavours) with its
+// quadratic backtracking line search, and the IFT / parameter-sensitivity
+// outputs.  Everything lives in registers: one thread owns one point.
+//
+// Semantics follow the reference (sandialabs/cmad), file:line relative to its
+// tree; nothing here is translated from it - the reference obtains every
+// derivative by tracing JAX AD, this file derives them in closed form:
+//   residual / branch select  cmad/models/small_elastic_plastic.py:238-302,
+//                             cmad/models/paths.py:26-27
+//   effective stresses        cmad/models/effective_stress.py:30-52,168-177
+//   hardening                 cmad/models/hardening.py:9-34
+//   traced Newton + IFT       cmad/models/nonlinear_solver.py:88-174
+//   imperative Newton         cmad/models/nonlinear_solver.py:14-85
+//   line search               cmad/util/line_search.py:74-85,95-189
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "cmad_b200.h"
+
+namespace cmadx {
+
+struct DevMat {
+    double lam, mu, two_mu, inv_two_mu;
+    double Y, S, D, K;
+    double hill[6];
+    double a;
+    double Q[9];
+    double yield_tol;
+    double dlam[2], dmu[2];   // d(lambda, mu)/d(elastic[0..1])
+    int hmask, rot, model, yield;
+};
+
+struct DevNewton {
+    int mode, max_iters, ls_max, pad;
+    double abs_tol, rel_tol, c1, bmin, bmax;
+};
+
+#define CMADX_DEV __device__ __forceinline__
+
+// component bookkeeping for the packing xx,xy,xz,yy,yz,zz
+CMADX_DEV constexpr bool is_diag(int a) { return a == 0 || a == 3 || a == 5; }
+CMADX_DEV constexpr double mult(int a) { return is_diag(a) ? 1.0 : 2.0; }
+
+// --------------------------------------------------------------------------
+// Effective stresses.  Each provides, for a symmetric sigma (6 comps):
+//   eval   : phi and the normal n_a = d phi / d sigma_a (single tensor entry,
+//            as jax.grad over the full 3x3 gives it), keeping what hess needs
+//   M(a,b) : d n_a / d(symmetric perturbation of component b)
+//   dparam : d phi / d theta and d n / d theta for a yield-surface parameter
+// All three surfaces are pressure-insensitive (n : I = 0, M : I = 0), which the
+// Jacobian assembly below uses.
+// --------------------------------------------------------------------------
+template <int YK> struct YieldFn;
+
+template <> struct YieldFn<CMADX_YIELD_J2> {
+    double c;       // sqrt(3/2)/||s||
+    double sh[6];   // s/||s||
+    CMADX_DEV void eval(const DevMat&, const double (&sig)[6], double& phi, double (&n)[6]) {
+        const double h = (sig[0] + sig[3] + sig[5]) / 3.0;
+        double s[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) s[a] = is_diag(a) ? sig[a] - h : sig[a];
+        double ss = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) ss = fma(mult(a) * s[a], s[a], ss);
+        const double sn = sqrt(ss);
+        const double r32 = 1.2247448713915890491;   // sqrt(3/2)
+        phi = r32 * sn;
+        const double inv = 1.0 / sn;                // inf at zero deviator -> NaN normal (as JAX)
+        c = r32 * inv;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) { sh[a] = s[a] * inv; n[a] = r32 * sh[a]; }
+    }
+    CMADX_DEV double M(int a, int b) const {
+        double v = -sh[a] * sh[b] * mult(b);
+        if (a == b) v += 1.0;
+        if (is_diag(a) && is_diag(b)) v -= 1.0 / 3.0;
+        return c * v;
+    }
+    CMADX_DEV bool dparam(const DevMat&, int, const double (&)[6], double&, double (&)[6]) const {
+        return false;
+    }
+};
+
+template <> struct YieldFn<CMADX_YIELD_HILL> {
+    double iphi;     // 1/phi
+    double nn[6];    // normal
+    double F, G, H, L, Mm, N;
+    double d12, d20, d01;
+    CMADX_DEV void eval(const DevMat& m, const double (&sig)[6], double& phi, double (&n)[6]) {
+        F = m.hill[0]; G = m.hill[1]; H = m.hill[2]; L = m.hill[3]; Mm = m.hill[4]; N = m.hill[5];
+        d12 = sig[3] - sig[5]; d20 = sig[5] - sig[0]; d01 = sig[0] - sig[3];
+        const double q = F * d12 * d12 + G * d20 * d20 + H * d01 * d01
+                         + L * (2.0 * sig[4] * sig[4]) + Mm * (2.0 * sig[2] * sig[2])
+                         + N * (2.0 * sig[1] * sig[1]);
+        phi = sqrt(q);
+        iphi = 1.0 / phi;
+        n[0] = (H * d01 - G * d20) * iphi;
+        n[3] = (F * d12 - H * d01) * iphi;
+        n[5] = (G * d20 - F * d12) * iphi;
+        n[1] = N * sig[1] * iphi;
+        n[2] = Mm * sig[2] * iphi;
+        n[4] = L * sig[4] * iphi;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) nn[a] = n[a];
+    }
+    CMADX_DEV double hq(int a, int b) const {   // (d2 q / d sigma_a d sym(b)) / 2
+        if (a == 0 && b == 0) return G + H;
+        if (a == 3 && b == 3) return F + H;
+        if (a == 5 && b == 5) return F + G;
+        if ((a == 0 && b == 3) || (a == 3 && b == 0)) return -H;
+        if ((a == 0 && b == 5) || (a == 5 && b == 0)) return -G;
+        if ((a == 3 && b == 5) || (a == 5 && b == 3)) return -F;
+        if (a == 1 && b == 1) return N;
+        if (a == 2 && b == 2) return Mm;
+        if (a == 4 && b == 4) return L;
+        return 0.0;
+    }
+    CMADX_DEV double M(int a, int b) const {
+        return (hq(a, b) - nn[a] * nn[b] * mult(b)) * iphi;
+    }
+    CMADX_DEV bool dparam(const DevMat&, int pid, const double (&sig)[6], double& dphi,
+                          double (&dn)[6]) const {
+        if (pid < CMADX_P_HILL_F || pid > CMADX_P_HILL_N) return false;
+        double dq = 0.0, dg[6] = {0, 0, 0, 0, 0, 0};   // dq/dtheta, d(grad q)/dtheta
+        switch (pid) {
+        case CMADX_P_HILL_F: dq = d12 * d12; dg[3] = 2.0 * d12; dg[5] = -2.0 * d12; break;
+        case CMADX_P_HILL_G: dq = d20 * d20; dg[5] = 2.0 * d20; dg[0] = -2.0 * d20; break;
+        case CMADX_P_HILL_H: dq = d01 * d01; dg[0] = 2.0 * d01; dg[3] = -2.0 * d01; break;
+        case CMADX_P_HILL_L: dq = 2.0 * sig[4] * sig[4]; dg[4] = 2.0 * sig[4]; break;
+        case CMADX_P_HILL_M: dq = 2.0 * sig[2] * sig[2]; dg[2] = 2.0 * sig[2]; break;
+        default:             dq = 2.0 * sig[1] * sig[1]; dg[1] = 2.0 * sig[1]; break;
+        }
+        dphi = 0.5 * dq * iphi;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) dn[a] = (0.5 * dg[a] - nn[a] * dphi) * iphi;
+        return true;
+    }
+};
+
+// Hosford: phi = vm * (1/2 sum_i |Delta_i/vm|^a)^(1/a) on the *diagonal* stress
+// entries only (the reference's documented limitation).  The vm scaling cancels
+// analytically (phi is the plain a-norm of the differences); it is kept for the
+// value so large exponents do not overflow, and dropped from the derivatives.
+template <> struct YieldFn<CMADX_YIELD_HOSFORD> {
+    double g[3];       // d phi / d Delta_i
+    double w[3];       // 1/2 r_i^(a-2)
+    double iphi, am1;
+    CMADX_DEV void eval(const DevMat& m, const double (&sig)[6], double& phi, double (&n)[6]) {
+        const double a = m.a;
+        const double h = (sig[0] + sig[3] + sig[5]) / 3.0;
+        double ss = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double s = is_diag(k) ? sig[k] - h : sig[k];
+            ss = fma(mult(k) * s, s, ss);
+        }
+        const double vm = 1.2247448713915890491 * sqrt(ss);
+        const double ivm = 1.0 / vm;
+        const double dl[3] = {sig[0] - sig[3], sig[3] - sig[5], sig[5] - sig[0]};
+        double q[3], sq = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { q[i] = pow(fabs(dl[i] * ivm), a); sq += q[i]; }
+        sq *= 0.5;
+        phi = vm * pow(sq, 1.0 / a);
+        iphi = 1.0 / phi;
+        am1 = a - 1.0;
+        const double isq = 1.0 / sq;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double r = fabs(dl[i]) * iphi;            // |Delta_i|/phi
+            const double ra = q[i] * isq;                   // r^a
+            const double t = (dl[i] > 0.0) - (dl[i] < 0.0); // sign, 0 at 0
+            const double ir = (r > 0.0) ? 1.0 / r : 0.0;
+            g[i] = 0.5 * t * ra * ir;                       // 1/2 t r^(a-1)
+            w[i] = 0.5 * ra * ir * ir;                      // 1/2 r^(a-2)
+        }
+        n[0] = g[0] - g[2]; n[3] = g[1] - g[0]; n[5] = g[2] - g[1];
+        n[1] = 0.0; n[2] = 0.0; n[4] = 0.0;
+    }
+    // G_ij = d2 phi / dDelta_i dDelta_j = (a-1)/phi (delta_ij w_i - g_i g_j)
+    CMADX_DEV double Gd(int i, int j) const {
+        double v = -g[i] * g[j];
+        if (i == j) v += w[i];
+        return am1 * iphi * v;
+    }
+    CMADX_DEV double M(int a, int b) const {
+        if (!is_diag(a) || !is_diag(b)) return 0.0;
+        // Delta = B sigma_diag, B rows: (1,-1,0),(0,1,-1),(-1,0,1); M = B^T G B
+        const int ia = (a == 0) ? 0 : (a == 3 ? 1 : 2);
+        const int ib = (b == 0) ? 0 : (b == 3 ? 1 : 2);
+        // column ia of B: +1 at row ia, -1 at row (ia+2)%3
+        const int pa = ia, ma = (ia + 2) % 3, pb = ib, mb = (ib + 2) % 3;
+        return Gd(pa, pb) - Gd(pa, mb) - Gd(ma, pb) + Gd(ma, mb);
+    }
+    CMADX_DEV bool dparam(const DevMat&, int, const double (&)[6], double&, double (&)[6]) const {
+        return false;   // d/d(hosford a) is not provided by the closed-form kernels
+    }
+};
+
+// --------------------------------------------------------------------------
+// register-resident dense LU with partial pivoting (row swaps as predicated
+// selects; the swap decisions are recorded so right-hand sides can be
+// permuted later).  a[k][k] holds 1/pivot after factor().
+// --------------------------------------------------------------------------
+template <int N>
+struct RegLU {
+    double a[N][N];
+    unsigned swaps;
+    CMADX_DEV void factor() {
+        swaps = 0u;
+        int bit = 0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) {
+                const bool sw = fabs(a[i][k]) > fabs(a[k][k]);
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    const double u = a[k][j], v = a[i][j];
+                    a[k][j] = sw ? v : u;
+                    a[i][j] = sw ? u : v;
+                }
+                swaps |= (sw ? 1u : 0u) << bit;
+                ++bit;
+            }
+            const double rp = 1.0 / a[k][k];
+            a[k][k] = rp;
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) {
+                const double l = a[i][k] * rp;
+                a[i][k] = l;
+#pragma unroll
+                for (int j = k + 1; j < N; ++j) a[i][j] = fma(-l, a[k][j], a[i][j]);
+            }
+        }
+    }
+    CMADX_DEV void solve(double (&b)[N]) const {
+        int bit = 0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) {
+                const bool sw = (swaps >> bit) & 1u;
+                const double u = b[k], v = b[i];
+                b[k] = sw ? v : u;
+                b[i] = sw ? u : v;
+                ++bit;
+            }
+        }
+#pragma unroll
+        for (int i = 1; i < N; ++i) {
+#pragma unroll
+            for (int j = 0; j < i; ++j) b[i] = fma(-a[i][j], b[j], b[i]);
+        }
+#pragma unroll
+        for (int i = N - 1; i >= 0; --i) {
+            double s = b[i];
+#pragma unroll
+            for (int j = i + 1; j < N; ++j) s = fma(-a[i][j], b[j], s);
+            b[i] = s * a[i][i];
+        }
+    }
+};
+
+// --------------------------------------------------------------------------
+// SmallElasticPlastic, FULL_3D.  State x = [ep(6), alpha], strain `em` already
+// in material axes.
+// --------------------------------------------------------------------------
+template <int YK>
+struct SepPoint {
+    static constexpr int N = 7;
+    YieldFn<YK> yf;
+    double n[6];      // yield normal at the last evaluated state
+    double f, eD;     // yield function, exp(-D alpha)
+    bool plastic;
+
+    CMADX_DEV void residual(const DevMat& m, const double (&x)[7], const double (&xp)[7],
+                            const double (&em)[6], double (&C)[7]) {
+        double ee[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) ee[a] = em[a] - x[a];
+        const double ltr = m.lam * (ee[0] + ee[3] + ee[5]);
+        double sig[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) sig[a] = is_diag(a) ? fma(m.two_mu, ee[a], ltr) : m.two_mu * ee[a];
+        double phi;
+        yf.eval(m, sig, phi, n);
+        double Hd = 0.0;
+        eD = 0.0;
+        if (m.hmask & CMADX_HARD_VOCE) { eD = exp(-m.D * x[6]); Hd = m.S * (1.0 - eD); }
+        if (m.hmask & CMADX_HARD_LINEAR) Hd = fma(m.K, x[6], Hd);
+        f = (phi - (m.Y + Hd)) * m.inv_two_mu;
+        const double dg = x[6] - xp[6];
+        plastic = (f > m.yield_tol) || (fabs(f) < m.yield_tol);   // paths.py:26
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const double ce = x[a] - xp[a];
+            C[a] = plastic ? fma(-dg, n[a], ce) : ce;
+        }
+        C[6] = plastic ? f : dg;
+    }
+
+    // dC/dx at the last evaluated state (dg = alpha - alpha_prev there)
+    CMADX_DEV void jacobian(const DevMat& m, double dg, double (&J)[7][7]) const {
+        if (plastic) {
+            const double s = dg * m.two_mu;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+#pragma unroll
+                for (int b = 0; b < 6; ++b) J[a][b] = fma(s, yf.M(a, b), (a == b) ? 1.0 : 0.0);
+                J[a][6] = -n[a];
+                J[6][a] = -mult(a) * n[a];
+            }
+            double Hp = 0.0;
+            if (m.hmask & CMADX_HARD_VOCE) Hp = m.S * m.D * eD;
+            if (m.hmask & CMADX_HARD_LINEAR) Hp += m.K;
+            J[6][6] = -Hp * m.inv_two_mu;
+        } else {
+#pragma unroll
+            for (int a = 0; a < 7; ++a)
+#pragma unroll
+                for (int b = 0; b < 7; ++b) J[a][b] = (a == b) ? 1.0 : 0.0;
+        }
+    }
+};
+
+template <int N> CMADX_DEV double normN(const double (&v)[N]) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) s = fma(v[i], v[i], s);
+    return sqrt(s);
+}
+template <int N> CMADX_DEV double dotN(const double (&u)[N], const double (&v)[N]) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) s = fma(u[i], v[i], s);
+    return s;
+}
+
+// Elastic model (cmad/models/elastic.py:139-173): state x = cauchy(6),
+// C = vec6(x - sigma_el(eps)) / (2 mu), sigma_el = kappa tr(eps) I + 2 mu dev(eps).
+struct ElasticPoint {
+    static constexpr int N = 6;
+    bool plastic;
+    CMADX_DEV void residual(const DevMat& m, const double (&x)[6], const double (&)[6],
+                            const double (&em)[6], double (&C)[6]) {
+        const double tr = em[0] + em[3] + em[5];
+        const double kappa = m.lam + 2.0 * m.mu / 3.0;
+        const double kt = kappa * tr;
+        const double t3 = tr / 3.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const double se = is_diag(a) ? fma(m.two_mu, em[a] - t3, kt) : m.two_mu * em[a];
+            C[a] = (x[a] - se) * m.inv_two_mu;
+        }
+        plastic = false;
+    }
+    CMADX_DEV void jacobian(const DevMat& m, double, double (&J)[6][6]) const {
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = 0; b < 6; ++b) J[a][b] = (a == b) ? m.inv_two_mu : 0.0;
+    }
+};
+
+struct NewtonResult {
+    int iters;
+    int flag_entry;
+    double cnorm;
+};
+
+// Local Newton for one point; `live` lanes take part, the loop exit is decided
+// warp-wide by ballot so the whole warp leaves together.  On return x is the
+// solution, C the residual there, and pt holds the state (n, f, plastic, yield
+// internals) at x.
+// Pt provides residual(m, x, xp, em, C), jacobian(m, dgamma, J) and `plastic`.
+template <class Pt, int N>
+CMADX_DEV NewtonResult local_newton(const DevMat& m, const DevNewton& nw, Pt& pt,
+                                    double (&x)[N], const double (&xp)[N],
+                                    const double (&em)[6], bool live, double (&C)[N]) {
+    NewtonResult r;
+    pt.residual(m, x, xp, em, C);
+    r.flag_entry = pt.plastic ? 1 : 0;
+    double n0 = normN<N>(C);
+    double nc = n0;
+    int ii = 0;
+    bool done = !live || nw.max_iters <= 0;
+    bool fresh = true;   // pt state corresponds to x
+    const unsigned full = 0xffffffffu;
+    if (nw.mode == CMADX_NEWTON_TRACED) {
+        while (__any_sync(full, !done)) {
+            if (!done) {
+                nc = normN<N>(C);
+                const double rel = nc / n0;                      // 0/0 -> NaN: test is false
+                if (rel < nw.rel_tol || nc < nw.abs_tol) {
+                    done = true;
+                } else {
+                    if (!fresh) { double Ct[N]; pt.residual(m, x, xp, em, Ct); }
+                    double dx[N];
+                    {
+                        RegLU<N> lu;
+                        pt.jacobian(m, x[N - 1] - xp[N - 1], lu.a);
+                        lu.factor();
+#pragma unroll
+                        for (int i = 0; i < N; ++i) dx[i] = C[i];
+                        lu.solve(dx);                             // delta = solve(J, C)
+                    }
+                    // ---- line search (quadratic model), line_search.py:125-181
+                    const double CC = dotN<N>(C, C);
+                    const double phi0 = 0.5 * CC, dphi0 = -CC, armijo = nw.c1 * dphi0;
+                    int ne = 0;
+                    double al = 1.0, best_al = 1.0, best_phi = CUDART_INF;
+                    double best_C[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) best_C[i] = C[i];
+                    bool acc = false;
+                    double Ct[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) Ct[i] = C[i];
+                    while (ne < nw.ls_max && !acc) {
+                        double xt[N];
+#pragma unroll
+                        for (int i = 0; i < N; ++i) xt[i] = fma(-al, dx[i], x[i]);
+                        pt.residual(m, xt, xp, em, Ct);
+                        const double ph = 0.5 * dotN<N>(Ct, Ct);
+                        const bool fin = isfinite(ph);
+                        if (fin && ph < best_phi) {
+                            best_al = al; best_phi = ph;
+#pragma unroll
+                            for (int i = 0; i < N; ++i) best_C[i] = Ct[i];
+                        }
+                        acc = fin && (ph <= fma(al, armijo, phi0));
+                        const double den = 2.0 * (ph - phi0 - dphi0 * al);
+                        const double am = (den == 0.0) ? 0.5 * al : -dphi0 * al * al / den;
+                        double ac = fmin(fmax(am, nw.bmin * al), nw.bmax * al);
+                        if (am != am) ac = am;                    // clip propagates NaN
+                        if (!acc) al = fin ? ac : 0.5 * al;
+                        ++ne;
+                    }
+                    const double ar = acc ? al : best_al;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        x[i] = fma(-ar, dx[i], x[i]);
+                        C[i] = acc ? Ct[i] : best_C[i];
+                    }
+                    fresh = acc;      // the last evaluated trial is x only if it was accepted
+                    ++ii;
+                    if (ii >= nw.max_iters) done = true;
+                }
+            }
+        }
+        nc = normN<N>(C);
+    } else {
+        // imperative newton_solve (no line search): rel := 1 on the first pass
+        while (__any_sync(full, !done)) {
+            if (!done) {
+                if (ii > 0) { pt.residual(m, x, xp, em, C); fresh = true; }
+                nc = normN<N>(C);
+                double rel = 1.0;
+                if (ii == 0) n0 = nc; else rel = nc / n0;
+                if (rel < nw.rel_tol || nc < nw.abs_tol) {
+                    done = true;
+                } else {
+                    RegLU<N> lu;
+                    pt.jacobian(m, x[N - 1] - xp[N - 1], lu.a);
+                    lu.factor();
+                    double dx[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) dx[i] = -C[i];
+                    lu.solve(dx);                                 // solve(J, -C)
+#pragma unroll
+                    for (int i = 0; i < N; ++i) x[i] += dx[i];
+                    fresh = false;
+                    ++ii;
+                    if (ii >= nw.max_iters) done = true;
+                }
+            }
+        }
+    }
+    if (!fresh) pt.residual(m, x, xp, em, C);
+    r.iters = ii;
+    r.cnorm = nc;
+    return r;
+}
+
+}  // namespace cmadx

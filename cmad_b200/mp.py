@@ -1,0 +1,143 @@
+"""Batched material-point update: Python front end of K1 (``cmadx_mp_update``).
+
+Arrays are torch CUDA tensors in the component-major ("SoA") layout of the
+C-ABI: ``xi_prev (n_xi, N)``, ``strain (6|9, N)``; torch is used only to own
+device memory and streams.  The host-buffer variant takes NumPy / pinned
+torch CPU tensors and runs the library's chunked H2D / kernel / D2H pipeline.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .material import NewtonSettings
+
+OUTPUT_COMPONENTS = {  # name -> (components as a function of n_xi, n_active), dtype
+    "xi": lambda n, a: n, "sigma": lambda n, a: 6, "dsig_deps": lambda n, a: 36,
+    "dxi_deps": lambda n, a: n * 6, "dC_dp": lambda n, a: n * a, "dC_dxi": lambda n, a: n * n,
+    "dC_dxi_prev": lambda n, a: n * n, "C": lambda n, a: n,
+}
+POINT_SCALARS = {"iters": torch.int32, "flags": torch.int32, "cnorm": torch.float64}
+DEFAULT_OUTPUTS = ("xi", "sigma", "dsig_deps", "dC_dp", "iters", "flags")
+
+
+def n_xi_of(material: L.Material) -> int:
+    return 6 if material.model == L.MODEL_ELASTIC else 7
+
+
+def _check_in(name, t, rows, n, device_type):
+    if t.dtype != torch.float64 or t.dim() != 2 or t.shape[0] != rows or t.shape[1] != n:
+        raise ValueError(f"{name}: expected float64 ({rows}, {n}), got {t.dtype} {tuple(t.shape)}")
+    if t.device.type != device_type:
+        raise ValueError(f"{name}: expected a {device_type} tensor")
+    if t.stride(1) != 1:
+        raise ValueError(f"{name}: innermost (point) dimension must be contiguous")
+
+
+def allocate_outputs(material: L.Material, n: int, n_active: int, outputs, device,
+                     pin: bool = False) -> dict:
+    nxi = n_xi_of(material)
+    out = {}
+    kw = dict(device=device)
+    if pin:
+        kw = dict(device="cpu", pin_memory=True)
+    for name in outputs:
+        if name in OUTPUT_COMPONENTS:
+            rows = OUTPUT_COMPONENTS[name](nxi, n_active)
+            if name == "dC_dp" and n_active == 0:
+                continue
+            out[name] = torch.empty((rows, n), dtype=torch.float64, **kw)
+        elif name in POINT_SCALARS:
+            out[name] = torch.empty((n,), dtype=POINT_SCALARS[name], **kw)
+        else:
+            raise ValueError(f"unknown output {name!r}")
+    return out
+
+
+def _buffers(material, xi_prev, strain, xi_init, out: dict) -> L.MpBuffers:
+    n = xi_prev.shape[1]
+    ld = xi_prev.stride(0) if xi_prev.shape[0] > 1 else max(n, 1)
+    tensors = [xi_prev, strain] + ([xi_init] if xi_init is not None else []) + \
+        [t for k, t in out.items() if k in OUTPUT_COMPONENTS]
+    for t in tensors:
+        s0 = t.stride(0) if t.shape[0] > 1 else ld
+        if s0 != ld:
+            raise ValueError("all component-major arrays must share one leading dimension")
+    b = L.MpBuffers()
+    b.n, b.ld, b.strain_comps = n, ld, strain.shape[0]
+    b.xi_prev, b.strain = xi_prev.data_ptr(), strain.data_ptr()
+    b.xi_init = xi_init.data_ptr() if xi_init is not None else None
+    for name in list(OUTPUT_COMPONENTS) + list(POINT_SCALARS):
+        setattr(b, name, out[name].data_ptr() if name in out else None)
+    return b
+
+
+def mp_update(material: L.Material, newton: NewtonSettings, active_pid, xi_prev: torch.Tensor,
+              strain: torch.Tensor, outputs=DEFAULT_OUTPUTS, out: dict | None = None,
+              xi_init: torch.Tensor | None = None, stream: torch.cuda.Stream | None = None) -> dict:
+    """One batched constitutive update on the GPU (asynchronous on ``stream``).
+
+    Returns the dict of requested output tensors (allocated unless ``out`` is
+    given).  Raises if the CUDA library is unavailable - there is no fallback.
+    """
+    lib = L.lib()
+    nxi = n_xi_of(material)
+    n = xi_prev.shape[1]
+    _check_in("xi_prev", xi_prev, nxi, n, "cuda")
+    if strain.shape[0] not in (6, 9):
+        raise ValueError("strain must have 6 (symmetric) or 9 (grad_u) components")
+    _check_in("strain", strain, strain.shape[0], n, "cuda")
+    if xi_init is not None:
+        _check_in("xi_init", xi_init, nxi, n, "cuda")
+    pid = np.ascontiguousarray(active_pid, dtype=np.int32)
+    if out is None:
+        out = allocate_outputs(material, n, len(pid), outputs, xi_prev.device)
+    b = _buffers(material, xi_prev, strain, xi_init, out)
+    nw = newton.to_struct()
+    s = stream if stream is not None else torch.cuda.current_stream(xi_prev.device)
+    with torch.cuda.device(xi_prev.device):
+        rc = lib.cmadx_mp_update(C.byref(material), C.byref(nw),
+                                 pid.ctypes.data_as(C.POINTER(C.c_int32)), len(pid),
+                                 C.byref(b), C.c_void_p(s.cuda_stream))
+    L.check(rc, "cmadx_mp_update")
+    return out
+
+
+def mp_update_host(material: L.Material, newton: NewtonSettings, active_pid, xi_prev, strain,
+                   outputs=DEFAULT_OUTPUTS, out: dict | None = None, xi_init=None,
+                   device: int = 0, chunk_points: int = 0) -> dict:
+    """Same update on HOST buffers (NumPy arrays or CPU torch tensors, ideally
+    pinned): chunked H2D -> kernel -> D2H pipeline inside the library. Blocking."""
+    lib = L.lib()
+    as_t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+    xi_prev, strain = as_t(xi_prev), as_t(strain)
+    xi_init = as_t(xi_init) if xi_init is not None else None
+    nxi = n_xi_of(material)
+    n = xi_prev.shape[1]
+    _check_in("xi_prev", xi_prev, nxi, n, "cpu")
+    _check_in("strain", strain, strain.shape[0], n, "cpu")
+    pid = np.ascontiguousarray(active_pid, dtype=np.int32)
+    if out is None:
+        out = allocate_outputs(material, n, len(pid), outputs, "cpu", pin=False)
+    b = _buffers(material, xi_prev, strain, xi_init, out)
+    nw = newton.to_struct()
+    rc = lib.cmadx_mp_update_host(C.byref(material), C.byref(nw),
+                                  pid.ctypes.data_as(C.POINTER(C.c_int32)), len(pid),
+                                  C.byref(b), int(device), int(chunk_points))
+    L.check(rc, "cmadx_mp_update_host")
+    return out
+
+
+def fp64_peak_tflops(iters: int = 20000) -> float:
+    v = C.c_double(0.0)
+    s = torch.cuda.current_stream()
+    L.check(L.lib().cmadx_fp64_peak(int(iters), C.byref(v), C.c_void_p(s.cuda_stream)), "cmadx_fp64_peak")
+    return float(v.value)
+
+
+def launch_count() -> int:
+    return int(L.lib().cmadx_launch_count())

@@ -1,0 +1,181 @@
+/*
+ * cmad_b200 - B200-native (sm_100a) constitutive-update hot path for CMAD.
+ *
+ * C-ABI drop-in boundary.  Plain pointers and sizes only; no torch / JAX types.
+ * Every entry point is asynchronous on the CUDA stream it is given (device
+ * entry points) or self-contained (host-buffer entry points), returns 0 on
+ * success or a CMADX_E* code, never throws, and allocates nothing persistent
+ * except the opaque handles it returns.  The caller owns all buffers.
+ *
+ * The reference (sandialabs/cmad) is pure Python on JAX and has no FFI of its
+ * own; each entry point below cites the reference *Python* interface it
+ * replaces (file:line relative to the reference tree).  INTEGRATION.md shows
+ * the jax.ffi / ctypes binding a maintainer adds on the reference side.
+ *
+ * Array layout ("SoA"): every per-point quantity is component-major, component
+ * c of point i at  base[c*ld + i]  (ld >= n, in elements).  Symmetric tensors
+ * use CMAD's packing order xx,xy,xz,yy,yz,zz (cmad/models/var_types.py:43-47,
+ * 73-77); off-diagonal entries are *tensor* components (not engineering).
+ */
+#ifndef CMAD_B200_H
+#define CMAD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMADX_VERSION 100
+
+/* ---- error codes -------------------------------------------------------- */
+enum {
+    CMADX_OK = 0,
+    CMADX_EINVAL = 1,       /* bad enum / size / null pointer                 */
+    CMADX_EUNSUPPORTED = 2, /* valid request the kernels do not implement     */
+    CMADX_ECUDA = 3,        /* CUDA runtime error (see cmadx_last_cuda_error) */
+    CMADX_ENOMEM = 4
+};
+
+/* ---- models: cmad/models/small_elastic_plastic.py:95, cmad/models/elastic.py:29 */
+enum { CMADX_MODEL_SMALL_ELASTIC_PLASTIC = 0, CMADX_MODEL_ELASTIC = 1 };
+/* ---- effective stress: cmad/models/effective_stress.py:16-27 */
+enum { CMADX_YIELD_J2 = 0, CMADX_YIELD_HILL = 1, CMADX_YIELD_HOSFORD = 2 };
+/* ---- which two elastic constants are given (cmad/models/elastic_constants.py:54-104),
+ *      values in sorted-key order "E" < "kappa" < "lambda" < "mu" < "nu"       */
+enum {
+    CMADX_EL_E_NU = 0, CMADX_EL_E_MU, CMADX_EL_E_KAPPA, CMADX_EL_E_LAMBDA,
+    CMADX_EL_KAPPA_MU, CMADX_EL_KAPPA_NU, CMADX_EL_KAPPA_LAMBDA,
+    CMADX_EL_LAMBDA_MU, CMADX_EL_LAMBDA_NU, CMADX_EL_MU_NU
+};
+/* ---- hardening terms present (cmad/models/hardening.py:25-34), bit mask */
+enum { CMADX_HARD_VOCE = 1, CMADX_HARD_LINEAR = 2 };
+/* ---- canonical parameter ids: columns of dC/dp are requested by id, in the
+ *      order the caller wants them (the reference's order is the sorted-key
+ *      pytree flatten order restricted to active leaves,
+ *      cmad/parameters/parameters.py:214-243, 368-377)                        */
+enum {
+    CMADX_P_EL0 = 0, CMADX_P_EL1, CMADX_P_Y, CMADX_P_VOCE_S, CMADX_P_VOCE_D,
+    CMADX_P_LIN_K, CMADX_P_HILL_F, CMADX_P_HILL_G, CMADX_P_HILL_H, CMADX_P_HILL_L,
+    CMADX_P_HILL_M, CMADX_P_HILL_N, CMADX_P_HOSFORD_A, CMADX_P_Q00,
+    CMADX_NUM_PARAM_IDS = CMADX_P_Q00 + 9
+};
+#define CMADX_MAX_ACTIVE 16
+
+/* ---- local Newton flavour ------------------------------------------------ */
+enum {
+    CMADX_NEWTON_TRACED = 0,     /* make_newton_solve,  cmad/models/nonlinear_solver.py:88-174 */
+    CMADX_NEWTON_IMPERATIVE = 1  /* newton_solve(model), cmad/models/nonlinear_solver.py:14-85 */
+};
+
+/* Material = the reference's parameter pytree for one element block
+ * (cmad/parameters/parameters.py:205-272), flattened to a POD. */
+typedef struct cmadx_material {
+    int32_t model;          /* CMADX_MODEL_*                                   */
+    int32_t yield;          /* CMADX_YIELD_*                                   */
+    int32_t elastic_pair;   /* CMADX_EL_*                                      */
+    int32_t hardening_mask; /* CMADX_HARD_* bits                               */
+    double elastic[2];      /* the two given constants, sorted-key order       */
+    double Y;               /* plastic/flow stress/initial yield/Y             */
+    double voce_S, voce_D;  /* plastic/flow stress/hardening/voce              */
+    double linear_K;        /* plastic/flow stress/hardening/linear            */
+    double hill[6];         /* F G H L M N                                     */
+    double hosford_a;
+    double Q[9];            /* "rotation matrix", row-major                    */
+    double yield_tol;       /* cmad/models/small_elastic_plastic.py:116 (1e-14)*/
+} cmadx_material_t;
+
+/* Local Newton + line-search settings: make_newton_solve kwargs
+ * (cmad/models/nonlinear_solver.py:88-100) and DEFAULT_LINE_SEARCH_SETTINGS
+ * (cmad/util/line_search.py:40-46). */
+typedef struct cmadx_newton {
+    int32_t mode;           /* CMADX_NEWTON_*                                  */
+    int32_t max_iters;
+    int32_t ls_max_evals;   /* traced mode only; >= 1                          */
+    int32_t reserved;
+    double abs_tol, rel_tol;
+    double ls_c1, ls_bmin, ls_bmax;
+} cmadx_newton_t;
+
+/* Per-point buffers of one batched update.  Inputs must be non-null; any
+ * output may be null (skipped).  n_xi = 7 (small_elastic_plastic, FULL_3D:
+ * plastic strain(6) + alpha) or 6 (elastic: cauchy(6)).                      */
+typedef struct cmadx_mp_buffers {
+    int64_t n;              /* points                                          */
+    int64_t ld;             /* leading dimension (elements), >= n              */
+    int32_t strain_comps;   /* 6: symmetric strain (grad_u := strain);
+                               9: grad_u row-major [k*3+j] = du_k/dx_j        */
+    int32_t reserved;
+    const double* xi_prev;  /* [n_xi][ld]                                      */
+    const double* strain;   /* [strain_comps][ld]                              */
+    const double* xi_init;  /* [n_xi][ld] or NULL: starting iterate (NULL =>
+                               xi_prev, the reference's behaviour after
+                               advance_xi / in make_newton_solve).  With
+                               max_iters = 0 every output is evaluated AT
+                               (xi_init, xi_prev): Model.evaluate() semantics,
+                               cmad/models/model.py:168-193                    */
+    double* xi;             /* [n_xi][ld]   converged local state              */
+    double* sigma;          /* [6][ld]      global cauchy stress               */
+    double* dsig_deps;      /* [36][ld]     consistent tangent, (a*6+b), wrt the
+                                           symmetric strain component b        */
+    double* dxi_deps;       /* [n_xi*6][ld] IFT dxi/deps, (r*6+b)              */
+    double* dC_dp;          /* [n_xi*n_active][ld]  dC/dp at (xi, xi_prev), (r*n_active+c) */
+    double* dC_dxi;         /* [n_xi*n_xi][ld]                                 */
+    double* dC_dxi_prev;    /* [n_xi*n_xi][ld]                                 */
+    int32_t* iters;         /* [n] Newton updates taken (ii)                   */
+    int32_t* flags;         /* [n] bit0: plastic branch at x0, bit1: at x*     */
+    double* cnorm;          /* [n] final ||C||_2                               */
+    double* C;              /* [n_xi][ld]   residual at the returned xi        */
+} cmadx_mp_buffers_t;
+
+int cmadx_version(void);
+/* sizeof(cmadx_material_t), sizeof(cmadx_newton_t), sizeof(cmadx_mp_buffers_t):
+ * lets a foreign-language binding verify its struct mirrors. */
+int cmadx_struct_sizes(int64_t* out3);
+const char* cmadx_error_string(int code);
+/* text of the last CUDA error seen by this thread ("" if none) */
+const char* cmadx_last_cuda_error(void);
+
+/* lambda, mu and d(lambda,mu)/d(elastic[0..1]) for a material:
+ * out6 = {lambda, mu, dlam/de0, dlam/de1, dmu/de0, dmu/de1}.
+ * Replaces ElasticConstants.from_params (cmad/models/elastic_constants.py:54-104). */
+int cmadx_lame(const cmadx_material_t* mat, double* out6);
+
+/* K1: batched constitutive update on DEVICE buffers, asynchronous on `stream`
+ * (a cudaStream_t).  One call = for every point: local Newton solve of
+ * C(xi; xi_prev, p, U) = 0, cauchy stress, consistent tangent, dC/dp, dC/dxi,
+ * dC/dxi_prev.  Replaces, for a batch of points,
+ *   make_newton_solve(model._residual)(xi_prev, params, U, U_prev) and its IFT
+ *   rule (cmad/models/nonlinear_solver.py:88-174) or newton_solve(model)
+ *   (:14-85); Model.cauchy / dC_dxi / dC_dxi_prev / dC_dp
+ *   (cmad/models/model.py:121-166, 316-350) with active-column selection
+ *   (cmad/parameters/parameters.py:368-377);
+ * i.e. the bodies of the per-point loops cmad/cli/primal.py:158-175 and
+ * cmad/objectives/mp_objective.py:73-87.                                      */
+int cmadx_mp_update(const cmadx_material_t* mat, const cmadx_newton_t* newton,
+                    const int32_t* active_pid, int32_t n_active,
+                    const cmadx_mp_buffers_t* dev, void* stream);
+
+/* Same operation on HOST buffers (pageable or pinned): copies inputs to the
+ * device in chunks, runs K1, copies every non-null output back, overlapping
+ * H2D / kernel / D2H on three streams.  Blocking.  `device` = CUDA ordinal.
+ * `chunk_points` <= 0 picks a default.  Scratch is cached per device in a
+ * handle created on first use and freed by cmadx_release_host_scratch().      */
+int cmadx_mp_update_host(const cmadx_material_t* mat, const cmadx_newton_t* newton,
+                         const int32_t* active_pid, int32_t n_active,
+                         const cmadx_mp_buffers_t* host, int device,
+                         int64_t chunk_points);
+int cmadx_release_host_scratch(void);
+
+/* number of kernel launches issued by this library since load (all threads) */
+int64_t cmadx_launch_count(void);
+
+/* FP64 FMA peak micro-benchmark (dependent-chain-free DFMA loop): returns
+ * achieved TFLOP/s on the current device through *tflops.  Used by bench.py to
+ * obtain the FP64 roofline denominator MEASURED_PEAKS.json lacks.             */
+int cmadx_fp64_peak(int iters, double* tflops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMAD_B200_H */

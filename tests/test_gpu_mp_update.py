@@ -1,0 +1,276 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU
+oracle on the same seeded inputs.  Values within 1e-10 (relative to the largest
+entry of each quantity in the batch), Newton iteration counts and plastic /
+elastic branch flags exactly equal."""
+import numpy as np
+import pytest
+import torch
+
+from cmad_b200 import NewtonSettings, Parameters, active_param_ids, material_from_values, mp
+from oracle import analytic, oracle_c as oc
+from tests.helpers import UP, param_tree, random_strains, rel_err, rotation_matrix
+
+pytestmark = pytest.mark.gpu
+ALL = ("xi", "sigma", "dsig_deps", "dxi_deps", "dC_dp", "dC_dxi", "dC_dxi_prev", "iters", "flags", "cnorm", "C")
+TOL = 1e-10
+
+
+def _compare(out, ref, keys, tol=TOL):
+    for k in keys:
+        g = out[k].cpu().numpy()
+        if k in ("iters", "flags"):
+            assert np.array_equal(g, ref[k]), f"{k}: {np.flatnonzero(g != ref[k])[:10]}"
+        else:
+            assert rel_err(g, ref[k]) < tol, (k, rel_err(g, ref[k]))
+
+
+def _run_pair(cuda_device, values, act, tr, n, mode, rng, model="small_elastic_plastic",
+              newton_kw=None, diag_only=False, steps=3, strain_comps=6):
+    newton_kw = newton_kw or dict(max_iters=20, abs_tol=1e-12, rel_tol=1e-12)
+    P = Parameters(values, act, tr)
+    mat = material_from_values(values, model=model)
+    pid = active_param_ids(P)
+    nw = NewtonSettings(mode=mode, **newton_kw)
+    prob = oc.describe(values, P.active_idx, model=model, newton_mode=mode,
+                       strain_comps=strain_comps, **newton_kw)
+    nxi = 6 if model == "elastic" else 7
+    xi_ref = np.zeros((nxi, n))
+    xi = torch.zeros((nxi, n), dtype=torch.float64, device=cuda_device)
+    e = np.zeros((6, n))
+    plastic_seen = False
+    for s in range(steps):
+        e = e * 1.25 + random_strains(rng, n, scale=1e-3 / (1 + s), diag_only=diag_only)
+        if strain_comps == 9:
+            skew = rng.normal(size=(3, n)) * 1e-3      # rigid rotation part must not matter
+            g = np.stack([e[0], e[1] + skew[0], e[2] + skew[1], e[1] - skew[0], e[3], e[4] + skew[2],
+                          e[2] - skew[1], e[4] - skew[2], e[5]])
+        else:
+            g = e
+        out = mp.mp_update(mat, nw, pid, xi, torch.from_numpy(g).to(cuda_device), outputs=ALL)
+        ref = oc.mp_update(prob, xi_ref, g, want=ALL[:-1])
+        torch.cuda.synchronize()
+        keys = [k for k in ALL[:-1] if k in out and (k != "dC_dp" or len(pid))]
+        _compare(out, ref, keys)
+        xi, xi_ref = out["xi"], ref["xi"]
+        plastic_seen |= bool((ref["flags"] & 2).any())
+    return plastic_seen
+
+
+@pytest.mark.parametrize("kind", ["J2", "hill", "hosford"])
+@pytest.mark.parametrize("mode", ["traced", "imperative"])
+def test_parity_vs_oracle(cuda_device, kind, mode):
+    rng = np.random.default_rng(11)
+    hill = (0.45, 0.6, 0.55, 1.4, 1.6, 1.5) if kind == "hill" else None
+    active = ("E", "nu", "D", "S", "Y") + (tuple("FGHLMN") if kind == "hill" else ())
+    values, act, tr = param_tree(kind, ("voce",), hill=hill, active=active)
+    assert _run_pair(cuda_device, values, act, tr, 20000, mode, rng, diag_only=(kind == "hosford"))
+
+
+def test_parity_default_tolerances_1e14(cuda_device):
+    """make_newton_solve defaults (10 iters, 1e-14/1e-14, nonlinear_solver.py:90-92)."""
+    rng = np.random.default_rng(5)
+    values, act, tr = param_tree("J2")
+    assert _run_pair(cuda_device, values, act, tr, 50000, "traced", rng,
+                     newton_kw=dict(max_iters=10, abs_tol=1e-14, rel_tol=1e-14))
+
+
+def test_parity_linear_plus_voce_and_other_elastic_pair(cuda_device):
+    rng = np.random.default_rng(2)
+    values, act, tr = param_tree("J2", ("voce", "linear"), elastic={"kappa": 166666.66666666666, "mu": 76923.07692307692},
+                                 active=("kappa", "mu", "K", "S", "D", "Y"))
+    assert _run_pair(cuda_device, values, act, tr, 8192, "traced", rng)
+
+
+def test_parity_rotated_material_axes(cuda_device):
+    rng = np.random.default_rng(3)
+    Q = rotation_matrix([1.0, 2.0, 3.0], 0.7)
+    values, act, tr = param_tree("hill", ("voce",), hill=(0.45, 0.6, 0.55, 1.4, 1.6, 1.5), rotation=Q)
+    assert _run_pair(cuda_device, values, act, tr, 4096, "traced", rng)
+
+
+def test_parity_grad_u_input_9_components(cuda_device):
+    rng = np.random.default_rng(4)
+    values, act, tr = param_tree("J2")
+    assert _run_pair(cuda_device, values, act, tr, 4096, "traced", rng, strain_comps=9)
+
+
+def test_parity_hosford_a100_long_line_search(cuda_device):
+    """notch_hosford.yaml:30-42: a=100, E=1000, nu=.25, Y=2, S=10, D=2, local
+    Newton 500 iters, line search 100 evals."""
+    rng = np.random.default_rng(6)
+    values, act, tr = param_tree("hosford", ("voce",), a=100.0, elastic={"E": 1000.0, "nu": 0.25}, active=())
+    values["plastic"]["flow stress"]["initial yield"]["Y"] = 2.0
+    values["plastic"]["flow stress"]["hardening"]["voce"] = {"S": 10.0, "D": 2.0}
+    P = Parameters(values, act, tr)
+    mat = material_from_values(values)
+    kw = dict(max_iters=500, abs_tol=1e-12, rel_tol=1e-12)
+    nw = NewtonSettings(mode="traced", ls_max_evals=100, **kw)
+    prob = oc.describe(values, [], newton_mode="traced", ls_max_evals=100, **kw)
+    n = 2048
+    e = random_strains(rng, n, scale=2e-3, diag_only=True)
+    out = mp.mp_update(mat, nw, [], torch.zeros((7, n), dtype=torch.float64, device=cuda_device),
+                       torch.from_numpy(e).to(cuda_device), outputs=("xi", "sigma", "dsig_deps", "iters", "flags", "cnorm"))
+    ref = oc.mp_update(prob, np.zeros((7, n)), e, want=("xi", "sigma", "dsig_deps", "iters", "flags", "cnorm"))
+    it = out["iters"].cpu().numpy()
+    # a=100 is ill-conditioned: iteration paths amplify 1-ulp differences, so counts are
+    # compared statistically and values on the converged points only
+    conv = (ref["cnorm"] < 1e-12) & (out["cnorm"].cpu().numpy() < 1e-12)
+    assert conv.mean() > 0.9
+    assert np.mean(it == ref["iters"]) > 0.9
+    assert np.array_equal(out["flags"].cpu().numpy()[conv], ref["flags"][conv])
+    assert rel_err(out["sigma"].cpu().numpy()[:, conv], ref["sigma"][:, conv]) < 1e-8
+
+
+def test_parity_elastic_model(cuda_device):
+    rng = np.random.default_rng(8)
+    values = {"elastic": {"kappa": 100.0, "mu": 50.0}}
+    act = {"elastic": {"kappa": True, "mu": True}}; tr = {"elastic": {"kappa": None, "mu": None}}
+    _run_pair(cuda_device, values, act, tr, 3000, "traced", rng, model="elastic")
+
+
+def test_ka1_analytic_path_through_kernel(cuda_device):
+    """KA1 on the GPU path exactly as the reference test drives it (imperative
+    Newton, 100 steps, tolerance 1e-6): tests/models/test_elastic_plastic_models.py:95-125."""
+    for kind in ("J2", "hill", "hosford"):
+        values, act, tr = analytic.j2_voce_param_tree(kind)
+        mat = material_from_values(values)
+        nw = NewtonSettings(mode="imperative")
+        masks = analytic.stress_masks_3d()
+        fields = [analytic.plastic_fields(m) for m in masks]
+        xi = torch.zeros((7, 2), dtype=torch.float64, device=cuda_device)
+        alphas, sigs = [], []
+        for k in range(100):
+            e = np.array([[f[1][i, j, k] for f in fields] for i, j in UP])
+            out = mp.mp_update(mat, nw, [], xi, torch.from_numpy(e).to(cuda_device), outputs=("xi", "sigma", "iters"))
+            xi = out["xi"]
+            alphas.append(xi[6].cpu().numpy()); sigs.append(out["sigma"].cpu().numpy())
+        alphas, sigs = np.array(alphas), np.array(sigs)            # (100,2), (100,6,2)
+        w = np.array([1, 2, 2, 1, 2, 1])[None, :]
+        for p, (stress, strain, alpha) in enumerate(fields):
+            ref = np.array([[stress[i, j, k] for i, j in UP] for k in range(100)])
+            assert np.linalg.norm(alphas[:, p] - alpha) < 1e-6
+            assert np.sqrt((w * (sigs[:, :, p] - ref) ** 2).sum()) < 1e-6
+
+
+def test_consistent_tangent_vs_central_fd(cuda_device):
+    """KA2-style check on the kernel itself: d sigma/d eps (IFT) against central
+    differences of the Newton-running stress (eps 1e-6, rtol 1e-5, atol 1e-7 x scale)."""
+    values, act, tr = param_tree("J2")
+    mat = material_from_values(values)
+    nw = NewtonSettings(max_iters=20, abs_tol=1e-12, rel_tol=1e-12)
+    # tet-barycentre fixture strain: grad_u = diag(.005,.003,.002) (test_for_model_coupled.py:65-82)
+    e0 = np.array([.005, 0, 0, .003, 0, .002])
+    cols = [e0]
+    h = 1e-6
+    for b in range(6):
+        for s in (+1, -1):
+            e = e0.copy(); e[b] += s * h; cols.append(e)
+    E = np.stack(cols, axis=1)
+    out = mp.mp_update(mat, nw, [], torch.zeros((7, 13), dtype=torch.float64, device=cuda_device),
+                       torch.from_numpy(E).to(cuda_device), outputs=("sigma", "dsig_deps", "flags", "cnorm", "xi"))
+    sig = out["sigma"].cpu().numpy(); D = out["dsig_deps"].cpu().numpy()[:, 0].reshape(6, 6)
+    assert out["flags"].cpu().numpy()[0] == 3 and out["xi"].cpu().numpy()[6, 0] > 0
+    assert out["cnorm"].cpu().numpy()[0] < 1e-10
+    fd = np.stack([(sig[:, 1 + 2 * b] - sig[:, 2 + 2 * b]) / (2 * h) for b in range(6)], axis=1)
+    assert np.allclose(D, fd, rtol=1e-5, atol=1e-7 * np.abs(fd).max())
+
+
+def test_evaluate_at_state_semantics(cuda_device):
+    """max_iters=0 with xi_init evaluates C, dC/dxi, dC/dxi_prev, dC/dp at an
+    arbitrary (xi, xi_prev): Model.evaluate() (cmad/models/model.py:168-193)."""
+    rng = np.random.default_rng(9)
+    values, act, tr = param_tree("J2")
+    P = Parameters(values, act, tr); mat = material_from_values(values); pid = active_param_ids(P)
+    n = 512
+    e = random_strains(rng, n, scale=3e-3)
+    solve = NewtonSettings(max_iters=20, abs_tol=1e-12, rel_tol=1e-12)
+    z = torch.zeros((7, n), dtype=torch.float64, device=cuda_device)
+    ed = torch.from_numpy(e).to(cuda_device)
+    a = mp.mp_update(mat, solve, pid, z, ed, outputs=ALL)
+    b = mp.mp_update(mat, NewtonSettings(max_iters=0), pid, z, ed, outputs=ALL, xi_init=a["xi"])
+    for k in ("dC_dxi", "dC_dxi_prev", "dC_dp", "sigma", "dsig_deps"):
+        assert torch.equal(a[k], b[k]), k
+    assert int(b["iters"].max()) == 0
+    assert float(b["C"].abs().max()) < 1e-10
+
+
+def test_ragged_sizes_padding_and_empty(cuda_device):
+    values, act, tr = param_tree("J2")
+    P = Parameters(values, act, tr); mat = material_from_values(values); pid = active_param_ids(P)
+    nw = NewtonSettings()
+    prob = oc.describe(values, P.active_idx)
+    rng = np.random.default_rng(10)
+    for n in (1, 31, 33, 129, 1000):
+        ld = n + 7                                             # padded leading dimension
+        e = random_strains(rng, n, scale=2e-3)
+        xs = torch.zeros((7, ld), dtype=torch.float64, device=cuda_device)
+        es = torch.full((6, ld), float("nan"), dtype=torch.float64, device=cuda_device)
+        es[:, :n] = torch.from_numpy(e).to(cuda_device)
+        bufs = mp.allocate_outputs(mat, ld, len(pid), ALL, cuda_device)
+        for t in bufs.values():
+            t.fill_(-77) if t.dtype == torch.int32 else t.fill_(-77.0)
+        views = {k: (v[:, :n] if v.dim() == 2 else v[:n]) for k, v in bufs.items()}
+        out = mp.mp_update(mat, nw, pid, xs[:, :n], es[:, :n], out=views)
+        ref = oc.mp_update(prob, np.zeros((7, n)), e, want=ALL[:-1])
+        _compare(out, ref, [k for k in ALL[:-1]])
+        for k, v in bufs.items():                              # padding untouched
+            if v.dim() == 2:
+                assert bool((v[:, n:] == -77).all()), k
+    empty = mp.mp_update(mat, nw, pid, torch.zeros((7, 0), dtype=torch.float64, device=cuda_device),
+                         torch.zeros((6, 0), dtype=torch.float64, device=cuda_device))
+    assert empty["xi"].shape == (7, 0)
+
+
+def test_host_buffer_path_matches_device_path(cuda_device):
+    rng = np.random.default_rng(12)
+    values, act, tr = param_tree("J2")
+    P = Parameters(values, act, tr); mat = material_from_values(values); pid = active_param_ids(P)
+    nw = NewtonSettings()
+    n = 70001
+    e = random_strains(rng, n, scale=2e-3)
+    xi0 = np.zeros((7, n))
+    dev = mp.mp_update(mat, nw, pid, torch.zeros((7, n), dtype=torch.float64, device=cuda_device),
+                       torch.from_numpy(e).to(cuda_device), outputs=ALL)
+    host = mp.mp_update_host(mat, nw, pid, xi0, e, outputs=ALL, chunk_points=16384)
+    torch.cuda.synchronize()
+    for k in ALL:
+        assert torch.equal(dev[k].cpu(), host[k]), k
+
+
+def test_maximum_batch_property_checks(cuda_device):
+    """Full bench size (2^24 points): size-independent properties - an elastic
+    unload/reload leaves the state unchanged (idempotence), stress is linear in the
+    strain increment inside the yield surface, and converged plastic points sit on
+    the yield surface (||C|| < 1e-10)."""
+    from cmad_b200 import synthetic
+    values, act, tr = param_tree("J2")
+    mat = material_from_values(values)
+    nw = NewtonSettings()
+    n = 1 << 24
+    dev = cuda_device
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    d = torch.randn((6, n), dtype=torch.float64, device=dev, generator=g)
+    d /= torch.sqrt(d[0] ** 2 + d[3] ** 2 + d[5] ** 2 + 2 * (d[1] ** 2 + d[2] ** 2 + d[4] ** 2))
+    amp = (0.5 + 4.5 * torch.rand(n, dtype=torch.float64, device=dev, generator=g)) * 1e-3
+    e1 = d * amp
+    z = torch.zeros((7, n), dtype=torch.float64, device=dev)
+    a = mp.mp_update(mat, nw, [], z, e1, outputs=("xi", "sigma", "flags", "cnorm", "iters"))
+    assert float(a["cnorm"].max()) < 1e-10
+    plastic = (a["flags"] & 2) != 0
+    assert 0.5 < float(plastic.double().mean()) < 0.95
+    assert int(a["iters"][~plastic].max()) == 0
+    # idempotence: same strain again from the converged state -> nothing moves, 0 iterations... 
+    b = mp.mp_update(mat, nw, [], a["xi"], e1, outputs=("xi", "sigma", "iters", "flags"))
+    assert float((b["xi"] - a["xi"]).abs().max()) < 1e-15
+    assert float((b["sigma"] - a["sigma"]).abs().max()) < 1e-9
+    # elastic unloading by 10%: stress increment is Hooke's law of the strain increment
+    e2 = 0.9 * e1
+    c = mp.mp_update(mat, nw, [], a["xi"], e2, outputs=("xi", "sigma", "flags", "iters"))
+    assert int(c["iters"].max()) == 0 and int((c["flags"] & 2).max()) == 0
+    assert torch.equal(c["xi"], a["xi"])
+    lam, mu = 200e3 * 0.3 / (1.3 * 0.4), 200e3 / 2.6
+    de = e2 - e1
+    tr_ = de[0] + de[3] + de[5]
+    ds = 2 * mu * de
+    ds[[0, 3, 5]] += lam * tr_
+    assert float((c["sigma"] - a["sigma"] - ds).abs().max()) < 1e-9
