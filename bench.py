@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 constitutive-update hot path (BASELINE.json metric).
+
+Workload (N=1): BASELINE.json configs[1] - batched small-strain J2 + Voce return
+mapping with consistent tangent and dC/dp, 2^24 = 16 777 216 material points x
+100 load steps of synthetic non-proportional strain paths.  One
+bench "step" = one load step of the whole batch = one K1 launch.  With
+``--steps K`` the 0..100 history is traversed in K equal increments (K = 100 is
+the named configuration).  Under torchrun (N > 1) every rank owns its own 2^24
+points (weak scaling, no data-path collective: points are independent).
+
+Prints ONE JSON line (rank 0).  ``--impl reference`` instead times the CPU
+restatement of the reference algorithm (oracle/, all host threads) on a bounded
+sample of the same workload - the reference itself is pure Python on JAX, which
+is not installable in this image.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_POINTS = 1 << 24
+HISTORY_STEPS = 100
+SEED = 22
+ALG_BYTES_PER_UPDATE = 784      # in 56+48, out 56+48+288+280+4+4
+OUTPUTS = ("xi", "sigma", "dsig_deps", "dC_dp", "iters", "flags")
+METRIC = "fp64 material-point updates/s (+tangent +dC/dp), J2+Voce return mapping"
+
+
+def material_setup():
+    from cmad_b200 import NewtonSettings, Parameters, active_param_ids, material_from_values
+    values = {
+        "rotation matrix": np.eye(3),
+        "elastic": {"E": 200e3, "nu": 0.3},
+        "plastic": {"effective stress": {"J2": 0.0},
+                    "flow stress": {"initial yield": {"Y": 200.0},
+                                    "hardening": {"voce": {"S": 200.0, "D": 20.0}}}}}
+    const = lambda t, c: {k: const(v, c) for k, v in t.items()} if isinstance(t, dict) else c
+    active = const(values, False)
+    active["elastic"] = {"E": True, "nu": True}
+    active["plastic"]["flow stress"] = const(values["plastic"]["flow stress"], True)
+    params = Parameters(values, active, const(values, None))
+    return values, params, material_from_values(values), active_param_ids(params), NewtonSettings()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU in a thread (NVML)."""
+
+    def __init__(self, index: int, period: float = 0.05):
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            phys = index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                phys = int(vis.split(",")[index])       # NVML ignores CUDA_VISIBLE_DEVICES
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_sample_rate(values, params, sample_points: int, steps, nthreads: int = 0):
+    """Oracle (C++ dual-number port of the reference algorithm) on a bounded
+    sample of the same workload; returns (updates/s, threads, description)."""
+    from cmad_b200 import synthetic
+    from oracle import oracle_c
+    prob = oracle_c.describe(values, params.active_idx)
+    d, d2, a = synthetic.path_params(SEED, 0, sample_points)
+    xi = np.zeros((7, sample_points))
+    oracle_c.mp_update(prob, xi[:, :256].copy(), synthetic.strain_at_step(d, d2, a, 50)[:, :256].copy())
+    total, updates = 0.0, 0
+    for t in steps:
+        e = synthetic.strain_at_step(d, d2, a, t)
+        t0 = time.perf_counter()
+        r = oracle_c.mp_update(prob, xi, e, want=OUTPUTS, nthreads=nthreads)
+        total += time.perf_counter() - t0
+        updates += sample_points
+        xi = r["xi"]
+    threads = nthreads if nthreads > 0 else oracle_c.num_threads()
+    return updates / total, threads, (f"first {sample_points} points of the workload, load steps "
+                                      f"{list(steps)} of {HISTORY_STEPS} (state carried), all outputs")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    values, params, _, _, _ = material_setup()
+    K, W = args.steps, args.warmup
+    # bounded sample: K steps of `sample` points spread over the history
+    sample = args.cpu_sample_points
+    ts = [max(1, round((j + 1) * HISTORY_STEPS / K)) for j in range(K)]
+    t_all = time.perf_counter()
+    # warm-up (untimed) then the timed sample; one "step" = one load step of the sample
+    cpu_sample_rate(values, params, min(sample, 4096), ts[:max(1, min(W, 3))])
+    rate, threads, desc = cpu_sample_rate(values, params, sample, ts)
+    ms = sample / rate * 1e3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "updates/s",
+        "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "J2+Voce batched return mapping, 2^24 points x 100 load steps "
+                               "(bounded CPU sample)", "points_per_step": sample,
+                   "history_steps": HISTORY_STEPS, "newton": "traced 10/1e-14/1e-14, ls 4"},
+        "cpu_baseline": {"value": rate, "unit": "updates/s", "cores": threads, "kind": "port",
+                         "sample": desc,
+                         "note": "reference is pure Python/JAX (not installable here); this is the "
+                                 "C++/OpenMP restatement in oracle/"},
+        "e2e": {"value": rate, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host_cpus": os.cpu_count(), "wall_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from cmad_b200 import mp, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    values, params, mat, pid, newton = material_setup()
+    K, W = args.steps, args.warmup
+    n = args.points
+    ts = [max(1, round((j + 1) * HISTORY_STEPS / K)) for j in range(K)]
+
+    # ---- synthetic inputs, resident in HBM before the timed region -----------
+    d_h, d2_h, a_h = synthetic.path_params(SEED, rank * n, n)
+    d, d2, a = (torch.from_numpy(x).to(dev) for x in (d_h, d2_h, a_h))
+    strains = [synthetic.strain_at_step(d, d2, a, t).contiguous() for t in ts]
+    del d, d2
+    xi_a = torch.zeros((7, n), dtype=torch.float64, device=dev)
+    xi_b = torch.empty_like(xi_a)
+    outs = mp.allocate_outputs(mat, n, len(pid), OUTPUTS, dev)
+    out_a = dict(outs); out_a["xi"] = xi_b
+    out_b = dict(outs); out_b["xi"] = xi_a
+    stream = torch.cuda.current_stream(dev)
+
+    def step(j, src, out):
+        mp.mp_update(mat, newton, pid, src, strains[j], out=out, stream=stream)
+
+    # ---- warm-up: W untimed launches on the mid-history strain (state untouched)
+    scratch = dict(outs); scratch["xi"] = xi_b
+    for _ in range(max(W, 3)):
+        step(K // 2, xi_a, scratch)
+    torch.cuda.synchronize(dev)
+    fp64_peak = mp.fp64_peak_tflops(20000)
+
+    sampler = ClockSampler(local)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    launches0 = mp.launch_count()
+    sampler.start()
+    ev[0].record(stream)
+    for j in range(K):
+        src, out = (xi_a, out_a) if j % 2 == 0 else (xi_b, out_b)
+        step(j, src, out)
+        ev[j + 1].record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    launches = mp.launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[K])
+    per_launch_ms = [ev[j].elapsed_time(ev[j + 1]) for j in range(K)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * n * K / (total_ms_max * 1e-3)
+
+    final_xi = xi_a if K % 2 == 0 else xi_b
+    plastic_frac = float(((outs["flags"] & 2) != 0).double().mean())
+    mean_iters = float(outs["iters"].double().mean())
+    checksum = float(final_xi[6].sum())
+
+    # ---- roofline of the dominant (only) kernel ------------------------------
+    hbm_peak, peak_src = peaks()
+    avg_kernel_ms = float(np.mean(per_launch_ms))
+    achieved = ALG_BYTES_PER_UPDATE * n / (avg_kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "kernel": "mp_update_kernel<J2>", "alg_bytes_per_update": ALG_BYTES_PER_UPDATE,
+                "avg_launch_ms": avg_kernel_ms,
+                "fp64": {"peak_tflops_measured": fp64_peak,
+                         "note": "DFMA micro-benchmark (cmadx_fp64_peak); kernel is FP64-pipe/"
+                                 "latency bound on plastic points, see profiles/"}}
+
+    # ---- e2e: same update through the host-buffer C-ABI call -----------------
+    e2e = None
+    if rank == 0 or world > 1:
+        e2e = run_e2e(args, mat, newton, pid, strains, ts, dev, local, world)
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "updates/s", "n_gpus": world,
+            "steps": K, "warmup": max(W, 3), "ms_per_step": total_ms_max / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: J2+Voce batched return mapping, 2^24 points x 100 "
+                                   "load steps, synthetic non-proportional strain paths",
+                       "points_per_gpu": n, "history_steps": HISTORY_STEPS, "load_steps_timed": ts,
+                       "newton": "make_newton_solve defaults: 10 iters, abs=rel=1e-14, line search 4 evals",
+                       "active_params": ["E", "nu", "D", "S", "Y"], "outputs": list(OUTPUTS),
+                       "l2": "inputs larger than L2 (1.74 GB read per step), no flush needed",
+                       "plastic_fraction_last_step": plastic_frac, "mean_newton_iters_last_step": mean_iters,
+                       "alpha_checksum": checksum},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "per_launch_ms": {"min": float(np.min(per_launch_ms)), "max": float(np.max(per_launch_ms))},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, threads, desc = cpu_sample_rate(values, params, args.cpu_sample_points,
+                                                  [10, 30, 50, 70, 90])
+            line["cpu_baseline"] = {"value": rate, "unit": "updates/s", "cores": threads,
+                                    "kind": "port", "sample": desc,
+                                    "host_cpus": os.cpu_count()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, mat, newton, pid, strains, ts, dev, local, world):
+    """K1 through ``cmadx_mp_update_host``: pinned HOST buffers in, every output
+    back to the host, copies inside the timed region."""
+    import torch
+    import torch.distributed as dist
+    from cmad_b200 import mp
+    n = min(args.e2e_points, strains[0].shape[1])
+    steps = min(args.e2e_steps, len(strains))
+    try:
+        xi_h = torch.zeros((7, n), dtype=torch.float64).pin_memory()
+        e_h = [strains[j][:, :n].cpu().pin_memory() for j in range(steps)]
+        out_h = mp.allocate_outputs(mat, n, len(pid), OUTPUTS, "cpu", pin=True)
+    except RuntimeError as exc:        # not enough pinnable host memory
+        return {"value": None, "unit": "updates/s", "error": str(exc)[:120]}
+    h2d = (7 + 6) * 8 * n
+    d2h = sum(t.numel() * t.element_size() for t in out_h.values())
+    mp.mp_update_host(mat, newton, pid, xi_h, e_h[0], out=out_h, device=local)      # warm-up
+    xi_h.zero_()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for j in range(steps):
+        mp.mp_update_host(mat, newton, pid, xi_h, e_h[j], out=out_h, device=local)
+        xi_h.copy_(out_h["xi"])        # host-side state carry (part of the user's loop)
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    return {"value": world * n * steps / dt, "unit": "updates/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "points_per_gpu": n, "steps": steps,
+            "api": "cmadx_mp_update_host (chunked H2D/kernel/D2H pipeline, pinned host buffers, "
+                   "all outputs returned to the host)",
+            "pcie_gbs": (h2d + d2h) * steps / dt / 1e9}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=N_POINTS)
+    ap.add_argument("--e2e-points", type=int, default=N_POINTS)
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--cpu-sample-points", type=int, default=1 << 20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.steps < 1:
+        raise SystemExit("--steps must be >= 1")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -197,16 +197,45 @@ template <class T> inline T phi_of(const Mat<T>& m, const T* c) {
     return phi_hosford(c, m.a);
 }
 
-// yield normal = jax.grad(effective_stress)(cauchy): one 9-direction dual
-// pass over the cauchy entries, nested over T (small_elastic_plastic.py:90)
+// yield normal = jax.grad(effective_stress)(cauchy) (small_elastic_plastic.py:90).
+// J2 and Hill: the first derivative is written out (it is validated against the
+// torch.func AD oracle in tests/test_oracle_cross.py); all *second* derivatives
+// still come from the dual numbers carried by T.  Hosford: one 9-direction dual
+// pass over the cauchy entries, nested over T.
 template <class T> inline void phi_and_normal(const Mat<T>& m, const T* c, T& phi, T* n) {
+    if (m.yield == YIELD_J2) {
+        T h = trace3(c) / 3.;
+        T s[9];
+        for (int i = 0; i < 9; ++i) s[i] = c[i];
+        s[0] = s[0] - h; s[4] = s[4] - h; s[8] = s[8] - h;
+        T ss = T(0.);
+        for (int i = 0; i < 9; ++i) ss = ss + s[i] * s[i];
+        T sn = dsqrt(ss);
+        phi = std::sqrt(3. / 2.) * sn;
+        T g = std::sqrt(3. / 2.) / sn;
+        T tr = T(0.);
+        for (int i = 0; i < 9; ++i) n[i] = g * s[i];
+        tr = (n[0] + n[4] + n[8]) / 3.;          // chain rule through s = c - tr(c)/3 I
+        n[0] = n[0] - tr; n[4] = n[4] - tr; n[8] = n[8] - tr;
+        return;
+    }
+    if (m.yield == YIELD_HILL) {
+        const T* h = m.hill;
+        T d12 = c[4] - c[8], d20 = c[8] - c[0], d01 = c[0] - c[4];
+        phi = phi_hill(c, m.hill);
+        T ip = 1. / phi;
+        n[0] = (h[2] * d01 - h[1] * d20) * ip;
+        n[4] = (h[0] * d12 - h[2] * d01) * ip;
+        n[8] = (h[1] * d20 - h[0] * d12) * ip;
+        n[1] = h[5] * c[1] * ip; n[3] = h[5] * c[3] * ip;
+        n[2] = h[4] * c[2] * ip; n[6] = h[4] * c[6] * ip;
+        n[5] = h[3] * c[5] * ip; n[7] = h[3] * c[7] * ip;
+        return;
+    }
     typedef Dual<T, 9> D9;
     D9 cc[9];
     for (int i = 0; i < 9; ++i) { cc[i].v = c[i]; cc[i].d[i] = T(1.); }
-    D9 p;
-    if (m.yield == YIELD_J2) p = phi_j2(cc);
-    else if (m.yield == YIELD_HILL) p = phi_hill(cc, m.hill);
-    else p = phi_hosford(cc, m.a);
+    D9 p = phi_hosford(cc, m.a);
     phi = p.v;
     for (int i = 0; i < 9; ++i) n[i] = p.d[i];
 }
