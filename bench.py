@@ -255,7 +255,7 @@ def run_b200(args):
 
     # ---- e2e: same update through the host-buffer C-ABI call -----------------
     e2e = None
-    if rank == 0 or world > 1:
+    if args.e2e_steps > 0 and (rank == 0 or world > 1):
         e2e = run_e2e(args, mat, newton, pid, strains, ts, dev, local, world)
 
     line = None

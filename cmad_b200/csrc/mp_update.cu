@@ -208,14 +208,21 @@ mp_update_kernel(const __grid_constant__ MpArgs A) {
 
     // IFT (nonlinear_solver.py:158-171).  In material axes dC/de = -(A[:, :6] - E),
     // E = [I6; 0], so dx/de = E - A^{-1}E and d sigma/de = Cel . (A^{-1})[0:6,0:6].
-    if (__any_sync(__activemask(), pl)) lu.factor();
+    // threshold pivoting (see RegLU): natural order unless some lane is troubled
+    bool trouble = false;
+    if (__any_sync(__activemask(), pl)) trouble = lu.factor_natural() && pl;
+    const bool slow = __any_sync(__activemask(), trouble);
+    if (slow && trouble) {
+        pt.jacobian(m, dg, lu.a);
+        lu.factor_pivot();
+    }
     if (!ROT) {
 #pragma unroll
         for (int b = 0; b < 6; ++b) {
             double X[7];
 #pragma unroll
             for (int r = 0; r < 7; ++r) X[r] = (r == b) ? 1.0 : 0.0;
-            if (pl) lu.solve(X);
+            if (pl) { if (slow && trouble) lu.solve_pivot(X); else lu.solve_natural(X); }
             if (A.b.dxi_deps) {
 #pragma unroll
                 for (int r = 0; r < 7; ++r) st(A.b.dxi_deps, r * 6 + b, ld, i, ((r == b) ? 1.0 : 0.0) - X[r]);
@@ -234,7 +241,7 @@ mp_update_kernel(const __grid_constant__ MpArgs A) {
             double X[7];
 #pragma unroll
             for (int r = 0; r < 7; ++r) X[r] = (r == b) ? 1.0 : 0.0;
-            if (pl) lu.solve(X);
+            if (pl) { if (slow && trouble) lu.solve_pivot(X); else lu.solve_natural(X); }
             const double ltr = m.lam * (X[0] + X[3] + X[5]);
 #pragma unroll
             for (int a = 0; a < 6; ++a) Dm[a][b] = is_diag(a) ? fma(m.two_mu, X[a], ltr) : m.two_mu * X[a];

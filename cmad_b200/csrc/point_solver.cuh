@@ -204,15 +204,67 @@ template <> struct YieldFn<CMADX_YIELD_HOSFORD> {
 };
 
 // --------------------------------------------------------------------------
-// register-resident dense LU with partial pivoting (row swaps as predicated
-// selects; the swap decisions are recorded so right-hand sides can be
-// permuted later).  a[k][k] holds 1/pivot after factor().
+// register-resident dense LU.
+//
+// The reference solves the local system with LAPACK-style partial pivoting
+// (jnp.linalg.solve, cmad/models/nonlinear_solver.py:123).  With the matrix
+// in registers a row exchange costs a sweep of predicated selects per
+// candidate row, which tripled the instruction count of the whole kernel
+// (profiles/r1_k1_v1: 37 % FSEL).  The plastic Jacobian
+// [[I + dgamma*2mu*H*W, -n], [-(W n)^T, -H'/2mu]] (H = yield-surface Hessian,
+// PSD; W = diag(1,2,2,1,2,1)) is a column-scaled SPD block bordered by the
+// consistency row, for which elimination in natural order is backward stable
+// whenever dgamma >= 0.  So: *threshold* pivoting - eliminate in natural order,
+// flag a lane as "troubled" if any natural pivot is more than 10x smaller than
+// an entry below it (or is NaN), and only troubled lanes re-do the solve with
+// full partial pivoting (factor_pivot / solve_pivot).  Both paths are stable
+// solves of the same system; they differ at rounding level only.
+// a[k][k] holds 1/pivot after factorisation.
 // --------------------------------------------------------------------------
 template <int N>
 struct RegLU {
     double a[N][N];
     unsigned swaps;
-    CMADX_DEV void factor() {
+
+    // natural-order elimination; returns true when this lane needs pivoting
+    CMADX_DEV bool factor_natural() {
+        bool trouble = false;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const double thr = 10.0 * fabs(a[k][k]);
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) trouble = trouble || !(fabs(a[i][k]) <= thr);
+            const double rp = 1.0 / a[k][k];
+            a[k][k] = rp;
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) {
+                const double l = a[i][k] * rp;
+                a[i][k] = l;
+#pragma unroll
+                for (int j = k + 1; j < N; ++j) a[i][j] = fma(-l, a[k][j], a[i][j]);
+            }
+        }
+        return trouble;
+    }
+    CMADX_DEV void solve_natural(double (&b)[N]) const {
+#pragma unroll
+        for (int i = 1; i < N; ++i) {
+#pragma unroll
+            for (int j = 0; j < i; ++j) b[i] = fma(-a[i][j], b[j], b[i]);
+        }
+#pragma unroll
+        for (int i = N - 1; i >= 0; --i) {
+            double s = b[i];
+#pragma unroll
+            for (int j = i + 1; j < N; ++j) s = fma(-a[i][j], b[j], s);
+            b[i] = s * a[i][i];
+        }
+    }
+
+    // full partial pivoting (rows bubble so that row k holds the column
+    // maximum, first maximum wins); the swap decisions are recorded so
+    // right-hand sides can be permuted later
+    CMADX_DEV void factor_pivot() {
         swaps = 0u;
         int bit = 0;
 #pragma unroll
@@ -240,7 +292,7 @@ struct RegLU {
             }
         }
     }
-    CMADX_DEV void solve(double (&b)[N]) const {
+    CMADX_DEV void solve_pivot(double (&b)[N]) const {
         int bit = 0;
 #pragma unroll
         for (int k = 0; k < N; ++k) {
@@ -253,20 +305,34 @@ struct RegLU {
                 ++bit;
             }
         }
-#pragma unroll
-        for (int i = 1; i < N; ++i) {
-#pragma unroll
-            for (int j = 0; j < i; ++j) b[i] = fma(-a[i][j], b[j], b[i]);
-        }
-#pragma unroll
-        for (int i = N - 1; i >= 0; --i) {
-            double s = b[i];
-#pragma unroll
-            for (int j = i + 1; j < N; ++j) s = fma(-a[i][j], b[j], s);
-            b[i] = s * a[i][i];
-        }
+        solve_natural(b);
     }
 };
+
+// delta = J(x)^{-1} rhs for the point's current state
+template <class Pt, int N>
+CMADX_DEV void newton_direction(const DevMat& m, const Pt& pt, double dg, double (&dx)[N]) {
+    double rhs[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) rhs[i] = dx[i];
+    bool trouble;
+    {
+        RegLU<N> lu;
+        pt.jacobian(m, dg, lu.a);
+        trouble = lu.factor_natural();
+        lu.solve_natural(dx);
+    }
+    if (__any_sync(__activemask(), trouble)) {
+        if (trouble) {
+            RegLU<N> lu;
+            pt.jacobian(m, dg, lu.a);
+            lu.factor_pivot();
+#pragma unroll
+            for (int i = 0; i < N; ++i) dx[i] = rhs[i];
+            lu.solve_pivot(dx);
+        }
+    }
+}
 
 // --------------------------------------------------------------------------
 // SmallElasticPlastic, FULL_3D.  State x = [ep(6), alpha], strain `em` already
@@ -403,14 +469,9 @@ CMADX_DEV NewtonResult local_newton(const DevMat& m, const DevNewton& nw, Pt& pt
                 } else {
                     if (!fresh) { double Ct[N]; pt.residual(m, x, xp, em, Ct); }
                     double dx[N];
-                    {
-                        RegLU<N> lu;
-                        pt.jacobian(m, x[N - 1] - xp[N - 1], lu.a);
-                        lu.factor();
 #pragma unroll
-                        for (int i = 0; i < N; ++i) dx[i] = C[i];
-                        lu.solve(dx);                             // delta = solve(J, C)
-                    }
+                    for (int i = 0; i < N; ++i) dx[i] = C[i];
+                    newton_direction<Pt, N>(m, pt, x[N - 1] - xp[N - 1], dx);   // solve(J, C)
                     // ---- line search (quadratic model), line_search.py:125-181
                     const double CC = dotN<N>(C, C);
                     const double phi0 = 0.5 * CC, dphi0 = -CC, armijo = nw.c1 * dphi0;
@@ -467,13 +528,10 @@ CMADX_DEV NewtonResult local_newton(const DevMat& m, const DevNewton& nw, Pt& pt
                 if (rel < nw.rel_tol || nc < nw.abs_tol) {
                     done = true;
                 } else {
-                    RegLU<N> lu;
-                    pt.jacobian(m, x[N - 1] - xp[N - 1], lu.a);
-                    lu.factor();
                     double dx[N];
 #pragma unroll
                     for (int i = 0; i < N; ++i) dx[i] = -C[i];
-                    lu.solve(dx);                                 // solve(J, -C)
+                    newton_direction<Pt, N>(m, pt, x[N - 1] - xp[N - 1], dx);   // solve(J, -C)
 #pragma unroll
                     for (int i = 0; i < N; ++i) x[i] += dx[i];
                     fresh = false;

@@ -427,13 +427,13 @@ inline void jac_x(int model, int n, const Mat<double>& md, const double* mat, co
 }
 
 inline void solve_point(const double* mat, const int* cfg, const double* sol,
-                        const double* xprev, const double* gu, PointOut& out) {
+                        const double* xprev, const double* xinit, const double* gu, PointOut& out) {
     const int model = cfg[0], mode = cfg[4], max_iters = cfg[5], ls_max = cfg[6];
     const int n = (model == MODEL_SEP) ? 7 : 6;
     const double abs_tol = sol[0], rel_tol = sol[1], c1 = sol[2], bmin = sol[3], bmax = sol[4];
     Mat<double> m = make_mat<double>(mat, cfg);
     double x[7] = {0}, xp[7] = {0}, C[7] = {0};
-    for (int i = 0; i < n; ++i) { x[i] = xprev[i]; xp[i] = xprev[i]; }
+    for (int i = 0; i < n; ++i) { x[i] = xinit ? xinit[i] : xprev[i]; xp[i] = xprev[i]; }
     out.flag_entry = residual(model, m, x, xp, gu, C);
     out.ls_evals = 0;
     int ii = 0; bool converged = false;
@@ -515,7 +515,7 @@ extern "C" {
 int oracle_mp_update(const double* mat, const int* cfg, const double* sol,
                      const int* active_pid, int n_active,
                      int64_t npts, int64_t ld,
-                     const double* xi_prev, const double* strain,
+                     const double* xi_prev, const double* strain, const double* xi_init,
                      double* xi, double* sigma, double* dsig_deps, double* dxi_deps,
                      double* dC_dp, double* dC_dxi, double* dC_dxi_prev,
                      int* iters, int* flags, double* cnorm, int* ls_evals,
@@ -541,7 +541,9 @@ int oracle_mp_update(const double* mat, const int* cfg, const double* sol,
             for (int c = 0; c < 9; ++c) gu[c] = strain[c * ld + i];
         }
         PointOut po;
-        solve_point(mat, cfg, sol, xp, gu, po);
+        double x0[7] = {0};
+        if (xi_init) for (int c = 0; c < n; ++c) x0[c] = xi_init[c * ld + i];
+        solve_point(mat, cfg, sol, xp, xi_init ? x0 : nullptr, gu, po);
         if (xi) for (int c = 0; c < n; ++c) xi[c * ld + i] = po.x[c];
         if (iters) iters[i] = po.iters;
         if (flags) flags[i] = po.flag_entry | (po.flag_exit << 1);

@@ -143,12 +143,15 @@ def _p(a, ct):
 
 def mp_update(prob: OracleProblem, xi_prev: np.ndarray, strain: np.ndarray,
               want=("xi", "sigma", "dsig_deps", "dC_dp", "iters", "flags", "cnorm"),
-              nthreads: int = 0) -> dict:
+              nthreads: int = 0, xi_init: np.ndarray | None = None) -> dict:
     """Batched update on component-major arrays: ``xi_prev (n_xi, N)``,
     ``strain (6|9, N)``.  Returns a dict of the requested outputs."""
     n_xi = prob.n_xi
     xi_prev = np.ascontiguousarray(xi_prev, dtype=np.float64)
     strain = np.ascontiguousarray(strain, dtype=np.float64)
+    if xi_init is not None:
+        xi_init = np.ascontiguousarray(xi_init, dtype=np.float64)
+        assert xi_init.shape == xi_prev.shape
     N = xi_prev.shape[1]
     assert xi_prev.shape == (n_xi, N) and strain.shape == (int(prob.cfg[7]), N)
     na = len(prob.active_pid)
@@ -161,7 +164,7 @@ def mp_update(prob: OracleProblem, xi_prev: np.ndarray, strain: np.ndarray,
     rc = lib().oracle_mp_update(
         _p(prob.mat, d), _p(prob.cfg, i32), _p(prob.sol, d), _p(prob.active_pid, i32),
         ctypes.c_int(na), ctypes.c_int64(N), ctypes.c_int64(N),
-        _p(xi_prev, d), _p(strain, d),
+        _p(xi_prev, d), _p(strain, d), _p(xi_init, d),
         _p(out["xi"], d), _p(out["sigma"], d), _p(out["dsig_deps"], d), _p(out["dxi_deps"], d),
         _p(out["dC_dp"], d), _p(out["dC_dxi"], d), _p(out["dC_dxi_prev"], d),
         _p(ints["iters"], i32), _p(ints["flags"], i32), _p(cnorm, d), _p(ints["ls_evals"], i32),

@@ -198,6 +198,39 @@ def test_evaluate_at_state_semantics(cuda_device):
     assert float(b["C"].abs().max()) < 1e-10
 
 
+def test_pivoted_fallback_path_matches_lapack_style_oracle(cuda_device):
+    """States with a strongly negative plastic increment make the natural pivots
+    of the local Jacobian tiny or negative; the kernel must then fall back to
+    full partial pivoting and still agree with the (always pivoting) oracle."""
+    rng = np.random.default_rng(13)
+    values, act, tr = param_tree("J2")
+    P = Parameters(values, act, tr); mat = material_from_values(values); pid = active_param_ids(P)
+    n = 4096
+    e = random_strains(rng, n, scale=4e-3)
+    lam, mu = 200e3 * 0.3 / (1.3 * 0.4), 200e3 / 2.6
+    dev_e = e.copy(); dev_e[[0, 3, 5]] -= (e[0] + e[3] + e[5]) / 3
+    snorm = 2 * mu * np.sqrt(dev_e[0] ** 2 + dev_e[3] ** 2 + dev_e[5] ** 2 + 2 * (dev_e[1] ** 2 + dev_e[2] ** 2 + dev_e[4] ** 2))
+    xi_init = np.zeros((7, n))
+    # dgamma*2mu*sqrt(1.5)/||s|| swept over [-3, -0.5]: diagonal 1 + s*M_kk crosses zero
+    xi_init[6] = -rng.uniform(0.5, 3.0, size=n) * snorm / (2 * mu * np.sqrt(1.5))
+    xi_prev = np.zeros((7, n))
+    kw = dict(max_iters=1, abs_tol=1e-12, rel_tol=1e-12)
+    for mode in ("imperative", "traced"):
+        nw = NewtonSettings(mode=mode, **kw)
+        prob = oc.describe(values, P.active_idx, newton_mode=mode, **kw)
+        want = ("xi", "iters", "flags", "dsig_deps", "dxi_deps")
+        out = mp.mp_update(mat, nw, pid, torch.from_numpy(xi_prev).to(cuda_device),
+                           torch.from_numpy(e).to(cuda_device), outputs=want,
+                           xi_init=torch.from_numpy(xi_init).to(cuda_device))
+        ref = oc.mp_update(prob, xi_prev, e, want=want, xi_init=xi_init)
+        assert np.array_equal(out["iters"].cpu().numpy(), ref["iters"])
+        # ill-conditioned on purpose: compare where the oracle's own solve is well scaled
+        good = np.isfinite(ref["xi"]).all(axis=0) & (np.abs(ref["xi"]).max(axis=0) < 1.0)
+        assert good.mean() > 0.9
+        g = out["xi"].cpu().numpy()
+        assert rel_err(g[:, good], ref["xi"][:, good]) < 1e-8
+
+
 def test_ragged_sizes_padding_and_empty(cuda_device):
     values, act, tr = param_tree("J2")
     P = Parameters(values, act, tr); mat = material_from_values(values); pid = active_param_ids(P)
