@@ -15,7 +15,8 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "lib", "libcmad_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
-SOURCES = ["api.cu", "mp_update.cu", "elastic_update.cu", "mp_sens.cu", "fe_block.cu"]
+SOURCES = ["api.cu", "mp_update.cu", "mp_update_j2.cu", "elastic_update.cu", "mp_sens.cu",
+           "fe_block.cu"]
 
 # ---- enums (mirror include/cmad_b200.h) ---------------------------------
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(5)
@@ -30,6 +31,7 @@ HARD_VOCE, HARD_LINEAR = 1, 2
 NUM_PARAM_IDS = P_Q00 + 9
 MAX_ACTIVE = 16
 NEWTON_TRACED, NEWTON_IMPERATIVE = 0, 1
+NEWTON_F_GENERIC = 1
 
 
 class Material(C.Structure):
@@ -42,7 +44,7 @@ class Material(C.Structure):
 
 class Newton(C.Structure):
     _fields_ = [("mode", C.c_int32), ("max_iters", C.c_int32), ("ls_max_evals", C.c_int32),
-                ("reserved", C.c_int32), ("abs_tol", C.c_double), ("rel_tol", C.c_double),
+                ("flags", C.c_int32), ("abs_tol", C.c_double), ("rel_tol", C.c_double),
                 ("ls_c1", C.c_double), ("ls_bmin", C.c_double), ("ls_bmax", C.c_double)]
 
 
@@ -97,6 +99,8 @@ def lib() -> C.CDLL:
     L.cmadx_error_string.argtypes = [C.c_int]
     L.cmadx_last_cuda_error.restype = C.c_char_p
     L.cmadx_launch_count.restype = C.c_int64
+    L.cmadx_debug_bail_count.restype = C.c_int64
+    L.cmadx_debug_bail_count.argtypes = [C.c_void_p]
     L.cmadx_lame.argtypes = [C.POINTER(Material), C.POINTER(C.c_double)]
     mp_args = [C.POINTER(Material), C.POINTER(Newton), C.POINTER(C.c_int32), C.c_int32,
                C.POINTER(MpBuffers)]

@@ -107,7 +107,7 @@ int make_dev_newton(const cmadx_newton_t* nw, DevNewton* o) {
     if (nw->mode != CMADX_NEWTON_TRACED && nw->mode != CMADX_NEWTON_IMPERATIVE) return CMADX_EINVAL;
     if (nw->max_iters < 0) return CMADX_EINVAL;
     if (nw->mode == CMADX_NEWTON_TRACED && nw->ls_max_evals < 1) return CMADX_EINVAL;
-    o->mode = nw->mode; o->max_iters = nw->max_iters; o->ls_max = nw->ls_max_evals; o->pad = 0;
+    o->mode = nw->mode; o->max_iters = nw->max_iters; o->ls_max = nw->ls_max_evals; o->flags = nw->flags;
     o->abs_tol = nw->abs_tol; o->rel_tol = nw->rel_tol;
     o->c1 = nw->ls_c1; o->bmin = nw->ls_bmin; o->bmax = nw->ls_bmax;
     return CMADX_OK;
@@ -134,13 +134,60 @@ static int build_args(const cmadx_material_t* mat, const cmadx_newton_t* nw,
     if (b->strain_comps != 6 && b->strain_comps != 9) return CMADX_EINVAL;
     if (b->n > 0 && (!b->xi_prev || !b->strain)) return CMADX_EINVAL;
     A->b = *b;
+    A->bail_count = nullptr; A->bail_list = nullptr; A->bail_cap = 0;
     return CMADX_OK;
 }
 
+// scratch of the J2 radial kernel's bail list, one per (device, stream)
+namespace {
+constexpr unsigned BAIL_CAP = 1u << 20;
+struct BailScratch {
+    int device;
+    cudaStream_t stream;
+    unsigned* count;   // count, then the index list
+};
+std::mutex g_bail_mutex;
+std::vector<BailScratch> g_bail;
+
+int get_bail_scratch(cudaStream_t s, BailScratch* out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    std::lock_guard<std::mutex> lock(g_bail_mutex);
+    for (auto& b : g_bail)
+        if (b.device == dev && b.stream == s) { *out = b; return CMADX_OK; }
+    BailScratch b{dev, s, nullptr};
+    e = cudaMalloc(&b.count, sizeof(unsigned) * (size_t)(BAIL_CAP + 64));
+    if (e != cudaSuccess) return (e == cudaErrorMemoryAllocation) ? CMADX_ENOMEM : cuda_fail(e);
+    g_bail.push_back(b);
+    *out = b;
+    return CMADX_OK;
+}
+}  // namespace
+
 static int launch(const MpArgs& A, cudaStream_t s) {
     if (A.b.n == 0) return CMADX_OK;
-    cudaError_t e = (A.m.model == CMADX_MODEL_ELASTIC) ? launch_mp_update_elastic(A, s)
-                                                       : launch_mp_update_sep(A, s);
+    cudaError_t e;
+    if (A.m.model == CMADX_MODEL_ELASTIC) {
+        e = launch_mp_update_elastic(A, s);
+    } else if (A.m.yield == CMADX_YIELD_J2 && !A.m.rot && !A.b.xi_init &&
+               !(A.nw.flags & CMADX_NEWTON_F_GENERIC) && A.b.n < (int64_t)0x7fffffff) {
+        // J2 radial-return kernel, then the generic kernel over whatever it handed back
+        BailScratch bs;
+        if (int rc = get_bail_scratch(s, &bs)) return rc;
+        MpArgs B = A;
+        B.bail_count = bs.count;
+        B.bail_list = reinterpret_cast<int*>(bs.count + 64);
+        B.bail_cap = BAIL_CAP;
+        e = cudaMemsetAsync(bs.count, 0, sizeof(unsigned), s);
+        if (e != cudaSuccess) return cuda_fail(e);
+        e = launch_mp_update_j2(B, s);
+        if (e != cudaSuccess) return cuda_fail(e);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = launch_mp_update_sep_list(B, s);
+    } else {
+        e = launch_mp_update_sep(A, s);
+    }
     if (e != cudaSuccess) return cuda_fail(e);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return CMADX_OK;
@@ -222,6 +269,22 @@ const char* cmadx_error_string(int code) {
 const char* cmadx_last_cuda_error(void) { return g_cuda_err; }
 
 int64_t cmadx_launch_count(void) { return g_launches.load(); }
+
+int64_t cmadx_debug_bail_count(void* stream) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    unsigned* p = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_bail_mutex);
+        for (auto& b : g_bail)
+            if (b.device == dev && b.stream == (cudaStream_t)stream) p = b.count;
+    }
+    if (!p) return -1;
+    unsigned v = 0;
+    if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return -1;
+    if (cudaMemcpy(&v, p, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int64_t)v;
+}
 
 int cmadx_lame(const cmadx_material_t* mat, double* out6) {
     if (!mat || !out6) return CMADX_EINVAL;
@@ -341,6 +404,11 @@ int cmadx_release_host_scratch(void) {
         }
     }
     g_hs.clear();
+    {
+        std::lock_guard<std::mutex> lock2(g_bail_mutex);
+        for (auto& b : g_bail) { cudaSetDevice(b.device); cudaFree(b.count); }
+        g_bail.clear();
+    }
     return CMADX_OK;
 }
 

@@ -10,15 +10,11 @@
 //   cmad/models/nonlinear_solver.py:88-174 (make_newton_solve + IFT rule) or
 //   :14-85 (newton_solve), cmad/models/model.py:121-166 (AD Jacobians),
 //   cmad/parameters/parameters.py:368-377 (active-column selection).
-#include "mp_update.cuh"
+#include "mp_outputs.cuh"
 
 namespace cmadx {
 
 namespace {
-
-CMADX_DEV void st(double* p, int64_t c, int64_t ld, int64_t i, double v) {
-    __stcs(p + c * ld + i, v);
-}
 
 // 6x6 maps between global and material symmetric-tensor components for a
 // rotation Q (cmad/models/small_elastic_plastic.py:44-62, 318-319):
@@ -39,33 +35,12 @@ CMADX_DEV void rot_maps(const double* Q, double (&T)[6][6], double (&S)[6][6]) {
 }
 
 template <int YK, bool ROT>
-__global__ void __launch_bounds__(MP_BLOCK)
-mp_update_kernel(const __grid_constant__ MpArgs A) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < A.b.n;
+CMADX_DEV void process_point(const MpArgs& A, const int64_t i, const bool live) {
     const int64_t ld = A.b.ld;
     const DevMat& m = A.m;
 
     double xp[7], x[7], e[6];
-    if (live) {
-#pragma unroll
-        for (int c = 0; c < 7; ++c) xp[c] = __ldg(A.b.xi_prev + c * ld + i);
-        if (A.b.strain_comps == 6) {
-#pragma unroll
-            for (int c = 0; c < 6; ++c) e[c] = __ldg(A.b.strain + c * ld + i);
-        } else {
-            double g[9];
-#pragma unroll
-            for (int c = 0; c < 9; ++c) g[c] = __ldg(A.b.strain + c * ld + i);
-            e[0] = g[0]; e[3] = g[4]; e[5] = g[8];
-            e[1] = 0.5 * (g[1] + g[3]); e[2] = 0.5 * (g[2] + g[6]); e[4] = 0.5 * (g[5] + g[7]);
-        }
-    } else {
-#pragma unroll
-        for (int c = 0; c < 7; ++c) xp[c] = 0.0;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) e[c] = 0.0;
-    }
+    load_point(A.b, i, live, xp, e);
     double em[6];
     if (ROT) {
         double T[6][6], S[6][6];
@@ -132,24 +107,10 @@ mp_update_kernel(const __grid_constant__ MpArgs A) {
     const double dg = x[6] - xp[6];
     const bool pl = pt.plastic;
 
-    // dC/dxi_prev: plastic rows a<6: -I and +n in the alpha column; yield row 0
-    if (A.b.dC_dxi_prev) {
-#pragma unroll
-        for (int r = 0; r < 7; ++r)
-#pragma unroll
-            for (int c = 0; c < 7; ++c) {
-                double v = (r == c) ? -1.0 : 0.0;
-                if (pl) {
-                    if (r == 6) v = 0.0;
-                    else if (c == 6) v = pt.n[r];
-                }
-                st(A.b.dC_dxi_prev, r * 7 + c, ld, i, v);
-            }
-    }
+    if (A.b.dC_dxi_prev) write_dC_dxi_prev(A.b.dC_dxi_prev, ld, i, pl, pt.n);
 
     // dC/dp at (x*, x_prev): elastic branch -> 0 (C_e holds no parameters)
     if (A.b.dC_dp && A.n_active > 0) {
-        const int na = A.n_active;
         double Mee[6];      // (dn/dsigma : ee)_a
         double nee = 0.0;   // n : ee
 #pragma unroll
@@ -160,37 +121,7 @@ mp_update_kernel(const __grid_constant__ MpArgs A) {
             Mee[a] = s;
             nee = fma(mult(a) * pt.n[a], ee[a], nee);
         }
-        const double imu = 1.0 / m.mu;
-        for (int c = 0; c < na; ++c) {
-            const int pid = A.pid[c];
-            double col[7] = {0, 0, 0, 0, 0, 0, 0};
-            if (pl) {
-                if (pid == CMADX_P_EL0 || pid == CMADX_P_EL1) {
-                    // only mu matters: all three surfaces are pressure-insensitive
-                    const double dmu = m.dmu[pid - CMADX_P_EL0];
-#pragma unroll
-                    for (int a = 0; a < 6; ++a) col[a] = -2.0 * dg * Mee[a] * dmu;
-                    col[6] = (nee - pt.f) * imu * dmu;
-                } else if (pid == CMADX_P_Y) {
-                    col[6] = -m.inv_two_mu;
-                } else if (pid == CMADX_P_VOCE_S) {
-                    col[6] = -(1.0 - pt.eD) * m.inv_two_mu;
-                } else if (pid == CMADX_P_VOCE_D) {
-                    col[6] = -m.S * x[6] * pt.eD * m.inv_two_mu;
-                } else if (pid == CMADX_P_LIN_K) {
-                    col[6] = -x[6] * m.inv_two_mu;
-                } else {
-                    double dphi, dn[6];
-                    if (pt.yf.dparam(m, pid, sig, dphi, dn)) {
-#pragma unroll
-                        for (int a = 0; a < 6; ++a) col[a] = -dg * dn[a];
-                        col[6] = dphi * m.inv_two_mu;
-                    }
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < 7; ++r) st(A.b.dC_dp, (int64_t)r * na + c, ld, i, col[r]);
-        }
+        write_dC_dp(A, i, pl, pt.yf, pt.n, pt.f, pt.eD, x[6], dg, Mee, nee, sig);
     }
 
     const bool want_ift = A.b.dsig_deps || A.b.dxi_deps;
@@ -285,6 +216,33 @@ mp_update_kernel(const __grid_constant__ MpArgs A) {
     }
 }
 
+// one thread per point over the whole batch
+template <int YK, bool ROT>
+__global__ void __launch_bounds__(MP_BLOCK)
+mp_update_kernel(const __grid_constant__ MpArgs A) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    process_point<YK, ROT>(A, i, i < A.b.n);
+}
+
+// list mode: a small grid walks the points the J2 radial kernel handed back
+// (bail_count == 0: nothing to do; > bail_cap: the list overflowed, redo all)
+template <int YK, bool ROT>
+__global__ void __launch_bounds__(MP_BLOCK)
+mp_update_list_kernel(const __grid_constant__ MpArgs A) {
+    const unsigned cnt = *A.bail_count;
+    if (cnt == 0u) return;
+    const bool all = cnt > A.bail_cap;
+    const int64_t total = all ? A.b.n : (int64_t)cnt;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); base < total; base += stride) {
+        const int64_t j = base + lane;
+        const bool live = j < total;
+        const int64_t i = live ? (all ? j : (int64_t)A.bail_list[j]) : 0;
+        process_point<YK, ROT>(A, i, live);
+    }
+}
+
 template <int YK>
 cudaError_t launch_yk(const MpArgs& A, cudaStream_t stream) {
     const int64_t nblk = (A.b.n + MP_BLOCK - 1) / MP_BLOCK;
@@ -303,6 +261,15 @@ cudaError_t launch_mp_update_sep(const MpArgs& A, cudaStream_t stream) {
     case CMADX_YIELD_HOSFORD: return launch_yk<CMADX_YIELD_HOSFORD>(A, stream);
     }
     return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_mp_update_sep_list(const MpArgs& A, cudaStream_t stream) {
+    if (A.b.n == 0) return cudaSuccess;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    mp_update_list_kernel<CMADX_YIELD_J2, false><<<(unsigned)(2 * sms), MP_BLOCK, 0, stream>>>(A);
+    return cudaGetLastError();
 }
 
 }  // namespace cmadx

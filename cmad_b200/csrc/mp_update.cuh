@@ -12,6 +12,11 @@ struct MpArgs {
     int n_active;
     int pid[CMADX_MAX_ACTIVE];
     cmadx_mp_buffers_t b;
+    // fallback ("bail") list written by the J2 radial kernel and consumed by the
+    // generic kernel in list mode; all NULL/0 for a plain full-batch launch
+    unsigned* bail_count;
+    int* bail_list;
+    unsigned bail_cap;
 };
 
 // host-side: validate + convert the C-ABI structs (defined in api.cu)
@@ -19,6 +24,10 @@ int make_dev_mat(const cmadx_material_t* mat, DevMat* out);
 int make_dev_newton(const cmadx_newton_t* nw, DevNewton* out);
 
 cudaError_t launch_mp_update_sep(const MpArgs& A, cudaStream_t stream);
+// J2 radial-return kernel (valid for yield J2, no rotation, no xi_init)
+cudaError_t launch_mp_update_j2(const MpArgs& A, cudaStream_t stream);
+// generic kernel over the bail list (small persistent grid)
+cudaError_t launch_mp_update_sep_list(const MpArgs& A, cudaStream_t stream);
 cudaError_t launch_mp_update_elastic(const MpArgs& A, cudaStream_t stream);
 
 }  // namespace cmadx

@@ -36,7 +36,7 @@ struct DevMat {
 };
 
 struct DevNewton {
-    int mode, max_iters, ls_max, pad;
+    int mode, max_iters, ls_max, flags;
     double abs_tol, rel_tol, c1, bmin, bmax;
 };
 
@@ -59,6 +59,7 @@ template <int YK> struct YieldFn;
 
 template <> struct YieldFn<CMADX_YIELD_J2> {
     double c;       // sqrt(3/2)/||s||
+    double sn;      // ||s||
     double sh[6];   // s/||s||
     CMADX_DEV void eval(const DevMat&, const double (&sig)[6], double& phi, double (&n)[6]) {
         const double h = (sig[0] + sig[3] + sig[5]) / 3.0;
@@ -68,7 +69,7 @@ template <> struct YieldFn<CMADX_YIELD_J2> {
         double ss = 0.0;
 #pragma unroll
         for (int a = 0; a < 6; ++a) ss = fma(mult(a) * s[a], s[a], ss);
-        const double sn = sqrt(ss);
+        sn = sqrt(ss);
         const double r32 = 1.2247448713915890491;   // sqrt(3/2)
         phi = r32 * sn;
         const double inv = 1.0 / sn;                // inf at zero deviator -> NaN normal (as JAX)

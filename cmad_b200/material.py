@@ -31,12 +31,14 @@ class NewtonSettings:
     ls_sufficient_decrease: float = 1.0e-4
     ls_min_backtrack: float = 0.5
     ls_max_backtrack: float = 0.9
+    force_generic: bool = False     # bypass the J2 radial-return specialisation (A/B testing)
 
     def to_struct(self) -> L.Newton:
         if self.mode not in ("traced", "imperative"):
             raise ValueError(f"unknown newton mode {self.mode!r}")
         return L.Newton(L.NEWTON_TRACED if self.mode == "traced" else L.NEWTON_IMPERATIVE,
-                        int(self.max_iters), int(self.ls_max_evals), 0,
+                        int(self.max_iters), int(self.ls_max_evals),
+                        L.NEWTON_F_GENERIC if self.force_generic else 0,
                         float(self.abs_tol), float(self.rel_tol),
                         float(self.ls_sufficient_decrease), float(self.ls_min_backtrack),
                         float(self.ls_max_backtrack))

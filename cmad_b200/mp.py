@@ -141,3 +141,9 @@ def fp64_peak_tflops(iters: int = 20000) -> float:
 
 def launch_count() -> int:
     return int(L.lib().cmadx_launch_count())
+
+
+def debug_bail_count(stream: torch.cuda.Stream | None = None) -> int:
+    """Points the last J2 radial-return launch handed to the generic kernel."""
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return int(L.lib().cmadx_debug_bail_count(C.c_void_p(s.cuda_stream)))

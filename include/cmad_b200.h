@@ -68,6 +68,10 @@ enum {
     CMADX_NEWTON_IMPERATIVE = 1  /* newton_solve(model), cmad/models/nonlinear_solver.py:14-85 */
 };
 
+/* cmadx_newton_t.flags: force the generic 7x7 Newton kernel even where the J2
+ * radial-return specialisation applies (testing / A-B comparison) */
+enum { CMADX_NEWTON_F_GENERIC = 1 };
+
 /* Material = the reference's parameter pytree for one element block
  * (cmad/parameters/parameters.py:205-272), flattened to a POD. */
 typedef struct cmadx_material {
@@ -92,7 +96,7 @@ typedef struct cmadx_newton {
     int32_t mode;           /* CMADX_NEWTON_*                                  */
     int32_t max_iters;
     int32_t ls_max_evals;   /* traced mode only; >= 1                          */
-    int32_t reserved;
+    int32_t flags;          /* CMADX_NEWTON_F_* bits                           */
     double abs_tol, rel_tol;
     double ls_c1, ls_bmin, ls_bmax;
 } cmadx_newton_t;
@@ -166,6 +170,10 @@ int cmadx_mp_update_host(const cmadx_material_t* mat, const cmadx_newton_t* newt
                          const cmadx_mp_buffers_t* host, int device,
                          int64_t chunk_points);
 int cmadx_release_host_scratch(void);
+
+/* debugging aid: how many points the last J2 radial-return launch on `stream`
+ * handed back to the generic kernel (synchronises the stream); -1 if none ran */
+int64_t cmadx_debug_bail_count(void* stream);
 
 /* number of kernel launches issued by this library since load (all threads) */
 int64_t cmadx_launch_count(void);
