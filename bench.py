@@ -247,11 +247,12 @@ def run_b200(args):
     achieved = ALG_BYTES_PER_UPDATE * n / (avg_kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "kernel": "mp_update_kernel<J2>", "alg_bytes_per_update": ALG_BYTES_PER_UPDATE,
-                "avg_launch_ms": avg_kernel_ms,
+                "kernel": "mp_update_j2_kernel (+ mp_update_list_kernel fallback, ~0.5% of the step)",
+                "alg_bytes_per_update": ALG_BYTES_PER_UPDATE, "avg_launch_ms": avg_kernel_ms,
+                "traffic_note": "ncu dram bytes r+w per launch = 0.98x algorithmic (profiles/r1_k1_j2_raw.txt)",
                 "fp64": {"peak_tflops_measured": fp64_peak,
-                         "note": "DFMA micro-benchmark (cmadx_fp64_peak); kernel is FP64-pipe/"
-                                 "latency bound on plastic points, see profiles/"}}
+                         "note": "DFMA micro-benchmark (cmadx_fp64_peak); FP64 pipe ~28% busy in the "
+                                 "J2 kernel (ncu), i.e. HBM binds"}}
 
     # ---- e2e: same update through the host-buffer C-ABI call -----------------
     e2e = None
