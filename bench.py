@@ -152,7 +152,8 @@ def run_reference(args):
     t_all = time.perf_counter()
     # warm-up (untimed) then the timed sample; one "step" = one load step of the sample
     cpu_sample_rate(values, params, min(sample, 4096), ts[:max(1, min(W, 3))])
-    rate, threads, desc = cpu_sample_rate(values, params, sample, ts)
+    nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    rate, threads, desc = cpu_sample_rate(values, params, sample, ts, nthreads=nthreads)   # torchrun pins OMP_NUM_THREADS=1
     ms = sample / rate * 1e3
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "updates/s",
@@ -278,8 +279,9 @@ def run_b200(args):
             "per_launch_ms": {"min": float(np.min(per_launch_ms)), "max": float(np.max(per_launch_ms))},
         }
         if world == 1 and not args.no_cpu_baseline:
+            nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
             rate, threads, desc = cpu_sample_rate(values, params, args.cpu_sample_points,
-                                                  [10, 30, 50, 70, 90])
+                                                  [10, 30, 50, 70, 90], nthreads=nthreads)
             line["cpu_baseline"] = {"value": rate, "unit": "updates/s", "cores": threads,
                                     "kind": "port", "sample": desc,
                                     "host_cpus": os.cpu_count()}

@@ -57,6 +57,13 @@ class MpBuffers(C.Structure):
                 ("cnorm", C.c_void_p), ("C", C.c_void_p)]
 
 
+class MpHistory(C.Structure):
+    _fields_ = [("n", C.c_int64), ("ld", C.c_int64), ("nsteps", C.c_int32),
+                ("strain_comps", C.c_int32), ("strain", C.c_void_p), ("data", C.c_void_p),
+                ("weight", C.c_double * 9), ("xi_hist", C.c_void_p), ("iters_hist", C.c_void_p),
+                ("result", C.c_void_p), ("workspace", C.c_void_p), ("J_point", C.c_void_p)]
+
+
 class CmadxError(RuntimeError):
     pass
 
@@ -107,6 +114,13 @@ def lib() -> C.CDLL:
     L.cmadx_mp_update.argtypes = mp_args + [C.c_void_p]
     L.cmadx_mp_update_host.argtypes = mp_args + [C.c_int, C.c_int64]
     L.cmadx_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_void_p]
+    L.cmadx_mp_objective_workspace_bytes.restype = C.c_int64
+    L.cmadx_mp_objective_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
+    L.cmadx_mp_forward_history.argtypes = [C.POINTER(Material), C.POINTER(Newton),
+                                           C.POINTER(MpHistory), C.c_void_p]
+    obj_args = [C.POINTER(Material), C.POINTER(C.c_int32), C.c_int32, C.POINTER(MpHistory), C.c_void_p]
+    L.cmadx_mp_objective_adjoint.argtypes = obj_args
+    L.cmadx_mp_objective_direct.argtypes = obj_args
     _lib = L
     return L
 

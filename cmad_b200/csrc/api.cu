@@ -11,6 +11,18 @@
 #include "mp_update.cuh"
 
 namespace cmadx {
+struct SensArgs {
+    DevMat m;
+    int n_active;
+    int pid[CMADX_MAX_ACTIVE];
+    cmadx_mp_history_t h;
+    double* partials;
+};
+cudaError_t launch_mp_sens(const SensArgs& A, bool adjoint, cudaStream_t stream);
+int64_t sens_blocks(int64_t n);
+}  // namespace cmadx
+
+namespace cmadx {
 
 std::atomic<int64_t> g_launches{0};
 thread_local char g_cuda_err[256] = "";
@@ -249,9 +261,10 @@ extern "C" {
 
 int cmadx_version(void) { return CMADX_VERSION; }
 
-int cmadx_struct_sizes(int64_t* out3) {
-    if (!out3) return CMADX_EINVAL;
-    out3[0] = sizeof(cmadx_material_t); out3[1] = sizeof(cmadx_newton_t); out3[2] = sizeof(cmadx_mp_buffers_t);
+int cmadx_struct_sizes(int64_t* out4) {
+    if (!out4) return CMADX_EINVAL;
+    out4[0] = sizeof(cmadx_material_t); out4[1] = sizeof(cmadx_newton_t); out4[2] = sizeof(cmadx_mp_buffers_t);
+    out4[3] = sizeof(cmadx_mp_history_t);
     return CMADX_OK;
 }
 
@@ -392,6 +405,70 @@ int cmadx_mp_update_host(const cmadx_material_t* mat, const cmadx_newton_t* newt
         if (e != cudaSuccess) return cuda_fail(e);
     }
     return CMADX_OK;
+}
+
+int64_t cmadx_mp_objective_workspace_bytes(int64_t n, int32_t n_active) {
+    if (n < 0 || n_active < 0 || n_active > CMADX_MAX_ACTIVE) return -1;
+    return (int64_t)sizeof(double) * (sens_blocks(n) + 1) * (1 + n_active);
+}
+
+static int check_history(const cmadx_material_t* mat, const cmadx_mp_history_t* h, DevMat* dm) {
+    if (!h) return CMADX_EINVAL;
+    if (int rc = make_dev_mat(mat, dm)) return rc;
+    if (dm->model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC) return CMADX_EUNSUPPORTED;
+    if (h->n < 0 || h->ld < h->n || h->nsteps < 0) return CMADX_EINVAL;
+    if (h->strain_comps != 6 && h->strain_comps != 9) return CMADX_EINVAL;
+    if (h->n > 0 && (!h->strain || !h->xi_hist)) return CMADX_EINVAL;
+    return CMADX_OK;
+}
+
+int cmadx_mp_forward_history(const cmadx_material_t* mat, const cmadx_newton_t* newton,
+                             const cmadx_mp_history_t* hist, void* stream) {
+    DevMat dm;
+    if (int rc = check_history(mat, hist, &dm)) return rc;
+    cmadx_mp_buffers_t b;
+    std::memset(&b, 0, sizeof(b));
+    b.n = hist->n; b.ld = hist->ld; b.strain_comps = hist->strain_comps;
+    for (int t = 1; t <= hist->nsteps; ++t) {
+        b.xi_prev = hist->xi_hist + (int64_t)(t - 1) * 7 * hist->ld;
+        b.xi = hist->xi_hist + (int64_t)t * 7 * hist->ld;
+        b.strain = hist->strain + (int64_t)t * hist->strain_comps * hist->ld;
+        b.iters = hist->iters_hist ? hist->iters_hist + (int64_t)t * hist->ld : nullptr;
+        if (int rc = cmadx_mp_update(mat, newton, nullptr, 0, &b, stream)) return rc;
+    }
+    return CMADX_OK;
+}
+
+static int objective(const cmadx_material_t* mat, const int32_t* active_pid, int32_t n_active,
+                     const cmadx_mp_history_t* hist, void* stream, bool adjoint) {
+    SensArgs A;
+    if (int rc = check_history(mat, hist, &A.m)) return rc;
+    if (A.m.rot) return CMADX_EUNSUPPORTED;
+    if (n_active < 0 || n_active > CMADX_MAX_ACTIVE || (n_active > 0 && !active_pid)) return CMADX_EINVAL;
+    if (!hist->result || !hist->workspace || (hist->n > 0 && !hist->data)) return CMADX_EINVAL;
+    for (int c = 0; c < n_active; ++c) {
+        const int pid = active_pid[c];
+        if (pid < 0 || pid >= CMADX_NUM_PARAM_IDS) return CMADX_EINVAL;
+        if (pid == CMADX_P_HOSFORD_A || pid >= CMADX_P_Q00) return CMADX_EUNSUPPORTED;
+        A.pid[c] = pid;
+    }
+    A.n_active = n_active;
+    A.h = *hist;
+    A.partials = hist->workspace;
+    cudaError_t e = launch_mp_sens(A, adjoint, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    return CMADX_OK;
+}
+
+int cmadx_mp_objective_adjoint(const cmadx_material_t* mat, const int32_t* active_pid,
+                               int32_t n_active, const cmadx_mp_history_t* hist, void* stream) {
+    return objective(mat, active_pid, n_active, hist, stream, true);
+}
+
+int cmadx_mp_objective_direct(const cmadx_material_t* mat, const int32_t* active_pid,
+                              int32_t n_active, const cmadx_mp_history_t* hist, void* stream) {
+    return objective(mat, active_pid, n_active, hist, stream, false);
 }
 
 int cmadx_release_host_scratch(void) {

@@ -50,42 +50,49 @@ CMADX_DEV void write_dC_dxi_prev(double* out, int64_t ld, int64_t i, bool pl, co
         }
 }
 
-// dC/dp at (x*, x_prev) for the requested canonical parameter ids.  Elastic
-// branch -> 0 (C_e holds no parameters).  Mee = (dn/dsigma : ee), nee = n : ee.
+// one column of dC/dp at (x*, x_prev) for canonical parameter id `pid`.
+// Elastic branch -> 0 (C_e holds no parameters).  Mee = (dn/dsigma : ee),
+// nee = n : ee, sig = material cauchy (for the yield-surface parameters).
+template <class YF>
+CMADX_DEV void dC_dp_column(const DevMat& m, int pid, bool pl, const YF& yf, const double (&n)[6],
+                            double f, double eD, double alpha, double dg,
+                            const double (&Mee)[6], double nee, const double (&sig)[6],
+                            double (&col)[7]) {
+#pragma unroll
+    for (int r = 0; r < 7; ++r) col[r] = 0.0;
+    if (!pl) return;
+    if (pid == CMADX_P_EL0 || pid == CMADX_P_EL1) {
+        // only mu matters: all three surfaces are pressure-insensitive
+        const double dmu = m.dmu[pid - CMADX_P_EL0];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) col[a] = -2.0 * dg * Mee[a] * dmu;
+        col[6] = (nee - f) / m.mu * dmu;
+    } else if (pid == CMADX_P_Y) {
+        col[6] = -m.inv_two_mu;
+    } else if (pid == CMADX_P_VOCE_S) {
+        col[6] = -(1.0 - eD) * m.inv_two_mu;
+    } else if (pid == CMADX_P_VOCE_D) {
+        col[6] = -m.S * alpha * eD * m.inv_two_mu;
+    } else if (pid == CMADX_P_LIN_K) {
+        col[6] = -alpha * m.inv_two_mu;
+    } else {
+        double dphi, dn[6];
+        if (yf.dparam(m, pid, sig, dphi, dn)) {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) col[a] = -dg * dn[a];
+            col[6] = dphi * m.inv_two_mu;
+        }
+    }
+}
+
 template <class YF>
 CMADX_DEV void write_dC_dp(const MpArgs& A, int64_t i, bool pl, const YF& yf, const double (&n)[6],
                            double f, double eD, double alpha, double dg,
                            const double (&Mee)[6], double nee, const double (&sig)[6]) {
-    const DevMat& m = A.m;
     const int na = A.n_active;
-    const double imu = 1.0 / m.mu;
     for (int c = 0; c < na; ++c) {
-        const int pid = A.pid[c];
-        double col[7] = {0, 0, 0, 0, 0, 0, 0};
-        if (pl) {
-            if (pid == CMADX_P_EL0 || pid == CMADX_P_EL1) {
-                // only mu matters: all three surfaces are pressure-insensitive
-                const double dmu = m.dmu[pid - CMADX_P_EL0];
-#pragma unroll
-                for (int a = 0; a < 6; ++a) col[a] = -2.0 * dg * Mee[a] * dmu;
-                col[6] = (nee - f) * imu * dmu;
-            } else if (pid == CMADX_P_Y) {
-                col[6] = -m.inv_two_mu;
-            } else if (pid == CMADX_P_VOCE_S) {
-                col[6] = -(1.0 - eD) * m.inv_two_mu;
-            } else if (pid == CMADX_P_VOCE_D) {
-                col[6] = -m.S * alpha * eD * m.inv_two_mu;
-            } else if (pid == CMADX_P_LIN_K) {
-                col[6] = -alpha * m.inv_two_mu;
-            } else {
-                double dphi, dn[6];
-                if (yf.dparam(m, pid, sig, dphi, dn)) {
-#pragma unroll
-                    for (int a = 0; a < 6; ++a) col[a] = -dg * dn[a];
-                    col[6] = dphi * m.inv_two_mu;
-                }
-            }
-        }
+        double col[7];
+        dC_dp_column(A.m, A.pid[c], pl, yf, n, f, eD, alpha, dg, Mee, nee, sig, col);
 #pragma unroll
         for (int r = 0; r < 7; ++r) st(A.b.dC_dp, (int64_t)r * na + c, A.b.ld, i, col[r]);
     }

@@ -1,0 +1,284 @@
+// K2 - calibration-objective sensitivities over whole load histories.
+//
+// One thread per material point walks that point's stored history in
+// registers: the adjoint variant backwards (phi_t = A_t^-T(-dJ/dxi_t + h),
+// h <- -B_t^T phi_t, g += phi_t^T dC/dp_t + dJ/dp_t), the direct variant forwards
+// (X_t = A_t^-1(-dC/dp_t - B_t X_{t-1}), g += dJ/dxi_t X_t + dJ/dp_t) with
+// A = dC/dxi, B = dC/dxi_prev evaluated at the stored (xi_t, xi_{t-1}).  Every
+// slab access is coalesced across the warp.  (J, grad) are reduced block-wise
+// (shuffle + shared memory) into per-block partials and then by a single block
+// in fixed order, so the result is bit-reproducible; the cross-GPU sum is one
+// NCCL allreduce of 1 + n_active doubles issued by the host layer.
+//
+// Replaces (reference file:line): cmad/objectives/mp_objective.py:92-147
+// (MPAdjointObjective), :150-215 (MPDirectObjective), with the QoI of
+// cmad/qois/calibration.py:56-66.
+#include "mp_outputs.cuh"
+
+namespace cmadx {
+
+struct SensArgs {
+    DevMat m;
+    int n_active;
+    int pid[CMADX_MAX_ACTIVE];
+    cmadx_mp_history_t h;
+    double* partials;     // [nblk][1 + n_active]
+};
+
+namespace {
+
+constexpr int SENS_BLOCK = 128;
+
+// Calibration QoI at one step: J, r_a = dJ/d sigma_a (both tensor entries of an
+// off-diagonal component summed)
+CMADX_DEV double qoi_terms(const double (&w)[9], const double (&sig)[6], const double (&d)[9],
+                           double (&r)[6]) {
+    // tensor entry (i,j) -> packed component
+    const int comp[9] = {0, 1, 2, 1, 3, 4, 2, 4, 5};
+    double J = 0.0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) r[a] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const double mis = w[k] * (sig[comp[k]] - d[k]);
+        J = fma(0.5 * mis, mis, J);
+        r[comp[k]] = fma(w[k], mis, r[comp[k]]);
+    }
+    return J;
+}
+
+template <int YK, bool ADJOINT>
+__global__ void __launch_bounds__(SENS_BLOCK)
+mp_sens_kernel(const __grid_constant__ SensArgs A) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < A.h.n;
+    const int64_t ld = A.h.ld;
+    const DevMat& m = A.m;
+    const int N = A.h.nsteps;
+    const int na = A.n_active;
+    const int sc = A.h.strain_comps;
+
+    double g[CMADX_MAX_ACTIVE];
+#pragma unroll
+    for (int c = 0; c < CMADX_MAX_ACTIVE; ++c) g[c] = 0.0;
+    double Jacc = 0.0;
+    double hist[7];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) hist[c] = 0.0;
+    double X[7][CMADX_MAX_ACTIVE];          // direct: dxi/dp carried forward (local memory)
+    if (!ADJOINT) {
+        for (int c = 0; c < na; ++c)
+#pragma unroll
+            for (int r = 0; r < 7; ++r) X[r][c] = 0.0;
+    }
+
+    for (int s = 0; s < N; ++s) {
+        const int t = ADJOINT ? N - s : s + 1;
+        double x[7], xp[7], em[6], d[9];
+        if (live) {
+            const double* xs = A.h.xi_hist + (int64_t)t * 7 * ld + i;
+            const double* xps = xs - 7 * ld;
+#pragma unroll
+            for (int c = 0; c < 7; ++c) { x[c] = __ldg(xs + c * ld); xp[c] = __ldg(xps + c * ld); }
+            const double* es = A.h.strain + (int64_t)t * sc * ld + i;
+            if (sc == 6) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) em[c] = __ldg(es + c * ld);
+            } else {
+                double gq[9];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) gq[c] = __ldg(es + c * ld);
+                em[0] = gq[0]; em[3] = gq[4]; em[5] = gq[8];
+                em[1] = 0.5 * (gq[1] + gq[3]); em[2] = 0.5 * (gq[2] + gq[6]); em[4] = 0.5 * (gq[5] + gq[7]);
+            }
+            const double* ds = A.h.data + (int64_t)t * 9 * ld + i;
+#pragma unroll
+            for (int c = 0; c < 9; ++c) d[c] = __ldg(ds + c * ld);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 7; ++c) { x[c] = 0.0; xp[c] = 0.0; }
+#pragma unroll
+            for (int c = 0; c < 6; ++c) em[c] = 1e-3 * (c == 0);
+#pragma unroll
+            for (int c = 0; c < 9; ++c) d[c] = 0.0;
+        }
+        SepPoint<YK> pt;
+        double C[7];
+        pt.residual(m, x, xp, em, C);
+        const bool pl = pt.plastic;
+        const double dg = x[6] - xp[6];
+        double ee[6], sig[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) ee[a] = em[a] - x[a];
+        const double tree = ee[0] + ee[3] + ee[5];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) sig[a] = is_diag(a) ? fma(m.two_mu, ee[a], m.lam * tree) : m.two_mu * ee[a];
+        double r[6];
+        Jacc += qoi_terms(A.h.weight, sig, d, r);
+        // dJ/dxi (row) : d sigma_a/d ep_b = -(2mu delta_ab + lam [a diag][b diag])
+        const double rtr = r[0] + r[3] + r[5];
+        double dJdx[7];
+#pragma unroll
+        for (int b = 0; b < 6; ++b) dJdx[b] = is_diag(b) ? fma(-m.two_mu, r[b], -m.lam * rtr) : -m.two_mu * r[b];
+        dJdx[6] = 0.0;
+        // dJ/dp: only through lambda, mu (sigma = lam tr(ee) I + 2 mu ee)
+        double ree = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) ree = fma(r[a], ee[a], ree);
+        const double dJdlam = tree * rtr, dJdmu = 2.0 * ree;
+        // (dn/dsigma : ee), n : ee for the dC/dp columns
+        double Mee[6], nee = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) sacc = fma(pt.yf.M(a, b), ee[b], sacc);
+            Mee[a] = sacc;
+            nee = fma(mult(a) * pt.n[a], ee[a], nee);
+        }
+        RegLU<7> lu;
+        if (ADJOINT) {
+            double Jm[7][7];
+            pt.jacobian(m, dg, Jm);
+#pragma unroll
+            for (int a = 0; a < 7; ++a)
+#pragma unroll
+                for (int b = 0; b < 7; ++b) lu.a[a][b] = Jm[b][a];
+        } else {
+            pt.jacobian(m, dg, lu.a);
+        }
+        // threshold pivoting as in the Newton kernels (RegLU): natural order is
+        // stable for these (row-/column-scaled SPD + border) matrices
+        bool trouble = lu.factor_natural();
+        const bool slow = __any_sync(__activemask(), trouble);
+        if (slow && trouble) {
+            if (ADJOINT) {
+                double Jm[7][7];
+                pt.jacobian(m, dg, Jm);
+#pragma unroll
+                for (int a = 0; a < 7; ++a)
+#pragma unroll
+                    for (int b = 0; b < 7; ++b) lu.a[a][b] = Jm[b][a];
+            } else {
+                pt.jacobian(m, dg, lu.a);
+            }
+            lu.factor_pivot();
+        }
+        if (ADJOINT) {
+            double phi[7];
+#pragma unroll
+            for (int c = 0; c < 7; ++c) phi[c] = hist[c] - dJdx[c];
+            if (slow && trouble) lu.solve_pivot(phi); else lu.solve_natural(phi);
+            // h <- -B^T phi
+            double nphi = 0.0;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) { hist[a] = phi[a]; nphi = fma(pt.n[a], phi[a], nphi); }
+            hist[6] = pl ? -nphi : phi[6];
+#pragma unroll
+            for (int c = 0; c < CMADX_MAX_ACTIVE; ++c) {
+                if (c < na) {
+                    const int pid = A.pid[c];
+                    double col[7];
+                    dC_dp_column(m, pid, pl, pt.yf, pt.n, pt.f, pt.eD, x[6], dg, Mee, nee, sig, col);
+                    double acc = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 7; ++q) acc = fma(phi[q], col[q], acc);
+                    if (pid == CMADX_P_EL0 || pid == CMADX_P_EL1)
+                        acc += dJdlam * m.dlam[pid - CMADX_P_EL0] + dJdmu * m.dmu[pid - CMADX_P_EL0];
+                    g[c] += acc;
+                }
+            }
+        } else {
+            for (int c = 0; c < na; ++c) {
+                const int pid = A.pid[c];
+                double col[7], rhs[7];
+                dC_dp_column(m, pid, pl, pt.yf, pt.n, pt.f, pt.eD, x[6], dg, Mee, nee, sig, col);
+                // rhs = -dC/dp - B X_prev ;  B = [-I, n; 0, 0] (plastic) or -I (elastic)
+                const double x6 = X[6][c];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) rhs[q] = -col[q] + X[q][c] - (pl ? pt.n[q] * x6 : 0.0);
+                rhs[6] = -col[6] + (pl ? 0.0 : x6);
+                if (slow && trouble) lu.solve_pivot(rhs); else lu.solve_natural(rhs);
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < 7; ++q) { X[q][c] = rhs[q]; acc = fma(dJdx[q], rhs[q], acc); }
+                if (pid == CMADX_P_EL0 || pid == CMADX_P_EL1)
+                    acc += dJdlam * m.dlam[pid - CMADX_P_EL0] + dJdmu * m.dmu[pid - CMADX_P_EL0];
+                g[c] += acc;
+            }
+        }
+    }
+    if (!live) {
+        Jacc = 0.0;
+#pragma unroll
+        for (int c = 0; c < CMADX_MAX_ACTIVE; ++c) g[c] = 0.0;
+    } else if (A.h.J_point) {
+        A.h.J_point[i] = Jacc;
+    }
+    // ---- block reduction (fixed order): warp shuffles, then 4 warps via smem
+    __shared__ double sm[SENS_BLOCK / 32][1 + CMADX_MAX_ACTIVE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c <= CMADX_MAX_ACTIVE; ++c) {
+        if (c <= na) {
+            double v = (c == 0) ? Jacc : g[c - 1];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0) sm[warp][c] = v;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x <= na) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < SENS_BLOCK / 32; ++w) v += sm[w][threadIdx.x];
+        A.partials[(int64_t)blockIdx.x * (1 + na) + threadIdx.x] = v;
+    }
+}
+
+// final reduction of the per-block partials by ONE block in fixed order
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const double* partials, int64_t nblk, int ncols, double* result) {
+    __shared__ double sm[256];
+    for (int c = 0; c < ncols; ++c) {
+        double v = 0.0;
+        for (int64_t b = threadIdx.x; b < nblk; b += 256) v += partials[b * ncols + c];
+        sm[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) result[c] = sm[0];
+        __syncthreads();
+    }
+}
+
+template <bool ADJOINT>
+cudaError_t launch_sens_t(const SensArgs& A, cudaStream_t stream) {
+    const int64_t nblk = (A.h.n + SENS_BLOCK - 1) / SENS_BLOCK;
+    switch (A.m.yield) {
+    case CMADX_YIELD_J2:
+        mp_sens_kernel<CMADX_YIELD_J2, ADJOINT><<<(unsigned)nblk, SENS_BLOCK, 0, stream>>>(A); break;
+    case CMADX_YIELD_HILL:
+        mp_sens_kernel<CMADX_YIELD_HILL, ADJOINT><<<(unsigned)nblk, SENS_BLOCK, 0, stream>>>(A); break;
+    case CMADX_YIELD_HOSFORD:
+        mp_sens_kernel<CMADX_YIELD_HOSFORD, ADJOINT><<<(unsigned)nblk, SENS_BLOCK, 0, stream>>>(A); break;
+    default: return cudaErrorInvalidValue;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    reduce_partials_kernel<<<1, 256, 0, stream>>>(A.partials, nblk, 1 + A.n_active, A.h.result);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_mp_sens(const SensArgs& A, bool adjoint, cudaStream_t stream) {
+    if (A.h.n == 0) return cudaMemsetAsync(A.h.result, 0, sizeof(double) * (1 + A.n_active), stream);
+    return adjoint ? launch_sens_t<true>(A, stream) : launch_sens_t<false>(A, stream);
+}
+
+int64_t sens_blocks(int64_t n) { return (n + SENS_BLOCK - 1) / SENS_BLOCK; }
+
+}  // namespace cmadx

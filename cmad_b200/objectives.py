@@ -1,0 +1,208 @@
+"""Material-point calibration objectives on the B200 path.
+
+Host-side mirror of ``cmad.objectives.mp_objective`` (MPAdjointObjective,
+MPDirectObjective; mp_objective.py:22-215), ``cmad.qois.calibration.Calibration``
+(calibration.py:21-66) and the model constructor surface they need
+(``cmad.models.small_elastic_plastic.SmallElasticPlastic``), *batched*: every
+objective evaluates many independent material points ("experiments") at once
+and sums J and dJ/dp over them - the reference's per-point Python loop
+(and its serial multi-experiment sum,
+cmad/calibrations/al7079/multi_experiment_hill_calibration.py:20-32) becomes
+
+    forward:  N launches of K1 (state history kept in HBM)
+    gradient: one launch of K2 (adjoint or direct recurrence per point, fused
+              with the QoI and a deterministic block reduction)
+    multi-GPU: points are sharded by rank; the only collective is ONE allreduce
+              (sum) of [J, grad] = 1 + n_active doubles over NCCL.
+
+The single-point constructors keep the reference's signatures so its tests read
+the same: ``MPAdjointObjective(Calibration(model, data, weight), F)`` with
+``F`` of shape (3, 3, N+1).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, NamedTuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .material import NewtonSettings, active_param_ids, material_from_values
+from .parameters import Parameters
+
+FULL_3D = 0
+
+
+class GradientResult(NamedTuple):
+    J: float
+    grad: np.ndarray
+
+
+class SmallElasticPlastic:
+    """Constructor-compatible stand-in for the reference model class: carries the
+    parameters and the deformation type; all evaluation happens in the kernels."""
+    model_name = "small_elastic_plastic"
+    num_dofs = 7
+    num_residuals = 2
+
+    def __init__(self, parameters: Parameters, def_type: int = FULL_3D, yield_tol: float = 1e-14,
+                 **unsupported):
+        if def_type != FULL_3D:
+            raise NotImplementedError("the B200 path covers DefType.FULL_3D (SURVEY.md 8f lists "
+                                      "PLANE_STRESS / UNIAXIAL_STRESS as later work)")
+        if unsupported:
+            raise NotImplementedError(f"unsupported model options: {sorted(unsupported)}")
+        self.parameters = parameters
+        self._def_type = def_type
+        self.yield_tol = yield_tol
+
+    def material(self) -> L.Material:
+        return material_from_values(self.parameters.values, self.model_name, self.yield_tol)
+
+
+class Calibration:
+    """``Calibration(model, data, weight)``: J = sum_t 1/2 ||weight o (cauchy - data[..., t])||^2.
+    ``data`` is (3, 3, N+1) for one point or (B, 3, 3, N+1) for a batch."""
+
+    def __init__(self, model: SmallElasticPlastic, data: np.ndarray, weight: np.ndarray) -> None:
+        weight = np.asarray(weight, dtype=np.float64)
+        assert weight.shape == (3, 3)
+        self._model, self._data, self._weight = model, np.asarray(data, dtype=np.float64), weight
+
+    def model(self):
+        return self._model
+
+    def data(self):
+        return self._data
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced range of point indices owned by ``rank``."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def strain_history_from_F(F: np.ndarray) -> np.ndarray:
+    """(B, 3, 3, N+1) deformation gradients -> (N+1, 9, B) grad_u = F - I slabs."""
+    F = np.asarray(F, dtype=np.float64)
+    gu = F - np.eye(3)[None, :, :, None]
+    return np.ascontiguousarray(gu.reshape(F.shape[0], 9, F.shape[-1]).transpose(2, 1, 0))
+
+
+def data_history(data: np.ndarray) -> np.ndarray:
+    """(B, 3, 3, N+1) -> (N+1, 9, B)."""
+    data = np.asarray(data, dtype=np.float64)
+    return np.ascontiguousarray(data.reshape(data.shape[0], 9, data.shape[-1]).transpose(2, 1, 0))
+
+
+class _DeviceHistories:
+    """Device-resident histories of this rank's shard."""
+
+    def __init__(self, strain_hist: np.ndarray, data_hist: np.ndarray, device: torch.device):
+        self.N = strain_hist.shape[0] - 1
+        self.n = strain_hist.shape[2]
+        self.strain = torch.from_numpy(np.ascontiguousarray(strain_hist)).to(device)
+        self.data = torch.from_numpy(np.ascontiguousarray(data_hist)).to(device)
+        self.xi = torch.zeros((self.N + 1, 7, self.n), dtype=torch.float64, device=device)
+        self.iters = torch.zeros((self.N + 1, self.n), dtype=torch.int32, device=device)
+        self.J_point = torch.zeros((self.n,), dtype=torch.float64, device=device)
+        self.device = device
+
+
+def gpu_local_evaluator(model: SmallElasticPlastic, strain_hist: np.ndarray, data_hist: np.ndarray,
+                        weight: np.ndarray, strategy: str, device: torch.device,
+                        newton: NewtonSettings | None = None) -> Callable[[], torch.Tensor]:
+    """Returns ``f() -> tensor[1 + n_active]`` (J, dJ/dp native) for this rank's
+    points, evaluated with K1 + K2 on ``device`` at the model's current parameters."""
+    lib = L.lib()
+    hist = _DeviceHistories(strain_hist, data_hist, device)
+    newton = newton or NewtonSettings(mode="imperative", max_iters=10, abs_tol=1e-14, rel_tol=1e-14)
+    adjoint = {"adjoint": True, "direct": False}[strategy]
+    w = np.asarray(weight, dtype=np.float64).reshape(9)
+
+    def evaluate() -> torch.Tensor:
+        pid = active_param_ids(model.parameters)
+        na = len(pid)
+        mat = model.material()
+        nw = newton.to_struct()
+        result = torch.zeros((1 + na,), dtype=torch.float64, device=device)
+        ws_bytes = lib.cmadx_mp_objective_workspace_bytes(C.c_int64(hist.n), C.c_int32(na))
+        ws = torch.empty((max(int(ws_bytes) // 8, 1),), dtype=torch.float64, device=device)
+        h = L.MpHistory()
+        h.n, h.ld, h.nsteps, h.strain_comps = hist.n, max(hist.n, 1), hist.N, hist.strain.shape[1]
+        h.strain, h.data = hist.strain.data_ptr(), hist.data.data_ptr()
+        for k in range(9):
+            h.weight[k] = float(w[k])
+        h.xi_hist, h.iters_hist = hist.xi.data_ptr(), hist.iters.data_ptr()
+        h.result, h.workspace, h.J_point = result.data_ptr(), ws.data_ptr(), hist.J_point.data_ptr()
+        stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        hist.xi[0].zero_()
+        with torch.cuda.device(device):
+            L.check(lib.cmadx_mp_forward_history(C.byref(mat), C.byref(nw), C.byref(h), stream),
+                    "cmadx_mp_forward_history")
+            fn = lib.cmadx_mp_objective_adjoint if adjoint else lib.cmadx_mp_objective_direct
+            L.check(fn(C.byref(mat), pid.ctypes.data_as(C.POINTER(C.c_int32)), na, C.byref(h), stream),
+                    "cmadx_mp_objective")
+        evaluate.histories = hist
+        return result
+
+    evaluate.histories = hist
+    return evaluate
+
+
+class BatchedMPObjective:
+    """J(p), dJ/dp summed over a batch of material points, optionally sharded
+    over the ranks of a ``torch.distributed`` process group.
+
+    ``local_evaluator() -> tensor[1 + n_active]`` returns this rank's partial
+    (J, grad) in native parameter coordinates; the class owns parameter
+    injection (``set_active_values_from_flat``), the single allreduce, and the
+    canonical-coordinate chain rule (``transform_grad``) - exactly the host
+    scaffolding of ``MPObjective.evaluate`` (mp_objective.py:53-57, 143-147).
+    """
+
+    def __init__(self, parameters: Parameters, local_evaluator: Callable[[], torch.Tensor],
+                 group=None) -> None:
+        self._parameters = parameters
+        self._local = local_evaluator
+        self._group = group
+
+    def evaluate(self, flat_active_values, are_canonical: bool = True) -> GradientResult:
+        self._parameters.set_active_values_from_flat(np.asarray(flat_active_values, dtype=np.float64),
+                                                     are_canonical)
+        return self._evaluate()
+
+    def _evaluate(self) -> GradientResult:
+        import torch.distributed as dist
+        partial = self._local()
+        if self._group is not None or (dist.is_available() and dist.is_initialized()):
+            dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=self._group)
+        host = partial.detach().cpu().numpy()
+        grad = host[1:].copy()
+        self._parameters.transform_grad(grad)
+        return GradientResult(J=float(host[0]), grad=grad)
+
+
+def _single_point_objective(qoi: Calibration, global_state: np.ndarray, strategy: str,
+                            device=None, group=None) -> BatchedMPObjective:
+    F = np.asarray(global_state, dtype=np.float64)
+    data = qoi.data()
+    if F.ndim == 3:
+        F, data = F[None], data[None]
+    device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    model = qoi.model()
+    ev = gpu_local_evaluator(model, strain_history_from_F(F), data_history(data), qoi._weight,
+                             strategy, device)
+    return BatchedMPObjective(model.parameters, ev, group)
+
+
+def MPAdjointObjective(qoi: Calibration, global_state: np.ndarray, device=None, group=None):
+    """Reference signature (mp_objective.py:92): gradient by the reverse-time adjoint."""
+    return _single_point_objective(qoi, global_state, "adjoint", device, group)
+
+
+def MPDirectObjective(qoi: Calibration, global_state: np.ndarray, device=None, group=None):
+    """Reference signature (mp_objective.py:150): gradient by forward sensitivities."""
+    return _single_point_objective(qoi, global_state, "direct", device, group)

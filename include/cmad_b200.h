@@ -133,9 +133,10 @@ typedef struct cmadx_mp_buffers {
 } cmadx_mp_buffers_t;
 
 int cmadx_version(void);
-/* sizeof(cmadx_material_t), sizeof(cmadx_newton_t), sizeof(cmadx_mp_buffers_t):
- * lets a foreign-language binding verify its struct mirrors. */
-int cmadx_struct_sizes(int64_t* out3);
+/* sizeof(cmadx_material_t), sizeof(cmadx_newton_t), sizeof(cmadx_mp_buffers_t),
+ * sizeof(cmadx_mp_history_t): lets a foreign-language binding verify its struct
+ * mirrors. */
+int cmadx_struct_sizes(int64_t* out4);
 const char* cmadx_error_string(int code);
 /* text of the last CUDA error seen by this thread ("" if none) */
 const char* cmadx_last_cuda_error(void);
@@ -170,6 +171,49 @@ int cmadx_mp_update_host(const cmadx_material_t* mat, const cmadx_newton_t* newt
                          const cmadx_mp_buffers_t* host, int device,
                          int64_t chunk_points);
 int cmadx_release_host_scratch(void);
+
+/* ---- K2: material-point calibration objective over whole load histories ------
+ * Buffers of a batch of independent material points ("experiments"), each with
+ * its own strain history and calibration data.  Histories are stored as N+1
+ * slabs (slab t = load step t, slab 0 = initial state / unused), every slab
+ * component-major [comps][ld].  Replaces the per-point Python loops of
+ * MPAdjointObjective / MPDirectObjective (cmad/objectives/mp_objective.py:
+ * 62-147, 158-215) with the Calibration QoI J = sum_t 1/2 ||w o (cauchy - data)||^2
+ * (cmad/qois/calibration.py:56-66), summed over all points of the batch.       */
+typedef struct cmadx_mp_history {
+    int64_t n;              /* points                                          */
+    int64_t ld;             /* leading dimension of every slab row (>= n)      */
+    int32_t nsteps;         /* N load steps                                    */
+    int32_t strain_comps;   /* 6 | 9 as in cmadx_mp_buffers_t                  */
+    const double* strain;   /* [N+1][strain_comps][ld]                         */
+    const double* data;     /* [N+1][9][ld] cauchy data, 3x3 row-major         */
+    double weight[9];       /* Calibration weight, 3x3 row-major, time-constant*/
+    double* xi_hist;        /* [N+1][n_xi][ld]: slab 0 = initial state (input),
+                               slabs 1..N written by cmadx_mp_forward_history  */
+    int32_t* iters_hist;    /* [N+1][ld] or NULL: Newton iterations per step   */
+    double* result;         /* [1 + n_active] device: J, dJ/dp (native params, before
+                               Parameters.transform_grad)                      */
+    double* workspace;      /* device scratch, cmadx_mp_objective_workspace_bytes() */
+    double* J_point;        /* [n] or NULL: per-point objective                */
+} cmadx_mp_history_t;
+
+/* bytes of `workspace` needed for n points and n_active parameters */
+int64_t cmadx_mp_objective_workspace_bytes(int64_t n, int32_t n_active);
+
+/* Forward pass: N successive K1 updates writing the converged state of step t
+ * into xi_hist slab t (run_primal_pass / _forward_pass_with_storage,
+ * cmad/cli/primal.py:129-176, cmad/objectives/mp_objective.py:62-89).          */
+int cmadx_mp_forward_history(const cmadx_material_t* mat, const cmadx_newton_t* newton,
+                             const cmadx_mp_history_t* hist, void* stream);
+
+/* Adjoint gradient (reverse-time recurrence, mp_objective.py:112-142) and direct
+ * (forward sensitivity, :174-210) gradient of the summed objective; both need
+ * xi_hist filled by the forward pass and write `result` (deterministic
+ * reduction, bit-reproducible run to run).                                    */
+int cmadx_mp_objective_adjoint(const cmadx_material_t* mat, const int32_t* active_pid,
+                               int32_t n_active, const cmadx_mp_history_t* hist, void* stream);
+int cmadx_mp_objective_direct(const cmadx_material_t* mat, const int32_t* active_pid,
+                              int32_t n_active, const cmadx_mp_history_t* hist, void* stream);
 
 /* debugging aid: how many points the last J2 radial-return launch on `stream`
  * handed back to the generic kernel (synchronises the stream); -1 if none ran */

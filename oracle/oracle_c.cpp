@@ -519,7 +519,7 @@ int oracle_mp_update(const double* mat, const int* cfg, const double* sol,
                      double* xi, double* sigma, double* dsig_deps, double* dxi_deps,
                      double* dC_dp, double* dC_dxi, double* dC_dxi_prev,
                      int* iters, int* flags, double* cnorm, int* ls_evals,
-                     int nthreads) {
+                     int nthreads, double* dsig_dxi, double* dsig_dp) {
     const int model = cfg[0];
     const int n = (model == MODEL_SEP) ? 7 : 6;
     const int ncomp = cfg[7];
@@ -601,6 +601,28 @@ int oracle_mp_update(const double* mat, const int* cfg, const double* sol,
                 for (int a = 0; a < 6; ++a)
                     for (int b = 0; b < 6; ++b) dsig_deps[(a * 6 + b) * ld + i] = sg[up[a]].d[b];
             }
+        }
+        if (dsig_dxi) {        // dcauchy/dxi (model.py:150), (a*n + c)
+            typedef Dual<double, 7> D7;
+            Mat<D7> m = make_mat<D7>(mat, cfg);
+            D7 xx[7], g[9], sg[9];
+            for (int k = 0; k < 7; ++k) xx[k] = D7(po.x[k]);
+            for (int k = 0; k < n; ++k) xx[k].d[k] = 1.;
+            for (int k = 0; k < 9; ++k) g[k] = D7(gu[k]);
+            cauchy(model, m, xx, g, sg);
+            for (int a = 0; a < 6; ++a)
+                for (int c = 0; c < n; ++c) dsig_dxi[(a * n + c) * ld + i] = sg[up[a]].d[c];
+        }
+        if (dsig_dp && n_active > 0) {   // dcauchy/dparams (model.py:152), (a*n_active + c)
+            typedef Dual<double, 16> DP;
+            Mat<DP> m = make_mat<DP>(mat, cfg);
+            for (int c = 0; c < n_active; ++c) mat_slot(m, active_pid[c]).d[c] = 1.;
+            DP xx[7], g[9], sg[9];
+            for (int k = 0; k < 7; ++k) xx[k] = DP(po.x[k]);
+            for (int k = 0; k < 9; ++k) g[k] = DP(gu[k]);
+            cauchy(model, m, xx, g, sg);
+            for (int a = 0; a < 6; ++a)
+                for (int c = 0; c < n_active; ++c) dsig_dp[(a * n_active + c) * ld + i] = sg[up[a]].d[c];
         }
         if (dC_dp && n_active > 0) {
             typedef Dual<double, 16> DP;

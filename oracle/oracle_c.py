@@ -156,7 +156,8 @@ def mp_update(prob: OracleProblem, xi_prev: np.ndarray, strain: np.ndarray,
     assert xi_prev.shape == (n_xi, N) and strain.shape == (int(prob.cfg[7]), N)
     na = len(prob.active_pid)
     shapes = {"xi": (n_xi, N), "sigma": (6, N), "dsig_deps": (36, N), "dxi_deps": (n_xi * 6, N),
-              "dC_dp": (n_xi * na, N), "dC_dxi": (n_xi * n_xi, N), "dC_dxi_prev": (n_xi * n_xi, N)}
+              "dC_dp": (n_xi * na, N), "dC_dxi": (n_xi * n_xi, N), "dC_dxi_prev": (n_xi * n_xi, N),
+              "dsig_dxi": (6 * n_xi, N), "dsig_dp": (6 * na, N)}
     out = {k: (np.zeros(shapes[k]) if k in want else None) for k in shapes}
     ints = {k: (np.zeros(N, dtype=np.int32) if k in want else None) for k in ("iters", "flags", "ls_evals")}
     cnorm = np.zeros(N) if "cnorm" in want else None
@@ -168,7 +169,7 @@ def mp_update(prob: OracleProblem, xi_prev: np.ndarray, strain: np.ndarray,
         _p(out["xi"], d), _p(out["sigma"], d), _p(out["dsig_deps"], d), _p(out["dxi_deps"], d),
         _p(out["dC_dp"], d), _p(out["dC_dxi"], d), _p(out["dC_dxi_prev"], d),
         _p(ints["iters"], i32), _p(ints["flags"], i32), _p(cnorm, d), _p(ints["ls_evals"], i32),
-        ctypes.c_int(nthreads))
+        ctypes.c_int(nthreads), _p(out["dsig_dxi"], d), _p(out["dsig_dp"], d))
     if rc != 0:
         raise RuntimeError(f"oracle_mp_update failed with code {rc}")
     res = {k: v for k, v in out.items() if v is not None}

@@ -1,0 +1,66 @@
+"""GPU parity of K2 (adjoint / direct calibration gradients over whole load
+histories) against the CPU oracle: J to 1e-12, gradients to 1e-9 relative (the
+reference's own cross-strategy tolerances, tests/objectives/
+test_jvp_vs_original.py:95-97), adjoint == direct, run-to-run bit reproducibility."""
+import numpy as np
+import pytest
+import torch
+
+from cmad_b200 import Parameters
+from cmad_b200.objectives import (BatchedMPObjective, Calibration, MPAdjointObjective,
+                                  MPDirectObjective, SmallElasticPlastic, gpu_local_evaluator)
+from oracle import analytic, mp_objective_np as mo
+from tests.helpers import param_tree
+from tests.test_objectives_host import _problem
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("kind", ["J2", "hill", "hosford"])
+def test_batched_objective_matches_oracle(cuda_device, kind):
+    hill = (0.45, 0.6, 0.55, 1.4, 1.6, 1.5) if kind == "hill" else None
+    active = ("E", "nu", "D", "S", "Y") + (tuple("FGHLMN") if kind == "hill" else ())
+    values, act, tr = param_tree(kind, ("voce",), hill=hill, active=active)
+    P = Parameters(values, act, tr)
+    sh, data, w = _problem(n=3000, N=12, seed=1, kind=kind)
+    Jr, gr, Jp, gp, xi_ref, it_ref = mo.objective(values, P.active_idx, sh, data, w, "adjoint")
+    model = SmallElasticPlastic(P)
+    res = {}
+    for strategy in ("adjoint", "direct"):
+        ev = gpu_local_evaluator(model, sh, data, w, strategy, cuda_device)
+        out = ev().cpu().numpy()
+        res[strategy] = out
+        assert abs(out[0] - Jr) < 1e-12 * abs(Jr)
+        assert np.abs(out[1:] - gr).max() < 1e-9 * np.abs(gr).max()
+        h = ev.histories
+        assert np.array_equal(h.iters.cpu().numpy(), it_ref)              # Newton counts, every step
+        assert np.abs(h.xi.cpu().numpy() - xi_ref).max() < 1e-10 * np.abs(xi_ref).max()
+        assert np.abs(h.J_point.cpu().numpy() - Jp).max() < 1e-12 * np.abs(Jp).max()
+        again = ev().cpu().numpy()
+        assert np.array_equal(out, again)                                  # deterministic reduction
+    assert np.abs(res["adjoint"][1:] - res["direct"][1:]).max() < 1e-10 * np.abs(gr).max()
+
+
+def test_reference_style_single_point_objectives(cuda_device):
+    """The reference's constructor signatures on one material point with
+    canonical (log / bounds) parameter transforms: adjoint == direct == oracle."""
+    values, act, tr = analytic.j2_voce_param_tree("J2")
+    sh, data, w = _problem(n=1, N=20, seed=2)
+    F = np.repeat(np.eye(3)[:, :, None], 21, axis=2)
+    for t in range(21):
+        e = sh[t, :, 0]
+        F[:, :, t] += np.array([[e[0], e[1], e[2]], [e[1], e[3], e[4]], [e[2], e[4], e[5]]])
+    dat = data[:, :, 0].T.reshape(3, 3, 21)
+    x = np.array([0.1, 0.1, 0.1])
+    results = []
+    for ctor in (MPAdjointObjective, MPDirectObjective):
+        P = Parameters(*analytic.j2_voce_param_tree("J2"))
+        obj = ctor(Calibration(SmallElasticPlastic(P), dat, w), F, device=cuda_device)
+        results.append(obj.evaluate(x))
+    Pn = Parameters(*analytic.j2_voce_param_tree("J2")); Pn.set_active_values_from_flat(x)
+    Jr, gr, *_ = mo.objective(Pn.values, Pn.active_idx, sh, data, w, "adjoint")
+    Pn.transform_grad(gr)
+    for r in results:
+        assert abs(r.J - Jr) < 1e-12 * abs(Jr)
+        assert np.allclose(r.grad, gr, rtol=1e-9)
+    assert np.allclose(results[0].grad, results[1].grad, rtol=1e-10)
