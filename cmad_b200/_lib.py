@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcmad_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
 SOURCES = ["api.cu", "mp_update.cu", "mp_update_j2.cu", "elastic_update.cu", "mp_sens.cu",
-           "fe_block.cu"]
+           "fe_block.cu", "fe_scatter.cu"]
 
 # ---- enums (mirror include/cmad_b200.h) ---------------------------------
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(5)
@@ -64,27 +64,54 @@ class MpHistory(C.Structure):
                 ("result", C.c_void_p), ("workspace", C.c_void_p), ("J_point", C.c_void_p)]
 
 
+class FeBlock(C.Structure):
+    _fields_ = [("n_elems", C.c_int64), ("n_dofs", C.c_int64), ("n_basis", C.c_int32),
+                ("n_ip", C.c_int32), ("elem_eq", C.c_void_p), ("U", C.c_void_p),
+                ("xi_prev", C.c_void_p), ("grad_N", C.c_void_p), ("det", C.c_void_p),
+                ("quad_w", C.c_void_p), ("xi", C.c_void_p), ("R_elem", C.c_void_p),
+                ("K_elem", C.c_void_p), ("R_global", C.c_void_p), ("sigma", C.c_void_p),
+                ("iters", C.c_void_p), ("flags", C.c_void_p)]
+
+
 class CmadxError(RuntimeError):
     pass
 
 
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-I" + INCLUDE]
+OBJ_DIR = os.path.join(_HERE, "lib", "obj")
+
+
 def nvcc_command(out: str = LIB_PATH) -> list[str]:
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
-            "-std=c++17", "-Xcompiler", "-fPIC", "-I" + INCLUDE, "-shared", "-o", out] + srcs
+    """Single-shot equivalent of what :func:`build` does (compile all + link)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    return ["nvcc"] + NVCC_FLAGS + ["-shared", "-o", out] + srcs
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into ``cmad_b200/lib/libcmad_b200.so``."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "cmad_b200.h")]
-    newest = max(os.path.getmtime(s) for s in srcs)
-    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
-        return LIB_PATH
-    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
-    cmd = nvcc_command()
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.check_call(cmd)
+    """Compile every CUDA source for sm_100a (``nvcc -gencode
+    arch=compute_100a,code=sm_100a -lineinfo``) into
+    ``cmad_b200/lib/libcmad_b200.so``; objects are compiled in parallel and only
+    when their source (or any header) is newer."""
+    from concurrent.futures import ThreadPoolExecutor
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(INCLUDE, "cmad_b200.h"))
+    hdr_time = max(os.path.getmtime(h) for h in headers)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    jobs, objs = [], []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(OBJ_DIR, s.replace(".cu", ".o"))
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_time):
+            cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas=-v"] if verbose else []) + ["-c", src, "-o", obj]
+            jobs.append(cmd)
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            list(ex.map(subprocess.check_call, jobs))
+    if jobs or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(o) for o in objs):
+        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared",
+                               "-o", LIB_PATH] + objs)
     return LIB_PATH
 
 
@@ -121,6 +148,12 @@ def lib() -> C.CDLL:
     obj_args = [C.POINTER(Material), C.POINTER(C.c_int32), C.c_int32, C.POINTER(MpHistory), C.c_void_p]
     L.cmadx_mp_objective_adjoint.argtypes = obj_args
     L.cmadx_mp_objective_direct.argtypes = obj_args
+    L.cmadx_fe_block_assemble.argtypes = [C.POINTER(Material), C.POINTER(Newton),
+                                          C.POINTER(FeBlock), C.c_void_p]
+    L.cmadx_segment_plan_create.argtypes = [C.POINTER(C.c_int64), C.c_int64, C.c_int64,
+                                            C.POINTER(C.c_void_p)]
+    L.cmadx_segment_plan_destroy.argtypes = [C.c_void_p]
+    L.cmadx_segment_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     _lib = L
     return L
 

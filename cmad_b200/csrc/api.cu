@@ -8,6 +8,7 @@
 #include <mutex>
 #include <vector>
 
+#include "fe_block.cuh"
 #include "mp_update.cuh"
 
 namespace cmadx {
@@ -261,10 +262,10 @@ extern "C" {
 
 int cmadx_version(void) { return CMADX_VERSION; }
 
-int cmadx_struct_sizes(int64_t* out4) {
-    if (!out4) return CMADX_EINVAL;
-    out4[0] = sizeof(cmadx_material_t); out4[1] = sizeof(cmadx_newton_t); out4[2] = sizeof(cmadx_mp_buffers_t);
-    out4[3] = sizeof(cmadx_mp_history_t);
+int cmadx_struct_sizes(int64_t* out5) {
+    if (!out5) return CMADX_EINVAL;
+    out5[0] = sizeof(cmadx_material_t); out5[1] = sizeof(cmadx_newton_t); out5[2] = sizeof(cmadx_mp_buffers_t);
+    out5[3] = sizeof(cmadx_mp_history_t); out5[4] = sizeof(cmadx_fe_block_t);
     return CMADX_OK;
 }
 
@@ -469,6 +470,53 @@ int cmadx_mp_objective_adjoint(const cmadx_material_t* mat, const int32_t* activ
 int cmadx_mp_objective_direct(const cmadx_material_t* mat, const int32_t* active_pid,
                               int32_t n_active, const cmadx_mp_history_t* hist, void* stream) {
     return objective(mat, active_pid, n_active, hist, stream, false);
+}
+
+int cmadx_fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* newton,
+                            const cmadx_fe_block_t* blk, void* stream) {
+    if (!blk) return CMADX_EINVAL;
+    FeArgs A;
+    if (int rc = make_dev_mat(mat, &A.m)) return rc;
+    if (int rc = make_dev_newton(newton, &A.nw)) return rc;
+    if (A.m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC) return CMADX_EUNSUPPORTED;
+    const cmadx_fe_block_t& b = *blk;
+    if (b.n_elems < 0 || b.n_dofs < 0) return CMADX_EINVAL;
+    if (!((b.n_basis == 4 && b.n_ip == 1) || (b.n_basis == 8 && b.n_ip == 8))) {
+        if ((b.n_basis == 4 || b.n_basis == 8) && b.n_ip >= 1 && b.n_ip <= 27) return CMADX_EUNSUPPORTED;
+        return CMADX_EINVAL;
+    }
+    if (b.n_elems > 0) {
+        if (!b.elem_eq || !b.U || !b.xi_prev || !b.grad_N || !b.det || !b.quad_w || !b.xi) return CMADX_EINVAL;
+        auto misaligned = [](const void* p, uintptr_t a) { return p && (reinterpret_cast<uintptr_t>(p) % a) != 0; };
+        if (misaligned(b.grad_N, 32) || misaligned(b.K_elem, 32) || misaligned(b.elem_eq, 16) ||
+            (b.n_basis == 4 && misaligned(b.R_elem, 32)))
+            return CMADX_EINVAL;
+        if (b.n_elems * b.n_ip >= (int64_t)0x7fffffff) return CMADX_EUNSUPPORTED;
+    }
+    A.b = b;
+    A.bail_count = nullptr; A.bail_list = nullptr; A.bail_cap = 0;
+    if (b.n_elems == 0) return CMADX_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e;
+    const bool radial = A.m.yield == CMADX_YIELD_J2 && !A.m.rot && !(A.nw.flags & CMADX_NEWTON_F_GENERIC);
+    if (radial) {
+        BailScratch bs;
+        if (int rc = get_bail_scratch(s, &bs)) return rc;
+        A.bail_count = bs.count;
+        A.bail_list = reinterpret_cast<int*>(bs.count + 64);
+        A.bail_cap = BAIL_CAP;
+        e = cudaMemsetAsync(bs.count, 0, sizeof(unsigned), s);
+        if (e != cudaSuccess) return cuda_fail(e);
+        e = launch_fe_block(A, true, s);
+        if (e != cudaSuccess) return cuda_fail(e);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = launch_fe_block_list(A, s);
+    } else {
+        e = launch_fe_block(A, false, s);
+    }
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return CMADX_OK;
 }
 
 int cmadx_release_host_scratch(void) {

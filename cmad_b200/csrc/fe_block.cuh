@@ -1,0 +1,20 @@
+// Launch-argument struct of the FE element-block kernels (fe_block.cu).
+#pragma once
+#include "point_solver.cuh"
+
+namespace cmadx {
+
+struct FeArgs {
+    DevMat m;
+    DevNewton nw;
+    cmadx_fe_block_t b;
+    // elements the J2 radial kernel hands back to the generic kernel (list mode)
+    unsigned* bail_count;
+    int* bail_list;
+    unsigned bail_cap;
+};
+
+cudaError_t launch_fe_block(const FeArgs& A, bool j2_radial, cudaStream_t stream);
+cudaError_t launch_fe_block_list(const FeArgs& A, cudaStream_t stream);
+
+}  // namespace cmadx

@@ -25,40 +25,11 @@
 //
 // One thread per point, ~13 coalesced loads and ~85 streaming stores per thread,
 // a handful of FP64 operations in between: HBM-bound by construction.
+#include "j2_radial.cuh"
 #include "mp_outputs.cuh"
 
 namespace cmadx {
 namespace {
-
-constexpr double R32 = 1.2247448713915890491;   // sqrt(3/2)
-
-struct Scalar {
-    double f, eD;
-    bool ok;      // plastic branch and radial reduction valid at this alpha
-};
-
-// yield function at alpha on the radial path: s = (sn0 - 2mu*sqrt(3/2)*dgamma) s^
-CMADX_DEV Scalar eval_alpha(const DevMat& m, double alpha, double alpha0, double sn0) {
-    Scalar r;
-    const double dg = alpha - alpha0;
-    const double sn = fma(-m.two_mu * R32, dg, sn0);
-    const double phi = R32 * sn;
-    double Hd = 0.0;
-    r.eD = 0.0;
-    if (m.hmask & CMADX_HARD_VOCE) { r.eD = exp(-m.D * alpha); Hd = m.S * (1.0 - r.eD); }
-    if (m.hmask & CMADX_HARD_LINEAR) Hd = fma(m.K, alpha, Hd);
-    r.f = (phi - (m.Y + Hd)) * m.inv_two_mu;
-    const bool plastic = (r.f > m.yield_tol) || (fabs(r.f) < m.yield_tol);
-    r.ok = plastic && (sn > 0.0);
-    return r;
-}
-
-CMADX_DEV double hardening_slope(const DevMat& m, double eD) {
-    double Hp = 0.0;
-    if (m.hmask & CMADX_HARD_VOCE) Hp = m.S * m.D * eD;
-    if (m.hmask & CMADX_HARD_LINEAR) Hp += m.K;
-    return Hp * m.inv_two_mu;
-}
 
 __global__ void __launch_bounds__(MP_BLOCK)
 mp_update_j2_kernel(const __grid_constant__ MpArgs A) {
@@ -71,114 +42,22 @@ mp_update_j2_kernel(const __grid_constant__ MpArgs A) {
     double xp[7], em[6];
     load_point(A.b, i, live, xp, em);
 
-    // state at x0 = xi_prev, evaluated by the generic residual (identical arithmetic)
-    SepPoint<CMADX_YIELD_J2> pt;
-    double C0[7];
-    pt.residual(m, xp, xp, em, C0);
-    const int flag_entry = pt.plastic ? 1 : 0;
-    const double alpha0 = xp[6];
-    const double sn0 = pt.yf.sn;
-    double n0v[6];
-#pragma unroll
-    for (int a = 0; a < 6; ++a) n0v[a] = pt.n[a];
-
-    double alpha = alpha0;
-    double f = C0[6];            // plastic: yield function; elastic: dgamma = 0
-    double eD = pt.eD;
-    bool bail = false;
-    int ii = 0;
-    double nc = sqrt(f * f), n0 = nc;
-    bool done = !live || nw.max_iters <= 0;
-    bool fresh = true;           // (f, eD) belong to the current alpha
-    if (live && !pt.plastic) {
-        // elastic entry: C_e(x0) = 0, converged on the absolute test with ii = 0;
-        // anything else (abs_tol <= 0) is left to the generic kernel
-        if (!done && !(nc < nw.abs_tol)) bail = true;
-        done = true;
-    }
-    if (live && pt.plastic && !(sn0 > 0.0)) { bail = true; done = true; }
-
-    const unsigned full = 0xffffffffu;
-    if (nw.mode == CMADX_NEWTON_TRACED) {
-        while (__any_sync(full, !done)) {
-            if (!done) {
-                nc = sqrt(f * f);
-                const double rel = nc / n0;
-                if (rel < nw.rel_tol || nc < nw.abs_tol) {
-                    done = true;
-                } else {
-                    const double h = hardening_slope(m, eD);
-                    const double dxa = f / -(1.5 + h);             // alpha component of solve(J, C)
-                    const double CC = f * f;
-                    const double phi0 = 0.5 * CC, dphi0 = -CC, armijo = nw.c1 * dphi0;
-                    int ne = 0;
-                    double al = 1.0, best_al = 1.0, best_phi = CUDART_INF;
-                    Scalar best; best.f = f; best.eD = eD; best.ok = true;
-                    Scalar tr = best;
-                    bool acc = false;
-                    while (ne < nw.ls_max && !acc) {
-                        tr = eval_alpha(m, fma(-al, dxa, alpha), alpha0, sn0);
-                        if (!tr.ok) bail = true;
-                        const double ph = 0.5 * (tr.f * tr.f);
-                        const bool fin = isfinite(ph);
-                        if (fin && ph < best_phi) { best_al = al; best_phi = ph; best = tr; }
-                        acc = fin && (ph <= fma(al, armijo, phi0));
-                        const double den = 2.0 * (ph - phi0 - dphi0 * al);
-                        const double am = (den == 0.0) ? 0.5 * al : -dphi0 * al * al / den;
-                        double ac = fmin(fmax(am, nw.bmin * al), nw.bmax * al);
-                        if (am != am) ac = am;
-                        if (!acc) al = fin ? ac : 0.5 * al;
-                        ++ne;
-                    }
-                    const double ar = acc ? al : best_al;
-                    alpha = fma(-ar, dxa, alpha);
-                    f = acc ? tr.f : best.f;
-                    eD = acc ? tr.eD : best.eD;
-                    ++ii;
-                    if (ii >= nw.max_iters || bail) done = true;
-                }
-            }
-        }
-        nc = sqrt(f * f);
-    } else {
-        while (__any_sync(full, !done)) {
-            if (!done) {
-                if (ii > 0) {
-                    const Scalar cur = eval_alpha(m, alpha, alpha0, sn0);
-                    f = cur.f; eD = cur.eD; fresh = true;
-                    if (!cur.ok) bail = true;
-                }
-                nc = sqrt(f * f);
-                double rel = 1.0;
-                if (ii == 0) n0 = nc; else rel = nc / n0;
-                if (rel < nw.rel_tol || nc < nw.abs_tol || bail) {
-                    done = true;
-                } else {
-                    const double h = hardening_slope(m, eD);
-                    alpha += (-f) / -(1.5 + h);                     // solve(J, -C), x += delta
-                    fresh = false;
-                    ++ii;
-                    if (ii >= nw.max_iters) done = true;
-                }
-            }
-        }
-        if (live && !fresh) {
-            const Scalar cur = eval_alpha(m, alpha, alpha0, sn0);
-            f = cur.f; eD = cur.eD;
-            if (!cur.ok) bail = true;
-        }
-    }
+    J2Radial rs;
+    j2_radial_solve(m, nw, xp, em, live, rs);   // see j2_radial.cuh
     if (!live) return;
-    if (!isfinite(f) || !isfinite(alpha)) bail = true;
-    if (bail) {
+    if (rs.bail) {
         // hand the point to the generic kernel; it rewrites every output
         const unsigned slot = atomicAdd(A.bail_count, 1u);
         if (slot < A.bail_cap) A.bail_list[slot] = (int)i;
         return;
     }
+    const double alpha = rs.alpha, alpha0 = rs.alpha0, f = rs.f, eD = rs.eD;
+    const int ii = rs.ii, flag_entry = rs.flag_entry;
+    double nc = rs.nc;
+    const double (&n0v)[6] = rs.n0;
 
     // ---------------------------------------------------------------- outputs
-    const bool pl = pt.plastic;          // branch at x*: unchanged along a valid radial solve
+    const bool pl = rs.plastic;          // branch at x*: unchanged along a valid radial solve
     const double dg = alpha - alpha0;
     double x[7];
 #pragma unroll
@@ -215,14 +94,14 @@ mp_update_j2_kernel(const __grid_constant__ MpArgs A) {
     if (A.b.dC_dxi_prev) write_dC_dxi_prev(A.b.dC_dxi_prev, ld, i, pl, n0v);
 
     // yield-surface state at x*: same direction, shrunken radius
-    const double snf = fma(-m.two_mu * R32, dg, sn0);
+    const double snf = fma(-m.two_mu * R32, dg, rs.sn0);
     YieldFn<CMADX_YIELD_J2> yf;
     yf.sn = snf;
     yf.c = R32 / snf;
 #pragma unroll
-    for (int a = 0; a < 6; ++a) yf.sh[a] = pt.yf.sh[a];
+    for (int a = 0; a < 6; ++a) yf.sh[a] = rs.sh[a];
     const double beta = dg * m.two_mu * yf.c;
-    const double h = hardening_slope(m, eD);
+    const double h = j2_hardening_slope(m, eD);
 
     if (A.b.dC_dp && A.n_active > 0) {
         // (dn/dsigma : ee)_a = c (dev(ee)_a - s^_a (s^:ee)),  n:ee

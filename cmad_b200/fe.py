@@ -1,0 +1,186 @@
+"""FE element-block assembly: Python front end of K3/K4 (``cmadx_fe_block_assemble``)
+and K5 (``cmadx_segment_sum``).
+
+Mirrors the reference's block-level entry points so a caller of
+``cmad.fem.assembly`` can switch over:
+
+  ``assemble_element_block``           cmad/fem/assembly.py:616-732
+  ``assemble_element_block_residual``  cmad/fem/assembly.py:735-813
+  ``assemble_global`` / ``assemble_global_residual``  cmad/fem/assembly.py:816-968
+
+Arrays are torch CUDA tensors in the reference's layouts; torch only owns the
+memory and streams.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Mapping
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .fe_mesh import FEBlockArrays
+from .material import NewtonSettings
+
+# for_model's COUPLED defaults (cmad/global_residuals/global_residual.py:292-297)
+FE_LOCAL_NEWTON_DEFAULTS = dict(max_iters=20, abs_tol=1e-12, rel_tol=1e-12)
+
+
+def fe_newton_settings(**kw) -> NewtonSettings:
+    """Local-Newton settings of the FE path: traced Newton with line search,
+    defaults 20 / 1e-12 / 1e-12 (for_model) unless a deck overrides them
+    (cmad/cli/common.py:393-398)."""
+    d = dict(FE_LOCAL_NEWTON_DEFAULTS)
+    d.update(kw)
+    return NewtonSettings(mode="traced", **d)
+
+
+class SegmentPlan:
+    """Deterministic segment-sum plan (K5): ``out[s] = sum vals[i] for seg[i] == s``
+    in increasing ``i``.  Built once per mesh from the reference's scatter maps
+    (``r_scatter_eq.ravel()`` or ``coo_dedup_scatter``)."""
+
+    def __init__(self, seg_of_item, n_segments: int, device=None):
+        seg = np.ascontiguousarray(
+            seg_of_item.cpu().numpy() if isinstance(seg_of_item, torch.Tensor) else seg_of_item,
+            dtype=np.int64).reshape(-1)
+        self.n_items, self.n_segments = int(seg.size), int(n_segments)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = L.lib().cmadx_segment_plan_create(seg.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                   self.n_items, self.n_segments, C.byref(self._h))
+        L.check(rc, "cmadx_segment_plan_create")
+
+    def sum(self, vals: torch.Tensor, out: torch.Tensor | None = None, accumulate: bool = False,
+            stream: torch.cuda.Stream | None = None) -> torch.Tensor:
+        if vals.dtype != torch.float64 or not vals.is_contiguous() or vals.numel() != self.n_items:
+            raise ValueError(f"vals: expected contiguous float64 with {self.n_items} entries")
+        if vals.device != self.device:
+            raise ValueError("vals must live on the plan's device")
+        if out is None:
+            if accumulate:
+                raise ValueError("accumulate=True needs an existing `out`")
+            out = torch.empty(self.n_segments, dtype=torch.float64, device=self.device)
+        elif out.dtype != torch.float64 or not out.is_contiguous() or out.numel() != self.n_segments:
+            raise ValueError(f"out: expected contiguous float64 with {self.n_segments} entries")
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            rc = L.lib().cmadx_segment_sum(self._h, C.c_void_p(vals.data_ptr()), C.c_void_p(out.data_ptr()),
+                                           int(bool(accumulate)), C.c_void_p(s.cuda_stream))
+        L.check(rc, "cmadx_segment_sum")
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            L.lib().cmadx_segment_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _fe_struct(arrays: FEBlockArrays, U, xi_prev, out: dict) -> L.FeBlock:
+    b = L.FeBlock()
+    b.n_elems, b.n_dofs = arrays.n_elems, arrays.n_dofs
+    b.n_basis, b.n_ip = arrays.n_basis, arrays.n_ip
+    b.elem_eq, b.U, b.xi_prev = arrays.elem_eq.data_ptr(), U.data_ptr(), xi_prev.data_ptr()
+    b.grad_N, b.det, b.quad_w = arrays.grad_N.data_ptr(), arrays.det.data_ptr(), arrays.quad_w.data_ptr()
+    for name in ("xi", "R_elem", "K_elem", "R_global", "sigma", "iters", "flags"):
+        setattr(b, name, out[name].data_ptr() if out.get(name) is not None else None)
+    return b
+
+
+def fe_block_launch(material: L.Material, newton: NewtonSettings, arrays: FEBlockArrays,
+                    U_global: torch.Tensor, xi_prev: torch.Tensor, outputs=("xi", "R_elem", "K_elem"),
+                    out: dict | None = None, stream: torch.cuda.Stream | None = None) -> dict:
+    """One K3/K4 launch over an element block (asynchronous on ``stream``).
+    ``outputs`` ⊆ {xi, R_elem, K_elem, R_global, sigma, iters, flags}; ``R_global``
+    (atomic scatter-add) is zero-initialised here unless passed in through ``out``."""
+    n_e, n_b, n_ip = arrays.n_elems, arrays.n_basis, arrays.n_ip
+    dev = arrays.grad_N.device
+    if dev.type != "cuda":
+        raise ValueError("FE block arrays must live on a CUDA device (there is no CPU fallback)")
+    n_xi = 7
+    if U_global.dtype != torch.float64 or U_global.numel() != arrays.n_dofs or not U_global.is_contiguous():
+        raise ValueError(f"U_global: expected contiguous float64 ({arrays.n_dofs},)")
+    if xi_prev.dtype != torch.float64 or tuple(xi_prev.shape) != (n_e, n_ip, n_xi) or not xi_prev.is_contiguous():
+        raise ValueError(f"xi_prev: expected contiguous float64 ({n_e}, {n_ip}, {n_xi}), got {tuple(xi_prev.shape)}")
+    for t in (arrays.elem_eq, arrays.grad_N, arrays.det, arrays.quad_w):
+        if not t.is_contiguous():
+            raise ValueError("FE block arrays must be contiguous")
+    shapes = {"xi": ((n_e, n_ip, n_xi), torch.float64), "R_elem": ((n_e, n_b * 3), torch.float64),
+              "K_elem": ((n_e, n_b * 3, n_b * 3), torch.float64), "R_global": ((arrays.n_dofs,), torch.float64),
+              "sigma": ((n_e, n_ip, 6), torch.float64), "iters": ((n_e, n_ip), torch.int32),
+              "flags": ((n_e, n_ip), torch.int32)}
+    out = dict(out) if out is not None else {}
+    for name in set(outputs) | {"xi"}:
+        if name not in shapes:
+            raise ValueError(f"unknown output {name!r}")
+        if out.get(name) is None:
+            shape, dt = shapes[name]
+            alloc = torch.zeros if name == "R_global" else torch.empty
+            out[name] = alloc(shape, dtype=dt, device=dev)
+    b = _fe_struct(arrays, U_global, xi_prev, out)
+    nw = newton.to_struct()
+    s = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        rc = L.lib().cmadx_fe_block_assemble(C.byref(material), C.byref(nw), C.byref(b),
+                                             C.c_void_p(s.cuda_stream))
+    L.check(rc, "cmadx_fe_block_assemble")
+    return out
+
+
+def assemble_element_block(material: L.Material, newton: NewtonSettings, arrays: FEBlockArrays,
+                           U_global: torch.Tensor, xi_prev_per_block: torch.Tensor,
+                           r_plan: SegmentPlan | None = None, out: dict | None = None,
+                           stream: torch.cuda.Stream | None = None):
+    """``(R_block, vals, xi_solved_per_block)`` of a COUPLED block, as the
+    reference's ``assemble_element_block`` returns them: ``R_block (n_dofs,)``,
+    ``vals`` = flattened ``(elem, row dof, col dof)`` COO data,
+    ``xi_solved (n_e, n_ip, n_xi)``.  With ``r_plan`` (a :class:`SegmentPlan` over
+    ``elem_eq.ravel()``) R is summed deterministically; otherwise by atomics."""
+    outs = ("xi", "R_elem", "K_elem") if r_plan is not None else ("xi", "K_elem", "R_global")
+    o = fe_block_launch(material, newton, arrays, U_global, xi_prev_per_block, outs, out, stream)
+    R = r_plan.sum(o["R_elem"].reshape(-1), stream=stream) if r_plan is not None else o["R_global"]
+    return R, o["K_elem"].reshape(-1), o["xi"]
+
+
+def assemble_element_block_residual(material, newton, arrays, U_global, xi_prev_per_block,
+                                    r_plan: SegmentPlan | None = None, out: dict | None = None,
+                                    stream=None) -> torch.Tensor:
+    """Residual-only block assembly (K4): line-search probes and reaction QoIs
+    (cmad/fem/assembly.py:735-813, cmad/qois/fe_load_match.py:179-196)."""
+    outs = ("xi", "R_elem") if r_plan is not None else ("xi", "R_global")
+    o = fe_block_launch(material, newton, arrays, U_global, xi_prev_per_block, outs, out, stream)
+    return r_plan.sum(o["R_elem"].reshape(-1), stream=stream) if r_plan is not None else o["R_global"]
+
+
+def assemble_global(blocks: Mapping[str, tuple], U_global: torch.Tensor,
+                    xi_prev_by_block: Mapping[str, torch.Tensor], coo_plan: SegmentPlan | None = None,
+                    r_plans: Mapping[str, SegmentPlan] | None = None, group=None):
+    """Walk all element blocks (``blocks[name] = (material, newton, arrays)``) and
+    return ``(K_data, R, xi_solved_by_block)``: ``K_data`` is the deduplicated COO
+    data (``coo_plan`` over the concatenated ``coo_dedup_scatter``) or, without a
+    plan, the with-duplicates stream; ``R`` the global residual.  With a
+    ``torch.distributed`` ``group`` the element blocks passed in are this rank's
+    partition and ``R`` is all-reduced (the one exchange step of the path)."""
+    R = torch.zeros(U_global.numel(), dtype=torch.float64, device=U_global.device)
+    vals_all, xi_out = [], {}
+    for name, (material, newton, arrays) in blocks.items():
+        plan = r_plans.get(name) if r_plans else None
+        Rb, vals, xi = assemble_element_block(material, newton, arrays, U_global,
+                                              xi_prev_by_block[name], r_plan=plan)
+        R += Rb
+        vals_all.append(vals)
+        xi_out[name] = xi
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(R, op=dist.ReduceOp.SUM, group=group)
+    vals = vals_all[0] if len(vals_all) == 1 else torch.cat(vals_all)
+    K = coo_plan.sum(vals) if coo_plan is not None else vals
+    return K, R, xi_out

@@ -1,0 +1,175 @@
+"""Synthetic FE workloads for the element-block kernels: structured hex / tet
+meshes and the mesh-derived arrays the kernels consume, in the REFERENCE's
+layouts.  Host-side set-up that runs once per mesh (torch used as an array
+library, on whatever device is asked for); nothing here is on the hot path.
+
+Layouts produced (reference file:line):
+  * connectivity / node numbering of ``StructuredHexMesh`` (cmad/fem/mesh.py:424-514):
+    node id = C-order index of the (nx+1, ny+1, nz+1) grid, element
+    ``e = i*ny*nz + j*nz + k``, hex_linear node order (cmad/fem/interpolants.py:15-24);
+  * geometry cache (cmad/fem/precompute.py:170-271): ``iso_jac_det (n_e, n_ip)``,
+    ``grad_N_phys (n_e, n_ip, n_b, 3)``, shared ``quad_w (n_ip)``, ``N (n_ip, n_b)``;
+  * default rules hex degree 2 (2x2x2 Gauss-Legendre, cmad/fem/quadrature.py:70-93) and
+    tet degree 1 (centroid, w = 1/6, :128-129) per cmad/fem/fe_problem.py:35-38;
+  * equation indices ``eq = offset + node*3 + comp`` in (basis, comp) order
+    (cmad/fem/assembly.py:142-165) = ``u_gather_eq`` = ``r_scatter_eq``
+    (cmad/fem/kernel_arrays.py:68-80);
+  * COO pattern and dedup scatter (cmad/fem/assembly.py:970-1070).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+_HEX_NODE_XI = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1],
+                         [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], dtype=np.float64)
+
+
+def structured_hex_mesh(divisions, lengths=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0)):
+    """``(nodes (n_nodes,3), connectivity (n_elems,8))`` of a Cartesian box."""
+    nx, ny, nz = (int(d) for d in divisions)
+    if min(nx, ny, nz) < 1:
+        raise ValueError(f"divisions must all be >= 1; got {divisions}")
+    axes = [np.linspace(o, o + L, n + 1) for o, L, n in zip(origin, lengths, (nx, ny, nz))]
+    nodes = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).reshape(-1, 3)
+    vid = np.arange((nx + 1) * (ny + 1) * (nz + 1), dtype=np.int64).reshape(nx + 1, ny + 1, nz + 1)
+    i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    corners = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]
+    conn = np.stack([vid[i + a, j + b, k + c] for a, b, c in corners], axis=-1).reshape(-1, 8)
+    return nodes, conn
+
+
+# six tets around the body diagonal 0-6 of a hex, every one positively oriented
+# on a positively oriented hex (volume checked in tests)
+_HEX_TO_TET = np.array([[0, 1, 2, 6], [0, 2, 3, 6], [0, 3, 7, 6],
+                        [0, 7, 4, 6], [0, 4, 5, 6], [0, 5, 1, 6]], dtype=np.int64)
+
+
+def split_hex_to_tets(conn_hex: np.ndarray) -> np.ndarray:
+    """Each hex -> 6 tets (tet ``6*e + t``), cf. ``hex_to_tet_split`` (cmad/fem/mesh.py:516-580)."""
+    return conn_hex[:, _HEX_TO_TET].reshape(-1, 4)
+
+
+def hex_quadrature_deg2():
+    g = 1.0 / np.sqrt(3.0)
+    x1 = np.array([-g, g])
+    xi = np.stack(np.meshgrid(x1, x1, x1, indexing="ij"), axis=-1).reshape(-1, 3)
+    return xi, np.ones(8)
+
+
+def tet_quadrature_deg1():
+    return np.array([[0.25, 0.25, 0.25]]), np.array([1.0 / 6.0])
+
+
+def hex_linear_shapes(xi: np.ndarray):
+    """``N (n_ip, 8)`` and reference gradients ``(n_ip, 8, 3)`` of the trilinear hex."""
+    t = 1.0 + xi[:, None, :] * _HEX_NODE_XI[None, :, :]          # (n_ip, 8, 3)
+    N = t.prod(axis=2) / 8.0
+    g = np.stack([_HEX_NODE_XI[None, :, 0] * t[:, :, 1] * t[:, :, 2],
+                  _HEX_NODE_XI[None, :, 1] * t[:, :, 0] * t[:, :, 2],
+                  _HEX_NODE_XI[None, :, 2] * t[:, :, 0] * t[:, :, 1]], axis=2) / 8.0
+    return N, g
+
+
+def tet_linear_shapes(xi: np.ndarray):
+    N = np.stack([1.0 - xi.sum(axis=1), xi[:, 0], xi[:, 1], xi[:, 2]], axis=1)
+    g = np.broadcast_to(np.array([[-1.0, -1, -1], [1, 0, 0], [0, 1, 0], [0, 0, 1]]),
+                        (xi.shape[0], 4, 3)).copy()
+    return N, g
+
+
+@dataclass
+class FEBlockArrays:
+    """Mesh-derived arrays of one element block (≙ the block's slices of the
+    reference's ``FEKernelArrays`` + ``BlockIPGeometryCache``)."""
+    elem_eq: torch.Tensor    # (n_e, n_b*3) int32
+    grad_N: torch.Tensor     # (n_e, n_ip, n_b, 3) float64, physical frame
+    det: torch.Tensor        # (n_e, n_ip) float64
+    quad_w: torch.Tensor     # (n_ip,) float64
+    N: torch.Tensor          # (n_ip, n_b) float64 (shared)
+    n_dofs: int
+
+    @property
+    def n_elems(self) -> int:
+        return int(self.elem_eq.shape[0])
+
+    @property
+    def n_basis(self) -> int:
+        return int(self.grad_N.shape[2])
+
+    @property
+    def n_ip(self) -> int:
+        return int(self.grad_N.shape[1])
+
+    def to(self, device) -> "FEBlockArrays":
+        return FEBlockArrays(self.elem_eq.to(device), self.grad_N.to(device), self.det.to(device),
+                             self.quad_w.to(device), self.N.to(device), self.n_dofs)
+
+    def slice(self, lo: int, hi: int) -> "FEBlockArrays":
+        """Contiguous element range (multi-GPU partition by element index)."""
+        return FEBlockArrays(self.elem_eq[lo:hi].contiguous(), self.grad_N[lo:hi].contiguous(),
+                             self.det[lo:hi].contiguous(), self.quad_w, self.N, self.n_dofs)
+
+
+def block_arrays(nodes, conn, device="cpu", chunk: int = 1 << 20) -> FEBlockArrays:
+    """Geometry cache + equation indices of one block (tet4 if ``conn`` has 4
+    columns, hex8 if 8), as ``precompute_block_geometry`` builds them."""
+    conn = np.asarray(conn)
+    n_b = conn.shape[1]
+    if n_b == 8:
+        xi, w = hex_quadrature_deg2()
+        N, gref = hex_linear_shapes(xi)
+    elif n_b == 4:
+        xi, w = tet_quadrature_deg1()
+        N, gref = tet_linear_shapes(xi)
+    else:
+        raise ValueError(f"unsupported element with {n_b} nodes")
+    dev = torch.device(device)
+    X_all = torch.as_tensor(np.asarray(nodes, dtype=np.float64))
+    gref_t = torch.as_tensor(gref).to(dev)
+    conn_t = torch.as_tensor(conn.astype(np.int64))
+    n_e = conn.shape[0]
+    grad_N = torch.empty((n_e, len(w), n_b, 3), dtype=torch.float64, device=dev)
+    det = torch.empty((n_e, len(w)), dtype=torch.float64, device=dev)
+    for lo in range(0, n_e, chunk):
+        hi = min(n_e, lo + chunk)
+        X = X_all[conn_t[lo:hi]].to(dev)                               # (c, n_b, 3)
+        jac = torch.einsum("eai,paj->epij", X, gref_t)                 # iso_jac[e,p,i,j]
+        det[lo:hi] = torch.linalg.det(jac)
+        grad_N[lo:hi] = torch.einsum("pnj,epji->epni", gref_t, torch.linalg.inv(jac))
+    eq = (conn_t[:, :, None] * 3 + torch.arange(3)[None, None, :]).reshape(n_e, n_b * 3)
+    return FEBlockArrays(eq.to(torch.int32).to(dev), grad_N, det, torch.as_tensor(w).to(dev),
+                         torch.as_tensor(N).to(dev), int(np.asarray(nodes).shape[0]) * 3)
+
+
+def coo_pattern(elem_eq: np.ndarray):
+    """With-duplicates ``(rows, cols)`` in ``assemble_element_block``'s emit order
+    ``(elem, row dof, col dof)`` (cmad/fem/assembly.py:970-1023)."""
+    eq = np.asarray(elem_eq, dtype=np.int64)
+    n_e, nd = eq.shape
+    rows = np.broadcast_to(eq[:, :, None], (n_e, nd, nd)).reshape(-1)
+    cols = np.broadcast_to(eq[:, None, :], (n_e, nd, nd)).reshape(-1)
+    return rows, cols
+
+
+def coo_dedup(elem_eq: np.ndarray):
+    """``(unique_rows, unique_cols, coo_dedup_scatter)`` as ``assembled_coo_dedup``
+    (cmad/fem/assembly.py:1026-1070): lex-sorted unique pattern + the map from each
+    with-duplicates triplet to its slot."""
+    rows, cols = coo_pattern(elem_eq)
+    n = int(max(rows.max(), cols.max())) + 1
+    key = rows * n + cols
+    uniq, inverse = np.unique(key, return_inverse=True)
+    return (uniq // n).astype(np.int64), (uniq % n).astype(np.int64), inverse.astype(np.int64)
+
+
+def synthetic_displacement(nodes: np.ndarray, t: float, seed: int = 42, ramp: float = 0.003,
+                           noise: float = 1e-4) -> np.ndarray:
+    """Uniaxial ramp ``u_x = ramp * t * x`` plus a random nodal perturbation
+    (seed/perturbation as tests/fem/test_assembly_coupled.py:177-178)."""
+    rng = np.random.default_rng(seed)
+    U = noise * rng.standard_normal(nodes.shape)
+    U[:, 0] += ramp * t * nodes[:, 0]
+    return U.reshape(-1)

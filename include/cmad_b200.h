@@ -134,9 +134,9 @@ typedef struct cmadx_mp_buffers {
 
 int cmadx_version(void);
 /* sizeof(cmadx_material_t), sizeof(cmadx_newton_t), sizeof(cmadx_mp_buffers_t),
- * sizeof(cmadx_mp_history_t): lets a foreign-language binding verify its struct
- * mirrors. */
-int cmadx_struct_sizes(int64_t* out4);
+ * sizeof(cmadx_mp_history_t), sizeof(cmadx_fe_block_t): lets a foreign-language
+ * binding verify its struct mirrors. */
+int cmadx_struct_sizes(int64_t* out5);
 const char* cmadx_error_string(int code);
 /* text of the last CUDA error seen by this thread ("" if none) */
 const char* cmadx_last_cuda_error(void);
@@ -214,6 +214,70 @@ int cmadx_mp_objective_adjoint(const cmadx_material_t* mat, const int32_t* activ
                                int32_t n_active, const cmadx_mp_history_t* hist, void* stream);
 int cmadx_mp_objective_direct(const cmadx_material_t* mat, const int32_t* active_pid,
                               int32_t n_active, const cmadx_mp_history_t* hist, void* stream);
+
+/* ---- K3/K4: FE element-block kernels (displacement formulation, COUPLED mode) ----
+ * One call = one mesh element block: for every element gather U, for every
+ * integration point interpolate grad_u = U_e^T grad_N
+ * (cmad/global_residuals/interpolation.py:49-55), run the local Newton from
+ * xi_prev (cmad/global_residuals/global_residual.py:361-395), evaluate the
+ * weak-form residual R = (grad_N @ sigma) w dv
+ * (cmad/global_residuals/small_disp_equilibrium.py:112-118) and its IFT-corrected
+ * tangent dR/dU, accumulate over the element's integration points
+ * (per_element_R_and_K_coupled, cmad/fem/assembly.py:416-535) and emit the
+ * per-element results in the layouts of assemble_element_block
+ * (cmad/fem/assembly.py:616-732).  All arrays use the REFERENCE's layouts
+ * (element-major, row-major trailing axes):
+ *   geometry cache  cmad/fem/precompute.py:51-72,107-122
+ *   index arrays    cmad/fem/kernel_arrays.py:58-114 (u_gather_eq == r_scatter_eq for
+ *                   the single-field displacement formulation; dof = basis*3 + comp,
+ *                   cmad/fem/assembly.py:142-165)
+ *   xi history      flat-trailing (n_elems, n_ip, n_xi), cmad/fem/fe_problem.py:310-313
+ * Supported element/rule pairs: tet4 x 1 IP, hex8 x 8 IPs (the reference's
+ * defaults, cmad/fem/fe_problem.py:35-38).  grad_N, K_elem and (tet4) R_elem must
+ * be 32-byte aligned (256-bit vector loads/stores).                            */
+typedef struct cmadx_fe_block {
+    int64_t n_elems;
+    int64_t n_dofs;          /* length of U and R_global                         */
+    int32_t n_basis;         /* 4 (tet4) | 8 (hex8)                              */
+    int32_t n_ip;            /* 1 | 8                                            */
+    const int32_t* elem_eq;  /* [n_elems][n_basis*3] global equation of (basis, comp) */
+    const double* U;         /* [n_dofs] global displacement vector              */
+    const double* xi_prev;   /* [n_elems][n_ip][n_xi]                            */
+    const double* grad_N;    /* [n_elems][n_ip][n_basis][3] physical-frame       */
+    const double* det;       /* [n_elems][n_ip] iso_jac_det (signed)             */
+    const double* quad_w;    /* [n_ip]                                           */
+    double* xi;              /* [n_elems][n_ip][n_xi] converged local state      */
+    double* R_elem;          /* [n_elems][n_basis*3] or NULL                     */
+    double* K_elem;          /* [n_elems][n_basis*3][n_basis*3] = the COO `vals`
+                                stream of assemble_element_block, or NULL (K4:
+                                residual-only, per_element_R_coupled :538-613)   */
+    double* R_global;        /* [n_dofs] or NULL: atomic scatter-add of R_elem
+                                (fast, not bit-reproducible; use
+                                cmadx_segment_sum on R_elem for a deterministic R) */
+    double* sigma;           /* [n_elems][n_ip][6] global cauchy at the IPs, or NULL
+                                (evaluate_cauchy_at_ips, cmad/fem/postprocess.py:35-185) */
+    int32_t* iters;          /* [n_elems][n_ip] or NULL                          */
+    int32_t* flags;          /* [n_elems][n_ip] or NULL (bit0 entry, bit1 exit)  */
+} cmadx_fe_block_t;
+
+int cmadx_fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* newton,
+                            const cmadx_fe_block_t* blk, void* stream);
+
+/* ---- K5: deterministic segment sums (R scatter-add, COO dedup) -----------------
+ * out[s] = sum of vals[i] over all items i with seg_of_item[i] == s, summed in
+ * increasing item order (bit-reproducible, and the order a sequential
+ * `.at[idx].add(vals)` uses).  Replaces R_block.at[eq].add(R_flat)
+ * (cmad/fem/assembly.py:715-720) with seg = r_scatter_eq, and the COO dedup
+ * unique_data.at[coo_dedup_scatter].add(vals) (cmad/fem/assembly.py:906-909,
+ * 1026-1070) with seg = coo_dedup_scatter.  The plan (a CSR of item lists per
+ * segment) is built once per mesh on the host and lives on the current device. */
+typedef struct cmadx_segment_plan cmadx_segment_plan_t;
+int cmadx_segment_plan_create(const int64_t* seg_of_item_host, int64_t n_items,
+                              int64_t n_segments, cmadx_segment_plan_t** plan);
+int cmadx_segment_plan_destroy(cmadx_segment_plan_t* plan);
+/* accumulate != 0: out[s] += sum (e.g. adding a block's R into the global R) */
+int cmadx_segment_sum(const cmadx_segment_plan_t* plan, const double* vals_dev,
+                      double* out_dev, int accumulate, void* stream);
 
 /* debugging aid: how many points the last J2 radial-return launch on `stream`
  * handed back to the generic kernel (synchronises the stream); -1 if none ran */

@@ -1,0 +1,83 @@
+"""CPU restatement of the FE element-block assembly (COUPLED mode).
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``): imported by ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs, never by the
+product package.
+
+Follows, vectorised over elements with NumPy:
+  cmad/global_residuals/interpolation.py:49-55      grad_u = U_e^T grad_N
+  cmad/global_residuals/global_residual.py:361-395  per-IP evaluator: local Newton from
+                                                    xi_prev, R, IFT-corrected dR/dU
+  cmad/global_residuals/small_disp_equilibrium.py:112-118  R = (grad_N @ sigma) * w * dv
+  cmad/fem/assembly.py:416-535   scan over IPs: R_e, K_e summed in IP order, xi stacked
+  cmad/fem/assembly.py:661-732   gather U, scatter-add R, emit COO ``vals``
+  cmad/fem/assembly.py:906-909   COO dedup (segment sum through coo_dedup_scatter)
+The per-point solve, stress and consistent tangent come from the dual-number
+C++ oracle (``oracle_c``), i.e. are AD-derived like the reference's.  The
+line-by-line torch-AD restatement of one element (``cmad_oracle.coupled_element``)
+cross-checks this file in tests/.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import oracle_c
+
+# symmetric component (xx,xy,xz,yy,yz,zz) of the 3x3 entry (i, j)
+_V = np.array([[0, 1, 2], [1, 3, 4], [2, 4, 5]])
+
+
+def full_tangent(dsig_deps: np.ndarray) -> np.ndarray:
+    """``Dfull[n, j, i, k, l] = d sigma_ji / d grad_u_kl`` from the symmetric-strain
+    tangent ``dsig_deps (36, n)`` (a*6+b): a grad_u entry (k,l), k != l, moves the
+    symmetric component by 1/2."""
+    n = dsig_deps.shape[1]
+    D = dsig_deps.reshape(6, 6, n)
+    half = np.array([1.0, 0.5, 0.5, 1.0, 0.5, 1.0])
+    Dh = D * half[None, :, None]
+    return np.moveaxis(Dh[_V][:, :, _V], -1, 0)          # (n, 3, 3, 3, 3) [j, i, k, l]
+
+
+def assemble_block(prob: oracle_c.OracleProblem, elem_eq, U, xi_prev, grad_N, det, quad_w,
+                   want_K: bool = True, nthreads: int = 0) -> dict:
+    """One COUPLED element block.  Inputs in the reference's layouts: ``elem_eq
+    (n_e, n_b*3)``, ``U (n_dofs,)``, ``xi_prev (n_e, n_ip, 7)``, ``grad_N (n_e, n_ip,
+    n_b, 3)``, ``det (n_e, n_ip)``, ``quad_w (n_ip,)``.  ``prob`` must be described
+    with ``strain_comps=9``.  Returns ``R_elem (n_e, n_b*3)``, ``K_elem (n_e, n_b*3,
+    n_b*3)``, ``xi``, ``sigma (n_e, n_ip, 6)``, ``iters``, ``flags``, ``R (n_dofs,)``."""
+    elem_eq = np.asarray(elem_eq, dtype=np.int64)
+    n_e, n_ip, n_b, _ = grad_N.shape
+    assert int(prob.cfg[7]) == 9
+    U_e = np.asarray(U)[elem_eq].reshape(n_e, n_b, 3)                    # assembly.py:121-139
+    R_e = np.zeros((n_e, n_b, 3))
+    K_e = np.zeros((n_e, n_b, 3, n_b, 3)) if want_K else None
+    xi = np.zeros((n_e, n_ip, 7)); sigma = np.zeros((n_e, n_ip, 6))
+    iters = np.zeros((n_e, n_ip), dtype=np.int32); flags = np.zeros((n_e, n_ip), dtype=np.int32)
+    want = ("xi", "sigma", "iters", "flags") + (("dsig_deps",) if want_K else ())
+    for ip in range(n_ip):                                               # lax.scan over IPs
+        gN = grad_N[:, ip]                                               # (n_e, n_b, 3)
+        gu = np.einsum("eak,eaj->ekj", U_e, gN)                          # grad_u[k, j]
+        r = oracle_c.mp_update(prob, xi_prev[:, ip].T.copy(), gu.reshape(n_e, 9).T.copy(),
+                               want=want, nthreads=nthreads)
+        xi[:, ip] = r["xi"].T; sigma[:, ip] = r["sigma"].T
+        iters[:, ip] = r["iters"]; flags[:, ip] = r["flags"]
+        sig33 = r["sigma"][_V]                                           # (3, 3, n_e)
+        wdv = quad_w[ip] * det[:, ip]
+        R_e += np.einsum("eaj,jie->eai", gN, sig33) * wdv[:, None, None]
+        if want_K:
+            Df = full_tangent(r["dsig_deps"])
+            K_e += np.einsum("eaj,ejikl,ebl->eaibk", gN, Df, gN) * wdv[:, None, None, None, None]
+    out = {"R_elem": R_e.reshape(n_e, n_b * 3), "xi": xi, "sigma": sigma, "iters": iters, "flags": flags}
+    if want_K:
+        out["K_elem"] = K_e.reshape(n_e, n_b * 3, n_b * 3)
+    R = np.zeros(np.asarray(U).shape[0])
+    np.add.at(R, elem_eq.reshape(-1), out["R_elem"].reshape(-1))         # assembly.py:715-720
+    out["R"] = R
+    return out
+
+
+def coo_dedup_sum(vals: np.ndarray, scatter: np.ndarray, n_unique: int) -> np.ndarray:
+    """``zeros(n_unique).at[coo_dedup_scatter].add(vals)`` (assembly.py:906-909)."""
+    out = np.zeros(n_unique)
+    np.add.at(out, scatter, vals)
+    return out

@@ -353,3 +353,26 @@ def test_maximum_batch_property_checks(cuda_device):
     ds = 2 * mu * de
     ds[[0, 3, 5]] += lam * tr_
     assert float((c["sigma"] - a["sigma"] - ds).abs().max()) < 1e-9
+
+
+@pytest.mark.parametrize("force_generic", [False, True])
+def test_zero_and_volumetric_strain_points_stay_finite(cuda_device, force_generic):
+    """Zero deviator (zero or purely volumetric strain): the J2 normal is NaN there
+    and the reference masks it with jnp.where (paths.py:27); the update must return
+    xi = xi_prev, the elastic tangent and finite everything, as the oracle does."""
+    values, act, tr = param_tree("J2")
+    P = Parameters(values, act, tr)
+    mat = material_from_values(values)
+    pid = active_param_ids(P)
+    n = 64
+    e = np.zeros((6, n)); e[[0, 3, 5], 32:] = 1e-4
+    nw = NewtonSettings(mode="traced", force_generic=force_generic)
+    xi = torch.zeros((7, n), dtype=torch.float64, device=cuda_device)
+    out = mp.mp_update(mat, nw, pid, xi, torch.from_numpy(e).to(cuda_device), outputs=ALL)
+    ref = oc.mp_update(oc.describe(values, P.active_idx), np.zeros((7, n)), e, want=ALL[:-1])
+    torch.cuda.synchronize()
+    for k in ("xi", "sigma", "dsig_deps", "dxi_deps", "dC_dp", "dC_dxi", "dC_dxi_prev"):
+        g = out[k].cpu().numpy()
+        assert np.isfinite(g).all(), k
+        assert np.abs(g - ref[k]).max() <= 1e-10 * max(np.abs(ref[k]).max(), 1.0), k
+    assert int(out["iters"].max()) == 0 and int(out["flags"].max()) == 0

@@ -70,10 +70,10 @@ def test_library_loads_and_exports_declared_symbols(built_lib):
     for n in names:
         assert hasattr(built_lib, n), f"{n} declared in include/cmad_b200.h but not exported"
     assert built_lib.cmadx_version() == 100
-    sizes = (C.c_int64 * 4)()
+    sizes = (C.c_int64 * 5)()
     assert built_lib.cmadx_struct_sizes(sizes) == 0
     assert list(sizes) == [C.sizeof(_lib.Material), C.sizeof(_lib.Newton), C.sizeof(_lib.MpBuffers),
-                           C.sizeof(_lib.MpHistory)]
+                           C.sizeof(_lib.MpHistory), C.sizeof(_lib.FeBlock)]
     assert built_lib.cmadx_error_string(1) == b"invalid argument"
 
 
