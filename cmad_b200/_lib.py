@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcmad_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
 SOURCES = ["api.cu", "mp_update.cu", "mp_update_j2.cu", "elastic_update.cu", "mp_sens.cu",
-           "fe_block.cu", "fe_scatter.cu"]
+           "fe_block.cu", "fe_tet4.cu", "fe_hex8.cu", "fe_scatter.cu"]
 
 # ---- enums (mirror include/cmad_b200.h) ---------------------------------
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(5)

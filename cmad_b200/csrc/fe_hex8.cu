@@ -1,0 +1,305 @@
+// K3 / K4 for hex8 elements with the degree-2 rule (8 integration points): the 8
+// threads of an element cooperate through shared memory; see fe_block.cu for the
+// contract and the references.
+//
+// Data movement.  Everything element-major in HBM is moved by the 8 threads of the
+// element as contiguous runs (grad_N: 48 x 32 B, xi_prev / xi: 56 doubles, K_e:
+// 144 x 32 B), lane t taking chunk q*8 + t, so one warp instruction touches 8
+// 128-byte lines instead of 32 (ncu on the first version: 0.65 L1 wavefronts per
+// 32-byte sector moved; the L1 data pipe, not HBM or FP64, was the limiter).
+// The transposition "thread owns a point" <-> "thread owns a chunk" goes through
+// the element's shared-memory region.
+//
+// Shared memory of one element (HEX_REGION doubles), reused in time:
+//   [0,24)    U_e
+//   [24,456)  8 integration-point records of HEX_REC = 54 doubles
+//             [0,21)  Dh = D[al][be] h(be) w dv, upper triangle; h = 1 for the diagonal
+//                     strain components, 1/2 for the off-diagonal ones (D is the
+//                     derivative w.r.t. a symmetric component, both tensor entries
+//                     moving), which makes Dh symmetric: 21 entries do
+//             [22,46) grad_N (8 nodes x 3), loaded straight from HBM into place
+//             [46,52) sigma w dv
+//   [456,512) xi_prev, then xi, of the 8 points (7 doubles each)
+//   phase C end: the 24x24 K_e tile (8 node blocks x 74 doubles) over the whole region
+//
+// Bank layout (ncu: the first version spent half its shared-memory wavefronts on
+// conflicts): 128-bit accesses are served per quarter-warp (= one element), 64-bit
+// ones per half-warp (= two elements).  HEX_REC*8 B = 27 x 16 B, odd: the 8 records of
+// an element start in distinct 16-byte bank groups.  The two elements of a half-warp
+// are 600 doubles = 8 mod 16 apart (16 banks): their node-strided 64-bit grad_N reads
+// fall in complementary banks.  The tile keeps the three rows of node a 74 doubles
+// apart (37 x 16 B, odd) so the block-wise 64-bit writes are conflict-free (simulated:
+// 162 wavefronts per warp, the minimum).
+#include "fe_common.cuh"
+
+namespace cmadx {
+namespace {
+
+constexpr int HEX_REC = 54;
+constexpr int HEX_RECS = 24;                      // records start here
+constexpr int HEX_GN = 22, HEX_SW = 46;           // within a record
+constexpr int HEX_XI = 456;
+constexpr int HEX_TILE_STRIDE = 74;               // 72 + 2: 37 x 16 B, odd
+constexpr int HEX_PAIR = 1192;                    // two element regions: 600 + 592 doubles
+constexpr int HEX_EPB = FE_BLOCK / 8;             // elements per block
+constexpr int HEX_SMEM_DOUBLES = (HEX_EPB / 2) * HEX_PAIR;
+
+// shared-memory base (in doubles) of block-local element `eloc`
+CMADX_DEV int hex_region(int eloc) { return (eloc >> 1) * HEX_PAIR + (eloc & 1) * 600; }
+// index of (al, be) in the packed upper triangle of a symmetric 6x6
+CMADX_DEV constexpr int sidx(int al, int be) {
+    return (al <= be) ? (al * 6 - al * (al - 1) / 2 + (be - al)) : (be * 6 - be * (be - 1) / 2 + (al - be));
+}
+// position of entry `o` (0..71: row i*24 + column) of node a's row block in the tile
+CMADX_DEV int tile_pos(int a, int o) { return a * HEX_TILE_STRIDE + o; }
+
+template <int SOLVER, bool ROT, bool WANT_K>
+CMADX_DEV void hex8_point(const FeArgs& A, const int64_t e, const bool live, double* smem) {
+    const cmadx_fe_block_t& b = A.b;
+    const int lane = threadIdx.x & 31;
+    const int ip = lane & 7;                      // this thread's point; also its node in phase C
+    const int eloc = threadIdx.x >> 3;
+    double* reg = smem + hex_region(eloc);
+    double* recs = reg + HEX_RECS;
+
+    // ---- phase A: element data -> shared memory, in contiguous runs
+    int eq3[3] = {0, 0, 0};
+    double wdv = 0.0;
+    if (live) {
+        // all global loads first (independent, in flight together), then the stores
+#pragma unroll
+        for (int k = 0; k < 3; ++k) eq3[k] = __ldg(b.elem_eq + e * 24 + 3 * ip + k);
+        const double* g = b.grad_N + e * 192;     // 8 points x 24 doubles = 48 chunks of 32 B
+        double c[6][4], xs[7], Un[3];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) ld256(g + 4 * (q * 8 + ip), c[q][0], c[q][1], c[q][2], c[q][3]);
+#pragma unroll
+        for (int r = 0; r < 7; ++r) xs[r] = __ldg(b.xi_prev + e * 56 + r * 8 + ip);
+        wdv = __ldg(b.quad_w + ip) * __ldg(b.det + e * 8 + ip);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Un[k] = __ldg(b.U + eq3[k]);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const int m = q * 8 + ip;             // chunk: point m / 6, part m % 6
+            double2* dst = reinterpret_cast<double2*>(recs + (m / 6) * HEX_REC + HEX_GN + (m % 6) * 4);
+            if ((m % 6) & 4) { dst[1] = make_double2(c[q][2], c[q][3]); dst[0] = make_double2(c[q][0], c[q][1]); }   // bank spread
+            else { dst[0] = make_double2(c[q][0], c[q][1]); dst[1] = make_double2(c[q][2], c[q][3]); }
+        }
+#pragma unroll
+        for (int r = 0; r < 7; ++r) reg[HEX_XI + r * 8 + ip] = xs[r];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) reg[3 * ip + k] = Un[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) reg[3 * ip + k] = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const int m = q * 8 + ip;
+            double2* dst = reinterpret_cast<double2*>(recs + (m / 6) * HEX_REC + HEX_GN + (m % 6) * 4);
+            dst[0] = make_double2(0.0, 0.0);
+            dst[1] = make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int r = 0; r < 7; ++r) reg[HEX_XI + r * 8 + ip] = 0.0;
+    }
+    __syncwarp();
+    double xp[7], eps[6];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) xp[c] = reg[HEX_XI + ip * 7 + c];
+    {
+        double gN[8][3], U[8][3];
+        const double* mine = recs + ip * HEX_REC + HEX_GN;
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { gN[a][k] = mine[3 * a + k]; U[a][k] = reg[3 * a + k]; }
+        strain_from_U<8>(U, gN, eps);
+    }
+
+    // ---- phase B: local Newton at this point
+    PointOut o;
+    double D[6][6];
+    solve_point<SOLVER, ROT, WANT_K>(A.m, A.nw, xp, eps, live, o, D);
+
+    // an element is handed to the generic kernel as a whole
+    bool ebail = false;
+    if (SOLVER == 0) {
+        const unsigned bal = __ballot_sync(0xffffffffu, o.bail);
+        ebail = ((bal >> (lane & ~7)) & 0xffu) != 0u;
+        if (ebail && live && ip == 0) append_bail(A, e);
+    }
+    const bool emit = live && !ebail;
+    {   // own record slots and own xi slot: no other thread has touched or read them yet
+        double* rec = recs + ip * HEX_REC;
+        if (WANT_K) {
+#pragma unroll
+            for (int al = 0; al < 6; ++al)
+#pragma unroll
+                for (int be = al; be < 6; ++be)
+                    rec[sidx(al, be)] = D[al][be] * (is_diag(be) ? wdv : 0.5 * wdv);
+        }
+#pragma unroll
+        for (int a = 0; a < 6; ++a) rec[HEX_SW + a] = o.sg[a] * wdv;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) reg[HEX_XI + ip * 7 + c] = o.x[c];
+    }
+    if (emit) {
+        const int64_t p = e * 8 + ip;
+        if (b.iters) b.iters[p] = o.iters;
+        if (b.flags) b.flags[p] = o.flags;
+        if (b.sigma) {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) b.sigma[p * 6 + a] = o.sg[a];
+        }
+    }
+    __syncwarp();
+    if (emit) {
+        double* xd = b.xi + e * 56;
+#pragma unroll
+        for (int r = 0; r < 7; ++r) xd[r * 8 + ip] = reg[HEX_XI + r * 8 + ip];
+    }
+
+    // ---- phase C: thread a owns the rows 3a..3a+2 of R_e / K_e; sums run over the 8
+    // points in fixed order (bit-reproducible)
+    const int a = ip;
+    const bool want_R = b.R_elem || b.R_global;
+    double Racc[3] = {0.0, 0.0, 0.0};
+    if constexpr (!WANT_K) {
+        if (emit && want_R) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const double* rec = recs + q * HEX_REC;
+                const double ga0 = rec[HEX_GN + 3 * a], ga1 = rec[HEX_GN + 3 * a + 1], ga2 = rec[HEX_GN + 3 * a + 2];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    Racc[i] = fma(ga2, rec[HEX_SW + vix(2, i)], fma(ga1, rec[HEX_SW + vix(1, i)], fma(ga0, rec[HEX_SW + vix(0, i)], Racc[i])));
+            }
+        }
+    } else {
+        // The consistent tangent of an associative model is symmetric (Dh = Dh^T), hence
+        // K_ba = K_ab^T: thread a computes the 3x3 node blocks (a, (a+d) mod 8), d = 0..3,
+        // plus d = 4 for a < 4 - 36 of the 64 blocks - and the mirror images are filled
+        // in through the shared-memory tile.  P[i][be] = sum_j gN[a][j] Dh[v(j,i)][be].
+        double acc[5][3][3];
+#pragma unroll
+        for (int d = 0; d < 5; ++d)
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) acc[d][i][k] = 0.0;
+#pragma unroll 1
+        for (int q = 0; q < 8; ++q) {
+            const double* rec = recs + q * HEX_REC;
+            const double ga[3] = {rec[HEX_GN + 3 * a], rec[HEX_GN + 3 * a + 1], rec[HEX_GN + 3 * a + 2]};
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                Racc[i] = fma(ga[2], rec[HEX_SW + vix(2, i)], fma(ga[1], rec[HEX_SW + vix(1, i)], fma(ga[0], rec[HEX_SW + vix(0, i)], Racc[i])));
+            double P[3][6];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int be = 0; be < 6; ++be)
+                    P[i][be] = fma(ga[2], rec[sidx(vix(2, i), be)],
+                                   fma(ga[1], rec[sidx(vix(1, i), be)], ga[0] * rec[sidx(vix(0, i), be)]));
+#pragma unroll
+            for (int d = 0; d < 5; ++d) {
+                const int bb = (a + d) & 7;
+                double g0, g1, g2;
+                if (d == 0) { g0 = ga[0]; g1 = ga[1]; g2 = ga[2]; }
+                else { g0 = rec[HEX_GN + 3 * bb]; g1 = rec[HEX_GN + 3 * bb + 1]; g2 = rec[HEX_GN + 3 * bb + 2]; }
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        acc[d][i][k] = fma(P[i][vix(k, 2)], g2, fma(P[i][vix(k, 1)], g1, fma(P[i][vix(k, 0)], g0, acc[d][i][k])));
+            }
+        }
+        __syncwarp();                             // all records consumed: the tile may overwrite them
+        double* tile = reg;
+#pragma unroll
+        for (int d = 0; d < 5; ++d) {
+            if (d < 4 || a < 4) {
+                const int bb = (a + d) & 7;
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        tile[tile_pos(a, i * 24 + 3 * bb + k)] = acc[d][i][k];
+                        if (d > 0) tile[tile_pos(bb, k * 24 + 3 * a + i)] = acc[d][i][k];
+                    }
+            }
+        }
+        __syncwarp();
+        if (emit) {
+            // K_e = 144 chunks of 32 B; lane t stores chunk c*8 + t.  Chunk s lives in node
+            // block s / 18 at 16-byte units 2(s % 18), +1; the lanes of the upper half read
+            // the units in swapped order so that a quarter-warp load hits 8 distinct groups.
+            double* Ke = b.K_elem + e * 576;
+            const int hi = ip >> 2;
+#pragma unroll
+            for (int c = 0; c < 18; ++c) {
+                const int s = c * 8 + ip;
+                const double2* src = reinterpret_cast<const double2*>(tile + (s / 18) * HEX_TILE_STRIDE + (s % 18) * 4);
+                const double2 u = src[hi], v = src[hi ^ 1];
+                st256(Ke + 4 * s, hi ? v.x : u.x, hi ? v.y : u.y, hi ? u.x : v.x, hi ? u.y : v.y);
+            }
+        }
+    }
+    if (emit && want_R) {
+        if (b.R_elem) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) b.R_elem[e * 24 + 3 * a + i] = Racc[i];
+        }
+        if (b.R_global) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) atomicAdd(b.R_global + eq3[i], Racc[i]);
+        }
+    }
+}
+
+template <int SOLVER, bool ROT, bool WANT_K, bool LIST>
+__global__ void __launch_bounds__(FE_BLOCK) fe_hex8_kernel(const __grid_constant__ FeArgs A) {
+    extern __shared__ __align__(16) double smem[];
+    if (!LIST) {
+        const int64_t e = (int64_t)blockIdx.x * HEX_EPB + (threadIdx.x >> 3);
+        hex8_point<SOLVER, ROT, WANT_K>(A, e, e < A.b.n_elems, smem);
+    } else {
+        const unsigned cnt = *A.bail_count;
+        if (cnt == 0u) return;
+        const bool all = cnt > A.bail_cap;
+        const int64_t total = all ? A.b.n_elems : (int64_t)cnt;
+        const int64_t stride = (int64_t)gridDim.x * HEX_EPB;
+        for (int64_t base = (int64_t)blockIdx.x * HEX_EPB; base < total; base += stride) {
+            const int64_t j = base + (threadIdx.x >> 3);
+            const bool live = j < total;
+            const int64_t e = live ? (all ? j : (int64_t)A.bail_list[j]) : 0;
+            hex8_point<SOLVER, ROT, WANT_K>(A, e, live, smem);
+            __syncwarp();
+        }
+    }
+}
+
+template <int SOLVER, bool ROT, bool WANT_K, bool LIST>
+struct Hex8Launcher {
+    static cudaError_t run(const FeArgs& A, cudaStream_t stream, int sms) {
+        auto kern = fe_hex8_kernel<SOLVER, ROT, WANT_K, LIST>;
+        const size_t smem = sizeof(double) * HEX_SMEM_DOUBLES;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        const int64_t nblk = LIST ? 2 * sms : (A.b.n_elems + HEX_EPB - 1) / HEX_EPB;
+        kern<<<(unsigned)nblk, FE_BLOCK, smem, stream>>>(A);
+        return cudaGetLastError();
+    }
+};
+
+}  // namespace
+
+cudaError_t launch_fe_hex8(const FeArgs& A, int solver, bool list, cudaStream_t stream, int sms) {
+    if (list) return Hex8Launcher<1, false, true, true>::run(A, stream, sms);
+    return dispatch_fe<Hex8Launcher, false>(A, solver, stream, sms);
+}
+cudaError_t launch_fe_hex8_list_nok(const FeArgs& A, cudaStream_t stream, int sms) {
+    return Hex8Launcher<1, false, false, true>::run(A, stream, sms);
+}
+
+}  // namespace cmadx
