@@ -32,6 +32,9 @@ N_POINTS = 1 << 24
 HISTORY_STEPS = 100
 SEED = 22
 ALG_BYTES_PER_UPDATE = 784      # in 56+48, out 56+48+288+280+4+4
+# ncu --set full capture of mp_update_j2_kernel (profiles/r1_k1_j2_raw.txt): dram__bytes_read
+# 436.27 MB + dram__bytes_write 2792.47 MB for a 4 194 304-point launch
+NCU_DRAM_BYTES_PER_UPDATE = (436.268288e6 + 2792.465e6) / 4194304
 OUTPUTS = ("xi", "sigma", "dsig_deps", "dC_dp", "iters", "flags")
 METRIC = "fp64 material-point updates/s (+tangent +dC/dp), J2+Voce return mapping"
 
@@ -247,10 +250,12 @@ def run_b200(args):
     avg_kernel_ms = float(np.mean(per_launch_ms))
     achieved = ALG_BYTES_PER_UPDATE * n / (avg_kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": NCU_DRAM_BYTES_PER_UPDATE * n, "peak_source": peak_src,
                 "kernel": "mp_update_j2_kernel (+ mp_update_list_kernel fallback, ~0.5% of the step)",
                 "alg_bytes_per_update": ALG_BYTES_PER_UPDATE, "avg_launch_ms": avg_kernel_ms,
-                "traffic_note": "ncu dram bytes r+w per launch = 0.98x algorithmic (profiles/r1_k1_j2_raw.txt)",
+                "traffic_note": "bytes per launch of this size, from the ncu --set full capture of a 2^22-point "
+                                "launch (769.8 B/update measured vs 784 algorithmic: no re-reads), "
+                                "profiles/r1_k1_j2_raw.txt",
                 "fp64": {"peak_tflops_measured": fp64_peak,
                          "note": "DFMA micro-benchmark (cmadx_fp64_peak); FP64 pipe ~28% busy in the "
                                  "J2 kernel (ncu), i.e. HBM binds"}}

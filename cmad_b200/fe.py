@@ -160,15 +160,34 @@ def assemble_element_block_residual(material, newton, arrays, U_global, xi_prev_
     return r_plan.sum(o["R_elem"].reshape(-1), stream=stream) if r_plan is not None else o["R_global"]
 
 
+def partition_block(arrays: FEBlockArrays, rank: int, world: int) -> tuple[FEBlockArrays, tuple[int, int]]:
+    """This rank's contiguous element range of a block (the path shards by element:
+    every element's local state, K_e and R_e are computed by exactly one rank)."""
+    from .objectives import shard_range
+    lo, hi = shard_range(arrays.n_elems, rank, world)
+    return arrays.slice(lo, hi), (lo, hi)
+
+
+def reduce_residual(R_local: torch.Tensor, group=None) -> torch.Tensor:
+    """The one exchange step of the FE path: sum the per-rank scatter-added residuals
+    (shared-node entries get contributions from several ranks).  NCCL over NVLink on
+    GPUs, gloo in the CPU tests; a no-op without an initialised process group."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(R_local, op=dist.ReduceOp.SUM, group=group)
+    return R_local
+
+
 def assemble_global(blocks: Mapping[str, tuple], U_global: torch.Tensor,
                     xi_prev_by_block: Mapping[str, torch.Tensor], coo_plan: SegmentPlan | None = None,
                     r_plans: Mapping[str, SegmentPlan] | None = None, group=None):
     """Walk all element blocks (``blocks[name] = (material, newton, arrays)``) and
     return ``(K_data, R, xi_solved_by_block)``: ``K_data`` is the deduplicated COO
     data (``coo_plan`` over the concatenated ``coo_dedup_scatter``) or, without a
-    plan, the with-duplicates stream; ``R`` the global residual.  With a
-    ``torch.distributed`` ``group`` the element blocks passed in are this rank's
-    partition and ``R`` is all-reduced (the one exchange step of the path)."""
+    plan, the with-duplicates stream; ``R`` the global residual.  Under
+    ``torch.distributed`` the element blocks passed in are this rank's partition
+    (:func:`partition_block`) and ``R`` is all-reduced - the one exchange step of the
+    path; ``K_data`` and ``xi`` stay rank-local (element-owned)."""
     R = torch.zeros(U_global.numel(), dtype=torch.float64, device=U_global.device)
     vals_all, xi_out = [], {}
     for name, (material, newton, arrays) in blocks.items():
@@ -178,9 +197,7 @@ def assemble_global(blocks: Mapping[str, tuple], U_global: torch.Tensor,
         R += Rb
         vals_all.append(vals)
         xi_out[name] = xi
-    if group is not None:
-        import torch.distributed as dist
-        dist.all_reduce(R, op=dist.ReduceOp.SUM, group=group)
+    R = reduce_residual(R, group)
     vals = vals_all[0] if len(vals_all) == 1 else torch.cat(vals_all)
     K = coo_plan.sum(vals) if coo_plan is not None else vals
     return K, R, xi_out

@@ -124,3 +124,40 @@ def test_block_oracle_tangent_vs_central_fd_tets():
     np.add.at(dense, (rows, cols), blk["K_elem"].reshape(-1))
     assert np.allclose(dense[ur, uc], Kd, rtol=1e-13)
     assert np.isclose(blk["R"].sum(), blk["R_elem"].sum())
+
+
+# ---- multi-rank host logic (gloo, world size 2): element partition + R all-reduce ----
+def _fe_gloo_worker(rank, world, port, nodes, conn, U, ret):
+    import os
+    import torch.distributed as dist
+    from cmad_b200 import fe
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    values, _, _ = analytic.j2_voce_param_tree("J2")
+    prob = oc.describe(values, None, newton_mode="traced", strain_comps=9, **NEWTON)
+    arr = fe_mesh.block_arrays(nodes, conn)
+    local, (lo, hi) = fe.partition_block(arr, rank, world)          # product host logic
+    o = fe_oracle.assemble_block(prob, local.elem_eq.numpy(), U, np.zeros((hi - lo, arr.n_ip, 7)),
+                                 local.grad_N.numpy(), local.det.numpy(), local.quad_w.numpy())
+    R = fe.reduce_residual(torch.from_numpy(o["R"].copy()))         # product exchange step
+    ret[rank] = (R.numpy(), lo, hi, o["K_elem"])
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_element_partition_equals_single_process():
+    import os
+    import torch.multiprocessing as tmp
+    values, _, _ = analytic.j2_voce_param_tree("J2")
+    nodes, conn = fe_mesh.structured_hex_mesh((3, 1, 1))            # 3 hexes: ragged 2 + 1 split
+    U = fe_mesh.synthetic_displacement(nodes, t=2.0, seed=9, noise=3e-4)
+    prob = oc.describe(values, None, newton_mode="traced", strain_comps=9, **NEWTON)
+    arr = fe_mesh.block_arrays(nodes, conn)
+    full = fe_oracle.assemble_block(prob, arr.elem_eq.numpy(), U, np.zeros((3, 8, 7)),
+                                    arr.grad_N.numpy(), arr.det.numpy(), arr.quad_w.numpy())
+    ret = tmp.Manager().dict()
+    tmp.spawn(_fe_gloo_worker, args=(2, 29500 + os.getpid() % 2000, nodes, conn, U, ret), nprocs=2, join=True)
+    for r in (0, 1):
+        R, lo, hi, K = ret[r]
+        assert np.allclose(R, full["R"], rtol=1e-13, atol=1e-13 * np.abs(full["R"]).max())
+        assert np.array_equal(K, full["K_elem"][lo:hi])             # element-owned data stays local
+    assert (ret[0][1], ret[0][2], ret[1][1], ret[1][2]) == (0, 2, 2, 3)
