@@ -104,6 +104,10 @@ int make_dev_mat(const cmadx_material_t* mat, DevMat* o) {
         o->Y = mat->Y; o->S = mat->voce_S; o->D = mat->voce_D; o->K = mat->linear_K;
         for (int i = 0; i < 6; ++i) o->hill[i] = mat->hill[i];
         o->a = mat->hosford_a;
+        o->a_int = 0;
+        if (mat->yield == CMADX_YIELD_HOSFORD && mat->hosford_a >= 1.0 && mat->hosford_a <= 1024.0 &&
+            mat->hosford_a == std::floor(mat->hosford_a))
+            o->a_int = (int)mat->hosford_a;
         o->yield_tol = mat->yield_tol;
     }
     bool ident = true;

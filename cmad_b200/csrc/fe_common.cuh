@@ -3,6 +3,8 @@
 // return and the generic 7x7 Newton) returning the converged state, the global
 // cauchy stress and the consistent tangent d sigma / d eps, and small helpers.
 #pragma once
+#include <type_traits>
+
 #include "fe_block.cuh"
 #include "j2_radial.cuh"
 
@@ -85,10 +87,15 @@ CMADX_DEV void rot_maps(const double* Q, double (&T)[6][6], double (&S)[6][6]) {
         }
 }
 
-// ---- generic 7x7 Newton point (point_solver.cuh) --------------------------------
+// ---- generic Newton point (point_solver.cuh): 7x7, or the 4x4 reduced system for
+// Hosford (the FE path always starts from xi_prev, so the reduction always applies)
 template <int YK, bool ROT, bool WANT_D>
 CMADX_DEV void point_generic(const DevMat& m, const DevNewton& nw, const double (&xp)[7],
                              const double (&e)[6], bool live, PointOut& o, double (&D)[6][6]) {
+    constexpr bool REDUCED = (YK == CMADX_YIELD_HOSFORD);
+    using Pt = typename std::conditional<REDUCED, HosfordPoint, SepPoint<YK>>::type;
+    using Tr = typename std::conditional<REDUCED, HosfordTraits, SepPointTraits<YK>>::type;
+    constexpr int N = Pt::N;
     double em[6];
     if (ROT) {
         double T[6][6], S[6][6];
@@ -106,9 +113,14 @@ CMADX_DEV void point_generic(const DevMat& m, const DevNewton& nw, const double 
     }
 #pragma unroll
     for (int c = 0; c < 7; ++c) o.x[c] = xp[c];
-    SepPoint<YK> pt;
-    double Cres[7];
-    const NewtonResult nr = local_newton<SepPoint<YK>, 7>(m, nw, pt, o.x, xp, em, live, Cres);
+    Pt pt;
+    if constexpr (REDUCED) { pt.shear[0] = xp[1]; pt.shear[1] = xp[2]; pt.shear[2] = xp[4]; }
+    double y[N], yp[N], Cy[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) { y[k] = xp[Tr::full(k)]; yp[k] = y[k]; }
+    const NewtonResult nr = local_newton<Pt, N>(m, nw, pt, y, yp, em, live, Cy);
+#pragma unroll
+    for (int k = 0; k < N; ++k) o.x[Tr::full(k)] = y[k];
     o.bail = false;
     o.iters = nr.iters;
     o.flags = nr.flag_entry | ((pt.plastic ? 1 : 0) << 1);
@@ -140,7 +152,7 @@ CMADX_DEV void point_generic(const DevMat& m, const DevNewton& nw, const double 
     // IFT (nonlinear_solver.py:158-171): d sigma/d eps = Cel . (A^{-1})[0:6,0:6] in material axes
     const bool pl = pt.plastic;
     const double dg = o.x[6] - xp[6];
-    RegLU<7> lu;
+    RegLU<N> lu;
     pt.jacobian(m, dg, lu.a);
     bool trouble = false;
     if (__any_sync(__activemask(), pl)) trouble = lu.factor_natural() && pl;
@@ -155,7 +167,14 @@ CMADX_DEV void point_generic(const DevMat& m, const DevNewton& nw, const double 
         double X[7];
 #pragma unroll
         for (int r = 0; r < 7; ++r) X[r] = (r == b) ? 1.0 : 0.0;
-        if (pl) { if (slow && trouble) lu.solve_pivot(X); else lu.solve_natural(X); }
+        if (Tr::local(b) >= 0 && pl) {
+            double Xl[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) Xl[k] = (k == Tr::local(b)) ? 1.0 : 0.0;
+            if (slow && trouble) lu.solve_pivot(Xl); else lu.solve_natural(Xl);
+#pragma unroll
+            for (int k = 0; k < N; ++k) X[Tr::full(k)] = Xl[k];
+        }
         const double ltr = m.lam * (X[0] + X[3] + X[5]);
 #pragma unroll
         for (int a = 0; a < 6; ++a) Dm[a][b] = is_diag(a) ? fma(m.two_mu, X[a], ltr) : m.two_mu * X[a];

@@ -10,6 +10,8 @@
 //   cmad/models/nonlinear_solver.py:88-174 (make_newton_solve + IFT rule) or
 //   :14-85 (newton_solve), cmad/models/model.py:121-166 (AD Jacobians),
 //   cmad/parameters/parameters.py:368-377 (active-column selection).
+#include <type_traits>
+
 #include "mp_outputs.cuh"
 
 namespace cmadx {
@@ -34,8 +36,13 @@ CMADX_DEV void rot_maps(const double* Q, double (&T)[6][6], double (&S)[6][6]) {
         }
 }
 
-template <int YK, bool ROT>
+// REDUCED: Hosford through the 4-unknown HosfordPoint (see point_solver.cuh); needs
+// the starting iterate to be xi_prev (no xi_init)
+template <int YK, bool ROT, bool REDUCED>
 CMADX_DEV void process_point(const MpArgs& A, const int64_t i, const bool live) {
+    using Pt = typename std::conditional<REDUCED, HosfordPoint, SepPoint<YK>>::type;
+    using Tr = typename std::conditional<REDUCED, HosfordTraits, SepPointTraits<YK>>::type;
+    constexpr int N = Pt::N;
     const int64_t ld = A.b.ld;
     const DevMat& m = A.m;
 
@@ -58,18 +65,23 @@ CMADX_DEV void process_point(const MpArgs& A, const int64_t i, const bool live) 
     }
 #pragma unroll
     for (int c = 0; c < 7; ++c) x[c] = xp[c];
-    if (live && A.b.xi_init) {
+    if (!REDUCED && live && A.b.xi_init) {
 #pragma unroll
         for (int c = 0; c < 7; ++c) x[c] = __ldg(A.b.xi_init + c * ld + i);
     }
 
-    SepPoint<YK> pt;
-    double Cres[7];
-    const NewtonResult nr = local_newton<SepPoint<YK>, 7>(m, A.nw, pt, x, xp, em, live, Cres);
+    Pt pt;
+    if constexpr (REDUCED) { pt.shear[0] = xp[1]; pt.shear[1] = xp[2]; pt.shear[2] = xp[4]; }
+    double y[N], yp[N], Cy[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) { y[k] = x[Tr::full(k)]; yp[k] = xp[Tr::full(k)]; }
+    const NewtonResult nr = local_newton<Pt, N>(m, A.nw, pt, y, yp, em, live, Cy);
     if (!live) return;
+#pragma unroll
+    for (int k = 0; k < N; ++k) x[Tr::full(k)] = y[k];
     if (A.b.C) {
 #pragma unroll
-        for (int c = 0; c < 7; ++c) st(A.b.C, c, ld, i, Cres[c]);
+        for (int c = 0; c < 7; ++c) st(A.b.C, c, ld, i, (Tr::local(c) >= 0) ? Cy[Tr::local(c) >= 0 ? Tr::local(c) : 0] : 0.0);
     }
 
     // ---------------------------------------------------------------- outputs
@@ -127,19 +139,20 @@ CMADX_DEV void process_point(const MpArgs& A, const int64_t i, const bool live) 
     const bool want_ift = A.b.dsig_deps || A.b.dxi_deps;
     if (!want_ift && !A.b.dC_dxi) return;
 
-    RegLU<7> lu;
-    pt.jacobian(m, dg, lu.a);
     if (A.b.dC_dxi) {
 #pragma unroll
         for (int r = 0; r < 7; ++r)
 #pragma unroll
-            for (int c = 0; c < 7; ++c) st(A.b.dC_dxi, r * 7 + c, ld, i, lu.a[r][c]);
+            for (int c = 0; c < 7; ++c) st(A.b.dC_dxi, r * 7 + c, ld, i, full_jacobian_entry(m, pt, dg, r, c));
     }
     if (!want_ift) return;
 
     // IFT (nonlinear_solver.py:158-171).  In material axes dC/de = -(A[:, :6] - E),
     // E = [I6; 0], so dx/de = E - A^{-1}E and d sigma/de = Cel . (A^{-1})[0:6,0:6].
-    // threshold pivoting (see RegLU): natural order unless some lane is troubled
+    // threshold pivoting (see RegLU): natural order unless some lane is troubled.
+    // Strain components that are not unknowns of a reduced point have A^{-1} e_b = e_b.
+    RegLU<N> lu;
+    pt.jacobian(m, dg, lu.a);
     bool trouble = false;
     if (__any_sync(__activemask(), pl)) trouble = lu.factor_natural() && pl;
     const bool slow = __any_sync(__activemask(), trouble);
@@ -147,13 +160,23 @@ CMADX_DEV void process_point(const MpArgs& A, const int64_t i, const bool live) 
         pt.jacobian(m, dg, lu.a);
         lu.factor_pivot();
     }
+    auto solve_dir = [&](int b, double (&X)[7]) {
+#pragma unroll
+        for (int r = 0; r < 7; ++r) X[r] = (r == b) ? 1.0 : 0.0;
+        if (Tr::local(b) >= 0 && pl) {
+            double Xl[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) Xl[k] = (k == Tr::local(b)) ? 1.0 : 0.0;
+            if (slow && trouble) lu.solve_pivot(Xl); else lu.solve_natural(Xl);
+#pragma unroll
+            for (int k = 0; k < N; ++k) X[Tr::full(k)] = Xl[k];
+        }
+    };
     if (!ROT) {
 #pragma unroll
         for (int b = 0; b < 6; ++b) {
             double X[7];
-#pragma unroll
-            for (int r = 0; r < 7; ++r) X[r] = (r == b) ? 1.0 : 0.0;
-            if (pl) { if (slow && trouble) lu.solve_pivot(X); else lu.solve_natural(X); }
+            solve_dir(b, X);
             if (A.b.dxi_deps) {
 #pragma unroll
                 for (int r = 0; r < 7; ++r) st(A.b.dxi_deps, r * 6 + b, ld, i, ((r == b) ? 1.0 : 0.0) - X[r]);
@@ -170,9 +193,7 @@ CMADX_DEV void process_point(const MpArgs& A, const int64_t i, const bool live) 
 #pragma unroll
         for (int b = 0; b < 6; ++b) {
             double X[7];
-#pragma unroll
-            for (int r = 0; r < 7; ++r) X[r] = (r == b) ? 1.0 : 0.0;
-            if (pl) { if (slow && trouble) lu.solve_pivot(X); else lu.solve_natural(X); }
+            solve_dir(b, X);
             const double ltr = m.lam * (X[0] + X[3] + X[5]);
 #pragma unroll
             for (int a = 0; a < 6; ++a) Dm[a][b] = is_diag(a) ? fma(m.two_mu, X[a], ltr) : m.two_mu * X[a];
@@ -217,11 +238,11 @@ CMADX_DEV void process_point(const MpArgs& A, const int64_t i, const bool live) 
 }
 
 // one thread per point over the whole batch
-template <int YK, bool ROT>
+template <int YK, bool ROT, bool REDUCED>
 __global__ void __launch_bounds__(MP_BLOCK)
 mp_update_kernel(const __grid_constant__ MpArgs A) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    process_point<YK, ROT>(A, i, i < A.b.n);
+    process_point<YK, ROT, REDUCED>(A, i, i < A.b.n);
 }
 
 // list mode: a small grid walks the points the J2 radial kernel handed back
@@ -239,7 +260,7 @@ mp_update_list_kernel(const __grid_constant__ MpArgs A) {
         const int64_t j = base + lane;
         const bool live = j < total;
         const int64_t i = live ? (all ? j : (int64_t)A.bail_list[j]) : 0;
-        process_point<YK, ROT>(A, i, live);
+        process_point<YK, ROT, false>(A, i, live);
     }
 }
 
@@ -247,8 +268,14 @@ template <int YK>
 cudaError_t launch_yk(const MpArgs& A, cudaStream_t stream) {
     const int64_t nblk = (A.b.n + MP_BLOCK - 1) / MP_BLOCK;
     if (nblk == 0) return cudaSuccess;
-    if (A.m.rot) mp_update_kernel<YK, true><<<(unsigned)nblk, MP_BLOCK, 0, stream>>>(A);
-    else mp_update_kernel<YK, false><<<(unsigned)nblk, MP_BLOCK, 0, stream>>>(A);
+    if (YK == CMADX_YIELD_HOSFORD && !A.b.xi_init && !(A.nw.flags & CMADX_NEWTON_F_GENERIC)) {
+        constexpr int H = CMADX_YIELD_HOSFORD;
+        if (A.m.rot) mp_update_kernel<H, true, true><<<(unsigned)nblk, MP_BLOCK, 0, stream>>>(A);
+        else mp_update_kernel<H, false, true><<<(unsigned)nblk, MP_BLOCK, 0, stream>>>(A);
+        return cudaGetLastError();
+    }
+    if (A.m.rot) mp_update_kernel<YK, true, false><<<(unsigned)nblk, MP_BLOCK, 0, stream>>>(A);
+    else mp_update_kernel<YK, false, false><<<(unsigned)nblk, MP_BLOCK, 0, stream>>>(A);
     return cudaGetLastError();
 }
 

@@ -33,6 +33,7 @@ struct DevMat {
     double yield_tol;
     double dlam[2], dmu[2];   // d(lambda, mu)/d(elastic[0..1])
     int hmask, rot, model, yield;
+    int a_int;                // Hosford exponent when it is a small positive integer, else 0
 };
 
 struct DevNewton {
@@ -144,6 +145,19 @@ template <> struct YieldFn<CMADX_YIELD_HILL> {
     }
 };
 
+// r^a for r >= 0: square-and-multiply when the exponent is a small positive integer
+// (a = 4 in the reference's tests, 100 in examples/notch_hosford.yaml; the branch is
+// uniform over the launch), the libm pow otherwise.  Agrees with pow to a few ulp.
+CMADX_DEV double hosford_pow(double r, double a, int a_int) {
+    if (a_int <= 0) return pow(r, a);
+    double res = 1.0, b = r;
+    for (int e = a_int; e != 0; e >>= 1) {
+        if (e & 1) res *= b;
+        b *= b;
+    }
+    return res;
+}
+
 // Hosford: phi = vm * (1/2 sum_i |Delta_i/vm|^a)^(1/a) on the *diagonal* stress
 // entries only (the reference's documented limitation).  The vm scaling cancels
 // analytically (phi is the plain a-norm of the differences); it is kept for the
@@ -166,7 +180,7 @@ template <> struct YieldFn<CMADX_YIELD_HOSFORD> {
         const double dl[3] = {sig[0] - sig[3], sig[3] - sig[5], sig[5] - sig[0]};
         double q[3], sq = 0.0;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { q[i] = pow(fabs(dl[i] * ivm), a); sq += q[i]; }
+        for (int i = 0; i < 3; ++i) { q[i] = hosford_pow(fabs(dl[i] * ivm), a, m.a_int); sq += q[i]; }
         sq *= 0.5;
         phi = vm * pow(sq, 1.0 / a);
         iphi = 1.0 / phi;
@@ -396,6 +410,100 @@ struct SepPoint {
         }
     }
 };
+
+// position in the full 7-vector [ep(6), alpha] of local unknown k
+template <int YK> struct SepPointTraits {
+    CMADX_DEV static constexpr int full(int k) { return k; }
+    CMADX_DEV static constexpr int local(int c) { return c; }      // -1: not an unknown
+};
+
+// --------------------------------------------------------------------------
+// Hosford, reduced: the reference's Hosford surface only sees the DIAGONAL stress
+// entries (effective_stress.py:167-177), so the yield normal and its derivative
+// vanish on the shear components: started from x0 = xi_prev the shear rows of the
+// residual are identically zero and those rows/columns of the Jacobian are the
+// identity.  Natural-order elimination of the 7x7 system then performs exactly the
+// operations of the 4x4 system in [ep_xx, ep_yy, ep_zz, alpha] (the other
+// multipliers are exact zeros), so this point type yields the same iterates, norms,
+// iteration counts and flags as SepPoint<HOSFORD> - with a 16-entry LU.
+// Valid when the starting iterate equals xi_prev on the shear components.
+// --------------------------------------------------------------------------
+struct HosfordPoint {
+    static constexpr int N = 4;
+    YieldFn<CMADX_YIELD_HOSFORD> yf;
+    double n[6];
+    double f, eD;
+    double shear[3];   // ep_xy, ep_xz, ep_yz: frozen
+    bool plastic;
+
+    CMADX_DEV void residual(const DevMat& m, const double (&x)[4], const double (&xp)[4],
+                            const double (&em)[6], double (&C)[4]) {
+        double ee[6];
+        ee[0] = em[0] - x[0]; ee[3] = em[3] - x[1]; ee[5] = em[5] - x[2];
+        ee[1] = em[1] - shear[0]; ee[2] = em[2] - shear[1]; ee[4] = em[4] - shear[2];
+        const double ltr = m.lam * (ee[0] + ee[3] + ee[5]);
+        double sig[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) sig[a] = is_diag(a) ? fma(m.two_mu, ee[a], ltr) : m.two_mu * ee[a];
+        double phi;
+        yf.eval(m, sig, phi, n);
+        double Hd = 0.0;
+        eD = 0.0;
+        if (m.hmask & CMADX_HARD_VOCE) { eD = exp(-m.D * x[3]); Hd = m.S * (1.0 - eD); }
+        if (m.hmask & CMADX_HARD_LINEAR) Hd = fma(m.K, x[3], Hd);
+        f = (phi - (m.Y + Hd)) * m.inv_two_mu;
+        const double dg = x[3] - xp[3];
+        plastic = (f > m.yield_tol) || (fabs(f) < m.yield_tol);   // paths.py:26
+        const double nd[3] = {n[0], n[3], n[5]};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double ce = x[k] - xp[k];
+            C[k] = plastic ? fma(-dg, nd[k], ce) : ce;
+        }
+        C[3] = plastic ? f : dg;
+    }
+
+    CMADX_DEV void jacobian(const DevMat& m, double dg, double (&J)[4][4]) const {
+        constexpr int D[3] = {0, 3, 5};
+        if (plastic) {
+            const double s = dg * m.two_mu;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+#pragma unroll
+                for (int b = 0; b < 3; ++b) J[a][b] = fma(s, yf.M(D[a], D[b]), (a == b) ? 1.0 : 0.0);
+                J[a][3] = -n[D[a]];
+                J[3][a] = -n[D[a]];
+            }
+            double Hp = 0.0;
+            if (m.hmask & CMADX_HARD_VOCE) Hp = m.S * m.D * eD;
+            if (m.hmask & CMADX_HARD_LINEAR) Hp += m.K;
+            J[3][3] = -Hp * m.inv_two_mu;
+        } else {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) J[a][b] = (a == b) ? 1.0 : 0.0;
+        }
+    }
+};
+
+struct HosfordTraits {
+    CMADX_DEV static constexpr int full(int k) { return k == 0 ? 0 : (k == 1 ? 3 : (k == 2 ? 5 : 6)); }
+    CMADX_DEV static constexpr int local(int c) { return c == 0 ? 0 : (c == 3 ? 1 : (c == 5 ? 2 : (c == 6 ? 3 : -1))); }
+};
+
+// full 7x7 dC/dx from a point's state (any point type with yf, n, eD, plastic)
+template <class Pt>
+CMADX_DEV double full_jacobian_entry(const DevMat& m, const Pt& pt, double dg, int r, int c) {
+    if (!pt.plastic) return (r == c) ? 1.0 : 0.0;
+    if (r < 6 && c < 6) return fma(dg * m.two_mu, pt.yf.M(r, c), (r == c) ? 1.0 : 0.0);
+    if (r < 6) return -pt.n[r];
+    if (c < 6) return -mult(c) * pt.n[c];
+    double Hp = 0.0;
+    if (m.hmask & CMADX_HARD_VOCE) Hp = m.S * m.D * pt.eD;
+    if (m.hmask & CMADX_HARD_LINEAR) Hp += m.K;
+    return -Hp * m.inv_two_mu;
+}
 
 template <int N> CMADX_DEV double normN(const double (&v)[N]) {
     double s = 0.0;

@@ -376,3 +376,34 @@ def test_zero_and_volumetric_strain_points_stay_finite(cuda_device, force_generi
         assert np.isfinite(g).all(), k
         assert np.abs(g - ref[k]).max() <= 1e-10 * max(np.abs(ref[k]).max(), 1.0), k
     assert int(out["iters"].max()) == 0 and int(out["flags"].max()) == 0
+
+
+@pytest.mark.parametrize("a", [4.0, 6.5, 8.0])
+@pytest.mark.parametrize("mode", ["traced", "imperative"])
+def test_hosford_reduced_4x4_path(cuda_device, a, mode):
+    """Hosford runs through the reduced [ep_xx, ep_yy, ep_zz, alpha] system (the surface
+    ignores shear, effective_stress.py:167-177) with strains that DO carry shear, for
+    integer exponents (square-and-multiply) and a non-integer one (libm pow): parity
+    with the oracle, and iteration counts / flags identical to the full 7x7 kernel."""
+    rng = np.random.default_rng(21)
+    values, act, tr = param_tree("hosford", ("voce", "linear"), a=a, active=("E", "nu", "D", "S", "Y", "K"))
+    assert _run_pair(cuda_device, values, act, tr, 20000, mode, rng, diag_only=False)
+    P = Parameters(values, act, tr)
+    mat = material_from_values(values)
+    pid = active_param_ids(P)
+    n = 8192
+    e = random_strains(rng, n, scale=1.5e-3)
+    xi0 = torch.zeros((7, n), dtype=torch.float64, device=cuda_device)
+    xi0[[1, 2, 4]] = torch.from_numpy(rng.normal(size=(3, n)) * 1e-4).to(cuda_device)   # frozen shear state
+    et = torch.from_numpy(e).to(cuda_device)
+    kw = dict(max_iters=20, abs_tol=1e-12, rel_tol=1e-12)
+    red = mp.mp_update(mat, NewtonSettings(mode=mode, **kw), pid, xi0, et, outputs=ALL)
+    gen = mp.mp_update(mat, NewtonSettings(mode=mode, force_generic=True, **kw), pid, xi0, et, outputs=ALL)
+    torch.cuda.synchronize()
+    assert torch.equal(red["iters"], gen["iters"]) and torch.equal(red["flags"], gen["flags"])
+    assert bool((red["flags"] & 2).any())
+    for k in ("xi", "sigma", "dsig_deps", "dxi_deps", "dC_dp", "dC_dxi", "dC_dxi_prev"):
+        assert rel_err(red[k].cpu().numpy(), gen[k].cpu().numpy()) < 1e-11, k
+    # the converged residual is rounding noise: compared absolutely
+    assert float((red["C"] - gen["C"]).abs().max()) < 1e-13
+    assert torch.equal(red["xi"][[1, 2, 4]], xi0[[1, 2, 4]])
