@@ -239,7 +239,7 @@ CMADX_DEV void process_point(const MpArgs& A, const int64_t i, const bool live) 
 
 // one thread per point over the whole batch
 template <int YK, bool ROT, bool REDUCED>
-__global__ void __launch_bounds__(MP_BLOCK)
+__global__ void __launch_bounds__(MP_BLOCK, REDUCED ? 4 : 1)
 mp_update_kernel(const __grid_constant__ MpArgs A) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     process_point<YK, ROT, REDUCED>(A, i, i < A.b.n);

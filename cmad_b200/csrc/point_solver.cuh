@@ -236,6 +236,35 @@ template <> struct YieldFn<CMADX_YIELD_HOSFORD> {
 // solves of the same system; they differ at rounding level only.
 // a[k][k] holds 1/pivot after factorisation.
 // --------------------------------------------------------------------------
+// partial-pivoting LU of an n x n matrix in (local) memory; returns the swap bits in
+// the order RegLU::solve_pivot replays them; a[k][k] holds 1/pivot afterwards
+static __device__ __noinline__ unsigned lu_factor_pivot_mem(double* a, int n) {
+    unsigned swaps = 0u;
+    int bit = 0;
+    for (int k = 0; k < n; ++k) {
+        for (int i = k + 1; i < n; ++i) {
+            const bool sw = fabs(a[i * n + k]) > fabs(a[k * n + k]);
+            if (sw) {
+                for (int j = 0; j < n; ++j) {
+                    const double u = a[k * n + j];
+                    a[k * n + j] = a[i * n + j];
+                    a[i * n + j] = u;
+                }
+            }
+            swaps |= (sw ? 1u : 0u) << bit;
+            ++bit;
+        }
+        const double rp = 1.0 / a[k * n + k];
+        a[k * n + k] = rp;
+        for (int i = k + 1; i < n; ++i) {
+            const double l = a[i * n + k] * rp;
+            a[i * n + k] = l;
+            for (int j = k + 1; j < n; ++j) a[i * n + j] = fma(-l, a[k * n + j], a[i * n + j]);
+        }
+    }
+    return swaps;
+}
+
 template <int N>
 struct RegLU {
     double a[N][N];
@@ -278,34 +307,19 @@ struct RegLU {
 
     // full partial pivoting (rows bubble so that row k holds the column
     // maximum, first maximum wins); the swap decisions are recorded so
-    // right-hand sides can be permuted later
+    // right-hand sides can be permuted later.  Rare path: done in local memory by
+    // one out-of-line routine shared by every kernel (keeps the hot code small).
     CMADX_DEV void factor_pivot() {
-        swaps = 0u;
-        int bit = 0;
+        double t[N * N];
 #pragma unroll
-        for (int k = 0; k < N; ++k) {
+        for (int i = 0; i < N; ++i)
 #pragma unroll
-            for (int i = k + 1; i < N; ++i) {
-                const bool sw = fabs(a[i][k]) > fabs(a[k][k]);
+            for (int j = 0; j < N; ++j) t[i * N + j] = a[i][j];
+        swaps = lu_factor_pivot_mem(t, N);
 #pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    const double u = a[k][j], v = a[i][j];
-                    a[k][j] = sw ? v : u;
-                    a[i][j] = sw ? u : v;
-                }
-                swaps |= (sw ? 1u : 0u) << bit;
-                ++bit;
-            }
-            const double rp = 1.0 / a[k][k];
-            a[k][k] = rp;
+        for (int i = 0; i < N; ++i)
 #pragma unroll
-            for (int i = k + 1; i < N; ++i) {
-                const double l = a[i][k] * rp;
-                a[i][k] = l;
-#pragma unroll
-                for (int j = k + 1; j < N; ++j) a[i][j] = fma(-l, a[k][j], a[i][j]);
-            }
-        }
+            for (int j = 0; j < N; ++j) a[i][j] = t[i * N + j];
     }
     CMADX_DEV void solve_pivot(double (&b)[N]) const {
         int bit = 0;
@@ -555,65 +569,77 @@ struct NewtonResult {
 // solution, C the residual there, and pt holds the state (n, f, plastic, yield
 // internals) at x.
 // Pt provides residual(m, x, xp, em, C), jacobian(m, dgamma, J) and `plastic`.
+//
+// Both Newton flavours are written as ONE loop around a SINGLE residual call
+// site, driven by a per-lane phase: the residual (with its pow / exp / sqrt) is
+// by far the largest piece of code, and five inlined copies of it made the
+// kernels instruction-cache bound (ncu: 26 % of the stalls "no instruction").
+// Lanes in different phases now also share the evaluation instead of serialising.
+// The sequence of evaluations, tests and updates of every lane is exactly that of
+// the reference loops (nonlinear_solver.py:102-155 and :14-85, line_search.py:125-181).
 template <class Pt, int N>
 CMADX_DEV NewtonResult local_newton(const DevMat& m, const DevNewton& nw, Pt& pt,
                                     double (&x)[N], const double (&xp)[N],
                                     const double (&em)[6], bool live, double (&C)[N]) {
     NewtonResult r;
-    pt.residual(m, x, xp, em, C);
-    r.flag_entry = pt.plastic ? 1 : 0;
-    double n0 = normN<N>(C);
-    double nc = n0;
+    r.flag_entry = 0;
+    const bool traced = (nw.mode == CMADX_NEWTON_TRACED);
+    enum { PH_INIT = 0, PH_PROBE = 1, PH_REFRESH = 2, PH_IMP = 3, PH_FINAL = 4 };
+    int phase = PH_INIT;
+    bool active = true;          // this lane wants the next residual evaluation
+    double xt[N];                // where it wants it
+#pragma unroll
+    for (int i = 0; i < N; ++i) xt[i] = x[i];
+    double n0 = 0.0, nc = 0.0;
     int ii = 0;
-    bool done = !live || nw.max_iters <= 0;
-    bool fresh = true;   // pt state corresponds to x
+    // line-search state (traced flavour)
+    double dx[N], best_C[N];
+    double al = 1.0, best_al = 1.0, best_phi = CUDART_INF, phi0 = 0.0, dphi0 = 0.0, armijo = 0.0;
+    int ne = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { dx[i] = 0.0; best_C[i] = 0.0; C[i] = 0.0; }
     const unsigned full = 0xffffffffu;
-    if (nw.mode == CMADX_NEWTON_TRACED) {
-        while (__any_sync(full, !done)) {
-            if (!done) {
-                nc = normN<N>(C);
-                const double rel = nc / n0;                      // 0/0 -> NaN: test is false
-                if (rel < nw.rel_tol || nc < nw.abs_tol) {
-                    done = true;
+    while (__any_sync(full, active)) {
+        if (active) {
+            double Ct[N];
+            pt.residual(m, xt, xp, em, Ct);                    // the only call site
+            bool need_dir = false;   // (x, C) current and pt fresh at x: take a Newton step
+            bool stepped = false;    // traced: a line search just ended, x / C updated
+            bool fresh = true;       // pt corresponds to x
+            if (phase == PH_INIT) {
+                r.flag_entry = pt.plastic ? 1 : 0;
+#pragma unroll
+                for (int i = 0; i < N; ++i) C[i] = Ct[i];
+                n0 = normN<N>(C);
+                nc = n0;
+                if (!live || nw.max_iters <= 0) {
+                    active = false;
                 } else {
-                    if (!fresh) { double Ct[N]; pt.residual(m, x, xp, em, Ct); }
-                    double dx[N];
+                    const double rel = traced ? nc / n0 : 1.0;   // 0/0 -> NaN: test is false
+                    if (rel < nw.rel_tol || nc < nw.abs_tol) active = false; else need_dir = true;
+                }
+            } else if (phase == PH_PROBE) {
+                // ---- line search (quadratic model), line_search.py:125-181
+                const double ph = 0.5 * dotN<N>(Ct, Ct);
+                const bool fin = isfinite(ph);
+                if (fin && ph < best_phi) {
+                    best_al = al; best_phi = ph;
 #pragma unroll
-                    for (int i = 0; i < N; ++i) dx[i] = C[i];
-                    newton_direction<Pt, N>(m, pt, x[N - 1] - xp[N - 1], dx);   // solve(J, C)
-                    // ---- line search (quadratic model), line_search.py:125-181
-                    const double CC = dotN<N>(C, C);
-                    const double phi0 = 0.5 * CC, dphi0 = -CC, armijo = nw.c1 * dphi0;
-                    int ne = 0;
-                    double al = 1.0, best_al = 1.0, best_phi = CUDART_INF;
-                    double best_C[N];
+                    for (int i = 0; i < N; ++i) best_C[i] = Ct[i];
+                }
+                const bool acc = fin && (ph <= fma(al, armijo, phi0));
+                const double den = 2.0 * (ph - phi0 - dphi0 * al);
+                const double am = (den == 0.0) ? 0.5 * al : -dphi0 * al * al / den;
+                double ac = fmin(fmax(am, nw.bmin * al), nw.bmax * al);
+                if (am != am) ac = am;                    // clip propagates NaN
+                const double al_used = al;
+                if (!acc) al = fin ? ac : 0.5 * al;
+                ++ne;
+                if (ne < nw.ls_max && !acc) {
 #pragma unroll
-                    for (int i = 0; i < N; ++i) best_C[i] = C[i];
-                    bool acc = false;
-                    double Ct[N];
-#pragma unroll
-                    for (int i = 0; i < N; ++i) Ct[i] = C[i];
-                    while (ne < nw.ls_max && !acc) {
-                        double xt[N];
-#pragma unroll
-                        for (int i = 0; i < N; ++i) xt[i] = fma(-al, dx[i], x[i]);
-                        pt.residual(m, xt, xp, em, Ct);
-                        const double ph = 0.5 * dotN<N>(Ct, Ct);
-                        const bool fin = isfinite(ph);
-                        if (fin && ph < best_phi) {
-                            best_al = al; best_phi = ph;
-#pragma unroll
-                            for (int i = 0; i < N; ++i) best_C[i] = Ct[i];
-                        }
-                        acc = fin && (ph <= fma(al, armijo, phi0));
-                        const double den = 2.0 * (ph - phi0 - dphi0 * al);
-                        const double am = (den == 0.0) ? 0.5 * al : -dphi0 * al * al / den;
-                        double ac = fmin(fmax(am, nw.bmin * al), nw.bmax * al);
-                        if (am != am) ac = am;                    // clip propagates NaN
-                        if (!acc) al = fin ? ac : 0.5 * al;
-                        ++ne;
-                    }
-                    const double ar = acc ? al : best_al;
+                    for (int i = 0; i < N; ++i) xt[i] = fma(-al, dx[i], x[i]);
+                } else {
+                    const double ar = acc ? al_used : best_al;
 #pragma unroll
                     for (int i = 0; i < N; ++i) {
                         x[i] = fma(-ar, dx[i], x[i]);
@@ -621,36 +647,66 @@ CMADX_DEV NewtonResult local_newton(const DevMat& m, const DevNewton& nw, Pt& pt
                     }
                     fresh = acc;      // the last evaluated trial is x only if it was accepted
                     ++ii;
-                    if (ii >= nw.max_iters) done = true;
+                    stepped = true;
+                }
+            } else if (phase == PH_REFRESH) {
+                need_dir = true;      // pt is fresh at x again; Ct (== C) is not needed
+            } else if (phase == PH_IMP) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) C[i] = Ct[i];
+                nc = normN<N>(C);
+                const double rel = nc / n0;
+                if (rel < nw.rel_tol || nc < nw.abs_tol) active = false; else need_dir = true;
+            } else {                  // PH_FINAL: state refreshed at the returned x
+#pragma unroll
+                for (int i = 0; i < N; ++i) C[i] = Ct[i];
+                active = false;
+            }
+            if (stepped) {
+                bool stop = ii >= nw.max_iters;
+                if (!stop) {
+                    nc = normN<N>(C);
+                    const double rel = nc / n0;
+                    stop = (rel < nw.rel_tol || nc < nw.abs_tol);
+                }
+                if (stop) {
+                    if (fresh) active = false;
+                    else phase = PH_FINAL;
+                } else if (fresh) {
+                    need_dir = true;
+                } else {
+                    phase = PH_REFRESH;
+                }
+                if (!fresh) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) xt[i] = x[i];
                 }
             }
-        }
-        nc = normN<N>(C);
-    } else {
-        // imperative newton_solve (no line search): rel := 1 on the first pass
-        while (__any_sync(full, !done)) {
-            if (!done) {
-                if (ii > 0) { pt.residual(m, x, xp, em, C); fresh = true; }
-                nc = normN<N>(C);
-                double rel = 1.0;
-                if (ii == 0) n0 = nc; else rel = nc / n0;
-                if (rel < nw.rel_tol || nc < nw.abs_tol) {
-                    done = true;
+            if (need_dir) {
+                if (traced) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) dx[i] = C[i];
+                    newton_direction<Pt, N>(m, pt, x[N - 1] - xp[N - 1], dx);   // solve(J, C)
+                    const double CC = dotN<N>(C, C);
+                    phi0 = 0.5 * CC; dphi0 = -CC; armijo = nw.c1 * dphi0;
+                    ne = 0; al = 1.0; best_al = 1.0; best_phi = CUDART_INF;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) { best_C[i] = C[i]; xt[i] = fma(-al, dx[i], x[i]); }
+                    phase = PH_PROBE;
                 } else {
-                    double dx[N];
+                    // imperative newton_solve (no line search)
 #pragma unroll
                     for (int i = 0; i < N; ++i) dx[i] = -C[i];
                     newton_direction<Pt, N>(m, pt, x[N - 1] - xp[N - 1], dx);   // solve(J, -C)
 #pragma unroll
-                    for (int i = 0; i < N; ++i) x[i] += dx[i];
-                    fresh = false;
+                    for (int i = 0; i < N; ++i) { x[i] += dx[i]; xt[i] = x[i]; }
                     ++ii;
-                    if (ii >= nw.max_iters) done = true;
+                    phase = (ii >= nw.max_iters) ? PH_FINAL : PH_IMP;
                 }
             }
         }
     }
-    if (!fresh) pt.residual(m, x, xp, em, C);
+    if (traced) nc = normN<N>(C);
     r.iters = ii;
     r.cnorm = nc;
     return r;
