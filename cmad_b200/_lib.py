@@ -150,6 +150,9 @@ def lib() -> C.CDLL:
     L.cmadx_mp_objective_direct.argtypes = obj_args
     L.cmadx_fe_block_assemble.argtypes = [C.POINTER(Material), C.POINTER(Newton),
                                           C.POINTER(FeBlock), C.c_void_p]
+    L.cmadx_fe_block_jvp.argtypes = [C.POINTER(Material), C.POINTER(C.c_int32), C.c_int32,
+                                     C.POINTER(C.c_double), C.POINTER(FeBlock), C.c_void_p,
+                                     C.c_void_p, C.c_void_p]
     L.cmadx_segment_plan_create.argtypes = [C.POINTER(C.c_int64), C.c_int64, C.c_int64,
                                             C.POINTER(C.c_void_p)]
     L.cmadx_segment_plan_destroy.argtypes = [C.c_void_p]

@@ -476,13 +476,10 @@ int cmadx_mp_objective_direct(const cmadx_material_t* mat, const int32_t* active
     return objective(mat, active_pid, n_active, hist, stream, false);
 }
 
-int cmadx_fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* newton,
-                            const cmadx_fe_block_t* blk, void* stream) {
+static int check_fe_block(const cmadx_material_t* mat, const cmadx_fe_block_t* blk, FeArgs* A) {
     if (!blk) return CMADX_EINVAL;
-    FeArgs A;
-    if (int rc = make_dev_mat(mat, &A.m)) return rc;
-    if (int rc = make_dev_newton(newton, &A.nw)) return rc;
-    if (A.m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC) return CMADX_EUNSUPPORTED;
+    if (int rc = make_dev_mat(mat, &A->m)) return rc;
+    if (A->m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC) return CMADX_EUNSUPPORTED;
     const cmadx_fe_block_t& b = *blk;
     if (b.n_elems < 0 || b.n_dofs < 0) return CMADX_EINVAL;
     if (!((b.n_basis == 4 && b.n_ip == 1) || (b.n_basis == 8 && b.n_ip == 8))) {
@@ -497,8 +494,18 @@ int cmadx_fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* n
             return CMADX_EINVAL;
         if (b.n_elems * b.n_ip >= (int64_t)0x7fffffff) return CMADX_EUNSUPPORTED;
     }
-    A.b = b;
-    A.bail_count = nullptr; A.bail_list = nullptr; A.bail_cap = 0;
+    A->b = b;
+    A->bail_count = nullptr; A->bail_list = nullptr; A->bail_cap = 0;
+    A->xi_state = nullptr; A->dxi_prev = nullptr; A->n_active = 0;
+    return CMADX_OK;
+}
+
+int cmadx_fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* newton,
+                            const cmadx_fe_block_t* blk, void* stream) {
+    FeArgs A;
+    if (int rc = check_fe_block(mat, blk, &A)) return rc;
+    if (int rc = make_dev_newton(newton, &A.nw)) return rc;
+    const cmadx_fe_block_t& b = *blk;
     if (b.n_elems == 0) return CMADX_OK;
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e;
@@ -518,6 +525,32 @@ int cmadx_fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* n
     } else {
         e = launch_fe_block(A, false, s);
     }
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return CMADX_OK;
+}
+
+int cmadx_fe_block_jvp(const cmadx_material_t* mat, const int32_t* active_pid, int32_t n_active,
+                       const double* dp_host, const cmadx_fe_block_t* blk,
+                       const double* xi_state, const double* dxi_prev, void* stream) {
+    FeArgs A;
+    if (int rc = check_fe_block(mat, blk, &A)) return rc;
+    if (blk->K_elem) return CMADX_EINVAL;
+    if (n_active < 0 || n_active > CMADX_MAX_ACTIVE || (n_active > 0 && (!active_pid || !dp_host))) return CMADX_EINVAL;
+    for (int c = 0; c < n_active; ++c) {
+        const int pid = active_pid[c];
+        if (pid < 0 || pid >= CMADX_NUM_PARAM_IDS) return CMADX_EINVAL;
+        if (pid == CMADX_P_HOSFORD_A || pid >= CMADX_P_Q00) return CMADX_EUNSUPPORTED;
+        A.pid[c] = pid;
+        A.dp[c] = dp_host[c];
+    }
+    A.n_active = n_active;
+    if (blk->n_elems == 0) return CMADX_OK;
+    if (!xi_state) return CMADX_EINVAL;
+    A.xi_state = xi_state;
+    A.dxi_prev = dxi_prev;
+    std::memset(&A.nw, 0, sizeof(A.nw));
+    cudaError_t e = launch_fe_block_jvp(A, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return CMADX_OK;

@@ -39,6 +39,14 @@ cudaError_t launch_fe_block(const FeArgs& A, bool j2_radial, cudaStream_t stream
                               : launch_fe_hex8(A, solver, false, stream, 0);
 }
 
+// K6: JVP at a given state (solver 4 + yield kind), residual-shaped outputs only
+cudaError_t launch_fe_block_jvp(const FeArgs& A, cudaStream_t stream) {
+    if (A.b.n_elems == 0) return cudaSuccess;
+    const int solver = 4 + A.m.yield;
+    return (A.b.n_basis == 4) ? launch_fe_tet4(A, solver, false, stream, 0)
+                              : launch_fe_hex8(A, solver, false, stream, 0);
+}
+
 // generic J2 kernel over the elements the radial kernel handed back
 cudaError_t launch_fe_block_list(const FeArgs& A, cudaStream_t stream) {
     if (A.b.n_elems == 0) return cudaSuccess;

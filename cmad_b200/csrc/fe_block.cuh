@@ -12,9 +12,16 @@ struct FeArgs {
     unsigned* bail_count;
     int* bail_list;
     unsigned bail_cap;
+    // K6 (JVP at a given state): converged local state, input tangents
+    const double* xi_state;   // [n_elems][n_ip][7]
+    const double* dxi_prev;   // [n_elems][n_ip][7] or NULL (= 0)
+    double dp[CMADX_MAX_ACTIVE];
+    int pid[CMADX_MAX_ACTIVE];
+    int n_active;
 };
 
 cudaError_t launch_fe_block(const FeArgs& A, bool j2_radial, cudaStream_t stream);
 cudaError_t launch_fe_block_list(const FeArgs& A, cudaStream_t stream);
+cudaError_t launch_fe_block_jvp(const FeArgs& A, cudaStream_t stream);
 
 }  // namespace cmadx

@@ -7,6 +7,7 @@
 
 #include "fe_block.cuh"
 #include "j2_radial.cuh"
+#include "mp_outputs.cuh"
 
 namespace cmadx {
 namespace {
@@ -209,7 +210,100 @@ CMADX_DEV void point_generic(const DevMat& m, const DevNewton& nw, const double 
     }
 }
 
-// SOLVER: 0 = J2 radial return (may bail), 1 + YK = generic Newton for yield surface YK
+// ---- K6: tangent (JVP) of the converged point w.r.t. (params, xi_prev) at fixed strain
+// What jax.jvp pushes through make_newton_solve's custom_jvp rule for the FE
+// sensitivities (cmad/models/nonlinear_solver.py:158-171 called from
+// cmad/fem/nonlinear_solver.py:490-537):  dxi = -A^{-1} (dC/dp dp + dC/dxi_prev dxi_prev),
+// d sigma = d cauchy/dxi dxi + d cauchy/dp dp, evaluated AT the given converged state.
+template <int YK, bool ROT>
+CMADX_DEV void point_jvp(const FeArgs& A, const double (&xp)[7], const double (&xs)[7],
+                         const double (&dxp)[7], const double (&e)[6], bool live, PointOut& o) {
+    const DevMat& m = A.m;
+    double em[6];
+    if (ROT) {
+        double T[6][6], S[6][6];
+        rot_maps(m.Q, T, S);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) s = fma(T[c][b], e[b], s);
+            em[c] = s;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) em[c] = e[c];
+    }
+    SepPoint<YK> pt;
+    double Cs[7];
+    pt.residual(m, xs, xp, em, Cs);
+    const bool pl = pt.plastic;
+    const double dg = xs[6] - xp[6];
+    double ee[6], sig[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) ee[a] = em[a] - xs[a];
+    const double tre = ee[0] + ee[3] + ee[5];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) sig[a] = is_diag(a) ? fma(m.two_mu, ee[a], m.lam * tre) : m.two_mu * ee[a];
+    double Mee[6], nee = 0.0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        double s = 0.0;
+#pragma unroll
+        for (int b = 0; b < 6; ++b) s = fma(pt.yf.M(a, b), ee[b], s);
+        Mee[a] = s;
+        nee = fma(mult(a) * pt.n[a], ee[a], nee);
+    }
+    double rhs[7], dlam = 0.0, dmu = 0.0;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) rhs[r] = 0.0;
+    for (int c = 0; c < A.n_active; ++c) {
+        double col[7];
+        dC_dp_column(m, A.pid[c], pl, pt.yf, pt.n, pt.f, pt.eD, xs[6], dg, Mee, nee, sig, col);
+#pragma unroll
+        for (int r = 0; r < 7; ++r) rhs[r] = fma(col[r], A.dp[c], rhs[r]);
+        if (A.pid[c] == CMADX_P_EL0 || A.pid[c] == CMADX_P_EL1) {
+            dlam = fma(m.dlam[A.pid[c] - CMADX_P_EL0], A.dp[c], dlam);
+            dmu = fma(m.dmu[A.pid[c] - CMADX_P_EL0], A.dp[c], dmu);
+        }
+    }
+    // + dC/dxi_prev dxi_prev: plastic rows a<6: -I and +n in the alpha column, yield row 0; elastic: -I
+#pragma unroll
+    for (int a = 0; a < 6; ++a) rhs[a] += pl ? fma(pt.n[a], dxp[6], -dxp[a]) : -dxp[a];
+    rhs[6] += pl ? 0.0 : -dxp[6];
+    newton_direction<SepPoint<YK>, 7>(m, pt, dg, rhs);          // rhs <- A^{-1} rhs
+#pragma unroll
+    for (int r = 0; r < 7; ++r) o.x[r] = live ? -rhs[r] : 0.0;
+    // d sigma (material axes) = Cel (-d ep) + (d lam tr(ee) I + 2 d mu ee)
+    const double trd = -(o.x[0] + o.x[3] + o.x[5]);
+    double ds[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        const double v = fma(2.0 * dmu, ee[a], -m.two_mu * o.x[a]);
+        ds[a] = is_diag(a) ? v + fma(m.lam, trd, dlam * tre) : v;
+    }
+    if (ROT) {
+        double T[6][6], S[6][6];
+        rot_maps(m.Q, T, S);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) s = fma(S[a][c], ds[c], s);
+            o.sg[a] = s;
+        }
+    } else {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) o.sg[a] = ds[a];
+    }
+    o.bail = false;
+    o.iters = 0;
+    o.flags = pl ? 3 : 0;
+}
+
+// SOLVER: 0 = J2 radial return (may bail), 1 + YK = generic Newton for yield surface YK,
+// 4 + YK = K6 (JVP at a given state; handled by the kernels through point_jvp)
+constexpr int FE_JVP = 4;
 template <int SOLVER, bool ROT, bool WANT_D>
 CMADX_DEV void solve_point(const DevMat& m, const DevNewton& nw, const double (&xp)[7],
                            const double (&e)[6], bool live, PointOut& o, double (&D)[6][6]) {
@@ -258,6 +352,9 @@ cudaError_t dispatch_fe(const FeArgs& A, int solver, cudaStream_t stream, int sm
         CMADX_FE_CASE(1)
         CMADX_FE_CASE(2)
         CMADX_FE_CASE(3)
+    case 4: return rot ? Launcher<4, true, false, LIST>::run(A, stream, sms) : Launcher<4, false, false, LIST>::run(A, stream, sms);
+    case 5: return rot ? Launcher<5, true, false, LIST>::run(A, stream, sms) : Launcher<5, false, false, LIST>::run(A, stream, sms);
+    case 6: return rot ? Launcher<6, true, false, LIST>::run(A, stream, sms) : Launcher<6, false, false, LIST>::run(A, stream, sms);
     }
 #undef CMADX_FE_CASE
     return cudaErrorInvalidValue;

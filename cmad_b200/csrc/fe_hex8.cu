@@ -119,7 +119,18 @@ CMADX_DEV void hex8_point(const FeArgs& A, const int64_t e, const bool live, dou
     // ---- phase B: local Newton at this point
     PointOut o;
     double D[6][6];
-    solve_point<SOLVER, ROT, WANT_K>(A.m, A.nw, xp, eps, live, o, D);
+    if constexpr (SOLVER >= FE_JVP) {
+        double xs[7], dxp[7];
+        const int64_t p = e * 8 + ip;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            xs[c] = live ? __ldg(A.xi_state + p * 7 + c) : 0.0;
+            dxp[c] = (live && A.dxi_prev) ? __ldg(A.dxi_prev + p * 7 + c) : 0.0;
+        }
+        point_jvp<SOLVER - FE_JVP, ROT>(A, xp, xs, dxp, eps, live, o);
+    } else {
+        solve_point<SOLVER, ROT, WANT_K>(A.m, A.nw, xp, eps, live, o, D);
+    }
 
     // an element is handed to the generic kernel as a whole
     bool ebail = false;

@@ -42,7 +42,17 @@ CMADX_DEV void tet4_element(const FeArgs& A, const int64_t e, const bool live) {
 
     PointOut o;
     double D[6][6];
-    solve_point<SOLVER, ROT, WANT_K>(A.m, A.nw, xp, eps, live, o, D);
+    if constexpr (SOLVER >= FE_JVP) {
+        double xs[7], dxp[7];
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            xs[c] = live ? __ldg(A.xi_state + e * 7 + c) : 0.0;
+            dxp[c] = (live && A.dxi_prev) ? __ldg(A.dxi_prev + e * 7 + c) : 0.0;
+        }
+        point_jvp<SOLVER - FE_JVP, ROT>(A, xp, xs, dxp, eps, live, o);
+    } else {
+        solve_point<SOLVER, ROT, WANT_K>(A.m, A.nw, xp, eps, live, o, D);
+    }
     if (!live) return;
     if (SOLVER == 0 && o.bail) { append_bail(A, e); return; }
 

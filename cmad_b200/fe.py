@@ -160,6 +160,51 @@ def assemble_element_block_residual(material, newton, arrays, U_global, xi_prev_
     return r_plan.sum(o["R_elem"].reshape(-1), stream=stream) if r_plan is not None else o["R_global"]
 
 
+def fe_block_jvp(material: L.Material, arrays: FEBlockArrays, U_global: torch.Tensor,
+                 xi_prev: torch.Tensor, xi_state: torch.Tensor, active_pid, dp,
+                 dxi_prev: torch.Tensor | None = None, outputs=("xi", "R_elem"), out: dict | None = None,
+                 stream: torch.cuda.Stream | None = None) -> dict:
+    """K6: tangent of the converged block w.r.t. (params, xi_prev) at fixed ``U``:
+    returns ``out["xi"]`` = ``dxi (n_e, n_ip, 7)`` and ``out["R_elem"]`` = ``dR_e``
+    (or ``R_global``) for the direction ``dp`` (native values of the active
+    parameters, in ``active_pid`` order) and ``dxi_prev``.  What ``jax.jvp`` pushes
+    through the assembled residual inside the FE Newton's IFT rule
+    (cmad/fem/nonlinear_solver.py:490-537)."""
+    n_e, n_b, n_ip = arrays.n_elems, arrays.n_basis, arrays.n_ip
+    dev = arrays.grad_N.device
+    if dev.type != "cuda":
+        raise ValueError("FE block arrays must live on a CUDA device (there is no CPU fallback)")
+    for name, t in (("xi_prev", xi_prev), ("xi_state", xi_state), ("dxi_prev", dxi_prev)):
+        if t is None:
+            continue
+        if t.dtype != torch.float64 or tuple(t.shape) != (n_e, n_ip, 7) or not t.is_contiguous():
+            raise ValueError(f"{name}: expected contiguous float64 ({n_e}, {n_ip}, 7)")
+    if U_global.dtype != torch.float64 or U_global.numel() != arrays.n_dofs or not U_global.is_contiguous():
+        raise ValueError(f"U_global: expected contiguous float64 ({arrays.n_dofs},)")
+    pid = np.ascontiguousarray(active_pid, dtype=np.int32)
+    dpv = np.ascontiguousarray(dp, dtype=np.float64)
+    if pid.shape != dpv.shape or pid.ndim != 1:
+        raise ValueError("dp must have one entry per active parameter")
+    shapes = {"xi": ((n_e, n_ip, 7), torch.float64), "R_elem": ((n_e, n_b * 3), torch.float64),
+              "R_global": ((arrays.n_dofs,), torch.float64)}
+    out = dict(out) if out is not None else {}
+    for name in set(outputs) | {"xi"}:
+        if name not in shapes:
+            raise ValueError(f"unknown JVP output {name!r}")
+        if out.get(name) is None:
+            shape, dt = shapes[name]
+            out[name] = (torch.zeros if name == "R_global" else torch.empty)(shape, dtype=dt, device=dev)
+    b = _fe_struct(arrays, U_global, xi_prev, out)
+    s = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        rc = L.lib().cmadx_fe_block_jvp(
+            C.byref(material), pid.ctypes.data_as(C.POINTER(C.c_int32)), len(pid),
+            dpv.ctypes.data_as(C.POINTER(C.c_double)), C.byref(b), C.c_void_p(xi_state.data_ptr()),
+            C.c_void_p(dxi_prev.data_ptr()) if dxi_prev is not None else None, C.c_void_p(s.cuda_stream))
+    L.check(rc, "cmadx_fe_block_jvp")
+    return out
+
+
 def partition_block(arrays: FEBlockArrays, rank: int, world: int) -> tuple[FEBlockArrays, tuple[int, int]]:
     """This rank's contiguous element range of a block (the path shards by element:
     every element's local state, K_e and R_e are computed by exactly one rank)."""

@@ -263,6 +263,21 @@ typedef struct cmadx_fe_block {
 int cmadx_fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* newton,
                             const cmadx_fe_block_t* blk, void* stream);
 
+/* ---- K6: forward sensitivities (JVP) of the element block at a converged state --------
+ * For a tangent direction (dp over the active parameters, dxi_prev per point) at FIXED U:
+ *   dxi = -A^{-1} (dC/dp dp + dC/dxi_prev dxi_prev),  A = dC/dxi at (xi_state, xi_prev),
+ *   dR_e = sum_ip gradN (dcauchy/dxi dxi + dcauchy/dp dp) w dv.
+ * This is what jax.jvp of the assembled residual w.r.t. (params, xi_prev) pushes through
+ * make_newton_solve's custom_jvp rule (cmad/models/nonlinear_solver.py:158-171) inside the
+ * FE Newton's IFT rule (cmad/fem/nonlinear_solver.py:490-537), and the per-step body of a
+ * direct FE sensitivity recurrence.  `blk` as in cmadx_fe_block_assemble with
+ * K_elem == NULL; blk->xi receives dxi, blk->R_elem / R_global receive dR.
+ * xi_state: the converged local state [n_elems][n_ip][7] (the `xi` output of the primal
+ * call); dxi_prev: [n_elems][n_ip][7] or NULL (zero); dp_host: n_active doubles (host).  */
+int cmadx_fe_block_jvp(const cmadx_material_t* mat, const int32_t* active_pid, int32_t n_active,
+                       const double* dp_host, const cmadx_fe_block_t* blk,
+                       const double* xi_state, const double* dxi_prev, void* stream);
+
 /* ---- K5: deterministic segment sums (R scatter-add, COO dedup) -----------------
  * out[s] = sum of vals[i] over all items i with seg_of_item[i] == s, summed in
  * increasing item order (bit-reproducible, and the order a sequential

