@@ -12,6 +12,9 @@
 #include "mp_update.cuh"
 
 namespace cmadx {
+int64_t fe_vjp_blocks(int64_t npts);
+cudaError_t launch_fe_block_vjp(const FeArgs& A, const double* Rbar, const double* xibar, double* partials,
+                                double* pbar, cudaStream_t s);
 struct SensArgs {
     DevMat m;
     int n_active;
@@ -553,6 +556,35 @@ int cmadx_fe_block_jvp(const cmadx_material_t* mat, const int32_t* active_pid, i
     cudaError_t e = launch_fe_block_jvp(A, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    return CMADX_OK;
+}
+
+int64_t cmadx_fe_vjp_workspace_bytes(int64_t n_elems, int32_t n_ip, int32_t n_active) {
+    if (n_elems < 0 || n_ip < 1 || n_active < 0 || n_active > CMADX_MAX_ACTIVE) return -1;
+    return (int64_t)sizeof(double) * (fe_vjp_blocks(n_elems * n_ip) + 1) * (n_active > 0 ? n_active : 1);
+}
+
+int cmadx_fe_block_vjp(const cmadx_material_t* mat, const int32_t* active_pid, int32_t n_active,
+                       const cmadx_fe_block_t* blk, const double* xi_state,
+                       const double* Rbar_global, const double* xibar, double* pbar_dev,
+                       double* workspace, void* stream) {
+    FeArgs A;
+    if (int rc = check_fe_block(mat, blk, &A)) return rc;
+    if (n_active < 0 || n_active > CMADX_MAX_ACTIVE || (n_active > 0 && (!active_pid || !pbar_dev || !workspace)))
+        return CMADX_EINVAL;
+    for (int c = 0; c < n_active; ++c) {
+        const int pid = active_pid[c];
+        if (pid < 0 || pid >= CMADX_NUM_PARAM_IDS) return CMADX_EINVAL;
+        if (pid == CMADX_P_HOSFORD_A || pid >= CMADX_P_Q00) return CMADX_EUNSUPPORTED;
+        A.pid[c] = pid;
+    }
+    A.n_active = n_active;
+    if (blk->n_elems > 0 && (!xi_state || !Rbar_global)) return CMADX_EINVAL;
+    A.xi_state = xi_state;
+    std::memset(&A.nw, 0, sizeof(A.nw));
+    cudaError_t e = launch_fe_block_vjp(A, Rbar_global, xibar, workspace, pbar_dev, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
     return CMADX_OK;
 }
 

@@ -274,6 +274,12 @@ cudaError_t launch_sens_t(const SensArgs& A, cudaStream_t stream) {
 
 }  // namespace
 
+cudaError_t launch_reduce_partials(const double* partials, int64_t nblk, int ncols, double* result,
+                                   cudaStream_t stream) {
+    reduce_partials_kernel<<<1, 256, 0, stream>>>(partials, nblk, ncols, result);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mp_sens(const SensArgs& A, bool adjoint, cudaStream_t stream) {
     if (A.h.n == 0) return cudaMemsetAsync(A.h.result, 0, sizeof(double) * (1 + A.n_active), stream);
     return adjoint ? launch_sens_t<true>(A, stream) : launch_sens_t<false>(A, stream);

@@ -205,6 +205,47 @@ def fe_block_jvp(material: L.Material, arrays: FEBlockArrays, U_global: torch.Te
     return out
 
 
+def fe_block_vjp(material: L.Material, arrays: FEBlockArrays, U_global: torch.Tensor,
+                 xi_prev: torch.Tensor, xi_state: torch.Tensor, active_pid, Rbar: torch.Tensor,
+                 xibar: torch.Tensor | None = None, group=None,
+                 stream: torch.cuda.Stream | None = None) -> tuple[torch.Tensor, torch.Tensor]:
+    """K6 reverse mode: ``(pbar (n_active,), xibar_prev (n_e, n_ip, 7))`` for the cotangents
+    ``Rbar (n_dofs,)`` of the assembled residual and ``xibar`` of the converged local
+    state - one step of a discrete FE adjoint, the transpose of :func:`fe_block_jvp`.
+    Under ``torch.distributed`` (element partition) ``pbar`` is all-reduced: the gradient
+    exchange of the calibration loop."""
+    n_e, n_ip = arrays.n_elems, arrays.n_ip
+    dev = arrays.grad_N.device
+    if dev.type != "cuda":
+        raise ValueError("FE block arrays must live on a CUDA device (there is no CPU fallback)")
+    for name, t in (("xi_prev", xi_prev), ("xi_state", xi_state), ("xibar", xibar)):
+        if t is not None and (t.dtype != torch.float64 or tuple(t.shape) != (n_e, n_ip, 7) or not t.is_contiguous()):
+            raise ValueError(f"{name}: expected contiguous float64 ({n_e}, {n_ip}, 7)")
+    for name, t in (("U_global", U_global), ("Rbar", Rbar)):
+        if t.dtype != torch.float64 or t.numel() != arrays.n_dofs or not t.is_contiguous():
+            raise ValueError(f"{name}: expected contiguous float64 ({arrays.n_dofs},)")
+    pid = np.ascontiguousarray(active_pid, dtype=np.int32)
+    na = len(pid)
+    out = {"xi": torch.empty((n_e, n_ip, 7), dtype=torch.float64, device=dev)}
+    b = _fe_struct(arrays, U_global, xi_prev, out)
+    pbar = torch.zeros((max(na, 1),), dtype=torch.float64, device=dev)
+    wsb = int(L.lib().cmadx_fe_vjp_workspace_bytes(n_e, n_ip, na))
+    ws = torch.empty((max(wsb // 8, 1),), dtype=torch.float64, device=dev)
+    s = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        rc = L.lib().cmadx_fe_block_vjp(
+            C.byref(material), pid.ctypes.data_as(C.POINTER(C.c_int32)), na, C.byref(b),
+            C.c_void_p(xi_state.data_ptr()), C.c_void_p(Rbar.data_ptr()),
+            C.c_void_p(xibar.data_ptr()) if xibar is not None else None,
+            C.c_void_p(pbar.data_ptr()), C.c_void_p(ws.data_ptr()), C.c_void_p(s.cuda_stream))
+    L.check(rc, "cmadx_fe_block_vjp")
+    pbar = pbar[:na]
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(pbar, op=dist.ReduceOp.SUM, group=group)
+    return pbar, out["xi"]
+
+
 def partition_block(arrays: FEBlockArrays, rank: int, world: int) -> tuple[FEBlockArrays, tuple[int, int]]:
     """This rank's contiguous element range of a block (the path shards by element:
     every element's local state, K_e and R_e are computed by exactly one rank)."""

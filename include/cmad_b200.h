@@ -278,6 +278,20 @@ int cmadx_fe_block_jvp(const cmadx_material_t* mat, const int32_t* active_pid, i
                        const double* dp_host, const cmadx_fe_block_t* blk,
                        const double* xi_state, const double* dxi_prev, void* stream);
 
+/* Reverse mode (VJP), the transpose of cmadx_fe_block_jvp: given the cotangent Rbar of the
+ * assembled residual (a nodal adjoint vector, [n_dofs]) and the cotangent xibar of the
+ * converged local state ([n_elems][n_ip][7] or NULL), computes
+ *   pbar[c] = sum over points of (dC/dp)^T mu + (dcauchy/dp)^T sbar   (device, n_active),
+ *   blk->xi := xibar_prev = (dC/dxi_prev)^T mu,     mu = -A^{-T}(xibar + (dcauchy/dxi)^T sbar),
+ * i.e. one step of a discrete FE adjoint (what jax.grad obtains by transposing the JVP
+ * above, cmad/cli/gradient.py:74-82).  pbar is reduced in fixed order (bit-reproducible);
+ * `workspace` needs cmadx_fe_vjp_workspace_bytes().  K_elem/R_elem/R_global are ignored. */
+int64_t cmadx_fe_vjp_workspace_bytes(int64_t n_elems, int32_t n_ip, int32_t n_active);
+int cmadx_fe_block_vjp(const cmadx_material_t* mat, const int32_t* active_pid, int32_t n_active,
+                       const cmadx_fe_block_t* blk, const double* xi_state,
+                       const double* Rbar_global, const double* xibar, double* pbar_dev,
+                       double* workspace, void* stream);
+
 /* ---- K5: deterministic segment sums (R scatter-add, COO dedup) -----------------
  * out[s] = sum of vals[i] over all items i with seg_of_item[i] == s, summed in
  * increasing item order (bit-reproducible, and the order a sequential

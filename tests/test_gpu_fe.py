@@ -267,3 +267,58 @@ def test_block_jvp_vs_oracle(cuda_device, family, kind):
 def _lib_pid_q00():
     from cmad_b200 import _lib
     return _lib.P_Q00
+
+
+@pytest.mark.parametrize("family", ["tet4", "hex8"])
+@pytest.mark.parametrize("kind", ["J2", "hill-rotated", "hosford"])
+def test_block_vjp_is_the_transpose_of_the_jvp(cuda_device, family, kind):
+    """K6 reverse mode against the ORACLE's JVP through the adjoint identity
+    <Rbar, dR> + <xibar, dxi> == <pbar, dp> + <xibar_prev, dxi_prev> for random directions
+    and cotangents, plus bit-reproducibility of the reduced parameter gradient."""
+    from cmad_b200 import Parameters, active_param_ids
+    if kind == "J2":
+        values, act, tr = param_tree("J2", active=("E", "nu", "D", "S", "Y"))
+    elif kind == "hosford":
+        values, act, tr = param_tree("hosford", a=6.0, active=("E", "nu", "D", "S", "Y"))
+    else:
+        values, act, tr = param_tree("hill", hill=(0.45, 0.55, 0.5, 1.4, 1.5, 1.6),
+                                     active=("E", "nu", "D", "S", "Y") + tuple("FGHLMN"),
+                                     rotation=rotation_matrix([1.0, 2.0, -0.5], 0.7))
+    P = Parameters(values, act, tr)
+    pid = active_param_ids(P)
+    nodes, conn = _mesh(family, (3, 2, 2))
+    arr_h = fe_mesh.block_arrays(nodes, conn); arr = arr_h.to(cuda_device)
+    mat = material_from_values(values)
+    nw = fe.fe_newton_settings(**NEWTON)
+    rng = np.random.default_rng(7)
+    n_e, n_ip = arr.n_elems, arr.n_ip
+    U1 = torch.from_numpy(fe_mesh.synthetic_displacement(nodes, 1.0, seed=1, ramp=0.004, noise=4e-4)).to(cuda_device)
+    U2 = torch.from_numpy(fe_mesh.synthetic_displacement(nodes, 2.0, seed=2, ramp=0.004, noise=4e-4)).to(cuda_device)
+    xi0 = torch.zeros((n_e, n_ip, 7), dtype=torch.float64, device=cuda_device)
+    xi1 = fe.fe_block_launch(mat, nw, arr, U1, xi0, ("xi",))["xi"]
+    prim = fe.fe_block_launch(mat, nw, arr, U2, xi1, ("xi", "flags"))
+    assert bool((prim["flags"] & 2).any())
+    Rbar = torch.from_numpy(rng.standard_normal(arr.n_dofs)).to(cuda_device)
+    xibar = torch.from_numpy(rng.standard_normal((n_e, n_ip, 7))).to(cuda_device)
+    pbar, xbp = fe.fe_block_vjp(mat, arr, U2, xi1, prim["xi"], pid, Rbar, xibar)
+    pbar2, xbp2 = fe.fe_block_vjp(mat, arr, U2, xi1, prim["xi"], pid, Rbar, xibar)
+    torch.cuda.synchronize()
+    assert torch.equal(pbar, pbar2) and torch.equal(xbp, xbp2)
+    prob_eval = oc.describe(values, P.active_idx, newton_mode="imperative", strain_comps=9, max_iters=0)
+    geo = (arr_h.grad_N.numpy(), arr_h.det.numpy(), arr_h.quad_w.numpy())
+    eq = arr_h.elem_eq.numpy()
+    scale = np.array([3e3, 0.01, 1.5, 7.0, 4.0] + [0.05] * (len(pid) - 5))
+    for trial in range(3):
+        dp = rng.standard_normal(len(pid)) * scale
+        dxp = 1e-4 * rng.standard_normal((n_e, n_ip, 7))
+        jv = fe_oracle.block_jvp(prob_eval, eq, U2.cpu().numpy(), xi1.cpu().numpy(), prim["xi"].cpu().numpy(),
+                                 *geo, dp, dxp)
+        dR = np.zeros(arr.n_dofs); np.add.at(dR, eq.reshape(-1), jv["R_elem"].reshape(-1))
+        lhs = float(Rbar.cpu().numpy() @ dR + (xibar.cpu().numpy() * jv["xi"]).sum())
+        rhs = float(pbar.cpu().numpy() @ dp + (xbp.cpu().numpy() * dxp).sum())
+        terms = abs(Rbar.cpu().numpy() @ dR) + abs((xibar.cpu().numpy() * jv["xi"]).sum())
+        assert abs(lhs - rhs) < 1e-9 * terms, (trial, lhs, rhs)
+    # without a state cotangent, and with no active parameters
+    pbar0, xbp0 = fe.fe_block_vjp(mat, arr, U2, xi1, prim["xi"], pid, Rbar, None)
+    pnone, xbpn = fe.fe_block_vjp(mat, arr, U2, xi1, prim["xi"], [], Rbar, None)
+    assert pnone.numel() == 0 and torch.equal(xbp0, xbpn)
