@@ -200,4 +200,42 @@ CMADX_DEV J2Tangent j2_tangent_coeffs(const DevMat& m, const J2Radial& r) {
     return t;
 }
 
+// b <- A^{-1} b for the J2 Jacobian dC/dxi at the state held by `pt` (any state, not
+// only a converged one): A = [[I + beta(Pdev - s^ (W s^)^T), -n], [-(W n)^T, -h]] with
+// beta = dgamma 2mu sqrt(3/2)/||s||, n = sqrt(3/2) s^.  Splitting the strain-like part of
+// b into its spherical part, its component y along s^ and the deviatoric remainder
+// b_perp gives  alpha = -(b_a + sqrt(3/2) s^:b)/(3/2 + h),  y = s^:b + sqrt(3/2) alpha,
+// e = sph(b) + y s^ + b_perp/(1 + beta).  Elastic branch: A = I.
+// With TRANSPOSED the system is A^T: in the packed representation A = T W (T symmetric,
+// W = diag(1,2,2,1,2,1,1)), so A^{-T} c = W A^{-1} W^{-1} c.
+template <bool TRANSPOSED>
+CMADX_DEV void j2_jacobian_solve(const DevMat& m, const SepPoint<CMADX_YIELD_J2>& pt, double dg,
+                                 double (&b)[7]) {
+    if (!pt.plastic) return;
+    if (TRANSPOSED) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) b[a] *= is_diag(a) ? 1.0 : 0.5;
+    }
+    const double beta = dg * m.two_mu * pt.yf.c;
+    const double h = j2_hardening_slope(m, pt.eD);
+    double sb = 0.0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) sb = fma(mult(a) * pt.yf.sh[a], b[a], sb);
+    const double sph = (b[0] + b[3] + b[5]) / 3.0;
+    const double alpha = -(b[6] + R32 * sb) / (1.5 + h);
+    const double y = fma(R32, alpha, sb);
+    const double ib = 1.0 / (1.0 + beta);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        const double dev = is_diag(a) ? b[a] - sph : b[a];
+        const double perp = fma(-pt.yf.sh[a], sb, dev);
+        b[a] = fma(pt.yf.sh[a], y, perp * ib) + (is_diag(a) ? sph : 0.0);
+    }
+    b[6] = alpha;
+    if (TRANSPOSED) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) b[a] *= mult(a);
+    }
+}
+
 }  // namespace cmadx

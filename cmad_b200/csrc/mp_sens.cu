@@ -13,6 +13,7 @@
 // Replaces (reference file:line): cmad/objectives/mp_objective.py:92-147
 // (MPAdjointObjective), :150-215 (MPDirectObjective), with the QoI of
 // cmad/qois/calibration.py:56-66.
+#include "j2_radial.cuh"
 #include "mp_outputs.cuh"
 
 namespace cmadx {
@@ -136,22 +137,12 @@ mp_sens_kernel(const __grid_constant__ SensArgs A) {
             Mee[a] = sacc;
             nee = fma(mult(a) * pt.n[a], ee[a], nee);
         }
-        RegLU<7> lu;
-        if (ADJOINT) {
-            double Jm[7][7];
-            pt.jacobian(m, dg, Jm);
-#pragma unroll
-            for (int a = 0; a < 7; ++a)
-#pragma unroll
-                for (int b = 0; b < 7; ++b) lu.a[a][b] = Jm[b][a];
-        } else {
-            pt.jacobian(m, dg, lu.a);
-        }
-        // threshold pivoting as in the Newton kernels (RegLU): natural order is
-        // stable for these (row-/column-scaled SPD + border) matrices
-        bool trouble = lu.factor_natural();
-        const bool slow = __any_sync(__activemask(), trouble);
-        if (slow && trouble) {
+        // J2: closed-form solve with the Jacobian (j2_radial.cuh) - no LU at all.
+        // Other surfaces: threshold-pivoted register LU as in the Newton kernels.
+        constexpr bool CLOSED = (YK == CMADX_YIELD_J2);
+        RegLU<CLOSED ? 1 : 7> lu;
+        bool trouble = false, slow = false;
+        if constexpr (!CLOSED) {
             if (ADJOINT) {
                 double Jm[7][7];
                 pt.jacobian(m, dg, Jm);
@@ -162,13 +153,35 @@ mp_sens_kernel(const __grid_constant__ SensArgs A) {
             } else {
                 pt.jacobian(m, dg, lu.a);
             }
-            lu.factor_pivot();
+            // natural order is stable for these (row-/column-scaled SPD + border) matrices
+            trouble = lu.factor_natural();
+            slow = __any_sync(__activemask(), trouble);
+            if (slow && trouble) {
+                if (ADJOINT) {
+                    double Jm[7][7];
+                    pt.jacobian(m, dg, Jm);
+#pragma unroll
+                    for (int a = 0; a < 7; ++a)
+#pragma unroll
+                        for (int b = 0; b < 7; ++b) lu.a[a][b] = Jm[b][a];
+                } else {
+                    pt.jacobian(m, dg, lu.a);
+                }
+                lu.factor_pivot();
+            }
         }
+        auto solve7 = [&](double (&v)[7]) {
+            if constexpr (CLOSED) {
+                j2_jacobian_solve<ADJOINT>(m, pt, dg, v);
+            } else {
+                if (slow && trouble) lu.solve_pivot(v); else lu.solve_natural(v);
+            }
+        };
         if (ADJOINT) {
             double phi[7];
 #pragma unroll
             for (int c = 0; c < 7; ++c) phi[c] = hist[c] - dJdx[c];
-            if (slow && trouble) lu.solve_pivot(phi); else lu.solve_natural(phi);
+            solve7(phi);
             // h <- -B^T phi
             double nphi = 0.0;
 #pragma unroll
@@ -198,7 +211,7 @@ mp_sens_kernel(const __grid_constant__ SensArgs A) {
 #pragma unroll
                 for (int q = 0; q < 6; ++q) rhs[q] = -col[q] + X[q][c] - (pl ? pt.n[q] * x6 : 0.0);
                 rhs[6] = -col[6] + (pl ? 0.0 : x6);
-                if (slow && trouble) lu.solve_pivot(rhs); else lu.solve_natural(rhs);
+                solve7(rhs);
                 double acc = 0.0;
 #pragma unroll
                 for (int q = 0; q < 7; ++q) { X[q][c] = rhs[q]; acc = fma(dJdx[q], rhs[q], acc); }
