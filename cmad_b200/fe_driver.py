@@ -1,0 +1,201 @@
+"""Quasi-static FE driver on top of the element-block kernels: global Newton with the
+embedded Dirichlet treatment and cubic backtracking line search, and the load-step
+loop with a step-QoI - the direct callers of the hot path.
+
+Host-side Python like the reference's; mirrors, with the same settings keys and defaults:
+
+  ``fe_newton_solve``        cmad/fem/nonlinear_solver.py:188-293 (``_fe_newton_primal``)
+  embedded BCs               cmad/fem/sparse_solve.py:1058-1174 (``_embedded_bc_enforce``,
+                             ``_embedded_residual``)
+  line search (cubic model)  cmad/util/line_search.py:49-71, 95-189
+  ``fe_quasistatic_drive``   cmad/fem/driver.py:103-146 (scan over load steps)
+  ``FEDisplacementL2``       cmad/qois/fe_displacement_l2.py:78-125
+
+Every assembly (the Newton iterates AND the line-search probes) is one K3 + K5 call on
+the device through ``assemble``; the sparse linear solve is the reference's default
+``direct`` solver - SciPy SuperLU on the host (cmad/fem/sparse_solve.py:89, reached
+there through ``jax.pure_callback``) - and, like every global sparse solver of the
+reference, is outside the B200 path.  The driver is written against an
+``assemble(U, xi_prev) -> (R, K_data, xi)`` callable so that the tests can run the very
+same loop over the CPU oracle.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Sequence
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+DEFAULT_LINE_SEARCH = {"max evals": 4, "sufficient decrease": 1.0e-4,
+                       "min backtrack factor": 0.5, "max backtrack factor": 0.9}
+# _FE_RESIDUALS_DEFAULTS["global residual"], cmad/io/deck.py:57-70
+DEFAULT_NONLINEAR = {"max iters": 10, "abs tol": 1.0e-12, "rel tol": 1.0e-12,
+                     "line search": DEFAULT_LINE_SEARCH}
+
+
+def cubic_min(phi_0, dphi_0, a, phi, slope_a):
+    """line_search.py:49-71: minimiser of the two-point Hermite cubic."""
+    d1 = dphi_0 + slope_a - 3.0 * (phi_0 - phi) / (0.0 - a)
+    radicand = d1 * d1 - dphi_0 * slope_a
+    d2 = math.sqrt(max(radicand, 0.0))
+    denom = slope_a - dphi_0 + 2.0 * d2
+    if radicand < 0.0 or denom == 0.0:
+        return 0.5 * a
+    return a - a * (slope_a + d2 - d1) / denom
+
+
+def line_search(eval_fn, phi_0, dphi_0, settings, init_aux):
+    """line_search.py:95-189 with trial slopes (cubic contraction).
+    ``eval_fn(alpha) -> (phi, slope, aux)``; returns ``(alpha, aux, n_evals)``."""
+    s = {**DEFAULT_LINE_SEARCH, **(settings or {})}
+    armijo = s["sufficient decrease"] * dphi_0
+    n, alpha, accepted, aux = 0, 1.0, False, init_aux
+    best_alpha, best_phi, best_aux = 1.0, math.inf, init_aux
+    while n < s["max evals"] and not accepted:
+        phi, slope, aux = eval_fn(alpha)
+        finite = math.isfinite(phi)
+        if finite and phi < best_phi:
+            best_alpha, best_phi, best_aux = alpha, phi, aux
+        accepted = finite and phi <= phi_0 + alpha * armijo
+        model = cubic_min(phi_0, dphi_0, alpha, phi, slope) if finite else float("nan")
+        lo, hi = s["min backtrack factor"] * alpha, s["max backtrack factor"] * alpha
+        contracted = model if model != model else min(max(model, lo), hi)
+        if not accepted:
+            alpha = contracted if finite else 0.5 * alpha
+        n += 1
+    return (alpha, aux, n) if accepted else (best_alpha, best_aux, n)
+
+
+@dataclass
+class DirichletBCs:
+    """Prescribed dofs and their values as a function of pseudo-time (the deck's
+    ``dirichlet bcs`` expressions evaluated per load step, cmad/fem/dof.py)."""
+    indices: np.ndarray                              # (n_presc,) global equations
+    values: Callable[[float], np.ndarray]            # t -> (n_presc,)
+
+
+@dataclass
+class SparsePattern:
+    """Deduplicated COO pattern of the assembled tangent (``coo_rows`` / ``coo_cols``,
+    cmad/fem/kernel_arrays.py:81-90)."""
+    rows: np.ndarray
+    cols: np.ndarray
+    n: int
+
+    def csr(self, data: np.ndarray) -> sp.csr_matrix:
+        return sp.csr_matrix((data, (self.rows, self.cols)), shape=(self.n, self.n))
+
+
+def embedded_system(pattern: SparsePattern, K_data, R, U, bcs: DirichletBCs, t: float):
+    """``(r, K_emb)`` of sparse_solve.py:1058-1174: prescribed rows and columns of K
+    zeroed, the assembled diagonal kept at the prescribed rows; the (free, prescribed)
+    coupling moved to the right-hand side; prescribed rows of r = K_ii (U - value)."""
+    K = pattern.csr(np.asarray(K_data))
+    idx = bcs.indices
+    vals = np.asarray(bcs.values(t), dtype=np.float64)
+    K_ii = K.diagonal()[idx]
+    inc = np.zeros(pattern.n)
+    inc[idx] = vals - U[idx]
+    r = np.asarray(R) + K @ inc
+    r[idx] = K_ii * (U[idx] - vals)
+    keep = np.ones(pattern.n)
+    keep[idx] = 0.0
+    D = sp.diags(keep)
+    K_emb = (D @ K @ D + sp.csr_matrix((K_ii, (idx, idx)), shape=K.shape)).tocsc()
+    return r, K_emb
+
+
+@dataclass
+class NewtonLog:
+    iters: int = 0
+    assemblies: int = 0
+    residual_norms: list = field(default_factory=list)
+    alphas: list = field(default_factory=list)
+
+
+def fe_newton_solve(assemble, pattern: SparsePattern, bcs: DirichletBCs, U_prev: np.ndarray,
+                    xi_prev, t: float, settings: dict | None = None):
+    """One load step: ``(U*, xi*, log)``.  ``assemble(U, xi_prev) -> (R, K_data, xi)``
+    with ``R (n_dofs,)`` and ``K_data`` on ``pattern`` as host arrays (``xi`` is opaque
+    to the driver and stays wherever ``assemble`` keeps it)."""
+    s = {**DEFAULT_NONLINEAR, **(settings or {})}
+    ls = {**DEFAULT_LINE_SEARCH, **(s.get("line search") or {})}
+    log = NewtonLog()
+
+    def assemble_enforced(U):
+        R, K_data, xi = assemble(U, xi_prev)
+        log.assemblies += 1
+        r, K_emb = embedded_system(pattern, K_data, R, U, bcs, t)
+        return r, K_emb, xi
+
+    U = np.array(U_prev, dtype=np.float64)
+    r, K, xi = assemble_enforced(U)
+    R0 = max(float(np.linalg.norm(r)), s["abs tol"])
+    i = 0
+    while True:
+        nrm = float(np.linalg.norm(r))
+        log.residual_norms.append(nrm)
+        if not (i < s["max iters"] and nrm >= s["abs tol"] and nrm >= s["rel tol"] * R0):
+            break
+        dU = spla.splu(K).solve(-r)
+        if ls["max evals"] > 0:
+            rr = float(r @ r)
+
+            def eval_fn(alpha, U=U, dU=dU):
+                rt, Kt, xit = assemble_enforced(U + alpha * dU)
+                return 0.5 * float(rt @ rt), float(rt @ (Kt @ dU)), (rt, Kt, xit)
+
+            alpha, (r, K, xi), _ = line_search(eval_fn, 0.5 * rr, -rr, ls, (r, K, xi))
+            U = U + alpha * dU
+            log.alphas.append(alpha)
+        else:
+            U = U + dU
+            r, K, xi = assemble_enforced(U)
+        i += 1
+    log.iters = i
+    return U, xi, log
+
+
+def displacement_l2_step(N: np.ndarray, wdet: np.ndarray, elem_eq: np.ndarray, U: np.ndarray) -> float:
+    """``sum_e sum_ip |N u_e|^2 w det`` (fe_displacement_l2.py:106-123)."""
+    U_e = np.asarray(U)[elem_eq].reshape(elem_eq.shape[0], -1, 3)
+    u_ip = np.einsum("pa,eak->epk", N, U_e)
+    return float(((u_ip * u_ip).sum(axis=-1) * wdet).sum())
+
+
+def fe_quasistatic_drive(assemble, pattern: SparsePattern, bcs: DirichletBCs, U0: np.ndarray, xi0,
+                         t_schedule: Sequence[float], settings: dict | None = None,
+                         step_qoi: Callable[[np.ndarray, float, float], float] | None = None):
+    """Load-step loop (driver.py:103-146): returns ``(U_steps, xi_last, J, logs)``;
+    ``step_qoi(U, t, t_prev)`` is summed into ``J`` after every converged step."""
+    U, xi = np.array(U0, dtype=np.float64), xi0
+    U_steps, logs, J = [], [], 0.0
+    for k in range(1, len(t_schedule)):
+        t, t_prev = float(t_schedule[k]), float(t_schedule[k - 1])
+        U, xi, log = fe_newton_solve(assemble, pattern, bcs, U, xi, t, settings)
+        U_steps.append(U.copy())
+        logs.append(log)
+        if step_qoi is not None:
+            J += step_qoi(U, t, t_prev)
+    return np.array(U_steps), xi, J, logs
+
+
+def cuda_assembler(material, newton, arrays, r_plan, k_plan, outputs=None):
+    """``assemble`` callable over the CUDA kernels for one element block: K3 (R_e, K_e,
+    xi) + K5 (deterministic R scatter, COO dedup); ``xi`` stays on the device."""
+    import torch
+    from . import fe
+    dev = arrays.grad_N.device
+
+    def assemble(U, xi_prev):
+        Ud = torch.from_numpy(np.ascontiguousarray(U)).to(dev)
+        R, vals, xi = fe.assemble_element_block(material, newton, arrays, Ud, xi_prev, r_plan=r_plan)
+        K_data = k_plan.sum(vals)
+        if outputs is not None:
+            outputs["last"] = (R, K_data, xi)
+        return R.cpu().numpy(), K_data.cpu().numpy(), xi
+
+    return assemble
