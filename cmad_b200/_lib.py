@@ -152,7 +152,7 @@ def lib() -> C.CDLL:
                                           C.POINTER(FeBlock), C.c_void_p]
     L.cmadx_fe_block_jvp.argtypes = [C.POINTER(Material), C.POINTER(C.c_int32), C.c_int32,
                                      C.POINTER(C.c_double), C.POINTER(FeBlock), C.c_void_p,
-                                     C.c_void_p, C.c_void_p]
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
     L.cmadx_fe_vjp_workspace_bytes.restype = C.c_int64
     L.cmadx_fe_vjp_workspace_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32]
     L.cmadx_fe_block_vjp.argtypes = [C.POINTER(Material), C.POINTER(C.c_int32), C.c_int32,

@@ -499,7 +499,7 @@ static int check_fe_block(const cmadx_material_t* mat, const cmadx_fe_block_t* b
     }
     A->b = b;
     A->bail_count = nullptr; A->bail_list = nullptr; A->bail_cap = 0;
-    A->xi_state = nullptr; A->dxi_prev = nullptr; A->n_active = 0;
+    A->xi_state = nullptr; A->dxi_prev = nullptr; A->dU = nullptr; A->n_active = 0;
     return CMADX_OK;
 }
 
@@ -535,7 +535,8 @@ int cmadx_fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* n
 
 int cmadx_fe_block_jvp(const cmadx_material_t* mat, const int32_t* active_pid, int32_t n_active,
                        const double* dp_host, const cmadx_fe_block_t* blk,
-                       const double* xi_state, const double* dxi_prev, void* stream) {
+                       const double* xi_state, const double* dxi_prev, const double* dU_global,
+                       void* stream) {
     FeArgs A;
     if (int rc = check_fe_block(mat, blk, &A)) return rc;
     if (blk->K_elem) return CMADX_EINVAL;
@@ -552,6 +553,7 @@ int cmadx_fe_block_jvp(const cmadx_material_t* mat, const int32_t* active_pid, i
     if (!xi_state) return CMADX_EINVAL;
     A.xi_state = xi_state;
     A.dxi_prev = dxi_prev;
+    A.dU = dU_global;
     std::memset(&A.nw, 0, sizeof(A.nw));
     cudaError_t e = launch_fe_block_jvp(A, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);

@@ -15,6 +15,7 @@ struct FeArgs {
     // K6 (JVP at a given state): converged local state, input tangents
     const double* xi_state;   // [n_elems][n_ip][7]
     const double* dxi_prev;   // [n_elems][n_ip][7] or NULL (= 0)
+    const double* dU;         // [n_dofs] or NULL (= 0): displacement direction
     double dp[CMADX_MAX_ACTIVE];
     int pid[CMADX_MAX_ACTIVE];
     int n_active;

@@ -213,11 +213,16 @@ CMADX_DEV void point_generic(const DevMat& m, const DevNewton& nw, const double 
 // ---- K6: tangent (JVP) of the converged point w.r.t. (params, xi_prev) at fixed strain
 // What jax.jvp pushes through make_newton_solve's custom_jvp rule for the FE
 // sensitivities (cmad/models/nonlinear_solver.py:158-171 called from
-// cmad/fem/nonlinear_solver.py:490-537):  dxi = -A^{-1} (dC/dp dp + dC/dxi_prev dxi_prev),
-// d sigma = d cauchy/dxi dxi + d cauchy/dp dp, evaluated AT the given converged state.
+// cmad/fem/nonlinear_solver.py:490-537):
+//   dxi = -A^{-1} (dC/dp dp + dC/dxi_prev dxi_prev + dC/deps deps),
+//   d sigma = d cauchy/dxi dxi + d cauchy/dp dp + d cauchy/deps deps,
+// evaluated AT the given converged state; `de` is the symmetric strain direction of an
+// optional displacement direction (zero for the fixed-U residual JVP).  With
+// dC/deps = -(A[:, :6] - E), E = [I6; 0]:  dxi = v - A^{-1}(r0 + v), v = [deps; 0].
 template <int YK, bool ROT>
 CMADX_DEV void point_jvp(const FeArgs& A, const double (&xp)[7], const double (&xs)[7],
-                         const double (&dxp)[7], const double (&e)[6], bool live, PointOut& o) {
+                         const double (&dxp)[7], const double (&e)[6], const double (&de)[6],
+                         bool live, PointOut& o) {
     const DevMat& m = A.m;
     double em[6];
     if (ROT) {
@@ -233,6 +238,21 @@ CMADX_DEV void point_jvp(const FeArgs& A, const double (&xp)[7], const double (&
     } else {
 #pragma unroll
         for (int c = 0; c < 6; ++c) em[c] = e[c];
+    }
+    double dem[6];
+    if (ROT) {
+        double T[6][6], S[6][6];
+        rot_maps(m.Q, T, S);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) s = fma(T[c][b], de[b], s);
+            dem[c] = s;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) dem[c] = de[c];
     }
     SepPoint<YK> pt;
     double Cs[7];
@@ -271,15 +291,20 @@ CMADX_DEV void point_jvp(const FeArgs& A, const double (&xp)[7], const double (&
 #pragma unroll
     for (int a = 0; a < 6; ++a) rhs[a] += pl ? fma(pt.n[a], dxp[6], -dxp[a]) : -dxp[a];
     rhs[6] += pl ? 0.0 : -dxp[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) rhs[a] += dem[a];                 // r0 + v
     newton_direction<SepPoint<YK>, 7>(m, pt, dg, rhs);          // rhs <- A^{-1} rhs
 #pragma unroll
-    for (int r = 0; r < 7; ++r) o.x[r] = live ? -rhs[r] : 0.0;
-    // d sigma (material axes) = Cel (-d ep) + (d lam tr(ee) I + 2 d mu ee)
-    const double trd = -(o.x[0] + o.x[3] + o.x[5]);
+    for (int r = 0; r < 7; ++r) o.x[r] = live ? ((r < 6 ? dem[r] : 0.0) - rhs[r]) : 0.0;
+    // d sigma (material axes) = Cel (d eps - d ep) + (d lam tr(ee) I + 2 d mu ee)
+    double dee[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) dee[a] = dem[a] - o.x[a];
+    const double trd = dee[0] + dee[3] + dee[5];
     double ds[6];
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
-        const double v = fma(2.0 * dmu, ee[a], -m.two_mu * o.x[a]);
+        const double v = fma(2.0 * dmu, ee[a], m.two_mu * dee[a]);
         ds[a] = is_diag(a) ? v + fma(m.lam, trd, dlam * tre) : v;
     }
     if (ROT) {

@@ -20,6 +20,7 @@
 //             [22,46) grad_N (8 nodes x 3), loaded straight from HBM into place
 //             [46,52) sigma w dv
 //   [456,512) xi_prev, then xi, of the 8 points (7 doubles each)
+//   [512,536) dU_e (K6 JVP with a displacement direction only)
 //   phase C end: the 24x24 K_e tile (8 node blocks x 74 doubles) over the whole region
 //
 // Bank layout (ncu: the first version spent half its shared-memory wavefronts on
@@ -89,6 +90,10 @@ CMADX_DEV void hex8_point(const FeArgs& A, const int64_t e, const bool live, dou
         for (int r = 0; r < 7; ++r) reg[HEX_XI + r * 8 + ip] = xs[r];
 #pragma unroll
         for (int k = 0; k < 3; ++k) reg[3 * ip + k] = Un[k];
+        if constexpr (SOLVER >= FE_JVP) {     // displacement direction of the JVP, next to xi
+#pragma unroll
+            for (int k = 0; k < 3; ++k) reg[HEX_XI + 56 + 3 * ip + k] = A.dU ? __ldg(A.dU + eq3[k]) : 0.0;
+        }
     } else {
 #pragma unroll
         for (int k = 0; k < 3; ++k) reg[3 * ip + k] = 0.0;
@@ -103,7 +108,7 @@ CMADX_DEV void hex8_point(const FeArgs& A, const int64_t e, const bool live, dou
         for (int r = 0; r < 7; ++r) reg[HEX_XI + r * 8 + ip] = 0.0;
     }
     __syncwarp();
-    double xp[7], eps[6];
+    double xp[7], eps[6], deps[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int c = 0; c < 7; ++c) xp[c] = reg[HEX_XI + ip * 7 + c];
     {
@@ -114,6 +119,15 @@ CMADX_DEV void hex8_point(const FeArgs& A, const int64_t e, const bool live, dou
 #pragma unroll
             for (int k = 0; k < 3; ++k) { gN[a][k] = mine[3 * a + k]; U[a][k] = reg[3 * a + k]; }
         strain_from_U<8>(U, gN, eps);
+        if constexpr (SOLVER >= FE_JVP) {
+            if (live) {
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) U[a][k] = reg[HEX_XI + 56 + 3 * a + k];
+                strain_from_U<8>(U, gN, deps);
+            }
+        }
     }
 
     // ---- phase B: local Newton at this point
@@ -127,7 +141,7 @@ CMADX_DEV void hex8_point(const FeArgs& A, const int64_t e, const bool live, dou
             xs[c] = live ? __ldg(A.xi_state + p * 7 + c) : 0.0;
             dxp[c] = (live && A.dxi_prev) ? __ldg(A.dxi_prev + p * 7 + c) : 0.0;
         }
-        point_jvp<SOLVER - FE_JVP, ROT>(A, xp, xs, dxp, eps, live, o);
+        point_jvp<SOLVER - FE_JVP, ROT>(A, xp, xs, dxp, eps, deps, live, o);
     } else {
         solve_point<SOLVER, ROT, WANT_K>(A.m, A.nw, xp, eps, live, o, D);
     }

@@ -49,7 +49,16 @@ CMADX_DEV void tet4_element(const FeArgs& A, const int64_t e, const bool live) {
             xs[c] = live ? __ldg(A.xi_state + e * 7 + c) : 0.0;
             dxp[c] = (live && A.dxi_prev) ? __ldg(A.dxi_prev + e * 7 + c) : 0.0;
         }
-        point_jvp<SOLVER - FE_JVP, ROT>(A, xp, xs, dxp, eps, live, o);
+        double de[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (live && A.dU) {
+            double dUe[4][3];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) dUe[a][k] = __ldg(A.dU + eq[3 * a + k]);
+            strain_from_U<4>(dUe, gN, de);
+        }
+        point_jvp<SOLVER - FE_JVP, ROT>(A, xp, xs, dxp, eps, de, live, o);
     } else {
         solve_point<SOLVER, ROT, WANT_K>(A.m, A.nw, xp, eps, live, o, D);
     }

@@ -163,17 +163,20 @@ def assemble_element_block_residual(material, newton, arrays, U_global, xi_prev_
 def fe_block_jvp(material: L.Material, arrays: FEBlockArrays, U_global: torch.Tensor,
                  xi_prev: torch.Tensor, xi_state: torch.Tensor, active_pid, dp,
                  dxi_prev: torch.Tensor | None = None, outputs=("xi", "R_elem"), out: dict | None = None,
-                 stream: torch.cuda.Stream | None = None) -> dict:
+                 stream: torch.cuda.Stream | None = None, dU: torch.Tensor | None = None) -> dict:
     """K6: tangent of the converged block w.r.t. (params, xi_prev) at fixed ``U``:
     returns ``out["xi"]`` = ``dxi (n_e, n_ip, 7)`` and ``out["R_elem"]`` = ``dR_e``
     (or ``R_global``) for the direction ``dp`` (native values of the active
     parameters, in ``active_pid`` order) and ``dxi_prev``.  What ``jax.jvp`` pushes
     through the assembled residual inside the FE Newton's IFT rule
-    (cmad/fem/nonlinear_solver.py:490-537)."""
+    (cmad/fem/nonlinear_solver.py:490-537).  ``dU (n_dofs,)`` optionally adds a displacement
+    direction (then ``dR`` includes ``K dU`` and ``dxi`` is the total state sensitivity)."""
     n_e, n_b, n_ip = arrays.n_elems, arrays.n_basis, arrays.n_ip
     dev = arrays.grad_N.device
     if dev.type != "cuda":
         raise ValueError("FE block arrays must live on a CUDA device (there is no CPU fallback)")
+    if dU is not None and (dU.dtype != torch.float64 or dU.numel() != arrays.n_dofs or not dU.is_contiguous()):
+        raise ValueError(f"dU: expected contiguous float64 ({arrays.n_dofs},)")
     for name, t in (("xi_prev", xi_prev), ("xi_state", xi_state), ("dxi_prev", dxi_prev)):
         if t is None:
             continue
@@ -200,7 +203,8 @@ def fe_block_jvp(material: L.Material, arrays: FEBlockArrays, U_global: torch.Te
         rc = L.lib().cmadx_fe_block_jvp(
             C.byref(material), pid.ctypes.data_as(C.POINTER(C.c_int32)), len(pid),
             dpv.ctypes.data_as(C.POINTER(C.c_double)), C.byref(b), C.c_void_p(xi_state.data_ptr()),
-            C.c_void_p(dxi_prev.data_ptr()) if dxi_prev is not None else None, C.c_void_p(s.cuda_stream))
+            C.c_void_p(dxi_prev.data_ptr()) if dxi_prev is not None else None,
+            C.c_void_p(dU.data_ptr()) if dU is not None else None, C.c_void_p(s.cuda_stream))
     L.check(rc, "cmadx_fe_block_jvp")
     return out
 

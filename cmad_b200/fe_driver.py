@@ -112,6 +112,7 @@ def embedded_system(pattern: SparsePattern, K_data, R, U, bcs: DirichletBCs, t: 
 class NewtonLog:
     iters: int = 0
     assemblies: int = 0
+    K_emb: object = None          # embedded tangent at the returned state (for sensitivities)
     residual_norms: list = field(default_factory=list)
     alphas: list = field(default_factory=list)
 
@@ -156,6 +157,7 @@ def fe_newton_solve(assemble, pattern: SparsePattern, bcs: DirichletBCs, U_prev:
             r, K, xi = assemble_enforced(U)
         i += 1
     log.iters = i
+    log.K_emb = K
     return U, xi, log
 
 
@@ -181,6 +183,66 @@ def fe_quasistatic_drive(assemble, pattern: SparsePattern, bcs: DirichletBCs, U0
         if step_qoi is not None:
             J += step_qoi(U, t, t_prev)
     return np.array(U_steps), xi, J, logs
+
+
+def displacement_l2_step_dU(N: np.ndarray, wdet: np.ndarray, elem_eq: np.ndarray, U: np.ndarray) -> np.ndarray:
+    """Gradient of :func:`displacement_l2_step` w.r.t. the global ``U``."""
+    U_e = np.asarray(U)[elem_eq].reshape(elem_eq.shape[0], -1, 3)
+    u_ip = np.einsum("pa,eak->epk", N, U_e)
+    g_e = 2.0 * np.einsum("pa,epk,ep->eak", N, u_ip, wdet)
+    g = np.zeros(np.asarray(U).shape[0])
+    np.add.at(g, elem_eq.reshape(-1), g_e.reshape(-1))
+    return g
+
+
+def fe_direct_gradient(assemble, jvp, pattern: SparsePattern, bcs: DirichletBCs, U0, xi0, dxi0,
+                       t_schedule: Sequence[float], n_active: int, settings: dict | None,
+                       step_qoi, step_qoi_dU):
+    """``(J, dJ/dp)`` in native parameter values by forward (direct) sensitivities through
+    the load steps - the discrete equivalent of differentiating the trajectory of
+    cmad/fem/driver.py:103-146 through the IFT rule of the FE Newton
+    (cmad/fem/nonlinear_solver.py:450-542): per step and active parameter c,
+        dR_c = JVP(e_c, dxi_prev_c) at fixed U*          (K6, device)
+        K_emb dU_c = -dR_c   on the free dofs            (host SuperLU, factored once per step)
+        dxi_c = JVP(e_c, dxi_prev_c, dU_c).xi            (K6 with the displacement direction)
+        dJ_c += dq/dU . dU_c
+    ``jvp(U, xi_prev, xi_state, c, dxi_prev_c, dU) -> (dR (n_dofs,) host, dxi)``;
+    ``dxi0(c)`` gives the initial (zero) state sensitivities in the assembler's format."""
+    U, xi = np.array(U0, dtype=np.float64), xi0
+    dX = [dxi0(c) for c in range(n_active)]
+    J, grad = 0.0, np.zeros(n_active)
+    for k in range(1, len(t_schedule)):
+        t, t_prev = float(t_schedule[k]), float(t_schedule[k - 1])
+        xi_prev = xi
+        U, xi, log = fe_newton_solve(assemble, pattern, bcs, U, xi_prev, t, settings)
+        lu = spla.splu(log.K_emb)
+        dq = step_qoi_dU(U, t, t_prev)
+        J += step_qoi(U, t, t_prev)
+        for c in range(n_active):
+            dR, _ = jvp(U, xi_prev, xi, c, dX[c], None)
+            rhs = -np.asarray(dR)
+            rhs[bcs.indices] = 0.0                     # prescribed values do not depend on p
+            dU = lu.solve(rhs)
+            _, dX[c] = jvp(U, xi_prev, xi, c, dX[c], dU)
+            grad[c] += float(dq @ dU)
+    return J, grad
+
+
+def cuda_jvp(material, arrays, r_plan, active_pid):
+    """``jvp`` callable of :func:`fe_direct_gradient` over the K6 kernels."""
+    import torch
+    from . import fe
+    dev = arrays.grad_N.device
+    pid = np.ascontiguousarray(active_pid, dtype=np.int32)
+
+    def jvp(U, xi_prev, xi_state, c, dxi_prev, dU):
+        Ud = torch.from_numpy(np.ascontiguousarray(U)).to(dev)
+        dp = np.zeros(len(pid)); dp[c] = 1.0
+        dUd = torch.from_numpy(np.ascontiguousarray(dU)).to(dev) if dU is not None else None
+        o = fe.fe_block_jvp(material, arrays, Ud, xi_prev, xi_state, pid, dp, dxi_prev, dU=dUd)
+        return r_plan.sum(o["R_elem"].reshape(-1)).cpu().numpy(), o["xi"]
+
+    return jvp
 
 
 def cuda_assembler(material, newton, arrays, r_plan, k_plan, outputs=None):

@@ -273,10 +273,14 @@ int cmadx_fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* n
  * direct FE sensitivity recurrence.  `blk` as in cmadx_fe_block_assemble with
  * K_elem == NULL; blk->xi receives dxi, blk->R_elem / R_global receive dR.
  * xi_state: the converged local state [n_elems][n_ip][7] (the `xi` output of the primal
- * call); dxi_prev: [n_elems][n_ip][7] or NULL (zero); dp_host: n_active doubles (host).  */
+ * call); dxi_prev: [n_elems][n_ip][7] or NULL (zero); dp_host: n_active doubles (host).
+ * dU_global ([n_dofs] or NULL) adds a displacement direction: dC/deps deps enters dxi
+ * and dcauchy/deps deps enters dR (then dR includes K dU) - the "jvp of the xi output"
+ * of cmad/fem/nonlinear_solver.py:534-538 once the global sensitivity dU is known.     */
 int cmadx_fe_block_jvp(const cmadx_material_t* mat, const int32_t* active_pid, int32_t n_active,
                        const double* dp_host, const cmadx_fe_block_t* blk,
-                       const double* xi_state, const double* dxi_prev, void* stream);
+                       const double* xi_state, const double* dxi_prev, const double* dU_global,
+                       void* stream);
 
 /* Reverse mode (VJP), the transpose of cmadx_fe_block_jvp: given the cotangent Rbar of the
  * assembled residual (a nodal adjoint vector, [n_dofs]) and the cotangent xibar of the

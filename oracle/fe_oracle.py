@@ -84,7 +84,7 @@ def coo_dedup_sum(vals: np.ndarray, scatter: np.ndarray, n_unique: int) -> np.nd
 
 
 def block_jvp(prob_eval: oracle_c.OracleProblem, elem_eq, U, xi_prev, xi_state, grad_N, det, quad_w,
-              dp, dxi_prev=None, nthreads: int = 0) -> dict:
+              dp, dxi_prev=None, nthreads: int = 0, dU=None) -> dict:
     """Forward sensitivities of a COUPLED block at the converged state, at fixed ``U``
     (what jax.jvp pushes through the custom_jvp rule of make_newton_solve,
     cmad/models/nonlinear_solver.py:158-171, inside cmad/fem/nonlinear_solver.py:490-537):
@@ -97,12 +97,15 @@ def block_jvp(prob_eval: oracle_c.OracleProblem, elem_eq, U, xi_prev, xi_state, 
     na = len(prob_eval.active_pid)
     dp = np.asarray(dp, dtype=np.float64).reshape(na)
     U_e = np.asarray(U)[elem_eq].reshape(n_e, n_b, 3)
+    dU_e = None if dU is None else np.asarray(dU)[elem_eq].reshape(n_e, n_b, 3)
     dR = np.zeros((n_e, n_b, 3)); dxi = np.zeros((n_e, n_ip, 7))
     for ip in range(n_ip):
         gN = grad_N[:, ip]
         gu = np.einsum("eak,eaj->ekj", U_e, gN).reshape(n_e, 9).T.copy()
+        want = ("dC_dxi", "dC_dxi_prev", "dC_dp", "dsig_dxi", "dsig_dp") + \
+            (("dxi_deps", "dsig_deps") if dU is not None else ())
         r = oracle_c.mp_update(prob_eval, xi_prev[:, ip].T.copy(), gu, xi_init=xi_state[:, ip].T.copy(),
-                               want=("dC_dxi", "dC_dxi_prev", "dC_dp", "dsig_dxi", "dsig_dp"), nthreads=nthreads)
+                               want=want, nthreads=nthreads)
         A = np.moveaxis(r["dC_dxi"].reshape(7, 7, n_e), 2, 0)
         B = np.moveaxis(r["dC_dxi_prev"].reshape(7, 7, n_e), 2, 0)
         rhs = np.zeros((n_e, 7))
@@ -111,10 +114,18 @@ def block_jvp(prob_eval: oracle_c.OracleProblem, elem_eq, U, xi_prev, xi_state, 
         if dxi_prev is not None:
             rhs += np.einsum("erc,ec->er", B, dxi_prev[:, ip])
         dx = -np.linalg.solve(A, rhs[:, :, None])[:, :, 0]
-        dxi[:, ip] = dx
         ds = np.einsum("ace,ec->ae", r["dsig_dxi"].reshape(6, 7, n_e), dx)
         if na:
             ds += np.einsum("ace,c->ae", r["dsig_dp"].reshape(6, na, n_e), dp)
+        if dU is not None:
+            # displacement direction: the IFT blocks dxi/deps and the TOTAL dsigma/deps of
+            # the oracle (symmetric strain components, both tensor entries moving)
+            dg = np.einsum("eak,eaj->ekj", dU_e, gN)
+            de = 0.5 * (dg + np.swapaxes(dg, 1, 2))
+            de6 = np.stack([de[:, 0, 0], de[:, 0, 1], de[:, 0, 2], de[:, 1, 1], de[:, 1, 2], de[:, 2, 2]])
+            dx = dx + np.einsum("rbe,be->er", r["dxi_deps"].reshape(7, 6, n_e), de6)
+            ds = ds + np.einsum("abe,be->ae", r["dsig_deps"].reshape(6, 6, n_e), de6)
+        dxi[:, ip] = dx
         wdv = quad_w[ip] * det[:, ip]
         dR += np.einsum("eaj,jie->eai", gN, ds[_V]) * wdv[:, None, None]
     return {"R_elem": dR.reshape(n_e, n_b * 3), "xi": dxi}

@@ -134,3 +134,110 @@ def test_cuda_driver_matches_oracle_driver(cuda_device, family, div):
                              torch.from_numpy(Ug[-1]).to(cuda_device), xig, ("xi", "sigma"))
     # re-evaluation at the converged state (xi_prev = xi*: an elastic step that returns the same stress)
     assert float((out["sigma"][:, :, 0] - sig_ref).abs().max()) < 1e-7 * sig_ref
+
+
+# ---------------------------------------------------------------- FE gradient (direct sensitivities)
+def _gradient_problem(div=2, family="hex8"):
+    from cmad_b200 import Parameters
+    from tests.helpers import param_tree
+    values, act, tr = param_tree("J2", active=("E", "nu", "D", "S", "Y"))
+    P = Parameters(values, act, tr)
+    nodes, arr, bcs, pattern, scatter = uniaxial_cube(div, family)
+    # distort the interior so the fields are not homogeneous
+    rng = np.random.default_rng(4)
+    inner = np.all((nodes > 1e-9) & (nodes < 1 - 1e-9), axis=1)
+    nodes = nodes.copy(); nodes[inner] += 0.08 / div * rng.uniform(-1, 1, size=(inner.sum(), 3))
+    conn = fe_mesh.structured_hex_mesh((div,) * 3)[1]
+    if family == "tet4":
+        conn = fe_mesh.split_hex_to_tets(conn)
+    arr = fe_mesh.block_arrays(nodes, conn)
+    return values, P, nodes, arr, bcs, pattern, scatter
+
+
+def oracle_jvp(values, P, arr):
+    prob_eval = oc.describe(values, P.active_idx, newton_mode="imperative", strain_comps=9, max_iters=0)
+    eq = arr.elem_eq.numpy(); geo = (arr.grad_N.numpy(), arr.det.numpy(), arr.quad_w.numpy())
+    na = len(prob_eval.active_pid)
+
+    def jvp(U, xi_prev, xi_state, c, dxi_prev, dU):
+        dp = np.zeros(na); dp[c] = 1.0
+        o = fe_oracle.block_jvp(prob_eval, eq, U, xi_prev, xi_state, *geo, dp, dxi_prev, dU=dU)
+        dR = np.zeros(arr.n_dofs); np.add.at(dR, eq.reshape(-1), o["R_elem"].reshape(-1))
+        return dR, o["xi"]
+    return jvp
+
+
+def _qois(arr, ts):
+    wdet = (arr.det * arr.quad_w[None, :]).numpy()
+    N, eq = arr.N.numpy(), arr.elem_eq.numpy()
+    c = 1.0 / (ts[-1] * wdet.sum())
+    q = lambda U, t, tp: c * (t - tp) * drv.displacement_l2_step(N, wdet, eq, U)
+    dq = lambda U, t, tp: c * (t - tp) * drv.displacement_l2_step_dU(N, wdet, eq, U)
+    return q, dq
+
+
+def test_direct_gradient_vs_central_fd_of_the_trajectory():
+    """`cmad gradient` on the FE deck, restated: dJ/dp of the displacement-L2 QoI through
+    3 load steps by forward sensitivities (K6 blocks + one factorisation per step), against
+    central differences of J over re-solved trajectories (all over the oracle assembler)."""
+    import copy
+    values, P, nodes, arr, bcs, pattern, scatter = _gradient_problem()
+    # t = 1/3 would put the homogeneous part of the field exactly AT first yield (0.003 t =
+    # Y/E), where J(p) has a kink in E and Y and a central difference averages the two
+    # one-sided slopes; keep every step clear of it
+    ts = np.array([0.0, 0.4, 0.7, 1.0])
+    q, dq = _qois(arr, ts)
+    tight = {"abs tol": 1e-13, "rel tol": 1e-13, "max iters": 15}
+    z = lambda: np.zeros((arr.n_elems, arr.n_ip, 7))
+    J, g = drv.fe_direct_gradient(oracle_assembler(values, arr, scatter, len(pattern.rows)),
+                                  oracle_jvp(values, P, arr), pattern, bcs, np.zeros(arr.n_dofs), z(),
+                                  lambda c: z(), ts, 5, tight, q, dq)
+
+    def J_of(v):
+        return drv.fe_quasistatic_drive(oracle_assembler(v, arr, scatter, len(pattern.rows)), pattern, bcs,
+                                        np.zeros(arr.n_dofs), z(), ts, tight, q)[2]
+    assert abs(J_of(values) - J) < 1e-14 * abs(J)
+    paths = [("elastic", "E"), ("elastic", "nu"), ("plastic", "flow stress", "hardening", "voce", "D"),
+             ("plastic", "flow stress", "hardening", "voce", "S"), ("plastic", "flow stress", "initial yield", "Y")]
+    assert np.abs(g).min() > 0
+    for c, path in enumerate(paths):
+        def bump(h):
+            v = copy.deepcopy(values); d = v
+            for k in path[:-1]:
+                d = d[k]
+            d[path[-1]] = d[path[-1]] * (1 + h)
+            return J_of(v)
+        h = 1e-5
+        d = values
+        for k in path:
+            d = d[k]
+        fd = (bump(h) - bump(-h)) / (2 * h * d)
+        assert abs(fd - g[c]) < 2e-5 * abs(g[c]) + 1e-16, (path, fd, g[c])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("family", ["hex8", "tet4"])
+def test_cuda_direct_gradient_matches_oracle(cuda_device, family):
+    import torch
+    from cmad_b200 import active_param_ids, fe, material_from_values
+    values, P, nodes, arr, bcs, pattern, scatter = _gradient_problem(3, family)
+    ts = np.array([0.0, 0.4, 0.7, 1.0])
+    q, dq = _qois(arr, ts)
+    z = lambda: np.zeros((arr.n_elems, arr.n_ip, 7))
+    Jo, go = drv.fe_direct_gradient(oracle_assembler(values, arr, scatter, len(pattern.rows)),
+                                    oracle_jvp(values, P, arr), pattern, bcs, np.zeros(arr.n_dofs), z(),
+                                    lambda c: z(), ts, 5, None, q, dq)
+    arr_d = arr.to(cuda_device)
+    mat = material_from_values(values)
+    r_plan = fe.SegmentPlan(arr.elem_eq.numpy().reshape(-1), arr.n_dofs, device=cuda_device)
+    k_plan = fe.SegmentPlan(scatter, len(pattern.rows), device=cuda_device)
+    zd = lambda: torch.zeros((arr.n_elems, arr.n_ip, 7), dtype=torch.float64, device=cuda_device)
+    Jg, gg = drv.fe_direct_gradient(
+        drv.cuda_assembler(mat, fe.fe_newton_settings(**LOCAL_NEWTON), arr_d, r_plan, k_plan),
+        drv.cuda_jvp(mat, arr_d, r_plan, active_param_ids(P)), pattern, bcs, np.zeros(arr.n_dofs), zd(),
+        lambda c: zd(), ts, 5, None, q, dq)
+    assert abs(Jg - Jo) < 1e-10 * abs(Jo)
+    assert np.abs(gg - go).max() < 1e-8 * np.abs(go).max(), (gg, go)
+    # canonical-coordinate chain rule as `cmad gradient` reports it (parameters.py:326-331)
+    gc = gg.copy(); P.transform_grad(gc)
+    assert np.all(np.isfinite(gc))

@@ -177,9 +177,9 @@ def test_block_jvp_oracle_vs_central_fd():
     eq = arr.elem_eq.numpy(); geo = (arr.grad_N.numpy(), arr.det.numpy(), arr.quad_w.numpy())
     tight = dict(max_iters=30, abs_tol=1e-14, rel_tol=1e-14)
 
-    def primal(vals, xi_prev):
+    def primal(vals, xi_prev, Uv=None):
         prob = oc.describe(vals, P.active_idx, newton_mode="traced", strain_comps=9, **tight)
-        return fe_oracle.assemble_block(prob, eq, U, xi_prev, *geo, want_K=False)
+        return fe_oracle.assemble_block(prob, eq, U if Uv is None else Uv, xi_prev, *geo, want_K=False)
 
     rng = np.random.default_rng(0)
     xi_prev = primal(values, np.zeros((2, 8, 7)))["xi"] * 0.5          # a non-trivial previous state
@@ -189,19 +189,22 @@ def test_block_jvp_oracle_vs_central_fd():
     dxp = 1e-4 * rng.standard_normal(xi_prev.shape)
     dxp[:, :, 6] = np.abs(dxp[:, :, 6])
     prob_eval = oc.describe(values, P.active_idx, newton_mode="imperative", strain_comps=9, max_iters=0)
-    jv = fe_oracle.block_jvp(prob_eval, eq, U, xi_prev, base["xi"], *geo, dp, dxp)
+    dUv = 1e-4 * rng.standard_normal(U.shape)
 
     import copy
-    def shifted(h):
+    def shifted(h, with_U):
         v = copy.deepcopy(values)
         v["elastic"]["E"] += h * dp[0]; v["elastic"]["nu"] += h * dp[1]
         vo = v["plastic"]["flow stress"]["hardening"]["voce"]
         vo["D"] += h * dp[2]; vo["S"] += h * dp[3]
         v["plastic"]["flow stress"]["initial yield"]["Y"] += h * dp[4]
-        return primal(v, xi_prev + h * dxp)
+        return primal(v, xi_prev + h * dxp, U + h * dUv if with_U else None)
     h = 1e-5
-    up, dn = shifted(h), shifted(-h)
-    fd_R = (up["R_elem"] - dn["R_elem"]) / (2 * h)
-    fd_x = (up["xi"] - dn["xi"]) / (2 * h)
-    assert np.abs(jv["R_elem"] - fd_R).max() < 1e-6 * np.abs(fd_R).max()
-    assert np.abs(jv["xi"] - fd_x).max() < 1e-6 * np.abs(fd_x).max()
+    for with_U in (False, True):
+        jv = fe_oracle.block_jvp(prob_eval, eq, U, xi_prev, base["xi"], *geo, dp, dxp,
+                                 dU=dUv if with_U else None)
+        up, dn = shifted(h, with_U), shifted(-h, with_U)
+        fd_R = (up["R_elem"] - dn["R_elem"]) / (2 * h)
+        fd_x = (up["xi"] - dn["xi"]) / (2 * h)
+        assert np.abs(jv["R_elem"] - fd_R).max() < 1e-6 * np.abs(fd_R).max()
+        assert np.abs(jv["xi"] - fd_x).max() < 1e-6 * np.abs(fd_x).max()

@@ -252,7 +252,15 @@ def test_block_jvp_vs_oracle(cuda_device, family, kind):
                               *geo, dp, dxp.cpu().numpy())
     ref0 = fe_oracle.block_jvp(prob_eval, eq, U2.cpu().numpy(), xi1.cpu().numpy(), prim["xi"].cpu().numpy(),
                                *geo, dp, None)
-    for o, r in ((out, ref), (out0, ref0)):
+    # with a displacement direction as well (total state sensitivity, dR includes K dU)
+    dUv = torch.from_numpy(1e-4 * rng.standard_normal(arr.n_dofs)).to(cuda_device)
+    outU = fe.fe_block_jvp(mat, arr, U2, xi1, prim["xi"], pid, dp, dxp, dU=dUv)
+    refU = fe_oracle.block_jvp(prob_eval, eq, U2.cpu().numpy(), xi1.cpu().numpy(), prim["xi"].cpu().numpy(),
+                               *geo, dp, dxp.cpu().numpy(), dU=dUv.cpu().numpy())
+    Kd = fe.fe_block_launch(mat, nw, arr, U2, xi1, ("xi", "K_elem"))["K_elem"]
+    KdU = torch.einsum("eij,ej->ei", Kd, dUv[arr.elem_eq.long()])
+    assert rel_err((outU["R_elem"] - out["R_elem"]).cpu().numpy(), KdU.cpu().numpy()) < 1e-8
+    for o, r in ((out, ref), (out0, ref0), (outU, refU)):
         assert rel_err(o["xi"].cpu().numpy(), r["xi"]) < 1e-9
         assert rel_err(o["R_elem"].cpu().numpy(), r["R_elem"]) < 1e-9
     Rg = np.zeros(arr.n_dofs); np.add.at(Rg, eq.reshape(-1), ref["R_elem"].reshape(-1))
