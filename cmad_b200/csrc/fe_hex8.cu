@@ -36,17 +36,25 @@
 namespace cmadx {
 namespace {
 
-constexpr int HEX_REC = 54;
-constexpr int HEX_RECS = 24;                      // records start here
-constexpr int HEX_GN = 22, HEX_SW = 46;           // within a record
-constexpr int HEX_XI = 456;
 constexpr int HEX_TILE_STRIDE = 74;               // 72 + 2: 37 x 16 B, odd
-constexpr int HEX_PAIR = 1192;                    // two element regions: 600 + 592 doubles
 constexpr int HEX_EPB = FE_BLOCK / 8;             // elements per block
-constexpr int HEX_SMEM_DOUBLES = (HEX_EPB / 2) * HEX_PAIR;
 
-// shared-memory base (in doubles) of block-local element `eloc`
-CMADX_DEV int hex_region(int eloc) { return (eloc >> 1) * HEX_PAIR + (eloc & 1) * 600; }
+// Layout constants.  K3 (WANT_K): as described above, 76 KB per block -> 3 blocks / SM.
+// K4 / K6 (no tangent): records shrink to grad_N + sigma (30 doubles = 15 x 16 B, odd) and
+// there is no tile: 344 doubles per element (= 8 mod 16, see above), 44 KB per block ->
+// the register file (<= 128 regs) allows 4 blocks / SM.
+template <bool WANT_K> struct HexLayout;
+template <> struct HexLayout<true> {
+    static constexpr int REC = 54, RECS = 24, GN = 22, SW = 46, XI = 456, DU = 512;
+    static constexpr int SMEM_DOUBLES = (HEX_EPB / 2) * 1192;      // element pairs: 600 + 592
+    CMADX_DEV static int region(int eloc) { return (eloc >> 1) * 1192 + (eloc & 1) * 600; }
+};
+template <> struct HexLayout<false> {
+    static constexpr int REC = 30, RECS = 24, GN = 0, SW = 24, XI = 264, DU = 320;
+    static constexpr int SMEM_DOUBLES = HEX_EPB * 344;
+    CMADX_DEV static int region(int eloc) { return eloc * 344; }
+};
+
 // index of (al, be) in the packed upper triangle of a symmetric 6x6
 CMADX_DEV constexpr int sidx(int al, int be) {
     return (al <= be) ? (al * 6 - al * (al - 1) / 2 + (be - al)) : (be * 6 - be * (be - 1) / 2 + (al - be));
@@ -60,8 +68,10 @@ CMADX_DEV void hex8_point(const FeArgs& A, const int64_t e, const bool live, dou
     const int lane = threadIdx.x & 31;
     const int ip = lane & 7;                      // this thread's point; also its node in phase C
     const int eloc = threadIdx.x >> 3;
-    double* reg = smem + hex_region(eloc);
-    double* recs = reg + HEX_RECS;
+    using LY = HexLayout<WANT_K>;
+    constexpr int HEX_REC = LY::REC, HEX_GN = LY::GN, HEX_SW = LY::SW, HEX_XI = LY::XI, HEX_DU = LY::DU;
+    double* reg = smem + LY::region(eloc);
+    double* recs = reg + LY::RECS;
 
     // ---- phase A: element data -> shared memory, in contiguous runs
     int eq3[3] = {0, 0, 0};
@@ -92,7 +102,7 @@ CMADX_DEV void hex8_point(const FeArgs& A, const int64_t e, const bool live, dou
         for (int k = 0; k < 3; ++k) reg[3 * ip + k] = Un[k];
         if constexpr (SOLVER >= FE_JVP) {     // displacement direction of the JVP, next to xi
 #pragma unroll
-            for (int k = 0; k < 3; ++k) reg[HEX_XI + 56 + 3 * ip + k] = A.dU ? __ldg(A.dU + eq3[k]) : 0.0;
+            for (int k = 0; k < 3; ++k) reg[HEX_DU + 3 * ip + k] = A.dU ? __ldg(A.dU + eq3[k]) : 0.0;
         }
     } else {
 #pragma unroll
@@ -124,7 +134,7 @@ CMADX_DEV void hex8_point(const FeArgs& A, const int64_t e, const bool live, dou
 #pragma unroll
                 for (int a = 0; a < 8; ++a)
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) U[a][k] = reg[HEX_XI + 56 + 3 * a + k];
+                    for (int k = 0; k < 3; ++k) U[a][k] = reg[HEX_DU + 3 * a + k];
                 strain_from_U<8>(U, gN, deps);
             }
         }
@@ -283,7 +293,7 @@ CMADX_DEV void hex8_point(const FeArgs& A, const int64_t e, const bool live, dou
 }
 
 template <int SOLVER, bool ROT, bool WANT_K, bool LIST>
-__global__ void __launch_bounds__(FE_BLOCK) fe_hex8_kernel(const __grid_constant__ FeArgs A) {
+__global__ void __launch_bounds__(FE_BLOCK, (SOLVER == 0) ? (WANT_K ? 3 : 4) : 1) fe_hex8_kernel(const __grid_constant__ FeArgs A) {
     extern __shared__ __align__(16) double smem[];
     if (!LIST) {
         const int64_t e = (int64_t)blockIdx.x * HEX_EPB + (threadIdx.x >> 3);
@@ -308,7 +318,7 @@ template <int SOLVER, bool ROT, bool WANT_K, bool LIST>
 struct Hex8Launcher {
     static cudaError_t run(const FeArgs& A, cudaStream_t stream, int sms) {
         auto kern = fe_hex8_kernel<SOLVER, ROT, WANT_K, LIST>;
-        const size_t smem = sizeof(double) * HEX_SMEM_DOUBLES;
+        const size_t smem = sizeof(double) * HexLayout<WANT_K>::SMEM_DOUBLES;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         const int64_t nblk = LIST ? 2 * sms : (A.b.n_elems + HEX_EPB - 1) / HEX_EPB;

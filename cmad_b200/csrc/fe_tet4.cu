@@ -136,7 +136,7 @@ CMADX_DEV void tet4_element(const FeArgs& A, const int64_t e, const bool live) {
 }
 
 template <int SOLVER, bool ROT, bool WANT_K, bool LIST>
-__global__ void __launch_bounds__(FE_BLOCK) fe_tet4_kernel(const __grid_constant__ FeArgs A) {
+__global__ void __launch_bounds__(FE_BLOCK, (SOLVER == 0) ? (WANT_K ? 3 : 4) : 1) fe_tet4_kernel(const __grid_constant__ FeArgs A) {
     if (!LIST) {
         const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         tet4_element<SOLVER, ROT, WANT_K>(A, e, e < A.b.n_elems);
