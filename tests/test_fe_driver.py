@@ -241,3 +241,78 @@ def test_cuda_direct_gradient_matches_oracle(cuda_device, family):
     # canonical-coordinate chain rule as `cmad gradient` reports it (parameters.py:326-331)
     gc = gg.copy(); P.transform_grad(gc)
     assert np.all(np.isfinite(gc))
+
+
+# ------------------------------------------------ examples/notch_hosford.yaml at its native size
+def _notch_problem():
+    """examples/notch_hosford.yaml:18-55 on the reference's own mesh (fixture produced by
+    tests/golden/make_notch_mesh.py): near-Tresca Hosford a=100, E=1000, nu=.25, Y=2,
+    Voce S=10 D=2; local Newton 500 iters / 1e-12 with a 100-eval line search; global
+    Newton 15 iters / 1e-8; symmetry on the three min faces, y-max face pulled 0.01 t;
+    4 steps of size 1."""
+    import os
+    from tests.helpers import param_tree
+    m = np.load(os.path.join(os.path.dirname(__file__), "golden", "notch_mesh.npz"))
+    nodes, tets = m["nodes"], m["tets"]
+    values, _, _ = param_tree("hosford", ("voce",), a=100.0, elastic={"E": 1000.0, "nu": 0.25}, active=())
+    values["plastic"]["flow stress"]["initial yield"]["Y"] = 2.0
+    values["plastic"]["flow stress"]["hardening"]["voce"] = {"S": 10.0, "D": 2.0}
+    arr = fe_mesh.block_arrays(nodes, tets)
+    nid = np.arange(nodes.shape[0])
+    ext = nodes.max(axis=0) - nodes.min(axis=0)
+    on = lambda ax, v: nid[np.abs(nodes[:, ax] - v) <= 1e-7 * ext[ax]]      # coordinate side sets
+    pin = np.concatenate([on(0, nodes[:, 0].min()) * 3, on(1, nodes[:, 1].min()) * 3 + 1,
+                          on(2, nodes[:, 2].min()) * 3 + 2])
+    load = on(1, nodes[:, 1].max()) * 3 + 1
+    bcs = drv.DirichletBCs(np.concatenate([pin, load]),
+                           lambda t: np.concatenate([np.zeros(len(pin)), np.full(len(load), 0.01 * t)]))
+    ur, uc, scatter = fe_mesh.coo_dedup(arr.elem_eq.numpy())
+    local = dict(max_iters=500, abs_tol=1e-12, rel_tol=1e-12, ls_max_evals=100)
+    glob = {"max iters": 15, "abs tol": 1e-8, "rel tol": 1e-8}
+    return values, nodes, arr, bcs, drv.SparsePattern(ur, uc, arr.n_dofs), scatter, local, glob
+
+
+def _notch_oracle_run(steps):
+    values, nodes, arr, bcs, pattern, scatter, local, glob = _notch_problem()
+    prob = oc.describe(values, None, newton_mode="traced", strain_comps=9, **local)
+    eq = arr.elem_eq.numpy(); geo = (arr.grad_N.numpy(), arr.det.numpy(), arr.quad_w.numpy())
+    rec = {}
+
+    def asm(U, xi_prev):
+        o = fe_oracle.assemble_block(prob, eq, U, xi_prev, *geo)
+        rec.update(o)
+        return o["R"], fe_oracle.coo_dedup_sum(o["K_elem"].reshape(-1), scatter, len(pattern.rows)), o["xi"]
+    out = drv.fe_quasistatic_drive(asm, pattern, bcs, np.zeros(arr.n_dofs), np.zeros((arr.n_elems, 1, 7)),
+                                   np.arange(steps + 1.0), glob)
+    return out, rec, (values, arr, bcs, pattern, scatter, local, glob)
+
+
+def test_notch_hosford_deck_converges_over_the_oracle():
+    (U_steps, xi, J, logs), rec, _ = _notch_oracle_run(2)
+    assert all(l.residual_norms[-1] < 1e-8 * max(l.residual_norms[0], 1.0) or l.residual_norms[-1] < 1e-8 for l in logs)
+    assert all(l.iters <= 15 for l in logs)
+    alpha = xi[:, 0, 6]
+    assert (alpha > 0).mean() > 0.5 and alpha.max() > 3.0 * alpha.mean()     # strain concentrates at the notch
+    assert any(a < 1.0 for l in logs for a in l.alphas)                      # the global line search engaged
+    assert np.isfinite(U_steps).all()
+
+
+@pytest.mark.gpu
+def test_notch_hosford_deck_cuda_matches_oracle(cuda_device):
+    """The reference's example deck at its native size through the CUDA assembler vs the
+    oracle assembler: same global Newton history, displacements to 1e-8 (a=100 is
+    ill-conditioned: local iteration paths may differ at rounding level, the converged
+    states may not)."""
+    import torch
+    from cmad_b200 import fe, material_from_values
+    (Uo, xio, _, lo), rec, (values, arr, bcs, pattern, scatter, local, glob) = _notch_oracle_run(4)
+    arr_d = arr.to(cuda_device)
+    r_plan = fe.SegmentPlan(arr.elem_eq.numpy().reshape(-1), arr.n_dofs, device=cuda_device)
+    k_plan = fe.SegmentPlan(scatter, len(pattern.rows), device=cuda_device)
+    nw = fe.fe_newton_settings(max_iters=500, abs_tol=1e-12, rel_tol=1e-12, ls_max_evals=100)
+    asm = drv.cuda_assembler(material_from_values(values), nw, arr_d, r_plan, k_plan)
+    xi0 = torch.zeros((arr.n_elems, 1, 7), dtype=torch.float64, device=cuda_device)
+    Ug, xig, _, lg = drv.fe_quasistatic_drive(asm, pattern, bcs, np.zeros(arr.n_dofs), xi0, np.arange(5.0), glob)
+    assert [l.iters for l in lg] == [l.iters for l in lo]
+    assert np.abs(Ug - Uo).max() < 1e-8 * np.abs(Uo).max()
+    assert np.abs(xig.cpu().numpy() - xio).max() < 1e-8 * np.abs(xio).max()
