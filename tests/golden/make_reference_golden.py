@@ -1,0 +1,384 @@
+"""Golden vectors produced by EXECUTING THE REFERENCE'S OWN, UNMODIFIED SOURCE
+(`/root/reference/cmad/...`) for the hot path.
+
+The reference is pure Python on JAX; JAX is not installable in the build
+container.  `tests/golden/jaxshim/` provides the slice of the JAX API the path
+uses (arrays, forward-mode AD transforms, eager control flow, pytrees) on NumPy
+fp64, so the reference's constitutive code - `SmallElasticPlastic._residual_fn`,
+the effective stresses, hardening, `cond_residual`, `make_newton_solve` and its
+`custom_jvp` IFT rule, `line_search`, the imperative `newton_solve`, `Model`'s
+AD products, `Parameters`, `MPAdjointObjective` / `MPDirectObjective`,
+`Calibration`, and the FE per-IP evaluator of `GlobalResidual._for_model_coupled`
+- runs line by line as written.  Only the arithmetic library differs from a real
+JAX run (NumPy/LAPACK instead of XLA), i.e. rounding-level.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_reference_golden.py [--jobs 8]
+
+Writes tests/golden/ref_*.npz; the fixtures are committed, `/root/reference` is
+never read at test time.
+"""
+from __future__ import annotations
+
+import argparse
+import multiprocessing as mp
+import os
+import sys
+import types
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REFERENCE = "/root/reference"
+
+
+def _enter_reference():
+    sys.path[:0] = [os.path.join(HERE, "jaxshim"), REFERENCE, ROOT]
+    for m in ("netCDF4", "gmsh", "pyamg", "matplotlib", "matplotlib.pyplot", "sympy", "jsonschema"):
+        try:
+            __import__(m)
+        except ImportError:
+            sys.modules[m] = types.ModuleType(m)
+
+
+_enter_reference()
+
+import numpy as np  # noqa: E402
+
+import jax  # noqa: E402  (the shim)
+from jax import _core  # noqa: E402
+from cmad.models.deriv_types import DerivType  # noqa: E402
+from cmad.models.effective_stress import conventional_effective_stress_fun  # noqa: E402
+from cmad.models.elastic_stress import isotropic_linear_elastic_stress  # noqa: E402
+from cmad.models.global_fields import GlobalFieldsAtPoint, mp_U_from_F  # noqa: E402
+from cmad.models.hardening import combined_hardening_fun, get_hardening_funs  # noqa: E402
+from cmad.models.nonlinear_solver import make_newton_solve, newton_solve  # noqa: E402
+from cmad.models.small_elastic_plastic import SmallElasticPlastic, compute_yield_fun_and_normal  # noqa: E402
+from cmad.objectives.mp_objective import MPAdjointObjective, MPDirectObjective  # noqa: E402
+from cmad.parameters.parameters import Parameters  # noqa: E402
+from cmad.qois.calibration import Calibration  # noqa: E402
+from functools import partial  # noqa: E402
+
+from cmad_b200 import synthetic  # noqa: E402  (input generator only: the inputs are stored in the fixture)
+
+UP = [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)]
+
+
+sys.path.insert(0, HERE)
+from materials import NEWTON, active_all_scalars, const_like, material, objective_trees  # noqa: E402
+
+
+def parameters(values):
+    return Parameters(values, active_all_scalars(values), const_like(values, None))
+
+
+def vec6(T):
+    T = np.asarray(T)
+    return np.array([T[i, j] for i, j in UP])
+
+
+def yield_fun_of(model, values):
+    kind = next(iter(values["plastic"]["effective stress"]))
+    return partial(compute_yield_fun_and_normal, def_type=0,
+                   elastic_stress=isotropic_linear_elastic_stress,
+                   effective_stress=conventional_effective_stress_fun(kind),
+                   hardening=partial(combined_hardening_fun, hardening_funs=get_hardening_funs()),
+                   uniaxial_stress_idx=0, is_complex=False)
+
+
+# --------------------------------------------------------------------------- #
+#  A. traced Newton (make_newton_solve + IFT rule), batched over points       #
+# --------------------------------------------------------------------------- #
+def _traced_chunk(job):
+    kind, newton_key, lo, hi, steps, seed, scale, with_tangent = job
+    values = material(kind)
+    P = parameters(values)
+    model = SmallElasticPlastic(P)
+    solve = make_newton_solve(model._residual, **NEWTON[newton_key])
+    yf = yield_fun_of(model, values)
+    d, d2, a = synthetic.path_params(seed, lo, hi - lo, diag_only=kind.startswith("hosford"))
+    n = hi - lo
+    nP = P.num_params
+    out = {k: [] for k in ("grad_u", "xi_prev", "xi", "iters", "flags", "sigma", "dsig_dgradu",
+                           "dxi_dgradu", "dC_dp", "dC_dxi", "dC_dxi_prev", "dxi_dp", "dsig_dp")}
+    rng = np.random.default_rng(1000 + lo)
+    xi_prev = [[np.zeros(6), np.zeros(1)] for _ in range(n)]
+    for t in steps:
+        e6 = synthetic.strain_at_step(d, d2, a * scale, t)                    # (6, n)
+        rec = {k: [] for k in out}
+        for i in range(n):
+            e = e6[:, i]
+            w = rng.normal(size=3) * 1e-3                                     # rigid-rotation part: must not matter
+            gu = np.array([[e[0], e[1] + w[0], e[2] + w[1]],
+                           [e[1] - w[0], e[3], e[4] + w[2]],
+                           [e[2] - w[1], e[4] - w[2], e[5]]])
+            U = mp_U_from_F(np.eye(3) + gu)
+            xp = xi_prev[i]
+            params = P.values
+            xi = solve(xp, params, U, U)
+            iters = int(_core.WHILE_LOG[-1][1][0])
+            xi_np = [np.asarray(x) for x in xi]
+            _, f0, _ = yf(xp, xp, params, U, U)
+            _, f1, _ = yf(xi_np, xp, params, U, U)
+            pl = lambda f: bool(f > 1e-14 or abs(f) < 1e-14)                  # noqa: E731  paths.py:26
+            flags = (1 if pl(float(f0)) else 0) | (2 if pl(float(f1)) else 0)
+            sig = np.asarray(model.cauchy(xi_np, xp, params, U, U))
+            rec["grad_u"].append(gu.reshape(9)); rec["xi_prev"].append(np.concatenate(xp))
+            rec["xi"].append(np.concatenate(xi_np)); rec["iters"].append(iters); rec["flags"].append(flags)
+            rec["sigma"].append(vec6(sig))
+            # Model AD products at the converged state (model.py:126-133, parameters.py:368-377)
+            jac = model._jacobian
+            rec["dC_dxi"].append(np.hstack([np.asarray(b) for b in jac[DerivType.DXI](xi_np, xp, params, U, U)]))
+            rec["dC_dxi_prev"].append(np.hstack([np.asarray(b) for b in jac[DerivType.DXI_PREV](xi_np, xp, params, U, U)]))
+            dcdp = jac[DerivType.DPARAMS](xi_np, xp, params, U, U)
+            flat = [np.asarray(x).reshape(7, -1) for x in jax.tree_util.tree_leaves(dcdp)]
+            rec["dC_dp"].append(np.hstack(flat))                              # (7, P) all leaves, flatten order
+            if with_tangent:
+                def state_and_stress(U_, p_):
+                    x = solve(xp, p_, U_, U)
+                    return jax.numpy.concatenate([jax.numpy.ravel(b) for b in x]), model.cauchy(x, xp, p_, U_, U)
+                (dx_dU, ds_dU) = jax.jacfwd(state_and_stress, argnums=0)(U, params)
+                rec["dxi_dgradu"].append(np.asarray(dx_dU.grad_fields["u"]).reshape(7, 9))
+                rec["dsig_dgradu"].append(np.asarray(ds_dU.grad_fields["u"]).reshape(9, 9))
+                (dx_dp, ds_dp) = jax.jacfwd(state_and_stress, argnums=1)(U, params)
+                rec["dxi_dp"].append(np.hstack([np.asarray(x).reshape(7, -1) for x in jax.tree_util.tree_leaves(dx_dp)]))
+                rec["dsig_dp"].append(np.hstack([np.asarray(x).reshape(9, -1) for x in jax.tree_util.tree_leaves(ds_dp)]))
+            xi_prev[i] = xi_np
+        for k in out:
+            if rec[k]:
+                out[k].append(np.array(rec[k]))
+    return {k: np.array(v) for k, v in out.items() if v}, nP       # each (steps, n, ...)
+
+
+def traced(pool, kind, newton_key, n, steps, seed=22, scale=1.0, chunk=4, with_tangent=True):
+    jobs = [(kind, newton_key, lo, min(lo + chunk, n), steps, seed, scale, with_tangent)
+            for lo in range(0, n, chunk)]
+    parts = pool.map(_traced_chunk, jobs)
+    res = {k: np.concatenate([p[0][k] for p in parts], axis=1) for k in parts[0][0]}
+    values = material(kind)
+    P = parameters(values)
+    res["param_names"] = np.array(P._names)
+    res["param_sizes"] = np.array(P.flat_param_sizes)
+    res["steps"] = np.array(steps)
+    return res
+
+
+# --------------------------------------------------------------------------- #
+#  B. imperative Newton through the Model object (newton_solve -> solver.json) #
+# --------------------------------------------------------------------------- #
+def two_leg_F(seed, nsteps, scale=1.0, diag_only=False):
+    d, d2, a = synthetic.path_params(seed, 0, 1, diag_only=diag_only)
+    F = np.repeat(np.eye(3)[:, :, None], nsteps + 1, axis=2)
+    for t in range(1, nsteps + 1):
+        e = synthetic.strain_at_step(d, d2, a * scale, int(round(t * 100 / nsteps)))[:, 0]
+        F[:, :, t] += np.array([[e[0], e[1], e[2]], [e[1], e[3], e[4]], [e[2], e[4], e[5]]])
+    return F
+
+
+def _imperative_job(job):
+    kind, F = job
+    values = material(kind)
+    model = SmallElasticPlastic(parameters(values))
+    N = F.shape[2] - 1
+    xi = np.zeros((N + 1, 7)); sig = np.zeros((N + 1, 6)); it = np.zeros(N + 1, int); cn = np.zeros(N + 1)
+    model.set_xi_to_init_vals()
+    for step in range(1, N + 1):
+        model.gather_global(mp_U_from_F(F[:, :, step]), mp_U_from_F(F[:, :, step - 1]))
+        it[step], cn[step] = newton_solve(model)                  # mp_objective.py:83, defaults 10/1e-14/1e-14
+        xi[step] = np.concatenate([np.asarray(b) for b in model.xi()])
+        model.seed_none()
+        model.evaluate_cauchy()
+        sig[step] = vec6(model.Sigma())
+        model.advance_xi()
+    return dict(F=F, xi=xi, sigma=sig, iters=it, cnorm=cn)
+
+
+# --------------------------------------------------------------------------- #
+#  C. MP adjoint / direct objectives with the Calibration QoI                 #
+# --------------------------------------------------------------------------- #
+def _objective_job(job):
+    kind, scaled, F, weight = job
+    values, act, tr = objective_trees(kind, scaled)
+    P = Parameters(values, act, tr)
+    model = SmallElasticPlastic(P)
+    N = F.shape[2] - 1
+    # data: the stress history at the "true" parameters (test_J2_fd_checks.py:21-47)
+    data = np.zeros((3, 3, N + 1))
+    model.set_xi_to_init_vals()
+    for step in range(1, N + 1):
+        model.gather_global(mp_U_from_F(F[:, :, step]), mp_U_from_F(F[:, :, step - 1]))
+        newton_solve(model)
+        model.seed_none(); model.evaluate_cauchy()
+        data[:, :, step] = model.Sigma().copy()
+        model.advance_xi()
+    qoi = Calibration(model, data, weight)
+    true_vals = P.flat_active_values(False)
+    offset = 1.1 * true_vals                                      # test_J2_fd_checks.py:326
+    P.set_active_values_from_flat(offset, False)
+    x = P.flat_active_values(True)                                # canonical coordinates of the offset point
+    res = {}
+    for name, ctor in (("adjoint", MPAdjointObjective), ("direct", MPDirectObjective)):
+        P.set_active_values_from_flat(offset, False)
+        J, g = ctor(qoi, F).evaluate(x)
+        res[f"J_{name}"], res[f"grad_{name}"] = float(J), np.asarray(g, float)
+    res.update(F=F, data=data, weight=weight, x_canonical=x, active_native=offset,
+               active_idx=np.asarray(P.active_idx), param_names=np.array(P._names))
+    return res
+
+
+
+# --------------------------------------------------------------------------- #
+#  D. FE element kernels: per_element_R_and_K_coupled / per_element_R_coupled  #
+#     over the per-IP COUPLED evaluator (displacement and mixed u-p)            #
+# --------------------------------------------------------------------------- #
+def _fe_job(job):
+    from cmad.fem.assembly import per_element_R_and_K_coupled, per_element_R_coupled
+    from cmad.fem.element_family import ElementFamily
+    from cmad.fem.interpolants import hex_linear, tet_linear
+    from cmad.fem.mesh import _LOCAL_EDGES_PER_ELEMENT
+    from cmad.fem.precompute import BlockIPGeometryPerElem, BlockIPGeometryShared
+    from cmad.fem.quadrature import hex_quadrature, tet_quadrature
+    from cmad.global_residuals.modes import GlobalResidualMode
+    from cmad.global_residuals.small_disp_equilibrium import SmallDispEquilibrium
+    from jax.flatten_util import ravel_pytree
+
+    family, kind, mixed, seed, n_elems = job
+    rng = np.random.default_rng(seed)
+    values = material(kind)
+    P = parameters(values)
+    model = SmallElasticPlastic(P)
+    gr = SmallDispEquilibrium(ndims=3, mixed=mixed, stabilization_multiplier=1.0)
+    ev = gr.for_model(model, GlobalResidualMode.COUPLED)            # local Newton 20 / 1e-12 / 1e-12
+    unravel_xi = ravel_pytree(model._init_xi)[1]
+    if family == "hex8":
+        rule, interp, fam = hex_quadrature(2), hex_linear, ElementFamily.HEX_LINEAR
+        Xref = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1],
+                         [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], float) * 0.5
+    else:
+        rule, interp, fam = tet_quadrature(1), tet_linear, ElementFamily.TET_LINEAR
+        Xref = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], float)
+    n_b, n_ip = Xref.shape[0], len(rule.w)
+    sh = [interp(np.asarray(x)) for x in rule.xi]
+    N = np.array([np.asarray(s_.N) for s_ in sh])                    # (n_ip, n_b)
+    gNref = np.array([np.asarray(s_.grad_N) for s_ in sh])           # (n_ip, n_b, 3)
+    edges = np.asarray(_LOCAL_EDGES_PER_ELEMENT[fam])
+    block_shapes = [(n_b, 3), (n_b, 1)] if mixed else [(n_b, 3)]
+    shared = BlockIPGeometryShared(quad_w=np.asarray(rule.w),
+                                   field_N_per_block=tuple(N for _ in block_shapes))
+    rec = {k: [] for k in ("X", "U", "p", "xi_prev", "grad_N", "det", "h", "xi", "R_u", "R_p",
+                           "K_uu", "K_up", "K_pu", "K_pp", "R_only_u", "R_only_p")}
+    for e in range(n_elems):
+        X = Xref + rng.normal(size=Xref.shape) * 0.06               # distorted element
+        iso = np.einsum("ai,paj->pij", X, gNref)                     # precompute.py:239-241
+        det = np.linalg.det(iso)
+        gN = np.einsum("pnj,pji->pni", gNref, np.linalg.inv(iso))     # precompute.py:250-257
+        ev_ = X[edges]
+        h = float(np.sqrt(np.mean(np.sum((ev_[:, 1] - ev_[:, 0]) ** 2, axis=-1))))   # mesh.py:631-636
+        geom = BlockIPGeometryPerElem(iso_jac_det=det, coords_ip=np.einsum("pa,ai->pi", N, X),
+                                      field_grad_N_phys_per_block=tuple(gN for _ in block_shapes),
+                                      element_size=h)
+        xi_prev = np.zeros((n_ip, 7))
+        for step in range(2):
+            ramp = np.array([0.004, -0.001, 0.0015]) if step == 0 else np.array([0.003, 0.004, -0.002])
+            U = X * ramp[None, :] * (1.0 + step) + rng.normal(size=X.shape) * 4e-4
+            Ue = [U]
+            if mixed:
+                pe = rng.normal(size=(n_b, 1)) * 40.0 - 100.0
+                Ue = [U, pe]
+            Uprev = [np.zeros_like(u) for u in Ue]
+            Rb, Kb, xi = per_element_R_and_K_coupled(
+                Ue, Uprev, P.values, xi_prev, geom, shared, ev["R_and_dR_dU_and_xi"], unravel_xi,
+                {}, block_shapes, 0.0)
+            Ronly = per_element_R_coupled(
+                Ue, Uprev, P.values, xi_prev, geom, shared, ev["R"], unravel_xi, {}, block_shapes, 0.0)
+            rec["X"].append(X); rec["U"].append(U); rec["xi_prev"].append(xi_prev.copy())
+            rec["grad_N"].append(gN); rec["det"].append(det); rec["h"].append(h)
+            rec["xi"].append(np.asarray(xi))
+            rec["R_u"].append(np.asarray(Rb[0])); rec["R_only_u"].append(np.asarray(Ronly[0]))
+            rec["K_uu"].append(np.asarray(Kb[0][0]).reshape(3 * n_b, 3 * n_b))
+            if mixed:
+                rec["p"].append(pe[:, 0])
+                rec["R_p"].append(np.asarray(Rb[1])[:, 0]); rec["R_only_p"].append(np.asarray(Ronly[1])[:, 0])
+                rec["K_up"].append(np.asarray(Kb[0][1]).reshape(3 * n_b, n_b))
+                rec["K_pu"].append(np.asarray(Kb[1][0]).reshape(n_b, 3 * n_b))
+                rec["K_pp"].append(np.asarray(Kb[1][1]).reshape(n_b, n_b))
+            xi_prev = np.asarray(xi)
+    out = {k: np.array(v) for k, v in rec.items() if v}
+    out["quad_w"], out["N"] = np.asarray(rule.w), N
+    return out
+
+
+# --------------------------------------------------------------------------- #
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--jobs", type=int, default=os.cpu_count())
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    pool = mp.Pool(a.jobs)
+    only = set(a.only.split(",")) if a.only else None
+
+    if only is None or "traced" in only:
+        out = {}
+        for kind, key, n, steps, scale in (
+                ("J2", "mp", 48, (12, 30, 48, 66, 84), 1.0),
+                ("J2", "fe", 16, (20, 60, 90), 1.0),
+                ("J2_kappa_mu", "mp", 8, (40, 80), 1.0),
+                ("hill", "mp", 32, (15, 45, 75), 1.0),
+                ("hill_rot", "fe", 32, (15, 45, 75), 1.0),
+                ("hosford", "mp", 32, (15, 45, 75), 1.0),
+                ("hosford_notch", "notch", 16, (25, 75), 2.0)):
+            r = traced(pool, kind, key, n, steps, scale=scale)
+            for k, v in r.items():
+                out[f"{kind}.{key}.{k}"] = v
+            print("traced", kind, key, "iters", np.bincount(r["iters"].ravel()), "flags", np.bincount(r["flags"].ravel()))
+        np.savez_compressed(os.path.join(HERE, "ref_traced_newton.npz"), **out)
+
+    if only is None or "imperative" in only:
+        from oracle import analytic
+        jobs, names = [], []
+        for kind in ("J2", "hill", "hill_rot", "hosford"):
+            for pname, F in (("uniaxial", None), ("biaxial", None),
+                             ("twoleg", two_leg_F(7, 40, diag_only=kind == "hosford"))):
+                if F is None:
+                    mask = analytic.stress_masks_3d()[0 if pname == "uniaxial" else 1]
+                    _, strain, _ = analytic.plastic_fields(mask, num_steps=30)
+                    F = analytic.deformation_gradient_history(strain)
+                jobs.append((kind, F)); names.append(f"{kind}.{pname}")
+        out = {}
+        for nm, r in zip(names, pool.map(_imperative_job, jobs)):
+            for k, v in r.items():
+                out[f"{nm}.{k}"] = v
+            print("imperative", nm, "iters", np.bincount(r["iters"]))
+        np.savez_compressed(os.path.join(HERE, "ref_imperative_newton.npz"), **out)
+
+    if only is None or "objective" in only:
+        w = np.array([[1.0, 0.5, 0.0], [0.5, 1.0, 0.0], [0.0, 0.0, 0.25]])
+        jobs, names = [], []
+        for kind in ("J2", "hill", "hosford"):
+            for scaled in (True, False):
+                jobs.append((kind, scaled, two_leg_F(11, 24, scale=1.5, diag_only=kind == "hosford"), w))
+                names.append(f"{kind}.{'scaled' if scaled else 'native'}")
+        out = {}
+        for nm, r in zip(names, pool.map(_objective_job, jobs)):
+            for k, v in r.items():
+                out[f"{nm}.{k}"] = v
+            print("objective", nm, r["J_adjoint"], r["grad_adjoint"], r["grad_direct"])
+        np.savez_compressed(os.path.join(HERE, "ref_mp_objectives.npz"), **out)
+
+    if only is None or "fe" in only:
+        jobs, names = [], []
+        for family in ("tet4", "hex8"):
+            for kind in ("J2", "hill_rot", "hosford"):
+                for mixed in (False, True):
+                    jobs.append((family, kind, mixed, 5 + len(jobs), 3 if family == "tet4" else 2))
+                    names.append(f"{family}.{kind}.{'mixed' if mixed else 'disp'}")
+        out = {}
+        for nm, r in zip(names, pool.map(_fe_job, jobs, chunksize=1)):
+            for k, v in r.items():
+                out[f"{nm}.{k}"] = v
+            print("fe", nm, "alpha max", r["xi"][..., 6].max())
+        np.savez_compressed(os.path.join(HERE, "ref_fe_elements.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()
