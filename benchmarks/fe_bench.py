@@ -125,6 +125,22 @@ def main():
                           "plastic_fraction": float(((fl & 2) != 0).double().mean()),
                           "mean_newton_iters": float(it.double().mean()),
                           "bailed_elements": mpmod.debug_bail_count() if base["solver"] == "j2-radial" else 0}))
+    if "MIX" in variants:
+        # mixed u-p formulation: K3 with the momentum stress dev(cauchy) - p I + the pressure-block
+        # kernel; algorithmic bytes = K3's + p_e, h, R_p and the (u,p), (p,u), (p,p) streams
+        n_b = arr.n_basis
+        arr_m = fe_mesh.block_arrays(nodes, conn, device=dev, mixed=True)
+        rng = np.random.default_rng(5)
+        Um = torch.cat([U, torch.from_numpy(-60.0 + 5.0 * rng.standard_normal(nodes.shape[0])).to(dev)])
+        l0 = mpmod.launch_count()
+        ms, ms_min = timed(lambda: fe.assemble_element_block_mixed(mat, nw, arr_m, Um, xi))
+        launches = (mpmod.launch_count() - l0) // (args.steps + args.warmup)
+        b = ALG_BYTES[args.family]["K3"] + 8 * (n_b + 1 + n_b + 2 * 3 * n_b * n_b + n_b * n_b)
+        print(json.dumps({**base, "kernel": "K3-mixed fe_block u-p (R_u, R_p, K_uu, K_up, K_pu, K_pp, xi) + atomic R",
+                          "ms_per_step": ms, "ms_min": ms_min, "elements_per_s": n_e / ms * 1e3,
+                          "alg_bytes_per_elem": b, "achieved_gbs": n_e * b / ms / 1e6,
+                          "frac_hbm": n_e * b / ms / 1e6 / hbm, "launches_per_step": launches}))
+        del arr_m, Um
     if "K4" in variants:
         o4 = {k: out[k] for k in ("xi", "R_elem")}
         ms, ms_min = timed(lambda: fe.fe_block_launch(mat, nw, arr, U, xi, tuple(o4), o4))

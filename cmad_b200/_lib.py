@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcmad_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
 SOURCES = ["api.cu", "mp_update.cu", "mp_update_j2.cu", "elastic_update.cu", "mp_sens.cu",
-           "fe_block.cu", "fe_tet4.cu", "fe_hex8.cu", "fe_vjp.cu", "fe_scatter.cu"]
+           "fe_block.cu", "fe_tet4.cu", "fe_hex8.cu", "fe_mixed.cu", "fe_vjp.cu", "fe_scatter.cu"]
 
 # ---- enums (mirror include/cmad_b200.h) ---------------------------------
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(5)
@@ -71,6 +71,12 @@ class FeBlock(C.Structure):
                 ("quad_w", C.c_void_p), ("xi", C.c_void_p), ("R_elem", C.c_void_p),
                 ("K_elem", C.c_void_p), ("R_global", C.c_void_p), ("sigma", C.c_void_p),
                 ("iters", C.c_void_p), ("flags", C.c_void_p)]
+
+
+class FeMixed(C.Structure):
+    _fields_ = [("elem_eq_p", C.c_void_p), ("N", C.c_void_p), ("h", C.c_void_p),
+                ("stab_mult", C.c_double), ("R_p_elem", C.c_void_p), ("K_up", C.c_void_p),
+                ("K_pu", C.c_void_p), ("K_pp", C.c_void_p), ("R_global", C.c_void_p)]
 
 
 class CmadxError(RuntimeError):
@@ -150,6 +156,8 @@ def lib() -> C.CDLL:
     L.cmadx_mp_objective_direct.argtypes = obj_args
     L.cmadx_fe_block_assemble.argtypes = [C.POINTER(Material), C.POINTER(Newton),
                                           C.POINTER(FeBlock), C.c_void_p]
+    L.cmadx_fe_block_assemble_mixed.argtypes = [C.POINTER(Material), C.POINTER(Newton),
+                                                C.POINTER(FeBlock), C.POINTER(FeMixed), C.c_void_p]
     L.cmadx_fe_block_jvp.argtypes = [C.POINTER(Material), C.POINTER(C.c_int32), C.c_int32,
                                      C.POINTER(C.c_double), C.POINTER(FeBlock), C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]

@@ -500,14 +500,26 @@ static int check_fe_block(const cmadx_material_t* mat, const cmadx_fe_block_t* b
     A->b = b;
     A->bail_count = nullptr; A->bail_list = nullptr; A->bail_cap = 0;
     A->xi_state = nullptr; A->dxi_prev = nullptr; A->dU = nullptr; A->n_active = 0;
+    A->mix_eq_p = nullptr; A->mix_N = nullptr;
     return CMADX_OK;
 }
 
-int cmadx_fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* newton,
-                            const cmadx_fe_block_t* blk, void* stream) {
+static int fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* newton,
+                             const cmadx_fe_block_t* blk, const cmadx_fe_mixed_t* mix, void* stream) {
     FeArgs A;
     if (int rc = check_fe_block(mat, blk, &A)) return rc;
     if (int rc = make_dev_newton(newton, &A.nw)) return rc;
+    if (mix) {
+        if (blk->n_elems > 0) {
+            if (!mix->elem_eq_p || !mix->N || !mix->h) return CMADX_EINVAL;
+            auto misaligned = [](const void* p, uintptr_t a) { return p && (reinterpret_cast<uintptr_t>(p) % a) != 0; };
+            if (misaligned(mix->K_up, 32) || misaligned(mix->K_pu, 32) || misaligned(mix->K_pp, 32) ||
+                misaligned(mix->elem_eq_p, 16))
+                return CMADX_EINVAL;
+        }
+        A.mix_eq_p = mix->elem_eq_p;
+        A.mix_N = mix->N;
+    }
     const cmadx_fe_block_t& b = *blk;
     if (b.n_elems == 0) return CMADX_OK;
     cudaStream_t s = (cudaStream_t)stream;
@@ -530,7 +542,25 @@ int cmadx_fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* n
     }
     if (e != cudaSuccess) return cuda_fail(e);
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (mix && (mix->R_p_elem || mix->K_up || mix->K_pu || mix->K_pp || mix->R_global)) {
+        const double kappa = A.m.lam + 2.0 * A.m.mu / 3.0;      // ElasticConstants.kappa
+        e = launch_fe_mixed_pressure(b, *mix, kappa, A.m.mu, s);
+        if (e != cudaSuccess) return cuda_fail(e);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
     return CMADX_OK;
+}
+
+int cmadx_fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* newton,
+                            const cmadx_fe_block_t* blk, void* stream) {
+    return fe_block_assemble(mat, newton, blk, nullptr, stream);
+}
+
+int cmadx_fe_block_assemble_mixed(const cmadx_material_t* mat, const cmadx_newton_t* newton,
+                                  const cmadx_fe_block_t* blk, const cmadx_fe_mixed_t* mix,
+                                  void* stream) {
+    if (!mix) return CMADX_EINVAL;
+    return fe_block_assemble(mat, newton, blk, mix, stream);
 }
 
 int cmadx_fe_block_jvp(const cmadx_material_t* mat, const int32_t* active_pid, int32_t n_active,

@@ -27,6 +27,21 @@ CMADX_DEV void st256(double* p, double a, double b, double c, double d) {
                  : "memory");
 }
 
+// mixed u-p (cmad/global_residuals/small_disp_equilibrium.py:87-101): the momentum stress is
+// dev(cauchy) - p I with p interpolated from the pressure dofs, so K_uu sees P_dev D
+template <bool WANT_D>
+CMADX_DEV void mixed_momentum_stress(const double p, double (&sg)[6], double (&D)[6][6]) {
+    const double m = (sg[0] + sg[3] + sg[5]) / 3.0 + p;
+    sg[0] -= m; sg[3] -= m; sg[5] -= m;
+    if (WANT_D) {
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            const double t = (D[0][b] + D[3][b] + D[5][b]) / 3.0;
+            D[0][b] -= t; D[3][b] -= t; D[5][b] -= t;
+        }
+    }
+}
+
 struct PointOut {
     double x[7];
     double sg[6];   // global cauchy

@@ -164,6 +164,26 @@ CMADX_DEV void hex8_point(const FeArgs& A, const int64_t e, const bool live, dou
         if (ebail && live && ip == 0) append_bail(A, e);
     }
     const bool emit = live && !ebail;
+    if (emit) {
+        const int64_t p = e * 8 + ip;
+        if (b.iters) b.iters[p] = o.iters;
+        if (b.flags) b.flags[p] = o.flags;
+        if (b.sigma) {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) b.sigma[p * 6 + a] = o.sg[a];
+        }
+    }
+    if constexpr (SOLVER < FE_JVP) {
+        if (A.mix_eq_p) {
+            double p = 0.0;
+            if (live) {
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+                    p = fma(__ldg(A.mix_N + ip * 8 + a), __ldg(b.U + __ldg(A.mix_eq_p + e * 8 + a)), p);
+            }
+            mixed_momentum_stress<WANT_K>(p, o.sg, D);
+        }
+    }
     {   // own record slots and own xi slot: no other thread has touched or read them yet
         double* rec = recs + ip * HEX_REC;
         if (WANT_K) {
@@ -177,15 +197,6 @@ CMADX_DEV void hex8_point(const FeArgs& A, const int64_t e, const bool live, dou
         for (int a = 0; a < 6; ++a) rec[HEX_SW + a] = o.sg[a] * wdv;
 #pragma unroll
         for (int c = 0; c < 7; ++c) reg[HEX_XI + ip * 7 + c] = o.x[c];
-    }
-    if (emit) {
-        const int64_t p = e * 8 + ip;
-        if (b.iters) b.iters[p] = o.iters;
-        if (b.flags) b.flags[p] = o.flags;
-        if (b.sigma) {
-#pragma unroll
-            for (int a = 0; a < 6; ++a) b.sigma[p * 6 + a] = o.sg[a];
-        }
     }
     __syncwarp();
     if (emit) {

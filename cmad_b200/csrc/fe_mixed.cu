@@ -1,0 +1,113 @@
+// Pressure blocks of the mixed u-p (stabilised equal-order) formulation of
+// SmallDispEquilibrium (cmad/global_residuals/small_disp_equilibrium.py:87-111):
+//   R_p[a]         = sum_ip ( -(p + hydro)/kappa N_a - tau gradN_a . grad p ) w dv
+//   K_up[(a,i), b] = d R_u[a,i] / d p_b = -sum_ip gradN[a,i] N_b w dv
+//   K_pu[a, (b,k)] = d R_p[a] / d U[b,k] = -sum_ip N_a gradN[b,k] w dv      (hydro = kappa tr eps)
+//   K_pp[a, b]     = -sum_ip ( N_a N_b / kappa + tau gradN_a . gradN_b ) w dv
+// with tau = mult * h^2 / (2 mu).  None of these depends on the local state xi: the local
+// Newton only enters the momentum block (R_u, K_uu), which the K3 kernels produce with the
+// momentum stress dev(cauchy) - p I (fe_common.cuh: mixed_momentum_stress).  The four blocks
+// are emitted as the reference's (r, s)-ordered COO value streams
+// (cmad/fem/assembly.py:722-732).  HBM-bound, no Newton: one thread per (element, node a)
+// owning row a of R_p / K_pu / K_pp and rows 3a..3a+2 of K_up; sums over the integration
+// points in fixed order (bit-reproducible); 256-bit stores of whole 32-byte sectors.
+#include "fe_common.cuh"
+
+namespace cmadx {
+namespace {
+
+template <int NB, int NIP>
+__global__ void __launch_bounds__(FE_BLOCK) fe_mixed_pressure_kernel(const cmadx_fe_block_t b,
+                                                                     const cmadx_fe_mixed_t mx,
+                                                                     const double kappa, const double mu) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = t / NB;
+    const int a = (int)(t - e * NB);
+    const bool live = e < b.n_elems;
+    if (__all_sync(0xffffffffu, !live)) return;
+    const int64_t el = live ? e : 0;
+    // this thread's node: displacement and pressure dofs; the sums over the nodes of the
+    // element (p, tr eps, grad p) are butterfly reductions over its NB lanes
+    double Ua[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Ua[k] = __ldg(b.U + __ldg(b.elem_eq + el * (NB * 3) + 3 * a + k));
+    const double pa = __ldg(b.U + __ldg(mx.elem_eq_p + el * NB + a));
+    const double h = __ldg(mx.h + el);
+    const double tau = mx.stab_mult * 0.5 * h * h / mu;
+    double Rp = 0.0, Kpu[NB][3], Kup[3][NB], Kpp[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+        Kpp[c] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { Kpu[c][k] = 0.0; Kup[k][c] = 0.0; }
+    }
+#pragma unroll 1
+    for (int q = 0; q < NIP; ++q) {
+        const double* g = b.grad_N + (el * NIP + q) * (NB * 3);
+        double gN[NB][3], N[NB];
+#pragma unroll
+        for (int c = 0; c < NB * 3 / 4; ++c) {
+            double v0, v1, v2, v3;
+            ld256(g + 4 * c, v0, v1, v2, v3);
+            (&gN[0][0])[4 * c] = v0; (&gN[0][0])[4 * c + 1] = v1; (&gN[0][0])[4 * c + 2] = v2; (&gN[0][0])[4 * c + 3] = v3;
+        }
+#pragma unroll
+        for (int c = 0; c < NB; ++c) N[c] = __ldg(mx.N + q * NB + c);
+        const double wdv = __ldg(b.quad_w + q) * __ldg(b.det + el * NIP + q);
+        const double Na = __ldg(mx.N + q * NB + a), ga0 = __ldg(g + 3 * a), ga1 = __ldg(g + 3 * a + 1), ga2 = __ldg(g + 3 * a + 2);
+        double p = Na * pa, tre = fma(Ua[2], ga2, fma(Ua[1], ga1, Ua[0] * ga0));
+        double gp[3] = {pa * ga0, pa * ga1, pa * ga2};
+#pragma unroll
+        for (int m = 1; m < NB; m <<= 1) {
+            p += __shfl_xor_sync(0xffffffffu, p, m);
+            tre += __shfl_xor_sync(0xffffffffu, tre, m);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) gp[k] += __shfl_xor_sync(0xffffffffu, gp[k], m);
+        }
+        const double hydro = kappa * tre;
+        Rp += (-(p + hydro) / kappa * Na - tau * fma(ga2, gp[2], fma(ga1, gp[1], ga0 * gp[0]))) * wdv;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+            Kpp[c] -= (Na * N[c] / kappa + tau * fma(ga2, gN[c][2], fma(ga1, gN[c][1], ga0 * gN[c][0]))) * wdv;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) Kpu[c][k] -= Na * gN[c][k] * wdv;
+            Kup[0][c] -= ga0 * N[c] * wdv;
+            Kup[1][c] -= ga1 * N[c] * wdv;
+            Kup[2][c] -= ga2 * N[c] * wdv;
+        }
+    }
+    if (!live) return;
+    if (mx.R_p_elem) mx.R_p_elem[e * NB + a] = Rp;
+    if (mx.R_global) atomicAdd(mx.R_global + __ldg(mx.elem_eq_p + e * NB + a), Rp);
+    if (mx.K_pu) {
+        double* r = mx.K_pu + (e * NB + a) * (NB * 3);
+#pragma unroll
+        for (int c = 0; c < NB * 3 / 4; ++c)
+            st256(r + 4 * c, (&Kpu[0][0])[4 * c], (&Kpu[0][0])[4 * c + 1], (&Kpu[0][0])[4 * c + 2], (&Kpu[0][0])[4 * c + 3]);
+    }
+    if (mx.K_up) {
+        double* r = mx.K_up + (e * NB * 3 + 3 * a) * NB;
+#pragma unroll
+        for (int c = 0; c < NB * 3 / 4; ++c)
+            st256(r + 4 * c, (&Kup[0][0])[4 * c], (&Kup[0][0])[4 * c + 1], (&Kup[0][0])[4 * c + 2], (&Kup[0][0])[4 * c + 3]);
+    }
+    if (mx.K_pp) {
+        double* r = mx.K_pp + (e * NB + a) * NB;
+#pragma unroll
+        for (int c = 0; c < NB / 4; ++c) st256(r + 4 * c, Kpp[4 * c], Kpp[4 * c + 1], Kpp[4 * c + 2], Kpp[4 * c + 3]);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_fe_mixed_pressure(const cmadx_fe_block_t& b, const cmadx_fe_mixed_t& mx, double kappa,
+                                     double mu, cudaStream_t stream) {
+    if (b.n_elems == 0) return cudaSuccess;
+    const int64_t nthr = b.n_elems * b.n_basis;
+    const unsigned nblk = (unsigned)((nthr + FE_BLOCK - 1) / FE_BLOCK);
+    if (b.n_basis == 4) fe_mixed_pressure_kernel<4, 1><<<nblk, FE_BLOCK, 0, stream>>>(b, mx, kappa, mu);
+    else fe_mixed_pressure_kernel<8, 8><<<nblk, FE_BLOCK, 0, stream>>>(b, mx, kappa, mu);
+    return cudaGetLastError();
+}
+
+}  // namespace cmadx

@@ -48,7 +48,10 @@ CMADX_DEV double qoi_terms(const double (&w)[9], const double (&sig)[6], const d
     return J;
 }
 
-template <int YK, bool ADJOINT>
+// NA_MAX: compile-time bound of the active-parameter loops (6 covers the usual calibration
+// sets such as [E, nu, D, S, Y]; 16 = CMADX_MAX_ACTIVE), which sizes the register-resident
+// gradient accumulators.
+template <int YK, bool ADJOINT, int NA_MAX>
 __global__ void __launch_bounds__(SENS_BLOCK)
 mp_sens_kernel(const __grid_constant__ SensArgs A) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,28 +62,41 @@ mp_sens_kernel(const __grid_constant__ SensArgs A) {
     const int na = A.n_active;
     const int sc = A.h.strain_comps;
 
-    double g[CMADX_MAX_ACTIVE];
+    double g[NA_MAX];
 #pragma unroll
-    for (int c = 0; c < CMADX_MAX_ACTIVE; ++c) g[c] = 0.0;
+    for (int c = 0; c < NA_MAX; ++c) g[c] = 0.0;
     double Jacc = 0.0;
     double hist[7];
 #pragma unroll
     for (int c = 0; c < 7; ++c) hist[c] = 0.0;
-    double X[7][CMADX_MAX_ACTIVE];          // direct: dxi/dp carried forward (local memory)
+    double X[7][NA_MAX];          // direct: dxi/dp carried forward (local memory)
     if (!ADJOINT) {
         for (int c = 0; c < na; ++c)
 #pragma unroll
             for (int r = 0; r < 7; ++r) X[r][c] = 0.0;
     }
 
+    // the state pair (xi_t, xi_{t-1}) shares one member with the next step's pair: it is
+    // carried in registers, so every stored state is read from HBM exactly once
+    double x[7], xp[7];
+    {
+        const double* x0 = A.h.xi_hist + (int64_t)(ADJOINT ? N : 0) * 7 * ld + i;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            const double v = live ? __ldg(x0 + c * ld) : 0.0;
+            x[c] = v; xp[c] = v;
+        }
+    }
     for (int s = 0; s < N; ++s) {
         const int t = ADJOINT ? N - s : s + 1;
-        double x[7], xp[7], em[6], d[9];
+        double em[6], d[9];
         if (live) {
-            const double* xs = A.h.xi_hist + (int64_t)t * 7 * ld + i;
-            const double* xps = xs - 7 * ld;
+            const double* xs = A.h.xi_hist + (int64_t)(ADJOINT ? t - 1 : t) * 7 * ld + i;
 #pragma unroll
-            for (int c = 0; c < 7; ++c) { x[c] = __ldg(xs + c * ld); xp[c] = __ldg(xps + c * ld); }
+            for (int c = 0; c < 7; ++c) {
+                const double v = __ldg(xs + c * ld);
+                if (ADJOINT) xp[c] = v; else x[c] = v;
+            }
             const double* es = A.h.strain + (int64_t)t * sc * ld + i;
             if (sc == 6) {
 #pragma unroll
@@ -96,8 +112,6 @@ mp_sens_kernel(const __grid_constant__ SensArgs A) {
 #pragma unroll
             for (int c = 0; c < 9; ++c) d[c] = __ldg(ds + c * ld);
         } else {
-#pragma unroll
-            for (int c = 0; c < 7; ++c) { x[c] = 0.0; xp[c] = 0.0; }
 #pragma unroll
             for (int c = 0; c < 6; ++c) em[c] = 1e-3 * (c == 0);
 #pragma unroll
@@ -188,7 +202,7 @@ mp_sens_kernel(const __grid_constant__ SensArgs A) {
             for (int a = 0; a < 6; ++a) { hist[a] = phi[a]; nphi = fma(pt.n[a], phi[a], nphi); }
             hist[6] = pl ? -nphi : phi[6];
 #pragma unroll
-            for (int c = 0; c < CMADX_MAX_ACTIVE; ++c) {
+            for (int c = 0; c < NA_MAX; ++c) {
                 if (c < na) {
                     const int pid = A.pid[c];
                     double col[7];
@@ -220,11 +234,15 @@ mp_sens_kernel(const __grid_constant__ SensArgs A) {
                 g[c] += acc;
             }
         }
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            if (ADJOINT) x[c] = xp[c]; else xp[c] = x[c];
+        }
     }
     if (!live) {
         Jacc = 0.0;
 #pragma unroll
-        for (int c = 0; c < CMADX_MAX_ACTIVE; ++c) g[c] = 0.0;
+        for (int c = 0; c < NA_MAX; ++c) g[c] = 0.0;
     } else if (A.h.J_point) {
         A.h.J_point[i] = Jacc;
     }
@@ -232,7 +250,7 @@ mp_sens_kernel(const __grid_constant__ SensArgs A) {
     __shared__ double sm[SENS_BLOCK / 32][1 + CMADX_MAX_ACTIVE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int c = 0; c <= CMADX_MAX_ACTIVE; ++c) {
+    for (int c = 0; c <= NA_MAX; ++c) {
         if (c <= na) {
             double v = (c == 0) ? Jacc : g[c - 1];
 #pragma unroll
@@ -267,16 +285,16 @@ reduce_partials_kernel(const double* partials, int64_t nblk, int ncols, double* 
     }
 }
 
-template <bool ADJOINT>
+template <bool ADJOINT, int NA_MAX>
 cudaError_t launch_sens_t(const SensArgs& A, cudaStream_t stream) {
     const int64_t nblk = (A.h.n + SENS_BLOCK - 1) / SENS_BLOCK;
     switch (A.m.yield) {
     case CMADX_YIELD_J2:
-        mp_sens_kernel<CMADX_YIELD_J2, ADJOINT><<<(unsigned)nblk, SENS_BLOCK, 0, stream>>>(A); break;
+        mp_sens_kernel<CMADX_YIELD_J2, ADJOINT, NA_MAX><<<(unsigned)nblk, SENS_BLOCK, 0, stream>>>(A); break;
     case CMADX_YIELD_HILL:
-        mp_sens_kernel<CMADX_YIELD_HILL, ADJOINT><<<(unsigned)nblk, SENS_BLOCK, 0, stream>>>(A); break;
+        mp_sens_kernel<CMADX_YIELD_HILL, ADJOINT, NA_MAX><<<(unsigned)nblk, SENS_BLOCK, 0, stream>>>(A); break;
     case CMADX_YIELD_HOSFORD:
-        mp_sens_kernel<CMADX_YIELD_HOSFORD, ADJOINT><<<(unsigned)nblk, SENS_BLOCK, 0, stream>>>(A); break;
+        mp_sens_kernel<CMADX_YIELD_HOSFORD, ADJOINT, NA_MAX><<<(unsigned)nblk, SENS_BLOCK, 0, stream>>>(A); break;
     default: return cudaErrorInvalidValue;
     }
     cudaError_t e = cudaGetLastError();
@@ -295,7 +313,8 @@ cudaError_t launch_reduce_partials(const double* partials, int64_t nblk, int nco
 
 cudaError_t launch_mp_sens(const SensArgs& A, bool adjoint, cudaStream_t stream) {
     if (A.h.n == 0) return cudaMemsetAsync(A.h.result, 0, sizeof(double) * (1 + A.n_active), stream);
-    return adjoint ? launch_sens_t<true>(A, stream) : launch_sens_t<false>(A, stream);
+    if (A.n_active <= 6) return adjoint ? launch_sens_t<true, 6>(A, stream) : launch_sens_t<false, 6>(A, stream);
+    return adjoint ? launch_sens_t<true, CMADX_MAX_ACTIVE>(A, stream) : launch_sens_t<false, CMADX_MAX_ACTIVE>(A, stream);
 }
 
 int64_t sens_blocks(int64_t n) { return (n + SENS_BLOCK - 1) / SENS_BLOCK; }

@@ -160,6 +160,65 @@ def assemble_element_block_residual(material, newton, arrays, U_global, xi_prev_
     return r_plan.sum(o["R_elem"].reshape(-1), stream=stream) if r_plan is not None else o["R_global"]
 
 
+def assemble_element_block_mixed(material: L.Material, newton: NewtonSettings, arrays: FEBlockArrays,
+                                 U_global: torch.Tensor, xi_prev_per_block: torch.Tensor,
+                                 stab_mult: float = 1.0, r_plan: SegmentPlan | None = None,
+                                 want_K: bool = True, stream: torch.cuda.Stream | None = None):
+    """Mixed u-p (``SmallDispEquilibrium(mixed=True)``, small_disp_equilibrium.py:87-111)
+    counterpart of :func:`assemble_element_block`: returns ``(R_block, vals, xi_solved)``
+    with ``R_block (n_dofs,)`` over the block-major (u, p) dofs and ``vals`` the
+    concatenated COO streams in the reference's (r, s) emit order - (u,u), (u,p), (p,u),
+    (p,p), each flattened ``(elem, row dof, col dof)`` (cmad/fem/assembly.py:722-732).
+    ``r_plan``: a :class:`SegmentPlan` over ``cat(elem_eq.ravel(), elem_eq_p.ravel())``
+    (deterministic R); otherwise atomics.  ``want_K=False``: residual only (vals is None)."""
+    if not arrays.mixed:
+        raise ValueError("block arrays were built without mixed=True")
+    n_e, n_b, n_ip = arrays.n_elems, arrays.n_basis, arrays.n_ip
+    dev = arrays.grad_N.device
+    if dev.type != "cuda":
+        raise ValueError("FE block arrays must live on a CUDA device (there is no CPU fallback)")
+    if U_global.dtype != torch.float64 or U_global.numel() != arrays.n_dofs or not U_global.is_contiguous():
+        raise ValueError(f"U_global: expected contiguous float64 ({arrays.n_dofs},)")
+    if xi_prev_per_block.dtype != torch.float64 or tuple(xi_prev_per_block.shape) != (n_e, n_ip, 7) \
+            or not xi_prev_per_block.is_contiguous():
+        raise ValueError(f"xi_prev: expected contiguous float64 ({n_e}, {n_ip}, 7)")
+    nu, npd = 3 * n_b, n_b
+    sizes = [n_e * nu * nu, n_e * nu * npd, n_e * npd * nu, n_e * npd * npd]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    vals = torch.empty(int(offs[-1]), dtype=torch.float64, device=dev) if want_K else None
+    R_elem = torch.empty(n_e * (nu + npd), dtype=torch.float64, device=dev)     # [R_u | R_p]
+    out = {"xi": torch.empty((n_e, n_ip, 7), dtype=torch.float64, device=dev),
+           "R_elem": R_elem[:n_e * nu].view(n_e, nu),
+           "K_elem": vals[:sizes[0]].view(n_e, nu, nu) if want_K else None}
+    R = None
+    if r_plan is None:
+        R = torch.zeros(arrays.n_dofs, dtype=torch.float64, device=dev)
+        out["R_global"] = R
+    b = _fe_struct(arrays, U_global, xi_prev_per_block, out)
+    mx = L.FeMixed()
+    mx.elem_eq_p, mx.N, mx.h = arrays.elem_eq_p.data_ptr(), arrays.N.data_ptr(), arrays.h.data_ptr()
+    mx.stab_mult = float(stab_mult)
+    mx.R_p_elem = R_elem[n_e * nu:].data_ptr()
+    if want_K:
+        mx.K_up, mx.K_pu, mx.K_pp = (vals[int(offs[i]):].data_ptr() for i in (1, 2, 3))
+    mx.R_global = R.data_ptr() if R is not None else None
+    nw = newton.to_struct()
+    s = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        rc = L.lib().cmadx_fe_block_assemble_mixed(C.byref(material), C.byref(nw), C.byref(b), C.byref(mx),
+                                                   C.c_void_p(s.cuda_stream))
+    L.check(rc, "cmadx_fe_block_assemble_mixed")
+    if r_plan is not None:
+        R = r_plan.sum(R_elem, stream=stream)
+    return R, vals, out["xi"]
+
+
+def mixed_r_plan(arrays: FEBlockArrays, device=None) -> SegmentPlan:
+    """Deterministic scatter plan of the mixed block's residual: items = ``[R_u | R_p]``."""
+    seg = np.concatenate([arrays.elem_eq.cpu().numpy().reshape(-1), arrays.elem_eq_p.cpu().numpy().reshape(-1)])
+    return SegmentPlan(seg, arrays.n_dofs, device=device if device is not None else arrays.grad_N.device)
+
+
 def fe_block_jvp(material: L.Material, arrays: FEBlockArrays, U_global: torch.Tensor,
                  xi_prev: torch.Tensor, xi_state: torch.Tensor, active_pid, dp,
                  dxi_prev: torch.Tensor | None = None, outputs=("xi", "R_elem"), out: dict | None = None,

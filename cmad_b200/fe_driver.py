@@ -261,3 +261,23 @@ def cuda_assembler(material, newton, arrays, r_plan, k_plan, outputs=None):
         return R.cpu().numpy(), K_data.cpu().numpy(), xi
 
     return assemble
+
+
+def cuda_assembler_mixed(material, newton, arrays, r_plan, k_plan, stab_mult: float = 1.0, outputs=None):
+    """``assemble`` callable for the mixed u-p formulation (K3 with the momentum stress
+    dev(cauchy) - p I + the pressure-block kernel + K5); ``U`` holds the block-major (u, p)
+    dofs, ``k_plan`` the dedup scatter of :func:`cmad_b200.fe_mesh.coo_pattern_mixed`."""
+    import torch
+    from . import fe
+    dev = arrays.grad_N.device
+
+    def assemble(U, xi_prev):
+        Ud = torch.from_numpy(np.ascontiguousarray(U)).to(dev)
+        R, vals, xi = fe.assemble_element_block_mixed(material, newton, arrays, Ud, xi_prev,
+                                                      stab_mult=stab_mult, r_plan=r_plan)
+        K_data = k_plan.sum(vals)
+        if outputs is not None:
+            outputs["last"] = (R, K_data, xi)
+        return R.cpu().numpy(), K_data.cpu().numpy(), xi
+
+    return assemble

@@ -83,13 +83,17 @@ def tet_linear_shapes(xi: np.ndarray):
 @dataclass
 class FEBlockArrays:
     """Mesh-derived arrays of one element block (≙ the block's slices of the
-    reference's ``FEKernelArrays`` + ``BlockIPGeometryCache``)."""
+    reference's ``FEKernelArrays`` + ``BlockIPGeometryCache``).  The mixed u-p
+    formulation adds the pressure block's equation indices (block-major dofs:
+    ``eq_p = 3 n_nodes + node``, cmad/fem/dof.py) and the element sizes."""
     elem_eq: torch.Tensor    # (n_e, n_b*3) int32
     grad_N: torch.Tensor     # (n_e, n_ip, n_b, 3) float64, physical frame
     det: torch.Tensor        # (n_e, n_ip) float64
     quad_w: torch.Tensor     # (n_ip,) float64
     N: torch.Tensor          # (n_ip, n_b) float64 (shared)
     n_dofs: int
+    elem_eq_p: torch.Tensor | None = None   # (n_e, n_b) int32   (mixed u-p only)
+    h: torch.Tensor | None = None           # (n_e,) float64 RMS edge length (mixed u-p only)
 
     @property
     def n_elems(self) -> int:
@@ -103,19 +107,43 @@ class FEBlockArrays:
     def n_ip(self) -> int:
         return int(self.grad_N.shape[1])
 
+    @property
+    def mixed(self) -> bool:
+        return self.elem_eq_p is not None
+
     def to(self, device) -> "FEBlockArrays":
+        mv = lambda t: None if t is None else t.to(device)  # noqa: E731
         return FEBlockArrays(self.elem_eq.to(device), self.grad_N.to(device), self.det.to(device),
-                             self.quad_w.to(device), self.N.to(device), self.n_dofs)
+                             self.quad_w.to(device), self.N.to(device), self.n_dofs,
+                             mv(self.elem_eq_p), mv(self.h))
 
     def slice(self, lo: int, hi: int) -> "FEBlockArrays":
         """Contiguous element range (multi-GPU partition by element index)."""
+        sl = lambda t: None if t is None else t[lo:hi].contiguous()  # noqa: E731
         return FEBlockArrays(self.elem_eq[lo:hi].contiguous(), self.grad_N[lo:hi].contiguous(),
-                             self.det[lo:hi].contiguous(), self.quad_w, self.N, self.n_dofs)
+                             self.det[lo:hi].contiguous(), self.quad_w, self.N, self.n_dofs,
+                             sl(self.elem_eq_p), sl(self.h))
 
 
-def block_arrays(nodes, conn, device="cpu", chunk: int = 1 << 20) -> FEBlockArrays:
+# local edges (cmad/fem/mesh.py _HEX_LOCAL_EDGES / _TET_LOCAL_EDGES; only the set matters here)
+_HEX_EDGES = np.array([[0, 1], [1, 2], [2, 3], [3, 0], [4, 5], [5, 6], [6, 7], [7, 4],
+                       [0, 4], [1, 5], [2, 6], [3, 7]])
+_TET_EDGES = np.array([[0, 1], [0, 2], [0, 3], [1, 2], [1, 3], [2, 3]])
+
+
+def element_rms_edge_sizes(nodes, conn) -> np.ndarray:
+    """``h[e] = sqrt(mean_k l_k^2)`` over the element's edges (cmad/fem/mesh.py:624-636):
+    the length scale of the mixed formulation's pressure stabilisation."""
+    conn = np.asarray(conn)
+    edges = _HEX_EDGES if conn.shape[1] == 8 else _TET_EDGES
+    X = np.asarray(nodes, dtype=np.float64)[conn[:, edges]]          # (n_e, n_edges, 2, 3)
+    return np.sqrt(np.mean(np.sum((X[:, :, 1] - X[:, :, 0]) ** 2, axis=-1), axis=-1))
+
+
+def block_arrays(nodes, conn, device="cpu", chunk: int = 1 << 20, mixed: bool = False) -> FEBlockArrays:
     """Geometry cache + equation indices of one block (tet4 if ``conn`` has 4
-    columns, hex8 if 8), as ``precompute_block_geometry`` builds them."""
+    columns, hex8 if 8), as ``precompute_block_geometry`` builds them.  ``mixed``:
+    the u-p formulation (one pressure dof per node after the 3 n_nodes displacement dofs)."""
     conn = np.asarray(conn)
     n_b = conn.shape[1]
     if n_b == 8:
@@ -140,8 +168,14 @@ def block_arrays(nodes, conn, device="cpu", chunk: int = 1 << 20) -> FEBlockArra
         det[lo:hi] = torch.linalg.det(jac)
         grad_N[lo:hi] = torch.einsum("pnj,epji->epni", gref_t, torch.linalg.inv(jac))
     eq = (conn_t[:, :, None] * 3 + torch.arange(3)[None, None, :]).reshape(n_e, n_b * 3)
-    return FEBlockArrays(eq.to(torch.int32).to(dev), grad_N, det, torch.as_tensor(w).to(dev),
-                         torch.as_tensor(N).to(dev), int(np.asarray(nodes).shape[0]) * 3)
+    n_nodes = int(np.asarray(nodes).shape[0])
+    arr = FEBlockArrays(eq.to(torch.int32).to(dev), grad_N, det, torch.as_tensor(w).to(dev),
+                        torch.as_tensor(N).to(dev), n_nodes * 3)
+    if mixed:
+        arr.n_dofs = n_nodes * 4
+        arr.elem_eq_p = (conn_t + 3 * n_nodes).to(torch.int32).to(dev).contiguous()
+        arr.h = torch.as_tensor(element_rms_edge_sizes(nodes, conn)).to(dev)
+    return arr
 
 
 def coo_pattern(elem_eq: np.ndarray):
@@ -154,11 +188,26 @@ def coo_pattern(elem_eq: np.ndarray):
     return rows, cols
 
 
-def coo_dedup(elem_eq: np.ndarray):
+def coo_pattern_mixed(elem_eq: np.ndarray, elem_eq_p: np.ndarray):
+    """With-duplicates ``(rows, cols)`` of the mixed u-p block in the emit order of
+    ``assemble_element_block``: the (u,u), (u,p), (p,u), (p,p) streams one after the other,
+    each ``(elem, row dof, col dof)`` (cmad/fem/assembly.py:722-732, 970-1023)."""
+    eqs = [np.asarray(elem_eq, dtype=np.int64), np.asarray(elem_eq_p, dtype=np.int64)]
+    rows, cols = [], []
+    for r in range(2):
+        for s_ in range(2):
+            n_e, nr = eqs[r].shape
+            nc = eqs[s_].shape[1]
+            rows.append(np.broadcast_to(eqs[r][:, :, None], (n_e, nr, nc)).reshape(-1))
+            cols.append(np.broadcast_to(eqs[s_][:, None, :], (n_e, nr, nc)).reshape(-1))
+    return np.concatenate(rows), np.concatenate(cols)
+
+
+def coo_dedup(elem_eq: np.ndarray, elem_eq_p: np.ndarray | None = None):
     """``(unique_rows, unique_cols, coo_dedup_scatter)`` as ``assembled_coo_dedup``
     (cmad/fem/assembly.py:1026-1070): lex-sorted unique pattern + the map from each
     with-duplicates triplet to its slot."""
-    rows, cols = coo_pattern(elem_eq)
+    rows, cols = coo_pattern(elem_eq) if elem_eq_p is None else coo_pattern_mixed(elem_eq, elem_eq_p)
     n = int(max(rows.max(), cols.max())) + 1
     key = rows * n + cols
     uniq, inverse = np.unique(key, return_inverse=True)

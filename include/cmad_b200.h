@@ -263,6 +263,33 @@ typedef struct cmadx_fe_block {
 int cmadx_fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* newton,
                             const cmadx_fe_block_t* blk, void* stream);
 
+/* ---- Mixed u-p (stabilised equal-order) formulation of SmallDispEquilibrium ------------
+ * cmad/global_residuals/small_disp_equilibrium.py:87-111 (`mixed: true`, examples/
+ * mixed_plastic.yaml): two residual blocks, u ("equilibrium") and p ("pressure"), block-major
+ * dofs in ONE global vector U (cmad/fem/dof.py block_offsets).  The momentum stress is
+ * dev(cauchy) - p I; R_p = (-(p + hydro)/kappa N - tau gradN.grad p) w dv with
+ * hydro = kappa tr(eps), tau = stab_mult h^2 / (2 mu), h = RMS edge length of the element
+ * (cmad/fem/mesh.py:624-636).  `blk` as for cmadx_fe_block_assemble: elem_eq / R_elem / K_elem
+ * describe the u block (K_elem = the (u,u) COO stream); `mix` adds the pressure block and the
+ * (u,p), (p,u), (p,p) streams, in the reference's (r, s) emit order
+ * (cmad/fem/assembly.py:722-732).  blk->R_global / mix->R_global may alias the same [n_dofs]
+ * vector (atomic scatter-add of both residual blocks).                                  */
+typedef struct cmadx_fe_mixed {
+    const int32_t* elem_eq_p; /* [n_elems][n_basis] global equation of the pressure dof  */
+    const double* N;          /* [n_ip][n_basis] shape values at the IPs (shared)        */
+    const double* h;          /* [n_elems] element size                                  */
+    double stab_mult;         /* `stabilization multiplier`                              */
+    double* R_p_elem;         /* [n_elems][n_basis] or NULL                              */
+    double* K_up;             /* [n_elems][n_basis*3][n_basis] or NULL                   */
+    double* K_pu;             /* [n_elems][n_basis][n_basis*3] or NULL                   */
+    double* K_pp;             /* [n_elems][n_basis][n_basis] or NULL                     */
+    double* R_global;         /* [n_dofs] or NULL: atomic scatter-add of R_p             */
+} cmadx_fe_mixed_t;
+
+int cmadx_fe_block_assemble_mixed(const cmadx_material_t* mat, const cmadx_newton_t* newton,
+                                  const cmadx_fe_block_t* blk, const cmadx_fe_mixed_t* mix,
+                                  void* stream);
+
 /* ---- K6: forward sensitivities (JVP) of the element block at a converged state --------
  * For a tangent direction (dp over the active parameters, dxi_prev per point) at FIXED U:
  *   dxi = -A^{-1} (dC/dp dp + dC/dxi_prev dxi_prev),  A = dC/dxi at (xi_state, xi_prev),

@@ -76,6 +76,66 @@ def assemble_block(prob: oracle_c.OracleProblem, elem_eq, U, xi_prev, grad_N, de
     return out
 
 
+def assemble_block_mixed(prob: oracle_c.OracleProblem, elem_eq, elem_eq_p, U, xi_prev, grad_N, N, det,
+                         quad_w, h, stab_mult: float = 1.0, want_K: bool = True, nthreads: int = 0) -> dict:
+    """One COUPLED element block of the MIXED u-p formulation
+    (cmad/global_residuals/small_disp_equilibrium.py:87-111), per IP:
+      sigma = dev(cauchy(xi)) - p I,                      R_u = (grad_N @ sigma) w dv
+      R_p = (-(p + hydro)/kappa N - tau grad_N @ grad p) w dv,  hydro = kappa tr(eps),
+      tau = mult * 0.5 h^2 / mu
+    and the four tangent blocks dR_r/dU_s (IFT-corrected through the local Newton, which
+    only sees grad_u).  ``U`` holds the block-major (u, p) dofs; ``N (n_ip, n_b)``; ``h (n_e,)``.
+    Returns R_u (n_e, 3n_b), R_p (n_e, n_b), K_uu, K_up, K_pu, K_pp, xi, R (n_dofs,)."""
+    elem_eq = np.asarray(elem_eq, dtype=np.int64); elem_eq_p = np.asarray(elem_eq_p, dtype=np.int64)
+    n_e, n_ip, n_b, _ = grad_N.shape
+    assert int(prob.cfg[7]) == 9
+    U = np.asarray(U)
+    U_e = U[elem_eq].reshape(n_e, n_b, 3); p_e = U[elem_eq_p]
+    lam, mu = oracle_c.lame(int(prob.cfg[2]), float(prob.mat[0]), float(prob.mat[1]))[:2]
+    kappa = lam + 2.0 * mu / 3.0                                         # elastic_constants.py:41-43
+    tau = stab_mult * 0.5 * np.asarray(h) ** 2 / mu
+    R_u = np.zeros((n_e, n_b, 3)); R_p = np.zeros((n_e, n_b))
+    K_uu = np.zeros((n_e, n_b, 3, n_b, 3)); K_up = np.zeros((n_e, n_b, 3, n_b))
+    K_pu = np.zeros((n_e, n_b, n_b, 3)); K_pp = np.zeros((n_e, n_b, n_b))
+    xi = np.zeros((n_e, n_ip, 7)); sigma_ip = np.zeros((n_e, n_ip, 6))
+    I3 = np.eye(3)
+    want = ("xi", "sigma") + (("dsig_deps",) if want_K else ())
+    for ip in range(n_ip):
+        gN, Nip = grad_N[:, ip], N[ip]
+        gu = np.einsum("eak,eaj->ekj", U_e, gN)
+        r = oracle_c.mp_update(prob, xi_prev[:, ip].T.copy(), gu.reshape(n_e, 9).T.copy(), want=want,
+                               nthreads=nthreads)
+        xi[:, ip] = r["xi"].T; sigma_ip[:, ip] = r["sigma"].T
+        sig = np.moveaxis(r["sigma"][_V], -1, 0)                         # (n_e, 3, 3) cauchy
+        dev = sig - (np.trace(sig, axis1=1, axis2=2) / 3.0)[:, None, None] * I3      # dev_cauchy :323-329
+        p = p_e @ Nip
+        sigma = dev - p[:, None, None] * I3
+        wdv = quad_w[ip] * det[:, ip]
+        R_u += np.einsum("eaj,eji->eai", gN, sigma) * wdv[:, None, None]
+        hydro = kappa * np.trace(gu, axis1=1, axis2=2)                   # hydro_cauchy :332-339
+        grad_p = np.einsum("ea,eaj->ej", p_e, gN)
+        R_p += (-(p + hydro)[:, None] / kappa * Nip[None, :]
+                - tau[:, None] * np.einsum("eaj,ej->ea", gN, grad_p)) * wdv[:, None]
+        if want_K:
+            Df = full_tangent(r["dsig_deps"])                            # [e, j, i, k, l]
+            tr = np.einsum("emmkl->ekl", Df) / 3.0
+            Ddev = Df - I3[None, :, :, None, None] * tr[:, None, None, :, :]
+            K_uu += np.einsum("eaj,ejikl,ebl->eaibk", gN, Ddev, gN) * wdv[:, None, None, None, None]
+            K_up += -np.einsum("eai,b->eaib", gN, Nip) * wdv[:, None, None, None]
+            K_pu += -np.einsum("a,ebk->eabk", Nip, gN) * wdv[:, None, None, None]
+            K_pp += (-np.einsum("a,b->ab", Nip, Nip)[None] / kappa
+                     - tau[:, None, None] * np.einsum("eaj,ebj->eab", gN, gN)) * wdv[:, None, None]
+    out = {"R_u": R_u.reshape(n_e, n_b * 3), "R_p": R_p, "xi": xi, "sigma": sigma_ip}
+    if want_K:
+        out.update(K_uu=K_uu.reshape(n_e, 3 * n_b, 3 * n_b), K_up=K_up.reshape(n_e, 3 * n_b, n_b),
+                   K_pu=K_pu.reshape(n_e, n_b, 3 * n_b), K_pp=K_pp)
+    R = np.zeros(U.shape[0])
+    np.add.at(R, elem_eq.reshape(-1), out["R_u"].reshape(-1))
+    np.add.at(R, elem_eq_p.reshape(-1), R_p.reshape(-1))
+    out["R"] = R
+    return out
+
+
 def coo_dedup_sum(vals: np.ndarray, scatter: np.ndarray, n_unique: int) -> np.ndarray:
     """``zeros(n_unique).at[coo_dedup_scatter].add(vals)`` (assembly.py:906-909)."""
     out = np.zeros(n_unique)

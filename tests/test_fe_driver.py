@@ -316,3 +316,89 @@ def test_notch_hosford_deck_cuda_matches_oracle(cuda_device):
     assert [l.iters for l in lg] == [l.iters for l in lo]
     assert np.abs(Ug - Uo).max() < 1e-8 * np.abs(Uo).max()
     assert np.abs(xig.cpu().numpy() - xio).max() < 1e-8 * np.abs(xio).max()
+
+
+# ---------------------------------------------------------------- mixed u-p formulation (KA6)
+def mixed_uniaxial_cube(div, family="hex8"):
+    """tests/fem/test_mixed_up_plastic.py:36-78: unit cube, u-p, symmetry planes on the
+    three min faces, the x = max face pulled to ``t``; pressure dofs free."""
+    nodes, conn = fe_mesh.structured_hex_mesh((div,) * 3)
+    if family == "tet4":
+        conn = fe_mesh.split_hex_to_tets(conn)
+    arr = fe_mesh.block_arrays(nodes, conn, mixed=True)
+    nid = np.arange(nodes.shape[0])
+    on = lambda ax, v: nid[np.isclose(nodes[:, ax], v)]
+    pin = np.concatenate([on(0, 0.0) * 3 + 0, on(1, 0.0) * 3 + 1, on(2, 0.0) * 3 + 2])
+    ramp = on(0, 1.0) * 3 + 0
+    bcs = drv.DirichletBCs(np.concatenate([pin, ramp]),
+                           lambda t: np.concatenate([np.zeros(len(pin)), np.full(len(ramp), t)]))
+    ur, uc, scatter = fe_mesh.coo_dedup(arr.elem_eq.numpy(), arr.elem_eq_p.numpy())
+    return nodes, arr, bcs, drv.SparsePattern(ur, uc, arr.n_dofs), scatter
+
+
+def oracle_assembler_mixed(values, arr, scatter, n_unique, record=None):
+    prob = oc.describe(values, None, newton_mode="traced", strain_comps=9, **LOCAL_NEWTON)
+
+    def assemble(U, xi_prev):
+        o = fe_oracle.assemble_block_mixed(prob, arr.elem_eq.numpy(), arr.elem_eq_p.numpy(), U, xi_prev,
+                                           arr.grad_N.numpy(), arr.N.numpy(), arr.det.numpy(), arr.quad_w.numpy(),
+                                           arr.h.numpy())
+        if record is not None:
+            record["sigma"] = o["sigma"]
+        vals = np.concatenate([o[k].reshape(-1) for k in ("K_uu", "K_up", "K_pu", "K_pp")])
+        return o["R"], fe_oracle.coo_dedup_sum(vals, scatter, n_unique), o["xi"]
+    return assemble
+
+
+def _ka6_targets():
+    """Analytic uniaxial J2+Voce state at alpha = 0.05 (MAX_ALPHA, num_steps=2)."""
+    mask = np.zeros((3, 3)); mask[0, 0] = 1.0
+    stress, strain, _ = analytic.plastic_fields(mask, max_alpha=0.05, num_steps=2)
+    return float(strain[0, 0, -1]), float(stress[0, 0, -1])
+
+
+@pytest.mark.parametrize("family", ["hex8", "tet4"])
+def test_mixed_up_uniaxial_cube_known_answer(family):
+    """KA6 (tests/fem/test_mixed_up_plastic.py:96-135): sigma_xx = analytic (rtol 1e-5),
+    lateral stresses < 1e-4 sigma, p = -sigma/3 - the driver over the oracle's mixed block."""
+    values, _, _ = analytic.j2_voce_param_tree("J2")
+    axial_strain, sigma_axial = _ka6_targets()
+    nodes, arr, bcs, pattern, scatter = mixed_uniaxial_cube(2, family)
+    rec = {}
+    asm = oracle_assembler_mixed(values, arr, scatter, len(pattern.rows), rec)
+    ts = axial_strain * np.arange(6) / 5.0
+    U_steps, xi, _, logs = drv.fe_quasistatic_drive(asm, pattern, bcs, np.zeros(arr.n_dofs),
+                                                    np.zeros((arr.n_elems, arr.n_ip, 7)), ts, None, None)
+    assert all(l.residual_norms[-1] < 1e-7 for l in logs)
+    sig = rec["sigma"]
+    np.testing.assert_allclose(sig[..., 0], sigma_axial, rtol=1e-5)
+    assert np.abs(sig[..., 3]).max() < 1e-4 * sigma_axial and np.abs(sig[..., 5]).max() < 1e-4 * sigma_axial
+    p = U_steps[-1][3 * nodes.shape[0]:]
+    np.testing.assert_allclose(p, -sigma_axial / 3.0, rtol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("family,div", [("hex8", 4), ("tet4", 3)])
+def test_cuda_mixed_driver_matches_oracle_driver_and_known_answer(cuda_device, family, div):
+    import torch
+    from cmad_b200 import fe, material_from_values
+    values, _, _ = analytic.j2_voce_param_tree("J2")
+    axial_strain, sigma_axial = _ka6_targets()
+    nodes, arr, bcs, pattern, scatter = mixed_uniaxial_cube(div, family)
+    ts = axial_strain * np.arange(6) / 5.0
+    arr_d = arr.to(cuda_device)
+    r_plan = fe.mixed_r_plan(arr, device=cuda_device)
+    k_plan = fe.SegmentPlan(scatter, len(pattern.rows), device=cuda_device)
+    mat, nw = material_from_values(values), fe.fe_newton_settings(**LOCAL_NEWTON)
+    asm = drv.cuda_assembler_mixed(mat, nw, arr_d, r_plan, k_plan)
+    xi0 = torch.zeros((arr.n_elems, arr.n_ip, 7), dtype=torch.float64, device=cuda_device)
+    Ug, xig, _, lg = drv.fe_quasistatic_drive(asm, pattern, bcs, np.zeros(arr.n_dofs), xi0, ts, None, None)
+    asm_o = oracle_assembler_mixed(values, arr, scatter, len(pattern.rows))
+    Uo, xio, _, lo = drv.fe_quasistatic_drive(asm_o, pattern, bcs, np.zeros(arr.n_dofs),
+                                              np.zeros((arr.n_elems, arr.n_ip, 7)), ts, None, None)
+    assert [l.iters for l in lg] == [l.iters for l in lo]
+    assert np.abs(Ug - Uo).max() < 1e-9 * np.abs(Uo).max()
+    assert np.abs(xig.cpu().numpy() - xio).max() < 1e-9 * np.abs(xio).max()
+    p = Ug[-1][3 * nodes.shape[0]:]
+    np.testing.assert_allclose(p, -sigma_axial / 3.0, rtol=1e-5)
+    np.testing.assert_allclose(xig.cpu().numpy()[..., 6], 0.05, rtol=1e-5)
