@@ -107,10 +107,11 @@ def _check_traced(case, run_update):
         ok = same & ((g["flags"][s] & 2) > 0)
         if ok.any():
             assert rel_err(dxdp[ok], g["dxi_dp"][s][:, :, aidx][ok]) < 1e-8, (case, s, "dxi_dp")
-            ds_dx = np.asarray(out["dsig_dxi"]).T.reshape(n, 6, 7)
-            ds_dp = np.asarray(out["dsig_dp"]).T.reshape(n, 6, len(aidx))
-            tot = ds_dp + ds_dx @ dxdp
-            assert rel_err(tot[ok], g["dsig_dp"][s][:, _ROW9][:, :, aidx][ok]) < 1e-8, (case, s, "dsig_dp")
+            if "dsig_dxi" in out:           # partial stress derivatives: oracle only (K6 uses them on the GPU)
+                ds_dx = np.asarray(out["dsig_dxi"]).T.reshape(n, 6, 7)
+                ds_dp = np.asarray(out["dsig_dp"]).T.reshape(n, 6, len(aidx))
+                tot = ds_dp + ds_dx @ dxdp
+                assert rel_err(tot[ok], g["dsig_dp"][s][:, _ROW9][:, :, aidx][ok]) < 1e-8, (case, s, "dsig_dp")
     assert n_plastic > 0
 
 
@@ -198,7 +199,7 @@ def test_cuda_vs_reference_traced_newton(cuda_device, case, force_generic):
         nw = NewtonSettings(mode="traced", force_generic=force_generic, **kw)
         out = mp.mp_update(material_from_values(values), nw, active_param_ids(P),
                            torch.from_numpy(xi_prev).to(cuda_device), torch.from_numpy(grad_u).to(cuda_device),
-                           outputs=WANT)
+                           outputs=WANT[:-2])
         torch.cuda.synchronize()
         return {k: v.cpu().numpy() for k, v in out.items()}
     if force_generic and not case.startswith("J2"):
