@@ -17,9 +17,9 @@ namespace cmadx {
 namespace {
 
 template <int NB, int NIP>
-__global__ void __launch_bounds__(FE_BLOCK) fe_mixed_pressure_kernel(const cmadx_fe_block_t b,
-                                                                     const cmadx_fe_mixed_t mx,
-                                                                     const double kappa, const double mu) {
+__global__ void __launch_bounds__(FE_BLOCK, 4) fe_mixed_pressure_kernel(const cmadx_fe_block_t b,
+                                                                        const cmadx_fe_mixed_t mx,
+                                                                        const double kappa, const double mu) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t e = t / NB;
     const int a = (int)(t - e * NB);
@@ -34,68 +34,77 @@ __global__ void __launch_bounds__(FE_BLOCK) fe_mixed_pressure_kernel(const cmadx
     const double pa = __ldg(b.U + __ldg(mx.elem_eq_p + el * NB + a));
     const double h = __ldg(mx.h + el);
     const double tau = mx.stab_mult * 0.5 * h * h / mu;
-    double Rp = 0.0, Kpu[NB][3], Kup[3][NB], Kpp[NB];
-#pragma unroll
-    for (int c = 0; c < NB; ++c) {
-        Kpp[c] = 0.0;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { Kpu[c][k] = 0.0; Kup[k][c] = 0.0; }
-    }
+    const double ik = 1.0 / kappa;
+    double Rp = 0.0;
+    // column blocks of 4 nodes keep the accumulators (28 doubles) and the staged grad_N
+    // quarter in registers at 4 blocks / SM; the re-read of grad_N per block hits L1
 #pragma unroll 1
-    for (int q = 0; q < NIP; ++q) {
-        const double* g = b.grad_N + (el * NIP + q) * (NB * 3);
-        double gN[NB][3], N[NB];
+    for (int cb = 0; cb < NB / 4; ++cb) {
+        double Kpu[4][3], Kup[3][4], Kpp[4];
 #pragma unroll
-        for (int c = 0; c < NB * 3 / 4; ++c) {
-            double v0, v1, v2, v3;
-            ld256(g + 4 * c, v0, v1, v2, v3);
-            (&gN[0][0])[4 * c] = v0; (&gN[0][0])[4 * c + 1] = v1; (&gN[0][0])[4 * c + 2] = v2; (&gN[0][0])[4 * c + 3] = v3;
+        for (int c = 0; c < 4; ++c) {
+            Kpp[c] = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { Kpu[c][k] = 0.0; Kup[k][c] = 0.0; }
         }
+#pragma unroll 1
+        for (int q = 0; q < NIP; ++q) {
+            const double* g = b.grad_N + (el * NIP + q) * (NB * 3);
+            double gN[4][3], N[4];
 #pragma unroll
-        for (int c = 0; c < NB; ++c) N[c] = __ldg(mx.N + q * NB + c);
-        const double wdv = __ldg(b.quad_w + q) * __ldg(b.det + el * NIP + q);
-        const double Na = __ldg(mx.N + q * NB + a), ga0 = __ldg(g + 3 * a), ga1 = __ldg(g + 3 * a + 1), ga2 = __ldg(g + 3 * a + 2);
-        double p = Na * pa, tre = fma(Ua[2], ga2, fma(Ua[1], ga1, Ua[0] * ga0));
-        double gp[3] = {pa * ga0, pa * ga1, pa * ga2};
+            for (int c = 0; c < 3; ++c) {
+                double v0, v1, v2, v3;
+                ld256(g + 12 * cb + 4 * c, v0, v1, v2, v3);
+                (&gN[0][0])[4 * c] = v0; (&gN[0][0])[4 * c + 1] = v1; (&gN[0][0])[4 * c + 2] = v2; (&gN[0][0])[4 * c + 3] = v3;
+            }
 #pragma unroll
-        for (int m = 1; m < NB; m <<= 1) {
-            p += __shfl_xor_sync(0xffffffffu, p, m);
-            tre += __shfl_xor_sync(0xffffffffu, tre, m);
+            for (int c = 0; c < 4; ++c) N[c] = __ldg(mx.N + q * NB + 4 * cb + c);
+            const double wdv = __ldg(b.quad_w + q) * __ldg(b.det + el * NIP + q);
+            const double Na = __ldg(mx.N + q * NB + a) * wdv;
+            const double ga0 = __ldg(g + 3 * a) * wdv, ga1 = __ldg(g + 3 * a + 1) * wdv, ga2 = __ldg(g + 3 * a + 2) * wdv;
+            if (cb == 0) {
+                double p = Na * pa, tre = fma(Ua[2], ga2, fma(Ua[1], ga1, Ua[0] * ga0));    // x w dv
+                double gp[3] = {pa * ga0, pa * ga1, pa * ga2};
 #pragma unroll
-            for (int k = 0; k < 3; ++k) gp[k] += __shfl_xor_sync(0xffffffffu, gp[k], m);
+                for (int m = 1; m < NB; m <<= 1) {
+                    p += __shfl_xor_sync(0xffffffffu, p, m);
+                    tre += __shfl_xor_sync(0xffffffffu, tre, m);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) gp[k] += __shfl_xor_sync(0xffffffffu, gp[k], m);
+                }
+                // p, tre, gp carry one factor w dv; N_a and gradN_a (unweighted) = Na / wdv ...
+                const double Nu = __ldg(mx.N + q * NB + a);
+                const double gu0 = __ldg(g + 3 * a), gu1 = __ldg(g + 3 * a + 1), gu2 = __ldg(g + 3 * a + 2);
+                Rp -= fma(p, ik, tre) * Nu + tau * fma(gu2, gp[2], fma(gu1, gp[1], gu0 * gp[0]));
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                Kpp[c] -= fma(Na * ik, N[c], tau * fma(ga2, gN[c][2], fma(ga1, gN[c][1], ga0 * gN[c][0])));
+#pragma unroll
+                for (int k = 0; k < 3; ++k) Kpu[c][k] = fma(-Na, gN[c][k], Kpu[c][k]);
+                Kup[0][c] = fma(-ga0, N[c], Kup[0][c]);
+                Kup[1][c] = fma(-ga1, N[c], Kup[1][c]);
+                Kup[2][c] = fma(-ga2, N[c], Kup[2][c]);
+            }
         }
-        const double hydro = kappa * tre;
-        Rp += (-(p + hydro) / kappa * Na - tau * fma(ga2, gp[2], fma(ga1, gp[1], ga0 * gp[0]))) * wdv;
+        if (live) {
+            if (mx.K_pu) {
+                double* r = mx.K_pu + (e * NB + a) * (NB * 3) + 12 * cb;
 #pragma unroll
-        for (int c = 0; c < NB; ++c) {
-            Kpp[c] -= (Na * N[c] / kappa + tau * fma(ga2, gN[c][2], fma(ga1, gN[c][1], ga0 * gN[c][0]))) * wdv;
+                for (int c = 0; c < 3; ++c)
+                    st256(r + 4 * c, (&Kpu[0][0])[4 * c], (&Kpu[0][0])[4 * c + 1], (&Kpu[0][0])[4 * c + 2], (&Kpu[0][0])[4 * c + 3]);
+            }
+            if (mx.K_up) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) Kpu[c][k] -= Na * gN[c][k] * wdv;
-            Kup[0][c] -= ga0 * N[c] * wdv;
-            Kup[1][c] -= ga1 * N[c] * wdv;
-            Kup[2][c] -= ga2 * N[c] * wdv;
+                for (int i = 0; i < 3; ++i)
+                    st256(mx.K_up + (e * NB * 3 + 3 * a + i) * NB + 4 * cb, Kup[i][0], Kup[i][1], Kup[i][2], Kup[i][3]);
+            }
+            if (mx.K_pp) st256(mx.K_pp + (e * NB + a) * NB + 4 * cb, Kpp[0], Kpp[1], Kpp[2], Kpp[3]);
         }
     }
     if (!live) return;
     if (mx.R_p_elem) mx.R_p_elem[e * NB + a] = Rp;
     if (mx.R_global) atomicAdd(mx.R_global + __ldg(mx.elem_eq_p + e * NB + a), Rp);
-    if (mx.K_pu) {
-        double* r = mx.K_pu + (e * NB + a) * (NB * 3);
-#pragma unroll
-        for (int c = 0; c < NB * 3 / 4; ++c)
-            st256(r + 4 * c, (&Kpu[0][0])[4 * c], (&Kpu[0][0])[4 * c + 1], (&Kpu[0][0])[4 * c + 2], (&Kpu[0][0])[4 * c + 3]);
-    }
-    if (mx.K_up) {
-        double* r = mx.K_up + (e * NB * 3 + 3 * a) * NB;
-#pragma unroll
-        for (int c = 0; c < NB * 3 / 4; ++c)
-            st256(r + 4 * c, (&Kup[0][0])[4 * c], (&Kup[0][0])[4 * c + 1], (&Kup[0][0])[4 * c + 2], (&Kup[0][0])[4 * c + 3]);
-    }
-    if (mx.K_pp) {
-        double* r = mx.K_pp + (e * NB + a) * NB;
-#pragma unroll
-        for (int c = 0; c < NB / 4; ++c) st256(r + 4 * c, Kpp[4 * c], Kpp[4 * c + 1], Kpp[4 * c + 2], Kpp[4 * c + 3]);
-    }
 }
 
 }  // namespace

@@ -84,6 +84,15 @@ template <> struct YieldFn<CMADX_YIELD_J2> {
         if (is_diag(a) && is_diag(b)) v -= 1.0 / 3.0;
         return c * v;
     }
+    // (dn/dsigma) : v in closed form: c (dev v - s^ (s^ : v))
+    CMADX_DEV void Mvec(const double (&v)[6], double (&out)[6]) const {
+        const double tr3 = (v[0] + v[3] + v[5]) * (1.0 / 3.0);
+        double sv = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) sv = fma(mult(a) * sh[a], v[a], sv);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) out[a] = c * fma(-sh[a], sv, is_diag(a) ? v[a] - tr3 : v[a]);
+    }
     CMADX_DEV bool dparam(const DevMat&, int, const double (&)[6], double&, double (&)[6]) const {
         return false;
     }
