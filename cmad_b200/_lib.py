@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcmad_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
 SOURCES = ["api.cu", "mp_update.cu", "mp_update_j2.cu", "elastic_update.cu", "mp_sens.cu",
-           "fe_block.cu", "fe_tet4.cu", "fe_hex8.cu", "fe_mixed.cu", "fe_vjp.cu", "fe_scatter.cu"]
+           "fe_block.cu", "fe_tet4.cu", "fe_hex8.cu", "fe_mixed.cu", "fe_post.cu", "fe_vjp.cu", "fe_scatter.cu"]
 
 # ---- enums (mirror include/cmad_b200.h) ---------------------------------
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(5)
@@ -158,6 +158,12 @@ def lib() -> C.CDLL:
                                           C.POINTER(FeBlock), C.c_void_p]
     L.cmadx_fe_block_assemble_mixed.argtypes = [C.POINTER(Material), C.POINTER(Newton),
                                                 C.POINTER(FeBlock), C.POINTER(FeMixed), C.c_void_p]
+    L.cmadx_fe_cauchy_at_ips.argtypes = [C.POINTER(Material), C.POINTER(FeBlock), C.c_void_p, C.c_void_p,
+                                         C.c_void_p]
+    L.cmadx_embedded_plan_create.argtypes = [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int64, C.c_int64,
+                                             C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_void_p)]
+    L.cmadx_embedded_plan_destroy.argtypes = [C.c_void_p]
+    L.cmadx_embedded_apply.argtypes = [C.c_void_p] * 8
     L.cmadx_fe_block_jvp.argtypes = [C.POINTER(Material), C.POINTER(C.c_int32), C.c_int32,
                                      C.POINTER(C.c_double), C.POINTER(FeBlock), C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]

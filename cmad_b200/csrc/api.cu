@@ -12,6 +12,17 @@
 #include "mp_update.cuh"
 
 namespace cmadx {
+struct EmbeddedPlan;
+cudaError_t launch_fe_cauchy(const DevMat& m, const cmadx_fe_block_t& b, const double* xi_state, double* sigma,
+                             cudaStream_t stream);
+cudaError_t embedded_plan_build(const int64_t* rows, const int64_t* cols, int64_t nnz, int64_t n,
+                                const int64_t* presc, int64_t n_presc, EmbeddedPlan** out);
+void embedded_plan_free(EmbeddedPlan* P);
+cudaError_t embedded_apply(const EmbeddedPlan* P, const double* K, const double* R, const double* U,
+                           const double* presc_vals, double* r_out, double* K_emb_out, cudaStream_t stream);
+}  // namespace cmadx
+
+namespace cmadx {
 int64_t fe_vjp_blocks(int64_t npts);
 cudaError_t launch_fe_block_vjp(const FeArgs& A, const double* Rbar, const double* xibar, double* partials,
                                 double* pbar, cudaStream_t s);
@@ -561,6 +572,50 @@ int cmadx_fe_block_assemble_mixed(const cmadx_material_t* mat, const cmadx_newto
                                   void* stream) {
     if (!mix) return CMADX_EINVAL;
     return fe_block_assemble(mat, newton, blk, mix, stream);
+}
+
+int cmadx_fe_cauchy_at_ips(const cmadx_material_t* mat, const cmadx_fe_block_t* blk,
+                           const double* xi_state, double* sigma, void* stream) {
+    if (!blk || !xi_state || !sigma) return CMADX_EINVAL;
+    cmadx_fe_block_t b = *blk;
+    if (!b.xi_prev) b.xi_prev = xi_state;       // not used by this entry point
+    if (!b.xi) b.xi = sigma;
+    FeArgs A;
+    if (int rc = check_fe_block(mat, &b, &A)) return rc;
+    cudaError_t e = cmadx::launch_fe_cauchy(A.m, A.b, xi_state, sigma, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return CMADX_OK;
+}
+
+int cmadx_embedded_plan_create(const int64_t* rows_host, const int64_t* cols_host, int64_t nnz,
+                               int64_t n_dofs, const int64_t* presc_idx_host, int64_t n_presc,
+                               cmadx_embedded_plan_t** plan) {
+    if (!plan || nnz < 0 || n_dofs < 0 || n_presc < 0 || (nnz && (!rows_host || !cols_host)) ||
+        (n_presc && !presc_idx_host) || n_dofs >= (int64_t)0x7fffffff)
+        return CMADX_EINVAL;
+    cmadx::EmbeddedPlan* P = nullptr;
+    cudaError_t e = cmadx::embedded_plan_build(rows_host, cols_host, nnz, n_dofs, presc_idx_host, n_presc, &P);
+    if (e == cudaErrorInvalidValue) return CMADX_EINVAL;
+    if (e != cudaSuccess) return cuda_fail(e);
+    *plan = reinterpret_cast<cmadx_embedded_plan_t*>(P);
+    return CMADX_OK;
+}
+
+int cmadx_embedded_plan_destroy(cmadx_embedded_plan_t* plan) {
+    cmadx::embedded_plan_free(reinterpret_cast<cmadx::EmbeddedPlan*>(plan));
+    return CMADX_OK;
+}
+
+int cmadx_embedded_apply(const cmadx_embedded_plan_t* plan, const double* K_data, const double* R,
+                         const double* U, const double* presc_vals, double* r_out,
+                         double* K_emb_out, void* stream) {
+    if (!plan || !K_data || (r_out && (!R || !U || !presc_vals)) || r_out == R) return CMADX_EINVAL;
+    cudaError_t e = cmadx::embedded_apply(reinterpret_cast<const cmadx::EmbeddedPlan*>(plan), K_data, R, U,
+                                          presc_vals, r_out, K_emb_out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add((r_out ? 1 : 0) + (K_emb_out ? 1 : 0), std::memory_order_relaxed);
+    return CMADX_OK;
 }
 
 int cmadx_fe_block_jvp(const cmadx_material_t* mat, const int32_t* active_pid, int32_t n_active,

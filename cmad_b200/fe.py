@@ -219,6 +219,92 @@ def mixed_r_plan(arrays: FEBlockArrays, device=None) -> SegmentPlan:
     return SegmentPlan(seg, arrays.n_dofs, device=device if device is not None else arrays.grad_N.device)
 
 
+def evaluate_cauchy_at_ips(material: L.Material, arrays: FEBlockArrays, U_global: torch.Tensor,
+                           xi: torch.Tensor, out: torch.Tensor | None = None,
+                           stream: torch.cuda.Stream | None = None) -> torch.Tensor:
+    """``(n_elems, n_ip, 6)`` cauchy stress at every integration point of a COUPLED block from
+    the stored converged state ``xi`` (cmad/fem/postprocess.py:35-185, ``model.cauchy`` branch):
+    no Newton, one HBM-bound launch."""
+    n_e, n_ip = arrays.n_elems, arrays.n_ip
+    dev = arrays.grad_N.device
+    if dev.type != "cuda":
+        raise ValueError("FE block arrays must live on a CUDA device (there is no CPU fallback)")
+    if U_global.dtype != torch.float64 or U_global.numel() != arrays.n_dofs or not U_global.is_contiguous():
+        raise ValueError(f"U_global: expected contiguous float64 ({arrays.n_dofs},)")
+    if xi.dtype != torch.float64 or tuple(xi.shape) != (n_e, n_ip, 7) or not xi.is_contiguous():
+        raise ValueError(f"xi: expected contiguous float64 ({n_e}, {n_ip}, 7)")
+    if out is None:
+        out = torch.empty((n_e, n_ip, 6), dtype=torch.float64, device=dev)
+    b = _fe_struct(arrays, U_global, xi, {"xi": out})
+    s = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        rc = L.lib().cmadx_fe_cauchy_at_ips(C.byref(material), C.byref(b), C.c_void_p(xi.data_ptr()),
+                                            C.c_void_p(out.data_ptr()), C.c_void_p(s.cuda_stream))
+    L.check(rc, "cmadx_fe_cauchy_at_ips")
+    return out
+
+
+class ReactionPlan:
+    """``FELoadMatch._reaction_at`` (cmad/qois/fe_load_match.py:179-196): the assembled residual
+    summed over each requested component's sideset dofs, deterministically (K5 over the
+    gathered entries).  ``eq_per_component``: list of int arrays of global equations."""
+
+    def __init__(self, eq_per_component, device):
+        self.device = torch.device(device)
+        eqs = [np.asarray(e, dtype=np.int64).reshape(-1) for e in eq_per_component]
+        self._gather = torch.from_numpy(np.concatenate(eqs) if eqs else np.zeros(0, np.int64)).to(self.device)
+        seg = np.concatenate([np.full(len(e), c, dtype=np.int64) for c, e in enumerate(eqs)]) if eqs \
+            else np.zeros(0, np.int64)
+        self._plan = SegmentPlan(seg, len(eqs), device=self.device)
+
+    def __call__(self, R: torch.Tensor) -> torch.Tensor:
+        return self._plan.sum(R.index_select(0, self._gather).contiguous())
+
+
+class EmbeddedBCPlan:
+    """Device-side ``_embedded_bc_enforce`` + ``_embedded_residual``
+    (cmad/fem/sparse_solve.py:1058-1174) over the deduplicated COO pattern ``(rows, cols)``
+    for a fixed prescribed set: ``apply(K_data, R, U, presc_vals) -> (r, K_emb_data)``."""
+
+    def __init__(self, rows, cols, n_dofs: int, presc_idx, device=None):
+        rows = np.ascontiguousarray(rows, dtype=np.int64); cols = np.ascontiguousarray(cols, dtype=np.int64)
+        idx = np.ascontiguousarray(presc_idx, dtype=np.int64)
+        self.n, self.nnz, self.n_presc = int(n_dofs), int(rows.size), int(idx.size)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._h = C.c_void_p()
+        p64 = C.POINTER(C.c_int64)
+        with torch.cuda.device(self.device):
+            rc = L.lib().cmadx_embedded_plan_create(rows.ctypes.data_as(p64), cols.ctypes.data_as(p64), self.nnz,
+                                                    self.n, idx.ctypes.data_as(p64), self.n_presc, C.byref(self._h))
+        L.check(rc, "cmadx_embedded_plan_create")
+
+    def apply(self, K_data: torch.Tensor, R: torch.Tensor, U: torch.Tensor, presc_vals: torch.Tensor,
+              stream: torch.cuda.Stream | None = None):
+        for name, t, n in (("K_data", K_data, self.nnz), ("R", R, self.n), ("U", U, self.n),
+                           ("presc_vals", presc_vals, self.n_presc)):
+            if t.dtype != torch.float64 or t.numel() != n or not t.is_contiguous() or t.device != self.device:
+                raise ValueError(f"{name}: expected contiguous float64 with {n} entries on {self.device}")
+        r = torch.empty(self.n, dtype=torch.float64, device=self.device)
+        K_emb = torch.empty(self.nnz, dtype=torch.float64, device=self.device)
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            rc = L.lib().cmadx_embedded_apply(self._h, K_data.data_ptr(), R.data_ptr(), U.data_ptr(),
+                                              presc_vals.data_ptr(), r.data_ptr(), K_emb.data_ptr(), s.cuda_stream)
+        L.check(rc, "cmadx_embedded_apply")
+        return r, K_emb
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            L.lib().cmadx_embedded_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def fe_block_jvp(material: L.Material, arrays: FEBlockArrays, U_global: torch.Tensor,
                  xi_prev: torch.Tensor, xi_state: torch.Tensor, active_pid, dp,
                  dxi_prev: torch.Tensor | None = None, outputs=("xi", "R_elem"), out: dict | None = None,

@@ -121,14 +121,19 @@ def fe_newton_solve(assemble, pattern: SparsePattern, bcs: DirichletBCs, U_prev:
                     xi_prev, t: float, settings: dict | None = None):
     """One load step: ``(U*, xi*, log)``.  ``assemble(U, xi_prev) -> (R, K_data, xi)``
     with ``R (n_dofs,)`` and ``K_data`` on ``pattern`` as host arrays (``xi`` is opaque
-    to the driver and stays wherever ``assemble`` keeps it)."""
+    to the driver and stays wherever ``assemble`` keeps it).  An assembler with an
+    ``enforced(U, xi_prev, t) -> (r, K_emb, xi)`` attribute (:class:`DeviceEmbeddedBCs`) applies
+    the embedded-BC treatment itself, on the device."""
     s = {**DEFAULT_NONLINEAR, **(settings or {})}
     ls = {**DEFAULT_LINE_SEARCH, **(s.get("line search") or {})}
     log = NewtonLog()
+    enforced = getattr(assemble, "enforced", None)
 
     def assemble_enforced(U):
-        R, K_data, xi = assemble(U, xi_prev)
         log.assemblies += 1
+        if enforced is not None:
+            return enforced(U, xi_prev, t)
+        R, K_data, xi = assemble(U, xi_prev)
         r, K_emb = embedded_system(pattern, K_data, R, U, bcs, t)
         return r, K_emb, xi
 
@@ -252,14 +257,19 @@ def cuda_assembler(material, newton, arrays, r_plan, k_plan, outputs=None):
     from . import fe
     dev = arrays.grad_N.device
 
-    def assemble(U, xi_prev):
+    def device(U, xi_prev):
         Ud = torch.from_numpy(np.ascontiguousarray(U)).to(dev)
         R, vals, xi = fe.assemble_element_block(material, newton, arrays, Ud, xi_prev, r_plan=r_plan)
         K_data = k_plan.sum(vals)
         if outputs is not None:
             outputs["last"] = (R, K_data, xi)
+        return R, K_data, xi
+
+    def assemble(U, xi_prev):
+        R, K_data, xi = device(U, xi_prev)
         return R.cpu().numpy(), K_data.cpu().numpy(), xi
 
+    assemble.device = device
     return assemble
 
 
@@ -271,13 +281,49 @@ def cuda_assembler_mixed(material, newton, arrays, r_plan, k_plan, stab_mult: fl
     from . import fe
     dev = arrays.grad_N.device
 
-    def assemble(U, xi_prev):
+    def device(U, xi_prev):
         Ud = torch.from_numpy(np.ascontiguousarray(U)).to(dev)
         R, vals, xi = fe.assemble_element_block_mixed(material, newton, arrays, Ud, xi_prev,
                                                       stab_mult=stab_mult, r_plan=r_plan)
         K_data = k_plan.sum(vals)
         if outputs is not None:
             outputs["last"] = (R, K_data, xi)
+        return R, K_data, xi
+
+    def assemble(U, xi_prev):
+        R, K_data, xi = device(U, xi_prev)
         return R.cpu().numpy(), K_data.cpu().numpy(), xi
 
+    assemble.device = device
     return assemble
+
+
+class DeviceEmbeddedBCs:
+    """Wraps a CUDA assembler so that the embedded-BC treatment (sparse_solve.py:1058-1174)
+    also runs on the device (``fe.EmbeddedBCPlan``): per assembly, K3 + K5 + two HBM-bound
+    passes, then ONE device->host copy of ``(r, K_emb data)`` for the host sparse solve.
+    The CSC structure of ``K_emb`` is fixed by the pattern and built once."""
+
+    def __init__(self, assemble, pattern: SparsePattern, bcs: DirichletBCs, device):
+        import torch
+        from . import fe
+        self._assemble, self._bcs, self._dev = assemble, bcs, torch.device(device)
+        self._plan = fe.EmbeddedBCPlan(pattern.rows, pattern.cols, pattern.n, bcs.indices, device=device)
+        ids = sp.csc_matrix((np.arange(1, len(pattern.rows) + 1, dtype=np.float64), (pattern.rows, pattern.cols)),
+                            shape=(pattern.n, pattern.n))
+        ids.sort_indices()
+        self._perm = ids.data.astype(np.int64) - 1          # csc slot -> COO entry
+        self._indices, self._indptr, self._n = ids.indices.copy(), ids.indptr.copy(), pattern.n
+        self.outputs = getattr(assemble, "outputs", None)
+
+    def __call__(self, U, xi_prev):                      # plain assembly (sensitivities etc.)
+        return self._assemble(U, xi_prev)
+
+    def enforced(self, U, xi_prev, t):
+        import torch
+        R, K_data, xi = self._assemble.device(U, xi_prev)
+        Ud = torch.from_numpy(np.ascontiguousarray(U)).to(self._dev)
+        vals = torch.from_numpy(np.ascontiguousarray(self._bcs.values(t), dtype=np.float64)).to(self._dev)
+        r, K_emb = self._plan.apply(K_data, R, Ud, vals)
+        data = K_emb.cpu().numpy()[self._perm]
+        return r.cpu().numpy(), sp.csc_matrix((data, self._indices, self._indptr), shape=(self._n, self._n)), xi

@@ -323,6 +323,31 @@ int cmadx_fe_block_vjp(const cmadx_material_t* mat, const int32_t* active_pid, i
                        const double* Rbar_global, const double* xibar, double* pbar_dev,
                        double* workspace, void* stream);
 
+/* ---- Post-processing at a stored state: evaluate_cauchy_at_ips ------------------------
+ * model.cauchy(xi, xi_prev, params, U_ip, U_ip_prev) at every (element, IP) of a COUPLED block
+ * from the converged local state (cmad/fem/postprocess.py:35-185): sigma [n_elems][n_ip][6],
+ * global axes, packed xx,xy,xz,yy,yz,zz.  Uses blk->elem_eq, U, grad_N and the counts only.  */
+int cmadx_fe_cauchy_at_ips(const cmadx_material_t* mat, const cmadx_fe_block_t* blk,
+                           const double* xi_state, double* sigma, void* stream);
+
+/* ---- Embedded Dirichlet BCs on the deduplicated COO tangent ---------------------------
+ * _embedded_bc_enforce + _embedded_residual (cmad/fem/sparse_solve.py:1058-1174) as two
+ * HBM-bound passes over device arrays.  The plan is built once per (pattern, prescribed set):
+ * rows/cols = the UNIQUE (deduplicated) pattern the COO dedup plan writes to.
+ *   K_emb[e] = K[e] where both indices are free or e is a prescribed diagonal, else 0
+ *              (the prescribed diagonal keeps the assembled K_ii, as the reference's);
+ *   r[i]     = R[i] + sum_{j prescribed} K[i,j] (val_j - U_j)   on free rows (entry order),
+ *   r[i]     = K_ii (U_i - val_i)                               on prescribed rows.
+ * presc_vals: device, in the order of presc_idx.  K_emb may alias K; r must not alias R.   */
+typedef struct cmadx_embedded_plan cmadx_embedded_plan_t;
+int cmadx_embedded_plan_create(const int64_t* rows_host, const int64_t* cols_host, int64_t nnz,
+                               int64_t n_dofs, const int64_t* presc_idx_host, int64_t n_presc,
+                               cmadx_embedded_plan_t** plan);
+int cmadx_embedded_plan_destroy(cmadx_embedded_plan_t* plan);
+int cmadx_embedded_apply(const cmadx_embedded_plan_t* plan, const double* K_data, const double* R,
+                         const double* U, const double* presc_vals, double* r_out,
+                         double* K_emb_out, void* stream);
+
 /* ---- K5: deterministic segment sums (R scatter-add, COO dedup) -----------------
  * out[s] = sum of vals[i] over all items i with seg_of_item[i] == s, summed in
  * increasing item order (bit-reproducible, and the order a sequential

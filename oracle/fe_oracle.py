@@ -136,6 +136,40 @@ def assemble_block_mixed(prob: oracle_c.OracleProblem, elem_eq, elem_eq_p, U, xi
     return out
 
 
+def cauchy_at_ips(prob_eval: oracle_c.OracleProblem, elem_eq, U, xi, grad_N) -> np.ndarray:
+    """``evaluate_cauchy_at_ips`` for a COUPLED block (cmad/fem/postprocess.py:35-185):
+    ``model.cauchy(xi, ., params, U_ip, .)`` at the stored state; ``prob_eval`` described with
+    ``strain_comps=9, max_iters=0``.  Returns ``(n_e, n_ip, 6)``."""
+    elem_eq = np.asarray(elem_eq, dtype=np.int64)
+    n_e, n_ip, n_b, _ = grad_N.shape
+    U_e = np.asarray(U)[elem_eq].reshape(n_e, n_b, 3)
+    out = np.zeros((n_e, n_ip, 6))
+    for ip in range(n_ip):
+        gu = np.einsum("eak,eaj->ekj", U_e, grad_N[:, ip]).reshape(n_e, 9).T.copy()
+        x = xi[:, ip].T.copy()
+        out[:, ip] = oracle_c.mp_update(prob_eval, x, gu, xi_init=x, want=("sigma",))["sigma"].T
+    return out
+
+
+def embedded_system(rows, cols, n, K_data, R, U, presc_idx, presc_vals):
+    """``_embedded_bc_enforce`` + ``_embedded_residual`` (cmad/fem/sparse_solve.py:1058-1174) on
+    a deduplicated COO pattern, restated with plain NumPy loops over the entries:
+    returns ``(r, K_emb_data)`` on the same pattern (prescribed diagonal = assembled K_ii)."""
+    rows = np.asarray(rows); cols = np.asarray(cols); K = np.asarray(K_data, dtype=np.float64)
+    p_mask = np.zeros(n, dtype=bool); p_mask[presc_idx] = True
+    keep = ~(p_mask[rows] | p_mask[cols])                          # :1146-1147
+    K_ii_full = np.zeros(n); np.add.at(K_ii_full, rows, K * (rows == cols))      # :1149-1152
+    K_ii = K_ii_full[presc_idx]
+    K_emb = K * keep
+    diag_presc = (rows == cols) & p_mask[rows]
+    K_emb[diag_presc] = K[diag_presc]                              # appended (presc, presc) entries, deduplicated
+    inc = np.zeros(n); inc[presc_idx] = np.asarray(presc_vals) - np.asarray(U)[presc_idx]      # :1173-1175
+    r = np.asarray(R, dtype=np.float64).copy()
+    np.add.at(r, rows, K * inc[cols])
+    r[presc_idx] = K_ii * (np.asarray(U)[presc_idx] - np.asarray(presc_vals))                 # :1177-1179
+    return r, K_emb
+
+
 def coo_dedup_sum(vals: np.ndarray, scatter: np.ndarray, n_unique: int) -> np.ndarray:
     """``zeros(n_unique).at[coo_dedup_scatter].add(vals)`` (assembly.py:906-909)."""
     out = np.zeros(n_unique)

@@ -360,3 +360,79 @@ def test_repeated_launches_are_bit_identical(cuda_device, family, div):
     assert float((K - K.transpose(1, 2)).abs().max()) < 1e-9 * float(K.abs().max())
     Rsum = ref["R_elem"].reshape(arr.n_elems, -1, 3).sum(dim=1).abs().max()
     assert float(Rsum) < 1e-9 * float(ref["R_elem"].abs().max())
+
+
+# ---------------------------------------------------------------- post-processing / QoI / embedded BCs
+@pytest.mark.parametrize("family", ["tet4", "hex8"])
+@pytest.mark.parametrize("kind", ["J2", "hill_rot"])
+def test_cauchy_at_ips_and_reaction(cuda_device, family, kind):
+    """evaluate_cauchy_at_ips (postprocess.py:35-185) and FELoadMatch._reaction_at
+    (fe_load_match.py:179-196) on the CUDA path vs the oracle."""
+    from cmad_b200 import fe, fe_mesh, material_from_values
+    from oracle import fe_oracle
+    from tests.golden.materials import material
+    values = material(kind)
+    nodes, conn = fe_mesh.structured_hex_mesh((3, 2, 2))
+    if family == "tet4":
+        conn = fe_mesh.split_hex_to_tets(conn)
+    arr_h = fe_mesh.block_arrays(nodes, conn)
+    arr = arr_h.to(cuda_device)
+    U = fe_mesh.synthetic_displacement(nodes, 2.0, seed=11, ramp=0.004, noise=5e-4)
+    mat, nw = material_from_values(values), fe.fe_newton_settings()
+    xi0 = torch.zeros((arr.n_elems, arr.n_ip, 7), dtype=torch.float64, device=cuda_device)
+    Ud = torch.from_numpy(U).to(cuda_device)
+    o = fe.fe_block_launch(mat, nw, arr, Ud, xi0, ("xi", "sigma", "R_elem"))
+    sig = fe.evaluate_cauchy_at_ips(mat, arr, Ud, o["xi"])
+    torch.cuda.synchronize()
+    # the kernel that solved the step and the post-processing kernel agree...
+    assert rel_err(sig.cpu().numpy(), o["sigma"].cpu().numpy()) < 1e-12
+    # ...and both agree with the oracle's model.cauchy at the stored state
+    prob = oc.describe(values, None, newton_mode="traced", strain_comps=9, max_iters=0)
+    ref = fe_oracle.cauchy_at_ips(prob, arr_h.elem_eq.numpy(), U, o["xi"].cpu().numpy(), arr_h.grad_N.numpy())
+    assert rel_err(sig.cpu().numpy(), ref) < 1e-10
+    # reactions: residual summed over the x = max face dofs, per component
+    nid = np.arange(nodes.shape[0])[np.isclose(nodes[:, 0], nodes[:, 0].max())]
+    eqs = [nid * 3 + c for c in range(3)]
+    plan = fe.SegmentPlan(arr_h.elem_eq.numpy().reshape(-1), arr.n_dofs, device=cuda_device)
+    R = plan.sum(o["R_elem"].reshape(-1))
+    react = fe.ReactionPlan(eqs, cuda_device)(R).cpu().numpy()
+    Rn = R.cpu().numpy()
+    assert np.allclose(react, [Rn[e].sum() for e in eqs], rtol=1e-12, atol=1e-12 * np.abs(Rn).max())
+
+
+def test_device_embedded_bcs_match_reference_restatement(cuda_device):
+    """_embedded_bc_enforce + _embedded_residual (sparse_solve.py:1058-1174) on the device vs the
+    NumPy restatement and vs the host treatment the driver uses; then the same Newton
+    trajectory with device-side enforcement as with host-side enforcement."""
+    from cmad_b200 import fe, fe_driver as drv, fe_mesh, material_from_values
+    from oracle import analytic, fe_oracle
+    from tests.test_fe_driver import LOCAL_NEWTON, uniaxial_cube
+    values, _, _ = analytic.j2_voce_param_tree("J2")
+    nodes, arr, bcs, pattern, scatter = uniaxial_cube(4, "hex8")
+    arr_d = arr.to(cuda_device)
+    r_plan = fe.SegmentPlan(arr.elem_eq.numpy().reshape(-1), arr.n_dofs, device=cuda_device)
+    k_plan = fe.SegmentPlan(scatter, len(pattern.rows), device=cuda_device)
+    mat, nw = material_from_values(values), fe.fe_newton_settings(**LOCAL_NEWTON)
+    asm = drv.cuda_assembler(mat, nw, arr_d, r_plan, k_plan)
+    rng = np.random.default_rng(0)
+    U = fe_mesh.synthetic_displacement(nodes, 1.5, seed=2, ramp=0.003, noise=3e-4)
+    xi0 = torch.zeros((arr.n_elems, arr.n_ip, 7), dtype=torch.float64, device=cuda_device)
+    R, K, _ = asm.device(U, xi0)
+    t = 0.7
+    vals = bcs.values(t)
+    plan = fe.EmbeddedBCPlan(pattern.rows, pattern.cols, pattern.n, bcs.indices, device=cuda_device)
+    r_d, K_d = plan.apply(K, R, torch.from_numpy(U).to(cuda_device), torch.from_numpy(vals).to(cuda_device))
+    r_ref, K_ref = fe_oracle.embedded_system(pattern.rows, pattern.cols, pattern.n, K.cpu().numpy(), R.cpu().numpy(),
+                                             U, bcs.indices, vals)
+    assert rel_err(r_d.cpu().numpy(), r_ref) < 1e-13 and rel_err(K_d.cpu().numpy(), K_ref) == 0.0
+    r_h, K_h = drv.embedded_system(pattern, K.cpu().numpy(), R.cpu().numpy(), U, bcs, t)
+    assert rel_err(r_h, r_ref) < 1e-13
+    assert abs(K_h - pattern.csr(K_ref).tocsc()).max() < 1e-13 * np.abs(K_ref).max()
+    # whole load-step loop
+    ts = np.linspace(0.0, 1.0, 4)
+    Uh, xih, _, lh = drv.fe_quasistatic_drive(asm, pattern, bcs, np.zeros(arr.n_dofs), xi0, ts)
+    asm_dev = drv.DeviceEmbeddedBCs(asm, pattern, bcs, cuda_device)
+    Ud, xid, _, ld = drv.fe_quasistatic_drive(asm_dev, pattern, bcs, np.zeros(arr.n_dofs), xi0, ts)
+    assert [l.iters for l in ld] == [l.iters for l in lh]
+    assert np.abs(Ud - Uh).max() < 1e-12 * np.abs(Uh).max()
+    assert np.abs(xid.cpu().numpy() - xih.cpu().numpy()).max() < 1e-12
