@@ -413,6 +413,42 @@ def reduce_residual(R_local: torch.Tensor, group=None) -> torch.Tensor:
     return R_local
 
 
+class InterfaceExchange:
+    """Halo exchange of the assembled residual for an element partition: only the dofs touched
+    by MORE than one rank need summing, so the per-step collective is one all-reduce of the
+    packed interface entries (O(interface) bytes) instead of the whole vector (O(n_dofs)).
+    After :meth:`reduce`, ``R`` is complete on every dof this rank's elements touch (its own
+    interior + the interfaces it shares); entries of other ranks' interiors stay untouched.
+    Set-up costs one all-reduce of an int32 touch-count vector, once per mesh partition.
+    NCCL over NVLink on GPUs; the same code runs on gloo in the CPU tests."""
+
+    def __init__(self, elem_eq: torch.Tensor, n_dofs: int, group=None, extra_eq: torch.Tensor | None = None):
+        import torch.distributed as dist
+        self._group = group
+        self._active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        dev = elem_eq.device
+        touched = torch.zeros(n_dofs, dtype=torch.int32, device=dev)
+        eqs = [elem_eq.reshape(-1).long()] + ([extra_eq.reshape(-1).long()] if extra_eq is not None else [])
+        for e in eqs:
+            touched[e] = 1
+        self.mine = touched.bool()
+        count = touched.clone()
+        if self._active:
+            dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
+        self.index = torch.nonzero(count > 1).reshape(-1)          # same on every rank, sorted
+        self.n_interface = int(self.index.numel())
+        self._buf = torch.empty(self.n_interface, dtype=torch.float64, device=dev)
+
+    def reduce(self, R: torch.Tensor) -> torch.Tensor:
+        if not self._active or self.n_interface == 0:
+            return R
+        import torch.distributed as dist
+        torch.index_select(R, 0, self.index, out=self._buf)
+        dist.all_reduce(self._buf, op=dist.ReduceOp.SUM, group=self._group)
+        R.index_copy_(0, self.index, self._buf)
+        return R
+
+
 def assemble_global(blocks: Mapping[str, tuple], U_global: torch.Tensor,
                     xi_prev_by_block: Mapping[str, torch.Tensor], coo_plan: SegmentPlan | None = None,
                     r_plans: Mapping[str, SegmentPlan] | None = None, group=None):

@@ -140,7 +140,10 @@ def _fe_gloo_worker(rank, world, port, nodes, conn, U, ret):
     o = fe_oracle.assemble_block(prob, local.elem_eq.numpy(), U, np.zeros((hi - lo, arr.n_ip, 7)),
                                  local.grad_N.numpy(), local.det.numpy(), local.quad_w.numpy())
     R = fe.reduce_residual(torch.from_numpy(o["R"].copy()))         # product exchange step
-    ret[rank] = (R.numpy(), lo, hi, o["K_elem"])
+    # halo variant: only the dofs shared between ranks are exchanged
+    halo = fe.InterfaceExchange(local.elem_eq, arr.n_dofs)
+    R_halo = halo.reduce(torch.from_numpy(o["R"].copy()))
+    ret[rank] = (R.numpy(), lo, hi, o["K_elem"], R_halo.numpy(), halo.mine.numpy(), halo.n_interface)
     dist.destroy_process_group()
 
 
@@ -157,9 +160,12 @@ def test_two_rank_gloo_element_partition_equals_single_process():
     ret = tmp.Manager().dict()
     tmp.spawn(_fe_gloo_worker, args=(2, 29500 + os.getpid() % 2000, nodes, conn, U, ret), nprocs=2, join=True)
     for r in (0, 1):
-        R, lo, hi, K = ret[r]
+        R, lo, hi, K, R_halo, mine, n_if = ret[r]
         assert np.allclose(R, full["R"], rtol=1e-13, atol=1e-13 * np.abs(full["R"]).max())
         assert np.array_equal(K, full["K_elem"][lo:hi])             # element-owned data stays local
+        # interface exchange: complete on every dof this rank touches, 4 shared nodes x 3 dofs moved
+        assert n_if == 12 and mine.sum() in (36, 24)
+        assert np.allclose(R_halo[mine], full["R"][mine], rtol=1e-13, atol=1e-13 * np.abs(full["R"]).max())
     assert (ret[0][1], ret[0][2], ret[1][1], ret[1][2]) == (0, 2, 2, 3)
 
 
