@@ -15,13 +15,14 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "lib", "libcmad_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
-SOURCES = ["api.cu", "mp_update.cu", "mp_update_j2.cu", "elastic_update.cu", "mp_sens.cu",
+SOURCES = ["api.cu", "mp_update.cu", "mp_update_j2.cu", "mp_update_dt.cu", "elastic_update.cu", "mp_sens.cu", "mp_sens_dt.cu",
            "fe_block.cu", "fe_tet4.cu", "fe_hex8.cu", "fe_mixed.cu", "fe_post.cu", "fe_vjp.cu", "fe_scatter.cu"]
 
 # ---- enums (mirror include/cmad_b200.h) ---------------------------------
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(5)
 MODEL_SMALL_ELASTIC_PLASTIC, MODEL_ELASTIC = 0, 1
 YIELD_J2, YIELD_HILL, YIELD_HOSFORD = 0, 1, 2
+DEF_FULL_3D, DEF_PLANE_STRESS, DEF_UNIAXIAL_STRESS = 0, 1, 2
 ELASTIC_PAIRS = [("E", "nu"), ("E", "mu"), ("E", "kappa"), ("E", "lambda"), ("kappa", "mu"),
                  ("kappa", "nu"), ("kappa", "lambda"), ("lambda", "mu"), ("lambda", "nu"),
                  ("mu", "nu")]
@@ -50,7 +51,7 @@ class Newton(C.Structure):
 
 class MpBuffers(C.Structure):
     _fields_ = [("n", C.c_int64), ("ld", C.c_int64), ("strain_comps", C.c_int32),
-                ("reserved", C.c_int32), ("xi_prev", C.c_void_p), ("strain", C.c_void_p), ("xi_init", C.c_void_p),
+                ("def_type", C.c_int32), ("xi_prev", C.c_void_p), ("strain", C.c_void_p), ("xi_init", C.c_void_p),
                 ("xi", C.c_void_p), ("sigma", C.c_void_p), ("dsig_deps", C.c_void_p),
                 ("dxi_deps", C.c_void_p), ("dC_dp", C.c_void_p), ("dC_dxi", C.c_void_p),
                 ("dC_dxi_prev", C.c_void_p), ("iters", C.c_void_p), ("flags", C.c_void_p),

@@ -34,6 +34,7 @@ struct SensArgs {
     double* partials;
 };
 cudaError_t launch_mp_sens(const SensArgs& A, bool adjoint, cudaStream_t stream);
+cudaError_t launch_mp_sens_dt(const SensArgs& A, int def_type, bool adjoint, cudaStream_t stream);
 int64_t sens_blocks(int64_t n);
 }  // namespace cmadx
 
@@ -162,7 +163,16 @@ static int build_args(const cmadx_material_t* mat, const cmadx_newton_t* nw,
     }
     A->n_active = n_active;
     if (b->n < 0 || b->ld < b->n) return CMADX_EINVAL;
-    if (b->strain_comps != 6 && b->strain_comps != 9) return CMADX_EINVAL;
+    if (b->def_type == CMADX_DEF_FULL_3D) {
+        if (b->strain_comps != 6 && b->strain_comps != 9) return CMADX_EINVAL;
+    } else if (b->def_type == CMADX_DEF_PLANE_STRESS || b->def_type == CMADX_DEF_UNIAXIAL_STRESS) {
+        const bool ps = b->def_type == CMADX_DEF_PLANE_STRESS;
+        if (ps ? (b->strain_comps != 3 && b->strain_comps != 4) : (b->strain_comps != 1)) return CMADX_EINVAL;
+        // identity material axes, SmallElasticPlastic only
+        if (A->m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC || A->m.rot) return CMADX_EUNSUPPORTED;
+    } else {
+        return CMADX_EINVAL;
+    }
     if (b->n > 0 && (!b->xi_prev || !b->strain)) return CMADX_EINVAL;
     A->b = *b;
     A->bail_count = nullptr; A->bail_list = nullptr; A->bail_cap = 0;
@@ -199,7 +209,9 @@ int get_bail_scratch(cudaStream_t s, BailScratch* out) {
 static int launch(const MpArgs& A, cudaStream_t s) {
     if (A.b.n == 0) return CMADX_OK;
     cudaError_t e;
-    if (A.m.model == CMADX_MODEL_ELASTIC) {
+    if (A.b.def_type != CMADX_DEF_FULL_3D) {
+        e = launch_mp_update_dt(A, s);
+    } else if (A.m.model == CMADX_MODEL_ELASTIC) {
         e = launch_mp_update_elastic(A, s);
     } else if (A.m.yield == CMADX_YIELD_J2 && !A.m.rot && !A.b.xi_init &&
                !(A.nw.flags & CMADX_NEWTON_F_GENERIC) && A.b.n < (int64_t)0x7fffffff) {
@@ -342,6 +354,7 @@ int cmadx_mp_update_host(const cmadx_material_t* mat, const cmadx_newton_t* newt
     if (int rc = build_args(mat, newton, active_pid, n_active, host, &A)) return rc;
     const int64_t n = host->n;
     if (n == 0) return CMADX_OK;
+    if (host->def_type != CMADX_DEF_FULL_3D) return CMADX_EUNSUPPORTED;   // device buffers only for now
     const int nxi = (A.m.model == CMADX_MODEL_ELASTIC) ? 6 : 7;
     int64_t chunk = chunk_points > 0 ? chunk_points : (int64_t)1 << 20;
     if (chunk > n) chunk = n;
@@ -431,12 +444,22 @@ int64_t cmadx_mp_objective_workspace_bytes(int64_t n, int32_t n_active) {
     return (int64_t)sizeof(double) * (sens_blocks(n) + 1) * (1 + n_active);
 }
 
+// the deformation type of a history is implied by its strain rows: 6 | 9 FULL_3D, 3 | 4
+// PLANE_STRESS (n_xi 8), 1 UNIAXIAL_STRESS (n_xi 9)
+static int history_def_type(const cmadx_mp_history_t* h) {
+    return (h->strain_comps == 6 || h->strain_comps == 9) ? CMADX_DEF_FULL_3D
+           : (h->strain_comps == 1 ? CMADX_DEF_UNIAXIAL_STRESS : CMADX_DEF_PLANE_STRESS);
+}
+static int history_n_xi(const cmadx_mp_history_t* h) { return 7 + history_def_type(h); }
+
 static int check_history(const cmadx_material_t* mat, const cmadx_mp_history_t* h, DevMat* dm) {
     if (!h) return CMADX_EINVAL;
     if (int rc = make_dev_mat(mat, dm)) return rc;
     if (dm->model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC) return CMADX_EUNSUPPORTED;
     if (h->n < 0 || h->ld < h->n || h->nsteps < 0) return CMADX_EINVAL;
-    if (h->strain_comps != 6 && h->strain_comps != 9) return CMADX_EINVAL;
+    const int sc = h->strain_comps;
+    if (sc != 6 && sc != 9 && sc != 3 && sc != 4 && sc != 1) return CMADX_EINVAL;
+    if (history_def_type(h) != CMADX_DEF_FULL_3D && dm->rot) return CMADX_EUNSUPPORTED;
     if (h->n > 0 && (!h->strain || !h->xi_hist)) return CMADX_EINVAL;
     return CMADX_OK;
 }
@@ -448,9 +471,11 @@ int cmadx_mp_forward_history(const cmadx_material_t* mat, const cmadx_newton_t* 
     cmadx_mp_buffers_t b;
     std::memset(&b, 0, sizeof(b));
     b.n = hist->n; b.ld = hist->ld; b.strain_comps = hist->strain_comps;
+    b.def_type = history_def_type(hist);
+    const int nxi = history_n_xi(hist);
     for (int t = 1; t <= hist->nsteps; ++t) {
-        b.xi_prev = hist->xi_hist + (int64_t)(t - 1) * 7 * hist->ld;
-        b.xi = hist->xi_hist + (int64_t)t * 7 * hist->ld;
+        b.xi_prev = hist->xi_hist + (int64_t)(t - 1) * nxi * hist->ld;
+        b.xi = hist->xi_hist + (int64_t)t * nxi * hist->ld;
         b.strain = hist->strain + (int64_t)t * hist->strain_comps * hist->ld;
         b.iters = hist->iters_hist ? hist->iters_hist + (int64_t)t * hist->ld : nullptr;
         if (int rc = cmadx_mp_update(mat, newton, nullptr, 0, &b, stream)) return rc;
@@ -474,7 +499,9 @@ static int objective(const cmadx_material_t* mat, const int32_t* active_pid, int
     A.n_active = n_active;
     A.h = *hist;
     A.partials = hist->workspace;
-    cudaError_t e = launch_mp_sens(A, adjoint, (cudaStream_t)stream);
+    const int dt = history_def_type(hist);
+    cudaError_t e = (dt == CMADX_DEF_FULL_3D) ? launch_mp_sens(A, adjoint, (cudaStream_t)stream)
+                                              : launch_mp_sens_dt(A, dt, adjoint, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     g_launches.fetch_add(2, std::memory_order_relaxed);
     return CMADX_OK;

@@ -247,8 +247,8 @@ template <> struct YieldFn<CMADX_YIELD_HOSFORD> {
 // --------------------------------------------------------------------------
 // partial-pivoting LU of an n x n matrix in (local) memory; returns the swap bits in
 // the order RegLU::solve_pivot replays them; a[k][k] holds 1/pivot afterwards
-static __device__ __noinline__ unsigned lu_factor_pivot_mem(double* a, int n) {
-    unsigned swaps = 0u;
+static __device__ __noinline__ unsigned long long lu_factor_pivot_mem(double* a, int n) {
+    unsigned long long swaps = 0ull;
     int bit = 0;
     for (int k = 0; k < n; ++k) {
         for (int i = k + 1; i < n; ++i) {
@@ -260,7 +260,7 @@ static __device__ __noinline__ unsigned lu_factor_pivot_mem(double* a, int n) {
                     a[i * n + j] = u;
                 }
             }
-            swaps |= (sw ? 1u : 0u) << bit;
+            swaps |= (sw ? 1ull : 0ull) << bit;
             ++bit;
         }
         const double rp = 1.0 / a[k * n + k];
@@ -277,7 +277,7 @@ static __device__ __noinline__ unsigned lu_factor_pivot_mem(double* a, int n) {
 template <int N>
 struct RegLU {
     double a[N][N];
-    unsigned swaps;
+    unsigned long long swaps;   // N (N - 1) / 2 row-exchange decisions (36 for N = 9)
 
     // natural-order elimination; returns true when this lane needs pivoting
     CMADX_DEV bool factor_natural() {
@@ -336,7 +336,7 @@ struct RegLU {
         for (int k = 0; k < N; ++k) {
 #pragma unroll
             for (int i = k + 1; i < N; ++i) {
-                const bool sw = (swaps >> bit) & 1u;
+                const bool sw = (swaps >> bit) & 1ull;
                 const double u = b[k], v = b[i];
                 b[k] = sw ? v : u;
                 b[i] = sw ? u : v;
@@ -378,7 +378,7 @@ CMADX_DEV void newton_direction(const DevMat& m, const Pt& pt, double dg, double
 // --------------------------------------------------------------------------
 template <int YK>
 struct SepPoint {
-    static constexpr int N = 7;
+    static constexpr int N = 7, ALPHA = 6;
     YieldFn<YK> yf;
     double n[6];      // yield normal at the last evaluated state
     double f, eD;     // yield function, exp(-D alpha)
@@ -452,7 +452,7 @@ template <int YK> struct SepPointTraits {
 // Valid when the starting iterate equals xi_prev on the shear components.
 // --------------------------------------------------------------------------
 struct HosfordPoint {
-    static constexpr int N = 4;
+    static constexpr int N = 4, ALPHA = 3;
     YieldFn<CMADX_YIELD_HOSFORD> yf;
     double n[6];
     double f, eD;
@@ -544,7 +544,7 @@ template <int N> CMADX_DEV double dotN(const double (&u)[N], const double (&v)[N
 // Elastic model (cmad/models/elastic.py:139-173): state x = cauchy(6),
 // C = vec6(x - sigma_el(eps)) / (2 mu), sigma_el = kappa tr(eps) I + 2 mu dev(eps).
 struct ElasticPoint {
-    static constexpr int N = 6;
+    static constexpr int N = 6, ALPHA = 5;
     bool plastic;
     CMADX_DEV void residual(const DevMat& m, const double (&x)[6], const double (&)[6],
                             const double (&em)[6], double (&C)[6]) {
@@ -695,7 +695,7 @@ CMADX_DEV NewtonResult local_newton(const DevMat& m, const DevNewton& nw, Pt& pt
                 if (traced) {
 #pragma unroll
                     for (int i = 0; i < N; ++i) dx[i] = C[i];
-                    newton_direction<Pt, N>(m, pt, x[N - 1] - xp[N - 1], dx);   // solve(J, C)
+                    newton_direction<Pt, N>(m, pt, x[Pt::ALPHA] - xp[Pt::ALPHA], dx);   // solve(J, C)
                     const double CC = dotN<N>(C, C);
                     phi0 = 0.5 * CC; dphi0 = -CC; armijo = nw.c1 * dphi0;
                     ne = 0; al = 1.0; best_al = 1.0; best_phi = CUDART_INF;
@@ -706,7 +706,7 @@ CMADX_DEV NewtonResult local_newton(const DevMat& m, const DevNewton& nw, Pt& pt
                     // imperative newton_solve (no line search)
 #pragma unroll
                     for (int i = 0; i < N; ++i) dx[i] = -C[i];
-                    newton_direction<Pt, N>(m, pt, x[N - 1] - xp[N - 1], dx);   // solve(J, -C)
+                    newton_direction<Pt, N>(m, pt, x[Pt::ALPHA] - xp[Pt::ALPHA], dx);   // solve(J, -C)
 #pragma unroll
                     for (int i = 0; i < N; ++i) { x[i] += dx[i]; xt[i] = x[i]; }
                     ++ii;

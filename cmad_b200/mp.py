@@ -16,17 +16,31 @@ import torch
 from . import _lib as L
 from .material import NewtonSettings
 
-OUTPUT_COMPONENTS = {  # name -> (components as a function of n_xi, n_active), dtype
-    "xi": lambda n, a: n, "sigma": lambda n, a: 6, "dsig_deps": lambda n, a: 36,
-    "dxi_deps": lambda n, a: n * 6, "dC_dp": lambda n, a: n * a, "dC_dxi": lambda n, a: n * n,
-    "dC_dxi_prev": lambda n, a: n * n, "C": lambda n, a: n,
+OUTPUT_COMPONENTS = {  # name -> components as a function of (n_xi, n_active, n_strain_dirs)
+    "xi": lambda n, a, s=6: n, "sigma": lambda n, a, s=6: 6, "dsig_deps": lambda n, a, s=6: 6 * s,
+    "dxi_deps": lambda n, a, s=6: n * s, "dC_dp": lambda n, a, s=6: n * a, "dC_dxi": lambda n, a, s=6: n * n,
+    "dC_dxi_prev": lambda n, a, s=6: n * n, "C": lambda n, a, s=6: n,
 }
+# deformation types (cmad/models/deformation_types.py): n_xi, prescribed symmetric strain
+# components (= derivative directions), accepted strain rows
+DEF_TYPES = {L.DEF_FULL_3D: (7, 6, (6, 9)), L.DEF_PLANE_STRESS: (8, 3, (3, 4)), L.DEF_UNIAXIAL_STRESS: (9, 1, (1,))}
 POINT_SCALARS = {"iters": torch.int32, "flags": torch.int32, "cnorm": torch.float64}
 DEFAULT_OUTPUTS = ("xi", "sigma", "dsig_deps", "dC_dp", "iters", "flags")
 
 
-def n_xi_of(material: L.Material) -> int:
+def n_xi_of(material: L.Material, def_type: int = L.DEF_FULL_3D) -> int:
+    if def_type != L.DEF_FULL_3D:
+        return DEF_TYPES[def_type][0]
     return 6 if material.model == L.MODEL_ELASTIC else 7
+
+
+def init_xi(material: L.Material, n: int, device, def_type: int = L.DEF_FULL_3D) -> torch.Tensor:
+    """Initial local state (small_elastic_plastic.py:139-180): zeros, stretches = 1."""
+    nxi = n_xi_of(material, def_type)
+    x = torch.zeros((nxi, n), dtype=torch.float64, device=device)
+    if def_type != L.DEF_FULL_3D:
+        x[7:] = 1.0
+    return x
 
 
 def _check_in(name, t, rows, n, device_type):
@@ -39,15 +53,16 @@ def _check_in(name, t, rows, n, device_type):
 
 
 def allocate_outputs(material: L.Material, n: int, n_active: int, outputs, device,
-                     pin: bool = False) -> dict:
-    nxi = n_xi_of(material)
+                     pin: bool = False, def_type: int = L.DEF_FULL_3D) -> dict:
+    nxi = n_xi_of(material, def_type)
+    ns = DEF_TYPES[def_type][1]
     out = {}
     kw = dict(device=device)
     if pin:
         kw = dict(device="cpu", pin_memory=True)
     for name in outputs:
         if name in OUTPUT_COMPONENTS:
-            rows = OUTPUT_COMPONENTS[name](nxi, n_active)
+            rows = OUTPUT_COMPONENTS[name](nxi, n_active, ns)
             if name == "dC_dp" and n_active == 0:
                 continue
             out[name] = torch.empty((rows, n), dtype=torch.float64, **kw)
@@ -58,7 +73,7 @@ def allocate_outputs(material: L.Material, n: int, n_active: int, outputs, devic
     return out
 
 
-def _buffers(material, xi_prev, strain, xi_init, out: dict) -> L.MpBuffers:
+def _buffers(material, xi_prev, strain, xi_init, out: dict, def_type: int = L.DEF_FULL_3D) -> L.MpBuffers:
     n = xi_prev.shape[1]
     ld = xi_prev.stride(0) if xi_prev.shape[0] > 1 else max(n, 1)
     tensors = [xi_prev, strain] + ([xi_init] if xi_init is not None else []) + \
@@ -68,7 +83,7 @@ def _buffers(material, xi_prev, strain, xi_init, out: dict) -> L.MpBuffers:
         if s0 != ld:
             raise ValueError("all component-major arrays must share one leading dimension")
     b = L.MpBuffers()
-    b.n, b.ld, b.strain_comps = n, ld, strain.shape[0]
+    b.n, b.ld, b.strain_comps, b.def_type = n, ld, strain.shape[0], int(def_type)
     b.xi_prev, b.strain = xi_prev.data_ptr(), strain.data_ptr()
     b.xi_init = xi_init.data_ptr() if xi_init is not None else None
     for name in list(OUTPUT_COMPONENTS) + list(POINT_SCALARS):
@@ -78,25 +93,30 @@ def _buffers(material, xi_prev, strain, xi_init, out: dict) -> L.MpBuffers:
 
 def mp_update(material: L.Material, newton: NewtonSettings, active_pid, xi_prev: torch.Tensor,
               strain: torch.Tensor, outputs=DEFAULT_OUTPUTS, out: dict | None = None,
-              xi_init: torch.Tensor | None = None, stream: torch.cuda.Stream | None = None) -> dict:
+              xi_init: torch.Tensor | None = None, stream: torch.cuda.Stream | None = None,
+              def_type: int = L.DEF_FULL_3D) -> dict:
     """One batched constitutive update on the GPU (asynchronous on ``stream``).
 
     Returns the dict of requested output tensors (allocated unless ``out`` is
     given).  Raises if the CUDA library is unavailable - there is no fallback.
+    ``def_type``: FULL_3D (default), PLANE_STRESS (``xi`` has 8 rows, ``strain`` 3 =
+    (e_xx, e_xy, e_yy) or 4 = 2x2 grad_u) or UNIAXIAL_STRESS (9 rows, 1 strain row).
     """
     lib = L.lib()
-    nxi = n_xi_of(material)
+    if def_type not in DEF_TYPES:
+        raise ValueError(f"unknown def_type {def_type}")
+    nxi = n_xi_of(material, def_type)
     n = xi_prev.shape[1]
     _check_in("xi_prev", xi_prev, nxi, n, "cuda")
-    if strain.shape[0] not in (6, 9):
-        raise ValueError("strain must have 6 (symmetric) or 9 (grad_u) components")
+    if strain.shape[0] not in DEF_TYPES[def_type][2]:
+        raise ValueError(f"strain must have one of {DEF_TYPES[def_type][2]} components for this def_type")
     _check_in("strain", strain, strain.shape[0], n, "cuda")
     if xi_init is not None:
         _check_in("xi_init", xi_init, nxi, n, "cuda")
     pid = np.ascontiguousarray(active_pid, dtype=np.int32)
     if out is None:
-        out = allocate_outputs(material, n, len(pid), outputs, xi_prev.device)
-    b = _buffers(material, xi_prev, strain, xi_init, out)
+        out = allocate_outputs(material, n, len(pid), outputs, xi_prev.device, def_type=def_type)
+    b = _buffers(material, xi_prev, strain, xi_init, out, def_type)
     nw = newton.to_struct()
     s = stream if stream is not None else torch.cuda.current_stream(xi_prev.device)
     with torch.cuda.device(xi_prev.device):

@@ -31,7 +31,10 @@ from . import _lib as L
 from .material import NewtonSettings, active_param_ids, material_from_values
 from .parameters import Parameters
 
-FULL_3D = 0
+# DefType of the reference (cmad/models/deformation_types.py:4-9)
+FULL_3D, PLANE_STRAIN, PLANE_STRESS, UNIAXIAL_STRESS, PURE_SHEAR = range(5)
+_N_XI = {FULL_3D: 7, PLANE_STRESS: 8, UNIAXIAL_STRESS: 9}
+_NDIMS = {FULL_3D: 3, PLANE_STRESS: 2, UNIAXIAL_STRESS: 1}
 
 
 class GradientResult(NamedTuple):
@@ -43,19 +46,21 @@ class SmallElasticPlastic:
     """Constructor-compatible stand-in for the reference model class: carries the
     parameters and the deformation type; all evaluation happens in the kernels."""
     model_name = "small_elastic_plastic"
-    num_dofs = 7
-    num_residuals = 2
 
     def __init__(self, parameters: Parameters, def_type: int = FULL_3D, yield_tol: float = 1e-14,
-                 **unsupported):
-        if def_type != FULL_3D:
-            raise NotImplementedError("the B200 path covers DefType.FULL_3D (SURVEY.md 8f lists "
-                                      "PLANE_STRESS / UNIAXIAL_STRESS as later work)")
+                 uniaxial_stress_idx: int = 0, **unsupported):
+        if def_type not in _N_XI:
+            raise NotImplementedError(f"DefType {def_type} is not on the B200 path (FULL_3D, PLANE_STRESS, "
+                                      "UNIAXIAL_STRESS are)")
+        if def_type == UNIAXIAL_STRESS and uniaxial_stress_idx != 0:
+            raise NotImplementedError("UNIAXIAL_STRESS: only uniaxial_stress_idx = 0 is on the B200 path")
         if unsupported:
             raise NotImplementedError(f"unsupported model options: {sorted(unsupported)}")
         self.parameters = parameters
         self._def_type = def_type
         self.yield_tol = yield_tol
+        self.num_dofs = _N_XI[def_type]                       # small_elastic_plastic.py:126-180
+        self.num_residuals = 2 if def_type == FULL_3D else 3
 
     def material(self) -> L.Material:
         return material_from_values(self.parameters.values, self.model_name, self.yield_tol)
@@ -85,10 +90,12 @@ def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
 
 
 def strain_history_from_F(F: np.ndarray) -> np.ndarray:
-    """(B, 3, 3, N+1) deformation gradients -> (N+1, 9, B) grad_u = F - I slabs."""
+    """(B, nd, nd, N+1) deformation gradients -> (N+1, nd*nd, B) grad_u = F - I slabs
+    (nd = 3 FULL_3D, 2 PLANE_STRESS, 1 UNIAXIAL_STRESS: cmad/models/kinematics.py:10-57)."""
     F = np.asarray(F, dtype=np.float64)
-    gu = F - np.eye(3)[None, :, :, None]
-    return np.ascontiguousarray(gu.reshape(F.shape[0], 9, F.shape[-1]).transpose(2, 1, 0))
+    nd = F.shape[1]
+    gu = F - np.eye(nd)[None, :, :, None]
+    return np.ascontiguousarray(gu.reshape(F.shape[0], nd * nd, F.shape[-1]).transpose(2, 1, 0))
 
 
 def data_history(data: np.ndarray) -> np.ndarray:
@@ -105,7 +112,8 @@ class _DeviceHistories:
         self.n = strain_hist.shape[2]
         self.strain = torch.from_numpy(np.ascontiguousarray(strain_hist)).to(device)
         self.data = torch.from_numpy(np.ascontiguousarray(data_hist)).to(device)
-        self.xi = torch.zeros((self.N + 1, 7, self.n), dtype=torch.float64, device=device)
+        self.n_xi = {9: 7, 6: 7, 4: 8, 3: 8, 1: 9}[strain_hist.shape[1]]
+        self.xi = torch.zeros((self.N + 1, self.n_xi, self.n), dtype=torch.float64, device=device)
         self.iters = torch.zeros((self.N + 1, self.n), dtype=torch.int32, device=device)
         self.J_point = torch.zeros((self.n,), dtype=torch.float64, device=device)
         self.device = device
@@ -117,6 +125,9 @@ def gpu_local_evaluator(model: SmallElasticPlastic, strain_hist: np.ndarray, dat
     """Returns ``f() -> tensor[1 + n_active]`` (J, dJ/dp native) for this rank's
     points, evaluated with K1 + K2 on ``device`` at the model's current parameters."""
     lib = L.lib()
+    nd = _NDIMS[getattr(model, "_def_type", FULL_3D)]
+    if strain_hist.shape[1] not in ((6, 9) if nd == 3 else (nd * nd, 3) if nd == 2 else (1,)):
+        raise ValueError(f"strain history with {strain_hist.shape[1]} rows does not fit the model's def_type")
     hist = _DeviceHistories(strain_hist, data_hist, device)
     newton = newton or NewtonSettings(mode="imperative", max_iters=10, abs_tol=1e-14, rel_tol=1e-14)
     adjoint = {"adjoint": True, "direct": False}[strategy]
@@ -139,6 +150,7 @@ def gpu_local_evaluator(model: SmallElasticPlastic, strain_hist: np.ndarray, dat
         h.result, h.workspace, h.J_point = result.data_ptr(), ws.data_ptr(), hist.J_point.data_ptr()
         stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         hist.xi[0].zero_()
+        hist.xi[0, 7:] = 1.0                               # stretches of the def-type variants start at 1
         with torch.cuda.device(device):
             L.check(lib.cmadx_mp_forward_history(C.byref(mat), C.byref(nw), C.byref(h), stream),
                     "cmadx_mp_forward_history")

@@ -62,6 +62,11 @@ enum {
 };
 #define CMADX_MAX_ACTIVE 16
 
+/* deformation types of the material-point path (cmad/models/deformation_types.py) */
+#define CMADX_DEF_FULL_3D 0
+#define CMADX_DEF_PLANE_STRESS 1
+#define CMADX_DEF_UNIAXIAL_STRESS 2
+
 /* ---- local Newton flavour ------------------------------------------------ */
 enum {
     CMADX_NEWTON_TRACED = 0,     /* make_newton_solve,  cmad/models/nonlinear_solver.py:88-174 */
@@ -107,9 +112,16 @@ typedef struct cmadx_newton {
 typedef struct cmadx_mp_buffers {
     int64_t n;              /* points                                          */
     int64_t ld;             /* leading dimension (elements), >= n              */
-    int32_t strain_comps;   /* 6: symmetric strain (grad_u := strain);
-                               9: grad_u row-major [k*3+j] = du_k/dx_j        */
-    int32_t reserved;
+    int32_t strain_comps;   /* FULL_3D: 6 = symmetric strain (grad_u := strain),
+                               9 = grad_u row-major [k*3+j] = du_k/dx_j;
+                               PLANE_STRESS: 3 = (e_xx, e_xy, e_yy), 4 = 2x2 grad_u row-major;
+                               UNIAXIAL_STRESS: 1 = axial strain                 */
+    int32_t def_type;       /* CMADX_DEF_* (cmad/models/deformation_types.py): 0 FULL_3D
+                               (n_xi 7), PLANE_STRESS (n_xi 8: + out-of-plane stretch),
+                               UNIAXIAL_STRESS (n_xi 9: + two off-axis stretches).  For the
+                               latter two the derivative outputs are w.r.t. the prescribed
+                               symmetric components only: dsig_deps [6*ns], dxi_deps
+                               [n_xi*ns] with ns = 3 (xx, xy, yy) or 1                  */
     const double* xi_prev;  /* [n_xi][ld]                                      */
     const double* strain;   /* [strain_comps][ld]                              */
     const double* xi_init;  /* [n_xi][ld] or NULL: starting iterate (NULL =>
@@ -184,7 +196,10 @@ typedef struct cmadx_mp_history {
     int64_t n;              /* points                                          */
     int64_t ld;             /* leading dimension of every slab row (>= n)      */
     int32_t nsteps;         /* N load steps                                    */
-    int32_t strain_comps;   /* 6 | 9 as in cmadx_mp_buffers_t                  */
+    int32_t strain_comps;   /* as in cmadx_mp_buffers_t; it also selects the deformation type:
+                               6 | 9 FULL_3D (n_xi 7), 3 | 4 PLANE_STRESS (n_xi 8),
+                               1 UNIAXIAL_STRESS (n_xi 9); xi_hist slabs have n_xi rows,
+                               slab 0 holds the initial state (stretches = 1)        */
     const double* strain;   /* [N+1][strain_comps][ld]                         */
     const double* data;     /* [N+1][9][ld] cauchy data, 3x3 row-major         */
     double weight[9];       /* Calibration weight, 3x3 row-major, time-constant*/

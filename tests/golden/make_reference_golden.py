@@ -308,6 +308,102 @@ def _fe_job(job):
     return out
 
 
+
+# --------------------------------------------------------------------------- #
+#  E. PLANE_STRESS / UNIAXIAL_STRESS deformation types (n_xi = 8 / 9)          #
+# --------------------------------------------------------------------------- #
+def deftype_F(def_type_name, nsteps=40):
+    """Two-leg histories: plane stress as tests/objectives/test_J2_fd_checks.py:266-289
+    (e_xx ramps to 0.02 then holds while e_yy ramps) plus a small in-plane shear;
+    uniaxial stress: axial ramp to 0.02, partial unloading, reloading to 0.03."""
+    h = nsteps // 2
+    if def_type_name == "PLANE_STRESS":
+        exx = np.r_[0.0, np.linspace(0.02 / h, 0.02, h), np.full(h, 0.02)]
+        eyy = np.r_[0.0, np.zeros(h), np.linspace(0.02 / h, 0.02, h)]
+        F = np.repeat(np.eye(2)[:, :, None], nsteps + 1, axis=2)
+        F[0, 0] += exx; F[1, 1] += eyy
+        F[0, 1] += 0.15 * exx; F[1, 0] += 0.05 * eyy          # unsymmetric grad_u: only sym part matters
+        return F
+    e = np.r_[0.0, np.linspace(0.02 / h, 0.02, h), np.linspace(0.02, 0.016, h // 2),
+              np.linspace(0.016, 0.03, nsteps - h - h // 2)]
+    return (1.0 + e).reshape(1, 1, nsteps + 1)
+
+
+def _deftype_job(job):
+    from cmad.models.deformation_types import DefType
+    kind, dt_name = job
+    dt = DefType[dt_name]
+    values = material(kind)
+    P = parameters(values)
+    model = SmallElasticPlastic(P, def_type=dt)
+    nxi = model.num_dofs
+    F = deftype_F(dt_name)
+    N = F.shape[2] - 1
+    nd = F.shape[0]
+    solve = make_newton_solve(model._residual)
+    rec = {k: [] for k in ("xi", "sigma", "iters", "cnorm", "dC_dxi", "dC_dxi_prev", "dC_dp",
+                           "traced_xi", "traced_iters", "dxi_dgradu", "dsig_dgradu")}
+    model.set_xi_to_init_vals()
+    for step in range(1, N + 1):
+        U, Up = mp_U_from_F(F[:, :, step]), mp_U_from_F(F[:, :, step - 1])
+        model.gather_global(U, Up)
+        xp = [np.asarray(b).copy() for b in model.xi_prev()]
+        # traced solver + IFT tangent from the same previous state
+        xt = solve(xp, P.values, U, Up)
+        rec["traced_iters"].append(int(_core.WHILE_LOG[-1][1][0]))
+        rec["traced_xi"].append(np.concatenate([np.asarray(b) for b in xt]))
+
+        def state_and_stress(U_):
+            x = solve(xp, P.values, U_, Up)
+            return jax.numpy.concatenate([jax.numpy.ravel(b) for b in x]), model.cauchy(x, xp, P.values, U_, Up)
+        dx_dU, ds_dU = jax.jacfwd(state_and_stress)(U)
+        rec["dxi_dgradu"].append(np.asarray(dx_dU.grad_fields["u"]).reshape(nxi, nd * nd))
+        rec["dsig_dgradu"].append(np.asarray(ds_dU.grad_fields["u"]).reshape(9, nd * nd))
+        # imperative solver on the Model object
+        ii, cn = newton_solve(model)
+        rec["iters"].append(ii); rec["cnorm"].append(cn)
+        xi = [np.asarray(b).copy() for b in model.xi()]
+        rec["xi"].append(np.concatenate(xi))
+        model.seed_none(); model.evaluate_cauchy()
+        rec["sigma"].append(vec6(model.Sigma()))
+        jac = model._jacobian
+        rec["dC_dxi"].append(np.hstack([np.asarray(b) for b in jac[DerivType.DXI](xi, xp, P.values, U, Up)]))
+        rec["dC_dxi_prev"].append(np.hstack([np.asarray(b) for b in jac[DerivType.DXI_PREV](xi, xp, P.values, U, Up)]))
+        dcdp = jac[DerivType.DPARAMS](xi, xp, P.values, U, Up)
+        rec["dC_dp"].append(np.hstack([np.asarray(x).reshape(nxi, -1) for x in jax.tree_util.tree_leaves(dcdp)]))
+        model.advance_xi()
+    out = {k: np.array(v) for k, v in rec.items()}
+    out["F"] = F
+    # objectives (KA5): Calibration on the in-plane / axial stresses, offset parameters
+    for scaled in (True, False):
+        vals, act, tr = objective_trees(kind, scaled)
+        Po = Parameters(vals, act, tr)
+        mo_ = SmallElasticPlastic(Po, def_type=dt)
+        data = np.zeros((3, 3, N + 1))
+        mo_.set_xi_to_init_vals()
+        for step in range(1, N + 1):
+            mo_.gather_global(mp_U_from_F(F[:, :, step]), mp_U_from_F(F[:, :, step - 1]))
+            newton_solve(mo_)
+            mo_.seed_none(); mo_.evaluate_cauchy()
+            data[:, :, step] = mo_.Sigma().copy()
+            mo_.advance_xi()
+        w = np.zeros((3, 3)); w[0, 0] = 1.0
+        if dt_name == "PLANE_STRESS":
+            w[1, 1] = 1.0; w[0, 1] = w[1, 0] = 0.5
+        qoi = Calibration(mo_, data, w)
+        offset = 1.1 * Po.flat_active_values(False)
+        Po.set_active_values_from_flat(offset, False)
+        x = Po.flat_active_values(True)
+        tag = "scaled" if scaled else "native"
+        for name, ctor in (("adjoint", MPAdjointObjective), ("direct", MPDirectObjective)):
+            Po.set_active_values_from_flat(offset, False)
+            J, g = ctor(qoi, F).evaluate(x)
+            out[f"obj_{tag}.J_{name}"], out[f"obj_{tag}.grad_{name}"] = float(J), np.asarray(g, float)
+        out[f"obj_{tag}.data"], out[f"obj_{tag}.weight"], out[f"obj_{tag}.x_canonical"] = data, w, x
+        out[f"obj_{tag}.active_native"], out[f"obj_{tag}.active_idx"] = offset, np.asarray(Po.active_idx)
+    return out
+
+
 # --------------------------------------------------------------------------- #
 def main():
     ap = argparse.ArgumentParser()
@@ -378,6 +474,16 @@ def main():
                 out[f"{nm}.{k}"] = v
             print("fe", nm, "alpha max", r["xi"][..., 6].max())
         np.savez_compressed(os.path.join(HERE, "ref_fe_elements.npz"), **out)
+
+    if only is None or "deftypes" in only:
+        jobs = [(kind, dt) for dt in ("PLANE_STRESS", "UNIAXIAL_STRESS") for kind in ("J2", "hill", "hosford")]
+        out = {}
+        for (kind, dt), r in zip(jobs, pool.map(_deftype_job, jobs, chunksize=1)):
+            for k, v in r.items():
+                out[f"{kind}.{dt}.{k}"] = v
+            print("deftypes", kind, dt, "iters", np.bincount(r["iters"]), "traced", np.bincount(r["traced_iters"]),
+                  "alpha", r["xi"][-1, 6], "J", r["obj_scaled.J_adjoint"])
+        np.savez_compressed(os.path.join(HERE, "ref_def_types.npz"), **out)
 
 
 if __name__ == "__main__":
