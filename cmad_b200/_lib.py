@@ -15,12 +15,12 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "lib", "libcmad_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
-SOURCES = ["api.cu", "mp_update.cu", "mp_update_j2.cu", "mp_update_dt.cu", "elastic_update.cu", "mp_sens.cu", "mp_sens_dt.cu",
+SOURCES = ["api.cu", "mp_update.cu", "mp_update_j2.cu", "mp_update_dt.cu", "mp_update_rate.cu", "elastic_update.cu", "mp_sens.cu", "mp_sens_dt.cu",
            "fe_block.cu", "fe_tet4.cu", "fe_hex8.cu", "fe_mixed.cu", "fe_post.cu", "fe_vjp.cu", "fe_scatter.cu"]
 
 # ---- enums (mirror include/cmad_b200.h) ---------------------------------
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(5)
-MODEL_SMALL_ELASTIC_PLASTIC, MODEL_ELASTIC = 0, 1
+MODEL_SMALL_ELASTIC_PLASTIC, MODEL_ELASTIC, MODEL_SMALL_RATE_ELASTIC_PLASTIC = 0, 1, 2
 YIELD_J2, YIELD_HILL, YIELD_HOSFORD = 0, 1, 2
 DEF_FULL_3D, DEF_PLANE_STRESS, DEF_UNIAXIAL_STRESS = 0, 1, 2
 ELASTIC_PAIRS = [("E", "nu"), ("E", "mu"), ("E", "kappa"), ("E", "lambda"), ("kappa", "mu"),

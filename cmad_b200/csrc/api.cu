@@ -101,7 +101,8 @@ int lame_pair(int pair, double e0, double e1, D2& lam, D2& mu) {
 
 int make_dev_mat(const cmadx_material_t* mat, DevMat* o) {
     if (!mat || !o) return CMADX_EINVAL;
-    if (mat->model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC && mat->model != CMADX_MODEL_ELASTIC)
+    if (mat->model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC && mat->model != CMADX_MODEL_ELASTIC &&
+        mat->model != CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC)
         return CMADX_EINVAL;
     D2 lam, mu;
     if (int rc = lame_pair(mat->elastic_pair, mat->elastic[0], mat->elastic[1], lam, mu)) return rc;
@@ -111,7 +112,7 @@ int make_dev_mat(const cmadx_material_t* mat, DevMat* o) {
     o->inv_two_mu = 1.0 / o->two_mu;
     o->dlam[0] = lam.a; o->dlam[1] = lam.b; o->dmu[0] = mu.a; o->dmu[1] = mu.b;
     o->model = mat->model;
-    if (mat->model == CMADX_MODEL_SMALL_ELASTIC_PLASTIC) {
+    if (mat->model == CMADX_MODEL_SMALL_ELASTIC_PLASTIC || mat->model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC) {
         if (mat->yield < CMADX_YIELD_J2 || mat->yield > CMADX_YIELD_HOSFORD) return CMADX_EINVAL;
         if (mat->hardening_mask & ~(CMADX_HARD_VOCE | CMADX_HARD_LINEAR)) return CMADX_EINVAL;
         o->yield = mat->yield;
@@ -130,7 +131,7 @@ int make_dev_mat(const cmadx_material_t* mat, DevMat* o) {
         o->Q[i] = mat->Q[i];
         if (mat->Q[i] != ((i % 4 == 0) ? 1.0 : 0.0)) ident = false;
     }
-    o->rot = (mat->model == CMADX_MODEL_SMALL_ELASTIC_PLASTIC && !ident) ? 1 : 0;
+    o->rot = (mat->model != CMADX_MODEL_ELASTIC && !ident) ? 1 : 0;
     return CMADX_OK;
 }
 
@@ -163,6 +164,9 @@ static int build_args(const cmadx_material_t* mat, const cmadx_newton_t* nw,
     }
     A->n_active = n_active;
     if (b->n < 0 || b->ld < b->n) return CMADX_EINVAL;
+    if (A->m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC &&
+        (A->m.rot || b->def_type != CMADX_DEF_FULL_3D))
+        return CMADX_EUNSUPPORTED;
     if (b->def_type == CMADX_DEF_FULL_3D) {
         if (b->strain_comps != 6 && b->strain_comps != 9) return CMADX_EINVAL;
     } else if (b->def_type == CMADX_DEF_PLANE_STRESS || b->def_type == CMADX_DEF_UNIAXIAL_STRESS) {
@@ -213,6 +217,8 @@ static int launch(const MpArgs& A, cudaStream_t s) {
         e = launch_mp_update_dt(A, s);
     } else if (A.m.model == CMADX_MODEL_ELASTIC) {
         e = launch_mp_update_elastic(A, s);
+    } else if (A.m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC) {
+        e = launch_mp_update_rate(A, s);
     } else if (A.m.yield == CMADX_YIELD_J2 && !A.m.rot && !A.b.xi_init &&
                !(A.nw.flags & CMADX_NEWTON_F_GENERIC) && A.b.n < (int64_t)0x7fffffff) {
         // J2 radial-return kernel, then the generic kernel over whatever it handed back

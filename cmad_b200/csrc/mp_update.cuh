@@ -29,6 +29,8 @@ cudaError_t launch_mp_update_j2(const MpArgs& A, cudaStream_t stream);
 // generic kernel over the bail list (small persistent grid)
 cudaError_t launch_mp_update_sep_list(const MpArgs& A, cudaStream_t stream);
 cudaError_t launch_mp_update_elastic(const MpArgs& A, cudaStream_t stream);
+// SmallRateElasticPlastic (rate form; `strain` = strain increment)
+cudaError_t launch_mp_update_rate(const MpArgs& A, cudaStream_t stream);
 // PLANE_STRESS / UNIAXIAL_STRESS deformation types (n_xi = 8 / 9)
 cudaError_t launch_mp_update_dt(const MpArgs& A, cudaStream_t stream);
 

@@ -83,7 +83,8 @@ def material_from_values(values: dict, model: str = "small_elastic_plastic",
     """Build ``cmadx_material_t`` from a parameter ``values`` pytree."""
     m = L.Material()
     m.model = {"small_elastic_plastic": L.MODEL_SMALL_ELASTIC_PLASTIC,
-               "elastic": L.MODEL_ELASTIC}[model]
+               "elastic": L.MODEL_ELASTIC,
+               "small_rate_elastic_plastic": L.MODEL_SMALL_RATE_ELASTIC_PLASTIC}[model]
     el = values["elastic"]
     pair = tuple(sorted(el))
     if pair not in L.ELASTIC_PAIRS:
@@ -94,7 +95,7 @@ def material_from_values(values: dict, model: str = "small_elastic_plastic",
     for i in range(9):
         m.Q[i] = float(Q[i])
     m.yield_tol = float(yield_tol)
-    if model == "small_elastic_plastic":
+    if model in ("small_elastic_plastic", "small_rate_elastic_plastic"):
         pl = values["plastic"]
         kind = next(iter(pl["effective stress"]))        # small_elastic_plastic.py:193-198
         if kind not in _YIELD:

@@ -38,7 +38,11 @@ enum {
 };
 
 /* ---- models: cmad/models/small_elastic_plastic.py:95, cmad/models/elastic.py:29 */
-enum { CMADX_MODEL_SMALL_ELASTIC_PLASTIC = 0, CMADX_MODEL_ELASTIC = 1 };
+/* CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC (cmad/models/small_rate_elastic_plastic.py): state =
+ * [cauchy(6), alpha]; the `strain` rows of a batch carry the strain INCREMENT eps - eps_prev
+ * (the reference forms it from U and U_prev); K1 only, FULL_3D, identity material axes. */
+enum { CMADX_MODEL_SMALL_ELASTIC_PLASTIC = 0, CMADX_MODEL_ELASTIC = 1,
+       CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC = 2 };
 /* ---- effective stress: cmad/models/effective_stress.py:16-27 */
 enum { CMADX_YIELD_J2 = 0, CMADX_YIELD_HILL = 1, CMADX_YIELD_HOSFORD = 2 };
 /* ---- which two elastic constants are given (cmad/models/elastic_constants.py:54-104),

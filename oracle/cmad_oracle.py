@@ -346,7 +346,7 @@ class ModelSpec:
     effective_stress: str | None = None      # None -> first key of the params subtree
 
     def block_sizes(self) -> list[int]:
-        if self.kind == "small_elastic_plastic":       # small_elastic_plastic.py:126-180
+        if self.kind in ("small_elastic_plastic", "small_rate_elastic_plastic"):   # small_elastic_plastic.py:126-180
             b = [6, 1]
         elif self.kind == "elastic":                   # elastic.py:57-97
             b = [6]
@@ -369,7 +369,7 @@ class ModelSpec:
         tensor/scalar state, ones for the stretches."""
         b = self.block_sizes()
         x = np.zeros(sum(b))
-        n0 = 7 if self.kind == "small_elastic_plastic" else 6
+        n0 = 6 if self.kind == "elastic" else 7
         x[n0:] = 1.0
         return x
 
@@ -494,12 +494,44 @@ def elastic_cauchy(x, x_prev, params, grad_u, grad_u_prev, spec: ModelSpec):
     return sym_tensor_from_vector(x[0:6])
 
 
+def rate_residual(x, x_prev, params, grad_u, grad_u_prev, spec: ModelSpec):
+    """small_rate_elastic_plastic.py:250-346 (FULL_3D): state = [cauchy(6), alpha]; the trial
+    stress increment comes from eps(U) - eps(U_prev) (:34-77), the yield function and its
+    normal are evaluated at the state's own stress (:80-100)."""
+    assert spec.def_type == FULL_3D
+    cauchy = sym_tensor_from_vector(x[0:6])
+    cauchy_prev = sym_tensor_from_vector(x_prev[0:6])
+    alpha, alpha_prev = x[6], x_prev[6]
+    Q = params["rotation matrix"]
+    de = 0.5 * (grad_u + grad_u.T) - 0.5 * (grad_u_prev + grad_u_prev.T)
+    trial = isotropic_linear_elastic_stress(Q.T @ de @ Q, params)
+    dgamma = alpha - alpha_prev
+    sc = two_mu_scale_factor(params)
+    pl = params["plastic"]
+    phi_fun = effective_stress_fun(_sep_es_kind(params, spec))
+    f = (phi_fun(cauchy, pl) - (pl["flow stress"]["initial yield"]["Y"]
+                                + combined_hardening(alpha, pl["flow stress"]["hardening"]))) / sc
+    n = grad(phi_fun)(cauchy, pl)
+    Ce = torch.cat([vector_from_sym_tensor(cauchy - cauchy_prev - trial) / sc, dgamma.reshape(1)])
+    dc = trial - isotropic_linear_elastic_stress(dgamma * n, params)
+    Cp = torch.cat([vector_from_sym_tensor(cauchy - cauchy_prev - dc) / sc, f.reshape(1)])
+    return torch.where(sep_is_plastic(f, spec.yield_tol), Cp, Ce)
+
+
+def rate_cauchy(x, x_prev, params, grad_u, grad_u_prev, spec: ModelSpec):
+    """small_rate_elastic_plastic.py:351-359."""
+    Q = params["rotation matrix"]
+    return Q @ sym_tensor_from_vector(x[0:6]) @ Q.T
+
+
 def residual_fun(spec: ModelSpec):
-    return sep_residual if spec.kind == "small_elastic_plastic" else elastic_residual
+    return {"small_elastic_plastic": sep_residual, "elastic": elastic_residual,
+            "small_rate_elastic_plastic": rate_residual}[spec.kind]
 
 
 def cauchy_fun(spec: ModelSpec):
-    return sep_cauchy if spec.kind == "small_elastic_plastic" else elastic_cauchy
+    return {"small_elastic_plastic": sep_cauchy, "elastic": elastic_cauchy,
+            "small_rate_elastic_plastic": rate_cauchy}[spec.kind]
 
 
 # --------------------------------------------------------------------------

@@ -404,6 +404,50 @@ def _deftype_job(job):
     return out
 
 
+
+# --------------------------------------------------------------------------- #
+#  F. SmallRateElasticPlastic (rate form), FULL_3D                              #
+# --------------------------------------------------------------------------- #
+def _rate_job(job):
+    from cmad.models.small_rate_elastic_plastic import SmallRateElasticPlastic
+    kind, = job
+    values = material(kind)
+    P = parameters(values)
+    model = SmallRateElasticPlastic(P)
+    F = two_leg_F(7, 30, diag_only=kind == "hosford")
+    N = F.shape[2] - 1
+    solve = make_newton_solve(model._residual)
+    rec = {k: [] for k in ("xi", "sigma", "iters", "cnorm", "dC_dxi", "dC_dxi_prev", "dC_dp",
+                           "traced_xi", "traced_iters", "dxi_dgradu")}
+    model.set_xi_to_init_vals()
+    with np.errstate(all="ignore"):
+        for step in range(1, N + 1):
+            U, Up = mp_U_from_F(F[:, :, step]), mp_U_from_F(F[:, :, step - 1])
+            model.gather_global(U, Up)
+            xp = [np.asarray(b).copy() for b in model.xi_prev()]
+            xt = solve(xp, P.values, U, Up)
+            rec["traced_iters"].append(int(_core.WHILE_LOG[-1][1][0]))
+            rec["traced_xi"].append(np.concatenate([np.asarray(b) for b in xt]))
+            dx_dU = jax.jacfwd(lambda U_: jax.numpy.concatenate(
+                [jax.numpy.ravel(b) for b in solve(xp, P.values, U_, Up)]))(U)
+            rec["dxi_dgradu"].append(np.asarray(dx_dU.grad_fields["u"]).reshape(7, 9))
+            ii, cn = newton_solve(model)
+            rec["iters"].append(ii); rec["cnorm"].append(cn)
+            xi = [np.asarray(b).copy() for b in model.xi()]
+            rec["xi"].append(np.concatenate(xi))
+            model.seed_none(); model.evaluate_cauchy()
+            rec["sigma"].append(vec6(model.Sigma()))
+            jac = model._jacobian
+            rec["dC_dxi"].append(np.hstack([np.asarray(b) for b in jac[DerivType.DXI](xi, xp, P.values, U, Up)]))
+            rec["dC_dxi_prev"].append(np.hstack([np.asarray(b) for b in jac[DerivType.DXI_PREV](xi, xp, P.values, U, Up)]))
+            dcdp = jac[DerivType.DPARAMS](xi, xp, P.values, U, Up)
+            rec["dC_dp"].append(np.hstack([np.asarray(x).reshape(7, -1) for x in jax.tree_util.tree_leaves(dcdp)]))
+            model.advance_xi()
+    out = {k: np.array(v) for k, v in rec.items()}
+    out["F"] = F
+    return out
+
+
 # --------------------------------------------------------------------------- #
 def main():
     ap = argparse.ArgumentParser()
@@ -484,6 +528,16 @@ def main():
             print("deftypes", kind, dt, "iters", np.bincount(r["iters"]), "traced", np.bincount(r["traced_iters"]),
                   "alpha", r["xi"][-1, 6], "J", r["obj_scaled.J_adjoint"])
         np.savez_compressed(os.path.join(HERE, "ref_def_types.npz"), **out)
+
+    if only is None or "rate" in only:
+        jobs = [(k,) for k in ("J2", "hill", "hosford")]
+        out = {}
+        for (kind,), r in zip(jobs, pool.map(_rate_job, jobs, chunksize=1)):
+            for k, v in r.items():
+                out[f"{kind}.{k}"] = v
+            print("rate", kind, "iters", np.bincount(r["iters"]), "traced", np.bincount(r["traced_iters"]),
+                  "alpha", r["xi"][-1, 6])
+        np.savez_compressed(os.path.join(HERE, "ref_rate_model.npz"), **out)
 
 
 if __name__ == "__main__":
