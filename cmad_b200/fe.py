@@ -36,6 +36,22 @@ def fe_newton_settings(**kw) -> NewtonSettings:
     return NewtonSettings(mode="traced", **d)
 
 
+def closed_form_elastic_material(values: dict) -> L.Material:
+    """Material for a CLOSED_FORM block of the ``Elastic`` model with the isotropic linear
+    stress (cmad/models/elastic.py, elastic_stress.py:24-42; the mode the deck builder picks for
+    ``supports_closed_form_cauchy`` models, e.g. examples/mixed_elastic.yaml): the element
+    kernels run their elastic branch only - a J2 surface with an infinite yield stress never
+    yields, so ``sigma = Cel eps``, ``D = Cel`` and the local state stays at its zero initial
+    value.  Pass ``xi_prev = zeros((n_e, n_ip, 7))``; the returned ``xi`` is zero as well (the
+    reference's CLOSED_FORM blocks carry no xi).  Works for the displacement and the mixed u-p
+    formulation (``dev_cauchy_closed_form`` / ``hydro_cauchy_closed_form``)."""
+    from .material import material_from_values
+    v = {"rotation matrix": np.eye(3), "elastic": dict(values["elastic"]),
+         "plastic": {"effective stress": {"J2": 0.0},
+                     "flow stress": {"initial yield": {"Y": float("inf")}, "hardening": {}}}}
+    return material_from_values(v)
+
+
 class SegmentPlan:
     """Deterministic segment-sum plan (K5): ``out[s] = sum vals[i] for seg[i] == s``
     in increasing ``i``.  Built once per mesh from the reference's scatter maps

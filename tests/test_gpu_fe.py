@@ -436,3 +436,62 @@ def test_device_embedded_bcs_match_reference_restatement(cuda_device):
     assert [l.iters for l in ld] == [l.iters for l in lh]
     assert np.abs(Ud - Uh).max() < 1e-12 * np.abs(Uh).max()
     assert np.abs(xid.cpu().numpy() - xih.cpu().numpy()).max() < 1e-12
+
+
+@pytest.mark.parametrize("family", ["tet4", "hex8"])
+@pytest.mark.parametrize("mixed", [False, True])
+def test_closed_form_elastic_blocks(cuda_device, family, mixed):
+    """CLOSED_FORM blocks of the `Elastic` model (kappa, mu given: examples/mixed_elastic.yaml;
+    KA4's material kappa = 100, mu = 50): R_e and K_e from the element kernels' elastic branch vs
+    the closed-form stress kappa tr(eps) I + 2 mu dev(eps) (elastic_stress.py:24-42) assembled
+    with NumPy; K_e constant = B^T Cel B; the u-p variant against the mixed oracle."""
+    values = {"elastic": {"kappa": 100.0, "mu": 50.0}}
+    nodes, conn = _mesh(family, (2, 2, 1), distort=0.08, seed=4)
+    arr_h = fe_mesh.block_arrays(nodes, conn, mixed=mixed)
+    arr = arr_h.to(cuda_device)
+    rng = np.random.default_rng(3)
+    U = 0.05 * rng.standard_normal(nodes.shape[0] * 3)
+    if mixed:
+        U = np.concatenate([U, 3.0 * rng.standard_normal(nodes.shape[0])])
+    mat = fe.closed_form_elastic_material(values)
+    xi0 = torch.zeros((arr.n_elems, arr.n_ip, 7), dtype=torch.float64, device=cuda_device)
+    Ud = torch.from_numpy(U).to(cuda_device)
+    eq = arr_h.elem_eq.numpy()
+    gN, det, w = arr_h.grad_N.numpy(), arr_h.det.numpy(), arr_h.quad_w.numpy()
+    n_e, n_ip, n_b, _ = gN.shape
+    U_e = U[eq].reshape(n_e, n_b, 3)
+    gu = np.einsum("eak,epaj->epkj", U_e, gN)
+    eps = 0.5 * (gu + np.swapaxes(gu, 2, 3))
+    tr = np.trace(eps, axis1=2, axis2=3)
+    I3 = np.eye(3)
+    sig = 100.0 * tr[..., None, None] * I3 + 2 * 50.0 * (eps - tr[..., None, None] / 3.0 * I3)
+    wdv = det * w[None, :]
+    if not mixed:
+        o = fe.fe_block_launch(mat, fe.fe_newton_settings(), arr, Ud, xi0, ("xi", "R_elem", "K_elem", "iters"))
+        torch.cuda.synchronize()
+        R_ref = np.einsum("epaj,epji,ep->eai", gN, sig, wdv).reshape(n_e, -1)
+        assert rel_err(o["R_elem"].cpu().numpy(), R_ref) < 1e-12
+        assert float(o["xi"].abs().max()) == 0.0 and int(o["iters"].max()) == 0
+        lam = 100.0 - 2 * 50.0 / 3.0
+        Cel = lam * np.einsum("ji,kl->jikl", I3, I3) + 50.0 * (np.einsum("jk,il->jikl", I3, I3) + np.einsum("jl,ik->jikl", I3, I3))
+        K_ref = np.einsum("epaj,jikl,epbl,ep->eaibk", gN, Cel, gN, wdv).reshape(n_e, 3 * n_b, 3 * n_b)
+        assert rel_err(o["K_elem"].cpu().numpy(), K_ref) < 1e-12
+    else:
+        R, vals, xi = fe.assemble_element_block_mixed(mat, fe.fe_newton_settings(), arr, Ud, xi0,
+                                                      r_plan=fe.mixed_r_plan(arr))
+        torch.cuda.synchronize()
+        prob = oc.describe({"rotation matrix": np.eye(3), "elastic": values["elastic"],
+                            "plastic": {"effective stress": {"J2": 0.0},
+                                        "flow stress": {"initial yield": {"Y": 1e300}, "hardening": {}}}},
+                           None, newton_mode="traced", strain_comps=9, **NEWTON)
+        ref = fe_oracle.assemble_block_mixed(prob, eq, arr_h.elem_eq_p.numpy(), U, np.zeros((n_e, n_ip, 7)), gN,
+                                             arr_h.N.numpy(), det, w, arr_h.h.numpy())
+        assert rel_err(R.cpu().numpy(), ref["R"]) < 1e-12
+        v_ref = np.concatenate([ref[k].reshape(-1) for k in ("K_uu", "K_up", "K_pu", "K_pp")])
+        assert rel_err(vals.cpu().numpy(), v_ref) < 1e-12
+        # momentum residual of the closed form: dev(sigma) - p I
+        p_ip = np.einsum("pa,ea->ep", arr_h.N.numpy(), U[arr_h.elem_eq_p.numpy()])
+        sdev = sig - np.trace(sig, axis1=2, axis2=3)[..., None, None] / 3.0 * I3 - p_ip[..., None, None] * I3
+        R_u = np.zeros(U.size); np.add.at(R_u, eq.reshape(-1), np.einsum("epaj,epji,ep->eai", gN, sdev, wdv).reshape(-1))
+        n_u = 3 * nodes.shape[0]
+        assert rel_err(R.cpu().numpy()[:n_u], R_u[:n_u]) < 1e-12
