@@ -32,9 +32,9 @@ N_POINTS = 1 << 24
 HISTORY_STEPS = 100
 SEED = 22
 ALG_BYTES_PER_UPDATE = 784      # in 56+48, out 56+48+288+280+4+4
-# ncu --set full capture of mp_update_j2_kernel (profiles/r1_k1_j2_raw.txt): dram__bytes_read
-# 436.27 MB + dram__bytes_write 2792.47 MB for a 4 194 304-point launch
-NCU_DRAM_BYTES_PER_UPDATE = (436.268288e6 + 2792.465e6) / 4194304
+# ncu --set full capture of mp_update_j2_kernel at the bench size (profiles/r1_final_k1_j2_raw.txt):
+# dram__bytes_read 1.745326 GB + dram__bytes_write 11.350847 GB for one 16 777 216-point launch
+NCU_DRAM_BYTES_PER_UPDATE = (1.745326e9 + 11.350847e9) / 16777216
 OUTPUTS = ("xi", "sigma", "dsig_deps", "dC_dp", "iters", "flags")
 METRIC = "fp64 material-point updates/s (+tangent +dC/dp), J2+Voce return mapping"
 

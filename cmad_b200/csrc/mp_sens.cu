@@ -52,7 +52,7 @@ CMADX_DEV double qoi_terms(const double (&w)[9], const double (&sig)[6], const d
 // sets such as [E, nu, D, S, Y]; 16 = CMADX_MAX_ACTIVE), which sizes the register-resident
 // gradient accumulators.
 template <int YK, bool ADJOINT, int NA_MAX>
-__global__ void __launch_bounds__(SENS_BLOCK, (YK == CMADX_YIELD_J2 && NA_MAX <= 6 && ADJOINT) ? 4 : 1)
+__global__ void __launch_bounds__(SENS_BLOCK, (YK == CMADX_YIELD_J2 && NA_MAX <= 6) ? 4 : 1)
 mp_sens_kernel(const __grid_constant__ SensArgs A) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < A.h.n;
