@@ -253,9 +253,9 @@ def run_b200(args):
                 "frac": achieved / hbm_peak, "traffic": NCU_DRAM_BYTES_PER_UPDATE * n, "peak_source": peak_src,
                 "kernel": "mp_update_j2_kernel (+ mp_update_list_kernel fallback, ~0.5% of the step)",
                 "alg_bytes_per_update": ALG_BYTES_PER_UPDATE, "avg_launch_ms": avg_kernel_ms,
-                "traffic_note": "bytes per launch of this size, from the ncu --set full capture of a 2^22-point "
-                                "launch (769.8 B/update measured vs 784 algorithmic: no re-reads), "
-                                "profiles/r1_k1_j2_raw.txt",
+                "traffic_note": "bytes per launch of this size, from the ncu --set full capture of a 2^24-point "
+                                "launch (780.6 B/update measured vs 784 algorithmic: no re-reads), "
+                                "profiles/r1_final_k1_j2_raw.txt",
                 "fp64": {"peak_tflops_measured": fp64_peak,
                          "note": "DFMA micro-benchmark (cmadx_fp64_peak); FP64 pipe ~28% busy in the "
                                  "J2 kernel (ncu), i.e. HBM binds"}}
