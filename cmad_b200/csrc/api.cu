@@ -143,6 +143,9 @@ int make_dev_newton(const cmadx_newton_t* nw, DevNewton* o) {
     o->mode = nw->mode; o->max_iters = nw->max_iters; o->ls_max = nw->ls_max_evals; o->flags = nw->flags;
     o->abs_tol = nw->abs_tol; o->rel_tol = nw->rel_tol;
     o->c1 = nw->ls_c1; o->bmin = nw->ls_bmin; o->bmax = nw->ls_bmax;
+    const int k = (nw->flags & CMADX_NEWTON_DEFER_MASK) >> CMADX_NEWTON_DEFER_SHIFT;
+    o->defer_request = (k == 0) ? 2 : (k == 255 ? 0 : k);
+    o->defer_after = 0;
     return CMADX_OK;
 }
 
@@ -190,22 +193,35 @@ struct BailScratch {
     int device;
     cudaStream_t stream;
     unsigned* count;   // count, then the index list
+    unsigned cap;      // list capacity (entries)
 };
 std::mutex g_bail_mutex;
 std::vector<BailScratch> g_bail;
 
-int get_bail_scratch(cudaStream_t s, BailScratch* out) {
+// scratch of a (device, stream) with room for at least `min_cap` list entries; grows on demand
+// (cudaFree synchronises the device, so a list still in use by earlier launches is safe)
+int get_bail_scratch(cudaStream_t s, BailScratch* out, unsigned min_cap = BAIL_CAP) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return cuda_fail(e);
     std::lock_guard<std::mutex> lock(g_bail_mutex);
+    BailScratch* slot = nullptr;
     for (auto& b : g_bail)
-        if (b.device == dev && b.stream == s) { *out = b; return CMADX_OK; }
-    BailScratch b{dev, s, nullptr};
-    e = cudaMalloc(&b.count, sizeof(unsigned) * (size_t)(BAIL_CAP + 64));
+        if (b.device == dev && b.stream == s) slot = &b;
+    if (slot && slot->cap >= min_cap) { *out = *slot; return CMADX_OK; }
+    unsigned cap = BAIL_CAP;
+    while (cap < min_cap) cap <<= 1;
+    unsigned* p = nullptr;
+    e = cudaMalloc(&p, sizeof(unsigned) * ((size_t)cap + 64));
     if (e != cudaSuccess) return (e == cudaErrorMemoryAllocation) ? CMADX_ENOMEM : cuda_fail(e);
-    g_bail.push_back(b);
-    *out = b;
+    if (slot) {
+        cudaFree(slot->count);
+        slot->count = p; slot->cap = cap;
+        *out = *slot;
+    } else {
+        g_bail.push_back(BailScratch{dev, s, p, cap});
+        *out = g_bail.back();
+    }
     return CMADX_OK;
 }
 }  // namespace
@@ -231,6 +247,22 @@ static int launch(const MpArgs& A, cudaStream_t s) {
         e = cudaMemsetAsync(bs.count, 0, sizeof(unsigned), s);
         if (e != cudaSuccess) return cuda_fail(e);
         e = launch_mp_update_j2(B, s);
+        if (e != cudaSuccess) return cuda_fail(e);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = launch_mp_update_sep_list(B, s);
+    } else if (A.nw.defer_request > 0 && A.nw.max_iters > A.nw.defer_request &&
+               A.b.n < (int64_t)0x7fffffff) {
+        // generic Newton in two passes: points that need more than defer_request updates are
+        // re-solved by a second launch made of such points only (warp-divergence control)
+        BailScratch bs;
+        if (int rc = get_bail_scratch(s, &bs, (unsigned)A.b.n)) return rc;
+        MpArgs B = A;
+        B.bail_count = bs.count;
+        B.bail_list = reinterpret_cast<int*>(bs.count + 64);
+        B.bail_cap = bs.cap;
+        e = cudaMemsetAsync(bs.count, 0, sizeof(unsigned), s);
+        if (e != cudaSuccess) return cuda_fail(e);
+        e = launch_mp_update_sep(B, s);
         if (e != cudaSuccess) return cuda_fail(e);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         e = launch_mp_update_sep_list(B, s);

@@ -39,7 +39,7 @@ CMADX_DEV void rot_maps(const double* Q, double (&T)[6][6], double (&S)[6][6]) {
 // REDUCED: Hosford through the 4-unknown HosfordPoint (see point_solver.cuh); needs
 // the starting iterate to be xi_prev (no xi_init)
 template <int YK, bool ROT, bool REDUCED>
-CMADX_DEV void process_point(const MpArgs& A, const int64_t i, const bool live) {
+CMADX_DEV void process_point(const MpArgs& A, const int64_t i, const bool live, const bool allow_defer) {
     using Pt = typename std::conditional<REDUCED, HosfordPoint, SepPoint<YK>>::type;
     using Tr = typename std::conditional<REDUCED, HosfordTraits, SepPointTraits<YK>>::type;
     constexpr int N = Pt::N;
@@ -75,8 +75,15 @@ CMADX_DEV void process_point(const MpArgs& A, const int64_t i, const bool live) 
     double y[N], yp[N], Cy[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) { y[k] = x[Tr::full(k)]; yp[k] = xp[Tr::full(k)]; }
-    const NewtonResult nr = local_newton<Pt, N>(m, A.nw, pt, y, yp, em, live, Cy);
+    DevNewton nw = A.nw;
+    nw.defer_after = allow_defer ? A.nw.defer_request : 0;
+    const NewtonResult nr = local_newton<Pt, N>(m, nw, pt, y, yp, em, live, Cy);
     if (!live) return;
+    if (nr.deferred) {                       // second pass (list mode) re-solves this point
+        const unsigned slot = atomicAdd(A.bail_count, 1u);
+        if (slot < A.bail_cap) A.bail_list[slot] = (int)i;
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < N; ++k) x[Tr::full(k)] = y[k];
     if (A.b.C) {
@@ -242,13 +249,13 @@ template <int YK, bool ROT, bool REDUCED>
 __global__ void __launch_bounds__(MP_BLOCK, REDUCED ? 4 : 1)
 mp_update_kernel(const __grid_constant__ MpArgs A) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    process_point<YK, ROT, REDUCED>(A, i, i < A.b.n);
+    process_point<YK, ROT, REDUCED>(A, i, i < A.b.n, A.bail_count != nullptr);
 }
 
 // list mode: a small grid walks the points the J2 radial kernel handed back
 // (bail_count == 0: nothing to do; > bail_cap: the list overflowed, redo all)
-template <int YK, bool ROT>
-__global__ void __launch_bounds__(MP_BLOCK)
+template <int YK, bool ROT, bool REDUCED>
+__global__ void __launch_bounds__(MP_BLOCK, REDUCED ? 4 : 1)
 mp_update_list_kernel(const __grid_constant__ MpArgs A) {
     const unsigned cnt = *A.bail_count;
     if (cnt == 0u) return;
@@ -260,7 +267,7 @@ mp_update_list_kernel(const __grid_constant__ MpArgs A) {
         const int64_t j = base + lane;
         const bool live = j < total;
         const int64_t i = live ? (all ? j : (int64_t)A.bail_list[j]) : 0;
-        process_point<YK, ROT, false>(A, i, live);
+        process_point<YK, ROT, REDUCED>(A, i, live, false);
     }
 }
 
@@ -290,13 +297,32 @@ cudaError_t launch_mp_update_sep(const MpArgs& A, cudaStream_t stream) {
     return cudaErrorInvalidValue;
 }
 
+template <int YK>
+cudaError_t launch_list_yk(const MpArgs& A, cudaStream_t stream, int sms) {
+    if (YK == CMADX_YIELD_HOSFORD && !A.b.xi_init && !(A.nw.flags & CMADX_NEWTON_F_GENERIC)) {
+        constexpr int H = CMADX_YIELD_HOSFORD;
+        if (A.m.rot) mp_update_list_kernel<H, true, true><<<(unsigned)(4 * sms), MP_BLOCK, 0, stream>>>(A);
+        else mp_update_list_kernel<H, false, true><<<(unsigned)(4 * sms), MP_BLOCK, 0, stream>>>(A);
+        return cudaGetLastError();
+    }
+    if (A.m.rot) mp_update_list_kernel<YK, true, false><<<(unsigned)(2 * sms), MP_BLOCK, 0, stream>>>(A);
+    else mp_update_list_kernel<YK, false, false><<<(unsigned)(2 * sms), MP_BLOCK, 0, stream>>>(A);
+    return cudaGetLastError();
+}
+
+// second pass over the listed points: the J2 radial kernel's hand-backs, or the points the
+// generic kernel deferred (DevNewton::defer_after); never defers itself
 cudaError_t launch_mp_update_sep_list(const MpArgs& A, cudaStream_t stream) {
     if (A.b.n == 0) return cudaSuccess;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    mp_update_list_kernel<CMADX_YIELD_J2, false><<<(unsigned)(2 * sms), MP_BLOCK, 0, stream>>>(A);
-    return cudaGetLastError();
+    switch (A.m.yield) {
+    case CMADX_YIELD_J2: return launch_list_yk<CMADX_YIELD_J2>(A, stream, sms);
+    case CMADX_YIELD_HILL: return launch_list_yk<CMADX_YIELD_HILL>(A, stream, sms);
+    case CMADX_YIELD_HOSFORD: return launch_list_yk<CMADX_YIELD_HOSFORD>(A, stream, sms);
+    }
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace cmadx

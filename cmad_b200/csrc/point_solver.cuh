@@ -38,6 +38,10 @@ struct DevMat {
 
 struct DevNewton {
     int mode, max_iters, ls_max, flags;
+    int defer_after;   // > 0: a lane that needs more than this many Newton updates stops and is
+                       // handed to the second (compacted) pass; 0: off.  Only kernels that own a
+                       // second pass set it (from defer_request); everywhere else it stays 0
+    int defer_request; // what the caller asked for (cmadx_newton_t flags bits 8..15)
     double abs_tol, rel_tol, c1, bmin, bmax;
 };
 
@@ -571,6 +575,7 @@ struct NewtonResult {
     int iters;
     int flag_entry;
     double cnorm;
+    bool deferred;   // stopped by DevNewton::defer_after before converging: outputs are not valid
 };
 
 // Local Newton for one point; `live` lanes take part, the loop exit is decided
@@ -592,6 +597,7 @@ CMADX_DEV NewtonResult local_newton(const DevMat& m, const DevNewton& nw, Pt& pt
                                     const double (&em)[6], bool live, double (&C)[N]) {
     NewtonResult r;
     r.flag_entry = 0;
+    r.deferred = false;
     const bool traced = (nw.mode == CMADX_NEWTON_TRACED);
     enum { PH_INIT = 0, PH_PROBE = 1, PH_REFRESH = 2, PH_IMP = 3, PH_FINAL = 4 };
     int phase = PH_INIT;
@@ -690,6 +696,16 @@ CMADX_DEV NewtonResult local_newton(const DevMat& m, const DevNewton& nw, Pt& pt
 #pragma unroll
                     for (int i = 0; i < N; ++i) xt[i] = x[i];
                 }
+            }
+            // Warp-divergence control: the Newton counts of a batch are multi-modal (elastic: 0,
+            // easy plastic: 2, near-Tresca surfaces: 5-10 and more), and a warp runs as long as its
+            // slowest lane.  A lane that still needs a direction after `defer_after` updates stops
+            // here; the kernel appends it to a list and a second pass re-solves those points from
+            // scratch in warps made of hard points only (same code, same iterates, same result).
+            if (need_dir && nw.defer_after > 0 && ii >= nw.defer_after) {
+                need_dir = false;
+                active = false;
+                r.deferred = true;
             }
             if (need_dir) {
                 if (traced) {

@@ -32,13 +32,17 @@ class NewtonSettings:
     ls_min_backtrack: float = 0.5
     ls_max_backtrack: float = 0.9
     force_generic: bool = False     # bypass the J2 radial-return specialisation (A/B testing)
+    defer_after: int | None = None  # generic kernels' two-pass scheme: None = library default (2),
+                                    # 0 = single pass, K = defer points needing more than K updates
 
     def to_struct(self) -> L.Newton:
         if self.mode not in ("traced", "imperative"):
             raise ValueError(f"unknown newton mode {self.mode!r}")
         return L.Newton(L.NEWTON_TRACED if self.mode == "traced" else L.NEWTON_IMPERATIVE,
                         int(self.max_iters), int(self.ls_max_evals),
-                        L.NEWTON_F_GENERIC if self.force_generic else 0,
+                        (L.NEWTON_F_GENERIC if self.force_generic else 0)
+                        | ((0 if self.defer_after is None else (255 if self.defer_after == 0 else
+                                                               min(int(self.defer_after), 254))) << 8),
                         float(self.abs_tol), float(self.rel_tol),
                         float(self.ls_sufficient_decrease), float(self.ls_min_backtrack),
                         float(self.ls_max_backtrack))

@@ -79,7 +79,13 @@ enum {
 
 /* cmadx_newton_t.flags: force the generic 7x7 Newton kernel even where the J2
  * radial-return specialisation applies (testing / A-B comparison) */
+/* flags of cmadx_newton_t: bit 0 = always use the generic Newton kernels (no J2 radial-return
+ * specialisation); bits 8..15 = `defer_after` K of the generic kernels' two-pass scheme: a point
+ * that needs more than K Newton updates is re-solved by a second launch made of such points only
+ * (warp-divergence control; results are identical).  0 = library default (2), 255 = off. */
 enum { CMADX_NEWTON_F_GENERIC = 1 };
+#define CMADX_NEWTON_DEFER_SHIFT 8
+#define CMADX_NEWTON_DEFER_MASK 0xff00
 
 /* Material = the reference's parameter pytree for one element block
  * (cmad/parameters/parameters.py:205-272), flattened to a POD. */

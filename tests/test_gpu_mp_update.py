@@ -407,3 +407,30 @@ def test_hosford_reduced_4x4_path(cuda_device, a, mode):
     # the converged residual is rounding noise: compared absolutely
     assert float((red["C"] - gen["C"]).abs().max()) < 1e-13
     assert torch.equal(red["xi"][[1, 2, 4]], xi0[[1, 2, 4]])
+
+
+@pytest.mark.parametrize("kind,a", [("hosford", 100.0), ("hosford", 4.0), ("hill", None)])
+def test_two_pass_deferral_is_bitwise_identical(cuda_device, kind, a):
+    """The generic kernels' two-pass scheme (points needing more than K Newton updates are
+    re-solved by a second launch made of such points only) must not change a single bit:
+    single pass (defer_after=0) vs K = 1, 2 (default), 5 on a batch with a multi-modal
+    iteration-count distribution (near-Tresca Hosford a = 100: 0 / 2 / 5-10 updates)."""
+    from cmad_b200 import synthetic
+    values, act, tr = param_tree(kind, a=a, hill=(0.45, 0.6, 0.55, 1.4, 1.6, 1.5) if kind == "hill" else None)
+    P = Parameters(values, act, tr)
+    mat, pid = material_from_values(values), active_param_ids(P)
+    n = 50_000
+    d, d2, amp = (torch.from_numpy(x).to(cuda_device) for x in synthetic.path_params(5, 0, n, diag_only=kind == "hosford"))
+    xi = torch.zeros((7, n), dtype=torch.float64, device=cuda_device)
+    for t in (20, 40):
+        xi = mp.mp_update(mat, NewtonSettings(defer_after=0), pid, xi, synthetic.strain_at_step(d, d2, amp, t),
+                          outputs=("xi",))["xi"]
+    e = synthetic.strain_at_step(d, d2, amp, 60)
+    keys = ("xi", "sigma", "dsig_deps", "dC_dp", "iters", "flags", "cnorm")
+    base = mp.mp_update(mat, NewtonSettings(defer_after=0), pid, xi, e, outputs=keys)
+    assert int(base["iters"].max()) >= 3
+    for K in (1, None, 5):
+        out = mp.mp_update(mat, NewtonSettings(defer_after=K), pid, xi, e, outputs=keys)
+        torch.cuda.synchronize()
+        for k in keys:
+            assert torch.equal(out[k], base[k]), (kind, K, k)
