@@ -613,6 +613,19 @@ static int fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* 
         if (e != cudaSuccess) return cuda_fail(e);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         e = launch_fe_block_list(A, s);
+    } else if (A.nw.defer_request > 0 && A.nw.max_iters > A.nw.defer_request) {
+        // generic Newton in two passes (see launch() of the material-point path)
+        BailScratch bs;
+        if (int rc = get_bail_scratch(s, &bs, (unsigned)b.n_elems)) return rc;
+        A.bail_count = bs.count;
+        A.bail_list = reinterpret_cast<int*>(bs.count + 64);
+        A.bail_cap = bs.cap;
+        e = cudaMemsetAsync(bs.count, 0, sizeof(unsigned), s);
+        if (e != cudaSuccess) return cuda_fail(e);
+        e = launch_fe_block(A, false, s);
+        if (e != cudaSuccess) return cuda_fail(e);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = launch_fe_block_list(A, s);
     } else {
         e = launch_fe_block(A, false, s);
     }

@@ -27,9 +27,7 @@
 namespace cmadx {
 
 cudaError_t launch_fe_tet4(const FeArgs& A, int solver, bool list, cudaStream_t stream, int sms);
-cudaError_t launch_fe_tet4_list_nok(const FeArgs& A, cudaStream_t stream, int sms);
 cudaError_t launch_fe_hex8(const FeArgs& A, int solver, bool list, cudaStream_t stream, int sms);
-cudaError_t launch_fe_hex8_list_nok(const FeArgs& A, cudaStream_t stream, int sms);
 
 // main launch: J2 radial kernel where it applies, else the generic kernel
 cudaError_t launch_fe_block(const FeArgs& A, bool j2_radial, cudaStream_t stream) {
@@ -47,15 +45,16 @@ cudaError_t launch_fe_block_jvp(const FeArgs& A, cudaStream_t stream) {
                               : launch_fe_hex8(A, solver, false, stream, 0);
 }
 
-// generic J2 kernel over the elements the radial kernel handed back
+// second pass: the generic solver over the elements the first pass handed back (J2 radial
+// return) or deferred (generic Newton needing more than defer_request updates)
 cudaError_t launch_fe_block_list(const FeArgs& A, cudaStream_t stream) {
     if (A.b.n_elems == 0) return cudaSuccess;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const bool k = A.b.K_elem != nullptr;
-    if (A.b.n_basis == 4) return k ? launch_fe_tet4(A, 1, true, stream, sms) : launch_fe_tet4_list_nok(A, stream, sms);
-    return k ? launch_fe_hex8(A, 1, true, stream, sms) : launch_fe_hex8_list_nok(A, stream, sms);
+    const int solver = 1 + A.m.yield;
+    return (A.b.n_basis == 4) ? launch_fe_tet4(A, solver, true, stream, sms)
+                              : launch_fe_hex8(A, solver, true, stream, sms);
 }
 
 }  // namespace cmadx

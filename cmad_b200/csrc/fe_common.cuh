@@ -137,7 +137,7 @@ CMADX_DEV void point_generic(const DevMat& m, const DevNewton& nw, const double 
     const NewtonResult nr = local_newton<Pt, N>(m, nw, pt, y, yp, em, live, Cy);
 #pragma unroll
     for (int k = 0; k < N; ++k) o.x[Tr::full(k)] = y[k];
-    o.bail = false;
+    o.bail = nr.deferred;        // needs more than nw.defer_after updates: second (list) pass
     o.iters = nr.iters;
     o.flags = nr.flag_entry | ((pt.plastic ? 1 : 0) << 1);
     double sig[6];
@@ -397,6 +397,26 @@ cudaError_t dispatch_fe(const FeArgs& A, int solver, cudaStream_t stream, int sm
     case 6: return rot ? Launcher<6, true, false, LIST>::run(A, stream, sms) : Launcher<6, false, false, LIST>::run(A, stream, sms);
     }
 #undef CMADX_FE_CASE
+    return cudaErrorInvalidValue;
+}
+
+// list mode (second pass): the generic solver of the block's yield surface, never deferring
+template <template <int, bool, bool, bool> class Launcher>
+cudaError_t dispatch_fe_list(const FeArgs& A, int solver, cudaStream_t stream, int sms) {
+    const bool k = A.b.K_elem != nullptr;
+    const bool rot = A.m.rot != 0;
+#define CMADX_FE_LIST_CASE(S)                                                                    \
+    case S:                                                                                      \
+        if (rot) return k ? Launcher<S, true, true, true>::run(A, stream, sms)                   \
+                          : Launcher<S, true, false, true>::run(A, stream, sms);                 \
+        return k ? Launcher<S, false, true, true>::run(A, stream, sms)                           \
+                 : Launcher<S, false, false, true>::run(A, stream, sms);
+    switch (solver) {
+        CMADX_FE_LIST_CASE(1)
+        CMADX_FE_LIST_CASE(2)
+        CMADX_FE_LIST_CASE(3)
+    }
+#undef CMADX_FE_LIST_CASE
     return cudaErrorInvalidValue;
 }
 

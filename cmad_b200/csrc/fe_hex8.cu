@@ -63,7 +63,8 @@ CMADX_DEV constexpr int sidx(int al, int be) {
 CMADX_DEV int tile_pos(int a, int o) { return a * HEX_TILE_STRIDE + o; }
 
 template <int SOLVER, bool ROT, bool WANT_K>
-CMADX_DEV void hex8_point(const FeArgs& A, const int64_t e, const bool live, double* smem) {
+CMADX_DEV void hex8_point(const FeArgs& A, const int64_t e, const bool live, double* smem,
+                           const bool allow_defer) {
     const cmadx_fe_block_t& b = A.b;
     const int lane = threadIdx.x & 31;
     const int ip = lane & 7;                      // this thread's point; also its node in phase C
@@ -153,12 +154,14 @@ CMADX_DEV void hex8_point(const FeArgs& A, const int64_t e, const bool live, dou
         }
         point_jvp<SOLVER - FE_JVP, ROT>(A, xp, xs, dxp, eps, deps, live, o);
     } else {
-        solve_point<SOLVER, ROT, WANT_K>(A.m, A.nw, xp, eps, live, o, D);
+        DevNewton nw = A.nw;
+        nw.defer_after = allow_defer ? A.nw.defer_request : 0;
+        solve_point<SOLVER, ROT, WANT_K>(A.m, nw, xp, eps, live, o, D);
     }
 
-    // an element is handed to the generic kernel as a whole
+    // an element is handed to the second pass as a whole (J2 radial hand-backs, deferred points)
     bool ebail = false;
-    if (SOLVER == 0) {
+    if (SOLVER < FE_JVP) {
         const unsigned bal = __ballot_sync(0xffffffffu, o.bail);
         ebail = ((bal >> (lane & ~7)) & 0xffu) != 0u;
         if (ebail && live && ip == 0) append_bail(A, e);
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(FE_BLOCK, (SOLVER == 0) ? (WANT_K ? 3 : 4) : 1
     extern __shared__ __align__(16) double smem[];
     if (!LIST) {
         const int64_t e = (int64_t)blockIdx.x * HEX_EPB + (threadIdx.x >> 3);
-        hex8_point<SOLVER, ROT, WANT_K>(A, e, e < A.b.n_elems, smem);
+        hex8_point<SOLVER, ROT, WANT_K>(A, e, e < A.b.n_elems, smem, A.bail_count != nullptr);
     } else {
         const unsigned cnt = *A.bail_count;
         if (cnt == 0u) return;
@@ -319,7 +322,7 @@ __global__ void __launch_bounds__(FE_BLOCK, (SOLVER == 0) ? (WANT_K ? 3 : 4) : 1
             const int64_t j = base + (threadIdx.x >> 3);
             const bool live = j < total;
             const int64_t e = live ? (all ? j : (int64_t)A.bail_list[j]) : 0;
-            hex8_point<SOLVER, ROT, WANT_K>(A, e, live, smem);
+            hex8_point<SOLVER, ROT, WANT_K>(A, e, live, smem, false);
             __syncwarp();
         }
     }
@@ -341,11 +344,8 @@ struct Hex8Launcher {
 }  // namespace
 
 cudaError_t launch_fe_hex8(const FeArgs& A, int solver, bool list, cudaStream_t stream, int sms) {
-    if (list) return Hex8Launcher<1, false, true, true>::run(A, stream, sms);
+    if (list) return dispatch_fe_list<Hex8Launcher>(A, solver, stream, sms);
     return dispatch_fe<Hex8Launcher, false>(A, solver, stream, sms);
-}
-cudaError_t launch_fe_hex8_list_nok(const FeArgs& A, cudaStream_t stream, int sms) {
-    return Hex8Launcher<1, false, false, true>::run(A, stream, sms);
 }
 
 }  // namespace cmadx

@@ -7,7 +7,7 @@ namespace {
 
 // ==================================================================== tet4, 1 IP
 template <int SOLVER, bool ROT, bool WANT_K>
-CMADX_DEV void tet4_element(const FeArgs& A, const int64_t e, const bool live) {
+CMADX_DEV void tet4_element(const FeArgs& A, const int64_t e, const bool live, const bool allow_defer) {
     const cmadx_fe_block_t& b = A.b;
     double gN[4][3], U[4][3], xp[7];
     int eq[12];
@@ -60,10 +60,12 @@ CMADX_DEV void tet4_element(const FeArgs& A, const int64_t e, const bool live) {
         }
         point_jvp<SOLVER - FE_JVP, ROT>(A, xp, xs, dxp, eps, de, live, o);
     } else {
-        solve_point<SOLVER, ROT, WANT_K>(A.m, A.nw, xp, eps, live, o, D);
+        DevNewton nw = A.nw;
+        nw.defer_after = allow_defer ? A.nw.defer_request : 0;
+        solve_point<SOLVER, ROT, WANT_K>(A.m, nw, xp, eps, live, o, D);
     }
     if (!live) return;
-    if (SOLVER == 0 && o.bail) { append_bail(A, e); return; }
+    if (SOLVER < FE_JVP && o.bail) { append_bail(A, e); return; }
 
 #pragma unroll
     for (int c = 0; c < 7; ++c) b.xi[e * 7 + c] = o.x[c];
@@ -148,7 +150,7 @@ template <int SOLVER, bool ROT, bool WANT_K, bool LIST>
 __global__ void __launch_bounds__(FE_BLOCK, (SOLVER == 0) ? (WANT_K ? 3 : 4) : 1) fe_tet4_kernel(const __grid_constant__ FeArgs A) {
     if (!LIST) {
         const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        tet4_element<SOLVER, ROT, WANT_K>(A, e, e < A.b.n_elems);
+        tet4_element<SOLVER, ROT, WANT_K>(A, e, e < A.b.n_elems, A.bail_count != nullptr);
     } else {
         // list mode: a small grid walks the elements the J2 kernel handed back
         const unsigned cnt = *A.bail_count;
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(FE_BLOCK, (SOLVER == 0) ? (WANT_K ? 3 : 4) : 1
             const int64_t j = base + lane;
             const bool live = j < total;
             const int64_t e = live ? (all ? j : (int64_t)A.bail_list[j]) : 0;
-            tet4_element<SOLVER, ROT, WANT_K>(A, e, live);
+            tet4_element<SOLVER, ROT, WANT_K>(A, e, live, false);
         }
     }
 }
@@ -179,12 +181,9 @@ struct Tet4Launcher {
 }  // namespace
 
 cudaError_t launch_fe_tet4(const FeArgs& A, int solver, bool list, cudaStream_t stream, int sms) {
-    // list mode only ever runs the generic J2 kernel (solver 1, no rotation)
-    if (list) return Tet4Launcher<1, false, true, true>::run(A, stream, sms);
+    // list mode: the generic solver over the elements handed back / deferred by the first pass
+    if (list) return dispatch_fe_list<Tet4Launcher>(A, solver, stream, sms);
     return dispatch_fe<Tet4Launcher, false>(A, solver, stream, sms);
-}
-cudaError_t launch_fe_tet4_list_nok(const FeArgs& A, cudaStream_t stream, int sms) {
-    return Tet4Launcher<1, false, false, true>::run(A, stream, sms);
 }
 
 }  // namespace cmadx

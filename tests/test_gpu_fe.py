@@ -495,3 +495,25 @@ def test_closed_form_elastic_blocks(cuda_device, family, mixed):
         R_u = np.zeros(U.size); np.add.at(R_u, eq.reshape(-1), np.einsum("epaj,epji,ep->eai", gN, sdev, wdv).reshape(-1))
         n_u = 3 * nodes.shape[0]
         assert rel_err(R.cpu().numpy()[:n_u], R_u[:n_u]) < 1e-12
+
+
+@pytest.mark.parametrize("family", ["tet4", "hex8"])
+def test_fe_two_pass_deferral_is_bitwise_identical(cuda_device, family):
+    """K3 with the generic Newton in two passes (elements with a point needing more than K
+    updates go to a compacted second launch) vs a single pass: bitwise identical R_e, K_e, xi."""
+    from tests.golden.materials import material
+    values = material("hosford_notch")                                  # near-Tresca: 0 / 2 / 5-10+ updates
+    nodes, conn = _mesh(family, (6, 6, 6), distort=0.05, seed=8)
+    arr = fe_mesh.block_arrays(nodes, conn).to(cuda_device)
+    U = torch.from_numpy(fe_mesh.synthetic_displacement(nodes, 1.0, seed=3, ramp=0.004, noise=6e-4)).to(cuda_device)
+    mat = material_from_values(values)
+    xi0 = torch.zeros((arr.n_elems, arr.n_ip, 7), dtype=torch.float64, device=cuda_device)
+    kw = dict(max_iters=500, abs_tol=1e-12, rel_tol=1e-12, ls_max_evals=100)
+    outs = ("xi", "R_elem", "K_elem", "iters", "flags")
+    base = fe.fe_block_launch(mat, fe.fe_newton_settings(defer_after=0, **kw), arr, U, xi0, outs)
+    assert int(base["iters"].max()) >= 4
+    for K in (1, None, 4):
+        o = fe.fe_block_launch(mat, fe.fe_newton_settings(defer_after=K, **kw), arr, U, xi0, outs)
+        torch.cuda.synchronize()
+        for k in outs:
+            assert torch.equal(o[k], base[k]), (family, K, k)
