@@ -144,9 +144,19 @@ int make_dev_newton(const cmadx_newton_t* nw, DevNewton* o) {
     o->abs_tol = nw->abs_tol; o->rel_tol = nw->rel_tol;
     o->c1 = nw->ls_c1; o->bmin = nw->ls_bmin; o->bmax = nw->ls_bmax;
     const int k = (nw->flags & CMADX_NEWTON_DEFER_MASK) >> CMADX_NEWTON_DEFER_SHIFT;
-    o->defer_request = (k == 0) ? 2 : (k == 255 ? 0 : k);
+    o->defer_request = (k == 0) ? -1 : (k == 255 ? 0 : k);   // -1: library default, see default_defer()
     o->defer_after = 0;
     return CMADX_OK;
+}
+
+// Library default of the two-pass scheme.  Measured (2^23 points, B200): near-Tresca Hosford
+// (a = 100) has a three-modal count distribution (0 / 2 / 5-10 updates) and gains 1.25x with
+// K = 2; Hosford a = 4, Hill and J2 through the generic kernel are unimodal after the elastic
+// points (re-solving the deferred points from scratch costs more than the divergence it
+// removes), so the scheme stays off for them unless asked for.
+static void default_defer(const DevMat& m, DevNewton* nw) {
+    if (nw->defer_request >= 0) return;
+    nw->defer_request = (m.yield == CMADX_YIELD_HOSFORD && m.a > 8.0) ? 2 : 0;
 }
 
 static int build_args(const cmadx_material_t* mat, const cmadx_newton_t* nw,
@@ -155,6 +165,7 @@ static int build_args(const cmadx_material_t* mat, const cmadx_newton_t* nw,
     if (!b) return CMADX_EINVAL;
     if (int rc = make_dev_mat(mat, &A->m)) return rc;
     if (int rc = make_dev_newton(nw, &A->nw)) return rc;
+    default_defer(A->m, &A->nw);
     if (n_active < 0 || n_active > CMADX_MAX_ACTIVE) return CMADX_EINVAL;
     if (n_active > 0 && !active_pid) return CMADX_EINVAL;
     for (int c = 0; c < n_active; ++c) {
@@ -585,6 +596,7 @@ static int fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* 
     FeArgs A;
     if (int rc = check_fe_block(mat, blk, &A)) return rc;
     if (int rc = make_dev_newton(newton, &A.nw)) return rc;
+    default_defer(A.m, &A.nw);
     if (mix) {
         if (blk->n_elems > 0) {
             if (!mix->elem_eq_p || !mix->N || !mix->h) return CMADX_EINVAL;

@@ -64,8 +64,9 @@ CMADX_DEV void tet4_element(const FeArgs& A, const int64_t e, const bool live, c
         nw.defer_after = allow_defer ? A.nw.defer_request : 0;
         solve_point<SOLVER, ROT, WANT_K>(A.m, nw, xp, eps, live, o, D);
     }
-    if (!live) return;
-    if (SOLVER < FE_JVP && o.bail) { append_bail(A, e); return; }
+    if (SOLVER < FE_JVP && A.bail_count)
+        list_append(live && o.bail, A.bail_count, A.bail_list, A.bail_cap, (int)e);
+    if (!live || (SOLVER < FE_JVP && o.bail)) return;
 
 #pragma unroll
     for (int c = 0; c < 7; ++c) b.xi[e * 7 + c] = o.x[c];

@@ -78,12 +78,9 @@ CMADX_DEV void process_point(const MpArgs& A, const int64_t i, const bool live, 
     DevNewton nw = A.nw;
     nw.defer_after = allow_defer ? A.nw.defer_request : 0;
     const NewtonResult nr = local_newton<Pt, N>(m, nw, pt, y, yp, em, live, Cy);
-    if (!live) return;
-    if (nr.deferred) {                       // second pass (list mode) re-solves this point
-        const unsigned slot = atomicAdd(A.bail_count, 1u);
-        if (slot < A.bail_cap) A.bail_list[slot] = (int)i;
-        return;
-    }
+    if (allow_defer && nw.defer_after > 0)    // second pass (list mode) re-solves the deferred points
+        list_append(live && nr.deferred, A.bail_count, A.bail_list, A.bail_cap, (int)i);
+    if (!live || nr.deferred) return;
 #pragma unroll
     for (int k = 0; k < N; ++k) x[Tr::full(k)] = y[k];
     if (A.b.C) {

@@ -578,6 +578,23 @@ struct NewtonResult {
     bool deferred;   // stopped by DevNewton::defer_after before converging: outputs are not valid
 };
 
+// warp-aggregated append to a device list: one atomicAdd per warp instead of one per lane
+// (a third of an a = 100 Hosford batch is deferred: millions of appends to one counter)
+CMADX_DEV void list_append(bool want, unsigned* count, int* list, unsigned cap, int value) {
+    const unsigned active = __activemask();
+    const unsigned m = __ballot_sync(active, want);
+    if (m == 0u) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    unsigned base = 0u;
+    if (lane == leader) base = atomicAdd(count, (unsigned)__popc(m));
+    base = __shfl_sync(active, base, leader);
+    if (want) {
+        const unsigned slot = base + (unsigned)__popc(m & ((1u << lane) - 1u));
+        if (slot < cap) list[slot] = value;
+    }
+}
+
 // Local Newton for one point; `live` lanes take part, the loop exit is decided
 // warp-wide by ballot so the whole warp leaves together.  On return x is the
 // solution, C the residual there, and pt holds the state (n, f, plastic, yield

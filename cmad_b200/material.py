@@ -32,7 +32,7 @@ class NewtonSettings:
     ls_min_backtrack: float = 0.5
     ls_max_backtrack: float = 0.9
     force_generic: bool = False     # bypass the J2 radial-return specialisation (A/B testing)
-    defer_after: int | None = None  # generic kernels' two-pass scheme: None = library default (2),
+    defer_after: int | None = None  # generic kernels' two-pass scheme: None = library default (K = 2 for Hosford a > 8, else off),
                                     # 0 = single pass, K = defer points needing more than K updates
 
     def to_struct(self) -> L.Newton:

@@ -82,7 +82,9 @@ enum {
 /* flags of cmadx_newton_t: bit 0 = always use the generic Newton kernels (no J2 radial-return
  * specialisation); bits 8..15 = `defer_after` K of the generic kernels' two-pass scheme: a point
  * that needs more than K Newton updates is re-solved by a second launch made of such points only
- * (warp-divergence control; results are identical).  0 = library default (2), 255 = off. */
+ * (warp-divergence control; same iterates, counts and flags - derivative outputs may differ at
+ * rounding level between the two launches).  0 = library default (K = 2 for near-Tresca Hosford
+ * exponents, off otherwise), 255 = off. */
 enum { CMADX_NEWTON_F_GENERIC = 1 };
 #define CMADX_NEWTON_DEFER_SHIFT 8
 #define CMADX_NEWTON_DEFER_MASK 0xff00
