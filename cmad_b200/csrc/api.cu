@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -33,6 +34,15 @@ struct SensArgs {
     cmadx_mp_history_t h;
     double* partials;
 };
+struct HistArgs {
+    DevMat m;
+    DevNewton nw;
+    cmadx_mp_history_t h;
+    unsigned* bail_count;
+    int* bail_list;
+    unsigned bail_cap;
+};
+cudaError_t launch_mp_history(const HistArgs& A, bool radial, cudaStream_t s);
 cudaError_t launch_mp_sens(const SensArgs& A, bool adjoint, cudaStream_t stream);
 cudaError_t launch_mp_sens_dt(const SensArgs& A, int def_type, bool adjoint, cudaStream_t stream);
 int64_t sens_blocks(int64_t n);
@@ -517,6 +527,31 @@ int cmadx_mp_forward_history(const cmadx_material_t* mat, const cmadx_newton_t* 
                              const cmadx_mp_history_t* hist, void* stream) {
     DevMat dm;
     if (int rc = check_history(mat, hist, &dm)) return rc;
+    if (history_def_type(hist) == CMADX_DEF_FULL_3D && !dm.rot && hist->n < (int64_t)0x7fffffff &&
+        !std::getenv("CMADX_HISTORY_PER_STEP")) {
+        // fused path: one launch for the whole history (mp_history.cu)
+        HistArgs A;
+        A.m = dm;
+        if (int rc = make_dev_newton(newton, &A.nw)) return rc;
+        A.h = *hist;
+        A.bail_count = nullptr; A.bail_list = nullptr; A.bail_cap = 0;
+        if (hist->n == 0 || hist->nsteps == 0) return CMADX_OK;
+        cudaStream_t s = (cudaStream_t)stream;
+        const bool radial = dm.yield == CMADX_YIELD_J2 && !(A.nw.flags & CMADX_NEWTON_F_GENERIC);
+        if (radial) {
+            BailScratch bs;
+            if (int rc = get_bail_scratch(s, &bs, (unsigned)hist->n)) return rc;
+            A.bail_count = bs.count;
+            A.bail_list = reinterpret_cast<int*>(bs.count + 64);
+            A.bail_cap = bs.cap;
+            cudaError_t e = cudaMemsetAsync(bs.count, 0, sizeof(unsigned), s);
+            if (e != cudaSuccess) return cuda_fail(e);
+        }
+        cudaError_t e = launch_mp_history(A, radial, s);
+        if (e != cudaSuccess) return cuda_fail(e);
+        g_launches.fetch_add(radial ? 2 : 1, std::memory_order_relaxed);
+        return CMADX_OK;
+    }
     cmadx_mp_buffers_t b;
     std::memset(&b, 0, sizeof(b));
     b.n = hist->n; b.ld = hist->ld; b.strain_comps = hist->strain_comps;

@@ -64,3 +64,26 @@ def test_reference_style_single_point_objectives(cuda_device):
         assert abs(r.J - Jr) < 1e-12 * abs(Jr)
         assert np.allclose(r.grad, gr, rtol=1e-9)
     assert np.allclose(results[0].grad, results[1].grad, rtol=1e-10)
+
+
+@pytest.mark.parametrize("kind", ["J2", "hill", "hosford"])
+def test_fused_forward_history_equals_per_step_path(cuda_device, kind, monkeypatch):
+    """cmadx_mp_forward_history: the fused one-launch kernel (state in registers across the load
+    steps) against the per-step K1 launches it replaces: identical states and Newton counts."""
+    hill = (0.45, 0.6, 0.55, 1.4, 1.6, 1.5) if kind == "hill" else None
+    values, act, tr = param_tree(kind, ("voce",), hill=hill)
+    P = Parameters(values, act, tr)
+    sh, data, w = _problem(n=20000, N=15, seed=4, kind=kind)
+    model = SmallElasticPlastic(P)
+    res = {}
+    for mode in ("fused", "per_step"):
+        if mode == "per_step":
+            monkeypatch.setenv("CMADX_HISTORY_PER_STEP", "1")
+        ev = gpu_local_evaluator(model, sh, data, w, "adjoint", cuda_device)
+        out = ev().cpu().numpy()
+        h = ev.histories
+        res[mode] = (out, h.xi.cpu().numpy().copy(), h.iters.cpu().numpy().copy())
+    assert np.array_equal(res["fused"][2], res["per_step"][2])
+    assert np.array_equal(res["fused"][1], res["per_step"][1])
+    assert np.array_equal(res["fused"][0], res["per_step"][0])
+    assert res["fused"][2].max() >= 2
