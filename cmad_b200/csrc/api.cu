@@ -527,8 +527,12 @@ int cmadx_mp_forward_history(const cmadx_material_t* mat, const cmadx_newton_t* 
                              const cmadx_mp_history_t* hist, void* stream) {
     DevMat dm;
     if (int rc = check_history(mat, hist, &dm)) return rc;
+    // fused one-launch path: J2 (radial-return first pass, HBM / latency-bound: 1.3x faster than the
+    // per-step launches at scale), and any surface for small batches (launch-bound regime); large
+    // generic batches keep the per-step kernels (higher occupancy, measured faster)
+    const bool j2_radial = dm.yield == CMADX_YIELD_J2 && newton && !(newton->flags & CMADX_NEWTON_F_GENERIC);
     if (history_def_type(hist) == CMADX_DEF_FULL_3D && !dm.rot && hist->n < (int64_t)0x7fffffff &&
-        !std::getenv("CMADX_HISTORY_PER_STEP")) {
+        (j2_radial || hist->n <= 32768) && !std::getenv("CMADX_HISTORY_PER_STEP")) {
         // fused path: one launch for the whole history (mp_history.cu)
         HistArgs A;
         A.m = dm;

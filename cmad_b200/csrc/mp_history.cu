@@ -45,21 +45,33 @@ mp_history_kernel(const __grid_constant__ HistArgs A) {
 #pragma unroll
     for (int c = 0; c < 7; ++c) xp[c] = live ? __ldg(A.h.xi_hist + c * ld + i) : 0.0;
     bool dead = false;                       // J2 radial: handed to the generic re-walk
+    // software pipeline: the strain of step t + 1 is in flight while step t is solved
+    double raw[9];
+    auto fetch = [&](int t) {
+        const double* es = A.h.strain + (int64_t)t * sc * ld + i;
+        if (sc == 6) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) raw[c] = __ldg(es + c * ld);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 9; ++c) raw[c] = __ldg(es + c * ld);
+        }
+    };
+#pragma unroll
+    for (int c = 0; c < 9; ++c) raw[c] = 0.0;
+    if (live && N >= 1) fetch(1);
     for (int t = 1; t <= N; ++t) {
         const bool on = live && !dead;
         double e[6] = {1e-3, 0.0, 0.0, 0.0, 0.0, 0.0};
         if (on) {
-            const double* es = A.h.strain + (int64_t)t * sc * ld + i;
             if (sc == 6) {
 #pragma unroll
-                for (int c = 0; c < 6; ++c) e[c] = __ldg(es + c * ld);
+                for (int c = 0; c < 6; ++c) e[c] = raw[c];
             } else {
-                double g[9];
-#pragma unroll
-                for (int c = 0; c < 9; ++c) g[c] = __ldg(es + c * ld);
-                e[0] = g[0]; e[3] = g[4]; e[5] = g[8];
-                e[1] = 0.5 * (g[1] + g[3]); e[2] = 0.5 * (g[2] + g[6]); e[4] = 0.5 * (g[5] + g[7]);
+                e[0] = raw[0]; e[3] = raw[4]; e[5] = raw[8];
+                e[1] = 0.5 * (raw[1] + raw[3]); e[2] = 0.5 * (raw[2] + raw[6]); e[4] = 0.5 * (raw[5] + raw[7]);
             }
+            if (t < N) fetch(t + 1);
         }
         PointOut o;
         double D[6][6];
