@@ -173,6 +173,12 @@ def lib() -> C.CDLL:
     L.cmadx_fe_block_vjp.argtypes = [C.POINTER(Material), C.POINTER(C.c_int32), C.c_int32,
                                      C.POINTER(FeBlock), C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
+    L.cmadx_fe_block_jvp_mixed.argtypes = [C.POINTER(Material), C.POINTER(C.c_int32), C.c_int32,
+                                           C.POINTER(C.c_double), C.POINTER(FeBlock), C.POINTER(FeMixed),
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.cmadx_fe_block_vjp_mixed.argtypes = [C.POINTER(Material), C.POINTER(C.c_int32), C.c_int32,
+                                           C.POINTER(FeBlock), C.POINTER(FeMixed), C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.cmadx_segment_plan_create.argtypes = [C.POINTER(C.c_int64), C.c_int64, C.c_int64,
                                             C.POINTER(C.c_void_p)]
     L.cmadx_segment_plan_destroy.argtypes = [C.c_void_p]

@@ -626,7 +626,7 @@ static int check_fe_block(const cmadx_material_t* mat, const cmadx_fe_block_t* b
     A->b = b;
     A->bail_count = nullptr; A->bail_list = nullptr; A->bail_cap = 0;
     A->xi_state = nullptr; A->dxi_prev = nullptr; A->dU = nullptr; A->n_active = 0;
-    A->mix_eq_p = nullptr; A->mix_N = nullptr;
+    A->mix_eq_p = nullptr; A->mix_N = nullptr; A->mix_h = nullptr; A->mix_stab = 0.0;
     return CMADX_OK;
 }
 
@@ -747,20 +747,39 @@ int cmadx_embedded_apply(const cmadx_embedded_plan_t* plan, const double* K_data
     return CMADX_OK;
 }
 
-int cmadx_fe_block_jvp(const cmadx_material_t* mat, const int32_t* active_pid, int32_t n_active,
-                       const double* dp_host, const cmadx_fe_block_t* blk,
-                       const double* xi_state, const double* dxi_prev, const double* dU_global,
-                       void* stream) {
+static int check_mixed(const cmadx_fe_block_t* blk, const cmadx_fe_mixed_t* mix, FeArgs* A) {
+    if (!mix) return CMADX_OK;
+    if (blk->n_elems > 0) {
+        if (!mix->elem_eq_p || !mix->N || !mix->h) return CMADX_EINVAL;
+        if (reinterpret_cast<uintptr_t>(mix->elem_eq_p) % 16 != 0) return CMADX_EINVAL;
+    }
+    A->mix_eq_p = mix->elem_eq_p;
+    A->mix_N = mix->N;
+    A->mix_h = mix->h;
+    A->mix_stab = mix->stab_mult;
+    return CMADX_OK;
+}
+
+static int fe_block_jvp(const cmadx_material_t* mat, const int32_t* active_pid, int32_t n_active,
+                        const double* dp_host, const cmadx_fe_block_t* blk, const cmadx_fe_mixed_t* mix,
+                        const double* xi_state, const double* dxi_prev, const double* dU_global,
+                        void* stream) {
     FeArgs A;
     if (int rc = check_fe_block(mat, blk, &A)) return rc;
-    if (blk->K_elem) return CMADX_EINVAL;
+    if (int rc = check_mixed(blk, mix, &A)) return rc;
+    if (blk->K_elem || (mix && (mix->K_up || mix->K_pu || mix->K_pp))) return CMADX_EINVAL;
     if (n_active < 0 || n_active > CMADX_MAX_ACTIVE || (n_active > 0 && (!active_pid || !dp_host))) return CMADX_EINVAL;
+    double dlam = 0.0, dmu = 0.0;
     for (int c = 0; c < n_active; ++c) {
         const int pid = active_pid[c];
         if (pid < 0 || pid >= CMADX_NUM_PARAM_IDS) return CMADX_EINVAL;
         if (pid == CMADX_P_HOSFORD_A || pid >= CMADX_P_Q00) return CMADX_EUNSUPPORTED;
         A.pid[c] = pid;
         A.dp[c] = dp_host[c];
+        if (pid == CMADX_P_EL0 || pid == CMADX_P_EL1) {
+            dlam += A.m.dlam[pid - CMADX_P_EL0] * dp_host[c];
+            dmu += A.m.dmu[pid - CMADX_P_EL0] * dp_host[c];
+        }
     }
     A.n_active = n_active;
     if (blk->n_elems == 0) return CMADX_OK;
@@ -772,7 +791,29 @@ int cmadx_fe_block_jvp(const cmadx_material_t* mat, const int32_t* active_pid, i
     cudaError_t e = launch_fe_block_jvp(A, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (mix && (mix->R_p_elem || mix->R_global)) {
+        const double kappa = A.m.lam + 2.0 * A.m.mu / 3.0;
+        e = launch_fe_mixed_pressure_jvp(*blk, *mix, dU_global, kappa, A.m.mu, dlam + 2.0 * dmu / 3.0, dmu,
+                                         (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(e);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
     return CMADX_OK;
+}
+
+int cmadx_fe_block_jvp(const cmadx_material_t* mat, const int32_t* active_pid, int32_t n_active,
+                       const double* dp_host, const cmadx_fe_block_t* blk,
+                       const double* xi_state, const double* dxi_prev, const double* dU_global,
+                       void* stream) {
+    return fe_block_jvp(mat, active_pid, n_active, dp_host, blk, nullptr, xi_state, dxi_prev, dU_global, stream);
+}
+
+int cmadx_fe_block_jvp_mixed(const cmadx_material_t* mat, const int32_t* active_pid, int32_t n_active,
+                             const double* dp_host, const cmadx_fe_block_t* blk,
+                             const cmadx_fe_mixed_t* mix, const double* xi_state,
+                             const double* dxi_prev, const double* dU_global, void* stream) {
+    if (!mix) return CMADX_EINVAL;
+    return fe_block_jvp(mat, active_pid, n_active, dp_host, blk, mix, xi_state, dxi_prev, dU_global, stream);
 }
 
 int64_t cmadx_fe_vjp_workspace_bytes(int64_t n_elems, int32_t n_ip, int32_t n_active) {
@@ -780,12 +821,13 @@ int64_t cmadx_fe_vjp_workspace_bytes(int64_t n_elems, int32_t n_ip, int32_t n_ac
     return (int64_t)sizeof(double) * (fe_vjp_blocks(n_elems * n_ip) + 1) * (n_active > 0 ? n_active : 1);
 }
 
-int cmadx_fe_block_vjp(const cmadx_material_t* mat, const int32_t* active_pid, int32_t n_active,
-                       const cmadx_fe_block_t* blk, const double* xi_state,
-                       const double* Rbar_global, const double* xibar, double* pbar_dev,
-                       double* workspace, void* stream) {
+static int fe_block_vjp(const cmadx_material_t* mat, const int32_t* active_pid, int32_t n_active,
+                        const cmadx_fe_block_t* blk, const cmadx_fe_mixed_t* mix, const double* xi_state,
+                        const double* Rbar_global, const double* xibar, double* pbar_dev,
+                        double* workspace, void* stream) {
     FeArgs A;
     if (int rc = check_fe_block(mat, blk, &A)) return rc;
+    if (int rc = check_mixed(blk, mix, &A)) return rc;
     if (n_active < 0 || n_active > CMADX_MAX_ACTIVE || (n_active > 0 && (!active_pid || !pbar_dev || !workspace)))
         return CMADX_EINVAL;
     for (int c = 0; c < n_active; ++c) {
@@ -802,6 +844,23 @@ int cmadx_fe_block_vjp(const cmadx_material_t* mat, const int32_t* active_pid, i
     if (e != cudaSuccess) return cuda_fail(e);
     g_launches.fetch_add(2, std::memory_order_relaxed);
     return CMADX_OK;
+}
+
+int cmadx_fe_block_vjp(const cmadx_material_t* mat, const int32_t* active_pid, int32_t n_active,
+                       const cmadx_fe_block_t* blk, const double* xi_state,
+                       const double* Rbar_global, const double* xibar, double* pbar_dev,
+                       double* workspace, void* stream) {
+    return fe_block_vjp(mat, active_pid, n_active, blk, nullptr, xi_state, Rbar_global, xibar, pbar_dev,
+                        workspace, stream);
+}
+
+int cmadx_fe_block_vjp_mixed(const cmadx_material_t* mat, const int32_t* active_pid, int32_t n_active,
+                             const cmadx_fe_block_t* blk, const cmadx_fe_mixed_t* mix,
+                             const double* xi_state, const double* Rbar_global, const double* xibar,
+                             double* pbar_dev, double* workspace, void* stream) {
+    if (!mix) return CMADX_EINVAL;
+    return fe_block_vjp(mat, active_pid, n_active, blk, mix, xi_state, Rbar_global, xibar, pbar_dev,
+                        workspace, stream);
 }
 
 int cmadx_release_host_scratch(void) {

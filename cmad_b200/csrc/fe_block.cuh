@@ -19,6 +19,8 @@ struct FeArgs {
     // mixed u-p formulation (small_disp_equilibrium.py:87-111): pressure dofs and shape values
     const int32_t* mix_eq_p;  // [n_elems][n_basis] equation of the pressure dof, or NULL (displacement form)
     const double* mix_N;      // [n_ip][n_basis]
+    const double* mix_h;      // [n_elems] element size (K6-mixed VJP: d tau / d mu), or NULL
+    double mix_stab;          // stabilization multiplier
     double dp[CMADX_MAX_ACTIVE];
     int pid[CMADX_MAX_ACTIVE];
     int n_active;
@@ -29,5 +31,7 @@ cudaError_t launch_fe_block_list(const FeArgs& A, cudaStream_t stream);
 cudaError_t launch_fe_block_jvp(const FeArgs& A, cudaStream_t stream);
 cudaError_t launch_fe_mixed_pressure(const cmadx_fe_block_t& b, const cmadx_fe_mixed_t& mx, double kappa,
                                      double mu, cudaStream_t stream);
+cudaError_t launch_fe_mixed_pressure_jvp(const cmadx_fe_block_t& b, const cmadx_fe_mixed_t& mx, const double* dU,
+                                         double kappa, double mu, double dkappa, double dmu, cudaStream_t stream);
 
 }  // namespace cmadx

@@ -176,16 +176,16 @@ CMADX_DEV void hex8_point(const FeArgs& A, const int64_t e, const bool live, dou
             for (int a = 0; a < 6; ++a) b.sigma[p * 6 + a] = o.sg[a];
         }
     }
-    if constexpr (SOLVER < FE_JVP) {
-        if (A.mix_eq_p) {
-            double p = 0.0;
-            if (live) {
+    if (A.mix_eq_p) {
+        // primal: p from U; K6: the momentum-stress direction dev(d cauchy) - dp I, dp from dU
+        const double* pv = (SOLVER >= FE_JVP) ? A.dU : b.U;
+        double p = 0.0;
+        if (live && pv) {
 #pragma unroll
-                for (int a = 0; a < 8; ++a)
-                    p = fma(__ldg(A.mix_N + ip * 8 + a), __ldg(b.U + __ldg(A.mix_eq_p + e * 8 + a)), p);
-            }
-            mixed_momentum_stress<WANT_K>(p, o.sg, D);
+            for (int a = 0; a < 8; ++a)
+                p = fma(__ldg(A.mix_N + ip * 8 + a), __ldg(pv + __ldg(A.mix_eq_p + e * 8 + a)), p);
         }
+        mixed_momentum_stress<WANT_K>(p, o.sg, D);
     }
     {   // own record slots and own xi slot: no other thread has touched or read them yet
         double* rec = recs + ip * HEX_REC;

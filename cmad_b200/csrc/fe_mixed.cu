@@ -107,7 +107,72 @@ __global__ void __launch_bounds__(FE_BLOCK, 4) fe_mixed_pressure_kernel(const cm
     if (mx.R_global) atomicAdd(mx.R_global + __ldg(mx.elem_eq_p + e * NB + a), Rp);
 }
 
+
+// K6 for the pressure block: tangent of R_p at fixed local state.  R_p is linear in the
+// (u, p) dofs and depends on the parameters only through kappa and mu:
+//   dR_p[a] = sum_ip ( (p dkappa/kappa^2 - dp/kappa - tr(d eps)) N_a
+//                      + tau_h (dmu/mu^2 gradN_a.grad p - 1/mu gradN_a.grad dp) ) w dv,
+// tau_h = mult h^2 / 2, (dp, d eps) interpolated from the direction dU (or zero).  This is the
+// pressure rows of what jax.jvp pushes through the assembled mixed residual
+// (cmad/fem/nonlinear_solver.py:490-537 over small_disp_equilibrium.py:94-110).  One thread
+// per (element, node); nodal sums by butterfly shuffles over the element's lanes.
+template <int NB, int NIP>
+__global__ void __launch_bounds__(FE_BLOCK) fe_mixed_pressure_jvp_kernel(const cmadx_fe_block_t b,
+                                                                         const cmadx_fe_mixed_t mx,
+                                                                         const double* __restrict__ dU,
+                                                                         const double kappa, const double mu,
+                                                                         const double dkappa, const double dmu) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = t / NB;
+    const int a = (int)(t - e * NB);
+    const bool live = e < b.n_elems;
+    if (__all_sync(0xffffffffu, !live)) return;
+    const int64_t el = live ? e : 0;
+    const int eqp = __ldg(mx.elem_eq_p + el * NB + a);
+    const double pa = __ldg(b.U + eqp);
+    double dUa[3] = {0.0, 0.0, 0.0}, dpa = 0.0;
+    if (dU) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dUa[k] = __ldg(dU + __ldg(b.elem_eq + el * (NB * 3) + 3 * a + k));
+        dpa = __ldg(dU + eqp);
+    }
+    const double h = __ldg(mx.h + el);
+    const double tau_h = mx.stab_mult * 0.5 * h * h;
+    const double cp = dkappa / (kappa * kappa), ct = dmu / (mu * mu), ik = 1.0 / kappa, im = 1.0 / mu;
+    double dRp = 0.0;
+#pragma unroll 1
+    for (int q = 0; q < NIP; ++q) {
+        const double* g = b.grad_N + (el * NIP + q) * (NB * 3);
+        const double Na = __ldg(mx.N + q * NB + a);
+        const double g0 = __ldg(g + 3 * a), g1 = __ldg(g + 3 * a + 1), g2 = __ldg(g + 3 * a + 2);
+        const double wdv = __ldg(b.quad_w + q) * __ldg(b.det + el * NIP + q);
+        // v[0] = p, v[1..3] = grad p, v[4] = dp, v[5] = tr(d eps), v[6..8] = grad dp
+        double v[9] = {Na * pa, pa * g0, pa * g1, pa * g2, Na * dpa,
+                       fma(dUa[2], g2, fma(dUa[1], g1, dUa[0] * g0)), dpa * g0, dpa * g1, dpa * g2};
+#pragma unroll
+        for (int m = 1; m < NB; m <<= 1)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], m);
+        const double gg = fma(g2, v[3], fma(g1, v[2], g0 * v[1]));
+        const double gd = fma(g2, v[8], fma(g1, v[7], g0 * v[6]));
+        dRp = fma(wdv, (cp * v[0] - ik * v[4] - v[5]) * Na + tau_h * (ct * gg - im * gd), dRp);
+    }
+    if (!live) return;
+    if (mx.R_p_elem) mx.R_p_elem[e * NB + a] = dRp;
+    if (mx.R_global) atomicAdd(mx.R_global + eqp, dRp);
+}
+
 }  // namespace
+
+cudaError_t launch_fe_mixed_pressure_jvp(const cmadx_fe_block_t& b, const cmadx_fe_mixed_t& mx, const double* dU,
+                                         double kappa, double mu, double dkappa, double dmu, cudaStream_t stream) {
+    if (b.n_elems == 0) return cudaSuccess;
+    const int64_t nthr = b.n_elems * b.n_basis;
+    const unsigned nblk = (unsigned)((nthr + FE_BLOCK - 1) / FE_BLOCK);
+    if (b.n_basis == 4) fe_mixed_pressure_jvp_kernel<4, 1><<<nblk, FE_BLOCK, 0, stream>>>(b, mx, dU, kappa, mu, dkappa, dmu);
+    else fe_mixed_pressure_jvp_kernel<8, 8><<<nblk, FE_BLOCK, 0, stream>>>(b, mx, dU, kappa, mu, dkappa, dmu);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_fe_mixed_pressure(const cmadx_fe_block_t& b, const cmadx_fe_mixed_t& mx, double kappa,
                                      double mu, cudaStream_t stream) {

@@ -76,14 +76,17 @@ CMADX_DEV void tet4_element(const FeArgs& A, const int64_t e, const bool live, c
 #pragma unroll
         for (int a = 0; a < 6; ++a) b.sigma[e * 6 + a] = o.sg[a];
     }
-    if constexpr (SOLVER < FE_JVP) {
-        if (A.mix_eq_p) {
+    if (A.mix_eq_p) {
+        // primal: p from U; K6: the momentum-stress direction dev(d cauchy) - dp I, dp from dU
+        const double* pv = (SOLVER >= FE_JVP) ? A.dU : b.U;
+        double p = 0.0;
+        if (pv) {
             const int4 qp = __ldg(reinterpret_cast<const int4*>(A.mix_eq_p + e * 4));
-            const double p = fma(__ldg(A.mix_N + 3), __ldg(b.U + qp.w),
-                                 fma(__ldg(A.mix_N + 2), __ldg(b.U + qp.z),
-                                     fma(__ldg(A.mix_N + 1), __ldg(b.U + qp.y), __ldg(A.mix_N) * __ldg(b.U + qp.x))));
-            mixed_momentum_stress<WANT_K>(p, o.sg, D);
+            p = fma(__ldg(A.mix_N + 3), __ldg(pv + qp.w),
+                    fma(__ldg(A.mix_N + 2), __ldg(pv + qp.z),
+                        fma(__ldg(A.mix_N + 1), __ldg(pv + qp.y), __ldg(A.mix_N) * __ldg(pv + qp.x))));
         }
+        mixed_momentum_stress<WANT_K>(p, o.sg, D);
     }
     // R[a][i] = sum_j gN[a][j] sigma[j][i] w dv
     if (b.R_elem || b.R_global) {

@@ -74,6 +74,32 @@ fe_vjp_kernel(const __grid_constant__ FeArgs A, const double* __restrict__ Rbar,
     eg[1] = 0.5 * (gu[0][1] + gu[1][0]); eg[2] = 0.5 * (gu[0][2] + gu[2][0]); eg[4] = 0.5 * (gu[1][2] + gu[2][1]);
     sbg[0] = sb33[0][0] * wdv; sbg[3] = sb33[1][1] * wdv; sbg[5] = sb33[2][2] * wdv;
     sbg[1] = (sb33[0][1] + sb33[1][0]) * wdv; sbg[2] = (sb33[0][2] + sb33[2][0]) * wdv; sbg[4] = (sb33[1][2] + sb33[2][1]) * wdv;
+    // mixed u-p: R_u sees dev(cauchy) - p I, and dev is self-adjoint: project the cotangent.
+    // The pressure rows depend on the parameters through kappa and mu only
+    // (small_disp_equilibrium.py:101-110): d/dkappa = p/kappa^2 N_a, d/dmu = tau/mu gradN_a.grad p
+    double mixk = 0.0, mixm = 0.0;     // cotangents of kappa and mu from the pressure block
+    if (A.mix_eq_p) {
+        const double tr3 = (sbg[0] + sbg[3] + sbg[5]) / 3.0;
+        sbg[0] -= tr3; sbg[3] -= tr3; sbg[5] -= tr3;
+        if (live) {
+            const double* gN = b.grad_N + (p * nb) * 3;
+            double rbN = 0.0, pip = 0.0, rbG[3] = {0.0, 0.0, 0.0}, gp[3] = {0.0, 0.0, 0.0};
+            for (int a = 0; a < nb; ++a) {
+                const int eqp = __ldg(A.mix_eq_p + e * nb + a);
+                const double rb = __ldg(Rbar + eqp), pa = __ldg(b.U + eqp), Na = __ldg(A.mix_N + ip * nb + a);
+                rbN = fma(rb, Na, rbN); pip = fma(pa, Na, pip);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double gk = __ldg(gN + 3 * a + k);
+                    rbG[k] = fma(rb, gk, rbG[k]); gp[k] = fma(pa, gk, gp[k]);
+                }
+            }
+            const double kappa = m.lam + 2.0 * m.mu / 3.0;
+            const double h = __ldg(A.mix_h + e);
+            mixk = wdv * pip * rbN / (kappa * kappa);
+            mixm = wdv * A.mix_stab * 0.5 * h * h / (m.mu * m.mu) * fma(rbG[2], gp[2], fma(rbG[1], gp[1], rbG[0] * gp[0]));
+        }
+    }
     double em[6], sbar[6];     // material axes
     if (ROT) {
         double T[6][6], S[6][6];
@@ -160,8 +186,11 @@ fe_vjp_kernel(const __grid_constant__ FeArgs A, const double* __restrict__ Rbar,
                 double acc = 0.0;
 #pragma unroll
                 for (int q = 0; q < 7; ++q) acc = fma(mu[q], col[q], acc);
-                if (pid == CMADX_P_EL0 || pid == CMADX_P_EL1)
-                    acc += m.dlam[pid - CMADX_P_EL0] * tre * strb + 2.0 * m.dmu[pid - CMADX_P_EL0] * see;
+                if (pid == CMADX_P_EL0 || pid == CMADX_P_EL1) {
+                    const double dl = m.dlam[pid - CMADX_P_EL0], dm = m.dmu[pid - CMADX_P_EL0];
+                    acc += dl * tre * strb + 2.0 * dm * see;
+                    acc += (dl + 2.0 * dm / 3.0) * mixk + dm * mixm;
+                }
                 g[c] = acc;
             }
         }

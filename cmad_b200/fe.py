@@ -324,14 +324,21 @@ class EmbeddedBCPlan:
 def fe_block_jvp(material: L.Material, arrays: FEBlockArrays, U_global: torch.Tensor,
                  xi_prev: torch.Tensor, xi_state: torch.Tensor, active_pid, dp,
                  dxi_prev: torch.Tensor | None = None, outputs=("xi", "R_elem"), out: dict | None = None,
-                 stream: torch.cuda.Stream | None = None, dU: torch.Tensor | None = None) -> dict:
+                 stream: torch.cuda.Stream | None = None, dU: torch.Tensor | None = None,
+                 stab_mult: float | None = None) -> dict:
     """K6: tangent of the converged block w.r.t. (params, xi_prev) at fixed ``U``:
     returns ``out["xi"]`` = ``dxi (n_e, n_ip, 7)`` and ``out["R_elem"]`` = ``dR_e``
     (or ``R_global``) for the direction ``dp`` (native values of the active
     parameters, in ``active_pid`` order) and ``dxi_prev``.  What ``jax.jvp`` pushes
     through the assembled residual inside the FE Newton's IFT rule
     (cmad/fem/nonlinear_solver.py:490-537).  ``dU (n_dofs,)`` optionally adds a displacement
-    direction (then ``dR`` includes ``K dU`` and ``dxi`` is the total state sensitivity)."""
+    direction (then ``dR`` includes ``K dU`` and ``dxi`` is the total state sensitivity).
+    ``stab_mult`` (mixed u-p block arrays only) selects the mixed formulation: ``U`` / ``dU``
+    cover the block-major (u, p) dofs, ``R_elem`` is ``dR_u`` and the extra output ``R_p_elem
+    (n_e, n_b)`` is ``dR_p``; ``R_global`` accumulates both."""
+    mixed = stab_mult is not None
+    if mixed and not arrays.mixed:
+        raise ValueError("block arrays were built without mixed=True")
     n_e, n_b, n_ip = arrays.n_elems, arrays.n_basis, arrays.n_ip
     dev = arrays.grad_N.device
     if dev.type != "cuda":
@@ -351,6 +358,9 @@ def fe_block_jvp(material: L.Material, arrays: FEBlockArrays, U_global: torch.Te
         raise ValueError("dp must have one entry per active parameter")
     shapes = {"xi": ((n_e, n_ip, 7), torch.float64), "R_elem": ((n_e, n_b * 3), torch.float64),
               "R_global": ((arrays.n_dofs,), torch.float64)}
+    if mixed:
+        shapes["R_p_elem"] = ((n_e, n_b), torch.float64)
+        outputs = tuple(outputs) + (("R_p_elem",) if "R_elem" in outputs else ())
     out = dict(out) if out is not None else {}
     for name in set(outputs) | {"xi"}:
         if name not in shapes:
@@ -360,25 +370,48 @@ def fe_block_jvp(material: L.Material, arrays: FEBlockArrays, U_global: torch.Te
             out[name] = (torch.zeros if name == "R_global" else torch.empty)(shape, dtype=dt, device=dev)
     b = _fe_struct(arrays, U_global, xi_prev, out)
     s = stream if stream is not None else torch.cuda.current_stream(dev)
-    with torch.cuda.device(dev):
-        rc = L.lib().cmadx_fe_block_jvp(
-            C.byref(material), pid.ctypes.data_as(C.POINTER(C.c_int32)), len(pid),
-            dpv.ctypes.data_as(C.POINTER(C.c_double)), C.byref(b), C.c_void_p(xi_state.data_ptr()),
+    tail = (C.c_void_p(xi_state.data_ptr()),
             C.c_void_p(dxi_prev.data_ptr()) if dxi_prev is not None else None,
             C.c_void_p(dU.data_ptr()) if dU is not None else None, C.c_void_p(s.cuda_stream))
+    with torch.cuda.device(dev):
+        if mixed:
+            mx = _fe_mixed_struct(arrays, stab_mult)
+            if out.get("R_p_elem") is not None:
+                mx.R_p_elem = out["R_p_elem"].data_ptr()
+            if out.get("R_global") is not None:
+                mx.R_global = out["R_global"].data_ptr()
+            rc = L.lib().cmadx_fe_block_jvp_mixed(
+                C.byref(material), pid.ctypes.data_as(C.POINTER(C.c_int32)), len(pid),
+                dpv.ctypes.data_as(C.POINTER(C.c_double)), C.byref(b), C.byref(mx), *tail)
+        else:
+            rc = L.lib().cmadx_fe_block_jvp(
+                C.byref(material), pid.ctypes.data_as(C.POINTER(C.c_int32)), len(pid),
+                dpv.ctypes.data_as(C.POINTER(C.c_double)), C.byref(b), *tail)
     L.check(rc, "cmadx_fe_block_jvp")
     return out
+
+
+def _fe_mixed_struct(arrays: FEBlockArrays, stab_mult: float) -> "L.FeMixed":
+    mx = L.FeMixed()
+    mx.elem_eq_p, mx.N, mx.h = arrays.elem_eq_p.data_ptr(), arrays.N.data_ptr(), arrays.h.data_ptr()
+    mx.stab_mult = float(stab_mult)
+    return mx
 
 
 def fe_block_vjp(material: L.Material, arrays: FEBlockArrays, U_global: torch.Tensor,
                  xi_prev: torch.Tensor, xi_state: torch.Tensor, active_pid, Rbar: torch.Tensor,
                  xibar: torch.Tensor | None = None, group=None,
-                 stream: torch.cuda.Stream | None = None) -> tuple[torch.Tensor, torch.Tensor]:
+                 stream: torch.cuda.Stream | None = None,
+                 stab_mult: float | None = None) -> tuple[torch.Tensor, torch.Tensor]:
     """K6 reverse mode: ``(pbar (n_active,), xibar_prev (n_e, n_ip, 7))`` for the cotangents
     ``Rbar (n_dofs,)`` of the assembled residual and ``xibar`` of the converged local
     state - one step of a discrete FE adjoint, the transpose of :func:`fe_block_jvp`.
     Under ``torch.distributed`` (element partition) ``pbar`` is all-reduced: the gradient
-    exchange of the calibration loop."""
+    exchange of the calibration loop.  ``stab_mult`` (mixed block arrays) selects the mixed
+    u-p formulation: ``Rbar`` covers both residual blocks."""
+    mixed = stab_mult is not None
+    if mixed and not arrays.mixed:
+        raise ValueError("block arrays were built without mixed=True")
     n_e, n_ip = arrays.n_elems, arrays.n_ip
     dev = arrays.grad_N.device
     if dev.type != "cuda":
@@ -397,12 +430,17 @@ def fe_block_vjp(material: L.Material, arrays: FEBlockArrays, U_global: torch.Te
     wsb = int(L.lib().cmadx_fe_vjp_workspace_bytes(n_e, n_ip, na))
     ws = torch.empty((max(wsb // 8, 1),), dtype=torch.float64, device=dev)
     s = stream if stream is not None else torch.cuda.current_stream(dev)
-    with torch.cuda.device(dev):
-        rc = L.lib().cmadx_fe_block_vjp(
-            C.byref(material), pid.ctypes.data_as(C.POINTER(C.c_int32)), na, C.byref(b),
-            C.c_void_p(xi_state.data_ptr()), C.c_void_p(Rbar.data_ptr()),
+    tail = (C.c_void_p(xi_state.data_ptr()), C.c_void_p(Rbar.data_ptr()),
             C.c_void_p(xibar.data_ptr()) if xibar is not None else None,
             C.c_void_p(pbar.data_ptr()), C.c_void_p(ws.data_ptr()), C.c_void_p(s.cuda_stream))
+    with torch.cuda.device(dev):
+        if mixed:
+            mx = _fe_mixed_struct(arrays, stab_mult)
+            rc = L.lib().cmadx_fe_block_vjp_mixed(
+                C.byref(material), pid.ctypes.data_as(C.POINTER(C.c_int32)), na, C.byref(b), C.byref(mx), *tail)
+        else:
+            rc = L.lib().cmadx_fe_block_vjp(
+                C.byref(material), pid.ctypes.data_as(C.POINTER(C.c_int32)), na, C.byref(b), *tail)
     L.check(rc, "cmadx_fe_block_vjp")
     pbar = pbar[:na]
     import torch.distributed as dist

@@ -350,6 +350,27 @@ int cmadx_fe_block_vjp(const cmadx_material_t* mat, const int32_t* active_pid, i
                        const double* Rbar_global, const double* xibar, double* pbar_dev,
                        double* workspace, void* stream);
 
+/* K6 for the mixed u-p block (cmad/global_residuals/small_disp_equilibrium.py:87-111; the
+ * sensitivities `cmad gradient` needs on examples/mixed_plastic.yaml-style decks): the same
+ * tangent / cotangent maps over BOTH residual blocks.  `mix` as in
+ * cmadx_fe_block_assemble_mixed with K_up = K_pu = K_pp = NULL.
+ * JVP: blk->R_elem / R_global receive dR_u = sum_ip gradN (dev(d cauchy) - dp I) w dv and
+ *      mix->R_p_elem / R_global receive
+ *      dR_p[a] = sum_ip ((p dkappa/kappa^2 - dp/kappa - tr(d eps)) N_a
+ *                        + (tau dmu/mu gradN_a.grad p - tau gradN_a.grad dp)) w dv;
+ *      dU_global covers the block-major (u, p) dofs, (dp, d eps) are interpolated from it.
+ * VJP: Rbar_global covers both blocks; the momentum cotangent is projected (dev is
+ *      self-adjoint) before it enters the local adjoint solve, and the pressure rows add
+ *      their (kappa, mu) cotangents to the elastic parameters' entries of pbar.          */
+int cmadx_fe_block_jvp_mixed(const cmadx_material_t* mat, const int32_t* active_pid, int32_t n_active,
+                             const double* dp_host, const cmadx_fe_block_t* blk,
+                             const cmadx_fe_mixed_t* mix, const double* xi_state,
+                             const double* dxi_prev, const double* dU_global, void* stream);
+int cmadx_fe_block_vjp_mixed(const cmadx_material_t* mat, const int32_t* active_pid, int32_t n_active,
+                             const cmadx_fe_block_t* blk, const cmadx_fe_mixed_t* mix,
+                             const double* xi_state, const double* Rbar_global, const double* xibar,
+                             double* pbar_dev, double* workspace, void* stream);
+
 /* ---- Post-processing at a stored state: evaluate_cauchy_at_ips ------------------------
  * model.cauchy(xi, xi_prev, params, U_ip, U_ip_prev) at every (element, IP) of a COUPLED block
  * from the converged local state (cmad/fem/postprocess.py:35-185): sigma [n_elems][n_ip][6],

@@ -178,7 +178,7 @@ def coo_dedup_sum(vals: np.ndarray, scatter: np.ndarray, n_unique: int) -> np.nd
 
 
 def block_jvp(prob_eval: oracle_c.OracleProblem, elem_eq, U, xi_prev, xi_state, grad_N, det, quad_w,
-              dp, dxi_prev=None, nthreads: int = 0, dU=None) -> dict:
+              dp, dxi_prev=None, nthreads: int = 0, dU=None, _want_dsigma: bool = False) -> dict:
     """Forward sensitivities of a COUPLED block at the converged state, at fixed ``U``
     (what jax.jvp pushes through the custom_jvp rule of make_newton_solve,
     cmad/models/nonlinear_solver.py:158-171, inside cmad/fem/nonlinear_solver.py:490-537):
@@ -192,7 +192,7 @@ def block_jvp(prob_eval: oracle_c.OracleProblem, elem_eq, U, xi_prev, xi_state, 
     dp = np.asarray(dp, dtype=np.float64).reshape(na)
     U_e = np.asarray(U)[elem_eq].reshape(n_e, n_b, 3)
     dU_e = None if dU is None else np.asarray(dU)[elem_eq].reshape(n_e, n_b, 3)
-    dR = np.zeros((n_e, n_b, 3)); dxi = np.zeros((n_e, n_ip, 7))
+    dR = np.zeros((n_e, n_b, 3)); dxi = np.zeros((n_e, n_ip, 7)); dsig = []
     for ip in range(n_ip):
         gN = grad_N[:, ip]
         gu = np.einsum("eak,eaj->ekj", U_e, gN).reshape(n_e, 9).T.copy()
@@ -220,6 +220,63 @@ def block_jvp(prob_eval: oracle_c.OracleProblem, elem_eq, U, xi_prev, xi_state, 
             dx = dx + np.einsum("rbe,be->er", r["dxi_deps"].reshape(7, 6, n_e), de6)
             ds = ds + np.einsum("abe,be->ae", r["dsig_deps"].reshape(6, 6, n_e), de6)
         dxi[:, ip] = dx
+        dsig.append(ds)
         wdv = quad_w[ip] * det[:, ip]
         dR += np.einsum("eaj,jie->eai", gN, ds[_V]) * wdv[:, None, None]
-    return {"R_elem": dR.reshape(n_e, n_b * 3), "xi": dxi}
+    out = {"R_elem": dR.reshape(n_e, n_b * 3), "xi": dxi}
+    if _want_dsigma:
+        out["dsigma"] = dsig                     # per IP: (6, n_e) direction of the global cauchy
+    return out
+
+
+def block_jvp_mixed(prob_eval: oracle_c.OracleProblem, elem_eq, elem_eq_p, U, xi_prev, xi_state, grad_N, N, det,
+                    quad_w, h, dp, dxi_prev=None, stab_mult: float = 1.0, nthreads: int = 0,
+                    dU=None) -> dict:
+    """Forward sensitivities of a MIXED u-p COUPLED block at the converged state (the mixed
+    counterpart of :func:`block_jvp`): what jax.jvp pushes through the two residual blocks of
+    cmad/global_residuals/small_disp_equilibrium.py:87-111 inside cmad/fem/nonlinear_solver.py:
+    490-537.  The local Newton only sees grad_u, so ``dxi`` and ``d cauchy`` are those of the
+    displacement form; then
+      dR_u = sum_ip gradN (dev(d cauchy) - dp_ip I) w dv,
+      dR_p = sum_ip ( -(dp_ip + d hydro)/kappa N + (p + hydro) dkappa/kappa^2 N
+                      - d tau gradN.grad p - tau gradN.grad dp ) w dv,
+    hydro = kappa tr(eps) (so the dkappa terms of hydro cancel except p dkappa/kappa^2),
+    tau = mult h^2/(2 mu), d tau = -tau dmu/mu, with (dlam, dmu) the direction of the Lame
+    constants for ``dp`` (dual-number Jacobian of elastic_constants.py:54-104)."""
+    elem_eq = np.asarray(elem_eq, dtype=np.int64); elem_eq_p = np.asarray(elem_eq_p, dtype=np.int64)
+    n_e, n_ip, n_b, _ = grad_N.shape
+    U = np.asarray(U)
+    base = block_jvp(prob_eval, elem_eq, U, xi_prev, xi_state, grad_N, det, quad_w, dp, dxi_prev,
+                     nthreads=nthreads, dU=dU, _want_dsigma=True)
+    lj = oracle_c.lame(int(prob_eval.cfg[2]), float(prob_eval.mat[0]), float(prob_eval.mat[1]))
+    lam, mu = lj[:2]
+    kappa = lam + 2.0 * mu / 3.0
+    dlam = dmu = 0.0
+    for c, pid in enumerate(np.asarray(prob_eval.active_pid)):
+        if pid in (oracle_c.PID["EL0"], oracle_c.PID["EL1"]):
+            k = int(pid) - oracle_c.PID["EL0"]
+            dlam += lj[2 + k] * float(np.asarray(dp)[c]); dmu += lj[4 + k] * float(np.asarray(dp)[c])
+    dkappa = dlam + 2.0 * dmu / 3.0
+    tau = stab_mult * 0.5 * np.asarray(h) ** 2 / mu
+    dtau = -tau * dmu / mu
+    U_e = U[elem_eq].reshape(n_e, n_b, 3); p_e = U[elem_eq_p]
+    dU_e = np.zeros_like(U_e) if dU is None else np.asarray(dU)[elem_eq].reshape(n_e, n_b, 3)
+    dp_e = np.zeros_like(p_e) if dU is None else np.asarray(dU)[elem_eq_p]
+    I3 = np.eye(3)
+    dR_u = np.zeros((n_e, n_b, 3)); dR_p = np.zeros((n_e, n_b))
+    for ip in range(n_ip):
+        gN, Nip = grad_N[:, ip], N[ip]
+        ds = np.moveaxis(base["dsigma"][ip][_V], -1, 0)                   # (n_e, 3, 3)
+        dpi = dp_e @ Nip
+        dsm = ds - (np.trace(ds, axis1=1, axis2=2) / 3.0)[:, None, None] * I3 - dpi[:, None, None] * I3
+        wdv = quad_w[ip] * det[:, ip]
+        dR_u += np.einsum("eaj,eji->eai", gN, dsm) * wdv[:, None, None]
+        p = p_e @ Nip
+        tre = np.trace(np.einsum("eak,eaj->ekj", U_e, gN), axis1=1, axis2=2)
+        dtre = np.trace(np.einsum("eak,eaj->ekj", dU_e, gN), axis1=1, axis2=2)
+        hydro, dhydro = kappa * tre, dkappa * tre + kappa * dtre
+        grad_p = np.einsum("ea,eaj->ej", p_e, gN); grad_dp = np.einsum("ea,eaj->ej", dp_e, gN)
+        dR_p += ((-(dpi + dhydro) / kappa + (p + hydro) * dkappa / kappa ** 2)[:, None] * Nip[None, :]
+                 - dtau[:, None] * np.einsum("eaj,ej->ea", gN, grad_p)
+                 - tau[:, None] * np.einsum("eaj,ej->ea", gN, grad_dp)) * wdv[:, None]
+    return {"R_elem": dR_u.reshape(n_e, n_b * 3), "R_p_elem": dR_p, "xi": base["xi"]}

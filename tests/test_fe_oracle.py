@@ -214,3 +214,55 @@ def test_block_jvp_oracle_vs_central_fd():
         fd_x = (up["xi"] - dn["xi"]) / (2 * h)
         assert np.abs(jv["R_elem"] - fd_R).max() < 1e-6 * np.abs(fd_R).max()
         assert np.abs(jv["xi"] - fd_x).max() < 1e-6 * np.abs(fd_x).max()
+
+
+def test_block_jvp_mixed_oracle_vs_central_fd():
+    """The mixed u-p K6 oracle (both residual blocks, parameters entering R_p through kappa
+    and mu) against central differences of the Newton-running mixed primal block."""
+    from cmad_b200 import Parameters
+    from tests.helpers import param_tree
+    import copy
+    values, act, tr = param_tree("J2", active=("E", "nu", "D", "S", "Y"))
+    P = Parameters(values, act, tr)
+    nodes, conn = fe_mesh.structured_hex_mesh((2, 1, 1))
+    rng = np.random.default_rng(5)
+    for family in ("hex8", "tet4"):
+        cn = conn if family == "hex8" else fe_mesh.split_hex_to_tets(conn)
+        arr = fe_mesh.block_arrays(nodes, cn, mixed=True)
+        n_e, n_ip = arr.n_elems, arr.n_ip
+        nu_dofs = 3 * nodes.shape[0]
+        U = np.zeros(arr.n_dofs)
+        U[:nu_dofs] = fe_mesh.synthetic_displacement(nodes, t=2.0, seed=3, noise=4e-4)
+        U[nu_dofs:] = 30.0 * rng.standard_normal(arr.n_dofs - nu_dofs)
+        eq, eqp = arr.elem_eq.numpy(), arr.elem_eq_p.numpy()
+        geo = (arr.grad_N.numpy(), arr.N.numpy(), arr.det.numpy(), arr.quad_w.numpy(), arr.h.numpy())
+        tight = dict(max_iters=30, abs_tol=1e-14, rel_tol=1e-14)
+
+        def primal(vals, xi_prev, Uv):
+            prob = oc.describe(vals, P.active_idx, newton_mode="traced", strain_comps=9, **tight)
+            return fe_oracle.assemble_block_mixed(prob, eq, eqp, Uv, xi_prev, *geo, stab_mult=0.7, want_K=False)
+
+        xi_prev = primal(values, np.zeros((n_e, n_ip, 7)), U)["xi"] * 0.5
+        base = primal(values, xi_prev, U)
+        dp = np.array([3.0e3, 0.01, 1.5, -7.0, 4.0])
+        dxp = 1e-4 * rng.standard_normal(xi_prev.shape)
+        dxp[:, :, 6] = np.abs(dxp[:, :, 6])
+        dUv = 1e-4 * rng.standard_normal(U.shape)
+        dUv[nu_dofs:] *= 1e4
+        prob_eval = oc.describe(values, P.active_idx, newton_mode="imperative", strain_comps=9, max_iters=0)
+
+        def shifted(hh, with_U):
+            v = copy.deepcopy(values)
+            v["elastic"]["E"] += hh * dp[0]; v["elastic"]["nu"] += hh * dp[1]
+            vo = v["plastic"]["flow stress"]["hardening"]["voce"]
+            vo["D"] += hh * dp[2]; vo["S"] += hh * dp[3]
+            v["plastic"]["flow stress"]["initial yield"]["Y"] += hh * dp[4]
+            return primal(v, xi_prev + hh * dxp, U + hh * dUv if with_U else U)
+        hh = 1e-5
+        for with_U in (False, True):
+            jv = fe_oracle.block_jvp_mixed(prob_eval, eq, eqp, U, xi_prev, base["xi"], *geo, dp, dxp,
+                                           stab_mult=0.7, dU=dUv if with_U else None)
+            up, dn = shifted(hh, with_U), shifted(-hh, with_U)
+            for k, ku in (("R_elem", "R_u"), ("R_p_elem", "R_p"), ("xi", "xi")):
+                fd = (up[ku] - dn[ku]) / (2 * hh)
+                assert np.abs(jv[k] - fd).max() < 2e-6 * np.abs(fd).max(), (family, with_U, k)

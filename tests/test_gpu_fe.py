@@ -521,3 +521,95 @@ def test_fe_two_pass_deferral_keeps_iterates_and_counts(cuda_device, family):
                 assert torch.equal(o[k], base[k]), (family, K, k)
             else:
                 assert rel_err(o[k].cpu().numpy(), base[k].cpu().numpy()) < 1e-12, (family, K, k)
+
+
+@pytest.mark.parametrize("family", ["tet4", "hex8"])
+@pytest.mark.parametrize("kind", ["J2", "hosford"])
+def test_mixed_block_jvp_and_vjp(cuda_device, family, kind):
+    """K6 for the mixed u-p block: the JVP of both residual blocks (momentum rows through
+    dev(d cauchy) - dp I, pressure rows through kappa, mu and the (u, p) direction) against
+    the oracle (itself FD-checked in the CPU suite), K dU against the assembled mixed tangent,
+    and the VJP through the adjoint identity over both blocks."""
+    from cmad_b200 import Parameters, active_param_ids
+    if kind == "J2":
+        values, act, tr = param_tree("J2", active=("E", "nu", "D", "S", "Y"))
+    else:
+        values, act, tr = param_tree("hosford", a=6.0, active=("E", "nu", "D", "S", "Y"))
+    P = Parameters(values, act, tr)
+    pid = active_param_ids(P)
+    nodes, conn = _mesh(family, (3, 2, 2))
+    arr_h = fe_mesh.block_arrays(nodes, conn, mixed=True); arr = arr_h.to(cuda_device)
+    mat = material_from_values(values)
+    nw = fe.fe_newton_settings(**NEWTON)
+    rng = np.random.default_rng(11)
+    n_e, n_ip, n_b = arr.n_elems, arr.n_ip, arr.n_basis
+    nud = 3 * nodes.shape[0]
+    stab = 0.7
+
+    def Uvec(t, seed):
+        U = np.zeros(arr.n_dofs)
+        U[:nud] = fe_mesh.synthetic_displacement(nodes, t, seed=seed, ramp=0.004, noise=4e-4)
+        U[nud:] = 30.0 * np.random.default_rng(seed).standard_normal(arr.n_dofs - nud)
+        return torch.from_numpy(U).to(cuda_device)
+    U1, U2 = Uvec(1.0, 1), Uvec(2.0, 2)
+    xi0 = torch.zeros((n_e, n_ip, 7), dtype=torch.float64, device=cuda_device)
+    _, _, xi1 = fe.assemble_element_block_mixed(mat, nw, arr, U1, xi0, stab_mult=stab, want_K=False)
+    _, vals, xi2 = fe.assemble_element_block_mixed(mat, nw, arr, U2, xi1, stab_mult=stab)
+    assert float((xi2[..., 6] - xi1[..., 6]).max()) > 0.0                # plastic somewhere
+    scale = np.array([3e3, 0.01, 1.5, 7.0, 4.0])
+    dp = rng.standard_normal(len(pid)) * scale
+    dxp = torch.from_numpy(1e-4 * rng.standard_normal((n_e, n_ip, 7))).to(cuda_device)
+    dUn = 1e-4 * rng.standard_normal(arr.n_dofs); dUn[nud:] *= 1e4
+    dUv = torch.from_numpy(dUn).to(cuda_device)
+    prob_eval = oc.describe(values, P.active_idx, newton_mode="imperative", strain_comps=9, max_iters=0)
+    eq, eqp = arr_h.elem_eq.numpy(), arr_h.elem_eq_p.numpy()
+    geo = (arr_h.grad_N.numpy(), arr_h.N.numpy(), arr_h.det.numpy(), arr_h.quad_w.numpy(), arr_h.h.numpy())
+    args = (prob_eval, eq, eqp, U2.cpu().numpy(), xi1.cpu().numpy(), xi2.cpu().numpy()) + geo
+    outs = {}
+    for name, dxx, dUU in (("plain", dxp, None), ("nodxp", None, None), ("withU", dxp, dUv)):
+        o = fe.fe_block_jvp(mat, arr, U2, xi1, xi2, pid, dp, dxx, outputs=("xi", "R_elem", "R_global"),
+                            dU=dUU, stab_mult=stab)
+        r = fe_oracle.block_jvp_mixed(*args, dp, None if dxx is None else dxx.cpu().numpy(), stab_mult=stab,
+                                      dU=None if dUU is None else dUU.cpu().numpy())
+        torch.cuda.synchronize()
+        for k in ("xi", "R_elem", "R_p_elem"):
+            assert rel_err(o[k].cpu().numpy(), r[k]) < 1e-9, (name, k, rel_err(o[k].cpu().numpy(), r[k]))
+        Rg = np.zeros(arr.n_dofs)
+        np.add.at(Rg, eq.reshape(-1), r["R_elem"].reshape(-1)); np.add.at(Rg, eqp.reshape(-1), r["R_p_elem"].reshape(-1))
+        assert rel_err(o["R_global"].cpu().numpy(), Rg) < 1e-9
+        outs[name] = o
+    # the displacement/pressure direction adds K dU over all four blocks of the mixed tangent
+    nu_, np_ = 3 * n_b, n_b
+    sz = [n_e * nu_ * nu_, n_e * nu_ * np_, n_e * np_ * nu_, n_e * np_ * np_]
+    of = np.concatenate([[0], np.cumsum(sz)])
+    Kuu = vals[of[0]:of[1]].view(n_e, nu_, nu_); Kup = vals[of[1]:of[2]].view(n_e, nu_, np_)
+    Kpu = vals[of[2]:of[3]].view(n_e, np_, nu_); Kpp = vals[of[3]:of[4]].view(n_e, np_, np_)
+    du_e, dp_e = dUv[arr.elem_eq.long()], dUv[arr.elem_eq_p.long()]
+    KdU_u = torch.einsum("eij,ej->ei", Kuu, du_e) + torch.einsum("eij,ej->ei", Kup, dp_e)
+    KdU_p = torch.einsum("eij,ej->ei", Kpu, du_e) + torch.einsum("eij,ej->ei", Kpp, dp_e)
+    assert rel_err((outs["withU"]["R_elem"] - outs["plain"]["R_elem"]).cpu().numpy(), KdU_u.cpu().numpy()) < 1e-8
+    assert rel_err((outs["withU"]["R_p_elem"] - outs["plain"]["R_p_elem"]).cpu().numpy(), KdU_p.cpu().numpy()) < 1e-8
+    # ---- VJP: adjoint identity against the oracle JVP, bit-reproducible
+    Rbar = torch.from_numpy(rng.standard_normal(arr.n_dofs)).to(cuda_device)
+    Rbar[nud:] *= 1e3                              # the pressure rows are ~1e-3 of the momentum rows
+    xibar = torch.from_numpy(rng.standard_normal((n_e, n_ip, 7))).to(cuda_device)
+    pbar, xbp = fe.fe_block_vjp(mat, arr, U2, xi1, xi2, pid, Rbar, xibar, stab_mult=stab)
+    pbar2, xbp2 = fe.fe_block_vjp(mat, arr, U2, xi1, xi2, pid, Rbar, xibar, stab_mult=stab)
+    torch.cuda.synchronize()
+    assert torch.equal(pbar, pbar2) and torch.equal(xbp, xbp2)
+    Rb, xb = Rbar.cpu().numpy(), xibar.cpu().numpy()
+    for trial in range(3):
+        dpt = rng.standard_normal(len(pid)) * scale
+        dxt = 1e-4 * rng.standard_normal((n_e, n_ip, 7))
+        jv = fe_oracle.block_jvp_mixed(*args, dpt, dxt, stab_mult=stab)
+        dR = np.zeros(arr.n_dofs)
+        np.add.at(dR, eq.reshape(-1), jv["R_elem"].reshape(-1)); np.add.at(dR, eqp.reshape(-1), jv["R_p_elem"].reshape(-1))
+        lhs = float(Rb @ dR + (xb * jv["xi"]).sum())
+        rhs = float(pbar.cpu().numpy() @ dpt + (xbp.cpu().numpy() * dxt).sum())
+        terms = abs(Rb[:nud] @ dR[:nud]) + abs(Rb[nud:] @ dR[nud:]) + abs((xb * jv["xi"]).sum())
+        assert abs(lhs - rhs) < 1e-9 * terms, (trial, lhs, rhs)
+    # the pressure rows really contribute: dropping them changes the elastic entries of pbar
+    Rb0 = Rbar.clone(); Rb0[nud:] = 0.0
+    pbar_u, _ = fe.fe_block_vjp(mat, arr, U2, xi1, xi2, pid, Rb0, xibar, stab_mult=stab)
+    assert not torch.allclose(pbar_u[:2], pbar[:2], rtol=1e-6, atol=0.0)
+    assert torch.allclose(pbar_u[2:], pbar[2:], rtol=1e-12, atol=0.0)
