@@ -32,6 +32,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--exchange", default="interface", choices=["interface", "allreduce"],
                     help="halo exchange of the interface dofs only, or all-reduce of the whole residual")
+    ap.add_argument("--mixed", action="store_true",
+                    help="mixed u-p formulation (examples/mixed_plastic.yaml-style, BASELINE configs[4]): "
+                         "K3-mixed + pressure block + K5 over [R_u | R_p] + exchange + K6-mixed VJP")
     args = ap.parse_args()
 
     import torch
@@ -53,8 +56,8 @@ def main():
     n_total = conn.shape[0]
     per = n_total // world                         # element e = i*ny*nz + ...: contiguous slabs in x
     lo, hi = rank * per, (rank + 1) * per
-    arr = fe_mesh.block_arrays(nodes, conn[lo:hi], device=dev)
-    arr.n_dofs = nodes.shape[0] * 3
+    arr = fe_mesh.block_arrays(nodes, conn[lo:hi], device=dev, mixed=args.mixed)
+    arr.n_dofs = nodes.shape[0] * (4 if args.mixed else 3)
     values = materials("J2")
     const = lambda t, c: {k: const(v, c) for k, v in t.items()} if isinstance(t, dict) else c
     active = const(values, False)
@@ -65,31 +68,42 @@ def main():
     mat = material_from_values(values)
     nw = fe.fe_newton_settings()
     h = 1.0 / d
-    U = torch.from_numpy(fe_mesh.synthetic_displacement(nodes, 2.0, seed=44, ramp=0.003, noise=1e-3 * h)).to(dev)
+    Uh = np.zeros(arr.n_dofs)
+    Uh[:nodes.shape[0] * 3] = fe_mesh.synthetic_displacement(nodes, 2.0, seed=44, ramp=0.003, noise=1e-3 * h)
+    if args.mixed:
+        Uh[nodes.shape[0] * 3:] = 30.0 * np.random.default_rng(6).standard_normal(nodes.shape[0])
+    U = torch.from_numpy(Uh).to(dev)
     lam = torch.from_numpy(np.random.default_rng(5).standard_normal(arr.n_dofs)).to(dev)
     n_e, n_ip = arr.n_elems, arr.n_ip
     xi0 = torch.zeros((n_e, n_ip, 7), dtype=torch.float64, device=dev)
-    r_plan = fe.SegmentPlan(arr.elem_eq.cpu().numpy().reshape(-1), arr.n_dofs, device=dev)
+    r_plan = fe.mixed_r_plan(arr, device=dev) if args.mixed else \
+        fe.SegmentPlan(arr.elem_eq.cpu().numpy().reshape(-1), arr.n_dofs, device=dev)
     out = {"xi": torch.empty_like(xi0),
            "R_elem": torch.empty((n_e, arr.n_basis * 3), dtype=torch.float64, device=dev),
            "K_elem": torch.empty((n_e, arr.n_basis * 3, arr.n_basis * 3), dtype=torch.float64, device=dev)}
     R = torch.empty(arr.n_dofs, dtype=torch.float64, device=dev)
-    halo = fe.InterfaceExchange(arr.elem_eq, arr.n_dofs) if args.exchange == "interface" else None
+    halo = fe.InterfaceExchange(arr.elem_eq, arr.n_dofs, extra_eq=arr.elem_eq_p if args.mixed else None) \
+        if args.exchange == "interface" else None
+    stab = 1.0 if args.mixed else None
 
     ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + args.warmup)]
           for k in ("t0", "asm", "red", "vjp", "end")}
 
     def step(k):
         ev["t0"][k].record()
-        fe.fe_block_launch(mat, nw, arr, U, xi0, ("xi", "R_elem", "K_elem"), out)
-        r_plan.sum(out["R_elem"].reshape(-1), out=R)
+        if args.mixed:
+            Rm, _, xis = fe.assemble_element_block_mixed(mat, nw, arr, U, xi0, stab_mult=stab, r_plan=r_plan)
+            R.copy_(Rm); out["xi"] = xis
+        else:
+            fe.fe_block_launch(mat, nw, arr, U, xi0, ("xi", "R_elem", "K_elem"), out)
+            r_plan.sum(out["R_elem"].reshape(-1), out=R)
         ev["asm"][k].record()
         if halo is not None:
             halo.reduce(R)                                              # NCCL all-reduce of the interface dofs
         else:
             fe.reduce_residual(R)                                       # NCCL all-reduce of the whole R
         ev["red"][k].record()
-        pbar, _ = fe.fe_block_vjp(mat, arr, U, xi0, out["xi"], pid, lam, None)   # incl. all-reduce of pbar
+        pbar, _ = fe.fe_block_vjp(mat, arr, U, xi0, out["xi"], pid, lam, None, stab_mult=stab)   # incl. all-reduce of pbar
         ev["end"][k].record()
         return pbar
 
@@ -112,7 +126,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         tot, asm, red, vjp = (float(x) for x in t)
-        print(json.dumps({"family": args.family, "n_gpus": world, "elements_per_gpu": n_e, "elements_total": n_total,
+        print(json.dumps({"family": args.family, "mixed": bool(args.mixed), "n_gpus": world, "elements_per_gpu": n_e, "elements_total": n_total,
                           "n_dofs": arr.n_dofs, "scaling": "weak", "steps": args.steps, "warmup": args.warmup,
                           "ms_step": tot, "ms_assemble_K3_K5": asm, "ms_allreduce_R": red,
                           "ms_vjp_plus_allreduce_grad": vjp, "R_bytes": arr.n_dofs * 8,

@@ -250,6 +250,28 @@ def cuda_jvp(material, arrays, r_plan, active_pid):
     return jvp
 
 
+def cuda_jvp_mixed(material, arrays, r_plan, active_pid, stab_mult: float = 1.0):
+    """``jvp`` callable of :func:`fe_direct_gradient` for the mixed u-p formulation (K6 over
+    both residual blocks); ``r_plan`` = :func:`cmad_b200.fe.mixed_r_plan`."""
+    import torch
+    from . import fe
+    dev = arrays.grad_N.device
+    pid = np.ascontiguousarray(active_pid, dtype=np.int32)
+    n_e, nu, npd = arrays.n_elems, 3 * arrays.n_basis, arrays.n_basis
+
+    def jvp(U, xi_prev, xi_state, c, dxi_prev, dU):
+        Ud = torch.from_numpy(np.ascontiguousarray(U)).to(dev)
+        dp = np.zeros(len(pid)); dp[c] = 1.0
+        dUd = torch.from_numpy(np.ascontiguousarray(dU)).to(dev) if dU is not None else None
+        R_elem = torch.empty(n_e * (nu + npd), dtype=torch.float64, device=dev)          # [dR_u | dR_p]
+        o = fe.fe_block_jvp(material, arrays, Ud, xi_prev, xi_state, pid, dp, dxi_prev, dU=dUd,
+                            stab_mult=stab_mult,
+                            out={"R_elem": R_elem[:n_e * nu].view(n_e, nu), "R_p_elem": R_elem[n_e * nu:].view(n_e, npd)})
+        return r_plan.sum(R_elem).cpu().numpy(), o["xi"]
+
+    return jvp
+
+
 def cuda_assembler(material, newton, arrays, r_plan, k_plan, outputs=None):
     """``assemble`` callable over the CUDA kernels for one element block: K3 (R_e, K_e,
     xi) + K5 (deterministic R scatter, COO dedup); ``xi`` stays on the device."""

@@ -402,3 +402,97 @@ def test_cuda_mixed_driver_matches_oracle_driver_and_known_answer(cuda_device, f
     p = Ug[-1][3 * nodes.shape[0]:]
     np.testing.assert_allclose(p, -sigma_axial / 3.0, rtol=1e-5)
     np.testing.assert_allclose(xig.cpu().numpy()[..., 6], 0.05, rtol=1e-5)
+
+
+# ---------------------------------------------------------------- mixed u-p FE gradient (config 5 style)
+def _mixed_gradient_problem(div=2, family="hex8"):
+    from cmad_b200 import Parameters
+    from tests.helpers import param_tree
+    values, act, tr = param_tree("J2", active=("E", "nu", "D", "S", "Y"))
+    P = Parameters(values, act, tr)
+    nodes, arr, bcs, pattern, scatter = mixed_uniaxial_cube(div, family)
+    rng = np.random.default_rng(4)
+    inner = np.all((nodes > 1e-9) & (nodes < 1 - 1e-9), axis=1)
+    nodes = nodes.copy(); nodes[inner] += 0.08 / div * rng.uniform(-1, 1, size=(inner.sum(), 3))
+    conn = fe_mesh.structured_hex_mesh((div,) * 3)[1]
+    if family == "tet4":
+        conn = fe_mesh.split_hex_to_tets(conn)
+    arr = fe_mesh.block_arrays(nodes, conn, mixed=True)
+    return values, P, nodes, arr, bcs, pattern, scatter
+
+
+def oracle_jvp_mixed(values, P, arr):
+    prob_eval = oc.describe(values, P.active_idx, newton_mode="imperative", strain_comps=9, max_iters=0)
+    eq, eqp = arr.elem_eq.numpy(), arr.elem_eq_p.numpy()
+    geo = (arr.grad_N.numpy(), arr.N.numpy(), arr.det.numpy(), arr.quad_w.numpy(), arr.h.numpy())
+    na = len(prob_eval.active_pid)
+
+    def jvp(U, xi_prev, xi_state, c, dxi_prev, dU):
+        dp = np.zeros(na); dp[c] = 1.0
+        o = fe_oracle.block_jvp_mixed(prob_eval, eq, eqp, U, xi_prev, xi_state, *geo, dp, dxi_prev, dU=dU)
+        dR = np.zeros(arr.n_dofs)
+        np.add.at(dR, eq.reshape(-1), o["R_elem"].reshape(-1)); np.add.at(dR, eqp.reshape(-1), o["R_p_elem"].reshape(-1))
+        return dR, o["xi"]
+    return jvp
+
+
+def test_mixed_direct_gradient_vs_central_fd_of_the_trajectory():
+    """`cmad gradient` on a mixed_plastic.yaml-style deck, restated: dJ/dp through the load
+    steps of the mixed u-p formulation by forward sensitivities (K6 over both residual
+    blocks - the elastic parameters also enter the pressure rows), against central
+    differences of J over re-solved trajectories (all over the oracle assembler)."""
+    import copy
+    values, P, nodes, arr, bcs, pattern, scatter = _mixed_gradient_problem()
+    ts = np.array([0.0, 0.004, 0.008])
+    q, dq = _qois(arr, ts)
+    tight = {"abs tol": 1e-13, "rel tol": 1e-13, "max iters": 15}
+    z = lambda: np.zeros((arr.n_elems, arr.n_ip, 7))
+    J, g = drv.fe_direct_gradient(oracle_assembler_mixed(values, arr, scatter, len(pattern.rows)),
+                                  oracle_jvp_mixed(values, P, arr), pattern, bcs, np.zeros(arr.n_dofs), z(),
+                                  lambda c: z(), ts, 5, tight, q, dq)
+
+    def J_of(v):
+        return drv.fe_quasistatic_drive(oracle_assembler_mixed(v, arr, scatter, len(pattern.rows)), pattern, bcs,
+                                        np.zeros(arr.n_dofs), z(), ts, tight, q)[2]
+    assert abs(J_of(values) - J) < 1e-14 * abs(J)
+    paths = [("elastic", "E"), ("elastic", "nu"), ("plastic", "flow stress", "hardening", "voce", "D"),
+             ("plastic", "flow stress", "hardening", "voce", "S"), ("plastic", "flow stress", "initial yield", "Y")]
+    assert np.abs(g).min() > 0
+    for c, path in enumerate(paths):
+        def bump(h):
+            v = copy.deepcopy(values); d = v
+            for k in path[:-1]:
+                d = d[k]
+            d[path[-1]] = d[path[-1]] * (1 + h)
+            return J_of(v)
+        h = 1e-5
+        d = values
+        for k in path:
+            d = d[k]
+        fd = (bump(h) - bump(-h)) / (2 * h * d)
+        assert abs(fd - g[c]) < 5e-5 * abs(g[c]) + 1e-16, (path, fd, g[c])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("family", ["hex8", "tet4"])
+def test_cuda_mixed_direct_gradient_matches_oracle(cuda_device, family):
+    import torch
+    from cmad_b200 import active_param_ids, fe, material_from_values
+    values, P, nodes, arr, bcs, pattern, scatter = _mixed_gradient_problem(3, family)
+    ts = np.array([0.0, 0.004, 0.008])
+    q, dq = _qois(arr, ts)
+    z = lambda: np.zeros((arr.n_elems, arr.n_ip, 7))
+    Jo, go = drv.fe_direct_gradient(oracle_assembler_mixed(values, arr, scatter, len(pattern.rows)),
+                                    oracle_jvp_mixed(values, P, arr), pattern, bcs, np.zeros(arr.n_dofs), z(),
+                                    lambda c: z(), ts, 5, None, q, dq)
+    arr_d = arr.to(cuda_device)
+    mat = material_from_values(values)
+    r_plan = fe.mixed_r_plan(arr, device=cuda_device)
+    k_plan = fe.SegmentPlan(scatter, len(pattern.rows), device=cuda_device)
+    zd = lambda: torch.zeros((arr.n_elems, arr.n_ip, 7), dtype=torch.float64, device=cuda_device)
+    Jg, gg = drv.fe_direct_gradient(
+        drv.cuda_assembler_mixed(mat, fe.fe_newton_settings(**LOCAL_NEWTON), arr_d, r_plan, k_plan),
+        drv.cuda_jvp_mixed(mat, arr_d, r_plan, active_param_ids(P)), pattern, bcs, np.zeros(arr.n_dofs), zd(),
+        lambda c: zd(), ts, 5, None, q, dq)
+    assert abs(Jg - Jo) < 1e-10 * abs(Jo)
+    assert np.abs(gg - go).max() < 1e-8 * np.abs(go).max(), (gg, go)
