@@ -15,7 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "lib", "libcmad_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
-SOURCES = ["api.cu", "mp_update.cu", "mp_update_j2.cu", "mp_update_dt.cu", "mp_update_rate.cu", "elastic_update.cu", "mp_sens.cu", "mp_sens_dt.cu", "mp_history.cu",
+SOURCES = ["api.cu", "mp_update.cu", "mp_update_j2.cu", "mp_update_dt.cu", "mp_update_rate.cu", "elastic_update.cu", "mp_sens.cu", "mp_sens_dt.cu", "mp_hess.cu", "mp_history.cu",
            "fe_block.cu", "fe_tet4.cu", "fe_hex8.cu", "fe_mixed.cu", "fe_post.cu", "fe_vjp.cu", "fe_scatter.cu"]
 
 # ---- enums (mirror include/cmad_b200.h) ---------------------------------
@@ -155,6 +155,9 @@ def lib() -> C.CDLL:
     obj_args = [C.POINTER(Material), C.POINTER(C.c_int32), C.c_int32, C.POINTER(MpHistory), C.c_void_p]
     L.cmadx_mp_objective_adjoint.argtypes = obj_args
     L.cmadx_mp_objective_direct.argtypes = obj_args
+    L.cmadx_mp_objective_hessian.argtypes = obj_args[:-1] + [C.c_int32, C.c_void_p]
+    L.cmadx_mp_hessian_workspace_bytes.restype = C.c_int64
+    L.cmadx_mp_hessian_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int32]
     L.cmadx_fe_block_assemble.argtypes = [C.POINTER(Material), C.POINTER(Newton),
                                           C.POINTER(FeBlock), C.c_void_p]
     L.cmadx_fe_block_assemble_mixed.argtypes = [C.POINTER(Material), C.POINTER(Newton),

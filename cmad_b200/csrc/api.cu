@@ -11,6 +11,7 @@
 
 #include "fe_block.cuh"
 #include "mp_update.cuh"
+#include "mp_sens.cuh"
 
 namespace cmadx {
 struct EmbeddedPlan;
@@ -27,13 +28,6 @@ namespace cmadx {
 int64_t fe_vjp_blocks(int64_t npts);
 cudaError_t launch_fe_block_vjp(const FeArgs& A, const double* Rbar, const double* xibar, double* partials,
                                 double* pbar, cudaStream_t s);
-struct SensArgs {
-    DevMat m;
-    int n_active;
-    int pid[CMADX_MAX_ACTIVE];
-    cmadx_mp_history_t h;
-    double* partials;
-};
 struct HistArgs {
     DevMat m;
     DevNewton nw;
@@ -46,6 +40,8 @@ cudaError_t launch_mp_history(const HistArgs& A, bool radial, cudaStream_t s);
 cudaError_t launch_mp_sens(const SensArgs& A, bool adjoint, cudaStream_t stream);
 cudaError_t launch_mp_sens_dt(const SensArgs& A, int def_type, bool adjoint, cudaStream_t stream);
 int64_t sens_blocks(int64_t n);
+int64_t hess_blocks(int64_t n);
+cudaError_t launch_mp_hess(const SensArgs& A, double* pair_sums, double* H_out, cudaStream_t stream);
 }  // namespace cmadx
 
 namespace cmadx {
@@ -60,26 +56,37 @@ int cuda_fail(cudaError_t e) {
 
 namespace {
 
-// minimal 2-direction forward dual for d(lambda, mu)/d(elastic pair)
+// minimal 2-direction, second-order forward dual for the first and second derivatives of
+// (lambda, mu) w.r.t. the given elastic pair (the Hessian path needs d2/dpair2)
 struct D2 {
-    double v, a, b;
+    double v, a, b, aa, ab, bb;
 };
-inline D2 C(double c) { return {c, 0, 0}; }
-inline D2 operator+(D2 x, D2 y) { return {x.v + y.v, x.a + y.a, x.b + y.b}; }
-inline D2 operator-(D2 x, D2 y) { return {x.v - y.v, x.a - y.a, x.b - y.b}; }
-inline D2 operator*(D2 x, D2 y) { return {x.v * y.v, x.a * y.v + x.v * y.a, x.b * y.v + x.v * y.b}; }
+inline D2 C(double c) { return {c, 0, 0, 0, 0, 0}; }
+inline D2 operator+(D2 x, D2 y) { return {x.v + y.v, x.a + y.a, x.b + y.b, x.aa + y.aa, x.ab + y.ab, x.bb + y.bb}; }
+inline D2 operator-(D2 x, D2 y) { return {x.v - y.v, x.a - y.a, x.b - y.b, x.aa - y.aa, x.ab - y.ab, x.bb - y.bb}; }
+inline D2 operator*(D2 x, D2 y) {
+    return {x.v * y.v, x.a * y.v + x.v * y.a, x.b * y.v + x.v * y.b,
+            x.aa * y.v + 2.0 * x.a * y.a + x.v * y.aa,
+            x.ab * y.v + x.a * y.b + x.b * y.a + x.v * y.ab,
+            x.bb * y.v + 2.0 * x.b * y.b + x.v * y.bb};
+}
+// g(u) with derivatives g1, g2 at u.v
+inline D2 chain(D2 u, double g, double g1, double g2) {
+    return {g, g1 * u.a, g1 * u.b, g1 * u.aa + g2 * u.a * u.a, g1 * u.ab + g2 * u.a * u.b,
+            g1 * u.bb + g2 * u.b * u.b};
+}
 inline D2 operator/(D2 x, D2 y) {
-    const double q = x.v / y.v;
-    return {q, (x.a - q * y.a) / y.v, (x.b - q * y.b) / y.v};
+    const double r = 1.0 / y.v;
+    return x * chain(y, r, -r * r, 2.0 * r * r * r);
 }
 inline D2 dsqrt(D2 x) {
     const double s = std::sqrt(x.v);
-    return {s, 0.5 * x.a / s, 0.5 * x.b / s};
+    return chain(x, s, 0.5 / s, -0.25 / (s * x.v));
 }
 
 // any two of {E, nu, mu, kappa, lambda} -> Lame pair (elastic_constants.py:54-104)
 int lame_pair(int pair, double e0, double e1, D2& lam, D2& mu) {
-    const D2 p{e0, 1, 0}, q{e1, 0, 1};
+    const D2 p{e0, 1, 0, 0, 0, 0}, q{e1, 0, 1, 0, 0, 0};
     switch (pair) {
     case CMADX_EL_E_NU:
         lam = p * q / ((C(1) + q) * (C(1) - C(2) * q)); mu = p / (C(2) * (C(1) + q)); break;
@@ -121,6 +128,8 @@ int make_dev_mat(const cmadx_material_t* mat, DevMat* o) {
     o->two_mu = 2.0 * mu.v;
     o->inv_two_mu = 1.0 / o->two_mu;
     o->dlam[0] = lam.a; o->dlam[1] = lam.b; o->dmu[0] = mu.a; o->dmu[1] = mu.b;
+    o->d2lam[0] = lam.aa; o->d2lam[1] = lam.ab; o->d2lam[2] = lam.bb;
+    o->d2mu[0] = mu.aa; o->d2mu[1] = mu.ab; o->d2mu[2] = mu.bb;
     o->model = mat->model;
     if (mat->model == CMADX_MODEL_SMALL_ELASTIC_PLASTIC || mat->model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC) {
         if (mat->yield < CMADX_YIELD_J2 || mat->yield > CMADX_YIELD_HOSFORD) return CMADX_EINVAL;
@@ -587,6 +596,8 @@ static int objective(const cmadx_material_t* mat, const int32_t* active_pid, int
     A.n_active = n_active;
     A.h = *hist;
     A.partials = hist->workspace;
+    A.phi_hist = nullptr;
+    A.hess_flags = 0;
     const int dt = history_def_type(hist);
     cudaError_t e = (dt == CMADX_DEF_FULL_3D) ? launch_mp_sens(A, adjoint, (cudaStream_t)stream)
                                               : launch_mp_sens_dt(A, dt, adjoint, (cudaStream_t)stream);
@@ -603,6 +614,49 @@ int cmadx_mp_objective_adjoint(const cmadx_material_t* mat, const int32_t* activ
 int cmadx_mp_objective_direct(const cmadx_material_t* mat, const int32_t* active_pid,
                               int32_t n_active, const cmadx_mp_history_t* hist, void* stream) {
     return objective(mat, active_pid, n_active, hist, stream, false);
+}
+
+// workspace layout of the Hessian path: [phi_hist (N+1) x 7 x ld][partials][pair sums]
+static int64_t hess_partials_doubles(int64_t n, int32_t n_active) {
+    const int64_t npairs = (int64_t)n_active * (n_active + 1) / 2;
+    const int64_t a = (sens_blocks(n) + 1) * (1 + n_active), b = (hess_blocks(n) + 1) * npairs;
+    return a > b ? a : b;
+}
+
+int64_t cmadx_mp_hessian_workspace_bytes(int64_t n, int64_t ld, int32_t nsteps, int32_t n_active) {
+    if (n < 0 || ld < n || nsteps < 0 || n_active < 0 || n_active > CMADX_MAX_ACTIVE) return -1;
+    const int64_t npairs = (int64_t)n_active * (n_active + 1) / 2;
+    return (int64_t)sizeof(double) * ((int64_t)(nsteps + 1) * 7 * ld + hess_partials_doubles(n, n_active) + npairs + 1);
+}
+
+int cmadx_mp_objective_hessian(const cmadx_material_t* mat, const int32_t* active_pid,
+                               int32_t n_active, const cmadx_mp_history_t* hist, int32_t flags,
+                               void* stream) {
+    SensArgs A;
+    if (flags & ~CMADX_HESS_F_REFERENCE_QOI_CROSS) return CMADX_EINVAL;
+    A.hess_flags = flags;
+    if (int rc = check_history(mat, hist, &A.m)) return rc;
+    if (A.m.rot || history_def_type(hist) != CMADX_DEF_FULL_3D) return CMADX_EUNSUPPORTED;
+    if (n_active < 0 || n_active > CMADX_MAX_ACTIVE || (n_active > 0 && !active_pid)) return CMADX_EINVAL;
+    if (!hist->result || !hist->workspace || (hist->n > 0 && !hist->data)) return CMADX_EINVAL;
+    for (int c = 0; c < n_active; ++c) {
+        const int pid = active_pid[c];
+        if (pid < 0 || pid >= CMADX_NUM_PARAM_IDS) return CMADX_EINVAL;
+        if (pid == CMADX_P_HOSFORD_A || pid >= CMADX_P_Q00) return CMADX_EUNSUPPORTED;
+        A.pid[c] = pid;
+    }
+    A.n_active = n_active;
+    A.h = *hist;
+    A.phi_hist = hist->workspace;
+    A.partials = hist->workspace + (int64_t)(hist->nsteps + 1) * 7 * hist->ld;
+    double* pair_sums = A.partials + hess_partials_doubles(hist->n, n_active);
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = launch_mp_sens(A, true, s);            // J, dJ/dp, and phi_t for every step
+    if (e != cudaSuccess) return cuda_fail(e);
+    e = launch_mp_hess(A, pair_sums, hist->result + 1 + n_active, s);
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(n_active > 0 ? 5 : 2, std::memory_order_relaxed);
+    return CMADX_OK;
 }
 
 static int check_fe_block(const cmadx_material_t* mat, const cmadx_fe_block_t* blk, FeArgs* A) {

@@ -1,0 +1,407 @@
+// K2-H - second-order (Hessian) pass of the material-point calibration objective: the
+// direct-adjoint recurrence of MPDirectAdjointObjective (cmad/objectives/mp_objective.py:
+// 218-343, arXiv:2501.04584) over whole stored load histories.
+//
+// With the adjoint states phi_t of the reverse pass (stored by the K2 adjoint kernel), the
+// forward sensitivities X_t = dxi_t/dp (the K2 direct recurrence) and
+//   L_t(z) = J_t(xi_t, p) + phi_t . C(xi_t, xi_{t-1}, p),   z = (p, xi_t, xi_{t-1}),
+// the reference's thirteen einsum terms (:317-336) are exactly
+//   H += Z^T (d2 L_t / dz2) Z,   Z = [I; X_t; X_{t-1}]:
+// H_ij = D2 L_t [Z_i, Z_j], a MIXED second directional derivative.  The reference builds the
+// tensors d2C/d(.)d(.) by jax.hessian / jacrev(jacfwd) (cmad/models/model.py:134-148,
+// cmad/qois/qoi.py:47-58); here every (i <= j) entry is ONE evaluation of L_t in hyper-dual
+// arithmetic (value, d/ds, d/du, d2/ds du) along (Z_i, Z_j): templated forward-mode dual
+// numbers instead of traced AD - no third-derivative formulas of the yield surfaces are
+// written down, the yield normal n = d phi/d sigma is evaluated from its closed form in
+// hyper-dual arithmetic.  The branch (plastic / elastic) is the one of the stored state, as
+// jnp.where differentiates (cmad/models/paths.py:26-27).
+//
+// One thread per material point walks its history forward; X_t / X_{t-1} and the pair
+// accumulators live in local memory (this is the small-batch calibration path, not a bench
+// line).  The pair sums are reduced in fixed order (bit-reproducible).  FULL_3D, identity
+// material axes; d/d(hosford a) and d/d(rotation) are not provided (as in K2).
+#include "mp_outputs.cuh"
+#include "mp_sens.cuh"
+
+namespace cmadx {
+cudaError_t launch_reduce_partials(const double* partials, int64_t nblk, int ncols, double* result,
+                                   cudaStream_t stream);
+
+namespace {
+
+constexpr int HESS_BLOCK = 64;
+constexpr int HESS_MAX_PAIRS = CMADX_MAX_ACTIVE * (CMADX_MAX_ACTIVE + 1) / 2;
+
+// hyper-dual number: f(z + s v + u w) = v + a s + b u + ab s u  (s^2 = u^2 = 0)
+struct HD {
+    double v, a, b, ab;
+};
+CMADX_DEV HD hd(double c) { return {c, 0.0, 0.0, 0.0}; }
+CMADX_DEV HD operator+(const HD& x, const HD& y) { return {x.v + y.v, x.a + y.a, x.b + y.b, x.ab + y.ab}; }
+CMADX_DEV HD operator-(const HD& x, const HD& y) { return {x.v - y.v, x.a - y.a, x.b - y.b, x.ab - y.ab}; }
+CMADX_DEV HD operator-(const HD& x) { return {-x.v, -x.a, -x.b, -x.ab}; }
+CMADX_DEV HD operator*(const HD& x, const HD& y) {
+    return {x.v * y.v, fma(x.a, y.v, x.v * y.a), fma(x.b, y.v, x.v * y.b),
+            fma(x.ab, y.v, fma(x.a, y.b, fma(x.b, y.a, x.v * y.ab)))};
+}
+CMADX_DEV HD operator*(double c, const HD& x) { return {c * x.v, c * x.a, c * x.b, c * x.ab}; }
+CMADX_DEV HD operator+(const HD& x, double c) { return {x.v + c, x.a, x.b, x.ab}; }
+CMADX_DEV HD operator-(const HD& x, double c) { return {x.v - c, x.a, x.b, x.ab}; }
+CMADX_DEV HD operator-(double c, const HD& x) { return {c - x.v, -x.a, -x.b, -x.ab}; }
+// g(u): value g, first and second derivative g1, g2 at u.v
+CMADX_DEV HD chain(const HD& u, double g, double g1, double g2) {
+    return {g, g1 * u.a, g1 * u.b, fma(g1, u.ab, g2 * u.a * u.b)};
+}
+CMADX_DEV HD inv(const HD& y) {
+    const double r = 1.0 / y.v;
+    return chain(y, r, -r * r, 2.0 * r * r * r);
+}
+CMADX_DEV HD operator/(const HD& x, const HD& y) { return x * inv(y); }
+CMADX_DEV HD hsqrt(const HD& x) {
+    const double s = sqrt(x.v);
+    return chain(x, s, 0.5 / s, -0.25 / (s * x.v));
+}
+CMADX_DEV HD hexp(const HD& x) {
+    const double e = exp(x.v);
+    return chain(x, e, e, e);
+}
+// u^r for u.v > 0
+CMADX_DEV HD hpow(const HD& u, double r) {
+    const double p2 = pow(u.v, r - 2.0);
+    return chain(u, p2 * u.v * u.v, r * p2 * u.v, r * (r - 1.0) * p2);
+}
+CMADX_DEV HD habs(const HD& x) { return (x.v < 0.0) ? -x : x; }
+
+struct HessParams {
+    HD lam, mu, Y, S, D, K, hill[6];
+};
+
+// phi(sigma) and the yield normal n_a = d phi/d sigma_a (single tensor entry) in hyper-dual
+// arithmetic (cmad/models/effective_stress.py:30-52, 168-177; the normal is what
+// jax.grad gives, small_elastic_plastic.py:90)
+template <int YK>
+CMADX_DEV void yield_hd(const DevMat& m, const HessParams& P, const HD (&sig)[6], HD& phi, HD (&n)[6]) {
+    if constexpr (YK == CMADX_YIELD_J2) {
+        const HD h = (1.0 / 3.0) * (sig[0] + sig[3] + sig[5]);
+        HD s[6], ss = hd(0.0);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            s[a] = is_diag(a) ? sig[a] - h : sig[a];
+            ss = ss + mult(a) * (s[a] * s[a]);
+        }
+        const double r32 = 1.2247448713915890491;
+        const HD sn = hsqrt(ss);
+        phi = r32 * sn;
+        const HD isn = inv(sn);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) n[a] = r32 * (s[a] * isn);
+    } else if constexpr (YK == CMADX_YIELD_HILL) {
+        const HD d12 = sig[3] - sig[5], d20 = sig[5] - sig[0], d01 = sig[0] - sig[3];
+        const HD& F = P.hill[0]; const HD& G = P.hill[1]; const HD& H = P.hill[2];
+        const HD& L = P.hill[3]; const HD& Mm = P.hill[4]; const HD& N = P.hill[5];
+        const HD q = F * d12 * d12 + G * d20 * d20 + H * d01 * d01
+                     + 2.0 * (L * sig[4] * sig[4]) + 2.0 * (Mm * sig[2] * sig[2]) + 2.0 * (N * sig[1] * sig[1]);
+        phi = hsqrt(q);
+        const HD ip = inv(phi);
+        n[0] = (H * d01 - G * d20) * ip;
+        n[3] = (F * d12 - H * d01) * ip;
+        n[5] = (G * d20 - F * d12) * ip;
+        n[1] = N * sig[1] * ip;
+        n[2] = Mm * sig[2] * ip;
+        n[4] = L * sig[4] * ip;
+    } else {
+        // Hosford on the diagonal entries: phi = (1/2 sum |Delta_i|^a)^(1/a); the reference's
+        // von Mises scaling is a positive homogeneity factor - applied here as a CONSTANT c0
+        // (phi(sigma) = c0 phi(sigma / c0) exactly), which keeps large exponents in range
+        const double a = m.a;
+        const double hv = (sig[0].v + sig[3].v + sig[5].v) / 3.0;
+        double ssv = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double s = is_diag(k) ? sig[k].v - hv : sig[k].v;
+            ssv = fma(mult(k) * s, s, ssv);
+        }
+        const double c0 = 1.2247448713915890491 * sqrt(ssv), ic0 = 1.0 / c0;
+        const HD dl[3] = {sig[0] - sig[3], sig[3] - sig[5], sig[5] - sig[0]};
+        HD sq = hd(0.0);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            if (dl[i].v != 0.0) sq = sq + hpow(ic0 * habs(dl[i]), a);
+        sq = 0.5 * sq;
+        phi = c0 * hpow(sq, 1.0 / a);
+        const HD ip = inv(phi);
+        HD g[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            // d phi/d Delta_i = 1/2 sign(Delta_i) (|Delta_i|/phi)^(a-1)
+            if (dl[i].v != 0.0) {
+                const HD r = hpow(habs(dl[i]) * ip, a - 1.0);
+                g[i] = (dl[i].v > 0.0 ? 0.5 : -0.5) * r;
+            } else {
+                g[i] = hd(0.0);
+            }
+        }
+        n[0] = g[0] - g[2]; n[3] = g[1] - g[0]; n[5] = g[2] - g[1];
+        n[1] = hd(0.0); n[2] = hd(0.0); n[4] = hd(0.0);
+    }
+}
+
+CMADX_DEV void stress_hd(const HD& lam, const HD& mu, const HD (&x)[7], const double (&em)[6], HD (&sig)[6]) {
+    HD ee[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) ee[a] = em[a] - x[a];
+    const HD ltr = lam * (ee[0] + ee[3] + ee[5]);
+    const HD two_mu = 2.0 * mu;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) sig[a] = is_diag(a) ? two_mu * ee[a] + ltr : two_mu * ee[a];
+}
+
+// Calibration QoI (cmad/qois/calibration.py:56-66)
+CMADX_DEV HD qoi_hd(const HD (&sig)[6], const double (&w)[9], const double (&d)[9]) {
+    const int comp[9] = {0, 1, 2, 1, 3, 4, 2, 4, 5};
+    HD J = hd(0.0);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const HD mis = w[k] * (sig[comp[k]] - d[k]);
+        J = J + 0.5 * (mis * mis);
+    }
+    return J;
+}
+
+// The (parameter, state) cross terms of the QoI's second derivative along the two directions:
+// D2 J [(p_i, 0), (0, X_j)] + D2 J [(0, X_i), (p_j, 0)].  The reference omits exactly these
+// (its QoI takes jacrev(jacfwd(., DXI_PREV), DPARAMS), cmad/qois/qoi.py:53-55, which is zero for
+// a QoI that does not depend on xi_prev); the reference-compatible mode subtracts them.
+__device__ __noinline__ double qoi_cross_terms(const HD& lam, const HD& mu, const HD (&x)[7],
+                                               const double (&em)[6], const double (&w)[9],
+                                               const double (&d)[9]) {
+    double acc = 0.0;
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+        // side 0: parameters keep slot a, the state keeps slot b; side 1: the other way round
+        const HD l = side ? HD{lam.v, 0.0, lam.b, 0.0} : HD{lam.v, lam.a, 0.0, 0.0};
+        const HD u = side ? HD{mu.v, 0.0, mu.b, 0.0} : HD{mu.v, mu.a, 0.0, 0.0};
+        HD xs[7], sig[6];
+#pragma unroll
+        for (int r = 0; r < 7; ++r) xs[r] = side ? HD{x[r].v, x[r].a, 0.0, 0.0} : HD{x[r].v, 0.0, x[r].b, 0.0};
+        stress_hd(l, u, xs, em, sig);
+        acc += qoi_hd(sig, w, d).ab;
+    }
+    return acc;
+}
+
+// d2/ds du of L_t = J_t + phi . C along the two directions carried by the hyper-duals
+template <int YK>
+__device__ __noinline__ double lagrangian_mixed(const DevMat& m, const HessParams& P, const HD (&x)[7],
+                                                const HD (&xp)[7], const double (&em)[6],
+                                                const double (&phi)[7], const double (&w)[9],
+                                                const double (&d)[9], bool plastic) {
+    HD sig[6];
+    stress_hd(P.lam, P.mu, x, em, sig);
+    const HD two_mu = 2.0 * P.mu;
+    HD L = qoi_hd(sig, w, d);
+    if (plastic) {
+        HD pe, n[6];
+        yield_hd<YK>(m, P, sig, pe, n);
+        HD hard = P.Y;
+        if (m.hmask & CMADX_HARD_VOCE) hard = hard + P.S * (1.0 - hexp(-(P.D * x[6])));
+        if (m.hmask & CMADX_HARD_LINEAR) hard = hard + P.K * x[6];
+        const HD f = (pe - hard) * inv(two_mu);
+        const HD dg = x[6] - xp[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) L = L + phi[a] * (x[a] - xp[a] - dg * n[a]);
+        L = L + phi[6] * f;
+    } else {
+#pragma unroll
+        for (int a = 0; a < 7; ++a) L = L + phi[a] * (x[a] - xp[a]);
+    }
+    return L.ab;
+}
+
+// seeds of parameter `pid` for the pass along (direction slot a: parameter pi, slot b: pj)
+CMADX_DEV HD seed(double value, int pid, int pi, int pj) {
+    return {value, pid == pi ? 1.0 : 0.0, pid == pj ? 1.0 : 0.0, 0.0};
+}
+
+template <int YK>
+__global__ void __launch_bounds__(HESS_BLOCK) mp_hess_kernel(const __grid_constant__ SensArgs A) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < A.h.n;
+    const int64_t ld = A.h.ld;
+    const DevMat& m = A.m;
+    const int N = A.h.nsteps, na = A.n_active, sc = A.h.strain_comps;
+    const int npairs = na * (na + 1) / 2;
+
+    double Hacc[HESS_MAX_PAIRS];
+    for (int q = 0; q < npairs; ++q) Hacc[q] = 0.0;
+    double X[CMADX_MAX_ACTIVE][7], Xp[CMADX_MAX_ACTIVE][7];
+    for (int c = 0; c < na; ++c)
+#pragma unroll
+        for (int r = 0; r < 7; ++r) { X[c][r] = 0.0; Xp[c][r] = 0.0; }
+    double x[7], xp[7];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+        const double v = live ? __ldg(A.h.xi_hist + c * ld + i) : 0.0;
+        x[c] = v; xp[c] = v;
+    }
+    for (int t = 1; t <= N; ++t) {
+        double em[6], d[9], phi[7];
+        if (live) {
+            const double* xs = A.h.xi_hist + (int64_t)t * 7 * ld + i;
+            const double* ph = A.phi_hist + (int64_t)t * 7 * ld + i;
+#pragma unroll
+            for (int c = 0; c < 7; ++c) { x[c] = __ldg(xs + c * ld); phi[c] = ph[c * ld]; }
+            const double* es = A.h.strain + (int64_t)t * sc * ld + i;
+            if (sc == 6) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) em[c] = __ldg(es + c * ld);
+            } else {
+                double gq[9];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) gq[c] = __ldg(es + c * ld);
+                em[0] = gq[0]; em[3] = gq[4]; em[5] = gq[8];
+                em[1] = 0.5 * (gq[1] + gq[3]); em[2] = 0.5 * (gq[2] + gq[6]); em[4] = 0.5 * (gq[5] + gq[7]);
+            }
+            const double* ds = A.h.data + (int64_t)t * 9 * ld + i;
+#pragma unroll
+            for (int c = 0; c < 9; ++c) d[c] = __ldg(ds + c * ld);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) em[c] = 1e-3 * (c == 0);
+#pragma unroll
+            for (int c = 0; c < 9; ++c) d[c] = 0.0;
+#pragma unroll
+            for (int c = 0; c < 7; ++c) phi[c] = 0.0;
+        }
+        // ---- forward sensitivities X_t = A^{-1}(-dC/dp - B X_{t-1})  (mp_objective.py:300-301)
+        SepPoint<YK> pt;
+        double C[7];
+        pt.residual(m, x, xp, em, C);
+        const bool pl = pt.plastic;
+        const double dg = x[6] - xp[6];
+        double ee[6], sig[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) ee[a] = em[a] - x[a];
+        const double tree = ee[0] + ee[3] + ee[5];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) sig[a] = is_diag(a) ? fma(m.two_mu, ee[a], m.lam * tree) : m.two_mu * ee[a];
+        double Mee[6], nee = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) sacc = fma(pt.yf.M(a, b), ee[b], sacc);
+            Mee[a] = sacc;
+            nee = fma(mult(a) * pt.n[a], ee[a], nee);
+        }
+        RegLU<7> lu;
+        pt.jacobian(m, dg, lu.a);
+        const bool trouble = lu.factor_natural();
+        const bool slow = __any_sync(__activemask(), trouble);
+        if (slow && trouble) {
+            pt.jacobian(m, dg, lu.a);
+            lu.factor_pivot();
+        }
+        for (int c = 0; c < na; ++c) {
+            double col[7], rhs[7];
+            dC_dp_column(m, A.pid[c], pl, pt.yf, pt.n, pt.f, pt.eD, x[6], dg, Mee, nee, sig, col);
+            const double x6 = Xp[c][6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) rhs[q] = -col[q] + Xp[c][q] - (pl ? pt.n[q] * x6 : 0.0);
+            rhs[6] = -col[6] + (pl ? 0.0 : x6);
+            if (slow && trouble) lu.solve_pivot(rhs); else lu.solve_natural(rhs);
+#pragma unroll
+            for (int q = 0; q < 7; ++q) X[c][q] = rhs[q];
+        }
+        // ---- H_ij += D2 L_t [Z_i, Z_j], one hyper-dual evaluation per pair
+        int q = 0;
+#pragma unroll 1
+        for (int ci = 0; ci < na; ++ci) {
+#pragma unroll 1
+            for (int cj = ci; cj < na; ++cj, ++q) {
+                const int pi = A.pid[ci], pj = A.pid[cj];
+                HessParams P;
+                {
+                    const int ki = pi - CMADX_P_EL0, kj = pj - CMADX_P_EL0;
+                    const bool ei = (ki == 0 || ki == 1), ej = (kj == 0 || kj == 1);
+                    const int k2 = ki + kj;     // (0,0) -> 0, (0,1)/(1,0) -> 1, (1,1) -> 2
+                    P.lam = {m.lam, ei ? m.dlam[ki] : 0.0, ej ? m.dlam[kj] : 0.0, (ei && ej) ? m.d2lam[k2] : 0.0};
+                    P.mu = {m.mu, ei ? m.dmu[ki] : 0.0, ej ? m.dmu[kj] : 0.0, (ei && ej) ? m.d2mu[k2] : 0.0};
+                }
+                P.Y = seed(m.Y, CMADX_P_Y, pi, pj);
+                P.S = seed(m.S, CMADX_P_VOCE_S, pi, pj);
+                P.D = seed(m.D, CMADX_P_VOCE_D, pi, pj);
+                P.K = seed(m.K, CMADX_P_LIN_K, pi, pj);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) P.hill[k] = seed(m.hill[k], CMADX_P_HILL_F + k, pi, pj);
+                HD xh[7], xph[7];
+#pragma unroll
+                for (int r = 0; r < 7; ++r) {
+                    xh[r] = {x[r], X[ci][r], X[cj][r], 0.0};
+                    xph[r] = {xp[r], Xp[ci][r], Xp[cj][r], 0.0};
+                }
+                double hij = lagrangian_mixed<YK>(m, P, xh, xph, em, phi, A.h.weight, d, pl);
+                if (A.hess_flags & CMADX_HESS_F_REFERENCE_QOI_CROSS)
+                    hij -= qoi_cross_terms(P.lam, P.mu, xh, em, A.h.weight, d);
+                Hacc[q] += hij;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 7; ++c) xp[c] = x[c];
+        for (int c = 0; c < na; ++c)
+#pragma unroll
+            for (int r = 0; r < 7; ++r) Xp[c][r] = X[c][r];
+    }
+    // ---- block reduction of the pair sums (fixed order)
+    __shared__ double sm[HESS_BLOCK / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = 0; q < npairs; ++q) {
+        double v = live ? Hacc[q] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) sm[warp] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+#pragma unroll
+            for (int wq = 0; wq < HESS_BLOCK / 32; ++wq) s += sm[wq];
+            A.partials[(int64_t)blockIdx.x * npairs + q] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// upper-triangle pair sums -> full symmetric na x na matrix
+__global__ void expand_pairs_kernel(const double* pairs, int na, double* H) {
+    const int ci = threadIdx.x / na, cj = threadIdx.x % na;
+    if (ci >= na) return;
+    const int lo = ci < cj ? ci : cj, hi = ci < cj ? cj : ci;
+    const int q = lo * na - lo * (lo - 1) / 2 + (hi - lo);
+    H[ci * na + cj] = pairs[q];
+}
+
+}  // namespace
+
+int64_t hess_blocks(int64_t n) { return (n + HESS_BLOCK - 1) / HESS_BLOCK; }
+
+// partials: [nblk][npairs], pair_sums: [npairs] scratch, H_out: [na*na]
+cudaError_t launch_mp_hess(const SensArgs& A, double* pair_sums, double* H_out, cudaStream_t stream) {
+    const int na = A.n_active, npairs = na * (na + 1) / 2;
+    if (na == 0) return cudaSuccess;
+    if (A.h.n == 0) return cudaMemsetAsync(H_out, 0, sizeof(double) * na * na, stream);
+    const int64_t nblk = hess_blocks(A.h.n);
+    switch (A.m.yield) {
+    case CMADX_YIELD_J2: mp_hess_kernel<CMADX_YIELD_J2><<<(unsigned)nblk, HESS_BLOCK, 0, stream>>>(A); break;
+    case CMADX_YIELD_HILL: mp_hess_kernel<CMADX_YIELD_HILL><<<(unsigned)nblk, HESS_BLOCK, 0, stream>>>(A); break;
+    case CMADX_YIELD_HOSFORD: mp_hess_kernel<CMADX_YIELD_HOSFORD><<<(unsigned)nblk, HESS_BLOCK, 0, stream>>>(A); break;
+    default: return cudaErrorInvalidValue;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    e = launch_reduce_partials(A.partials, nblk, npairs, pair_sums, stream);
+    if (e != cudaSuccess) return e;
+    expand_pairs_kernel<<<1, na * na, 0, stream>>>(pair_sums, na, H_out);
+    return cudaGetLastError();
+}
+
+}  // namespace cmadx

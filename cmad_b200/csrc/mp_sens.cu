@@ -15,16 +15,10 @@
 // cmad/qois/calibration.py:56-66.
 #include "j2_radial.cuh"
 #include "mp_outputs.cuh"
+#include "mp_sens.cuh"
 
 namespace cmadx {
 
-struct SensArgs {
-    DevMat m;
-    int n_active;
-    int pid[CMADX_MAX_ACTIVE];
-    cmadx_mp_history_t h;
-    double* partials;     // [nblk][1 + n_active]
-};
 
 namespace {
 
@@ -202,6 +196,11 @@ mp_sens_kernel(const __grid_constant__ SensArgs A) {
 #pragma unroll
             for (int c = 0; c < 7; ++c) phi[c] = hist[c] - dJdx[c];
             solve7(phi);
+            if (A.phi_hist && live) {      // kept for the direct-adjoint Hessian pass (mp_hess.cu)
+                double* ph = A.phi_hist + (int64_t)t * 7 * ld + i;
+#pragma unroll
+                for (int c = 0; c < 7; ++c) ph[c * ld] = phi[c];
+            }
             // h <- -B^T phi
             double nphi = 0.0;
 #pragma unroll

@@ -8,16 +8,10 @@
 // for the adjoint), fixed-order block reduction -> partials -> reduce_partials_kernel.
 #include "mp_outputs.cuh"
 #include "sep_point_dt.cuh"
+#include "mp_sens.cuh"
 
 namespace cmadx {
 
-struct SensArgs {
-    DevMat m;
-    int n_active;
-    int pid[CMADX_MAX_ACTIVE];
-    cmadx_mp_history_t h;
-    double* partials;
-};
 cudaError_t launch_reduce_partials(const double* partials, int64_t nblk, int ncols, double* result,
                                    cudaStream_t stream);
 

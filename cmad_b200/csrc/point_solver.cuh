@@ -32,6 +32,7 @@ struct DevMat {
     double Q[9];
     double yield_tol;
     double dlam[2], dmu[2];   // d(lambda, mu)/d(elastic[0..1])
+    double d2lam[3], d2mu[3]; // second derivatives (00, 01, 11): Hessian path only
     int hmask, rot, model, yield;
     int a_int;                // Hosford exponent when it is a small positive integer, else 0
 };

@@ -42,6 +42,13 @@ class GradientResult(NamedTuple):
     grad: np.ndarray
 
 
+class HessianResult(NamedTuple):
+    """cmad/objectives/objective.py HessianResult: canonical-coordinate gradient and Hessian."""
+    J: float
+    grad: np.ndarray
+    hessian: np.ndarray
+
+
 class SmallElasticPlastic:
     """Constructor-compatible stand-in for the reference model class: carries the
     parameters and the deformation type; all evaluation happens in the kernels."""
@@ -121,7 +128,8 @@ class _DeviceHistories:
 
 def gpu_local_evaluator(model: SmallElasticPlastic, strain_hist: np.ndarray, data_hist: np.ndarray,
                         weight: np.ndarray, strategy: str, device: torch.device,
-                        newton: NewtonSettings | None = None) -> Callable[[], torch.Tensor]:
+                        newton: NewtonSettings | None = None,
+                        reference_qoi_cross_terms: bool = False) -> Callable[[], torch.Tensor]:
     """Returns ``f() -> tensor[1 + n_active]`` (J, dJ/dp native) for this rank's
     points, evaluated with K1 + K2 on ``device`` at the model's current parameters."""
     lib = L.lib()
@@ -130,7 +138,10 @@ def gpu_local_evaluator(model: SmallElasticPlastic, strain_hist: np.ndarray, dat
         raise ValueError(f"strain history with {strain_hist.shape[1]} rows does not fit the model's def_type")
     hist = _DeviceHistories(strain_hist, data_hist, device)
     newton = newton or NewtonSettings(mode="imperative", max_iters=10, abs_tol=1e-14, rel_tol=1e-14)
-    adjoint = {"adjoint": True, "direct": False}[strategy]
+    adjoint = {"adjoint": True, "direct": False, "direct_adjoint": True}[strategy]
+    hessian = strategy == "direct_adjoint"
+    if hessian and nd != 3:
+        raise NotImplementedError("the Hessian pass covers FULL_3D only")
     w = np.asarray(weight, dtype=np.float64).reshape(9)
 
     def evaluate() -> torch.Tensor:
@@ -138,8 +149,12 @@ def gpu_local_evaluator(model: SmallElasticPlastic, strain_hist: np.ndarray, dat
         na = len(pid)
         mat = model.material()
         nw = newton.to_struct()
-        result = torch.zeros((1 + na,), dtype=torch.float64, device=device)
-        ws_bytes = lib.cmadx_mp_objective_workspace_bytes(C.c_int64(hist.n), C.c_int32(na))
+        result = torch.zeros((1 + na + (na * na if hessian else 0),), dtype=torch.float64, device=device)
+        if hessian:
+            ws_bytes = lib.cmadx_mp_hessian_workspace_bytes(C.c_int64(hist.n), C.c_int64(max(hist.n, 1)),
+                                                            C.c_int32(hist.N), C.c_int32(na))
+        else:
+            ws_bytes = lib.cmadx_mp_objective_workspace_bytes(C.c_int64(hist.n), C.c_int32(na))
         ws = torch.empty((max(int(ws_bytes) // 8, 1),), dtype=torch.float64, device=device)
         h = L.MpHistory()
         h.n, h.ld, h.nsteps, h.strain_comps = hist.n, max(hist.n, 1), hist.N, hist.strain.shape[1]
@@ -154,9 +169,14 @@ def gpu_local_evaluator(model: SmallElasticPlastic, strain_hist: np.ndarray, dat
         with torch.cuda.device(device):
             L.check(lib.cmadx_mp_forward_history(C.byref(mat), C.byref(nw), C.byref(h), stream),
                     "cmadx_mp_forward_history")
-            fn = lib.cmadx_mp_objective_adjoint if adjoint else lib.cmadx_mp_objective_direct
-            L.check(fn(C.byref(mat), pid.ctypes.data_as(C.POINTER(C.c_int32)), na, C.byref(h), stream),
-                    "cmadx_mp_objective")
+            pidp = pid.ctypes.data_as(C.POINTER(C.c_int32))
+            if hessian:
+                rc = lib.cmadx_mp_objective_hessian(C.byref(mat), pidp, na, C.byref(h),
+                                                    C.c_int32(1 if reference_qoi_cross_terms else 0), stream)
+            else:
+                fn = lib.cmadx_mp_objective_adjoint if adjoint else lib.cmadx_mp_objective_direct
+                rc = fn(C.byref(mat), pidp, na, C.byref(h), stream)
+            L.check(rc, "cmadx_mp_objective")
         evaluate.histories = hist
         return result
 
@@ -192,13 +212,20 @@ class BatchedMPObjective:
         if self._group is not None or (dist.is_available() and dist.is_initialized()):
             dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=self._group)
         host = partial.detach().cpu().numpy()
-        grad = host[1:].copy()
+        na = self._parameters.num_active_params
+        grad = host[1:1 + na].copy()
+        if host.size > 1 + na:                       # (J, grad, H): MPDirectAdjointObjective :269-340
+            hess = host[1 + na:].reshape(na, na).copy()
+            native_grad = grad.copy()
+            self._parameters.transform_grad(grad)
+            self._parameters.transform_hessian(hess, native_grad)
+            return HessianResult(J=float(host[0]), grad=grad, hessian=hess)
         self._parameters.transform_grad(grad)
         return GradientResult(J=float(host[0]), grad=grad)
 
 
 def _single_point_objective(qoi: Calibration, global_state: np.ndarray, strategy: str,
-                            device=None, group=None) -> BatchedMPObjective:
+                            device=None, group=None, **kwargs) -> BatchedMPObjective:
     F = np.asarray(global_state, dtype=np.float64)
     data = qoi.data()
     if F.ndim == 3:
@@ -206,13 +233,25 @@ def _single_point_objective(qoi: Calibration, global_state: np.ndarray, strategy
     device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
     model = qoi.model()
     ev = gpu_local_evaluator(model, strain_history_from_F(F), data_history(data), qoi._weight,
-                             strategy, device)
+                             strategy, device, **kwargs)
     return BatchedMPObjective(model.parameters, ev, group)
 
 
 def MPAdjointObjective(qoi: Calibration, global_state: np.ndarray, device=None, group=None):
     """Reference signature (mp_objective.py:92): gradient by the reverse-time adjoint."""
     return _single_point_objective(qoi, global_state, "adjoint", device, group)
+
+
+def MPDirectAdjointObjective(qoi: Calibration, global_state: np.ndarray, device=None, group=None,
+                             reference_qoi_cross_terms: bool = False):
+    """Reference signature (mp_objective.py:218): J, gradient and Hessian (canonical
+    coordinates) by the direct-adjoint method; ``evaluate`` returns a :class:`HessianResult`.
+    Under ``torch.distributed`` the single all-reduce carries ``1 + P_a + P_a^2`` doubles.
+    ``reference_qoi_cross_terms=True`` reproduces the reference entry for entry where its QoI
+    drops the d2J/dxi dparams block (see CMADX_HESS_F_REFERENCE_QOI_CROSS in the header);
+    the default is the complete Hessian."""
+    return _single_point_objective(qoi, global_state, "direct_adjoint", device, group,
+                                   reference_qoi_cross_terms=reference_qoi_cross_terms)
 
 
 def MPDirectObjective(qoi: Calibration, global_state: np.ndarray, device=None, group=None):

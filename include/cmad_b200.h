@@ -242,6 +242,28 @@ int cmadx_mp_objective_adjoint(const cmadx_material_t* mat, const int32_t* activ
 int cmadx_mp_objective_direct(const cmadx_material_t* mat, const int32_t* active_pid,
                               int32_t n_active, const cmadx_mp_history_t* hist, void* stream);
 
+/* Second-order pass: MPDirectAdjointObjective (cmad/objectives/mp_objective.py:218-343) -
+ * J, dJ/dp and the Hessian d2J/dp2 of the summed objective in NATIVE parameter values
+ * (before Parameters.transform_grad / transform_hessian, cmad/parameters/parameters.py:
+ * 326-357).  Runs the adjoint pass (keeping phi_t), then the forward direct-adjoint pass in
+ * which every Hessian entry is one hyper-dual evaluation of J_t + phi_t . C_t along
+ * (dz/dp_i, dz/dp_j) - the templated forward-mode counterpart of Model.evaluate_hessians /
+ * QoI.evaluate_hessians (cmad/models/model.py:134-148, 245-270).  `result` holds
+ * 1 + n_active + n_active^2 doubles: J, grad, H row-major (symmetric).  `workspace` needs
+ * cmadx_mp_hessian_workspace_bytes().  FULL_3D, identity material axes; deterministic.
+ * flags: 0 = the complete Hessian (equals the derivative of the gradient).
+ * CMADX_HESS_F_REFERENCE_QOI_CROSS reproduces the reference entry for entry: its QoI builds
+ * the mixed block d2J/dxi dparams by differentiating w.r.t. xi_PREV (cmad/qois/qoi.py:53-55),
+ * which is zero for the Calibration QoI, so the terms d2J_dp_dxi . dxi_dp of
+ * mp_objective.py:320,322 are missing there.  Both agree whenever no active parameter enters
+ * the Cauchy stress (flow-stress parameters only - the reference's own tests); they differ
+ * when elastic parameters are active.                                                     */
+enum { CMADX_HESS_F_REFERENCE_QOI_CROSS = 1 };
+int64_t cmadx_mp_hessian_workspace_bytes(int64_t n, int64_t ld, int32_t nsteps, int32_t n_active);
+int cmadx_mp_objective_hessian(const cmadx_material_t* mat, const int32_t* active_pid,
+                               int32_t n_active, const cmadx_mp_history_t* hist, int32_t flags,
+                               void* stream);
+
 /* ---- K3/K4: FE element-block kernels (displacement formulation, COUPLED mode) ----
  * One call = one mesh element block: for every element gather U, for every
  * integration point interpolate grad_u = U_e^T grad_N

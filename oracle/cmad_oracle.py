@@ -840,6 +840,125 @@ def mp_objective_direct(parameters: OracleParameters, F, data, weight, spec: Mod
     return J, g
 
 
+def second_deriv_transform(value, transform):
+    """parameters.py:105-112."""
+    if transform is None or len(transform) == 2:
+        return 0.0
+    if len(transform) == 1:
+        return value
+    raise ValueError
+
+
+def transform_hessian(parameters: OracleParameters, H: np.ndarray, grad_native: np.ndarray) -> None:
+    """parameters.py:334-357 with diagonal_/off_diagonal_hessian_transform (:115-138), in place."""
+    av = parameters.flat_values()[parameters.active_idx]
+    tr = parameters._flat_active_transforms
+    for i in range(parameters.num_active_params):
+        for j in range(parameters.num_active_params):
+            if i == j:
+                H[i, i] = H[i, i] * first_deriv_transform(av[i], tr[i]) ** 2 \
+                    + grad_native[i] * second_deriv_transform(av[i], tr[i])
+            elif i < j:
+                H[i, j] = H[i, j] * first_deriv_transform(av[i], tr[i]) * first_deriv_transform(av[j], tr[j])
+            else:
+                H[i, j] = H[j, i]
+
+
+def _tree_with_active(values: dict, active_idx: np.ndarray, pa: torch.Tensor) -> dict:
+    """The params pytree with its ACTIVE flat entries replaced by the entries of the torch
+    vector ``pa`` (so AD w.r.t. ``pa`` is AD w.r.t. the active parameters, native values)."""
+    pos = {int(i): k for k, i in enumerate(active_idx)}
+    it = [0]
+
+    def rebuild(t):
+        if isinstance(t, dict):
+            return {k: rebuild(t[k]) for k in sorted(t.keys())}
+        a = np.asarray(t, dtype=np.float64)
+        n = a.size
+        ent = [pa[pos[it[0] + q]] if (it[0] + q) in pos else torch.as_tensor(float(a.reshape(-1)[q]), dtype=DT)
+               for q in range(n)]
+        it[0] += n
+        return torch.stack(ent).reshape(a.shape) if a.ndim else ent[0]
+
+    return rebuild(values)
+
+
+def mp_objective_direct_adjoint(parameters: OracleParameters, F, data, weight, spec: ModelSpec,
+                                flat_active_values=None, are_canonical=True,
+                                reference_qoi_cross_terms: bool = False):
+    """``MPDirectAdjointObjective`` (mp_objective.py:218-343): J, gradient and Hessian in
+    canonical coordinates.  Forward pass with storage, the adjoint pass keeping phi_t, then the
+    forward direct-adjoint pass.  The thirteen einsum terms of :317-336 are
+    ``Z^T (d2(J_t + phi_t . C_t)/dz2) Z`` with ``z = (p, xi_t, xi_{t-1})`` and
+    ``Z = [I; dxi_t/dp; dxi_{t-1}/dp]``; the second-derivative tensors come from
+    ``torch.func.hessian`` where the reference uses ``jax.hessian / jacrev(jacfwd)``
+    (model.py:134-148, qoi.py:47-58).
+
+    ``reference_qoi_cross_terms``: the reference builds the QoI's mixed block
+    ``d2J/dxi dparams`` as ``jacrev(jacfwd(qoi_fun, argnums=DXI_PREV), DPARAMS)`` (qoi.py:53-55) -
+    differentiating w.r.t. xi_PREV, which the Calibration QoI does not depend on - so that block
+    is identically zero there and the terms ``d2J_dp_dxi . dxi_dp`` (:320, :322) drop out.  That
+    is exact only while no active parameter enters the Cauchy stress (flow-stress parameters, the
+    reference's own tests); with elastic parameters active the reference's Hessian misses them
+    (central differences of its own gradient show it: tests/test_hessian.py).  False (default):
+    the mathematically complete Hessian; True: the reference's output, entry for entry."""
+    from torch.func import hessian
+    if flat_active_values is not None:
+        parameters.set_active_values_from_flat(np.asarray(flat_active_values, float), are_canonical)
+    params = to_torch_tree(parameters.values)
+    N = F.shape[-1] - 1
+    w = torch.as_tensor(weight, dtype=DT)
+    nx, Pa = spec.num_dofs, parameters.num_active_params
+    xs = [torch.as_tensor(spec.init_xi())]
+    J = 0.0
+    for step in range(1, N + 1):
+        gu = _grad_u_from_F(F[:, :, step], spec); gup = _grad_u_from_F(F[:, :, step - 1], spec)
+        x, _ = newton_imperative(xs[-1], params, gu, gup, spec)
+        d = torch.as_tensor(data[..., step], dtype=DT)
+        J += float(calibration_qoi(x, xs[-1], params, gu, gup, spec, d, w))
+        xs.append(x)
+    g = np.zeros((1, Pa)); hist = np.zeros((nx, 1)); phis = [None] * (N + 1)
+    for step in range(N, 0, -1):                                   # :239-268
+        gu = _grad_u_from_F(F[:, :, step], spec); gup = _grad_u_from_F(F[:, :, step - 1], spec)
+        d = torch.as_tensor(data[..., step], dtype=DT)
+        A, B, dCdp, dJdx, dJdp = _step_derivs(xs[step], xs[step - 1], params, gu, gup, spec, parameters, d, w)
+        phi = np.linalg.solve(A.T, -dJdx.T + hist)
+        phis[step] = phi[:, 0].copy()
+        hist = -B.T @ phi
+        g += phi.T @ dCdp + dJdp
+    g = g.squeeze(0).copy()
+    g_native = g.copy()
+    parameters.transform_grad(g)
+    H = np.zeros((Pa, Pa)); X_prev = np.zeros((nx, Pa))
+    pa0 = torch.as_tensor(parameters.flat_values()[parameters.active_idx], dtype=DT)
+    res = residual_fun(spec)
+    for step in range(1, N + 1):                                   # :275-338
+        gu = _grad_u_from_F(F[:, :, step], spec); gup = _grad_u_from_F(F[:, :, step - 1], spec)
+        d = torch.as_tensor(data[..., step], dtype=DT)
+        A, B, dCdp, dJdx, dJdp = _step_derivs(xs[step], xs[step - 1], params, gu, gup, spec, parameters, d, w)
+        X = np.linalg.solve(A, -dCdp - B @ X_prev)
+        phi_t = torch.as_tensor(phis[step], dtype=DT)
+
+        def qoi_z(z):
+            p = _tree_with_active(parameters.values, parameters.active_idx, z[:Pa])
+            return calibration_qoi(z[Pa:Pa + nx], z[Pa + nx:], p, gu, gup, spec, d, w)
+
+        def constraint_z(z):
+            p = _tree_with_active(parameters.values, parameters.active_idx, z[:Pa])
+            return phi_t @ res(z[Pa:Pa + nx], z[Pa + nx:], p, gu, gup, spec)
+        z0 = torch.cat([pa0, xs[step], xs[step - 1]])
+        HJ = hessian(qoi_z)(z0).numpy()
+        if reference_qoi_cross_terms:                              # qoi.py:53-55, see the docstring
+            HJ[:Pa, Pa:Pa + nx] = 0.0
+            HJ[Pa:Pa + nx, :Pa] = 0.0
+        Hz = HJ + hessian(constraint_z)(z0).numpy()
+        Z = np.vstack([np.eye(Pa), X, X_prev])
+        H += Z.T @ Hz @ Z
+        X_prev = X
+    transform_hessian(parameters, H, g_native)
+    return J, g, H
+
+
 # --------------------------------------------------------------------------
 # FE per-IP / per-element / per-block (global_residuals/*, fem/assembly.py)
 # --------------------------------------------------------------------------

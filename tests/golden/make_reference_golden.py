@@ -54,7 +54,7 @@ from cmad.models.global_fields import GlobalFieldsAtPoint, mp_U_from_F  # noqa: 
 from cmad.models.hardening import combined_hardening_fun, get_hardening_funs  # noqa: E402
 from cmad.models.nonlinear_solver import make_newton_solve, newton_solve  # noqa: E402
 from cmad.models.small_elastic_plastic import SmallElasticPlastic, compute_yield_fun_and_normal  # noqa: E402
-from cmad.objectives.mp_objective import MPAdjointObjective, MPDirectObjective  # noqa: E402
+from cmad.objectives.mp_objective import MPAdjointObjective, MPDirectAdjointObjective, MPDirectObjective  # noqa: E402
 from cmad.parameters.parameters import Parameters  # noqa: E402
 from cmad.qois.calibration import Calibration  # noqa: E402
 from functools import partial  # noqa: E402
@@ -225,6 +225,33 @@ def _objective_job(job):
                active_idx=np.asarray(P.active_idx), param_names=np.array(P._names))
     return res
 
+
+
+def _hessian_job(job):
+    """MPDirectAdjointObjective (mp_objective.py:218-343): J, gradient and Hessian in
+    canonical coordinates through Model.evaluate_hessians / qoi.evaluate_hessians."""
+    kind, scaled, F, weight = job
+    values, act, tr = objective_trees(kind, scaled)
+    P = Parameters(values, act, tr)
+    model = SmallElasticPlastic(P)
+    N = F.shape[2] - 1
+    data = np.zeros((3, 3, N + 1))
+    model.set_xi_to_init_vals()
+    for step in range(1, N + 1):
+        model.gather_global(mp_U_from_F(F[:, :, step]), mp_U_from_F(F[:, :, step - 1]))
+        newton_solve(model)
+        model.seed_none(); model.evaluate_cauchy()
+        data[:, :, step] = model.Sigma().copy()
+        model.advance_xi()
+    qoi = Calibration(model, data, weight)
+    true_vals = P.flat_active_values(False)
+    offset = 1.1 * true_vals
+    P.set_active_values_from_flat(offset, False)
+    x = P.flat_active_values(True)
+    r = MPDirectAdjointObjective(qoi, F).evaluate(x)
+    return dict(J=float(r.J), grad=np.asarray(r.grad, float), hessian=np.asarray(r.hessian, float),
+                F=F, data=data, weight=weight, x_canonical=x, active_native=offset,
+                active_idx=np.asarray(P.active_idx), param_names=np.array(P._names))
 
 
 # --------------------------------------------------------------------------- #
@@ -504,6 +531,20 @@ def main():
                 out[f"{nm}.{k}"] = v
             print("objective", nm, r["J_adjoint"], r["grad_adjoint"], r["grad_direct"])
         np.savez_compressed(os.path.join(HERE, "ref_mp_objectives.npz"), **out)
+
+    if only is None or "hessian" in only:
+        w = np.array([[1.0, 0.5, 0.0], [0.5, 1.0, 0.0], [0.0, 0.0, 0.25]])
+        jobs, names = [], []
+        for kind in ("J2", "hill", "hosford"):
+            for scaled in (True, False):
+                jobs.append((kind, scaled, two_leg_F(11, 12, scale=1.5, diag_only=kind == "hosford"), w))
+                names.append(f"{kind}.{'scaled' if scaled else 'native'}")
+        out = {}
+        for nm, r in zip(names, pool.map(_hessian_job, jobs, chunksize=1)):
+            for k, v in r.items():
+                out[f"{nm}.{k}"] = v
+            print("hessian", nm, r["J"], r["grad"], np.linalg.eigvalsh(r["hessian"]))
+        np.savez_compressed(os.path.join(HERE, "ref_mp_hessian.npz"), **out)
 
     if only is None or "fe" in only:
         jobs, names = [], []

@@ -1,0 +1,180 @@
+"""Second-order (Hessian) path of the material-point calibration objective.
+
+Fixture ``tests/golden/ref_mp_hessian.npz``: the reference's own, unmodified
+``MPDirectAdjointObjective`` (cmad/objectives/mp_objective.py:218-343, through
+``Model.evaluate_hessians`` / ``QoI.evaluate_hessians``) executed by
+``tests/golden/make_reference_golden.py --only hessian`` - J, the canonical-coordinate gradient
+and Hessian for J2 / Hill / Hosford(a = 4), with log / bounds transforms ("scaled", flow-stress
+parameters active) and without ("native", elastic + flow-stress parameters active).
+
+CPU: the torch oracle's restatement of the direct-adjoint recurrence against the fixture.
+GPU: K2-H (cmadx_mp_objective_hessian, hyper-dual forward mode) through the reference-style
+constructor against the fixture, against the torch oracle on a small batch, and against central
+differences of the CUDA adjoint gradient (a size-independent property) on a large one.
+Tolerance: the reference's own cross-strategy Hessian tolerance is 1e-8
+(tests/objectives/test_jvp_vs_original.py:95-97); entries are compared relative to
+sqrt(|H_ii H_jj|) (the parameters' scales differ by six decades in the native cases)."""
+import os
+
+import numpy as np
+import pytest
+
+from cmad_b200 import Parameters
+from oracle import cmad_oracle as co
+from tests.golden.materials import objective_trees
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+HS = np.load(os.path.join(G, "ref_mp_hessian.npz"))
+CASES = sorted({k.rsplit(".", 1)[0] for k in HS.files})
+
+
+def hess_err(H, Href):
+    d = np.sqrt(np.abs(np.diag(Href)))
+    return float((np.abs(H - Href) / np.outer(d, d)).max())
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_torch_oracle_hessian_vs_reference(case):
+    kind, mode = case.split(".")
+    values, act, tr = objective_trees(kind, mode == "scaled")
+    P = co.OracleParameters(values, act, tr)
+    assert np.array_equal(P.active_idx, HS[f"{case}.active_idx"])
+    spec = co.ModelSpec()
+    J, g, H = co.mp_objective_direct_adjoint(P, HS[f"{case}.F"], HS[f"{case}.data"], HS[f"{case}.weight"], spec,
+                                             HS[f"{case}.x_canonical"], True, reference_qoi_cross_terms=True)
+    assert np.allclose(P.flat_values()[P.active_idx], HS[f"{case}.active_native"], rtol=1e-14)
+    assert abs(J - HS[f"{case}.J"]) < 1e-11 * abs(J)
+    assert np.abs(g - HS[f"{case}.grad"]).max() < 1e-9 * np.abs(g).max()
+    assert hess_err(H, HS[f"{case}.hessian"]) < 1e-8
+    assert np.array_equal(H, H.T)
+
+
+@pytest.mark.parametrize("kind", ["J2", "hosford"])
+def test_complete_hessian_is_the_derivative_of_the_gradient(kind):
+    """With elastic parameters active the reference's Hessian drops the d2J/dxi dp terms
+    (qoi.py:53-55 differentiates w.r.t. xi_prev).  The oracle's default keeps them: it equals
+    central differences of the adjoint gradient, the reference-compatible variant does not."""
+    case = f"{kind}.native"
+    F, data, w, x = (HS[f"{case}.{k}"] for k in ("F", "data", "weight", "x_canonical"))
+    F, data = F[:, :, :7], data[:, :, :7]
+    spec = co.ModelSpec()
+    mk = lambda: co.OracleParameters(*objective_trees(kind, False))
+    _, _, H = co.mp_objective_direct_adjoint(mk(), F, data, w, spec, x, True)
+    _, _, Href = co.mp_objective_direct_adjoint(mk(), F, data, w, spec, x, True, reference_qoi_cross_terms=True)
+    fd = np.zeros_like(H)
+    for c in range(len(x)):
+        h = 1e-6 * abs(x[c])
+        gs = []
+        for sgn in (1.0, -1.0):
+            xx = x.copy(); xx[c] += sgn * h
+            gs.append(co.mp_objective_adjoint(mk(), F, data, w, spec, xx, True)[1])
+        fd[:, c] = (gs[0] - gs[1]) / (2 * h)
+    assert hess_err(H, fd) < 1e-6
+    assert hess_err(Href, fd) > 1e-2
+    # the flow-stress block is the same in both
+    assert np.allclose(H[2:, 2:], Href[2:, 2:], rtol=1e-12)
+
+
+def test_hessian_transform_matches_oracle_restatement():
+    """Parameters.transform_hessian (parameters.py:334-357) on log and bounds transforms."""
+    values, act, tr = objective_trees("J2", True)
+    P, Po = Parameters(values, act, tr), co.OracleParameters(*objective_trees("J2", True))
+    x = np.array([0.2, -0.3, 0.1])
+    P.set_active_values_from_flat(x, True); Po.set_active_values_from_flat(x, True)
+    rng = np.random.default_rng(0)
+    H = rng.standard_normal((3, 3)); H = H + H.T
+    g = rng.standard_normal(3)
+    H1, H2 = H.copy(), H.copy()
+    P.transform_hessian(H1, g); co.transform_hessian(Po, H2, g)
+    assert np.allclose(H1, H2, rtol=1e-15) and np.array_equal(H1, H1.T)
+    assert not np.allclose(H1, H)
+
+
+# ------------------------------------------------------------------------------------------ #
+#  GPU                                                                                       #
+# ------------------------------------------------------------------------------------------ #
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES)
+def test_cuda_hessian_vs_reference(cuda_device, case):
+    from cmad_b200.objectives import (Calibration, HessianResult, MPAdjointObjective, MPDirectAdjointObjective,
+                                      SmallElasticPlastic)
+    kind, mode = case.split(".")
+    x = HS[f"{case}.x_canonical"]
+    F, data, w = HS[f"{case}.F"], HS[f"{case}.data"], HS[f"{case}.weight"]
+    P = Parameters(*objective_trees(kind, mode == "scaled"))
+    obj = MPDirectAdjointObjective(Calibration(SmallElasticPlastic(P), data, w), F, device=cuda_device,
+                                   reference_qoi_cross_terms=True)
+    r = obj.evaluate(x)
+    assert isinstance(r, HessianResult)
+    assert abs(r.J - HS[f"{case}.J"]) < 1e-11 * abs(r.J)
+    assert np.abs(r.grad - HS[f"{case}.grad"]).max() < 1e-9 * np.abs(r.grad).max()
+    assert hess_err(r.hessian, HS[f"{case}.hessian"]) < 1e-8, hess_err(r.hessian, HS[f"{case}.hessian"])
+    assert np.array_equal(r.hessian, r.hessian.T)
+    # same J and gradient as the plain adjoint objective; bit-reproducible
+    P2 = Parameters(*objective_trees(kind, mode == "scaled"))
+    ra = MPAdjointObjective(Calibration(SmallElasticPlastic(P2), data, w), F, device=cuda_device).evaluate(x)
+    assert ra.J == r.J and np.array_equal(ra.grad, r.grad)
+    r2 = obj.evaluate(x)
+    assert np.array_equal(r.hessian, r2.hessian)
+    # the complete Hessian differs from the reference's exactly when elastic parameters are active
+    P3 = Parameters(*objective_trees(kind, mode == "scaled"))
+    rc = MPDirectAdjointObjective(Calibration(SmallElasticPlastic(P3), data, w), F, device=cuda_device).evaluate(x)
+    if mode == "scaled":
+        assert hess_err(rc.hessian, r.hessian) < 1e-12
+    else:
+        assert hess_err(rc.hessian, r.hessian) > 1e-3
+        assert hess_err(rc.hessian[2:, 2:], r.hessian[2:, 2:]) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["J2", "hill", "hosford"])
+def test_cuda_hessian_batch_vs_oracle_and_fd(cuda_device, kind):
+    """A batch of points: (i) the summed Hessian of the first few points against the torch
+    oracle run point by point; (ii) every Hessian column of the whole batch against central
+    differences of the CUDA adjoint gradient in native parameter values."""
+    import torch
+    from cmad_b200.objectives import SmallElasticPlastic, gpu_local_evaluator
+    from tests.helpers import param_tree
+    from tests.test_objectives_host import _problem
+    hill = (0.45, 0.6, 0.55, 1.4, 1.6, 1.5) if kind == "hill" else None
+    active = ("E", "nu", "D", "S", "Y") + (("F", "L", "N") if kind == "hill" else ())
+    values, act, tr = param_tree(kind, ("voce",), hill=hill, active=active)
+    P = Parameters(values, act, tr)
+    na = P.num_active_params
+    model = SmallElasticPlastic(P)
+    # (i) 4 points against the oracle
+    sh, data, w = _problem(n=4, N=10, seed=3, kind=kind)
+    out = gpu_local_evaluator(model, sh, data, w, "direct_adjoint", cuda_device)().cpu().numpy()
+    Jo, go, Ho = 0.0, np.zeros(na), np.zeros((na, na))
+    for p in range(4):
+        F = np.repeat(np.eye(3)[:, :, None], 11, axis=2)
+        for t in range(11):
+            e = sh[t, :, p]
+            F[:, :, t] += np.array([[e[0], e[1], e[2]], [e[1], e[3], e[4]], [e[2], e[4], e[5]]])
+        Po = co.OracleParameters(*param_tree(kind, ("voce",), hill=hill, active=active))
+        J, g, H = co.mp_objective_direct_adjoint(Po, F, data[:, :, p].T.reshape(3, 3, 11), w, co.ModelSpec())
+        Jo += J; go += g; Ho += H                       # no transforms in this tree: native == canonical
+    assert abs(out[0] - Jo) < 1e-11 * abs(Jo)
+    assert np.abs(out[1:1 + na] - go).max() < 1e-9 * np.abs(go).max()
+    Hg = out[1 + na:].reshape(na, na)
+    assert hess_err(Hg, Ho) < 1e-8, hess_err(Hg, Ho)
+    # (ii) FD of the adjoint gradient over a large batch
+    sh, data, w = _problem(n=5000, N=10, seed=5, kind=kind)
+    ev_h = gpu_local_evaluator(model, sh, data, w, "direct_adjoint", cuda_device)
+    ev_g = gpu_local_evaluator(model, sh, data, w, "adjoint", cuda_device)
+    out = ev_h().cpu().numpy()
+    H = out[1 + na:].reshape(na, na)
+    assert np.array_equal(H, H.T)
+    assert np.array_equal(ev_h().cpu().numpy(), out)                   # deterministic
+    p0 = P.flat_active_values(False).copy()
+    for c in range(na):
+        h = 1e-6 * abs(p0[c])
+        gs = []
+        for sgn in (1.0, -1.0):
+            pp = p0.copy(); pp[c] += sgn * h
+            P.set_active_values_from_flat(pp, False)
+            gs.append(ev_g().cpu().numpy()[1:].copy())
+        P.set_active_values_from_flat(p0, False)
+        fd = (gs[0] - gs[1]) / (2 * h)
+        d = np.sqrt(np.abs(np.diag(H)))
+        assert (np.abs(fd - H[:, c]) / (d * d[c])).max() < 2e-5, (c, fd, H[:, c])
