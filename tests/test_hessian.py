@@ -178,3 +178,63 @@ def test_cuda_hessian_batch_vs_oracle_and_fd(cuda_device, kind):
         fd = (gs[0] - gs[1]) / (2 * h)
         d = np.sqrt(np.abs(np.diag(H)))
         assert (np.abs(fd - H[:, c]) / (d * d[c])).max() < 2e-5, (c, fd, H[:, c])
+
+
+# ------------------------------------------------------------------------------------------ #
+#  world size 2 (gloo): the Hessian objective's single all-reduce of 1 + P_a + P_a^2 doubles  #
+# ------------------------------------------------------------------------------------------ #
+def _hess_local_evaluator(P, Fs, datas, w):
+    """Oracle-backed stand-in for the CUDA evaluator: this rank's (J, grad, H) in native
+    parameter values, summed over its points."""
+    import torch
+
+    def ev():
+        na = P.num_active_params
+        out = np.zeros(1 + na + na * na)
+        for F, data in zip(Fs, datas):
+            Po = co.OracleParameters(*objective_trees("J2", True))
+            Po.set_active_values_from_flat(P.flat_active_values(False), False)
+            Po._flat_active_transforms = [None] * na              # native values, no chain rule here
+            J, g, H = co.mp_objective_direct_adjoint(Po, F, data, w, co.ModelSpec())
+            out += np.concatenate([[J], g, H.reshape(-1)])
+        return torch.tensor(out)
+    return ev
+
+
+def _gloo_hess_worker(rank, world, port, Fs, datas, w, x, ret):
+    import torch.distributed as dist
+    from cmad_b200.objectives import BatchedMPObjective, shard_range
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P = Parameters(*objective_trees("J2", True))
+    lo, hi = shard_range(len(Fs), rank, world)
+    res = BatchedMPObjective(P, _hess_local_evaluator(P, Fs[lo:hi], datas[lo:hi], w)).evaluate(x)
+    if rank == 0:
+        ret["J"], ret["grad"], ret["hessian"] = res.J, res.grad, res.hessian
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_hessian_equals_single_process():
+    import torch.multiprocessing as tmp
+    from cmad_b200.objectives import BatchedMPObjective, HessianResult
+    case = "J2.scaled"
+    F, data, w, x = (HS[f"{case}.{k}"] for k in ("F", "data", "weight", "x_canonical"))
+    F, data = F[:, :, :5], data[:, :, :5]
+    Fs = [F, np.eye(3)[:, :, None] + 0.8 * (F - np.eye(3)[:, :, None]), F]
+    datas = [data, 0.9 * data, 1.05 * data]                       # 3 points: ragged 2 + 1 split
+    P = Parameters(*objective_trees("J2", True))
+    single = BatchedMPObjective(P, _hess_local_evaluator(P, Fs, datas, w)).evaluate(x)
+    assert isinstance(single, HessianResult)
+    mgr = tmp.Manager(); ret = mgr.dict()
+    port = 29000 + (os.getpid() + 7) % 2000
+    tmp.spawn(_gloo_hess_worker, args=(2, port, Fs, datas, w, x, ret), nprocs=2, join=True)
+    assert abs(ret["J"] - single.J) < 1e-12 * abs(single.J)
+    assert np.allclose(ret["grad"], single.grad, rtol=1e-11, atol=0)
+    assert hess_err(ret["hessian"], single.hessian) < 1e-11
+    # canonical chain rule (log / bounds transforms) applied once, after the reduction: the
+    # one-point oracle with transforms gives the same numbers
+    Po = co.OracleParameters(*objective_trees("J2", True))
+    J1, g1, H1 = co.mp_objective_direct_adjoint(Po, Fs[0], datas[0], w, co.ModelSpec(), x, True)
+    P1 = Parameters(*objective_trees("J2", True))
+    one = BatchedMPObjective(P1, _hess_local_evaluator(P1, Fs[:1], datas[:1], w)).evaluate(x)
+    assert np.allclose(one.grad, g1, rtol=1e-11) and hess_err(one.hessian, H1) < 1e-11
