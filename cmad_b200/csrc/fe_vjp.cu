@@ -23,13 +23,14 @@ namespace {
 
 constexpr int VJP_BLOCK = 128;
 
-template <int YK, bool ROT>
-__global__ void __launch_bounds__(VJP_BLOCK)
+template <int YK, bool ROT, int NB>
+__global__ void __launch_bounds__(VJP_BLOCK, (YK == CMADX_YIELD_J2 && !ROT) ? 4 : 1)
 fe_vjp_kernel(const __grid_constant__ FeArgs A, const double* __restrict__ Rbar,
               const double* __restrict__ xibar, double* __restrict__ partials) {
     const cmadx_fe_block_t& b = A.b;
     const DevMat& m = A.m;
-    const int nb = b.n_basis, nip = b.n_ip, na = A.n_active;
+    constexpr int nb = NB;
+    const int nip = b.n_ip, na = A.n_active;
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t npts = b.n_elems * nip;
     const bool live = p < npts;
@@ -45,12 +46,22 @@ fe_vjp_kernel(const __grid_constant__ FeArgs A, const double* __restrict__ Rbar,
     double xs[7], xp[7], xb[7];
     double wdv = 0.0;
     if (live) {
+        // the point's grad_N rows and the element's equation row as whole 32- / 16-byte chunks
         const double* gN = b.grad_N + (p * nb) * 3;
+        double gr[NB * 3];
+        int eqr[NB * 3];
+#pragma unroll
+        for (int q = 0; q < NB * 3 / 4; ++q) {
+            ld256(gN + 4 * q, gr[4 * q], gr[4 * q + 1], gr[4 * q + 2], gr[4 * q + 3]);
+            const int4 v = __ldg(reinterpret_cast<const int4*>(b.elem_eq + e * (NB * 3)) + q);
+            eqr[4 * q] = v.x; eqr[4 * q + 1] = v.y; eqr[4 * q + 2] = v.z; eqr[4 * q + 3] = v.w;
+        }
+#pragma unroll
         for (int a = 0; a < nb; ++a) {
-            const double g0 = __ldg(gN + 3 * a), g1 = __ldg(gN + 3 * a + 1), g2 = __ldg(gN + 3 * a + 2);
+            const double g0 = gr[3 * a], g1 = gr[3 * a + 1], g2 = gr[3 * a + 2];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const int eq = __ldg(b.elem_eq + e * (nb * 3) + 3 * a + k);
+                const int eq = eqr[3 * a + k];
                 const double u = __ldg(b.U + eq), rb = __ldg(Rbar + eq);
                 gu[k][0] = fma(u, g0, gu[k][0]); gu[k][1] = fma(u, g1, gu[k][1]); gu[k][2] = fma(u, g2, gu[k][2]);
                 // R[a][i] = sum_j gN[a][j] sigma[j][i] w dv  ->  sbar[j][i] += gN[a][j] Rbar[a][i]
@@ -131,31 +142,37 @@ fe_vjp_kernel(const __grid_constant__ FeArgs A, const double* __restrict__ Rbar,
     const double strb = sbar[0] + sbar[3] + sbar[5];
 #pragma unroll
     for (int c = 0; c < 6; ++c) xb[c] += is_diag(c) ? fma(-m.two_mu, sbar[c], -m.lam * strb) : -m.two_mu * sbar[c];
-    // mu = -A^{-T} xbar
-    RegLU<7> lu;
-    {
-        double Jm[7][7];
-        pt.jacobian(m, dg, Jm);
-#pragma unroll
-        for (int a = 0; a < 7; ++a)
-#pragma unroll
-            for (int c = 0; c < 7; ++c) lu.a[a][c] = Jm[c][a];
-    }
-    const bool trouble = lu.factor_natural();
-    const bool slow = __any_sync(__activemask(), trouble);
-    if (slow && trouble) {
-        double Jm[7][7];
-        pt.jacobian(m, dg, Jm);
-#pragma unroll
-        for (int a = 0; a < 7; ++a)
-#pragma unroll
-            for (int c = 0; c < 7; ++c) lu.a[a][c] = Jm[c][a];
-        lu.factor_pivot();
-    }
+    // mu = -A^{-T} xbar.  J2: the Jacobian's inverse in closed form (j2_radial.cuh), no LU;
+    // other surfaces: threshold-pivoted register LU of the transposed Jacobian
     double mu[7];
 #pragma unroll
     for (int c = 0; c < 7; ++c) mu[c] = xb[c];
-    if (slow && trouble) lu.solve_pivot(mu); else lu.solve_natural(mu);
+    constexpr bool CLOSED = (YK == CMADX_YIELD_J2);
+    if constexpr (CLOSED) {
+        j2_jacobian_solve<true>(m, pt, dg, mu);
+    } else {
+        RegLU<7> lu;
+        {
+            double Jm[7][7];
+            pt.jacobian(m, dg, Jm);
+#pragma unroll
+            for (int a = 0; a < 7; ++a)
+#pragma unroll
+                for (int c = 0; c < 7; ++c) lu.a[a][c] = Jm[c][a];
+        }
+        const bool trouble = lu.factor_natural();
+        const bool slow = __any_sync(__activemask(), trouble);
+        if (slow && trouble) {
+            double Jm[7][7];
+            pt.jacobian(m, dg, Jm);
+#pragma unroll
+            for (int a = 0; a < 7; ++a)
+#pragma unroll
+                for (int c = 0; c < 7; ++c) lu.a[a][c] = Jm[c][a];
+            lu.factor_pivot();
+        }
+        if (slow && trouble) lu.solve_pivot(mu); else lu.solve_natural(mu);
+    }
 #pragma unroll
     for (int c = 0; c < 7; ++c) mu[c] = -mu[c];
     // xibar_prev = B^T mu;  B = [-I, n; 0, 0] (plastic) or -I (elastic)
@@ -167,12 +184,15 @@ fe_vjp_kernel(const __grid_constant__ FeArgs A, const double* __restrict__ Rbar,
     }
     // pbar
     double Mee[6], nee = 0.0, see = 0.0;
+    if constexpr (CLOSED) pt.yf.Mvec(ee, Mee);
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
-        double s = 0.0;
+        if constexpr (!CLOSED) {
+            double s = 0.0;
 #pragma unroll
-        for (int q = 0; q < 6; ++q) s = fma(pt.yf.M(a, q), ee[q], s);
-        Mee[a] = s;
+            for (int q = 0; q < 6; ++q) s = fma(pt.yf.M(a, q), ee[q], s);
+            Mee[a] = s;
+        }
         nee = fma(mult(a) * pt.n[a], ee[a], nee);
         see = fma(sbar[a], ee[a], see);
     }
@@ -219,8 +239,13 @@ fe_vjp_kernel(const __grid_constant__ FeArgs A, const double* __restrict__ Rbar,
 template <int YK>
 cudaError_t launch_yk(const FeArgs& A, const double* Rbar, const double* xibar, double* partials,
                       unsigned nblk, cudaStream_t s) {
-    if (A.m.rot) fe_vjp_kernel<YK, true><<<nblk, VJP_BLOCK, 0, s>>>(A, Rbar, xibar, partials);
-    else fe_vjp_kernel<YK, false><<<nblk, VJP_BLOCK, 0, s>>>(A, Rbar, xibar, partials);
+    if (A.b.n_basis == 4) {
+        if (A.m.rot) fe_vjp_kernel<YK, true, 4><<<nblk, VJP_BLOCK, 0, s>>>(A, Rbar, xibar, partials);
+        else fe_vjp_kernel<YK, false, 4><<<nblk, VJP_BLOCK, 0, s>>>(A, Rbar, xibar, partials);
+    } else {
+        if (A.m.rot) fe_vjp_kernel<YK, true, 8><<<nblk, VJP_BLOCK, 0, s>>>(A, Rbar, xibar, partials);
+        else fe_vjp_kernel<YK, false, 8><<<nblk, VJP_BLOCK, 0, s>>>(A, Rbar, xibar, partials);
+    }
     return cudaGetLastError();
 }
 
