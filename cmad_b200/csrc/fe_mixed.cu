@@ -36,8 +36,31 @@ __global__ void __launch_bounds__(FE_BLOCK, 4) fe_mixed_pressure_kernel(const cm
     const double tau = mx.stab_mult * 0.5 * h * h / mu;
     const double ik = 1.0 / kappa;
     double Rp = 0.0;
-    // column blocks of 4 nodes keep the accumulators (28 doubles) and the staged grad_N
-    // quarter in registers at 4 blocks / SM; the re-read of grad_N per block hits L1
+    // hex8: the element's grad_N (8 points x 24 doubles) is staged ONCE in shared memory by
+    // contiguous 32-byte chunks (the 8 threads of an element cover 256 contiguous bytes per
+    // request) and every later read is a broadcast within the element; the region stride of
+    // 194 doubles puts the 4 elements of a warp 4 banks apart, so 128-bit reads of the same
+    // offset are conflict-free.  (Before: every thread re-read the chunks through L1 - 8x the
+    // wavefronts, the kernel was L1-data-pipe bound.)  tet4 keeps the direct loads (12 doubles).
+    constexpr int REGION = 194;
+    __shared__ __align__(16) double smem[(NB == 8) ? (FE_BLOCK / 8) * REGION : 2];
+    const double* reg = smem + (threadIdx.x >> 3) * REGION;
+    if constexpr (NB == 8) {
+        double* wr = smem + (threadIdx.x >> 3) * REGION;
+        const double* g = b.grad_N + el * (NIP * NB * 3);
+        double c[6][4];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) ld256(g + 4 * (a + 8 * r), c[r][0], c[r][1], c[r][2], c[r][3]);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            double2* dst = reinterpret_cast<double2*>(wr + 4 * (a + 8 * r));
+            dst[0] = make_double2(c[r][0], c[r][1]);
+            dst[1] = make_double2(c[r][2], c[r][3]);
+        }
+        __syncwarp();
+    }
+    // column blocks of 4 nodes keep the accumulators (28 doubles) and the grad_N quarter in
+    // registers at 4 blocks / SM
 #pragma unroll 1
     for (int cb = 0; cb < NB / 4; ++cb) {
         double Kpu[4][3], Kup[3][4], Kpp[4];
@@ -51,17 +74,29 @@ __global__ void __launch_bounds__(FE_BLOCK, 4) fe_mixed_pressure_kernel(const cm
         for (int q = 0; q < NIP; ++q) {
             const double* g = b.grad_N + (el * NIP + q) * (NB * 3);
             double gN[4][3], N[4];
+            if constexpr (NB == 8) {
+                const double2* src = reinterpret_cast<const double2*>(reg + q * 24 + 12 * cb);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                double v0, v1, v2, v3;
-                ld256(g + 12 * cb + 4 * c, v0, v1, v2, v3);
-                (&gN[0][0])[4 * c] = v0; (&gN[0][0])[4 * c + 1] = v1; (&gN[0][0])[4 * c + 2] = v2; (&gN[0][0])[4 * c + 3] = v3;
+                for (int c = 0; c < 6; ++c) {
+                    const double2 v = src[c];
+                    (&gN[0][0])[2 * c] = v.x; (&gN[0][0])[2 * c + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    double v0, v1, v2, v3;
+                    ld256(g + 12 * cb + 4 * c, v0, v1, v2, v3);
+                    (&gN[0][0])[4 * c] = v0; (&gN[0][0])[4 * c + 1] = v1; (&gN[0][0])[4 * c + 2] = v2; (&gN[0][0])[4 * c + 3] = v3;
+                }
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) N[c] = __ldg(mx.N + q * NB + 4 * cb + c);
             const double wdv = __ldg(b.quad_w + q) * __ldg(b.det + el * NIP + q);
             const double Na = __ldg(mx.N + q * NB + a) * wdv;
-            const double ga0 = __ldg(g + 3 * a) * wdv, ga1 = __ldg(g + 3 * a + 1) * wdv, ga2 = __ldg(g + 3 * a + 2) * wdv;
+            const double gu0 = (NB == 8) ? reg[q * 24 + 3 * a] : __ldg(g + 3 * a);
+            const double gu1 = (NB == 8) ? reg[q * 24 + 3 * a + 1] : __ldg(g + 3 * a + 1);
+            const double gu2 = (NB == 8) ? reg[q * 24 + 3 * a + 2] : __ldg(g + 3 * a + 2);
+            const double ga0 = gu0 * wdv, ga1 = gu1 * wdv, ga2 = gu2 * wdv;
             if (cb == 0) {
                 double p = Na * pa, tre = fma(Ua[2], ga2, fma(Ua[1], ga1, Ua[0] * ga0));    // x w dv
                 double gp[3] = {pa * ga0, pa * ga1, pa * ga2};
@@ -74,7 +109,6 @@ __global__ void __launch_bounds__(FE_BLOCK, 4) fe_mixed_pressure_kernel(const cm
                 }
                 // p, tre, gp carry one factor w dv; N_a and gradN_a (unweighted) = Na / wdv ...
                 const double Nu = __ldg(mx.N + q * NB + a);
-                const double gu0 = __ldg(g + 3 * a), gu1 = __ldg(g + 3 * a + 1), gu2 = __ldg(g + 3 * a + 2);
                 Rp -= fma(p, ik, tre) * Nu + tau * fma(gu2, gp[2], fma(gu1, gp[1], gu0 * gp[0]));
             }
 #pragma unroll
