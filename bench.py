@@ -187,6 +187,10 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the ONE JSON line: NCCL prints its version banner there at
+        # NCCL_DEBUG=VERSION (the GPU boxes' default); explicit INFO / TRACE requests are kept
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     values, params, mat, pid, newton = material_setup()
     K, W = args.steps, args.warmup
