@@ -41,7 +41,7 @@ cudaError_t launch_mp_sens(const SensArgs& A, bool adjoint, cudaStream_t stream)
 cudaError_t launch_mp_sens_dt(const SensArgs& A, int def_type, bool adjoint, cudaStream_t stream);
 int64_t sens_blocks(int64_t n);
 int64_t hess_blocks(int64_t n);
-cudaError_t launch_mp_hess(const SensArgs& A, double* pair_sums, double* H_out, cudaStream_t stream);
+cudaError_t launch_mp_hess(const SensArgs& A, int def_type, double* pair_sums, double* H_out, cudaStream_t stream);
 }  // namespace cmadx
 
 namespace cmadx {
@@ -626,7 +626,8 @@ static int64_t hess_partials_doubles(int64_t n, int32_t n_active) {
 int64_t cmadx_mp_hessian_workspace_bytes(int64_t n, int64_t ld, int32_t nsteps, int32_t n_active) {
     if (n < 0 || ld < n || nsteps < 0 || n_active < 0 || n_active > CMADX_MAX_ACTIVE) return -1;
     const int64_t npairs = (int64_t)n_active * (n_active + 1) / 2;
-    return (int64_t)sizeof(double) * ((int64_t)(nsteps + 1) * 7 * ld + hess_partials_doubles(n, n_active) + npairs + 1);
+    // phi_hist is sized for the largest local system (n_xi = 9, UNIAXIAL_STRESS)
+    return (int64_t)sizeof(double) * ((int64_t)(nsteps + 1) * 9 * ld + hess_partials_doubles(n, n_active) + npairs + 1);
 }
 
 int cmadx_mp_objective_hessian(const cmadx_material_t* mat, const int32_t* active_pid,
@@ -636,7 +637,8 @@ int cmadx_mp_objective_hessian(const cmadx_material_t* mat, const int32_t* activ
     if (flags & ~CMADX_HESS_F_REFERENCE_QOI_CROSS) return CMADX_EINVAL;
     A.hess_flags = flags;
     if (int rc = check_history(mat, hist, &A.m)) return rc;
-    if (A.m.rot || history_def_type(hist) != CMADX_DEF_FULL_3D) return CMADX_EUNSUPPORTED;
+    if (A.m.rot) return CMADX_EUNSUPPORTED;
+    const int dt = history_def_type(hist);
     if (n_active < 0 || n_active > CMADX_MAX_ACTIVE || (n_active > 0 && !active_pid)) return CMADX_EINVAL;
     if (!hist->result || !hist->workspace || (hist->n > 0 && !hist->data)) return CMADX_EINVAL;
     for (int c = 0; c < n_active; ++c) {
@@ -648,12 +650,13 @@ int cmadx_mp_objective_hessian(const cmadx_material_t* mat, const int32_t* activ
     A.n_active = n_active;
     A.h = *hist;
     A.phi_hist = hist->workspace;
-    A.partials = hist->workspace + (int64_t)(hist->nsteps + 1) * 7 * hist->ld;
+    A.partials = hist->workspace + (int64_t)(hist->nsteps + 1) * 9 * hist->ld;
     double* pair_sums = A.partials + hess_partials_doubles(hist->n, n_active);
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = launch_mp_sens(A, true, s);            // J, dJ/dp, and phi_t for every step
+    // J, dJ/dp, and phi_t for every step
+    cudaError_t e = (dt == CMADX_DEF_FULL_3D) ? launch_mp_sens(A, true, s) : launch_mp_sens_dt(A, dt, true, s);
     if (e != cudaSuccess) return cuda_fail(e);
-    e = launch_mp_hess(A, pair_sums, hist->result + 1 + n_active, s);
+    e = launch_mp_hess(A, dt, pair_sums, hist->result + 1 + n_active, s);
     if (e != cudaSuccess) return cuda_fail(e);
     g_launches.fetch_add(n_active > 0 ? 5 : 2, std::memory_order_relaxed);
     return CMADX_OK;

@@ -18,10 +18,12 @@
 //
 // One thread per material point walks its history forward; X_t / X_{t-1} and the pair
 // accumulators live in local memory (this is the small-batch calibration path, not a bench
-// line).  The pair sums are reduced in fixed order (bit-reproducible).  FULL_3D, identity
-// material axes; d/d(hosford a) and d/d(rotation) are not provided (as in K2).
+// line).  The pair sums are reduced in fixed order (bit-reproducible).  FULL_3D, PLANE_STRESS and
+// UNIAXIAL_STRESS with identity material axes; d/d(hosford a) and d/d(rotation) are not
+// provided (as in K2).
 #include "mp_outputs.cuh"
 #include "mp_sens.cuh"
+#include "sep_point_dt.cuh"
 
 namespace cmadx {
 cudaError_t launch_reduce_partials(const double* partials, int64_t nblk, int ncols, double* result,
@@ -371,6 +373,231 @@ __global__ void __launch_bounds__(HESS_BLOCK) mp_hess_kernel(const __grid_consta
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// PLANE_STRESS / UNIAXIAL_STRESS (n_xi = 8 / 9): the reference's Hessian known answer (KA5,
+// tests/objectives/test_jvp_vs_original.py:75-97) lives in plane stress.  Same scheme; the
+// bordered residual (sep_point_dt.cuh: stretch unknowns, stress-constraint rows cauchy_cc/2mu)
+// is evaluated in hyper-dual arithmetic, the linear algebra of X_t reuses SepPointDT.
+template <int DT, int N>
+CMADX_DEV void stress_hd_dt(const HD& lam, const HD& mu, const HD (&x)[N], const double (&em)[6],
+                            HD (&ee)[6], HD (&sig)[6]) {
+    HD et[6];
+    if (DT == CMADX_DEF_PLANE_STRESS) {
+        et[0] = hd(em[0]); et[1] = hd(em[1]); et[2] = hd(0.0); et[3] = hd(em[3]); et[4] = hd(0.0); et[5] = x[7] - 1.0;
+    } else {
+        et[0] = hd(em[0]); et[1] = x[1]; et[2] = x[2]; et[3] = x[7] - 1.0; et[4] = x[4]; et[5] = x[8] - 1.0;
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) ee[a] = et[a] - x[a];
+    const HD ltr = lam * (ee[0] + ee[3] + ee[5]);
+    const HD two_mu = 2.0 * mu;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) sig[a] = is_diag(a) ? two_mu * ee[a] + ltr : two_mu * ee[a];
+}
+
+template <int DT, int N>
+__device__ __noinline__ double qoi_cross_terms_dt(const HD& lam, const HD& mu, const HD (&x)[N],
+                                                  const double (&em)[6], const double (&w)[9],
+                                                  const double (&d)[9]) {
+    double acc = 0.0;
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+        const HD l = side ? HD{lam.v, 0.0, lam.b, 0.0} : HD{lam.v, lam.a, 0.0, 0.0};
+        const HD u = side ? HD{mu.v, 0.0, mu.b, 0.0} : HD{mu.v, mu.a, 0.0, 0.0};
+        HD xs[N], ee[6], sig[6];
+#pragma unroll
+        for (int r = 0; r < N; ++r) xs[r] = side ? HD{x[r].v, x[r].a, 0.0, 0.0} : HD{x[r].v, 0.0, x[r].b, 0.0};
+        stress_hd_dt<DT, N>(l, u, xs, em, ee, sig);
+        acc += qoi_hd(sig, w, d).ab;
+    }
+    return acc;
+}
+
+template <int YK, int DT, int N>
+__device__ __noinline__ double lagrangian_mixed_dt(const DevMat& m, const HessParams& P, const HD (&x)[N],
+                                                   const HD (&xp)[N], const double (&em)[6],
+                                                   const double (&phi)[N], const double (&w)[9],
+                                                   const double (&d)[9], bool plastic) {
+    constexpr int NZ = N - 7;
+    HD ee[6], sig[6];
+    stress_hd_dt<DT, N>(P.lam, P.mu, x, em, ee, sig);
+    const HD two_mu = 2.0 * P.mu;
+    const HD i2m = inv(two_mu);
+    HD L = qoi_hd(sig, w, d);
+    if (plastic) {
+        HD pe, n[6];
+        yield_hd<YK>(m, P, sig, pe, n);
+        HD hard = P.Y;
+        if (m.hmask & CMADX_HARD_VOCE) hard = hard + P.S * (1.0 - hexp(-(P.D * x[6])));
+        if (m.hmask & CMADX_HARD_LINEAR) hard = hard + P.K * x[6];
+        const HD f = (pe - hard) * i2m;
+        const HD dg = x[6] - xp[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) L = L + phi[a] * (x[a] - xp[a] - dg * n[a]);
+        L = L + phi[6] * f;
+    } else {
+#pragma unroll
+        for (int a = 0; a < 7; ++a) L = L + phi[a] * (x[a] - xp[a]);
+    }
+    // stress-constraint rows (both branches): cauchy_cc / 2mu for the stretch-driven components
+#pragma unroll
+    for (int k = 0; k < NZ; ++k) L = L + phi[7 + k] * (sig[SepPointDT<YK, DT>::zcomp(k)] * i2m);
+    return L.ab;
+}
+
+template <int YK, int DT>
+__global__ void __launch_bounds__(HESS_BLOCK) mp_hess_dt_kernel(const __grid_constant__ SensArgs A) {
+    using Pt = SepPointDT<YK, DT>;
+    constexpr int N = Pt::N, NZ = Pt::NZ;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < A.h.n;
+    const int64_t ld = A.h.ld;
+    const DevMat& m = A.m;
+    const int NT = A.h.nsteps, na = A.n_active, sc = A.h.strain_comps;
+    const int npairs = na * (na + 1) / 2;
+
+    double Hacc[HESS_MAX_PAIRS];
+    for (int q = 0; q < npairs; ++q) Hacc[q] = 0.0;
+    double X[CMADX_MAX_ACTIVE][N], Xp[CMADX_MAX_ACTIVE][N];
+    for (int c = 0; c < na; ++c)
+#pragma unroll
+        for (int r = 0; r < N; ++r) { X[c][r] = 0.0; Xp[c][r] = 0.0; }
+    double x[N], xp[N];
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        const double v = live ? __ldg(A.h.xi_hist + c * ld + i) : ((c < 7) ? 0.0 : 1.0);
+        x[c] = v; xp[c] = v;
+    }
+    for (int t = 1; t <= NT; ++t) {
+        double em[6] = {1e-3, 0.0, 0.0, 0.0, 0.0, 0.0}, d[9], phi[N];
+        if (live) {
+            const double* xs = A.h.xi_hist + (int64_t)t * N * ld + i;
+            const double* ph = A.phi_hist + (int64_t)t * N * ld + i;
+#pragma unroll
+            for (int c = 0; c < N; ++c) { x[c] = __ldg(xs + c * ld); phi[c] = ph[c * ld]; }
+            load_dt_strain<DT>(A.h.strain + (int64_t)t * sc * ld, sc, ld, i, em);
+            const double* ds = A.h.data + (int64_t)t * 9 * ld + i;
+#pragma unroll
+            for (int c = 0; c < 9; ++c) d[c] = __ldg(ds + c * ld);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 9; ++c) d[c] = 0.0;
+#pragma unroll
+            for (int c = 0; c < N; ++c) phi[c] = 0.0;
+        }
+        // ---- forward sensitivities X_t = A^{-1}(-dC/dp - B X_{t-1}) as in mp_sens_dt.cu
+        Pt pt;
+        double C[N];
+        pt.residual(m, x, xp, em, C);
+        const bool pl = pt.plastic;
+        const double dg = x[6] - xp[6];
+        double et[6], ee[6], sig[6];
+        pt.total_strain(x, em, et);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) ee[a] = et[a] - x[a];
+        const double tree = ee[0] + ee[3] + ee[5];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) sig[a] = is_diag(a) ? fma(m.two_mu, ee[a], m.lam * tree) : m.two_mu * ee[a];
+        double Mee[6], nee = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) sacc = fma(pt.b.yf.M(a, b), ee[b], sacc);
+            Mee[a] = sacc;
+            nee = fma(mult(a) * pt.b.n[a], ee[a], nee);
+        }
+        RegLU<N> lu;
+        pt.jacobian(m, dg, lu.a);
+        const bool trouble = lu.factor_natural();
+        const bool slow = __any_sync(__activemask(), trouble);
+        if (slow && trouble) { pt.jacobian(m, dg, lu.a); lu.factor_pivot(); }
+        for (int c = 0; c < na; ++c) {
+            const int pid = A.pid[c];
+            double c7[7], rhs[N];
+            dC_dp_column(m, pid, pl, pt.b.yf, pt.b.n, pt.b.f, pt.b.eD, x[6], dg, Mee, nee, sig, c7);
+            double dr = 0.0;
+            if (pid == CMADX_P_EL0 || pid == CMADX_P_EL1) {
+                const int k = pid - CMADX_P_EL0;
+                dr = (m.dlam[k] * m.two_mu - m.lam * 2.0 * m.dmu[k]) * m.inv_two_mu * m.inv_two_mu * tree;
+            }
+            const double x6 = Xp[c][6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) rhs[q] = -c7[q] + Xp[c][q] - (pl ? pt.b.n[q] * x6 : 0.0);
+            rhs[6] = -c7[6] + (pl ? 0.0 : x6);
+#pragma unroll
+            for (int k = 0; k < NZ; ++k) rhs[7 + k] = -dr;
+            if (slow && trouble) lu.solve_pivot(rhs); else lu.solve_natural(rhs);
+#pragma unroll
+            for (int q = 0; q < N; ++q) X[c][q] = rhs[q];
+        }
+        int q = 0;
+#pragma unroll 1
+        for (int ci = 0; ci < na; ++ci) {
+#pragma unroll 1
+            for (int cj = ci; cj < na; ++cj, ++q) {
+                const int pi = A.pid[ci], pj = A.pid[cj];
+                HessParams P;
+                {
+                    const int ki = pi - CMADX_P_EL0, kj = pj - CMADX_P_EL0;
+                    const bool ei = (ki == 0 || ki == 1), ej = (kj == 0 || kj == 1);
+                    const int k2 = ki + kj;
+                    P.lam = {m.lam, ei ? m.dlam[ki] : 0.0, ej ? m.dlam[kj] : 0.0, (ei && ej) ? m.d2lam[k2] : 0.0};
+                    P.mu = {m.mu, ei ? m.dmu[ki] : 0.0, ej ? m.dmu[kj] : 0.0, (ei && ej) ? m.d2mu[k2] : 0.0};
+                }
+                P.Y = seed(m.Y, CMADX_P_Y, pi, pj);
+                P.S = seed(m.S, CMADX_P_VOCE_S, pi, pj);
+                P.D = seed(m.D, CMADX_P_VOCE_D, pi, pj);
+                P.K = seed(m.K, CMADX_P_LIN_K, pi, pj);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) P.hill[k] = seed(m.hill[k], CMADX_P_HILL_F + k, pi, pj);
+                HD xh[N], xph[N];
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    xh[r] = {x[r], X[ci][r], X[cj][r], 0.0};
+                    xph[r] = {xp[r], Xp[ci][r], Xp[cj][r], 0.0};
+                }
+                double hij = lagrangian_mixed_dt<YK, DT, N>(m, P, xh, xph, em, phi, A.h.weight, d, pl);
+                if (A.hess_flags & CMADX_HESS_F_REFERENCE_QOI_CROSS)
+                    hij -= qoi_cross_terms_dt<DT, N>(P.lam, P.mu, xh, em, A.h.weight, d);
+                Hacc[q] += hij;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < N; ++c) xp[c] = x[c];
+        for (int c = 0; c < na; ++c)
+#pragma unroll
+            for (int r = 0; r < N; ++r) Xp[c][r] = X[c][r];
+    }
+    __shared__ double sm[HESS_BLOCK / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = 0; q < npairs; ++q) {
+        double v = live ? Hacc[q] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) sm[warp] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+#pragma unroll
+            for (int wq = 0; wq < HESS_BLOCK / 32; ++wq) s += sm[wq];
+            A.partials[(int64_t)blockIdx.x * npairs + q] = s;
+        }
+        __syncthreads();
+    }
+}
+
+template <int DT>
+cudaError_t launch_hess_dt(const SensArgs& A, unsigned nblk, cudaStream_t stream) {
+    switch (A.m.yield) {
+    case CMADX_YIELD_J2: mp_hess_dt_kernel<CMADX_YIELD_J2, DT><<<nblk, HESS_BLOCK, 0, stream>>>(A); break;
+    case CMADX_YIELD_HILL: mp_hess_dt_kernel<CMADX_YIELD_HILL, DT><<<nblk, HESS_BLOCK, 0, stream>>>(A); break;
+    case CMADX_YIELD_HOSFORD: mp_hess_dt_kernel<CMADX_YIELD_HOSFORD, DT><<<nblk, HESS_BLOCK, 0, stream>>>(A); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 // upper-triangle pair sums -> full symmetric na x na matrix
 __global__ void expand_pairs_kernel(const double* pairs, int na, double* H) {
     const int ci = threadIdx.x / na, cj = threadIdx.x % na;
@@ -385,18 +612,25 @@ __global__ void expand_pairs_kernel(const double* pairs, int na, double* H) {
 int64_t hess_blocks(int64_t n) { return (n + HESS_BLOCK - 1) / HESS_BLOCK; }
 
 // partials: [nblk][npairs], pair_sums: [npairs] scratch, H_out: [na*na]
-cudaError_t launch_mp_hess(const SensArgs& A, double* pair_sums, double* H_out, cudaStream_t stream) {
+cudaError_t launch_mp_hess(const SensArgs& A, int def_type, double* pair_sums, double* H_out, cudaStream_t stream) {
     const int na = A.n_active, npairs = na * (na + 1) / 2;
     if (na == 0) return cudaSuccess;
     if (A.h.n == 0) return cudaMemsetAsync(H_out, 0, sizeof(double) * na * na, stream);
     const int64_t nblk = hess_blocks(A.h.n);
-    switch (A.m.yield) {
-    case CMADX_YIELD_J2: mp_hess_kernel<CMADX_YIELD_J2><<<(unsigned)nblk, HESS_BLOCK, 0, stream>>>(A); break;
-    case CMADX_YIELD_HILL: mp_hess_kernel<CMADX_YIELD_HILL><<<(unsigned)nblk, HESS_BLOCK, 0, stream>>>(A); break;
-    case CMADX_YIELD_HOSFORD: mp_hess_kernel<CMADX_YIELD_HOSFORD><<<(unsigned)nblk, HESS_BLOCK, 0, stream>>>(A); break;
-    default: return cudaErrorInvalidValue;
+    cudaError_t e;
+    if (def_type == CMADX_DEF_PLANE_STRESS) {
+        e = launch_hess_dt<CMADX_DEF_PLANE_STRESS>(A, (unsigned)nblk, stream);
+    } else if (def_type == CMADX_DEF_UNIAXIAL_STRESS) {
+        e = launch_hess_dt<CMADX_DEF_UNIAXIAL_STRESS>(A, (unsigned)nblk, stream);
+    } else {
+        switch (A.m.yield) {
+        case CMADX_YIELD_J2: mp_hess_kernel<CMADX_YIELD_J2><<<(unsigned)nblk, HESS_BLOCK, 0, stream>>>(A); break;
+        case CMADX_YIELD_HILL: mp_hess_kernel<CMADX_YIELD_HILL><<<(unsigned)nblk, HESS_BLOCK, 0, stream>>>(A); break;
+        case CMADX_YIELD_HOSFORD: mp_hess_kernel<CMADX_YIELD_HOSFORD><<<(unsigned)nblk, HESS_BLOCK, 0, stream>>>(A); break;
+        default: return cudaErrorInvalidValue;
+        }
+        e = cudaGetLastError();
     }
-    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     e = launch_reduce_partials(A.partials, nblk, npairs, pair_sums, stream);
     if (e != cudaSuccess) return e;

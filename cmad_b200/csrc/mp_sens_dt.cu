@@ -155,6 +155,11 @@ __global__ void __launch_bounds__(SENS_DT_BLOCK) mp_sens_dt_kernel(const __grid_
 #pragma unroll
             for (int c = 0; c < N; ++c) phi[c] = hist[c] - dJdx[c];
             solveN(phi);
+            if (A.phi_hist && live) {      // kept for the direct-adjoint Hessian pass (mp_hess.cu)
+                double* ph = A.phi_hist + (int64_t)t * N * ld + i;
+#pragma unroll
+                for (int c = 0; c < N; ++c) ph[c * ld] = phi[c];
+            }
             // h <- -B^T phi, B = dC/dxi_prev = [[-I, n, 0], [0, 0, 0], [0, 0, 0]] (plastic) or diag(-I7, 0)
             double nphi = 0.0;
 #pragma unroll

@@ -140,8 +140,6 @@ def gpu_local_evaluator(model: SmallElasticPlastic, strain_hist: np.ndarray, dat
     newton = newton or NewtonSettings(mode="imperative", max_iters=10, abs_tol=1e-14, rel_tol=1e-14)
     adjoint = {"adjoint": True, "direct": False, "direct_adjoint": True}[strategy]
     hessian = strategy == "direct_adjoint"
-    if hessian and nd != 3:
-        raise NotImplementedError("the Hessian pass covers FULL_3D only")
     w = np.asarray(weight, dtype=np.float64).reshape(9)
 
     def evaluate() -> torch.Tensor:

@@ -250,7 +250,8 @@ int cmadx_mp_objective_direct(const cmadx_material_t* mat, const int32_t* active
  * (dz/dp_i, dz/dp_j) - the templated forward-mode counterpart of Model.evaluate_hessians /
  * QoI.evaluate_hessians (cmad/models/model.py:134-148, 245-270).  `result` holds
  * 1 + n_active + n_active^2 doubles: J, grad, H row-major (symmetric).  `workspace` needs
- * cmadx_mp_hessian_workspace_bytes().  FULL_3D, identity material axes; deterministic.
+ * cmadx_mp_hessian_workspace_bytes().  FULL_3D, PLANE_STRESS and UNIAXIAL_STRESS (by
+ * strain_comps, as for the gradient entry points), identity material axes; deterministic.
  * flags: 0 = the complete Hessian (equals the derivative of the gradient).
  * CMADX_HESS_F_REFERENCE_QOI_CROSS reproduces the reference entry for entry: its QoI builds
  * the mixed block d2J/dxi dparams by differentiating w.r.t. xi_PREV (cmad/qois/qoi.py:53-55),

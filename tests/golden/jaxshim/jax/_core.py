@@ -417,7 +417,14 @@ def _np_pow(x, y):
 
 def power(a, b):
     def rule(pa, pb, ta, tb, o):
-        da = None if ta is None else ta * (pb * power(pa, pb - 1))
+        # integer exponents follow lax.integer_pow (what `x ** 2` lowers to): d/dx x**n =
+        # n x**(n-1), and x**0 is a constant - its derivative is an exact zero, never
+        # 0 * x**(-1) (which is NaN at x = 0 and would poison third derivatives of x**2)
+        b_ = _A(pb)
+        if ta is not None and b_.tag == 0 and np.issubdtype(b_.p.dtype, np.integer) and np.all(b_.p == 0):
+            da = ta * 0.0
+        else:
+            da = None if ta is None else ta * (pb * power(pa, pb - 1))
         db = None if tb is None else tb * (o * log(pa))
         return _addt(da, db)
     a, b = _A(a), _A(b)

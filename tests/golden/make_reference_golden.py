@@ -230,10 +230,12 @@ def _objective_job(job):
 def _hessian_job(job):
     """MPDirectAdjointObjective (mp_objective.py:218-343): J, gradient and Hessian in
     canonical coordinates through Model.evaluate_hessians / qoi.evaluate_hessians."""
-    kind, scaled, F, weight = job
+    kind, scaled, F, weight = job[:4]
+    dt_name = job[4] if len(job) > 4 else "FULL_3D"
+    from cmad.models.deformation_types import DefType
     values, act, tr = objective_trees(kind, scaled)
     P = Parameters(values, act, tr)
-    model = SmallElasticPlastic(P)
+    model = SmallElasticPlastic(P, def_type=DefType[dt_name])
     N = F.shape[2] - 1
     data = np.zeros((3, 3, N + 1))
     model.set_xi_to_init_vals()
@@ -243,9 +245,13 @@ def _hessian_job(job):
         model.seed_none(); model.evaluate_cauchy()
         data[:, :, step] = model.Sigma().copy()
         model.advance_xi()
-    qoi = Calibration(model, data, weight)
     true_vals = P.flat_active_values(False)
     offset = 1.1 * true_vals
+    # a FRESH parameters / model pair for the objective, as a run that reads its data from file
+    # has (the data-generation model above is not reused)
+    P = Parameters(*objective_trees(kind, scaled))
+    model = SmallElasticPlastic(P, def_type=DefType[dt_name])
+    qoi = Calibration(model, data, weight)
     P.set_active_values_from_flat(offset, False)
     x = P.flat_active_values(True)
     r = MPDirectAdjointObjective(qoi, F).evaluate(x)
@@ -545,6 +551,29 @@ def main():
                 out[f"{nm}.{k}"] = v
             print("hessian", nm, r["J"], r["grad"], np.linalg.eigvalsh(r["hessian"]))
         np.savez_compressed(os.path.join(HERE, "ref_mp_hessian.npz"), **out)
+
+    if only is None or "hessian_dt" in only:
+        # KA5 setting (tests/objectives/test_jvp_vs_original.py, test_J2_fd_checks.py:266-289): the
+        # Hessian in PLANE_STRESS (and UNIAXIAL_STRESS), in-plane / axial stress data only
+        jobs, names = [], []
+        for kind, scaled, dt_name in (("J2", True, "PLANE_STRESS"), ("J2", False, "PLANE_STRESS"),
+                                      ("hill", False, "PLANE_STRESS"), ("hosford", True, "PLANE_STRESS"),
+                                      ("J2", True, "UNIAXIAL_STRESS"), ("J2", False, "UNIAXIAL_STRESS")):
+            w = np.zeros((3, 3)); w[0, 0] = 1.0
+            if dt_name == "PLANE_STRESS":
+                w[1, 1] = 1.0; w[0, 1] = w[1, 0] = 0.5
+            jobs.append((kind, scaled, deftype_F(dt_name, nsteps=12), w, dt_name))
+            names.append(f"{kind}.{'scaled' if scaled else 'native'}.{dt_name}")
+        out = {}
+        for nm, r in zip(names, pool.map(_hessian_job, jobs, chunksize=1)):
+            if not np.all(np.isfinite(r["hessian"])):
+                # a non-finite entry would be an artefact of the NumPy stand-in, not a fixture
+                print("hessian_dt", nm, "NON-FINITE Hessian - case dropped")
+                continue
+            for k, v in r.items():
+                out[f"{nm}.{k}"] = v
+            print("hessian_dt", nm, r["J"], r["grad"], np.linalg.eigvalsh(r["hessian"]))
+        np.savez_compressed(os.path.join(HERE, "ref_mp_hessian_dt.npz"), **out)
 
     if only is None or "fe" in only:
         jobs, names = [], []
