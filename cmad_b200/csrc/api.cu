@@ -584,7 +584,7 @@ static int objective(const cmadx_material_t* mat, const int32_t* active_pid, int
                      const cmadx_mp_history_t* hist, void* stream, bool adjoint) {
     SensArgs A;
     if (int rc = check_history(mat, hist, &A.m)) return rc;
-    if (A.m.rot) return CMADX_EUNSUPPORTED;
+    // rotated material axes: FULL_3D only (check_history rejects them for the other def-types)
     if (n_active < 0 || n_active > CMADX_MAX_ACTIVE || (n_active > 0 && !active_pid)) return CMADX_EINVAL;
     if (!hist->result || !hist->workspace || (hist->n > 0 && !hist->data)) return CMADX_EINVAL;
     for (int c = 0; c < n_active; ++c) {

@@ -42,11 +42,31 @@ CMADX_DEV double qoi_terms(const double (&w)[9], const double (&sig)[6], const d
     return J;
 }
 
+// 6x6 maps between global and material symmetric-tensor components for a rotation Q
+// (cmad/models/small_elastic_plastic.py:44-62, 318-319): T[c][b] = d(Q^T e Q)_c / d e_b,
+// S[a][c] = d(Q s Q^T)_a / d s_c (packed components, both tensor entries moving)
+CMADX_DEV void sens_rot_maps(const double* Q, double (&T)[6][6], double (&S)[6][6]) {
+    const int ci[6] = {0, 0, 0, 1, 1, 2}, cj[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            const int i = ci[c], j = cj[c], k = ci[b], l = cj[b];
+            double t = Q[3 * k + i] * Q[3 * l + j];
+            double s = Q[3 * i + k] * Q[3 * j + l];
+            if (k != l) { t += Q[3 * l + i] * Q[3 * k + j]; s += Q[3 * i + l] * Q[3 * j + k]; }
+            T[c][b] = t;
+            S[c][b] = s;
+        }
+}
+
 // NA_MAX: compile-time bound of the active-parameter loops (6 covers the usual calibration
 // sets such as [E, nu, D, S, Y]; 16 = CMADX_MAX_ACTIVE), which sizes the register-resident
 // gradient accumulators.
-template <int YK, bool ADJOINT, int NA_MAX>
-__global__ void __launch_bounds__(SENS_BLOCK, (YK == CMADX_YIELD_J2 && NA_MAX <= 6) ? 4 : 1)
+// ROT: rotated material axes ("rotation matrix" != I): the strain is taken to material axes, the
+// state lives there, and the QoI compares the GLOBAL cauchy Q sigma_m Q^T with the data.
+template <int YK, bool ADJOINT, int NA_MAX, bool ROT = false>
+__global__ void __launch_bounds__(SENS_BLOCK, (YK == CMADX_YIELD_J2 && NA_MAX <= 6 && !ROT) ? 4 : 1)
 mp_sens_kernel(const __grid_constant__ SensArgs A) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < A.h.n;
@@ -112,6 +132,19 @@ mp_sens_kernel(const __grid_constant__ SensArgs A) {
 #pragma unroll
             for (int c = 0; c < 9; ++c) d[c] = 0.0;
         }
+        if constexpr (ROT) {                       // global strain -> material axes
+            double T[6][6], S[6][6], eg[6];
+            sens_rot_maps(m.Q, T, S);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) eg[c] = em[c];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int b = 0; b < 6; ++b) sacc = fma(T[c][b], eg[b], sacc);
+                em[c] = sacc;
+            }
+        }
         SepPoint<YK> pt;
         double C[7];
         pt.residual(m, x, xp, em, C);
@@ -124,7 +157,28 @@ mp_sens_kernel(const __grid_constant__ SensArgs A) {
 #pragma unroll
         for (int a = 0; a < 6; ++a) sig[a] = is_diag(a) ? fma(m.two_mu, ee[a], m.lam * tree) : m.two_mu * ee[a];
         double r[6];
-        Jacc += qoi_terms(A.h.weight, sig, d, r);
+        if constexpr (ROT) {
+            // J on the global cauchy S sigma_m; cotangent back to material axes: r_m = S^T r_g
+            double T[6][6], S[6][6], sg[6], rg[6];
+            sens_rot_maps(m.Q, T, S);
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) sacc = fma(S[a][c], sig[c], sacc);
+                sg[a] = sacc;
+            }
+            Jacc += qoi_terms(A.h.weight, sg, d, rg);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int a = 0; a < 6; ++a) sacc = fma(S[a][c], rg[a], sacc);
+                r[c] = sacc;
+            }
+        } else {
+            Jacc += qoi_terms(A.h.weight, sig, d, r);
+        }
         // dJ/dxi (row) : d sigma_a/d ep_b = -(2mu delta_ab + lam [a diag][b diag])
         const double rtr = r[0] + r[3] + r[5];
         double dJdx[7];
@@ -292,6 +346,25 @@ reduce_partials_kernel(const double* partials, int64_t nblk, int ncols, double* 
     }
 }
 
+template <bool ADJOINT>
+cudaError_t launch_sens_rot(const SensArgs& A, cudaStream_t stream) {
+    const int64_t nblk = (A.h.n + SENS_BLOCK - 1) / SENS_BLOCK;
+    constexpr int NA = CMADX_MAX_ACTIVE;
+    switch (A.m.yield) {
+    case CMADX_YIELD_J2:
+        mp_sens_kernel<CMADX_YIELD_J2, ADJOINT, NA, true><<<(unsigned)nblk, SENS_BLOCK, 0, stream>>>(A); break;
+    case CMADX_YIELD_HILL:
+        mp_sens_kernel<CMADX_YIELD_HILL, ADJOINT, NA, true><<<(unsigned)nblk, SENS_BLOCK, 0, stream>>>(A); break;
+    case CMADX_YIELD_HOSFORD:
+        mp_sens_kernel<CMADX_YIELD_HOSFORD, ADJOINT, NA, true><<<(unsigned)nblk, SENS_BLOCK, 0, stream>>>(A); break;
+    default: return cudaErrorInvalidValue;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    reduce_partials_kernel<<<1, 256, 0, stream>>>(A.partials, nblk, 1 + A.n_active, A.h.result);
+    return cudaGetLastError();
+}
+
 template <bool ADJOINT, int NA_MAX>
 cudaError_t launch_sens_t(const SensArgs& A, cudaStream_t stream) {
     const int64_t nblk = (A.h.n + SENS_BLOCK - 1) / SENS_BLOCK;
@@ -320,6 +393,7 @@ cudaError_t launch_reduce_partials(const double* partials, int64_t nblk, int nco
 
 cudaError_t launch_mp_sens(const SensArgs& A, bool adjoint, cudaStream_t stream) {
     if (A.h.n == 0) return cudaMemsetAsync(A.h.result, 0, sizeof(double) * (1 + A.n_active), stream);
+    if (A.m.rot) return adjoint ? launch_sens_rot<true>(A, stream) : launch_sens_rot<false>(A, stream);
     if (A.n_active <= 6) return adjoint ? launch_sens_t<true, 6>(A, stream) : launch_sens_t<false, 6>(A, stream);
     return adjoint ? launch_sens_t<true, CMADX_MAX_ACTIVE>(A, stream) : launch_sens_t<false, CMADX_MAX_ACTIVE>(A, stream);
 }

@@ -87,3 +87,35 @@ def test_fused_forward_history_equals_per_step_path(cuda_device, kind, monkeypat
     assert np.array_equal(res["fused"][1], res["per_step"][1])
     assert np.array_equal(res["fused"][0], res["per_step"][0])
     assert res["fused"][2].max() >= 2
+
+
+@pytest.mark.parametrize("kind", ["J2", "hill", "hosford"])
+def test_batched_objective_rotated_material_axes(cuda_device, kind):
+    """K2 with a rotated "rotation matrix" (cmad/models/small_elastic_plastic.py:44-62, 318-319):
+    the state lives in material axes, the QoI compares the global cauchy Q sigma_m Q^T - adjoint
+    and direct gradients against the oracle, for every yield surface."""
+    from tests.helpers import rotation_matrix
+    hill = (0.45, 0.6, 0.55, 1.4, 1.6, 1.5) if kind == "hill" else None
+    active = ("E", "nu", "D", "S", "Y") + (tuple("FGHLMN") if kind == "hill" else ())
+    values, act, tr = param_tree(kind, ("voce",), hill=hill, active=active,
+                                 rotation=rotation_matrix([1.0, 2.0, -0.5], 0.7))
+    P = Parameters(values, act, tr)
+    sh, data, w = _problem(n=2000, N=10, seed=7, kind="J2")      # full (non-diagonal) strain paths
+    Jr, gr, Jp, gp, xi_ref, it_ref = mo.objective(values, P.active_idx, sh, data, w, "adjoint")
+    model = SmallElasticPlastic(P)
+    res = {}
+    for strategy in ("adjoint", "direct"):
+        ev = gpu_local_evaluator(model, sh, data, w, strategy, cuda_device)
+        out = ev().cpu().numpy()
+        res[strategy] = out
+        assert abs(out[0] - Jr) < 1e-12 * abs(Jr)
+        assert np.abs(out[1:] - gr).max() < 1e-9 * np.abs(gr).max(), (strategy, out[1:], gr)
+        h = ev.histories
+        assert np.array_equal(h.iters.cpu().numpy(), it_ref)
+        assert np.abs(h.xi.cpu().numpy() - xi_ref).max() < 1e-10 * np.abs(xi_ref).max()
+    assert np.abs(res["adjoint"][1:] - res["direct"][1:]).max() < 1e-10 * np.abs(gr).max()
+    # the rotation matters: same histories with identity axes give a different objective (Hill)
+    if kind == "hill":
+        v0, a0, t0 = param_tree(kind, ("voce",), hill=hill, active=active)
+        J0 = mo.objective(v0, Parameters(v0, a0, t0).active_idx, sh, data, w, "adjoint")[0]
+        assert abs(J0 - Jr) > 1e-6 * abs(Jr)
