@@ -48,7 +48,7 @@ def _check_in(name, t, rows, n, device_type):
         raise ValueError(f"{name}: expected float64 ({rows}, {n}), got {t.dtype} {tuple(t.shape)}")
     if t.device.type != device_type:
         raise ValueError(f"{name}: expected a {device_type} tensor")
-    if t.stride(1) != 1:
+    if t.shape[1] > 1 and t.stride(1) != 1:          # (a size-1 axis may carry any stride)
         raise ValueError(f"{name}: innermost (point) dimension must be contiguous")
 
 
