@@ -182,6 +182,8 @@ def lib() -> C.CDLL:
     L.cmadx_fe_block_vjp_mixed.argtypes = [C.POINTER(Material), C.POINTER(C.c_int32), C.c_int32,
                                            C.POINTER(FeBlock), C.POINTER(FeMixed), C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.cmadx_fe_block_vjp_disp.argtypes = [C.POINTER(Material), C.POINTER(FeBlock), C.POINTER(FeMixed),
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.cmadx_segment_plan_create.argtypes = [C.POINTER(C.c_int64), C.c_int64, C.c_int64,
                                             C.POINTER(C.c_void_p)]
     L.cmadx_segment_plan_destroy.argtypes = [C.c_void_p]

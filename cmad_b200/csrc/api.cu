@@ -28,6 +28,8 @@ namespace cmadx {
 int64_t fe_vjp_blocks(int64_t npts);
 cudaError_t launch_fe_block_vjp(const FeArgs& A, const double* Rbar, const double* xibar, double* partials,
                                 double* pbar, cudaStream_t s);
+cudaError_t launch_fe_block_vjp_disp(const FeArgs& A, const double* Rbar, const double* xibar, double* Ubar_ip,
+                                     cudaStream_t s);
 struct HistArgs {
     DevMat m;
     DevNewton nw;
@@ -918,6 +920,23 @@ int cmadx_fe_block_vjp_mixed(const cmadx_material_t* mat, const int32_t* active_
     if (!mix) return CMADX_EINVAL;
     return fe_block_vjp(mat, active_pid, n_active, blk, mix, xi_state, Rbar_global, xibar, pbar_dev,
                         workspace, stream);
+}
+
+int cmadx_fe_block_vjp_disp(const cmadx_material_t* mat, const cmadx_fe_block_t* blk,
+                            const cmadx_fe_mixed_t* mix, const double* xi_state,
+                            const double* Rbar_global, const double* xibar, double* Ubar_ip,
+                            void* stream) {
+    FeArgs A;
+    if (int rc = check_fe_block(mat, blk, &A)) return rc;
+    if (int rc = check_mixed(blk, mix, &A)) return rc;
+    if (blk->n_elems > 0 && (!xi_state || !Ubar_ip)) return CMADX_EINVAL;
+    A.n_active = 0;
+    A.xi_state = xi_state;
+    std::memset(&A.nw, 0, sizeof(A.nw));
+    cudaError_t e = launch_fe_block_vjp_disp(A, Rbar_global, xibar, Ubar_ip, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return CMADX_OK;
 }
 
 int cmadx_release_host_scratch(void) {

@@ -23,10 +23,16 @@ namespace {
 
 constexpr int VJP_BLOCK = 128;
 
-template <int YK, bool ROT, int NB>
-__global__ void __launch_bounds__(VJP_BLOCK, (YK == CMADX_YIELD_J2 && !ROT) ? 4 : 1)
+// WANT_U: also emit the per-point cotangent of the element displacements,
+//   Ubar_ip[p][(a,k)] = sum_j gbar[k][j] gN[a][j],  gbar = sym-unpack(T^T E^T (xibar + mu)),
+// i.e. (d xi/dU)^T xibar + (d R/dU |total)^T Rbar restricted to this point: with
+// d xi/d eps = E - A^{-1} E and d sigma/d eps |total = Cel E^T A^{-1} E the explicit stress
+// terms cancel and the strain cotangent is E^T (xibar + mu).  Rbar may be NULL there.
+template <int YK, bool ROT, int NB, bool WANT_U = false>
+__global__ void __launch_bounds__(VJP_BLOCK, (YK == CMADX_YIELD_J2 && !ROT && !WANT_U) ? 4 : 1)
 fe_vjp_kernel(const __grid_constant__ FeArgs A, const double* __restrict__ Rbar,
-              const double* __restrict__ xibar, double* __restrict__ partials) {
+              const double* __restrict__ xibar, double* __restrict__ partials,
+              double* __restrict__ Ubar_ip = nullptr) {
     const cmadx_fe_block_t& b = A.b;
     const DevMat& m = A.m;
     constexpr int nb = NB;
@@ -62,7 +68,7 @@ fe_vjp_kernel(const __grid_constant__ FeArgs A, const double* __restrict__ Rbar,
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const int eq = eqr[3 * a + k];
-                const double u = __ldg(b.U + eq), rb = __ldg(Rbar + eq);
+                const double u = __ldg(b.U + eq), rb = (WANT_U && !Rbar) ? 0.0 : __ldg(Rbar + eq);
                 gu[k][0] = fma(u, g0, gu[k][0]); gu[k][1] = fma(u, g1, gu[k][1]); gu[k][2] = fma(u, g2, gu[k][2]);
                 // R[a][i] = sum_j gN[a][j] sigma[j][i] w dv  ->  sbar[j][i] += gN[a][j] Rbar[a][i]
                 sb33[0][k] = fma(g0, rb, sb33[0][k]); sb33[1][k] = fma(g1, rb, sb33[1][k]); sb33[2][k] = fma(g2, rb, sb33[2][k]);
@@ -97,7 +103,8 @@ fe_vjp_kernel(const __grid_constant__ FeArgs A, const double* __restrict__ Rbar,
             double rbN = 0.0, pip = 0.0, rbG[3] = {0.0, 0.0, 0.0}, gp[3] = {0.0, 0.0, 0.0};
             for (int a = 0; a < nb; ++a) {
                 const int eqp = __ldg(A.mix_eq_p + e * nb + a);
-                const double rb = __ldg(Rbar + eqp), pa = __ldg(b.U + eqp), Na = __ldg(A.mix_N + ip * nb + a);
+                const double rb = (WANT_U && !Rbar) ? 0.0 : __ldg(Rbar + eqp);
+                const double pa = __ldg(b.U + eqp), Na = __ldg(A.mix_N + ip * nb + a);
                 rbN = fma(rb, Na, rbN); pip = fma(pa, Na, pip);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
@@ -175,6 +182,44 @@ fe_vjp_kernel(const __grid_constant__ FeArgs A, const double* __restrict__ Rbar,
     }
 #pragma unroll
     for (int c = 0; c < 7; ++c) mu[c] = -mu[c];
+    if constexpr (WANT_U) {
+        if (live) {
+            // strain cotangent in material axes: xibar + mu on the strain-like rows (xb holds
+            // xibar - Cel sbar: add the stress term back), then to global axes and to grad_u
+            double ebm[6], ebg[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c)
+                ebm[c] = xb[c] + (is_diag(c) ? fma(m.two_mu, sbar[c], m.lam * strb) : m.two_mu * sbar[c]) + mu[c];
+            if (ROT) {
+                double T[6][6], S[6][6];
+                rot_maps(m.Q, T, S);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) t = fma(T[c][q], ebm[c], t);     // T^T ebar_m
+                    ebg[q] = t;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) ebg[c] = ebm[c];
+            }
+            // gbar[k][j]: diagonal entries take ebar, off-diagonal entries half of it each
+            double gb[3][3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) gb[k][j] = (k == j) ? ebg[vix(k, j)] : 0.5 * ebg[vix(k, j)];
+            const double* gN = b.grad_N + (p * nb) * 3;
+            double* ub = Ubar_ip + p * (NB * 3);
+#pragma unroll
+            for (int a = 0; a < NB; ++a) {
+                const double g0 = __ldg(gN + 3 * a), g1 = __ldg(gN + 3 * a + 1), g2 = __ldg(gN + 3 * a + 2);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) ub[3 * a + k] = fma(gb[k][2], g2, fma(gb[k][1], g1, gb[k][0] * g0));
+            }
+        }
+    }
     // xibar_prev = B^T mu;  B = [-I, n; 0, 0] (plastic) or -I (elastic)
     if (live) {
         double nmu = 0.0;
@@ -252,6 +297,33 @@ cudaError_t launch_yk(const FeArgs& A, const double* Rbar, const double* xibar, 
 }  // namespace
 
 int64_t fe_vjp_blocks(int64_t npts) { return (npts + VJP_BLOCK - 1) / VJP_BLOCK; }
+
+// displacement cotangent only (no parameter gradient): per-point contributions Ubar_ip
+template <int YK>
+cudaError_t launch_yk_disp(const FeArgs& A, const double* Rbar, const double* xibar, double* Ubar_ip,
+                           unsigned nblk, cudaStream_t s) {
+    if (A.b.n_basis == 4) {
+        if (A.m.rot) fe_vjp_kernel<YK, true, 4, true><<<nblk, VJP_BLOCK, 0, s>>>(A, Rbar, xibar, nullptr, Ubar_ip);
+        else fe_vjp_kernel<YK, false, 4, true><<<nblk, VJP_BLOCK, 0, s>>>(A, Rbar, xibar, nullptr, Ubar_ip);
+    } else {
+        if (A.m.rot) fe_vjp_kernel<YK, true, 8, true><<<nblk, VJP_BLOCK, 0, s>>>(A, Rbar, xibar, nullptr, Ubar_ip);
+        else fe_vjp_kernel<YK, false, 8, true><<<nblk, VJP_BLOCK, 0, s>>>(A, Rbar, xibar, nullptr, Ubar_ip);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fe_block_vjp_disp(const FeArgs& A, const double* Rbar, const double* xibar, double* Ubar_ip,
+                                     cudaStream_t s) {
+    const int64_t npts = A.b.n_elems * A.b.n_ip;
+    if (npts == 0) return cudaSuccess;
+    const unsigned nblk = (unsigned)fe_vjp_blocks(npts);
+    switch (A.m.yield) {
+    case CMADX_YIELD_J2: return launch_yk_disp<CMADX_YIELD_J2>(A, Rbar, xibar, Ubar_ip, nblk, s);
+    case CMADX_YIELD_HILL: return launch_yk_disp<CMADX_YIELD_HILL>(A, Rbar, xibar, Ubar_ip, nblk, s);
+    case CMADX_YIELD_HOSFORD: return launch_yk_disp<CMADX_YIELD_HOSFORD>(A, Rbar, xibar, Ubar_ip, nblk, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
 
 cudaError_t launch_fe_block_vjp(const FeArgs& A, const double* Rbar, const double* xibar, double* partials,
                                 double* pbar, cudaStream_t s) {

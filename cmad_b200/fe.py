@@ -449,6 +449,48 @@ def fe_block_vjp(material: L.Material, arrays: FEBlockArrays, U_global: torch.Te
     return pbar, out["xi"]
 
 
+def fe_block_vjp_disp(material: L.Material, arrays: FEBlockArrays, U_global: torch.Tensor,
+                      xi_prev: torch.Tensor, xi_state: torch.Tensor, xibar: torch.Tensor | None = None,
+                      Rbar: torch.Tensor | None = None, stream: torch.cuda.Stream | None = None,
+                      stab_mult: float | None = None) -> torch.Tensor:
+    """Displacement cotangent of the converged block, per integration point:
+    ``Ubar_ip (n_e, n_ip, 3 n_b)`` with ``sum_ip`` scattered over ``elem_eq`` =
+    ``(d xi/dU)^T xibar + (d R_u/dU |total)^T Rbar`` - the transpose of the displacement
+    direction of :func:`fe_block_jvp`, the piece a discrete FE adjoint through the load steps
+    needs besides the assembled tangent (:func:`cmad_b200.fe_driver.fe_adjoint_gradient`)."""
+    n_e, n_ip, n_b = arrays.n_elems, arrays.n_ip, arrays.n_basis
+    dev = arrays.grad_N.device
+    if dev.type != "cuda":
+        raise ValueError("FE block arrays must live on a CUDA device (there is no CPU fallback)")
+    for name, t in (("xi_prev", xi_prev), ("xi_state", xi_state), ("xibar", xibar)):
+        if t is not None and (t.dtype != torch.float64 or tuple(t.shape) != (n_e, n_ip, 7) or not t.is_contiguous()):
+            raise ValueError(f"{name}: expected contiguous float64 ({n_e}, {n_ip}, 7)")
+    for name, t in (("U_global", U_global), ("Rbar", Rbar)):
+        if t is not None and (t.dtype != torch.float64 or t.numel() != arrays.n_dofs or not t.is_contiguous()):
+            raise ValueError(f"{name}: expected contiguous float64 ({arrays.n_dofs},)")
+    out = {"xi": torch.empty((n_e, n_ip, 7), dtype=torch.float64, device=dev)}
+    b = _fe_struct(arrays, U_global, xi_prev, out)
+    Ubar_ip = torch.empty((n_e, n_ip, 3 * n_b), dtype=torch.float64, device=dev)
+    mx = _fe_mixed_struct(arrays, stab_mult) if stab_mult is not None else None
+    s = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        rc = L.lib().cmadx_fe_block_vjp_disp(
+            C.byref(material), C.byref(b), C.byref(mx) if mx is not None else None,
+            C.c_void_p(xi_state.data_ptr()), C.c_void_p(Rbar.data_ptr()) if Rbar is not None else None,
+            C.c_void_p(xibar.data_ptr()) if xibar is not None else None,
+            C.c_void_p(Ubar_ip.data_ptr()), C.c_void_p(s.cuda_stream))
+    L.check(rc, "cmadx_fe_block_vjp_disp")
+    return Ubar_ip
+
+
+def disp_cotangent_plan(arrays: FEBlockArrays, device=None) -> SegmentPlan:
+    """Deterministic scatter plan of :func:`fe_block_vjp_disp`'s per-point rows into the nodal
+    vector: items = the element's equation row repeated for each of its points."""
+    eq = arrays.elem_eq.cpu().numpy()
+    seg = np.repeat(eq[:, None, :], arrays.n_ip, axis=1).reshape(-1)
+    return SegmentPlan(seg, arrays.n_dofs, device=device if device is not None else arrays.grad_N.device)
+
+
 def partition_block(arrays: FEBlockArrays, rank: int, world: int) -> tuple[FEBlockArrays, tuple[int, int]]:
     """This rank's contiguous element range of a block (the path shards by element:
     every element's local state, K_e and R_e are computed by exactly one rank)."""

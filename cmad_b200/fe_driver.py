@@ -233,6 +233,67 @@ def fe_direct_gradient(assemble, jvp, pattern: SparsePattern, bcs: DirichletBCs,
     return J, grad
 
 
+def fe_adjoint_gradient(assemble, vjp, vjp_disp, pattern: SparsePattern, bcs: DirichletBCs, U0, xi0,
+                        t_schedule: Sequence[float], n_active: int, settings: dict | None,
+                        step_qoi, step_qoi_dU):
+    """``(J, dJ/dp)`` in native parameter values by the DISCRETE ADJOINT through the load
+    steps - what ``jax.grad`` of the trajectory of cmad/fem/driver.py:103-146 computes through
+    the IFT rules of the FE Newton (cmad/fem/nonlinear_solver.py:450-542) and of the local
+    Newton (cmad/models/nonlinear_solver.py:158-171).  Forward: the load steps, keeping
+    ``(U_k, xi_k, K_emb_k)``.  Backward, k = N..1, with ``xbar`` the cotangent of ``xi_k``:
+        ub        = (d xi_k/dU_k)^T xbar                     (K6 ``vjp_disp``, device)
+        K_emb^T lam = -(dq_k/dU + ub)  on the free dofs      (host SuperLU)
+        pbar, xbar <- VJP(Rbar = lam, xibar = xbar)          (K6 ``vjp``, device)
+        grad += pbar
+    One sparse solve per step instead of one per parameter (:func:`fe_direct_gradient`).
+    ``vjp(U, xi_prev, xi_state, Rbar, xibar) -> (pbar (n_active,), xibar_prev)``;
+    ``vjp_disp(U, xi_prev, xi_state, xibar) -> ubar (n_dofs,)``; ``xibar`` may be None (zero)."""
+    U, xi = np.array(U0, dtype=np.float64), xi0
+    J = 0.0
+    steps = []
+    for k in range(1, len(t_schedule)):
+        t, t_prev = float(t_schedule[k]), float(t_schedule[k - 1])
+        xi_prev = xi
+        U, xi, log = fe_newton_solve(assemble, pattern, bcs, U, xi_prev, t, settings)
+        J += step_qoi(U, t, t_prev)
+        steps.append((U.copy(), xi_prev, xi, log.K_emb, step_qoi_dU(U, t, t_prev)))
+    grad = np.zeros(n_active)
+    xbar = None
+    for U, xi_prev, xi, K_emb, dq in reversed(steps):
+        rhs = np.asarray(dq, dtype=np.float64).copy()
+        if xbar is not None:
+            rhs += np.asarray(vjp_disp(U, xi_prev, xi, xbar))
+        rhs[bcs.indices] = 0.0                          # prescribed values do not depend on p
+        lam = spla.splu(sp.csc_matrix(K_emb.T)).solve(-rhs)
+        lam[bcs.indices] = 0.0
+        pbar, xbar = vjp(U, xi_prev, xi, lam, xbar)
+        grad += np.asarray(pbar)
+    return J, grad
+
+
+def cuda_vjp(material, arrays, active_pid, stab_mult: float | None = None):
+    """``(vjp, vjp_disp)`` callables of :func:`fe_adjoint_gradient` over the K6 reverse-mode
+    kernels (``stab_mult``: the mixed u-p formulation)."""
+    import torch
+    from . import fe
+    dev = arrays.grad_N.device
+    pid = np.ascontiguousarray(active_pid, dtype=np.int32)
+    u_plan = fe.disp_cotangent_plan(arrays, device=dev)
+
+    def vjp(U, xi_prev, xi_state, Rbar, xibar):
+        Ud = torch.from_numpy(np.ascontiguousarray(U)).to(dev)
+        Rd = torch.from_numpy(np.ascontiguousarray(Rbar)).to(dev)
+        pbar, xbp = fe.fe_block_vjp(material, arrays, Ud, xi_prev, xi_state, pid, Rd, xibar, stab_mult=stab_mult)
+        return pbar.cpu().numpy(), xbp
+
+    def vjp_disp(U, xi_prev, xi_state, xibar):
+        Ud = torch.from_numpy(np.ascontiguousarray(U)).to(dev)
+        ub = fe.fe_block_vjp_disp(material, arrays, Ud, xi_prev, xi_state, xibar, stab_mult=stab_mult)
+        return u_plan.sum(ub.reshape(-1)).cpu().numpy()
+
+    return vjp, vjp_disp
+
+
 def cuda_jvp(material, arrays, r_plan, active_pid):
     """``jvp`` callable of :func:`fe_direct_gradient` over the K6 kernels."""
     import torch

@@ -394,6 +394,22 @@ int cmadx_fe_block_vjp_mixed(const cmadx_material_t* mat, const int32_t* active_
                              const double* xi_state, const double* Rbar_global, const double* xibar,
                              double* pbar_dev, double* workspace, void* stream);
 
+/* Displacement cotangent of the converged block (the piece a discrete FE adjoint through the
+ * load steps needs besides the assembled tangent): per integration point p,
+ *   Ubar_ip[p][(a,k)] = contribution of point p to (d xi/dU)^T xibar + (d R_u/dU |total)^T Rbar
+ * ([n_elems*n_ip][n_basis*3]; sum the rows of an element - or scatter them with a
+ * cmadx_segment_sum plan over the equation row repeated per point - to obtain the nodal
+ * vector; bit-reproducible that way).  This transposes the displacement direction of
+ * cmadx_fe_block_jvp: what jax.grad obtains from the `xi` output of the FE Newton's IFT rule
+ * (cmad/fem/nonlinear_solver.py:534-538).  Rbar_global and xibar may each be NULL (zero);
+ * blk->xi receives xibar_prev as in cmadx_fe_block_vjp.  `mix` (or NULL): for the mixed u-p
+ * formulation the momentum cotangent is projected (dev); the pressure rows' dependence on U
+ * (K_pu) is state-independent and is NOT included - it is in the assembled tangent.        */
+int cmadx_fe_block_vjp_disp(const cmadx_material_t* mat, const cmadx_fe_block_t* blk,
+                            const cmadx_fe_mixed_t* mix, const double* xi_state,
+                            const double* Rbar_global, const double* xibar, double* Ubar_ip,
+                            void* stream);
+
 /* ---- Post-processing at a stored state: evaluate_cauchy_at_ips ------------------------
  * model.cauchy(xi, xi_prev, params, U_ip, U_ip_prev) at every (element, IP) of a COUPLED block
  * from the converged local state (cmad/fem/postprocess.py:35-185): sigma [n_elems][n_ip][6],

@@ -496,3 +496,108 @@ def test_cuda_mixed_direct_gradient_matches_oracle(cuda_device, family):
         lambda c: zd(), ts, 5, None, q, dq)
     assert abs(Jg - Jo) < 1e-10 * abs(Jo)
     assert np.abs(gg - go).max() < 1e-8 * np.abs(go).max(), (gg, go)
+
+
+# ---------------------------------------------------------------- FE gradient by the discrete adjoint
+def oracle_vjp_pair(values, P, arr):
+    """``(vjp, vjp_disp)`` of fe_adjoint_gradient over the ORACLE: the JVP oracle is linear in
+    (dp, dxi_prev, dU); its transposes are obtained by probing it with unit directions."""
+    prob_eval = oc.describe(values, P.active_idx, newton_mode="imperative", strain_comps=9, max_iters=0)
+    eq = arr.elem_eq.numpy(); geo = (arr.grad_N.numpy(), arr.det.numpy(), arr.quad_w.numpy())
+    na = len(prob_eval.active_pid)
+    shape = (arr.n_elems, arr.n_ip, 7)
+    nx = int(np.prod(shape))
+
+    def out_vec(o):
+        dR = np.zeros(arr.n_dofs); np.add.at(dR, eq.reshape(-1), o["R_elem"].reshape(-1))
+        return dR, o["xi"].reshape(-1)
+
+    def vjp(U, xi_prev, xi_state, Rbar, xibar):
+        xb = np.zeros(nx) if xibar is None else np.asarray(xibar).reshape(-1)
+        pbar = np.zeros(na); xbp = np.zeros(nx)
+        for c in range(na):
+            dp = np.zeros(na); dp[c] = 1.0
+            dR, dx = out_vec(fe_oracle.block_jvp(prob_eval, eq, U, xi_prev, xi_state, *geo, dp, None))
+            pbar[c] = Rbar @ dR + xb @ dx
+        for j in range(nx):
+            d = np.zeros(nx); d[j] = 1.0
+            dR, dx = out_vec(fe_oracle.block_jvp(prob_eval, eq, U, xi_prev, xi_state, *geo, np.zeros(na), d.reshape(shape)))
+            xbp[j] = Rbar @ dR + xb @ dx
+        return pbar, xbp.reshape(shape)
+
+    def vjp_disp(U, xi_prev, xi_state, xibar):
+        xb = np.asarray(xibar).reshape(-1)
+        ub = np.zeros(arr.n_dofs)
+        for j in range(arr.n_dofs):
+            d = np.zeros(arr.n_dofs); d[j] = 1.0
+            o = fe_oracle.block_jvp(prob_eval, eq, U, xi_prev, xi_state, *geo, np.zeros(na), None, dU=d)
+            ub[j] = xb @ o["xi"].reshape(-1)
+        return ub
+    return vjp, vjp_disp
+
+
+def test_adjoint_gradient_equals_direct_gradient_oracle():
+    """The discrete adjoint through the load steps (one sparse solve per step) reproduces the
+    direct-sensitivity gradient (one per parameter) - both over the oracle."""
+    values, P, nodes, arr, bcs, pattern, scatter = _gradient_problem(2, "tet4")
+    ts = np.array([0.0, 0.4, 0.7, 1.0])
+    q, dq = _qois(arr, ts)
+    z = lambda: np.zeros((arr.n_elems, arr.n_ip, 7))
+    asm = oracle_assembler(values, arr, scatter, len(pattern.rows))
+    Jd, gd = drv.fe_direct_gradient(asm, oracle_jvp(values, P, arr), pattern, bcs, np.zeros(arr.n_dofs), z(),
+                                    lambda c: z(), ts, 5, None, q, dq)
+    vjp, vjp_disp = oracle_vjp_pair(values, P, arr)
+    Ja, ga = drv.fe_adjoint_gradient(asm, vjp, vjp_disp, pattern, bcs, np.zeros(arr.n_dofs), z(), ts, 5, None, q, dq)
+    assert Ja == Jd
+    assert np.abs(ga - gd).max() < 1e-9 * np.abs(gd).max(), (ga, gd)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("family", ["hex8", "tet4"])
+@pytest.mark.parametrize("mixed", [False, True])
+def test_cuda_adjoint_gradient_matches_direct_and_oracle(cuda_device, family, mixed):
+    """`cmad gradient` on an FE deck by the discrete adjoint over the K6 reverse-mode kernels
+    (cmadx_fe_block_vjp + cmadx_fe_block_vjp_disp), displacement and mixed u-p: equal to the
+    CUDA direct-sensitivity gradient and to the oracle's."""
+    import torch
+    from cmad_b200 import active_param_ids, fe, material_from_values
+    if mixed:
+        values, P, nodes, arr, bcs, pattern, scatter = _mixed_gradient_problem(3, family)
+        ts = np.array([0.0, 0.004, 0.008])
+    else:
+        values, P, nodes, arr, bcs, pattern, scatter = _gradient_problem(3, family)
+        ts = np.array([0.0, 0.4, 0.7, 1.0])
+    q, dq = _qois(arr, ts)
+    arr_d = arr.to(cuda_device)
+    mat = material_from_values(values)
+    pid = active_param_ids(P)
+    k_plan = fe.SegmentPlan(scatter, len(pattern.rows), device=cuda_device)
+    nw = fe.fe_newton_settings(**LOCAL_NEWTON)
+    zd = lambda: torch.zeros((arr.n_elems, arr.n_ip, 7), dtype=torch.float64, device=cuda_device)
+    if mixed:
+        r_plan = fe.mixed_r_plan(arr, device=cuda_device)
+        asm = drv.cuda_assembler_mixed(mat, nw, arr_d, r_plan, k_plan)
+        jvp = drv.cuda_jvp_mixed(mat, arr_d, r_plan, pid)
+        vjp, vjp_disp = drv.cuda_vjp(mat, arr_d, pid, stab_mult=1.0)
+    else:
+        r_plan = fe.SegmentPlan(arr.elem_eq.numpy().reshape(-1), arr.n_dofs, device=cuda_device)
+        asm = drv.cuda_assembler(mat, nw, arr_d, r_plan, k_plan)
+        jvp = drv.cuda_jvp(mat, arr_d, r_plan, pid)
+        vjp, vjp_disp = drv.cuda_vjp(mat, arr_d, pid)
+    Jd, gd = drv.fe_direct_gradient(asm, jvp, pattern, bcs, np.zeros(arr.n_dofs), zd(), lambda c: zd(), ts, 5,
+                                    None, q, dq)
+    Ja, ga = drv.fe_adjoint_gradient(asm, vjp, vjp_disp, pattern, bcs, np.zeros(arr.n_dofs), zd(), ts, 5, None, q, dq)
+    assert Ja == Jd
+    assert np.abs(ga - gd).max() < 1e-9 * np.abs(gd).max(), (ga, gd)
+    # and against the oracle-driven direct gradient
+    z = lambda: np.zeros((arr.n_elems, arr.n_ip, 7))
+    if mixed:
+        Jo, go = drv.fe_direct_gradient(oracle_assembler_mixed(values, arr, scatter, len(pattern.rows)),
+                                        oracle_jvp_mixed(values, P, arr), pattern, bcs, np.zeros(arr.n_dofs), z(),
+                                        lambda c: z(), ts, 5, None, q, dq)
+    else:
+        Jo, go = drv.fe_direct_gradient(oracle_assembler(values, arr, scatter, len(pattern.rows)),
+                                        oracle_jvp(values, P, arr), pattern, bcs, np.zeros(arr.n_dofs), z(),
+                                        lambda c: z(), ts, 5, None, q, dq)
+    assert abs(Ja - Jo) < 1e-10 * abs(Jo)
+    assert np.abs(ga - go).max() < 1e-8 * np.abs(go).max(), (ga, go)

@@ -613,3 +613,55 @@ def test_mixed_block_jvp_and_vjp(cuda_device, family, kind):
     pbar_u, _ = fe.fe_block_vjp(mat, arr, U2, xi1, xi2, pid, Rb0, xibar, stab_mult=stab)
     assert not torch.allclose(pbar_u[:2], pbar[:2], rtol=1e-6, atol=0.0)
     assert torch.allclose(pbar_u[2:], pbar[2:], rtol=1e-12, atol=0.0)
+
+
+@pytest.mark.parametrize("family", ["tet4", "hex8"])
+@pytest.mark.parametrize("kind", ["J2", "hill-rotated", "hosford"])
+def test_block_vjp_disp_is_the_transpose_of_the_displacement_direction(cuda_device, family, kind):
+    """cmadx_fe_block_vjp_disp against the ORACLE's JVP with a displacement direction:
+    <Ubar, dU> == <xibar, dxi(dU)> + <Rbar, dR(dU)> for random directions and cotangents
+    (xibar only, Rbar only, both), deterministic through the segment-sum plan."""
+    from cmad_b200 import Parameters, active_param_ids
+    if kind == "J2":
+        values, act, tr = param_tree("J2", active=("E", "nu", "D", "S", "Y"))
+    elif kind == "hosford":
+        values, act, tr = param_tree("hosford", a=6.0, active=("E", "nu", "D", "S", "Y"))
+    else:
+        values, act, tr = param_tree("hill", hill=(0.45, 0.55, 0.5, 1.4, 1.5, 1.6),
+                                     active=("E", "nu", "D", "S", "Y"),
+                                     rotation=rotation_matrix([1.0, 2.0, -0.5], 0.7))
+    P = Parameters(values, act, tr)
+    nodes, conn = _mesh(family, (3, 2, 2))
+    arr_h = fe_mesh.block_arrays(nodes, conn); arr = arr_h.to(cuda_device)
+    mat = material_from_values(values)
+    nw = fe.fe_newton_settings(**NEWTON)
+    rng = np.random.default_rng(13)
+    n_e, n_ip = arr.n_elems, arr.n_ip
+    U1 = torch.from_numpy(fe_mesh.synthetic_displacement(nodes, 1.0, seed=1, ramp=0.004, noise=4e-4)).to(cuda_device)
+    U2 = torch.from_numpy(fe_mesh.synthetic_displacement(nodes, 2.0, seed=2, ramp=0.004, noise=4e-4)).to(cuda_device)
+    xi0 = torch.zeros((n_e, n_ip, 7), dtype=torch.float64, device=cuda_device)
+    xi1 = fe.fe_block_launch(mat, nw, arr, U1, xi0, ("xi",))["xi"]
+    prim = fe.fe_block_launch(mat, nw, arr, U2, xi1, ("xi", "flags"))
+    assert bool((prim["flags"] & 2).any())
+    Rbar = torch.from_numpy(rng.standard_normal(arr.n_dofs)).to(cuda_device)
+    xibar = torch.from_numpy(rng.standard_normal((n_e, n_ip, 7))).to(cuda_device)
+    plan = fe.disp_cotangent_plan(arr, device=cuda_device)
+    prob_eval = oc.describe(values, P.active_idx, newton_mode="imperative", strain_comps=9, max_iters=0)
+    geo = (arr_h.grad_N.numpy(), arr_h.det.numpy(), arr_h.quad_w.numpy())
+    eq = arr_h.elem_eq.numpy()
+    na = len(prob_eval.active_pid)
+    for xb, rb in ((xibar, None), (None, Rbar), (xibar, Rbar)):
+        ub_ip = fe.fe_block_vjp_disp(mat, arr, U2, xi1, prim["xi"], xb, rb)
+        ub = plan.sum(ub_ip.reshape(-1))
+        ub2 = plan.sum(fe.fe_block_vjp_disp(mat, arr, U2, xi1, prim["xi"], xb, rb).reshape(-1))
+        torch.cuda.synchronize()
+        assert torch.equal(ub, ub2)
+        for trial in range(2):
+            dU = 1e-4 * rng.standard_normal(arr.n_dofs)
+            jv = fe_oracle.block_jvp(prob_eval, eq, U2.cpu().numpy(), xi1.cpu().numpy(), prim["xi"].cpu().numpy(),
+                                     *geo, np.zeros(na), None, dU=dU)
+            dR = np.zeros(arr.n_dofs); np.add.at(dR, eq.reshape(-1), jv["R_elem"].reshape(-1))
+            t1 = float((xb.cpu().numpy() * jv["xi"]).sum()) if xb is not None else 0.0
+            t2 = float(rb.cpu().numpy() @ dR) if rb is not None else 0.0
+            lhs = float(ub.cpu().numpy() @ dU)
+            assert abs(lhs - (t1 + t2)) < 1e-9 * (abs(t1) + abs(t2)), (trial, lhs, t1, t2)
