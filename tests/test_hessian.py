@@ -294,3 +294,41 @@ def test_cuda_hessian_vs_reference_def_types(cuda_device, case):
     assert np.abs((rc.hessian - fd) * sx).max() < 2e-5 * np.abs(rc.hessian * sx).max(), (rc.hessian, fd)
     if mode == "scaled":
         assert hess_err(rc.hessian, r.hessian) < 1e-12
+
+
+@pytest.mark.gpu
+def test_hessian_entry_point_edge_cases(cuda_device):
+    """Argument errors and degenerate sizes of cmadx_mp_objective_hessian: no active parameter
+    (J only), rotated axes (unsupported -> NotImplementedError, never a silent fallback), an
+    unknown flag bit (EINVAL), and an elastic-only history (zero plastic sensitivity terms)."""
+    import ctypes as C
+    import torch
+    from cmad_b200 import _lib as L
+    from cmad_b200.objectives import SmallElasticPlastic, gpu_local_evaluator
+    from tests.helpers import param_tree, rotation_matrix
+    from tests.test_objectives_host import _problem
+    sh, data, w = _problem(n=64, N=6, seed=9)
+    # (1) nothing active
+    v, a, t = param_tree("J2", ("voce",), active=())
+    out = gpu_local_evaluator(SmallElasticPlastic(Parameters(v, a, t)), sh, data, w, "direct_adjoint",
+                              cuda_device)().cpu().numpy()
+    assert out.shape == (1,) and np.isfinite(out[0]) and out[0] > 0
+    # (2) rotated axes
+    v, a, t = param_tree("J2", ("voce",), rotation=rotation_matrix([1.0, 2.0, -0.5], 0.7))
+    with pytest.raises(NotImplementedError):
+        gpu_local_evaluator(SmallElasticPlastic(Parameters(v, a, t)), sh, data, w, "direct_adjoint", cuda_device)()
+    # (3) elastic-only history: H = d2J/dp2 through the elastic constants only; flow-stress block zero
+    v, a, t = param_tree("J2", ("voce",))
+    P = Parameters(v, a, t)
+    out = gpu_local_evaluator(SmallElasticPlastic(P), 1e-3 * sh, data, w, "direct_adjoint", cuda_device)().cpu().numpy()
+    na = P.num_active_params
+    H = out[1 + na:].reshape(na, na)
+    assert np.all(H[2:, :] == 0.0) and np.all(H[:, 2:] == 0.0) and H[0, 0] > 0.0
+    # (4) unknown flag bit straight through the C-ABI
+    h = L.MpHistory()
+    h.n, h.ld, h.nsteps, h.strain_comps = 0, 1, 1, 6
+    res = torch.zeros(8, dtype=torch.float64, device=cuda_device)
+    h.result, h.workspace = res.data_ptr(), res.data_ptr()
+    mat = SmallElasticPlastic(P).material()
+    rc = L.lib().cmadx_mp_objective_hessian(C.byref(mat), None, 0, C.byref(h), C.c_int32(2), None)
+    assert rc == L.EINVAL
