@@ -142,6 +142,18 @@ def main():
                           "point_steps_per_s": n * N / ms * 1e3, "alg_bytes_per_point_step": b,
                           "achieved_gbs": n * N * b / ms / 1e6, "frac_hbm": n * N * b / ms / 1e6 / hbm,
                           "J": float(result[0])}))
+    # ---- K2-H: adjoint pass + direct-adjoint Hessian pass (hyper-dual forward mode) ---------
+    result_h = torch.zeros((1 + na + na * na,), dtype=torch.float64, device=dev)
+    wsh = torch.empty((max(int(lib.cmadx_mp_hessian_workspace_bytes(C.c_int64(n), C.c_int64(n), C.c_int32(N),
+                                                                     C.c_int32(na))) // 8, 1),),
+                      dtype=torch.float64, device=dev)
+    h.result, h.workspace = result_h.data_ptr(), wsh.data_ptr()
+    hes = lambda: L.check(lib.cmadx_mp_objective_hessian(C.byref(mat), pidp, na, C.byref(h), C.c_int32(0), stream), "hess")
+    ms, mn = timed(hes, args.steps, args.warmup)
+    print(json.dumps({**base, "kernel": "K2-H Hessian objective (J, dJ/dp, d2J/dp2): adjoint + hyper-dual pass",
+                      "ms_per_step": ms, "ms_min": mn, "point_steps_per_s": n * N / ms * 1e3,
+                      "hyperdual_evals_per_point_step": na * (na + 1) // 2,
+                      "J": float(result_h[0]), "H_trace": float(result_h[1 + na:].reshape(na, na).diagonal().sum())}))
 
 
 if __name__ == "__main__":
