@@ -173,7 +173,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host_cpus": os.cpu_count(), "wall_s": time.perf_counter() - t_all,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_json_out(), flush=True)
 
 
 def run_b200(args):
@@ -294,7 +294,7 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": rate, "unit": "updates/s", "cores": threads,
                                     "kind": "port", "sample": desc,
                                     "host_cpus": os.cpu_count()}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_json_out(), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -336,7 +336,26 @@ def run_e2e(args, mat, newton, pid, strains, ts, dev, local, world):
             "pcie_gbs": (h2d + d2h) * steps / dt / 1e9}
 
 
+_JSON_OUT = None
+
+
+def _json_out():
+    return _JSON_OUT if _JSON_OUT is not None else sys.stdout
+
+
+def _reserve_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints
+    its version banner to fd 1 when the process group starts), so keep a private handle on the
+    original stdout for the JSON line and point fd 1 at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
 def main():
+    _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
