@@ -670,10 +670,9 @@ static int check_fe_block(const cmadx_material_t* mat, const cmadx_fe_block_t* b
     if (A->m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC) return CMADX_EUNSUPPORTED;
     const cmadx_fe_block_t& b = *blk;
     if (b.n_elems < 0 || b.n_dofs < 0) return CMADX_EINVAL;
-    if (!((b.n_basis == 4 && b.n_ip == 1) || (b.n_basis == 8 && b.n_ip == 8))) {
-        if ((b.n_basis == 4 || b.n_basis == 8) && b.n_ip >= 1 && b.n_ip <= 27) return CMADX_EUNSUPPORTED;
-        return CMADX_EINVAL;
-    }
+    // tet4 / hex8 with any volume rule (cmad/cli/common.py:497-540: up to 24 / 64 points); the
+    // default rules (tet4 x 1, hex8 x 8) run the tuned kernels, the others fe_generic.cu
+    if (!(b.n_basis == 4 || b.n_basis == 8) || b.n_ip < 1 || b.n_ip > 64) return CMADX_EINVAL;
     if (b.n_elems > 0) {
         if (!b.elem_eq || !b.U || !b.xi_prev || !b.grad_N || !b.det || !b.quad_w || !b.xi) return CMADX_EINVAL;
         auto misaligned = [](const void* p, uintptr_t a) { return p && (reinterpret_cast<uintptr_t>(p) % a) != 0; };
@@ -710,7 +709,10 @@ static int fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* 
     if (b.n_elems == 0) return CMADX_OK;
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e;
-    const bool radial = A.m.yield == CMADX_YIELD_J2 && !A.m.rot && !(A.nw.flags & CMADX_NEWTON_F_GENERIC);
+    const bool default_rule = (b.n_basis == 4 && b.n_ip == 1) || (b.n_basis == 8 && b.n_ip == 8);
+    const bool radial = default_rule && A.m.yield == CMADX_YIELD_J2 && !A.m.rot &&
+                        !(A.nw.flags & CMADX_NEWTON_F_GENERIC);
+    if (!default_rule) A.nw.defer_request = 0;       // one pass of the generic-rule kernel
     if (radial) {
         BailScratch bs;
         if (int rc = get_bail_scratch(s, &bs)) return rc;

@@ -28,10 +28,17 @@ namespace cmadx {
 
 cudaError_t launch_fe_tet4(const FeArgs& A, int solver, bool list, cudaStream_t stream, int sms);
 cudaError_t launch_fe_hex8(const FeArgs& A, int solver, bool list, cudaStream_t stream, int sms);
+cudaError_t launch_fe_generic(const FeArgs& A, int solver, cudaStream_t stream);
+
+// the tuned kernels cover the reference's default rules (cmad/fem/fe_problem.py:35-38)
+static bool default_rule(const FeArgs& A) {
+    return (A.b.n_basis == 4 && A.b.n_ip == 1) || (A.b.n_basis == 8 && A.b.n_ip == 8);
+}
 
 // main launch: J2 radial kernel where it applies, else the generic kernel
 cudaError_t launch_fe_block(const FeArgs& A, bool j2_radial, cudaStream_t stream) {
     if (A.b.n_elems == 0) return cudaSuccess;
+    if (!default_rule(A)) return launch_fe_generic(A, 1 + A.m.yield, stream);
     const int solver = j2_radial ? 0 : 1 + A.m.yield;
     return (A.b.n_basis == 4) ? launch_fe_tet4(A, solver, false, stream, 0)
                               : launch_fe_hex8(A, solver, false, stream, 0);
@@ -41,6 +48,7 @@ cudaError_t launch_fe_block(const FeArgs& A, bool j2_radial, cudaStream_t stream
 cudaError_t launch_fe_block_jvp(const FeArgs& A, cudaStream_t stream) {
     if (A.b.n_elems == 0) return cudaSuccess;
     const int solver = 4 + A.m.yield;
+    if (!default_rule(A)) return launch_fe_generic(A, solver, stream);
     return (A.b.n_basis == 4) ? launch_fe_tet4(A, solver, false, stream, 0)
                               : launch_fe_hex8(A, solver, false, stream, 0);
 }

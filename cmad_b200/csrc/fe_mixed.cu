@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(FE_BLOCK, 4) fe_mixed_pressure_kernel(const cm
     const bool live = e < b.n_elems;
     if (__all_sync(0xffffffffu, !live)) return;
     const int64_t el = live ? e : 0;
+    const int nip = NIP ? NIP : b.n_ip;        // NIP = 0: any quadrature rule (runtime count)
     // this thread's node: displacement and pressure dofs; the sums over the nodes of the
     // element (p, tr eps, grad p) are butterfly reductions over its NB lanes
     double Ua[3];
@@ -43,9 +44,10 @@ __global__ void __launch_bounds__(FE_BLOCK, 4) fe_mixed_pressure_kernel(const cm
     // offset are conflict-free.  (Before: every thread re-read the chunks through L1 - 8x the
     // wavefronts, the kernel was L1-data-pipe bound.)  tet4 keeps the direct loads (12 doubles).
     constexpr int REGION = 194;
-    __shared__ __align__(16) double smem[(NB == 8) ? (FE_BLOCK / 8) * REGION : 2];
-    const double* reg = smem + (threadIdx.x >> 3) * REGION;
-    if constexpr (NB == 8) {
+    constexpr bool STAGED = (NB == 8 && NIP == 8);
+    __shared__ __align__(16) double smem[STAGED ? (FE_BLOCK / 8) * REGION : 2];
+    const double* reg = smem + (STAGED ? (threadIdx.x >> 3) * REGION : 0);
+    if constexpr (STAGED) {
         double* wr = smem + (threadIdx.x >> 3) * REGION;
         const double* g = b.grad_N + el * (NIP * NB * 3);
         double c[6][4];
@@ -71,10 +73,10 @@ __global__ void __launch_bounds__(FE_BLOCK, 4) fe_mixed_pressure_kernel(const cm
             for (int k = 0; k < 3; ++k) { Kpu[c][k] = 0.0; Kup[k][c] = 0.0; }
         }
 #pragma unroll 1
-        for (int q = 0; q < NIP; ++q) {
-            const double* g = b.grad_N + (el * NIP + q) * (NB * 3);
+        for (int q = 0; q < nip; ++q) {
+            const double* g = b.grad_N + (el * nip + q) * (NB * 3);
             double gN[4][3], N[4];
-            if constexpr (NB == 8) {
+            if constexpr (STAGED) {
                 const double2* src = reinterpret_cast<const double2*>(reg + q * 24 + 12 * cb);
 #pragma unroll
                 for (int c = 0; c < 6; ++c) {
@@ -91,11 +93,11 @@ __global__ void __launch_bounds__(FE_BLOCK, 4) fe_mixed_pressure_kernel(const cm
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) N[c] = __ldg(mx.N + q * NB + 4 * cb + c);
-            const double wdv = __ldg(b.quad_w + q) * __ldg(b.det + el * NIP + q);
+            const double wdv = __ldg(b.quad_w + q) * __ldg(b.det + el * nip + q);
             const double Na = __ldg(mx.N + q * NB + a) * wdv;
-            const double gu0 = (NB == 8) ? reg[q * 24 + 3 * a] : __ldg(g + 3 * a);
-            const double gu1 = (NB == 8) ? reg[q * 24 + 3 * a + 1] : __ldg(g + 3 * a + 1);
-            const double gu2 = (NB == 8) ? reg[q * 24 + 3 * a + 2] : __ldg(g + 3 * a + 2);
+            const double gu0 = STAGED ? reg[q * 24 + 3 * a] : __ldg(g + 3 * a);
+            const double gu1 = STAGED ? reg[q * 24 + 3 * a + 1] : __ldg(g + 3 * a + 1);
+            const double gu2 = STAGED ? reg[q * 24 + 3 * a + 2] : __ldg(g + 3 * a + 2);
             const double ga0 = gu0 * wdv, ga1 = gu1 * wdv, ga2 = gu2 * wdv;
             if (cb == 0) {
                 double p = Na * pa, tre = fma(Ua[2], ga2, fma(Ua[1], ga1, Ua[0] * ga0));    // x w dv
@@ -173,13 +175,14 @@ __global__ void __launch_bounds__(FE_BLOCK) fe_mixed_pressure_jvp_kernel(const c
     const double h = __ldg(mx.h + el);
     const double tau_h = mx.stab_mult * 0.5 * h * h;
     const double cp = dkappa / (kappa * kappa), ct = dmu / (mu * mu), ik = 1.0 / kappa, im = 1.0 / mu;
+    const int nip = NIP ? NIP : b.n_ip;
     double dRp = 0.0;
 #pragma unroll 1
-    for (int q = 0; q < NIP; ++q) {
-        const double* g = b.grad_N + (el * NIP + q) * (NB * 3);
+    for (int q = 0; q < nip; ++q) {
+        const double* g = b.grad_N + (el * nip + q) * (NB * 3);
         const double Na = __ldg(mx.N + q * NB + a);
         const double g0 = __ldg(g + 3 * a), g1 = __ldg(g + 3 * a + 1), g2 = __ldg(g + 3 * a + 2);
-        const double wdv = __ldg(b.quad_w + q) * __ldg(b.det + el * NIP + q);
+        const double wdv = __ldg(b.quad_w + q) * __ldg(b.det + el * nip + q);
         // v[0] = p, v[1..3] = grad p, v[4] = dp, v[5] = tr(d eps), v[6..8] = grad dp
         double v[9] = {Na * pa, pa * g0, pa * g1, pa * g2, Na * dpa,
                        fma(dUa[2], g2, fma(dUa[1], g1, dUa[0] * g0)), dpa * g0, dpa * g1, dpa * g2};
@@ -203,8 +206,10 @@ cudaError_t launch_fe_mixed_pressure_jvp(const cmadx_fe_block_t& b, const cmadx_
     if (b.n_elems == 0) return cudaSuccess;
     const int64_t nthr = b.n_elems * b.n_basis;
     const unsigned nblk = (unsigned)((nthr + FE_BLOCK - 1) / FE_BLOCK);
-    if (b.n_basis == 4) fe_mixed_pressure_jvp_kernel<4, 1><<<nblk, FE_BLOCK, 0, stream>>>(b, mx, dU, kappa, mu, dkappa, dmu);
-    else fe_mixed_pressure_jvp_kernel<8, 8><<<nblk, FE_BLOCK, 0, stream>>>(b, mx, dU, kappa, mu, dkappa, dmu);
+    if (b.n_basis == 4 && b.n_ip == 1) fe_mixed_pressure_jvp_kernel<4, 1><<<nblk, FE_BLOCK, 0, stream>>>(b, mx, dU, kappa, mu, dkappa, dmu);
+    else if (b.n_basis == 8 && b.n_ip == 8) fe_mixed_pressure_jvp_kernel<8, 8><<<nblk, FE_BLOCK, 0, stream>>>(b, mx, dU, kappa, mu, dkappa, dmu);
+    else if (b.n_basis == 4) fe_mixed_pressure_jvp_kernel<4, 0><<<nblk, FE_BLOCK, 0, stream>>>(b, mx, dU, kappa, mu, dkappa, dmu);
+    else fe_mixed_pressure_jvp_kernel<8, 0><<<nblk, FE_BLOCK, 0, stream>>>(b, mx, dU, kappa, mu, dkappa, dmu);
     return cudaGetLastError();
 }
 
@@ -213,8 +218,10 @@ cudaError_t launch_fe_mixed_pressure(const cmadx_fe_block_t& b, const cmadx_fe_m
     if (b.n_elems == 0) return cudaSuccess;
     const int64_t nthr = b.n_elems * b.n_basis;
     const unsigned nblk = (unsigned)((nthr + FE_BLOCK - 1) / FE_BLOCK);
-    if (b.n_basis == 4) fe_mixed_pressure_kernel<4, 1><<<nblk, FE_BLOCK, 0, stream>>>(b, mx, kappa, mu);
-    else fe_mixed_pressure_kernel<8, 8><<<nblk, FE_BLOCK, 0, stream>>>(b, mx, kappa, mu);
+    if (b.n_basis == 4 && b.n_ip == 1) fe_mixed_pressure_kernel<4, 1><<<nblk, FE_BLOCK, 0, stream>>>(b, mx, kappa, mu);
+    else if (b.n_basis == 8 && b.n_ip == 8) fe_mixed_pressure_kernel<8, 8><<<nblk, FE_BLOCK, 0, stream>>>(b, mx, kappa, mu);
+    else if (b.n_basis == 4) fe_mixed_pressure_kernel<4, 0><<<nblk, FE_BLOCK, 0, stream>>>(b, mx, kappa, mu);   // any rule
+    else fe_mixed_pressure_kernel<8, 0><<<nblk, FE_BLOCK, 0, stream>>>(b, mx, kappa, mu);
     return cudaGetLastError();
 }
 

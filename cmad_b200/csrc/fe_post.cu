@@ -19,9 +19,10 @@ template <int NB, int NIP, bool ROT>
 __global__ void __launch_bounds__(FE_BLOCK) fe_cauchy_kernel(const DevMat m, const cmadx_fe_block_t b,
                                                              const double* __restrict__ xi_state,
                                                              double* __restrict__ sigma) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // point = e * NIP + ip
-    if (p >= b.n_elems * NIP) return;
-    const int64_t e = p / NIP;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // point = e * n_ip + ip
+    const int nip = NIP ? NIP : b.n_ip;                                    // NIP = 0: any rule
+    if (p >= b.n_elems * nip) return;
+    const int64_t e = p / nip;
     const double* g = b.grad_N + p * (NB * 3);
     double gN[NB][3], U[NB][3];
 #pragma unroll
@@ -109,11 +110,11 @@ cudaError_t launch_fe_cauchy(const DevMat& m, const cmadx_fe_block_t& b, const d
     const unsigned nblk = (unsigned)((npts + FE_BLOCK - 1) / FE_BLOCK);
     const bool rot = m.rot != 0;
     if (b.n_basis == 4) {
-        if (rot) fe_cauchy_kernel<4, 1, true><<<nblk, FE_BLOCK, 0, stream>>>(m, b, xi_state, sigma);
-        else fe_cauchy_kernel<4, 1, false><<<nblk, FE_BLOCK, 0, stream>>>(m, b, xi_state, sigma);
+        if (rot) fe_cauchy_kernel<4, 0, true><<<nblk, FE_BLOCK, 0, stream>>>(m, b, xi_state, sigma);
+        else fe_cauchy_kernel<4, 0, false><<<nblk, FE_BLOCK, 0, stream>>>(m, b, xi_state, sigma);
     } else {
-        if (rot) fe_cauchy_kernel<8, 8, true><<<nblk, FE_BLOCK, 0, stream>>>(m, b, xi_state, sigma);
-        else fe_cauchy_kernel<8, 8, false><<<nblk, FE_BLOCK, 0, stream>>>(m, b, xi_state, sigma);
+        if (rot) fe_cauchy_kernel<8, 0, true><<<nblk, FE_BLOCK, 0, stream>>>(m, b, xi_state, sigma);
+        else fe_cauchy_kernel<8, 0, false><<<nblk, FE_BLOCK, 0, stream>>>(m, b, xi_state, sigma);
     }
     return cudaGetLastError();
 }

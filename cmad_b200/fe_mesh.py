@@ -63,6 +63,29 @@ def tet_quadrature_deg1():
     return np.array([[0.25, 0.25, 0.25]]), np.array([1.0 / 6.0])
 
 
+def hex_quadrature(degree: int):
+    """Tensor Gauss-Legendre rule on [-1, 1]^3 exact to ``degree`` per axis: ceil((d+1)/2)
+    points per axis, first axis slowest (cmad/fem/quadrature.py:70-93)."""
+    n = (int(degree) + 2) // 2
+    x1, w1 = np.polynomial.legendre.leggauss(n)
+    xi = np.stack(np.meshgrid(x1, x1, x1, indexing="ij"), axis=-1).reshape(-1, 3)
+    w = (w1[:, None, None] * w1[None, :, None] * w1[None, None, :]).reshape(-1)
+    return xi, w
+
+
+def tet_quadrature(degree: int):
+    """Rules on the unit tetrahedron (weights sum to 1/6): degree 1 = centroid; degree 2 = the
+    symmetric 4-point rule (the rule the reference's mixed formulation needs on tets,
+    cmad/cli/common.py:379-391; cmad/fem/quadrature.py:251-272)."""
+    if degree == 1:
+        return tet_quadrature_deg1()
+    if degree == 2:
+        a, b = (5.0 + 3.0 * np.sqrt(5.0)) / 20.0, (5.0 - np.sqrt(5.0)) / 20.0
+        xi = np.array([[b, b, b], [a, b, b], [b, a, b], [b, b, a]])
+        return xi, np.full(4, 1.0 / 24.0)
+    raise ValueError(f"tet_quadrature: degree {degree} is not tabulated here (1, 2)")
+
+
 def hex_linear_shapes(xi: np.ndarray):
     """``N (n_ip, 8)`` and reference gradients ``(n_ip, 8, 3)`` of the trilinear hex."""
     t = 1.0 + xi[:, None, :] * _HEX_NODE_XI[None, :, :]          # (n_ip, 8, 3)
@@ -140,17 +163,20 @@ def element_rms_edge_sizes(nodes, conn) -> np.ndarray:
     return np.sqrt(np.mean(np.sum((X[:, :, 1] - X[:, :, 0]) ** 2, axis=-1), axis=-1))
 
 
-def block_arrays(nodes, conn, device="cpu", chunk: int = 1 << 20, mixed: bool = False) -> FEBlockArrays:
+def block_arrays(nodes, conn, device="cpu", chunk: int = 1 << 20, mixed: bool = False,
+                 volume_degree: int | None = None) -> FEBlockArrays:
     """Geometry cache + equation indices of one block (tet4 if ``conn`` has 4
     columns, hex8 if 8), as ``precompute_block_geometry`` builds them.  ``mixed``:
-    the u-p formulation (one pressure dof per node after the 3 n_nodes displacement dofs)."""
+    the u-p formulation (one pressure dof per node after the 3 n_nodes displacement dofs).
+    ``volume_degree``: the deck's ``discretization.quadrature.volume degree`` override (None =
+    the family defaults hex 2 / tet 1, cmad/fem/fe_problem.py:35-38)."""
     conn = np.asarray(conn)
     n_b = conn.shape[1]
     if n_b == 8:
-        xi, w = hex_quadrature_deg2()
+        xi, w = hex_quadrature_deg2() if volume_degree is None else hex_quadrature(volume_degree)
         N, gref = hex_linear_shapes(xi)
     elif n_b == 4:
-        xi, w = tet_quadrature_deg1()
+        xi, w = tet_quadrature_deg1() if volume_degree is None else tet_quadrature(volume_degree)
         N, gref = tet_linear_shapes(xi)
     else:
         raise ValueError(f"unsupported element with {n_b} nodes")

@@ -282,9 +282,12 @@ int cmadx_mp_objective_hessian(const cmadx_material_t* mat, const int32_t* activ
  *                   the single-field displacement formulation; dof = basis*3 + comp,
  *                   cmad/fem/assembly.py:142-165)
  *   xi history      flat-trailing (n_elems, n_ip, n_xi), cmad/fem/fe_problem.py:310-313
- * Supported element/rule pairs: tet4 x 1 IP, hex8 x 8 IPs (the reference's
- * defaults, cmad/fem/fe_problem.py:35-38).  grad_N, K_elem and (tet4) R_elem must
- * be 32-byte aligned (256-bit vector loads/stores).                            */
+ * Element families: tet4 and hex8 with any volume rule (n_ip 1..64).  The reference's
+ * defaults tet4 x 1 IP and hex8 x 8 IPs (cmad/fem/fe_problem.py:35-38) run the tuned
+ * kernels; other rules (`discretization.quadrature.volume degree`, cmad/cli/common.py:
+ * 497-540 - e.g. tet4 x 4, which the mixed formulation requires on tets, :379-391) run a
+ * correctness-first kernel with one thread per element.  grad_N, K_elem and (tet4 x 1)
+ * R_elem must be 32-byte aligned (256-bit vector loads/stores).                */
 typedef struct cmadx_fe_block {
     int64_t n_elems;
     int64_t n_dofs;          /* length of U and R_global                         */

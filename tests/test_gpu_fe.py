@@ -201,11 +201,11 @@ def test_empty_block_and_argument_errors(cuda_device):
         fe.fe_block_launch(mat, nw, arr, U[:-1].contiguous(), torch.zeros((6, 1, 7), dtype=torch.float64, device=cuda_device))
     with pytest.raises(ValueError):
         fe.fe_block_launch(mat, nw, arr, U, torch.zeros((6, 2, 7), dtype=torch.float64, device=cuda_device))
-    # an element/rule pair outside the reference's defaults is refused, not mis-assembled
-    bad = fe_mesh.FEBlockArrays(arr.elem_eq, arr.grad_N.repeat(1, 4, 1, 1).contiguous(), arr.det.repeat(1, 4).contiguous(),
-                                arr.quad_w.repeat(4).contiguous(), arr.N, arr.n_dofs)
-    with pytest.raises(NotImplementedError):
-        fe.fe_block_launch(mat, nw, bad, U, torch.zeros((6, 4, 7), dtype=torch.float64, device=cuda_device))
+    # a rule with more points than any the reference tabulates (> 64) is rejected, not mis-assembled
+    bad = fe_mesh.FEBlockArrays(arr.elem_eq, arr.grad_N.repeat(1, 65, 1, 1).contiguous(), arr.det.repeat(1, 65).contiguous(),
+                                arr.quad_w.repeat(65).contiguous(), arr.N, arr.n_dofs)
+    with pytest.raises(ValueError):
+        fe.fe_block_launch(mat, nw, bad, U, torch.zeros((6, 65, 7), dtype=torch.float64, device=cuda_device))
     # Elastic model blocks are CLOSED_FORM in the reference (cli/common.py:347-354): not this kernel
     with pytest.raises(NotImplementedError):
         fe.fe_block_launch(material_from_values({"elastic": {"kappa": 100.0, "mu": 50.0}}, model="elastic"),
@@ -665,3 +665,140 @@ def test_block_vjp_disp_is_the_transpose_of_the_displacement_direction(cuda_devi
             t2 = float(rb.cpu().numpy() @ dR) if rb is not None else 0.0
             lhs = float(ub.cpu().numpy() @ dU)
             assert abs(lhs - (t1 + t2)) < 1e-9 * (abs(t1) + abs(t2)), (trial, lhs, t1, t2)
+
+
+@pytest.mark.parametrize("family,degree,n_ip", [("tet4", 2, 4), ("hex8", 4, 27), ("hex8", 1, 1)])
+@pytest.mark.parametrize("kind", ["J2", "hosford"])
+def test_block_parity_other_quadrature_rules(cuda_device, family, degree, n_ip, kind):
+    """`discretization.quadrature.volume degree` overrides (cmad/cli/common.py:497-540): tet4 x 4
+    (what the mixed formulation requires on tets), hex8 x 27, hex8 x 1 through the any-rule
+    kernel (fe_generic.cu) against the block oracle: values 1e-10, counts and flags exact; then
+    the K6 companions (JVP vs oracle, VJP adjoint identity) and evaluate_cauchy_at_ips."""
+    from cmad_b200 import Parameters, active_param_ids
+    values, act, tr = (param_tree("J2", active=("E", "nu", "D", "S", "Y")) if kind == "J2" else
+                       param_tree("hosford", a=6.0, active=("E", "nu", "D", "S", "Y")))
+    P = Parameters(values, act, tr)
+    pid = active_param_ids(P)
+    nodes, conn = _mesh(family, (3, 2, 2))
+    arr_h = fe_mesh.block_arrays(nodes, conn, volume_degree=degree); arr = arr_h.to(cuda_device)
+    assert arr.n_ip == n_ip
+    mat = material_from_values(values)
+    nw = fe.fe_newton_settings(**NEWTON)
+    prob = oc.describe(values, None, newton_mode="traced", strain_comps=9, **NEWTON)
+    n_e = arr.n_elems
+    geo = (arr_h.grad_N.numpy(), arr_h.det.numpy(), arr_h.quad_w.numpy())
+    eq = arr_h.elem_eq.numpy()
+    xi_ref = np.zeros((n_e, n_ip, 7))
+    xi = torch.zeros((n_e, n_ip, 7), dtype=torch.float64, device=cuda_device)
+    plastic = False
+    for s in (1, 2):
+        U = fe_mesh.synthetic_displacement(nodes, t=float(s), seed=40 + s, ramp=0.004, noise=4e-4)
+        Ud = torch.from_numpy(U).to(cuda_device)
+        xi_prev_d, xi_prev_ref = xi, xi_ref
+        out = fe.fe_block_launch(mat, nw, arr, Ud, xi, outputs=("xi", "R_elem", "K_elem", "sigma", "iters", "flags"))
+        ref = fe_oracle.assemble_block(prob, eq, U, xi_ref, *geo)
+        torch.cuda.synchronize()
+        assert np.array_equal(out["iters"].cpu().numpy(), ref["iters"])
+        assert np.array_equal(out["flags"].cpu().numpy(), ref["flags"])
+        for k in ("xi", "sigma", "R_elem", "K_elem"):
+            assert rel_err(out[k].cpu().numpy(), ref[k]) < TOL, (k, s, rel_err(out[k].cpu().numpy(), ref[k]))
+        # residual-only variant and the atomic global scatter
+        o4 = fe.fe_block_launch(mat, nw, arr, Ud, xi, outputs=("xi", "R_elem", "R_global"))
+        assert torch.equal(o4["R_elem"], out["R_elem"])
+        Rg = np.zeros(arr.n_dofs); np.add.at(Rg, eq.reshape(-1), ref["R_elem"].reshape(-1))
+        assert rel_err(o4["R_global"].cpu().numpy(), Rg) < 1e-9
+        xi, xi_ref = out["xi"], ref["xi"]
+        plastic |= bool((ref["flags"] & 2).any())
+    assert plastic
+    # evaluate_cauchy_at_ips at the stored state
+    sig = fe.evaluate_cauchy_at_ips(mat, arr, Ud, xi)
+    assert rel_err(sig.cpu().numpy(), ref["sigma"]) < TOL
+    # K6: JVP against the oracle, VJP / displacement cotangent through the adjoint identity
+    rng = np.random.default_rng(3)
+    prob_eval = oc.describe(values, P.active_idx, newton_mode="imperative", strain_comps=9, max_iters=0)
+    dp = rng.standard_normal(len(pid)) * np.array([3e3, 0.01, 1.5, 7.0, 4.0])
+    dxp = 1e-4 * rng.standard_normal((n_e, n_ip, 7))
+    dU = 1e-4 * rng.standard_normal(arr.n_dofs)
+    jv = fe.fe_block_jvp(mat, arr, Ud, xi_prev_d, xi, pid, dp, torch.from_numpy(dxp).to(cuda_device),
+                         dU=torch.from_numpy(dU).to(cuda_device))
+    jr = fe_oracle.block_jvp(prob_eval, eq, U, xi_prev_ref, xi_ref, *geo, dp, dxp, dU=dU)
+    assert rel_err(jv["xi"].cpu().numpy(), jr["xi"]) < 1e-9 and rel_err(jv["R_elem"].cpu().numpy(), jr["R_elem"]) < 1e-9
+    Rbar = torch.from_numpy(rng.standard_normal(arr.n_dofs)).to(cuda_device)
+    xibar = torch.from_numpy(rng.standard_normal((n_e, n_ip, 7))).to(cuda_device)
+    pbar, xbp = fe.fe_block_vjp(mat, arr, Ud, xi_prev_d, xi, pid, Rbar, xibar)
+    ub = fe.disp_cotangent_plan(arr, device=cuda_device).sum(
+        fe.fe_block_vjp_disp(mat, arr, Ud, xi_prev_d, xi, xibar, Rbar).reshape(-1))
+    dR = np.zeros(arr.n_dofs); np.add.at(dR, eq.reshape(-1), jr["R_elem"].reshape(-1))
+    lhs = float(Rbar.cpu().numpy() @ dR + (xibar.cpu().numpy() * jr["xi"]).sum())
+    rhs = float(pbar.cpu().numpy() @ dp + (xbp.cpu().numpy() * dxp).sum() + ub.cpu().numpy() @ dU)
+    terms = abs(Rbar.cpu().numpy() @ dR) + abs((xibar.cpu().numpy() * jr["xi"]).sum())
+    assert abs(lhs - rhs) < 1e-9 * terms, (lhs, rhs)
+
+
+@pytest.mark.parametrize("kind", ["J2", "hosford"])
+def test_mixed_tet4_with_the_degree_2_rule(cuda_device, kind):
+    """The reference requires volume degree >= 2 for the mixed u-p formulation
+    (cmad/cli/common.py:379-391): on tets that is the 4-point rule.  All six outputs of the mixed
+    block, the K6-mixed JVP and the VJP adjoint identity against the oracle."""
+    from cmad_b200 import Parameters, active_param_ids
+    values, act, tr = (param_tree("J2", active=("E", "nu", "D", "S", "Y")) if kind == "J2" else
+                       param_tree("hosford", a=6.0, active=("E", "nu", "D", "S", "Y")))
+    P = Parameters(values, act, tr)
+    pid = active_param_ids(P)
+    nodes, conn = _mesh("tet4", (3, 2, 2))
+    arr_h = fe_mesh.block_arrays(nodes, conn, mixed=True, volume_degree=2); arr = arr_h.to(cuda_device)
+    n_e, n_ip, n_b = arr.n_elems, arr.n_ip, arr.n_basis
+    assert (n_ip, n_b) == (4, 4)
+    mat = material_from_values(values)
+    nw = fe.fe_newton_settings(**NEWTON)
+    prob = oc.describe(values, None, newton_mode="traced", strain_comps=9, **NEWTON)
+    nud = 3 * nodes.shape[0]
+    rng = np.random.default_rng(21)
+    stab = 0.7
+
+    def Uvec(t, seed):
+        U = np.zeros(arr.n_dofs)
+        U[:nud] = fe_mesh.synthetic_displacement(nodes, t, seed=seed, ramp=0.004, noise=4e-4)
+        U[nud:] = 30.0 * np.random.default_rng(seed).standard_normal(arr.n_dofs - nud)
+        return U
+    eq, eqp = arr_h.elem_eq.numpy(), arr_h.elem_eq_p.numpy()
+    geo = (arr_h.grad_N.numpy(), arr_h.N.numpy(), arr_h.det.numpy(), arr_h.quad_w.numpy(), arr_h.h.numpy())
+    U1, U2 = Uvec(1.0, 1), Uvec(2.0, 2)
+    z = np.zeros((n_e, n_ip, 7))
+    r1 = fe_oracle.assemble_block_mixed(prob, eq, eqp, U1, z, *geo, stab_mult=stab, want_K=False)
+    r2 = fe_oracle.assemble_block_mixed(prob, eq, eqp, U2, r1["xi"], *geo, stab_mult=stab)
+    U1d, U2d = (torch.from_numpy(u).to(cuda_device) for u in (U1, U2))
+    xi0 = torch.zeros((n_e, n_ip, 7), dtype=torch.float64, device=cuda_device)
+    _, _, xi1 = fe.assemble_element_block_mixed(mat, nw, arr, U1d, xi0, stab_mult=stab, want_K=False)
+    R, vals, xi2 = fe.assemble_element_block_mixed(mat, nw, arr, U2d, xi1, stab_mult=stab,
+                                                   r_plan=fe.mixed_r_plan(arr, device=cuda_device))
+    torch.cuda.synchronize()
+    assert rel_err(xi2.cpu().numpy(), r2["xi"]) < TOL and rel_err(R.cpu().numpy(), r2["R"]) < TOL
+    ref_vals = np.concatenate([r2[k].reshape(-1) for k in ("K_uu", "K_up", "K_pu", "K_pp")])
+    off = 0
+    for k in ("K_uu", "K_up", "K_pu", "K_pp"):
+        m_ = r2[k].size
+        assert rel_err(vals[off:off + m_].cpu().numpy(), r2[k].reshape(-1)) < TOL, k
+        off += m_
+    assert off == ref_vals.size and float((xi2[..., 6] - xi1[..., 6]).max()) > 0.0
+    # K6-mixed
+    prob_eval = oc.describe(values, P.active_idx, newton_mode="imperative", strain_comps=9, max_iters=0)
+    dp = rng.standard_normal(len(pid)) * np.array([3e3, 0.01, 1.5, 7.0, 4.0])
+    dxp = 1e-4 * rng.standard_normal((n_e, n_ip, 7))
+    dUn = 1e-4 * rng.standard_normal(arr.n_dofs); dUn[nud:] *= 1e4
+    jv = fe.fe_block_jvp(mat, arr, U2d, xi1, xi2, pid, dp, torch.from_numpy(dxp).to(cuda_device),
+                         dU=torch.from_numpy(dUn).to(cuda_device), stab_mult=stab)
+    jr = fe_oracle.block_jvp_mixed(prob_eval, eq, eqp, U2, r1["xi"], r2["xi"], *geo, dp, dxp, stab_mult=stab, dU=dUn)
+    for k in ("xi", "R_elem", "R_p_elem"):
+        assert rel_err(jv[k].cpu().numpy(), jr[k]) < 1e-9, k
+    Rbar = torch.from_numpy(rng.standard_normal(arr.n_dofs)).to(cuda_device)
+    xibar = torch.from_numpy(rng.standard_normal((n_e, n_ip, 7))).to(cuda_device)
+    pbar, xbp = fe.fe_block_vjp(mat, arr, U2d, xi1, xi2, pid, Rbar, xibar, stab_mult=stab)
+    j0 = fe_oracle.block_jvp_mixed(prob_eval, eq, eqp, U2, r1["xi"], r2["xi"], *geo, dp, dxp, stab_mult=stab)
+    dR = np.zeros(arr.n_dofs)
+    np.add.at(dR, eq.reshape(-1), j0["R_elem"].reshape(-1)); np.add.at(dR, eqp.reshape(-1), j0["R_p_elem"].reshape(-1))
+    lhs = float(Rbar.cpu().numpy() @ dR + (xibar.cpu().numpy() * j0["xi"]).sum())
+    rhs = float(pbar.cpu().numpy() @ dp + (xbp.cpu().numpy() * dxp).sum())
+    terms = abs(Rbar.cpu().numpy()[:nud] @ dR[:nud]) + abs(Rbar.cpu().numpy()[nud:] @ dR[nud:]) + \
+        abs((xibar.cpu().numpy() * j0["xi"]).sum())
+    assert abs(lhs - rhs) < 1e-9 * terms, (lhs, rhs)
