@@ -58,6 +58,8 @@ def main():
     ap.add_argument("--load-steps", type=int, default=2, help="load steps taken before timing (state carried)")
     ap.add_argument("--variants", default="K3,K4,K5")
     ap.add_argument("--generic", action="store_true")
+    ap.add_argument("--volume-degree", type=int, default=None,
+                    help="quadrature override (tet4: 2 -> 4 points; hex8: 4 -> 27 points): the any-rule kernel")
     args = ap.parse_args()
 
     import torch
@@ -71,7 +73,7 @@ def main():
     nodes, conn = fe_mesh.structured_hex_mesh((args.div,) * 3)
     if args.family == "tet4":
         conn = fe_mesh.split_hex_to_tets(conn)
-    arr = fe_mesh.block_arrays(nodes, conn, device=dev)
+    arr = fe_mesh.block_arrays(nodes, conn, device=dev, volume_degree=args.volume_degree)
     n_e, n_ip = arr.n_elems, arr.n_ip
     h = 1.0 / args.div
     values = materials(args.kind)
@@ -129,7 +131,7 @@ def main():
         # mixed u-p formulation: K3 with the momentum stress dev(cauchy) - p I + the pressure-block
         # kernel; algorithmic bytes = K3's + p_e, h, R_p and the (u,p), (p,u), (p,p) streams
         n_b = arr.n_basis
-        arr_m = fe_mesh.block_arrays(nodes, conn, device=dev, mixed=True)
+        arr_m = fe_mesh.block_arrays(nodes, conn, device=dev, mixed=True, volume_degree=args.volume_degree)
         rng = np.random.default_rng(5)
         Um = torch.cat([U, torch.from_numpy(-60.0 + 5.0 * rng.standard_normal(nodes.shape[0])).to(dev)])
         l0 = mpmod.launch_count()

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(FE_BLOCK) fe_generic_kernel(const __grid_const
                         for (int j = 0; j < 3; ++j) s = fma(gN[a][j], D[vix(j, i)][be], s);
                         P[be] = s;
                     }
-                    double* r = Ke + (3 * a + i) * ND;
+                    double row[ND];
 #pragma unroll
                     for (int bb = 0; bb < NB; ++bb)
 #pragma unroll
@@ -121,8 +121,20 @@ __global__ void __launch_bounds__(FE_BLOCK) fe_generic_kernel(const __grid_const
                             double s = 0.0;
 #pragma unroll
                             for (int l = 0; l < 3; ++l) s = fma(P[vix(k, l)], gN[bb][l], s);
-                            r[3 * bb + k] = (ip == 0) ? s : r[3 * bb + k] + s;
+                            row[3 * bb + k] = s;
                         }
+                    // whole 32-byte sectors: first point stores the row, later points add to it
+                    double* r = Ke + (3 * a + i) * ND;
+#pragma unroll
+                    for (int q = 0; q < ND / 4; ++q) {
+                        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+                        if (ip > 0)
+                            asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                                         : "=d"(v0), "=d"(v1), "=d"(v2), "=d"(v3) : "l"(r + 4 * q) : "memory");
+                        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(r + 4 * q), "d"(v0 + row[4 * q]),
+                                     "d"(v1 + row[4 * q + 1]), "d"(v2 + row[4 * q + 2]), "d"(v3 + row[4 * q + 3])
+                                     : "memory");
+                    }
                 }
         }
     }

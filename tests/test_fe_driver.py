@@ -325,7 +325,9 @@ def mixed_uniaxial_cube(div, family="hex8"):
     nodes, conn = fe_mesh.structured_hex_mesh((div,) * 3)
     if family == "tet4":
         conn = fe_mesh.split_hex_to_tets(conn)
-    arr = fe_mesh.block_arrays(nodes, conn, mixed=True)
+    # the reference's deck driver forces volume degree >= 2 for mixed (cli/common.py:379-391):
+    # hex8 x 8 (its default) and tet4 x 4
+    arr = fe_mesh.block_arrays(nodes, conn, mixed=True, volume_degree=2)
     nid = np.arange(nodes.shape[0])
     on = lambda ax, v: nid[np.isclose(nodes[:, ax], v)]
     pin = np.concatenate([on(0, 0.0) * 3 + 0, on(1, 0.0) * 3 + 1, on(2, 0.0) * 3 + 2])
@@ -417,7 +419,7 @@ def _mixed_gradient_problem(div=2, family="hex8"):
     conn = fe_mesh.structured_hex_mesh((div,) * 3)[1]
     if family == "tet4":
         conn = fe_mesh.split_hex_to_tets(conn)
-    arr = fe_mesh.block_arrays(nodes, conn, mixed=True)
+    arr = fe_mesh.block_arrays(nodes, conn, mixed=True, volume_degree=2)
     return values, P, nodes, arr, bcs, pattern, scatter
 
 
