@@ -710,7 +710,8 @@ static int fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* 
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e;
     const bool default_rule = (b.n_basis == 4 && b.n_ip == 1) || (b.n_basis == 8 && b.n_ip == 8);
-    const bool radial = default_rule && A.m.yield == CMADX_YIELD_J2 && !A.m.rot &&
+    const bool tuned = default_rule || (b.n_basis == 4 && b.n_ip == 4);       // + fe_tet4x4.cu
+    const bool radial = tuned && A.m.yield == CMADX_YIELD_J2 && !A.m.rot &&
                         !(A.nw.flags & CMADX_NEWTON_F_GENERIC);
     if (!default_rule) A.nw.defer_request = 0;       // one pass of the generic-rule kernel
     if (radial) {

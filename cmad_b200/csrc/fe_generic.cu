@@ -16,10 +16,17 @@
 namespace cmadx {
 namespace {
 
-template <int SOLVER, bool ROT, bool WANT_K, int NB>
+// LIST: the elements a tuned first pass handed back (bail list), one thread per list entry
+template <int SOLVER, bool ROT, bool WANT_K, int NB, bool LIST = false>
 __global__ void __launch_bounds__(FE_BLOCK) fe_generic_kernel(const __grid_constant__ FeArgs A) {
     const cmadx_fe_block_t& b = A.b;
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (LIST) {
+        const unsigned cnt = *A.bail_count;
+        const bool all = cnt > A.bail_cap;
+        if (e >= (all ? b.n_elems : (int64_t)cnt)) return;
+        if (!all) e = A.bail_list[e];
+    }
     if (e >= b.n_elems) return;
     const int nip = b.n_ip;
     constexpr int ND = NB * 3;
@@ -164,7 +171,28 @@ struct GenericLauncher {
     };
 };
 
+template <int NB>
+struct GenericListLauncher {
+    template <int SOLVER, bool ROT, bool WANT_K, bool LIST>
+    struct L {
+        static cudaError_t run(const FeArgs& A, cudaStream_t stream, int) {
+            // sized for the whole block (the count lives on the device); surplus threads exit at once
+            const int64_t nblk = (A.b.n_elems + FE_BLOCK - 1) / FE_BLOCK;
+            fe_generic_kernel<SOLVER, ROT, WANT_K, NB, true><<<(unsigned)nblk, FE_BLOCK, 0, stream>>>(A);
+            return cudaGetLastError();
+        }
+    };
+};
+
 }  // namespace
+
+// second pass over a bail list with the generic solver of the block's yield surface
+cudaError_t launch_fe_generic_list(const FeArgs& A, cudaStream_t stream) {
+    if (A.b.n_elems == 0) return cudaSuccess;
+    const int solver = 1 + A.m.yield;
+    if (A.b.n_basis == 4) return dispatch_fe_list<GenericListLauncher<4>::L>(A, solver, stream, 0);
+    return dispatch_fe_list<GenericListLauncher<8>::L>(A, solver, stream, 0);
+}
 
 // solver: 1 + yield (primal, generic Newton) or 4 + yield (JVP)
 cudaError_t launch_fe_generic(const FeArgs& A, int solver, cudaStream_t stream) {

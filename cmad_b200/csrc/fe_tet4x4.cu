@@ -1,0 +1,171 @@
+// K3 / K4 for tet4 elements with the 4-point degree-2 rule - the rule the reference's deck
+// driver forces on the mixed u-p formulation (cmad/cli/common.py:379-391) and the first
+// `volume degree` override a tet deck would use.  Four lanes own one element, one integration
+// point each (8 elements per warp): every lane gathers U_e, interpolates grad_u at its point,
+// runs the local Newton there (J2 radial return with the element-level hand-back list, or the
+// generic solver), and the element sums - R_e and the twelve rows of K_e - are butterfly
+// reductions over the 4 lanes in fixed order (bit-reproducible; the same association for every
+// element).  Row r of K_e ends up on lane r mod 4, so after every group of four rows each lane
+// streams one 96-byte row out as three 256-bit stores: K_e is written exactly once (the
+// any-rule kernel of fe_generic.cu makes n_ip passes over it).
+#include "fe_common.cuh"
+
+namespace cmadx {
+namespace {
+
+CMADX_DEV double quad_sum(double v) {          // sum over the 4 lanes of an element
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+
+template <int SOLVER, bool ROT, bool WANT_K>
+__global__ void __launch_bounds__(FE_BLOCK, (SOLVER == 0) ? 3 : 1) fe_tet4x4_kernel(const __grid_constant__ FeArgs A) {
+    const cmadx_fe_block_t& b = A.b;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = t >> 2;
+    const int ip = (int)(t & 3);
+    const bool live = e < b.n_elems;
+    const int64_t el = live ? e : 0;
+    const int64_t p = el * 4 + ip;
+    double gN[4][3], U[4][3], xp[7];
+    int eq[12];
+    {
+        const int4* q = reinterpret_cast<const int4*>(b.elem_eq + el * 12);
+        const int4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+        eq[0] = q0.x; eq[1] = q0.y; eq[2] = q0.z; eq[3] = q0.w;
+        eq[4] = q1.x; eq[5] = q1.y; eq[6] = q1.z; eq[7] = q1.w;
+        eq[8] = q2.x; eq[9] = q2.y; eq[10] = q2.z; eq[11] = q2.w;
+        const double* g = b.grad_N + p * 12;
+        ld256(g, gN[0][0], gN[0][1], gN[0][2], gN[1][0]);
+        ld256(g + 4, gN[1][1], gN[1][2], gN[2][0], gN[2][1]);
+        ld256(g + 8, gN[2][2], gN[3][0], gN[3][1], gN[3][2]);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) U[a][k] = __ldg(b.U + eq[3 * a + k]);
+#pragma unroll
+        for (int c = 0; c < 7; ++c) xp[c] = __ldg(b.xi_prev + p * 7 + c);
+    }
+    const double wdv = live ? __ldg(b.quad_w + ip) * __ldg(b.det + p) : 0.0;
+    double eps[6];
+    strain_from_U<4>(U, gN, eps);
+    if (!live) { eps[0] = 1e-3; eps[1] = eps[2] = eps[3] = eps[4] = eps[5] = 0.0; }
+
+    PointOut o;
+    double D[6][6];
+    DevNewton nw = A.nw;
+    nw.defer_after = 0;
+    solve_point<SOLVER, ROT, WANT_K>(A.m, nw, xp, eps, live, o, D);
+
+    // an element is handed to the generic second pass as a whole
+    bool ebail = false;
+    if (SOLVER == 0) {
+        const unsigned bal = __ballot_sync(0xffffffffu, live && o.bail);
+        ebail = ((bal >> ((threadIdx.x & 31) & ~3)) & 0xfu) != 0u;
+        if (ebail && live && ip == 0 && A.bail_count) append_bail(A, e);
+    }
+    const bool emit = live && !ebail;
+    if (emit) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) b.xi[p * 7 + c] = o.x[c];
+        if (b.iters) b.iters[p] = o.iters;
+        if (b.flags) b.flags[p] = o.flags;
+        if (b.sigma) {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) b.sigma[p * 6 + a] = o.sg[a];
+        }
+    }
+    if (A.mix_eq_p) {
+        const int4 qp = __ldg(reinterpret_cast<const int4*>(A.mix_eq_p + el * 4));
+        const double* Np = A.mix_N + ip * 4;
+        const double pr = fma(__ldg(Np + 3), __ldg(b.U + qp.w),
+                              fma(__ldg(Np + 2), __ldg(b.U + qp.z),
+                                  fma(__ldg(Np + 1), __ldg(b.U + qp.y), __ldg(Np) * __ldg(b.U + qp.x))));
+        mixed_momentum_stress<WANT_K>(pr, o.sg, D);
+    }
+    // ---- R_e: this point's contribution, summed over the element's 4 lanes; lane a keeps node a
+    if (b.R_elem || b.R_global) {
+        double mine[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                double s = 0.0;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) s = fma(gN[a][j], o.sg[vix(j, i)], s);
+                s = quad_sum(s * wdv);
+                if (a == ip) mine[i] = s;
+            }
+        if (emit) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                if (b.R_elem) b.R_elem[e * 12 + 3 * ip + i] = mine[i];
+                if (b.R_global) atomicAdd(b.R_global + eq[3 * ip + i], mine[i]);
+            }
+        }
+    }
+    if constexpr (WANT_K) {
+#pragma unroll
+        for (int al = 0; al < 6; ++al)
+#pragma unroll
+            for (int be = 0; be < 6; ++be) D[al][be] *= is_diag(be) ? wdv : 0.5 * wdv;
+        double* Ke = b.K_elem + el * 144;
+#pragma unroll 1
+        for (int g4 = 0; g4 < 3; ++g4) {             // rows 4 g4 .. 4 g4 + 3
+            double keep[12];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int r = 4 * g4 + rr, a = r / 3, i = r - 3 * a;
+                double P[6];
+#pragma unroll
+                for (int be = 0; be < 6; ++be) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) s = fma(gN[a][j], D[vix(j, i)][be], s);
+                    P[be] = s;
+                }
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int l = 0; l < 3; ++l) s = fma(P[vix(k, l)], gN[bb][l], s);
+                        s = quad_sum(s);
+                        if (rr == ip) keep[3 * bb + k] = s;
+                    }
+            }
+            if (emit) {
+                double* r = Ke + (4 * g4 + ip) * 12;
+                st256(r, keep[0], keep[1], keep[2], keep[3]);
+                st256(r + 4, keep[4], keep[5], keep[6], keep[7]);
+                st256(r + 8, keep[8], keep[9], keep[10], keep[11]);
+            }
+        }
+    }
+}
+
+template <int SOLVER, bool ROT, bool WANT_K, bool LIST>
+struct Tet4x4Launcher {
+    static cudaError_t run(const FeArgs& A, cudaStream_t stream, int) {
+        if constexpr (SOLVER >= FE_JVP) {
+            return cudaErrorInvalidValue;            // K6-JVP of this rule runs the any-rule kernel
+        } else {
+            const int64_t nthr = A.b.n_elems * 4;
+            const int64_t nblk = (nthr + FE_BLOCK - 1) / FE_BLOCK;
+            fe_tet4x4_kernel<SOLVER, ROT, WANT_K><<<(unsigned)nblk, FE_BLOCK, 0, stream>>>(A);
+            return cudaGetLastError();
+        }
+    }
+};
+
+}  // namespace
+
+// solver: 0 = J2 radial return (hand-backs go to the any-rule kernel in list mode), 1 + yield
+cudaError_t launch_fe_tet4x4(const FeArgs& A, int solver, cudaStream_t stream) {
+    if (A.b.n_elems == 0) return cudaSuccess;
+    return dispatch_fe<Tet4x4Launcher, false>(A, solver, stream, 0);
+}
+
+}  // namespace cmadx

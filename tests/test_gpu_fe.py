@@ -802,3 +802,38 @@ def test_mixed_tet4_with_the_degree_2_rule(cuda_device, kind):
     terms = abs(Rbar.cpu().numpy()[:nud] @ dR[:nud]) + abs(Rbar.cpu().numpy()[nud:] @ dR[nud:]) + \
         abs((xibar.cpu().numpy() * j0["xi"]).sum())
     assert abs(lhs - rhs) < 1e-9 * terms, (lhs, rhs)
+
+
+@pytest.mark.parametrize("family,degree", [("tet4", 2), ("tet4", None), ("hex8", None)])
+def test_softening_elements_take_the_hand_back_pass(cuda_device, family, degree):
+    """Voce softening (S < 0): the J2 radial-return first pass hands elements back and the second
+    pass re-solves them with the generic Newton - for tet4 x 4 that second pass is the any-rule
+    kernel in list mode (fe_generic.cu).  States / residual / tangent still match the oracle
+    (counts compared on the agreeing points: softening sits on the branch knife-edge)."""
+    from cmad_b200 import mp
+    values, _, _ = param_tree("J2")
+    values["plastic"]["flow stress"]["hardening"]["voce"] = {"S": -80.0, "D": 40.0}
+    nodes, conn = _mesh(family, (4, 3, 3))
+    arr_h = fe_mesh.block_arrays(nodes, conn, volume_degree=degree); arr = arr_h.to(cuda_device)
+    mat = material_from_values(values)
+    nw = fe.fe_newton_settings(**NEWTON)
+    prob = oc.describe(values, None, newton_mode="traced", strain_comps=9, **NEWTON)
+    n_e, n_ip = arr.n_elems, arr.n_ip
+    geo = (arr_h.grad_N.numpy(), arr_h.det.numpy(), arr_h.quad_w.numpy())
+    xi_ref = np.zeros((n_e, n_ip, 7))
+    xi = torch.zeros((n_e, n_ip, 7), dtype=torch.float64, device=cuda_device)
+    bailed = 0
+    for s in (1, 2, 3):
+        U = fe_mesh.synthetic_displacement(nodes, t=float(s), seed=60 + s, ramp=0.004, noise=6e-4)
+        out = fe.fe_block_launch(mat, nw, arr, torch.from_numpy(U).to(cuda_device), xi,
+                                 outputs=("xi", "R_elem", "K_elem", "iters", "flags"))
+        bailed += mp.debug_bail_count()
+        ref = fe_oracle.assemble_block(prob, arr_h.elem_eq.numpy(), U, xi_ref, *geo)
+        same = (out["iters"].cpu().numpy() == ref["iters"]) & (out["flags"].cpu().numpy() == ref["flags"])
+        assert same.mean() > 0.99
+        ok = same.all(axis=1)                                  # elements whose points all agree
+        for k in ("xi", "R_elem", "K_elem"):
+            g, r = out[k].cpu().numpy()[ok], ref[k][ok]
+            assert rel_err(g, r) < 1e-9, (k, s, rel_err(g, r))
+        xi, xi_ref = out["xi"], ref["xi"]
+    assert bailed > 0
