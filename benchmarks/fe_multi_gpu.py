@@ -56,7 +56,10 @@ def main():
     n_total = conn.shape[0]
     per = n_total // world                         # element e = i*ny*nz + ...: contiguous slabs in x
     lo, hi = rank * per, (rank + 1) * per
-    arr = fe_mesh.block_arrays(nodes, conn[lo:hi], device=dev, mixed=args.mixed)
+    # the reference's deck driver forces volume degree >= 2 on the mixed formulation
+    # (cmad/cli/common.py:379-391): tet4 x 4 points (hex8 x 8 is its default anyway)
+    arr = fe_mesh.block_arrays(nodes, conn[lo:hi], device=dev, mixed=args.mixed,
+                               volume_degree=2 if args.mixed else None)
     arr.n_dofs = nodes.shape[0] * (4 if args.mixed else 3)
     values = materials("J2")
     const = lambda t, c: {k: const(v, c) for k, v in t.items()} if isinstance(t, dict) else c
@@ -126,7 +129,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         tot, asm, red, vjp = (float(x) for x in t)
-        print(json.dumps({"family": args.family, "mixed": bool(args.mixed), "n_gpus": world, "elements_per_gpu": n_e, "elements_total": n_total,
+        print(json.dumps({"family": args.family, "mixed": bool(args.mixed), "n_ip": n_ip, "n_gpus": world, "elements_per_gpu": n_e, "elements_total": n_total,
                           "n_dofs": arr.n_dofs, "scaling": "weak", "steps": args.steps, "warmup": args.warmup,
                           "ms_step": tot, "ms_assemble_K3_K5": asm, "ms_allreduce_R": red,
                           "ms_vjp_plus_allreduce_grad": vjp, "R_bytes": arr.n_dofs * 8,
