@@ -252,6 +252,34 @@ def MPDirectAdjointObjective(qoi: Calibration, global_state: np.ndarray, device=
                                    reference_qoi_cross_terms=reference_qoi_cross_terms)
 
 
+class MPJVPObjective:
+    """The ``JVP`` strategy (cmad/objectives/mp_jvp_objective.py:14-80): J, its gradient and its
+    Hessian as ``jax.value_and_grad`` / ``jax.hessian`` of the whole traced time loop give them -
+    the TRACED local Newton with its line search (``update_fun = make_newton_solve(...)``,
+    cmad/cli/sensitivity.py:98-107) and the exact second derivatives (``jax.hessian`` has no
+    omitted block: this is the library's complete Hessian).  Same three entry points, canonical
+    coordinates.  ``update_fun`` is accepted for signature compatibility and must be None or
+    carry the traced solver's settings as attributes ``max_iters / abs_tol / rel_tol /
+    ls_max_evals`` (the kernels implement make_newton_solve themselves)."""
+
+    def __init__(self, qoi: Calibration, global_state: np.ndarray, update_fun=None, device=None, group=None):
+        kw = {k: getattr(update_fun, k) for k in ("max_iters", "abs_tol", "rel_tol", "ls_max_evals")
+              if update_fun is not None and hasattr(update_fun, k)}
+        newton = NewtonSettings(mode="traced", **{"max_iters": 10, "abs_tol": 1e-14, "rel_tol": 1e-14, **kw})
+        self._grad = _single_point_objective(qoi, global_state, "adjoint", device, group, newton=newton)
+        self._hess = _single_point_objective(qoi, global_state, "direct_adjoint", device, group, newton=newton)
+
+    def evaluate_objective(self, flat_active_values) -> float:
+        return self._grad.evaluate(flat_active_values).J
+
+    def evaluate_objective_and_grad(self, flat_active_values):
+        r = self._grad.evaluate(flat_active_values)
+        return r.J, r.grad
+
+    def evaluate_hessian(self, flat_active_values) -> np.ndarray:
+        return self._hess.evaluate(flat_active_values).hessian
+
+
 def MPDirectObjective(qoi: Calibration, global_state: np.ndarray, device=None, group=None):
     """Reference signature (mp_objective.py:150): gradient by forward sensitivities."""
     return _single_point_objective(qoi, global_state, "direct", device, group)

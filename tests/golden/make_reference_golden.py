@@ -260,6 +260,37 @@ def _hessian_job(job):
                 active_idx=np.asarray(P.active_idx), param_names=np.array(P._names))
 
 
+def _hessian_jvp_job(job):
+    """MPJVPObjective (mp_jvp_objective.py:14-80): jax.value_and_grad / jax.hessian of the whole
+    time loop through make_newton_solve and its custom_jvp rule - the reference's OTHER Hessian
+    strategy, with no hand-assembled blocks."""
+    from cmad.objectives.mp_jvp_objective import MPJVPObjective
+    kind, scaled, F, weight = job
+    values, act, tr = objective_trees(kind, scaled)
+    P = Parameters(values, act, tr)
+    model = SmallElasticPlastic(P)
+    N = F.shape[2] - 1
+    data = np.zeros((3, 3, N + 1))
+    model.set_xi_to_init_vals()
+    for step in range(1, N + 1):
+        model.gather_global(mp_U_from_F(F[:, :, step]), mp_U_from_F(F[:, :, step - 1]))
+        newton_solve(model)
+        model.seed_none(); model.evaluate_cauchy()
+        data[:, :, step] = model.Sigma().copy()
+        model.advance_xi()
+    offset = 1.1 * P.flat_active_values(False)
+    P = Parameters(*objective_trees(kind, scaled))
+    model = SmallElasticPlastic(P)
+    P.set_active_values_from_flat(offset, False)
+    x = P.flat_active_values(True)
+    obj = MPJVPObjective(Calibration(model, data, weight), F, make_newton_solve(model._residual))
+    J, g = obj.evaluate_objective_and_grad(x)
+    H = obj.evaluate_hessian(x)
+    return dict(J=float(np.asarray(J)), grad=np.asarray(g, float), hessian=np.asarray(H, float),
+                F=F, data=data, weight=weight, x_canonical=x, active_native=offset,
+                active_idx=np.asarray(P.active_idx))
+
+
 # --------------------------------------------------------------------------- #
 #  D. FE element kernels: per_element_R_and_K_coupled / per_element_R_coupled  #
 #     over the per-IP COUPLED evaluator (displacement and mixed u-p)            #
@@ -551,6 +582,20 @@ def main():
                 out[f"{nm}.{k}"] = v
             print("hessian", nm, r["J"], r["grad"], np.linalg.eigvalsh(r["hessian"]))
         np.savez_compressed(os.path.join(HERE, "ref_mp_hessian.npz"), **out)
+
+    if only is None or "hessian_jvp" in only:
+        w = np.array([[1.0, 0.5, 0.0], [0.5, 1.0, 0.0], [0.0, 0.0, 0.25]])
+        jobs, names = [], []
+        for kind in ("J2", "hill", "hosford"):
+            for scaled in (True, False):
+                jobs.append((kind, scaled, two_leg_F(11, 8, scale=1.5, diag_only=kind == "hosford"), w))
+                names.append(f"{kind}.{'scaled' if scaled else 'native'}")
+        out = {}
+        for nm, r in zip(names, pool.map(_hessian_jvp_job, jobs, chunksize=1)):
+            for k, v in r.items():
+                out[f"{nm}.{k}"] = v
+            print("hessian_jvp", nm, r["J"], r["grad"], np.linalg.eigvalsh(r["hessian"]))
+        np.savez_compressed(os.path.join(HERE, "ref_mp_hessian_jvp.npz"), **out)
 
     if only is None or "hessian_dt" in only:
         # KA5 setting (tests/objectives/test_jvp_vs_original.py, test_J2_fd_checks.py:266-289): the
