@@ -194,7 +194,7 @@ __device__ __noinline__ double qoi_cross_terms(const HD& lam, const HD& mu, cons
 
 // d2/ds du of L_t = J_t + phi . C along the two directions carried by the hyper-duals
 template <int YK>
-__device__ __noinline__ double lagrangian_mixed(const DevMat& m, const HessParams& P, const HD (&x)[7],
+__device__ __forceinline__ double lagrangian_mixed(const DevMat& m, const HessParams& P, const HD (&x)[7],
                                                 const HD (&xp)[7], const double (&em)[6],
                                                 const double (&phi)[7], const double (&w)[9],
                                                 const double (&d)[9], bool plastic) {
@@ -234,12 +234,18 @@ __global__ void __launch_bounds__(HESS_BLOCK) mp_hess_kernel(const __grid_consta
     const int N = A.h.nsteps, na = A.n_active, sc = A.h.strain_comps;
     const int npairs = na * (na + 1) / 2;
 
-    double Hacc[HESS_MAX_PAIRS];
-    for (int q = 0; q < npairs; ++q) Hacc[q] = 0.0;
-    double X[CMADX_MAX_ACTIVE][7], Xp[CMADX_MAX_ACTIVE][7];
+    // X_t, X_{t-1} and the pair sums live in SHARED memory, [slot][thread] (conflict-free): as
+    // per-thread local arrays (4.3 KB of stack) they overflowed L1 and L2 and the pass was bound
+    // by local-memory round trips to DRAM (ncu: long-scoreboard 7.4 per issue, FP64 pipe 18 %)
+    extern __shared__ double hs[];
+    constexpr int NX = 7;
+    auto X = [&](int c, int r) -> double& { return hs[(c * NX + r) * HESS_BLOCK + threadIdx.x]; };
+    auto Xp = [&](int c, int r) -> double& { return hs[((na + c) * NX + r) * HESS_BLOCK + threadIdx.x]; };
+    auto Hacc = [&](int q) -> double& { return hs[(2 * na * NX + q) * HESS_BLOCK + threadIdx.x]; };
+    for (int q = 0; q < npairs; ++q) Hacc(q) = 0.0;
     for (int c = 0; c < na; ++c)
 #pragma unroll
-        for (int r = 0; r < 7; ++r) { X[c][r] = 0.0; Xp[c][r] = 0.0; }
+        for (int r = 0; r < 7; ++r) { X(c, r) = 0.0; Xp(c, r) = 0.0; }
     double x[7], xp[7];
 #pragma unroll
     for (int c = 0; c < 7; ++c) {
@@ -307,13 +313,13 @@ __global__ void __launch_bounds__(HESS_BLOCK) mp_hess_kernel(const __grid_consta
         for (int c = 0; c < na; ++c) {
             double col[7], rhs[7];
             dC_dp_column(m, A.pid[c], pl, pt.yf, pt.n, pt.f, pt.eD, x[6], dg, Mee, nee, sig, col);
-            const double x6 = Xp[c][6];
+            const double x6 = Xp(c, 6);
 #pragma unroll
-            for (int q = 0; q < 6; ++q) rhs[q] = -col[q] + Xp[c][q] - (pl ? pt.n[q] * x6 : 0.0);
+            for (int q = 0; q < 6; ++q) rhs[q] = -col[q] + Xp(c, q) - (pl ? pt.n[q] * x6 : 0.0);
             rhs[6] = -col[6] + (pl ? 0.0 : x6);
             if (slow && trouble) lu.solve_pivot(rhs); else lu.solve_natural(rhs);
 #pragma unroll
-            for (int q = 0; q < 7; ++q) X[c][q] = rhs[q];
+            for (int q = 0; q < 7; ++q) X(c, q) = rhs[q];
         }
         // ---- H_ij += D2 L_t [Z_i, Z_j], one hyper-dual evaluation per pair
         int q = 0;
@@ -339,26 +345,26 @@ __global__ void __launch_bounds__(HESS_BLOCK) mp_hess_kernel(const __grid_consta
                 HD xh[7], xph[7];
 #pragma unroll
                 for (int r = 0; r < 7; ++r) {
-                    xh[r] = {x[r], X[ci][r], X[cj][r], 0.0};
-                    xph[r] = {xp[r], Xp[ci][r], Xp[cj][r], 0.0};
+                    xh[r] = {x[r], X(ci, r), X(cj, r), 0.0};
+                    xph[r] = {xp[r], Xp(ci, r), Xp(cj, r), 0.0};
                 }
                 double hij = lagrangian_mixed<YK>(m, P, xh, xph, em, phi, A.h.weight, d, pl);
                 if (A.hess_flags & CMADX_HESS_F_REFERENCE_QOI_CROSS)
                     hij -= qoi_cross_terms(P.lam, P.mu, xh, em, A.h.weight, d);
-                Hacc[q] += hij;
+                Hacc(q) += hij;
             }
         }
 #pragma unroll
         for (int c = 0; c < 7; ++c) xp[c] = x[c];
         for (int c = 0; c < na; ++c)
 #pragma unroll
-            for (int r = 0; r < 7; ++r) Xp[c][r] = X[c][r];
+            for (int r = 0; r < 7; ++r) Xp(c, r) = X(c, r);
     }
     // ---- block reduction of the pair sums (fixed order)
     __shared__ double sm[HESS_BLOCK / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int q = 0; q < npairs; ++q) {
-        double v = live ? Hacc[q] : 0.0;
+        double v = live ? Hacc(q) : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if (lane == 0) sm[warp] = v;
@@ -414,7 +420,7 @@ __device__ __noinline__ double qoi_cross_terms_dt(const HD& lam, const HD& mu, c
 }
 
 template <int YK, int DT, int N>
-__device__ __noinline__ double lagrangian_mixed_dt(const DevMat& m, const HessParams& P, const HD (&x)[N],
+__device__ __forceinline__ double lagrangian_mixed_dt(const DevMat& m, const HessParams& P, const HD (&x)[N],
                                                    const HD (&xp)[N], const double (&em)[6],
                                                    const double (&phi)[N], const double (&w)[9],
                                                    const double (&d)[9], bool plastic) {
@@ -456,12 +462,14 @@ __global__ void __launch_bounds__(HESS_BLOCK) mp_hess_dt_kernel(const __grid_con
     const int NT = A.h.nsteps, na = A.n_active, sc = A.h.strain_comps;
     const int npairs = na * (na + 1) / 2;
 
-    double Hacc[HESS_MAX_PAIRS];
-    for (int q = 0; q < npairs; ++q) Hacc[q] = 0.0;
-    double X[CMADX_MAX_ACTIVE][N], Xp[CMADX_MAX_ACTIVE][N];
+    extern __shared__ double hs[];          // X_t, X_{t-1}, pair sums: [slot][thread], see mp_hess_kernel
+    auto X = [&](int c, int r) -> double& { return hs[(c * N + r) * HESS_BLOCK + threadIdx.x]; };
+    auto Xp = [&](int c, int r) -> double& { return hs[((na + c) * N + r) * HESS_BLOCK + threadIdx.x]; };
+    auto Hacc = [&](int q) -> double& { return hs[(2 * na * N + q) * HESS_BLOCK + threadIdx.x]; };
+    for (int q = 0; q < npairs; ++q) Hacc(q) = 0.0;
     for (int c = 0; c < na; ++c)
 #pragma unroll
-        for (int r = 0; r < N; ++r) { X[c][r] = 0.0; Xp[c][r] = 0.0; }
+        for (int r = 0; r < N; ++r) { X(c, r) = 0.0; Xp(c, r) = 0.0; }
     double x[N], xp[N];
 #pragma unroll
     for (int c = 0; c < N; ++c) {
@@ -521,15 +529,15 @@ __global__ void __launch_bounds__(HESS_BLOCK) mp_hess_dt_kernel(const __grid_con
                 const int k = pid - CMADX_P_EL0;
                 dr = (m.dlam[k] * m.two_mu - m.lam * 2.0 * m.dmu[k]) * m.inv_two_mu * m.inv_two_mu * tree;
             }
-            const double x6 = Xp[c][6];
+            const double x6 = Xp(c, 6);
 #pragma unroll
-            for (int q = 0; q < 6; ++q) rhs[q] = -c7[q] + Xp[c][q] - (pl ? pt.b.n[q] * x6 : 0.0);
+            for (int q = 0; q < 6; ++q) rhs[q] = -c7[q] + Xp(c, q) - (pl ? pt.b.n[q] * x6 : 0.0);
             rhs[6] = -c7[6] + (pl ? 0.0 : x6);
 #pragma unroll
             for (int k = 0; k < NZ; ++k) rhs[7 + k] = -dr;
             if (slow && trouble) lu.solve_pivot(rhs); else lu.solve_natural(rhs);
 #pragma unroll
-            for (int q = 0; q < N; ++q) X[c][q] = rhs[q];
+            for (int q = 0; q < N; ++q) X(c, q) = rhs[q];
         }
         int q = 0;
 #pragma unroll 1
@@ -554,25 +562,25 @@ __global__ void __launch_bounds__(HESS_BLOCK) mp_hess_dt_kernel(const __grid_con
                 HD xh[N], xph[N];
 #pragma unroll
                 for (int r = 0; r < N; ++r) {
-                    xh[r] = {x[r], X[ci][r], X[cj][r], 0.0};
-                    xph[r] = {xp[r], Xp[ci][r], Xp[cj][r], 0.0};
+                    xh[r] = {x[r], X(ci, r), X(cj, r), 0.0};
+                    xph[r] = {xp[r], Xp(ci, r), Xp(cj, r), 0.0};
                 }
                 double hij = lagrangian_mixed_dt<YK, DT, N>(m, P, xh, xph, em, phi, A.h.weight, d, pl);
                 if (A.hess_flags & CMADX_HESS_F_REFERENCE_QOI_CROSS)
                     hij -= qoi_cross_terms_dt<DT, N>(P.lam, P.mu, xh, em, A.h.weight, d);
-                Hacc[q] += hij;
+                Hacc(q) += hij;
             }
         }
 #pragma unroll
         for (int c = 0; c < N; ++c) xp[c] = x[c];
         for (int c = 0; c < na; ++c)
 #pragma unroll
-            for (int r = 0; r < N; ++r) Xp[c][r] = X[c][r];
+            for (int r = 0; r < N; ++r) Xp(c, r) = X(c, r);
     }
     __shared__ double sm[HESS_BLOCK / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int q = 0; q < npairs; ++q) {
-        double v = live ? Hacc[q] : 0.0;
+        double v = live ? Hacc(q) : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if (lane == 0) sm[warp] = v;
@@ -587,15 +595,28 @@ __global__ void __launch_bounds__(HESS_BLOCK) mp_hess_dt_kernel(const __grid_con
     }
 }
 
+// dynamic shared memory of a block: (2 na n_xi + npairs) doubles per thread
+template <class K>
+cudaError_t launch_hess_kernel(K kernel, const SensArgs& A, int n_xi, unsigned nblk, cudaStream_t stream) {
+    const int na = A.n_active;
+    const size_t smem = sizeof(double) * HESS_BLOCK * (size_t)(2 * na * n_xi + na * (na + 1) / 2);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kernel<<<nblk, HESS_BLOCK, smem, stream>>>(A);
+    return cudaGetLastError();
+}
+
 template <int DT>
 cudaError_t launch_hess_dt(const SensArgs& A, unsigned nblk, cudaStream_t stream) {
+    constexpr int NX = (DT == CMADX_DEF_PLANE_STRESS) ? 8 : 9;
     switch (A.m.yield) {
-    case CMADX_YIELD_J2: mp_hess_dt_kernel<CMADX_YIELD_J2, DT><<<nblk, HESS_BLOCK, 0, stream>>>(A); break;
-    case CMADX_YIELD_HILL: mp_hess_dt_kernel<CMADX_YIELD_HILL, DT><<<nblk, HESS_BLOCK, 0, stream>>>(A); break;
-    case CMADX_YIELD_HOSFORD: mp_hess_dt_kernel<CMADX_YIELD_HOSFORD, DT><<<nblk, HESS_BLOCK, 0, stream>>>(A); break;
+    case CMADX_YIELD_J2: return launch_hess_kernel(mp_hess_dt_kernel<CMADX_YIELD_J2, DT>, A, NX, nblk, stream);
+    case CMADX_YIELD_HILL: return launch_hess_kernel(mp_hess_dt_kernel<CMADX_YIELD_HILL, DT>, A, NX, nblk, stream);
+    case CMADX_YIELD_HOSFORD: return launch_hess_kernel(mp_hess_dt_kernel<CMADX_YIELD_HOSFORD, DT>, A, NX, nblk, stream);
     default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
 }
 
 // upper-triangle pair sums -> full symmetric na x na matrix
@@ -624,12 +645,11 @@ cudaError_t launch_mp_hess(const SensArgs& A, int def_type, double* pair_sums, d
         e = launch_hess_dt<CMADX_DEF_UNIAXIAL_STRESS>(A, (unsigned)nblk, stream);
     } else {
         switch (A.m.yield) {
-        case CMADX_YIELD_J2: mp_hess_kernel<CMADX_YIELD_J2><<<(unsigned)nblk, HESS_BLOCK, 0, stream>>>(A); break;
-        case CMADX_YIELD_HILL: mp_hess_kernel<CMADX_YIELD_HILL><<<(unsigned)nblk, HESS_BLOCK, 0, stream>>>(A); break;
-        case CMADX_YIELD_HOSFORD: mp_hess_kernel<CMADX_YIELD_HOSFORD><<<(unsigned)nblk, HESS_BLOCK, 0, stream>>>(A); break;
+        case CMADX_YIELD_J2: e = launch_hess_kernel(mp_hess_kernel<CMADX_YIELD_J2>, A, 7, (unsigned)nblk, stream); break;
+        case CMADX_YIELD_HILL: e = launch_hess_kernel(mp_hess_kernel<CMADX_YIELD_HILL>, A, 7, (unsigned)nblk, stream); break;
+        case CMADX_YIELD_HOSFORD: e = launch_hess_kernel(mp_hess_kernel<CMADX_YIELD_HOSFORD>, A, 7, (unsigned)nblk, stream); break;
         default: return cudaErrorInvalidValue;
         }
-        e = cudaGetLastError();
     }
     if (e != cudaSuccess) return e;
     e = launch_reduce_partials(A.partials, nblk, npairs, pair_sums, stream);
