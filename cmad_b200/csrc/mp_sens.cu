@@ -328,22 +328,25 @@ mp_sens_kernel(const __grid_constant__ SensArgs A) {
     }
 }
 
-// final reduction of the per-block partials by ONE block in fixed order
-__global__ void __launch_bounds__(256)
+// final reduction of the per-block partials in fixed order: one block per column (the columns
+// are independent), 1024 threads striding over the partials, then a shared-memory tree - the
+// summation order depends only on (nblk, thread count): bit-reproducible.  (The first version
+// used ONE block of 256 threads for all columns: 116 us for the 32 000 partial rows of a 4 M-point
+// FE adjoint step - 15 % of the step.)
+constexpr int REDUCE_THREADS = 1024;
+__global__ void __launch_bounds__(REDUCE_THREADS)
 reduce_partials_kernel(const double* partials, int64_t nblk, int ncols, double* result) {
-    __shared__ double sm[256];
-    for (int c = 0; c < ncols; ++c) {
-        double v = 0.0;
-        for (int64_t b = threadIdx.x; b < nblk; b += 256) v += partials[b * ncols + c];
-        sm[threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 128; o > 0; o >>= 1) {
-            if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) result[c] = sm[0];
+    __shared__ double sm[REDUCE_THREADS];
+    const int c = blockIdx.x;
+    double v = 0.0;
+    for (int64_t b = threadIdx.x; b < nblk; b += REDUCE_THREADS) v += partials[b * ncols + c];
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = REDUCE_THREADS / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
         __syncthreads();
     }
+    if (threadIdx.x == 0) result[c] = sm[0];
 }
 
 template <bool ADJOINT>
@@ -361,7 +364,7 @@ cudaError_t launch_sens_rot(const SensArgs& A, cudaStream_t stream) {
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    reduce_partials_kernel<<<1, 256, 0, stream>>>(A.partials, nblk, 1 + A.n_active, A.h.result);
+    reduce_partials_kernel<<<1 + A.n_active, REDUCE_THREADS, 0, stream>>>(A.partials, nblk, 1 + A.n_active, A.h.result);
     return cudaGetLastError();
 }
 
@@ -379,7 +382,7 @@ cudaError_t launch_sens_t(const SensArgs& A, cudaStream_t stream) {
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    reduce_partials_kernel<<<1, 256, 0, stream>>>(A.partials, nblk, 1 + A.n_active, A.h.result);
+    reduce_partials_kernel<<<1 + A.n_active, REDUCE_THREADS, 0, stream>>>(A.partials, nblk, 1 + A.n_active, A.h.result);
     return cudaGetLastError();
 }
 
@@ -387,7 +390,8 @@ cudaError_t launch_sens_t(const SensArgs& A, cudaStream_t stream) {
 
 cudaError_t launch_reduce_partials(const double* partials, int64_t nblk, int ncols, double* result,
                                    cudaStream_t stream) {
-    reduce_partials_kernel<<<1, 256, 0, stream>>>(partials, nblk, ncols, result);
+    if (ncols <= 0) return cudaSuccess;
+    reduce_partials_kernel<<<ncols, REDUCE_THREADS, 0, stream>>>(partials, nblk, ncols, result);
     return cudaGetLastError();
 }
 
