@@ -73,6 +73,18 @@ class SmallElasticPlastic:
         return material_from_values(self.parameters.values, self.model_name, self.yield_tol)
 
 
+class SmallRateElasticPlastic(SmallElasticPlastic):
+    """Stand-in for the rate form (cmad/models/small_rate_elastic_plastic.py): state =
+    [cauchy(6), alpha], FULL_3D; on the B200 path for the material-point update and the
+    ``cmad primal`` loop (:mod:`cmad_b200.primal`)."""
+    model_name = "small_rate_elastic_plastic"
+
+    def __init__(self, parameters: Parameters, def_type: int = FULL_3D, yield_tol: float = 1e-14, **unsupported):
+        if def_type != FULL_3D:
+            raise NotImplementedError("SmallRateElasticPlastic: FULL_3D only on the B200 path")
+        super().__init__(parameters, FULL_3D, yield_tol, **unsupported)
+
+
 class Calibration:
     """``Calibration(model, data, weight)``: J = sum_t 1/2 ||weight o (cauchy - data[..., t])||^2.
     ``data`` is (3, 3, N+1) for one point or (B, 3, 3, N+1) for a batch."""

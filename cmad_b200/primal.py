@@ -79,8 +79,10 @@ def run_primal_pass(model: SmallElasticPlastic, F: np.ndarray, num_steps: int,
     if qoi is not None:
         data = qoi.data() if not single else qoi.data()[None]
         w = qoi._weight
+    rate = model.model_name == "small_rate_elastic_plastic"     # its kernel takes the strain INCREMENT
     for step in range(1, num_steps + 1):
-        out = mp.mp_update(mat, newton, [], xi, strain[step].contiguous(),
+        e = (strain[step] - strain[step - 1]) if rate else strain[step]
+        out = mp.mp_update(mat, newton, [], xi, e.contiguous(),
                            outputs=("xi", "sigma", "iters", "cnorm"), def_type=dt)
         xi = out["xi"]
         sig = out["sigma"].T.cpu().numpy()[:, _COMP].reshape(B, 3, 3)

@@ -105,3 +105,27 @@ def test_run_primal_pass_def_types_vs_reference(cuda_device, dtn):
     from tests.helpers import UP
     sig6 = np.array([[cauchy[i, j, t] for i, j in UP] for t in range(1, N + 1)])
     assert np.abs(sig6 - DT[f"{case}.sigma"]).max() < 1e-10 * np.abs(DT[f"{case}.sigma"]).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["J2", "hill"])
+def test_run_primal_pass_rate_model_vs_reference(cuda_device, kind):
+    """`cmad primal` with SmallRateElasticPlastic (state = [cauchy, alpha]) against the
+    reference's own imperative run (ref_rate_model.npz): states, stresses, Newton counts."""
+    from cmad_b200 import objectives as ob, primal
+    from tests.golden.materials import const_like, material
+    RT = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_rate_model.npz"))
+    if f"{kind}.F" not in RT.files:
+        pytest.skip("no fixture for this surface")
+    values = material(kind)
+    model = ob.SmallRateElasticPlastic(Parameters(values, const_like(values, False), const_like(values, None)))
+    F = RT[f"{kind}.F"]
+    N = F.shape[2] - 1
+    cauchy, traj, log, _ = primal.run_primal_pass(model, F, N, None, device=cuda_device)
+    assert len(traj[0]) == 2 and traj[0][0].shape == (6,)
+    got = np.array([np.concatenate(t) for t in traj[1:]])
+    assert np.abs(got - RT[f"{kind}.xi"]).max() < 1e-10 * np.abs(RT[f"{kind}.xi"]).max()
+    assert [s["iters"] for s in log] == list(RT[f"{kind}.iters"])
+    from tests.helpers import UP
+    sig6 = np.array([[cauchy[i, j, t] for i, j in UP] for t in range(1, N + 1)])
+    assert np.abs(sig6 - RT[f"{kind}.sigma"]).max() < 1e-10 * np.abs(RT[f"{kind}.sigma"]).max()
