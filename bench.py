@@ -13,6 +13,12 @@ Prints ONE JSON line (rank 0).  ``--impl reference`` instead times the CPU
 restatement of the reference algorithm (oracle/, all host threads) on a bounded
 sample of the same workload - the reference itself is pure Python on JAX, which
 is not installable in this image.
+
+Besides the headline the line carries
+  * ``parity``: the final state of a strided sample of the timed 2^24-point batch compared
+    with the CPU oracle walking the same load steps (the same run that times ``cpu_baseline``);
+  * ``extra.configs``: BASELINE.json configs[2..4] and the path's NCCL collectives, each with
+    its own CUDA-event timing, clocks and roofline fractions (benchmarks/extra_configs.py).
 """
 from __future__ import annotations
 
@@ -63,6 +69,30 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def pin_to_gpu_numa_node(index: int):
+    """Bind this process to the CPU cores NVML reports as local to GPU ``index`` (its NUMA node):
+    the e2e leg's pinned buffers are then first-touched on that node and its copies do not cross
+    the socket interconnect.  Returns a short description (None if NVML cannot do it)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        phys = index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if vis and all(v.strip().isdigit() for v in vis.split(",")):
+            phys = int(vis.split(",")[index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        allowed = os.sched_getaffinity(0)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= allowed
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"cpus": len(cpus), "first": min(cpus), "last": max(cpus)}
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -121,16 +151,18 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
-def cpu_sample_rate(values, params, sample_points: int, steps, nthreads: int = 0):
-    """Oracle (C++ dual-number port of the reference algorithm) on a bounded
-    sample of the same workload; returns (updates/s, threads, description)."""
+def cpu_sample_rate(values, params, sample_points: int, steps, nthreads: int = 0, stride: int = 1,
+                    keep_last: bool = False):
+    """Oracle (C++ dual-number port of the reference algorithm) on a bounded sample of the same
+    workload: points 0, stride, 2 stride, ... walked through ``steps`` with the state carried.
+    Returns (updates/s, threads, description, last-step outputs or None)."""
     from cmad_b200 import synthetic
     from oracle import oracle_c
     prob = oracle_c.describe(values, params.active_idx)
-    d, d2, a = synthetic.path_params(SEED, 0, sample_points)
+    d, d2, a = synthetic.path_params(SEED, 0, sample_points, stride=stride)
     xi = np.zeros((7, sample_points))
     oracle_c.mp_update(prob, xi[:, :256].copy(), synthetic.strain_at_step(d, d2, a, 50)[:, :256].copy())
-    total, updates = 0.0, 0
+    total, updates, r = 0.0, 0, None
     for t in steps:
         e = synthetic.strain_at_step(d, d2, a, t)
         t0 = time.perf_counter()
@@ -139,8 +171,9 @@ def cpu_sample_rate(values, params, sample_points: int, steps, nthreads: int = 0
         updates += sample_points
         xi = r["xi"]
     threads = nthreads if nthreads > 0 else oracle_c.num_threads()
-    return updates / total, threads, (f"first {sample_points} points of the workload, load steps "
-                                      f"{list(steps)} of {HISTORY_STEPS} (state carried), all outputs")
+    which = f"first {sample_points} points" if stride == 1 else f"every {stride}th point ({sample_points} points)"
+    return updates / total, threads, (f"{which} of the workload, load steps {list(steps)} of {HISTORY_STEPS} "
+                                      f"(state carried), all outputs"), (r if keep_last else None)
 
 
 def run_reference(args):
@@ -156,7 +189,7 @@ def run_reference(args):
     # warm-up (untimed) then the timed sample; one "step" = one load step of the sample
     cpu_sample_rate(values, params, min(sample, 4096), ts[:max(1, min(W, 3))])
     nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    rate, threads, desc = cpu_sample_rate(values, params, sample, ts, nthreads=nthreads)   # torchrun pins OMP_NUM_THREADS=1
+    rate, threads, desc, _ = cpu_sample_rate(values, params, sample, ts, nthreads=nthreads)   # torchrun pins OMP_NUM_THREADS=1
     ms = sample / rate * 1e3
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "updates/s",
@@ -186,6 +219,8 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    full_affinity = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa = pin_to_gpu_numa_node(local)      # host threads + pinned buffers next to this rank's GPU
     if world > 1:
         # keep stdout to the ONE JSON line: NCCL prints its version banner there at
         # NCCL_DEBUG=VERSION (the GPU boxes' default); explicit INFO / TRACE requests are kept
@@ -287,13 +322,39 @@ def run_b200(args):
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "per_launch_ms": {"min": float(np.min(per_launch_ms)), "max": float(np.max(per_launch_ms))},
         }
+        line["host"] = {"cpus": os.cpu_count(), "numa_binding": numa}
         if world == 1 and not args.no_cpu_baseline:
+            # the CPU baseline walks a strided sample of THIS batch through the SAME load steps, so
+            # its final state is also the parity check of the timed 2^24-point run
+            if full_affinity:
+                os.sched_setaffinity(0, full_affinity)          # the CPU legs use every core of the box
             nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-            rate, threads, desc = cpu_sample_rate(values, params, args.cpu_sample_points,
-                                                  [10, 30, 50, 70, 90], nthreads=nthreads)
+            stride = max(1, n // max(1, min(args.cpu_sample_points, n)))
+            ns = (n + stride - 1) // stride
+            rate, threads, desc, last = cpu_sample_rate(values, params, ns, ts, nthreads=nthreads,
+                                                        stride=stride, keep_last=True)
             line["cpu_baseline"] = {"value": rate, "unit": "updates/s", "cores": threads,
-                                    "kind": "port", "sample": desc,
-                                    "host_cpus": os.cpu_count()}
+                                    "kind": "port", "sample": desc, "host_cpus": os.cpu_count(),
+                                    "note": "kind 'port' = dual-number AD restatement of the reference "
+                                            "(fidelity oracle, ~6 us/update/core); see cpu_baseline_handderived "
+                                            "for the radial-return routine of the CUDA kernel compiled for the host"}
+            line["parity"] = parity_vs_oracle(final_xi, outs, last, stride)
+            hd = handderived_cpu_rate(values, params, ts, nthreads)
+            if hd is not None:
+                line["cpu_baseline_handderived"] = hd
+    del strains, xi_a, xi_b, outs, out_a, out_b, scratch
+    torch.cuda.empty_cache()
+    if not args.no_extra:
+        from benchmarks import extra_configs as xc
+        ctx = xc.Ctx(dev, rank, world, local, hbm_peak, fp64_peak, ClockSampler, args.extra_steps, W)
+        which = set(args.extra.split(",")) if args.extra else None
+        extra = xc.run_all(ctx, which, log=(lambda m: print(m, file=sys.stderr, flush=True)) if rank == 0 else None)
+        if rank == 0:
+            line["extra"] = {"configs": extra,
+                             "note": "each entry: own CUDA-event timing (max over ranks), clocks, algorithmic "
+                                     "bytes vs the measured HBM peak and ncu-counted FP64 flops vs the measured "
+                                     "DFMA peak; see benchmarks/extra_configs.py"}
+    if rank == 0:
         print(json.dumps(line), file=_json_out(), flush=True)
     if world > 1:
         dist.barrier()
@@ -309,31 +370,92 @@ def run_e2e(args, mat, newton, pid, strains, ts, dev, local, world):
     n = min(args.e2e_points, strains[0].shape[1])
     steps = min(args.e2e_steps, len(strains))
     try:
-        xi_h = torch.zeros((7, n), dtype=torch.float64).pin_memory()
+        xi_h = [torch.zeros((7, n), dtype=torch.float64).pin_memory() for _ in range(2)]   # state ping-pong
         e_h = [strains[j][:, :n].cpu().pin_memory() for j in range(steps)]
         out_h = mp.allocate_outputs(mat, n, len(pid), OUTPUTS, "cpu", pin=True)
     except RuntimeError as exc:        # not enough pinnable host memory
         return {"value": None, "unit": "updates/s", "error": str(exc)[:120]}
+    out_ab = [dict(out_h, xi=xi_h[1]), dict(out_h, xi=xi_h[0])]
     h2d = (7 + 6) * 8 * n
     d2h = sum(t.numel() * t.element_size() for t in out_h.values())
-    mp.mp_update_host(mat, newton, pid, xi_h, e_h[0], out=out_h, device=local)      # warm-up
-    xi_h.zero_()
+    mp.mp_update_host(mat, newton, pid, xi_h[0], e_h[0], out=out_ab[0], device=local)      # warm-up
+    xi_h[0].zero_()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for j in range(steps):
-        mp.mp_update_host(mat, newton, pid, xi_h, e_h[j], out=out_h, device=local)
-        xi_h.copy_(out_h["xi"])        # host-side state carry (part of the user's loop)
+        # the state carry is a buffer swap: step j reads xi_h[j % 2] and writes xi_h[(j + 1) % 2]
+        mp.mp_update_host(mat, newton, pid, xi_h[j % 2], e_h[j], out=out_ab[j % 2], device=local)
     dt = time.perf_counter() - t0
     tt = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt.item())
+    # what the host fabric can do: all ranks copy 1 GiB device -> pinned host at the same time
+    ceiling = None
+    try:
+        nb = 1 << 30
+        src = torch.empty(nb, dtype=torch.uint8, device=dev)
+        dst = out_h["dsig_deps"].view(torch.uint8).reshape(-1)[:nb]
+        if dst.numel() == nb:
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+            c0 = time.perf_counter()
+            for _ in range(3):
+                dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            ct = torch.tensor([time.perf_counter() - c0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ct, op=dist.ReduceOp.MAX)
+            ceiling = 3 * nb / float(ct.item()) / 1e9
+        del src
+    except Exception:
+        ceiling = None
+    gbs = (h2d + d2h) * steps / dt / 1e9
     return {"value": world * n * steps / dt, "unit": "updates/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "points_per_gpu": n, "steps": steps,
             "api": "cmadx_mp_update_host (chunked H2D/kernel/D2H pipeline, pinned host buffers, "
-                   "all outputs returned to the host)",
-            "pcie_gbs": (h2d + d2h) * steps / dt / 1e9}
+                   "all outputs returned to the host; state carried by swapping two pinned buffers)",
+            "pcie_gbs": gbs, "pinned_d2h_ceiling_gbs_per_gpu_concurrent": ceiling,
+            "frac_of_d2h_ceiling": (gbs / ceiling) if ceiling else None,
+            "note": "PCIe-bound by construction (13.2 GB per step per GPU): with host buffers the GPU has no "
+                    "margin over a tuned multi-core CPU code; the drop-in keeps buffers on the device "
+                    "(JAX device arrays through the FFI), where `value` applies"}
+
+
+def parity_vs_oracle(final_xi, outs, ref, stride):
+    """GPU state of the timed batch after the last timed step vs the CPU oracle on every
+    ``stride``-th point: xi / cauchy / tangent / dC/dp relative to the largest reference entry,
+    Newton counts and branch flags compared exactly."""
+    idx = slice(0, None, stride)
+    res = {"points": int(ref["xi"].shape[1]), "stride": int(stride), "tolerance": 1e-10}
+    worst = 0.0
+    for k, g in (("xi", final_xi), ("sigma", outs["sigma"]), ("dsig_deps", outs["dsig_deps"]), ("dC_dp", outs["dC_dp"])):
+        gv = g[:, idx].cpu().numpy()
+        err = float(np.abs(gv - ref[k]).max() / max(np.abs(ref[k]).max(), 1e-300))
+        res[f"max_rel_err_{k}"] = err
+        worst = max(worst, err)
+    res["iters_equal"] = bool(np.array_equal(outs["iters"][idx].cpu().numpy(), ref["iters"]))
+    res["flags_equal"] = bool(np.array_equal(outs["flags"][idx].cpu().numpy(), ref["flags"]))
+    res["iters_mismatches"] = int((outs["iters"][idx].cpu().numpy() != ref["iters"]).sum())
+    res["ok"] = bool(worst < 1e-10 and res["iters_equal"] and res["flags_equal"])
+    return res
+
+
+def handderived_cpu_rate(values, params, ts, nthreads):
+    """the J2 radial-return routine of the CUDA kernel (cmad_b200/csrc/j2_radial.cuh
+    + the closed-form outputs) compiled for the host, OpenMP over points - the honest multi-core
+    number next to the AD port.  None when oracle/ does not provide it."""
+    try:
+        from oracle import j2_host
+    except Exception:
+        return None
+    try:
+        return j2_host.bench_rate(values, params, SEED, ts, HISTORY_STEPS, nthreads)
+    except Exception as exc:
+        return {"error": f"{type(exc).__name__}: {exc}"[:200]}
 
 
 _JSON_OUT = None
@@ -366,6 +488,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--cpu-sample-points", type=int, default=1 << 20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra.configs (configs[2..4], collectives)")
+    ap.add_argument("--extra", default="", help="comma-separated subset of the extra configs")
+    ap.add_argument("--extra-steps", type=int, default=10)
     args = ap.parse_args()
     if args.steps < 1:
         raise SystemExit("--steps must be >= 1")

@@ -48,6 +48,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    from cmad_b200.comm import WORLD
+    grp = WORLD if world > 1 else None       # the elements below are this rank's partition
 
     d = args.div
     nodes, conn = fe_mesh.structured_hex_mesh((d * world, d, d), lengths=(float(world), 1.0, 1.0))
@@ -85,7 +87,7 @@ def main():
            "R_elem": torch.empty((n_e, arr.n_basis * 3), dtype=torch.float64, device=dev),
            "K_elem": torch.empty((n_e, arr.n_basis * 3, arr.n_basis * 3), dtype=torch.float64, device=dev)}
     R = torch.empty(arr.n_dofs, dtype=torch.float64, device=dev)
-    halo = fe.InterfaceExchange(arr.elem_eq, arr.n_dofs, extra_eq=arr.elem_eq_p if args.mixed else None) \
+    halo = fe.InterfaceExchange(arr.elem_eq, arr.n_dofs, extra_eq=arr.elem_eq_p if args.mixed else None, group=grp) \
         if args.exchange == "interface" else None
     stab = 1.0 if args.mixed else None
 
@@ -104,9 +106,9 @@ def main():
         if halo is not None:
             halo.reduce(R)                                              # NCCL all-reduce of the interface dofs
         else:
-            fe.reduce_residual(R)                                       # NCCL all-reduce of the whole R
+            fe.reduce_residual(R, grp)                                    # NCCL all-reduce of the whole R
         ev["red"][k].record()
-        pbar, _ = fe.fe_block_vjp(mat, arr, U, xi0, out["xi"], pid, lam, None, stab_mult=stab)   # incl. all-reduce of pbar
+        pbar, _ = fe.fe_block_vjp(mat, arr, U, xi0, out["xi"], pid, lam, None, stab_mult=stab, group=grp)   # incl. all-reduce of pbar
         ev["end"][k].record()
         return pbar
 

@@ -68,6 +68,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--diag-only", action="store_true", help="strain paths with zero shear")
     ap.add_argument("--generic", action="store_true")
+    ap.add_argument("--one-pass", action="store_true", help="one-pass generic kernels instead of the lane-refill kernel")
+    ap.add_argument("--max-iters", type=int, default=10)
+    ap.add_argument("--ls-evals", type=int, default=4)
     args = ap.parse_args()
 
     import torch
@@ -86,7 +89,8 @@ def main():
             "fp64_peak_tflops": mp.fp64_peak_tflops()}
 
     if args.what == "k1":
-        nw = NewtonSettings(force_generic=args.generic)
+        nw = NewtonSettings(force_generic=args.generic, one_pass=args.one_pass, max_iters=args.max_iters,
+                            ls_max_evals=args.ls_evals)
         outs = ("xi", "sigma", "dsig_deps", "dC_dp", "iters", "flags")
         xi = torch.zeros((7, n), dtype=torch.float64, device=dev)
         for t in (20, 40):                                   # carry the state into the plastic range
@@ -97,7 +101,9 @@ def main():
         ms, ms_min = timed(lambda: mp.mp_update(mat, nw, pid, xi, e, outputs=outs, out=out), args.steps, args.warmup)
         b = 784
         print(json.dumps({**base, "kernel": "K1 mp_update (xi, sigma, tangent, dC/dp)",
-                          "solver": "generic" if (args.generic or args.kind != "J2") else "j2-radial",
+                          "solver": ("generic" if (args.generic or args.kind != "J2") else "j2-radial")
+                          + ("" if (args.kind == "J2" and not args.generic) else (" one-pass" if args.one_pass else " lane-refill")),
+                          "newton": [args.max_iters, args.ls_evals],
                           "ms_per_step": ms, "ms_min": ms_min, "updates_per_s": n / ms * 1e3,
                           "alg_bytes_per_update": b, "achieved_gbs": n * b / ms / 1e6, "frac_hbm": n * b / ms / 1e6 / hbm,
                           "plastic_fraction": float(((out["flags"] & 2) != 0).double().mean()),

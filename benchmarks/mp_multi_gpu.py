@@ -120,7 +120,8 @@ def main():
         L.check(lib.cmadx_mp_objective_adjoint(C.byref(mat), pidp, na, C.byref(h), stream), "adj")
         return result.clone()
 
-    obj = BatchedMPObjective(P, local)
+    from cmad_b200.comm import WORLD
+    obj = BatchedMPObjective(P, local, group=WORLD if world > 1 else None)   # points are sharded by rank
     x0 = P.flat_active_values(True)
     res = {}
 

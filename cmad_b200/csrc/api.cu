@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -270,18 +271,27 @@ static int launch(const MpArgs& A, cudaStream_t s) {
     } else if (A.m.yield == CMADX_YIELD_J2 && !A.m.rot && !A.b.xi_init &&
                !(A.nw.flags & CMADX_NEWTON_F_GENERIC) && A.b.n < (int64_t)0x7fffffff) {
         // J2 radial-return kernel, then the generic kernel over whatever it handed back
+        // the list is sized to the batch: it cannot overflow, so the list kernels never take
+        // their "redo everything" branch (which would double-count atomics and break aliasing)
         BailScratch bs;
-        if (int rc = get_bail_scratch(s, &bs)) return rc;
+        if (int rc = get_bail_scratch(s, &bs, (unsigned)A.b.n)) return rc;
         MpArgs B = A;
         B.bail_count = bs.count;
         B.bail_list = reinterpret_cast<int*>(bs.count + 64);
-        B.bail_cap = BAIL_CAP;
+        B.bail_cap = bs.cap;
         e = cudaMemsetAsync(bs.count, 0, sizeof(unsigned), s);
         if (e != cudaSuccess) return cuda_fail(e);
         e = launch_mp_update_j2(B, s);
         if (e != cudaSuccess) return cuda_fail(e);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         e = launch_mp_update_sep_list(B, s);
+    } else if (!(A.nw.flags & CMADX_NEWTON_F_ONE_PASS) && mp_update_stream_supported(A)) {
+        // generic Newton with lane refill: a persistent grid takes chunks of points from a counter
+        BailScratch bs;
+        if (int rc = get_bail_scratch(s, &bs)) return rc;
+        e = cudaMemsetAsync(bs.count + 1, 0, sizeof(unsigned), s);
+        if (e != cudaSuccess) return cuda_fail(e);
+        e = launch_mp_update_stream(A, bs.count + 1, s);
     } else if (A.nw.defer_request > 0 && A.nw.max_iters > A.nw.defer_request &&
                A.b.n < (int64_t)0x7fffffff) {
         // generic Newton in two passes: points that need more than defer_request updates are
@@ -315,14 +325,22 @@ struct HostScratch {
     cudaStream_t st[SLOTS] = {nullptr, nullptr, nullptr};
     void* dev[SLOTS] = {nullptr, nullptr, nullptr};
     size_t bytes = 0;
+    std::mutex mu;     // held for one host-buffer call on this device; other devices run concurrently
 };
-std::mutex g_hs_mutex;
-std::vector<HostScratch> g_hs;
+std::mutex g_hs_mutex;                              // guards the table only
+std::vector<std::unique_ptr<HostScratch>> g_hs;
 
-HostScratch* get_scratch(int device, size_t bytes, int* rc) {
-    HostScratch* h = nullptr;
-    for (auto& s : g_hs) if (s.device == device) h = &s;
-    if (!h) { g_hs.emplace_back(); h = &g_hs.back(); h->device = device; }
+// the scratch of `device` (created on first use); the caller locks h->mu around its use
+HostScratch* find_scratch(int device) {
+    std::lock_guard<std::mutex> lock(g_hs_mutex);
+    for (auto& s : g_hs) if (s->device == device) return s.get();
+    g_hs.emplace_back(new HostScratch());
+    g_hs.back()->device = device;
+    return g_hs.back().get();
+}
+
+// h->mu must be held
+HostScratch* get_scratch(HostScratch* h, size_t bytes, int* rc) {
     cudaError_t e;
     for (int k = 0; k < HostScratch::SLOTS; ++k) {
         if (!h->st[k]) {
@@ -400,6 +418,23 @@ int64_t cmadx_debug_bail_count(void* stream) {
     return (int64_t)v;
 }
 
+int cmadx_debug_device_structs(const cmadx_material_t* mat, const cmadx_newton_t* newton,
+                               void* dev_mat, void* dev_newton, int64_t* sizes) {
+    if (sizes) { sizes[0] = sizeof(DevMat); sizes[1] = sizeof(DevNewton); }
+    DevMat m;
+    DevNewton nw;
+    if (dev_mat) {
+        if (int rc = make_dev_mat(mat, &m)) return rc;
+        std::memcpy(dev_mat, &m, sizeof m);
+    }
+    if (dev_newton) {
+        if (int rc = make_dev_newton(newton, &nw)) return rc;
+        nw.defer_request = 0;
+        std::memcpy(dev_newton, &nw, sizeof nw);
+    }
+    return CMADX_OK;
+}
+
 int cmadx_lame(const cmadx_material_t* mat, double* out6) {
     if (!mat || !out6) return CMADX_EINVAL;
     DevMat m;
@@ -430,7 +465,14 @@ int cmadx_mp_update_host(const cmadx_material_t* mat, const cmadx_newton_t* newt
     if (chunk > n) chunk = n;
     chunk = (chunk + 31) / 32 * 32;
 
-    cudaError_t e = cudaSetDevice(device);
+    // run on `device`, then hand the caller's current device back (a PyTorch host thread owns it)
+    struct DeviceGuard {
+        int prev = -1;
+        ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    } guard;
+    cudaError_t e = cudaGetDevice(&guard.prev);
+    if (e != cudaSuccess) { guard.prev = -1; return cuda_fail(e); }
+    e = cudaSetDevice(device);
     if (e != cudaSuccess) return cuda_fail(e);
 
     // slot layout: every array [comps][chunk]
@@ -460,9 +502,9 @@ int cmadx_mp_update_host(const cmadx_material_t* mat, const cmadx_newton_t* newt
     add(nullptr, host->C, nxi, 8);
 
     int rc = CMADX_OK;
-    std::lock_guard<std::mutex> lock(g_hs_mutex);
-    HostScratch* hs = get_scratch(device, off, &rc);
-    if (!hs) return rc;
+    HostScratch* hs = find_scratch(device);
+    std::lock_guard<std::mutex> lock(hs->mu);       // per device: two host threads driving two GPUs overlap
+    if (!get_scratch(hs, off, &rc)) return rc;
 
     const int64_t nchunks = (n + chunk - 1) / chunk;
     for (int64_t c = 0; c < nchunks; ++c) {
@@ -715,11 +757,13 @@ static int fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* 
                         !(A.nw.flags & CMADX_NEWTON_F_GENERIC);
     if (!default_rule) A.nw.defer_request = 0;       // one pass of the generic-rule kernel
     if (radial) {
+        // sized to the block: no overflow, hence no second pass over elements whose first pass
+        // already added R_e into R_global
         BailScratch bs;
-        if (int rc = get_bail_scratch(s, &bs)) return rc;
+        if (int rc = get_bail_scratch(s, &bs, (unsigned)b.n_elems)) return rc;
         A.bail_count = bs.count;
         A.bail_list = reinterpret_cast<int*>(bs.count + 64);
-        A.bail_cap = BAIL_CAP;
+        A.bail_cap = bs.cap;
         e = cudaMemsetAsync(bs.count, 0, sizeof(unsigned), s);
         if (e != cudaSuccess) return cuda_fail(e);
         e = launch_fe_block(A, true, s);
@@ -945,10 +989,11 @@ int cmadx_fe_block_vjp_disp(const cmadx_material_t* mat, const cmadx_fe_block_t*
 int cmadx_release_host_scratch(void) {
     std::lock_guard<std::mutex> lock(g_hs_mutex);
     for (auto& h : g_hs) {
-        cudaSetDevice(h.device);
+        std::lock_guard<std::mutex> busy(h->mu);
+        cudaSetDevice(h->device);
         for (int k = 0; k < HostScratch::SLOTS; ++k) {
-            if (h.dev[k]) cudaFree(h.dev[k]);
-            if (h.st[k]) cudaStreamDestroy(h.st[k]);
+            if (h->dev[k]) cudaFree(h->dev[k]);
+            if (h->st[k]) cudaStreamDestroy(h->st[k]);
         }
     }
     g_hs.clear();

@@ -28,6 +28,10 @@ cudaError_t launch_mp_update_sep(const MpArgs& A, cudaStream_t stream);
 cudaError_t launch_mp_update_j2(const MpArgs& A, cudaStream_t stream);
 // generic kernel over the bail list (small persistent grid)
 cudaError_t launch_mp_update_sep_list(const MpArgs& A, cudaStream_t stream);
+// generic Newton with lane refill (mp_update_stream.cu): persistent grid, points handed out in
+// chunks from `counter` (one zeroed unsigned in device memory)
+bool mp_update_stream_supported(const MpArgs& A);
+cudaError_t launch_mp_update_stream(const MpArgs& A, unsigned* counter, cudaStream_t stream);
 cudaError_t launch_mp_update_elastic(const MpArgs& A, cudaStream_t stream);
 // SmallRateElasticPlastic (rate form; `strain` = strain increment)
 cudaError_t launch_mp_update_rate(const MpArgs& A, cudaStream_t stream);

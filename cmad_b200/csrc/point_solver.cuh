@@ -596,162 +596,174 @@ CMADX_DEV void list_append(bool want, unsigned* count, int* list, unsigned cap, 
     }
 }
 
-// Local Newton for one point; `live` lanes take part, the loop exit is decided
-// warp-wide by ballot so the whole warp leaves together.  On return x is the
-// solution, C the residual there, and pt holds the state (n, f, plastic, yield
-// internals) at x.
-// Pt provides residual(m, x, xp, em, C), jacobian(m, dgamma, J) and `plastic`.
+// Local Newton of one point as a resumable per-lane state machine.
 //
-// Both Newton flavours are written as ONE loop around a SINGLE residual call
+// Both Newton flavours are written as ONE routine around a SINGLE residual call
 // site, driven by a per-lane phase: the residual (with its pow / exp / sqrt) is
 // by far the largest piece of code, and five inlined copies of it made the
 // kernels instruction-cache bound (ncu: 26 % of the stalls "no instruction").
-// Lanes in different phases now also share the evaluation instead of serialising.
-// The sequence of evaluations, tests and updates of every lane is exactly that of
-// the reference loops (nonlinear_solver.py:102-155 and :14-85, line_search.py:125-181).
+// Lanes in different phases share the evaluation instead of serialising.
+// `trip()` = one residual evaluation plus everything the reference does between
+// that evaluation and the next one; the sequence of evaluations, tests and
+// updates of a lane is exactly that of the reference loops
+// (nonlinear_solver.py:102-155 and :14-85, line_search.py:125-181).
+// Two drivers use it: local_newton() below (a warp iterates until its slowest
+// lane is done) and the streaming kernel (mp_update_stream.cu), where a lane
+// that finishes takes the next point while its neighbours keep iterating.
+//
+// State carried between trips is kept minimal (it is what a lane holds in
+// registers while its neighbours work): the iterate x, the Newton direction dx
+// and six scalars.  In particular
+//   * the trial point is recomputed as x - al dx instead of being stored;
+//   * the residual at x is never stored: every trip that needs it has just
+//     evaluated it (a line search that runs out of probes moves x to its best
+//     probe and RE-EVALUATES there - the reference's best_aux, bit for bit, since
+//     the same routine sees the same arguments - which is also the evaluation that
+//     makes the yield-surface state fresh at x for the next Jacobian);
+//   * phi0, phi0' and the Armijo slope are functions of C.C alone.
+// The one visible difference to the reference: if NO probe of a line search is
+// finite, the reference continues with the stale residual of the previous
+// iterate at a non-finite x; here the residual is the (non-finite) one at x.
+// Either way the point runs to max_iters and returns a non-finite state.
+// Pt provides residual(m, x, xp, em, C), jacobian(m, dgamma, J) and `plastic`.
 template <class Pt, int N>
-CMADX_DEV NewtonResult local_newton(const DevMat& m, const DevNewton& nw, Pt& pt,
-                                    double (&x)[N], const double (&xp)[N],
-                                    const double (&em)[6], bool live, double (&C)[N]) {
-    NewtonResult r;
-    r.flag_entry = 0;
-    r.deferred = false;
-    const bool traced = (nw.mode == CMADX_NEWTON_TRACED);
-    enum { PH_INIT = 0, PH_PROBE = 1, PH_REFRESH = 2, PH_IMP = 3, PH_FINAL = 4 };
-    int phase = PH_INIT;
-    bool active = true;          // this lane wants the next residual evaluation
-    double xt[N];                // where it wants it
+struct NewtonLane {
+    enum { PH_INIT = 0, PH_PROBE = 1, PH_EVAL = 2 };
+    double x[N];                 // current iterate
+    double dx[N];                // Newton direction of the running line search / last step
+    double n0, nc;               // ||C|| at x0 and at the last convergence test
+    double al, best_al, best_phi, CC;   // line search: trial step, best so far, C.C at x
+    int phase, ii, ne, flag_entry;
+    bool active;                 // this lane wants another residual evaluation
+    bool deferred;               // stopped by DevNewton::defer_after before converging
+
+    CMADX_DEV void start(const double (&x0)[N]) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) xt[i] = x[i];
-    double n0 = 0.0, nc = 0.0;
-    int ii = 0;
-    // line-search state (traced flavour)
-    double dx[N], best_C[N];
-    double al = 1.0, best_al = 1.0, best_phi = CUDART_INF, phi0 = 0.0, dphi0 = 0.0, armijo = 0.0;
-    int ne = 0;
+        for (int i = 0; i < N; ++i) { x[i] = x0[i]; dx[i] = 0.0; }
+        n0 = 0.0; nc = 0.0;
+        al = 1.0; best_al = 1.0; best_phi = CUDART_INF; CC = 0.0;
+        phase = PH_INIT; ii = 0; ne = 0; flag_entry = 0;
+        active = true; deferred = false;
+    }
+
+    // One evaluation.  `Ct` returns the residual just evaluated; when the lane finishes in this
+    // trip (`active` turns false) it is the residual at the returned x and `pt` is fresh there.
+    // `live == false`: evaluate the entry state only (padding lanes of the one-pass kernels).
+    CMADX_DEV void trip(const DevMat& m, const DevNewton& nw, Pt& pt, const double (&xp)[N],
+                        const double (&em)[6], bool live, double (&Ct)[N]) {
+        const bool traced = (nw.mode == CMADX_NEWTON_TRACED);
+        {
+            double xt[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) { dx[i] = 0.0; best_C[i] = 0.0; C[i] = 0.0; }
-    const unsigned full = 0xffffffffu;
-    while (__any_sync(full, active)) {
-        if (active) {
-            double Ct[N];
-            pt.residual(m, xt, xp, em, Ct);                    // the only call site
-            bool need_dir = false;   // (x, C) current and pt fresh at x: take a Newton step
-            bool stepped = false;    // traced: a line search just ended, x / C updated
-            bool fresh = true;       // pt corresponds to x
-            if (phase == PH_INIT) {
-                r.flag_entry = pt.plastic ? 1 : 0;
-#pragma unroll
-                for (int i = 0; i < N; ++i) C[i] = Ct[i];
-                n0 = normN<N>(C);
-                nc = n0;
-                if (!live || nw.max_iters <= 0) {
-                    active = false;
-                } else {
-                    const double rel = traced ? nc / n0 : 1.0;   // 0/0 -> NaN: test is false
-                    if (rel < nw.rel_tol || nc < nw.abs_tol) active = false; else need_dir = true;
-                }
-            } else if (phase == PH_PROBE) {
+            for (int i = 0; i < N; ++i) xt[i] = (phase == PH_PROBE) ? fma(-al, dx[i], x[i]) : x[i];
+            pt.residual(m, xt, xp, em, Ct);                // the only call site
+        }
+        bool need_dir = false;   // (x, Ct) current and pt fresh at x: take a Newton step
+        if (phase == PH_INIT) {
+            flag_entry = pt.plastic ? 1 : 0;
+            n0 = normN<N>(Ct);
+            nc = n0;
+            if (!live || nw.max_iters <= 0) {
+                active = false;
+            } else {
+                const double rel = traced ? nc / n0 : 1.0;   // 0/0 -> NaN: test is false
+                if (rel < nw.rel_tol || nc < nw.abs_tol) active = false; else need_dir = true;
+            }
+        } else {
+            bool test = (phase == PH_EVAL);                  // x is where Ct was evaluated
+            if (phase == PH_PROBE) {
                 // ---- line search (quadratic model), line_search.py:125-181
+                const double phi0 = 0.5 * CC, dphi0 = -CC, armijo = nw.c1 * dphi0;
                 const double ph = 0.5 * dotN<N>(Ct, Ct);
                 const bool fin = isfinite(ph);
-                if (fin && ph < best_phi) {
-                    best_al = al; best_phi = ph;
-#pragma unroll
-                    for (int i = 0; i < N; ++i) best_C[i] = Ct[i];
-                }
+                if (fin && ph < best_phi) { best_al = al; best_phi = ph; }
                 const bool acc = fin && (ph <= fma(al, armijo, phi0));
                 const double den = 2.0 * (ph - phi0 - dphi0 * al);
                 const double am = (den == 0.0) ? 0.5 * al : -dphi0 * al * al / den;
                 double ac = fmin(fmax(am, nw.bmin * al), nw.bmax * al);
                 if (am != am) ac = am;                    // clip propagates NaN
-                const double al_used = al;
-                if (!acc) al = fin ? ac : 0.5 * al;
                 ++ne;
-                if (ne < nw.ls_max && !acc) {
+                if (acc) {
 #pragma unroll
-                    for (int i = 0; i < N; ++i) xt[i] = fma(-al, dx[i], x[i]);
-                } else {
-                    const double ar = acc ? al_used : best_al;
-#pragma unroll
-                    for (int i = 0; i < N; ++i) {
-                        x[i] = fma(-ar, dx[i], x[i]);
-                        C[i] = acc ? Ct[i] : best_C[i];
-                    }
-                    fresh = acc;      // the last evaluated trial is x only if it was accepted
+                    for (int i = 0; i < N; ++i) x[i] = fma(-al, dx[i], x[i]);
                     ++ii;
-                    stepped = true;
+                    test = true;                          // the accepted probe is the new (x, C)
+                } else if (ne < nw.ls_max) {
+                    al = fin ? ac : 0.5 * al;             // next probe
+                } else {
+                    // out of probes: the lowest-merit step; its residual (the reference's best_aux)
+                    // and the yield-surface state at it come from re-evaluating there
+#pragma unroll
+                    for (int i = 0; i < N; ++i) x[i] = fma(-best_al, dx[i], x[i]);
+                    ++ii;
+                    phase = PH_EVAL;
                 }
-            } else if (phase == PH_REFRESH) {
-                need_dir = true;      // pt is fresh at x again; Ct (== C) is not needed
-            } else if (phase == PH_IMP) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) C[i] = Ct[i];
-                nc = normN<N>(C);
-                const double rel = nc / n0;
-                if (rel < nw.rel_tol || nc < nw.abs_tol) active = false; else need_dir = true;
-            } else {                  // PH_FINAL: state refreshed at the returned x
-#pragma unroll
-                for (int i = 0; i < N; ++i) C[i] = Ct[i];
-                active = false;
             }
-            if (stepped) {
-                bool stop = ii >= nw.max_iters;
+            if (test) {
+                const bool by_iters = ii >= nw.max_iters;
+                // imperative flavour at max_iters: newton_solve returns the norm of its last test
+                if (traced || !by_iters) nc = normN<N>(Ct);
+                bool stop = by_iters;
                 if (!stop) {
-                    nc = normN<N>(C);
                     const double rel = nc / n0;
                     stop = (rel < nw.rel_tol || nc < nw.abs_tol);
                 }
-                if (stop) {
-                    if (fresh) active = false;
-                    else phase = PH_FINAL;
-                } else if (fresh) {
-                    need_dir = true;
-                } else {
-                    phase = PH_REFRESH;
-                }
-                if (!fresh) {
-#pragma unroll
-                    for (int i = 0; i < N; ++i) xt[i] = x[i];
-                }
+                if (stop) active = false; else need_dir = true;
             }
-            // Warp-divergence control: the Newton counts of a batch are multi-modal (elastic: 0,
-            // easy plastic: 2, near-Tresca surfaces: 5-10 and more), and a warp runs as long as its
-            // slowest lane.  A lane that still needs a direction after `defer_after` updates stops
-            // here; the kernel appends it to a list and a second pass re-solves those points from
-            // scratch in warps made of hard points only (same code, same iterates, same result).
-            if (need_dir && nw.defer_after > 0 && ii >= nw.defer_after) {
-                need_dir = false;
-                active = false;
-                r.deferred = true;
-            }
-            if (need_dir) {
-                if (traced) {
+        }
+        // Two-pass divergence control of the one-pass kernels: a lane that still needs a
+        // direction after `defer_after` updates stops here; the kernel appends it to a list and
+        // a second pass re-solves those points in warps made of hard points only.
+        if (need_dir && nw.defer_after > 0 && ii >= nw.defer_after) {
+            need_dir = false;
+            active = false;
+            deferred = true;
+        }
+        if (need_dir) {
+            if (traced) {
 #pragma unroll
-                    for (int i = 0; i < N; ++i) dx[i] = C[i];
-                    newton_direction<Pt, N>(m, pt, x[Pt::ALPHA] - xp[Pt::ALPHA], dx);   // solve(J, C)
-                    const double CC = dotN<N>(C, C);
-                    phi0 = 0.5 * CC; dphi0 = -CC; armijo = nw.c1 * dphi0;
-                    ne = 0; al = 1.0; best_al = 1.0; best_phi = CUDART_INF;
+                for (int i = 0; i < N; ++i) dx[i] = Ct[i];
+                newton_direction<Pt, N>(m, pt, x[Pt::ALPHA] - xp[Pt::ALPHA], dx);   // solve(J, C)
+                CC = dotN<N>(Ct, Ct);
+                ne = 0; al = 1.0; best_al = 1.0; best_phi = CUDART_INF;
+                phase = PH_PROBE;
+            } else {
+                // imperative newton_solve (no line search)
 #pragma unroll
-                    for (int i = 0; i < N; ++i) { best_C[i] = C[i]; xt[i] = fma(-al, dx[i], x[i]); }
-                    phase = PH_PROBE;
-                } else {
-                    // imperative newton_solve (no line search)
+                for (int i = 0; i < N; ++i) dx[i] = -Ct[i];
+                newton_direction<Pt, N>(m, pt, x[Pt::ALPHA] - xp[Pt::ALPHA], dx);   // solve(J, -C)
 #pragma unroll
-                    for (int i = 0; i < N; ++i) dx[i] = -C[i];
-                    newton_direction<Pt, N>(m, pt, x[Pt::ALPHA] - xp[Pt::ALPHA], dx);   // solve(J, -C)
-#pragma unroll
-                    for (int i = 0; i < N; ++i) { x[i] += dx[i]; xt[i] = x[i]; }
-                    ++ii;
-                    phase = (ii >= nw.max_iters) ? PH_FINAL : PH_IMP;
-                }
+                for (int i = 0; i < N; ++i) x[i] += dx[i];
+                ++ii;
+                phase = PH_EVAL;
             }
         }
     }
-    if (traced) nc = normN<N>(C);
-    r.iters = ii;
-    r.cnorm = nc;
+};
+
+// Local Newton for one point; `live` lanes take part, the loop exit is decided
+// warp-wide by ballot so the whole warp leaves together.  On return x is the
+// solution, C the residual there, and pt holds the state (n, f, plastic, yield
+// internals) at x.
+template <class Pt, int N>
+CMADX_DEV NewtonResult local_newton(const DevMat& m, const DevNewton& nw, Pt& pt,
+                                    double (&x)[N], const double (&xp)[N],
+                                    const double (&em)[6], bool live, double (&C)[N]) {
+    NewtonLane<Pt, N> L;
+    L.start(x);
+#pragma unroll
+    for (int i = 0; i < N; ++i) C[i] = 0.0;
+    const unsigned full = 0xffffffffu;
+    while (__any_sync(full, L.active)) {
+        if (L.active) L.trip(m, nw, pt, xp, em, live, C);   // the finishing trip leaves C at x
+    }
+    NewtonResult r;
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = L.x[i];
+    r.flag_entry = L.flag_entry;
+    r.deferred = L.deferred;
+    r.iters = L.ii;
+    r.cnorm = L.nc;
     return r;
 }
 

@@ -20,6 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from .comm import all_reduce_sum, resolve as comm_resolve
 from .fe_mesh import FEBlockArrays
 from .material import NewtonSettings
 
@@ -406,8 +407,9 @@ def fe_block_vjp(material: L.Material, arrays: FEBlockArrays, U_global: torch.Te
     """K6 reverse mode: ``(pbar (n_active,), xibar_prev (n_e, n_ip, 7))`` for the cotangents
     ``Rbar (n_dofs,)`` of the assembled residual and ``xibar`` of the converged local
     state - one step of a discrete FE adjoint, the transpose of :func:`fe_block_jvp`.
-    Under ``torch.distributed`` (element partition) ``pbar`` is all-reduced: the gradient
-    exchange of the calibration loop.  ``stab_mult`` (mixed block arrays) selects the mixed
+    With ``group`` given (``comm.WORLD`` or a process group: the elements are this rank's
+    partition) ``pbar`` is all-reduced: the gradient exchange of the calibration loop;
+    ``group=None`` never communicates.  ``stab_mult`` (mixed block arrays) selects the mixed
     u-p formulation: ``Rbar`` covers both residual blocks."""
     mixed = stab_mult is not None
     if mixed and not arrays.mixed:
@@ -442,10 +444,7 @@ def fe_block_vjp(material: L.Material, arrays: FEBlockArrays, U_global: torch.Te
             rc = L.lib().cmadx_fe_block_vjp(
                 C.byref(material), pid.ctypes.data_as(C.POINTER(C.c_int32)), na, C.byref(b), *tail)
     L.check(rc, "cmadx_fe_block_vjp")
-    pbar = pbar[:na]
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(pbar, op=dist.ReduceOp.SUM, group=group)
+    pbar = all_reduce_sum(pbar[:na], group)
     return pbar, out["xi"]
 
 
@@ -502,11 +501,9 @@ def partition_block(arrays: FEBlockArrays, rank: int, world: int) -> tuple[FEBlo
 def reduce_residual(R_local: torch.Tensor, group=None) -> torch.Tensor:
     """The one exchange step of the FE path: sum the per-rank scatter-added residuals
     (shared-node entries get contributions from several ranks).  NCCL over NVLink on
-    GPUs, gloo in the CPU tests; a no-op without an initialised process group."""
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(R_local, op=dist.ReduceOp.SUM, group=group)
-    return R_local
+    GPUs, gloo in the CPU tests; opt-in (``group=comm.WORLD`` or a process group), a no-op
+    with ``group=None``."""
+    return all_reduce_sum(R_local, group)
 
 
 class InterfaceExchange:
@@ -520,8 +517,7 @@ class InterfaceExchange:
 
     def __init__(self, elem_eq: torch.Tensor, n_dofs: int, group=None, extra_eq: torch.Tensor | None = None):
         import torch.distributed as dist
-        self._group = group
-        self._active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self._active, self._group = comm_resolve(group)
         dev = elem_eq.device
         touched = torch.zeros(n_dofs, dtype=torch.int32, device=dev)
         eqs = [elem_eq.reshape(-1).long()] + ([extra_eq.reshape(-1).long()] if extra_eq is not None else [])
@@ -530,7 +526,7 @@ class InterfaceExchange:
         self.mine = touched.bool()
         count = touched.clone()
         if self._active:
-            dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(count, op=dist.ReduceOp.SUM, group=self._group)
         self.index = torch.nonzero(count > 1).reshape(-1)          # same on every rank, sorted
         self.n_interface = int(self.index.numel())
         self._buf = torch.empty(self.n_interface, dtype=torch.float64, device=dev)

@@ -28,6 +28,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from .comm import all_reduce_sum
 from .material import NewtonSettings, active_param_ids, material_from_values
 from .parameters import Parameters
 
@@ -203,6 +204,12 @@ class BatchedMPObjective:
     injection (``set_active_values_from_flat``), the single allreduce, and the
     canonical-coordinate chain rule (``transform_grad``) - exactly the host
     scaffolding of ``MPObjective.evaluate`` (mp_objective.py:53-57, 143-147).
+
+    The all-reduce is opt-in: pass ``group=cmad_b200.comm.WORLD`` (or a process group)
+    when the evaluator's points are this rank's shard (:func:`shard_range`).  With
+    ``group=None`` (the default, and what the reference-signature constructors use)
+    nothing is summed across ranks, whether or not ``torch.distributed`` is initialised:
+    every rank evaluating the same experiment gets that experiment's J, not world_size x J.
     """
 
     def __init__(self, parameters: Parameters, local_evaluator: Callable[[], torch.Tensor],
@@ -217,10 +224,7 @@ class BatchedMPObjective:
         return self._evaluate()
 
     def _evaluate(self) -> GradientResult:
-        import torch.distributed as dist
-        partial = self._local()
-        if self._group is not None or (dist.is_available() and dist.is_initialized()):
-            dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=self._group)
+        partial = all_reduce_sum(self._local(), self._group)
         host = partial.detach().cpu().numpy()
         na = self._parameters.num_active_params
         grad = host[1:1 + na].copy()

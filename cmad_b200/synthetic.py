@@ -51,9 +51,9 @@ def _unit(d: np.ndarray, diag_only: bool) -> np.ndarray:
 
 
 def path_params(seed: int, i0: int, n: int, yield_strain: float = 1e-3,
-                diag_only: bool = False):
-    """(d (6,n), d2 (6,n), a (n)) for points i0 .. i0+n-1."""
-    i = np.arange(i0, i0 + n, dtype=np.uint64)
+                diag_only: bool = False, stride: int = 1):
+    """(d (6,n), d2 (6,n), a (n)) for points i0, i0 + stride, ... (n of them)."""
+    i = np.uint64(i0) + np.arange(n, dtype=np.uint64) * np.uint64(stride)
     d = _unit(normals(seed, i, 0, 6), diag_only)
     d2 = _unit(normals(seed, i, 8, 6), diag_only)
     a = (0.5 + 4.5 * uniform01(seed, i, 16)) * yield_strain

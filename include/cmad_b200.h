@@ -85,7 +85,13 @@ enum {
  * (warp-divergence control; same iterates, counts and flags - derivative outputs may differ at
  * rounding level between the two launches).  0 = library default (K = 2 for near-Tresca Hosford
  * exponents, off otherwise), 255 = off. */
-enum { CMADX_NEWTON_F_GENERIC = 1 };
+enum {
+    CMADX_NEWTON_F_GENERIC = 1,
+    /* material-point batches: use the one-pass generic kernels (one thread = one point, a warp
+     * waits for its slowest lane, optional two-pass deferral) instead of the streaming kernel
+     * with lane refill (mp_update_stream.cu) - A/B comparison; results are identical */
+    CMADX_NEWTON_F_ONE_PASS = 2
+};
 #define CMADX_NEWTON_DEFER_SHIFT 8
 #define CMADX_NEWTON_DEFER_MASK 0xff00
 
@@ -457,6 +463,14 @@ int cmadx_segment_sum(const cmadx_segment_plan_t* plan, const double* vals_dev,
 /* debugging aid: how many points the last J2 radial-return launch on `stream`
  * handed back to the generic kernel (synchronises the stream); -1 if none ran */
 int64_t cmadx_debug_bail_count(void* stream);
+
+/* test / bench support: the kernel-side forms of a material and of the Newton settings (Lame
+ * constants and their derivatives, integer Hosford exponent, line-search constants ...) as
+ * opaque bytes, so that a host build of the per-point routines (the CPU baseline
+ * oracle/j2_host.cpp) runs with exactly the constants the kernels get.  `sizes[2]` receives the
+ * byte sizes; either buffer may be NULL to query them. */
+int cmadx_debug_device_structs(const cmadx_material_t* mat, const cmadx_newton_t* newton,
+                               void* dev_mat, void* dev_newton, int64_t* sizes);
 
 /* number of kernel launches issued by this library since load (all threads) */
 int64_t cmadx_launch_count(void);

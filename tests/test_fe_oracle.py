@@ -139,9 +139,12 @@ def _fe_gloo_worker(rank, world, port, nodes, conn, U, ret):
     local, (lo, hi) = fe.partition_block(arr, rank, world)          # product host logic
     o = fe_oracle.assemble_block(prob, local.elem_eq.numpy(), U, np.zeros((hi - lo, arr.n_ip, 7)),
                                  local.grad_N.numpy(), local.det.numpy(), local.quad_w.numpy())
-    R = fe.reduce_residual(torch.from_numpy(o["R"].copy()))         # product exchange step
+    from cmad_b200.comm import WORLD
+    R = fe.reduce_residual(torch.from_numpy(o["R"].copy()), WORLD)  # product exchange step (opt-in)
+    R_none = fe.reduce_residual(torch.from_numpy(o["R"].copy()))    # group=None: no collective
+    assert np.array_equal(R_none.numpy(), o["R"])
     # halo variant: only the dofs shared between ranks are exchanged
-    halo = fe.InterfaceExchange(local.elem_eq, arr.n_dofs)
+    halo = fe.InterfaceExchange(local.elem_eq, arr.n_dofs, group=WORLD)
     R_halo = halo.reduce(torch.from_numpy(o["R"].copy()))
     ret[rank] = (R.numpy(), lo, hi, o["K_elem"], R_halo.numpy(), halo.mine.numpy(), halo.n_interface)
     dist.destroy_process_group()

@@ -437,3 +437,58 @@ def test_two_pass_deferral_keeps_iterates_and_counts(cuda_device, kind, a):
                 assert torch.equal(out[k], base[k]), (kind, K, k)
             else:
                 assert rel_err(out[k].cpu().numpy(), base[k].cpu().numpy()) < 1e-12, (kind, K, k)
+
+
+# ----------------------------------------------------------------- streaming (lane-refill) kernel
+@pytest.mark.parametrize("case", ["J2", "hill", "hill-rot", "hosford4", "hosford100", "hosford4-rot", "hosford-generic"])
+@pytest.mark.parametrize("mode", ["traced", "imperative"])
+def test_streaming_kernel_equals_one_pass_kernel(cuda_device, case, mode):
+    """The lane-refill kernel (mp_update_stream.cu, the default for generic-Newton batches) hands
+    points to lanes in a different order and computes the outputs in a separate drain step, but every
+    lane runs the same evaluation sequence: state, Newton counts, flags and ||C|| must equal the
+    one-pass kernel's BIT FOR BIT, the derivative outputs to rounding.  Ragged and tiny batches, a
+    padded leading dimension, grad_u (9-row) input and rotated material axes included."""
+    rng = np.random.default_rng(17)
+    kind = case.split("-")[0]
+    rot = rotation_matrix([0.3, -0.5, 0.8], 0.7) if case.endswith("-rot") else None
+    a = {"hosford4": 4.0, "hosford100": 100.0, "hosford": 6.5}.get(kind)
+    hill = (0.45, 0.6, 0.55, 1.4, 1.6, 1.5) if kind == "hill" else None
+    values, act, tr = param_tree("hosford" if a else kind, ("voce", "linear"), hill=hill, a=a, rotation=rot,
+                                 active=("E", "nu", "D", "S", "Y", "K") + (tuple("FGHLMN") if hill else ()))
+    P = Parameters(values, act, tr)
+    mat = material_from_values(values)
+    pid = active_param_ids(P)
+    kw = dict(max_iters=40, abs_tol=1e-12, rel_tol=1e-12, ls_max_evals=8) if kind == "hosford100" else \
+        dict(max_iters=20, abs_tol=1e-12, rel_tol=1e-12)
+    generic = case.endswith("-generic")
+    nws = NewtonSettings(mode=mode, force_generic=True if kind == "J2" or generic else False, **kw)
+    nwo = NewtonSettings(mode=mode, force_generic=True if kind == "J2" or generic else False, one_pass=True,
+                         defer_after=0, **kw)
+    for n, comps, pad in ((1, 6, 0), (31, 6, 0), (33, 9, 3), (4099, 6, 5), (70001, 9, 0)):
+        ld = n + pad
+        xi = torch.zeros((7, ld), dtype=torch.float64, device=cuda_device)
+        e = np.zeros((6, n))
+        for s in range(3):
+            e = e * 1.3 + random_strains(rng, n, scale=1.2e-3 / (1 + s), diag_only=(kind.startswith("hosford") and not rot))
+            if comps == 9:
+                sk = rng.normal(size=(3, n)) * 1e-3
+                g = np.stack([e[0], e[1] + sk[0], e[2] + sk[1], e[1] - sk[0], e[3], e[4] + sk[2],
+                              e[2] - sk[1], e[4] - sk[2], e[5]])
+            else:
+                g = e
+            gd = torch.zeros((comps, ld), dtype=torch.float64, device=cuda_device)
+            gd[:, :n] = torch.from_numpy(g).to(cuda_device)
+            def run(nw):
+                full = mp.allocate_outputs(mat, ld, len(pid), ALL, cuda_device)     # padded leading dimension
+                view = {k: (t[:, :n] if t.dim() == 2 else t[:n]) for k, t in full.items()}
+                return mp.mp_update(mat, nw, pid, xi[:, :n], gd[:, :n], out=view)
+            a_, b_ = run(nws), run(nwo)
+            torch.cuda.synchronize()
+            for k in ("xi", "iters", "flags", "cnorm", "C"):
+                assert torch.equal(a_[k], b_[k]), (case, mode, n, s, k)
+            for k in ("sigma", "dsig_deps", "dxi_deps", "dC_dp", "dC_dxi", "dC_dxi_prev"):
+                ra, rb = a_[k].cpu().numpy(), b_[k].cpu().numpy()
+                assert rel_err(ra, rb) < 1e-12, (case, mode, n, s, k, rel_err(ra, rb))
+            xi = torch.zeros((7, ld), dtype=torch.float64, device=cuda_device)
+            xi[:, :n] = a_["xi"]
+        assert bool((a_["flags"] & 2).any()) or n < 32

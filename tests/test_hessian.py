@@ -208,7 +208,8 @@ def _gloo_hess_worker(rank, world, port, Fs, datas, w, x, ret):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     P = Parameters(*objective_trees("J2", True))
     lo, hi = shard_range(len(Fs), rank, world)
-    res = BatchedMPObjective(P, _hess_local_evaluator(P, Fs[lo:hi], datas[lo:hi], w)).evaluate(x)
+    from cmad_b200.comm import WORLD
+    res = BatchedMPObjective(P, _hess_local_evaluator(P, Fs[lo:hi], datas[lo:hi], w), group=WORLD).evaluate(x)
     if rank == 0:
         ret["J"], ret["grad"], ret["hessian"] = res.J, res.grad, res.hessian
     dist.destroy_process_group()

@@ -84,9 +84,15 @@ def _gloo_worker(rank, world, port, sh, data, w, x, ret):
     P = Parameters(values, act, tr)
     lo, hi = shard_range(sh.shape[2], rank, world)
     ev = _oracle_local_evaluator(P, values, sh[:, :, lo:hi], data[:, :, lo:hi], w, "adjoint")
-    res = BatchedMPObjective(P, ev).evaluate(x)
+    from cmad_b200.comm import WORLD
+    res = BatchedMPObjective(P, ev, group=WORLD).evaluate(x)
+    # an UNSHARDED objective (every rank evaluates the same experiment, as the reference-signature
+    # constructors do) must not be summed over the ranks of an initialised job
+    ev_all = _oracle_local_evaluator(P, values, sh, data, w, "adjoint")
+    res_all = BatchedMPObjective(P, ev_all).evaluate(x)
     if rank == 0:
         ret["J"], ret["grad"] = res.J, res.grad
+        ret["J_unsharded"], ret["grad_unsharded"] = res_all.J, res_all.grad
     dist.destroy_process_group()
 
 
@@ -101,6 +107,7 @@ def test_two_rank_gloo_objective_equals_single_process():
     mp.spawn(_gloo_worker, args=(2, port, sh, data, w, x, ret), nprocs=2, join=True)
     assert abs(ret["J"] - single.J) < 1e-12 * abs(single.J)
     assert np.allclose(ret["grad"], single.grad, rtol=1e-11, atol=0)
+    assert ret["J_unsharded"] == single.J and np.array_equal(ret["grad_unsharded"], single.grad)
     # the canonical chain rule was applied once, after the reduction
     Pn = Parameters(*analytic.j2_voce_param_tree("J2")); Pn.set_active_values_from_flat(x)
     _, g_native, *_ = mo.objective(Pn.values, Pn.active_idx, sh, data, w, "adjoint")
