@@ -147,7 +147,7 @@ def hosford(ctx: Ctx, a: float, log2n: int = 23):
     res = {"name": key, "config": "configs[2]: Hosford plasticity with tangent + dC/dp sensitivities",
            "points_per_gpu": n, "n_gpus": ctx.world, "hosford_a": a, "newton": newton, "scaling": "weak",
            "collective": "none (points are independent)",
-           "kernel": "mp_update_stream_kernel<HOSFORD, reduced 4x4> (lane refill)",
+           "kernel": "mp_update_kernel<HOSFORD, reduced 4x4> (one thread per point; a > 8: two-pass deferral)",
            "ms_per_step": ms, "value": ctx.world * n / ms * 1e3, "unit": "updates/s",
            "launches_per_step": int(launches), "clocks": clocks,
            "plastic_fraction": float(((out["flags"] & 2) != 0).double().mean()),

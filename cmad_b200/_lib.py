@@ -34,6 +34,7 @@ MAX_ACTIVE = 16
 NEWTON_TRACED, NEWTON_IMPERATIVE = 0, 1
 NEWTON_F_GENERIC = 1
 NEWTON_F_ONE_PASS = 2
+NEWTON_F_STREAM = 4
 
 
 class Material(C.Structure):

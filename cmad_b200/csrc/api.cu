@@ -285,7 +285,7 @@ static int launch(const MpArgs& A, cudaStream_t s) {
         if (e != cudaSuccess) return cuda_fail(e);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         e = launch_mp_update_sep_list(B, s);
-    } else if (!(A.nw.flags & CMADX_NEWTON_F_ONE_PASS) && mp_update_stream_supported(A)) {
+    } else if ((A.nw.flags & CMADX_NEWTON_F_STREAM) && mp_update_stream_supported(A)) {
         // generic Newton with lane refill: a persistent grid takes chunks of points from a counter
         BailScratch bs;
         if (int rc = get_bail_scratch(s, &bs)) return rc;

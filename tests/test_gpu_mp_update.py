@@ -443,7 +443,7 @@ def test_two_pass_deferral_keeps_iterates_and_counts(cuda_device, kind, a):
 @pytest.mark.parametrize("case", ["J2", "hill", "hill-rot", "hosford4", "hosford100", "hosford4-rot", "hosford-generic"])
 @pytest.mark.parametrize("mode", ["traced", "imperative"])
 def test_streaming_kernel_equals_one_pass_kernel(cuda_device, case, mode):
-    """The lane-refill kernel (mp_update_stream.cu, the default for generic-Newton batches) hands
+    """The lane-refill kernel (mp_update_stream.cu, opt-in: NewtonSettings(stream=True)) hands
     points to lanes in a different order and computes the outputs in a separate drain step, but every
     lane runs the same evaluation sequence: state, Newton counts, flags and ||C|| must equal the
     one-pass kernel's BIT FOR BIT, the derivative outputs to rounding.  Ragged and tiny batches, a
@@ -461,7 +461,7 @@ def test_streaming_kernel_equals_one_pass_kernel(cuda_device, case, mode):
     kw = dict(max_iters=40, abs_tol=1e-12, rel_tol=1e-12, ls_max_evals=8) if kind == "hosford100" else \
         dict(max_iters=20, abs_tol=1e-12, rel_tol=1e-12)
     generic = case.endswith("-generic")
-    nws = NewtonSettings(mode=mode, force_generic=True if kind == "J2" or generic else False, **kw)
+    nws = NewtonSettings(mode=mode, force_generic=True if kind == "J2" or generic else False, stream=True, **kw)
     nwo = NewtonSettings(mode=mode, force_generic=True if kind == "J2" or generic else False, one_pass=True,
                          defer_after=0, **kw)
     for n, comps, pad in ((1, 6, 0), (31, 6, 0), (33, 9, 3), (4099, 6, 5), (70001, 9, 0)):
@@ -469,7 +469,7 @@ def test_streaming_kernel_equals_one_pass_kernel(cuda_device, case, mode):
         xi = torch.zeros((7, ld), dtype=torch.float64, device=cuda_device)
         e = np.zeros((6, n))
         for s in range(3):
-            e = e * 1.3 + random_strains(rng, n, scale=1.2e-3 / (1 + s), diag_only=(kind.startswith("hosford") and not rot))
+            e = e * 1.3 + random_strains(rng, n, scale=1.2e-3 / (1 + s), diag_only=(kind.startswith("hosford") and rot is None))
             if comps == 9:
                 sk = rng.normal(size=(3, n)) * 1e-3
                 g = np.stack([e[0], e[1] + sk[0], e[2] + sk[1], e[1] - sk[0], e[3], e[4] + sk[2],
