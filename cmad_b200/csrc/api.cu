@@ -285,6 +285,13 @@ static int launch(const MpArgs& A, cudaStream_t s) {
         if (e != cudaSuccess) return cuda_fail(e);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         e = launch_mp_update_sep_list(B, s);
+    } else if ((A.nw.flags & CMADX_NEWTON_F_QUEUE) && mp_update_queue_supported(A)) {
+        // generic Newton with warp-level parking: a persistent grid takes chunks of tiles from a counter
+        BailScratch bs;
+        if (int rc = get_bail_scratch(s, &bs)) return rc;
+        e = cudaMemsetAsync(bs.count + 2, 0, sizeof(unsigned), s);
+        if (e != cudaSuccess) return cuda_fail(e);
+        e = launch_mp_update_queue(A, bs.count + 2, s);
     } else if ((A.nw.flags & CMADX_NEWTON_F_STREAM) && mp_update_stream_supported(A)) {
         // generic Newton with lane refill: a persistent grid takes chunks of points from a counter
         BailScratch bs;

@@ -7,8 +7,15 @@
 
 namespace cmadx {
 
+// streaming store (write-once data, keep L2 for the inputs of the next launch); translation units
+// whose stores are scattered over partially written sectors (mp_update_queue.cu) define
+// CMADX_ST_WRITEBACK so the sectors can be completed in L2 before they are evicted
 CMADX_DEV void st(double* p, int64_t c, int64_t ld, int64_t i, double v) {
+#ifdef CMADX_ST_WRITEBACK
+    p[c * ld + i] = v;
+#else
     __stcs(p + c * ld + i, v);
+#endif
 }
 
 // xi_prev (7) and the symmetric strain (6) of point i

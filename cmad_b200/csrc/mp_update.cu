@@ -20,7 +20,7 @@ namespace {
 
 // REDUCED: Hosford through the 4-unknown HosfordPoint (see point_solver.cuh); needs
 // the starting iterate to be xi_prev (no xi_init)
-template <int YK, bool ROT, bool REDUCED>
+template <int YK, bool ROT, bool REDUCED, bool CTA_SYNC = false>
 CMADX_DEV void process_point(const MpArgs& A, const int64_t i, const bool live, const bool allow_defer) {
     using Pt = typename std::conditional<REDUCED, HosfordPoint, SepPoint<YK>>::type;
     using Tr = typename std::conditional<REDUCED, HosfordTraits, SepPointTraits<YK>>::type;
@@ -59,7 +59,8 @@ CMADX_DEV void process_point(const MpArgs& A, const int64_t i, const bool live, 
     for (int k = 0; k < N; ++k) { y[k] = x[Tr::full(k)]; yp[k] = xp[Tr::full(k)]; }
     DevNewton nw = A.nw;
     nw.defer_after = allow_defer ? A.nw.defer_request : 0;
-    const NewtonResult nr = local_newton<Pt, N>(m, nw, pt, y, yp, em, live, Cy);
+    const NewtonResult nr = local_newton<Pt, N, CTA_SYNC>(m, nw, pt, y, yp, em, live, Cy);
+    if (CTA_SYNC) __syncthreads();     // outputs start together as well
     if (allow_defer && nw.defer_after > 0)    // second pass (list mode) re-solves the deferred points
         list_append(live && nr.deferred, A.bail_count, A.bail_list, A.bail_cap, (int)i);
     if (!live || nr.deferred) return;
@@ -80,6 +81,20 @@ __global__ void __launch_bounds__(MP_BLOCK, REDUCED ? 4 : 1)
 mp_update_kernel(const __grid_constant__ MpArgs A) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     process_point<YK, ROT, REDUCED>(A, i, i < A.b.n, A.bail_count != nullptr);
+}
+
+// lock-step variant of the reduced Hosford kernel: 256-thread blocks whose warps vote the Newton
+// loop together (see local_newton).  Measured on B200 (2^23 points, a = 4, profiles/r2g_k1.jsonl,
+// r2h_k1.jsonl): 2.04 -> 1.80 ms; "no instruction" stalls 2.0 -> 0.2 per issue.  512-thread blocks
+// lose the gain to barrier waits and to every warp hitting memory at the same time; tighter
+// register budgets (5 / 6 blocks of 128, 3 of 256) gain nothing; the 7x7 kernels (8 warps / SM)
+// do not benefit.
+constexpr int LOCKSTEP_BLOCK = 256;
+template <bool ROT>
+__global__ void __launch_bounds__(LOCKSTEP_BLOCK, 2)
+mp_update_hosford_lockstep_kernel(const __grid_constant__ MpArgs A) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    process_point<CMADX_YIELD_HOSFORD, ROT, true, true>(A, i, i < A.b.n, A.bail_count != nullptr);
 }
 
 // list mode: a small grid walks the points the J2 radial kernel handed back
@@ -107,6 +122,12 @@ cudaError_t launch_yk(const MpArgs& A, cudaStream_t stream) {
     if (nblk == 0) return cudaSuccess;
     if (YK == CMADX_YIELD_HOSFORD && !A.b.xi_init && !(A.nw.flags & CMADX_NEWTON_F_GENERIC)) {
         constexpr int H = CMADX_YIELD_HOSFORD;
+        if (!A.bail_count && !(A.nw.flags & CMADX_NEWTON_F_ONE_PASS)) {      // single pass: the lock-step blocks
+            const unsigned nb = (unsigned)((A.b.n + LOCKSTEP_BLOCK - 1) / LOCKSTEP_BLOCK);
+            if (A.m.rot) mp_update_hosford_lockstep_kernel<true><<<nb, LOCKSTEP_BLOCK, 0, stream>>>(A);
+            else mp_update_hosford_lockstep_kernel<false><<<nb, LOCKSTEP_BLOCK, 0, stream>>>(A);
+            return cudaGetLastError();
+        }
         if (A.m.rot) mp_update_kernel<H, true, true><<<(unsigned)nblk, MP_BLOCK, 0, stream>>>(A);
         else mp_update_kernel<H, false, true><<<(unsigned)nblk, MP_BLOCK, 0, stream>>>(A);
         return cudaGetLastError();

@@ -32,6 +32,10 @@ cudaError_t launch_mp_update_sep_list(const MpArgs& A, cudaStream_t stream);
 // chunks from `counter` (one zeroed unsigned in device memory)
 bool mp_update_stream_supported(const MpArgs& A);
 cudaError_t launch_mp_update_stream(const MpArgs& A, unsigned* counter, cudaStream_t stream);
+// generic Newton with warp-level parking of unfinished lanes (mp_update_queue.cu): persistent grid,
+// tiles handed out in chunks from `counter` (one zeroed unsigned in device memory)
+bool mp_update_queue_supported(const MpArgs& A);
+cudaError_t launch_mp_update_queue(const MpArgs& A, unsigned* counter, cudaStream_t stream);
 cudaError_t launch_mp_update_elastic(const MpArgs& A, cudaStream_t stream);
 // SmallRateElasticPlastic (rate form; `strain` = strain increment)
 cudaError_t launch_mp_update_rate(const MpArgs& A, cudaStream_t stream);

@@ -745,7 +745,11 @@ struct NewtonLane {
 // warp-wide by ballot so the whole warp leaves together.  On return x is the
 // solution, C the residual there, and pt holds the state (n, f, plastic, yield
 // internals) at x.
-template <class Pt, int N>
+// CTA_SYNC: the loop exit is voted by the whole thread block (every thread of the block must call):
+// the warps of a block then execute the same stretch of code at the same time, which is what the
+// instruction caches want (the generic kernels are 70-120 KB of straight-line code and were
+// losing a quarter of their issue slots to "no instruction" stalls with unsynchronised warps).
+template <class Pt, int N, bool CTA_SYNC = false>
 CMADX_DEV NewtonResult local_newton(const DevMat& m, const DevNewton& nw, Pt& pt,
                                     double (&x)[N], const double (&xp)[N],
                                     const double (&em)[6], bool live, double (&C)[N]) {
@@ -754,7 +758,7 @@ CMADX_DEV NewtonResult local_newton(const DevMat& m, const DevNewton& nw, Pt& pt
 #pragma unroll
     for (int i = 0; i < N; ++i) C[i] = 0.0;
     const unsigned full = 0xffffffffu;
-    while (__any_sync(full, L.active)) {
+    while (CTA_SYNC ? (__syncthreads_or(L.active ? 1 : 0) != 0) : (__any_sync(full, L.active) != 0)) {
         if (L.active) L.trip(m, nw, pt, xp, em, live, C);   // the finishing trip leaves C at x
     }
     NewtonResult r;

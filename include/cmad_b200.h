@@ -87,14 +87,19 @@ enum {
  * exponents, off otherwise), 255 = off. */
 enum {
     CMADX_NEWTON_F_GENERIC = 1,
-    /* accepted and ignored (the one-pass generic kernels are the default again) */
+    /* reduced Hosford batches: the plain one-thread-per-point kernel (128-thread blocks, warps
+     * unsynchronised) instead of the lock-step blocks - A/B comparison; results are identical */
     CMADX_NEWTON_F_ONE_PASS = 2,
     /* material-point batches: use the streaming kernel with lane refill (mp_update_stream.cu)
      * instead of the one-pass generic kernels (one thread = one point, a warp waits for its
      * slowest lane, optional two-pass deferral).  Results are identical; measured on B200 it is
      * slower (profiles/r2e_k1_ab.jsonl) because the Jacobian / LU still runs partially filled
      * and every point pays one more residual evaluation in the drain - kept for A/B work */
-    CMADX_NEWTON_F_STREAM = 4
+    CMADX_NEWTON_F_STREAM = 4,
+    /* material-point batches: generic kernel with warp-level parking (mp_update_queue.cu): lanes
+     * that still iterate when most of their warp is done are parked in shared memory and resumed
+     * in full warps; results equal the one-pass kernels' bit for bit */
+    CMADX_NEWTON_F_QUEUE = 8
 };
 #define CMADX_NEWTON_DEFER_SHIFT 8
 #define CMADX_NEWTON_DEFER_MASK 0xff00

@@ -7,8 +7,8 @@ import types
 
 from . import _core
 from ._core import (Array, checkpoint, config, custom_jvp, debug, grad, hessian, jacfwd, jacobian,  # noqa: F401
-                    jacrev, jit, jvp, value_and_grad, vmap)
-from . import numpy, lax, tree_util, flatten_util  # noqa: F401,E402
+                    jacrev, jit, jvp, value_and_grad, vmap, ShapeDtypeStruct, pure_callback)
+from . import numpy, lax, tree_util, flatten_util, experimental  # noqa: F401,E402
 
 remat = checkpoint
 __version__ = "0.0-shim"

@@ -234,6 +234,12 @@ class Array:
     def __or__(self, o):
         return Array(_raw(self) | _raw(o))
 
+    def __rand__(self, o):
+        return Array(_raw(o) & _raw(self))
+
+    def __ror__(self, o):
+        return Array(_raw(o) | _raw(self))
+
     def __invert__(self):
         return Array(~_raw(self))
 
@@ -1096,6 +1102,24 @@ def jit(fun=None, **kw):
     if fun is None:
         return lambda f: f
     return fun
+
+
+class ShapeDtypeStruct:
+    def __init__(self, shape, dtype, **kw):
+        self.shape, self.dtype = tuple(shape), dtype
+
+
+def pure_callback(callback, result_shape_dtypes, *args, **kw):
+    """Eager: the host callback sees plain NumPy operands (forward evaluation only)."""
+    kw.pop("vmap_method", None)
+    kw.pop("vectorized", None)
+    res = callback(*[tree_map(lambda l: np.asarray(_raw(l)) if isinstance(l, Array) else l, a) for a in args], **kw)
+    return tree_map(lambda l: asarray(l), res)
+
+
+def custom_linear_solve(matvec, b, solve, transpose_solve=None, symmetric=False, has_aux=False):
+    """Forward evaluation of lax.custom_linear_solve: x = solve(matvec, b)."""
+    return solve(matvec, b)
 
 
 def stop_gradient(x):

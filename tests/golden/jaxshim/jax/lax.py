@@ -1,5 +1,5 @@
 """`jax.lax` stand-in: eager control flow."""
-from ._core import cond, fori_loop, scan, stop_gradient, switch, while_loop  # noqa: F401
+from ._core import cond, custom_linear_solve, fori_loop, scan, stop_gradient, switch, while_loop  # noqa: F401
 
 
 def __getattr__(name):
