@@ -191,6 +191,8 @@ def lib() -> C.CDLL:
                                             C.POINTER(C.c_void_p)]
     L.cmadx_segment_plan_destroy.argtypes = [C.c_void_p]
     L.cmadx_segment_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.cmadx_index_gather.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.cmadx_index_scatter.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 

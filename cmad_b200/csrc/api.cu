@@ -142,6 +142,7 @@ int make_dev_mat(const cmadx_material_t* mat, DevMat* o) {
         o->Y = mat->Y; o->S = mat->voce_S; o->D = mat->voce_D; o->K = mat->linear_K;
         for (int i = 0; i < 6; ++i) o->hill[i] = mat->hill[i];
         o->a = mat->hosford_a;
+        o->inv_a = 1.0 / mat->hosford_a;
         o->a_int = 0;
         if (mat->yield == CMADX_YIELD_HOSFORD && mat->hosford_a >= 1.0 && mat->hosford_a <= 1024.0 &&
             mat->hosford_a == std::floor(mat->hosford_a))
@@ -193,9 +194,15 @@ static int build_args(const cmadx_material_t* mat, const cmadx_newton_t* nw,
     for (int c = 0; c < n_active; ++c) {
         const int pid = active_pid[c];
         if (pid < 0 || pid >= CMADX_NUM_PARAM_IDS) return CMADX_EINVAL;
-        // the closed-form kernels do not differentiate w.r.t. the Hosford
-        // exponent or the rotation matrix entries
-        if (pid == CMADX_P_HOSFORD_A || pid >= CMADX_P_Q00) return CMADX_EUNSUPPORTED;
+        // the Hosford exponent: SmallElasticPlastic / rate model in FULL_3D (the def-type kernels
+        // do not carry it); rotation-matrix entries: FULL_3D SmallElasticPlastic, dC/dp output
+        // of the generic kernels only (see write_point_outputs)
+        if (pid == CMADX_P_HOSFORD_A && b->def_type != CMADX_DEF_FULL_3D) return CMADX_EUNSUPPORTED;
+        if (pid >= CMADX_P_Q00) {
+            if (b->def_type != CMADX_DEF_FULL_3D || A->m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC)
+                return CMADX_EUNSUPPORTED;
+            A->nw.flags |= CMADX_NEWTON_F_GENERIC;       // not the J2 radial / reduced Hosford specialisations
+        }
         A->pid[c] = pid;
     }
     A->n_active = n_active;
@@ -641,7 +648,7 @@ static int objective(const cmadx_material_t* mat, const int32_t* active_pid, int
     for (int c = 0; c < n_active; ++c) {
         const int pid = active_pid[c];
         if (pid < 0 || pid >= CMADX_NUM_PARAM_IDS) return CMADX_EINVAL;
-        if (pid == CMADX_P_HOSFORD_A || pid >= CMADX_P_Q00) return CMADX_EUNSUPPORTED;
+        if (pid >= CMADX_P_Q00) return CMADX_EUNSUPPORTED;
         A.pid[c] = pid;
     }
     A.n_active = n_active;
@@ -886,7 +893,7 @@ static int fe_block_jvp(const cmadx_material_t* mat, const int32_t* active_pid, 
     for (int c = 0; c < n_active; ++c) {
         const int pid = active_pid[c];
         if (pid < 0 || pid >= CMADX_NUM_PARAM_IDS) return CMADX_EINVAL;
-        if (pid == CMADX_P_HOSFORD_A || pid >= CMADX_P_Q00) return CMADX_EUNSUPPORTED;
+        if (pid >= CMADX_P_Q00) return CMADX_EUNSUPPORTED;
         A.pid[c] = pid;
         A.dp[c] = dp_host[c];
         if (pid == CMADX_P_EL0 || pid == CMADX_P_EL1) {
@@ -946,7 +953,7 @@ static int fe_block_vjp(const cmadx_material_t* mat, const int32_t* active_pid, 
     for (int c = 0; c < n_active; ++c) {
         const int pid = active_pid[c];
         if (pid < 0 || pid >= CMADX_NUM_PARAM_IDS) return CMADX_EINVAL;
-        if (pid == CMADX_P_HOSFORD_A || pid >= CMADX_P_Q00) return CMADX_EUNSUPPORTED;
+        if (pid >= CMADX_P_Q00) return CMADX_EUNSUPPORTED;
         A.pid[c] = pid;
     }
     A.n_active = n_active;

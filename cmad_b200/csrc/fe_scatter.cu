@@ -46,6 +46,17 @@ segment_sum_kernel(const int64_t* __restrict__ offsets, const IT* __restrict__ i
     out[s] = acc;
 }
 
+__global__ void index_gather_kernel(const int64_t* __restrict__ index, int64_t n, const double* __restrict__ src,
+                                    double* __restrict__ packed) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) packed[i] = src[index[i]];
+}
+__global__ void index_scatter_kernel(const int64_t* __restrict__ index, int64_t n, const double* __restrict__ packed,
+                                     double* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[index[i]] = packed[i];
+}
+
 }  // namespace
 }  // namespace cmadx
 
@@ -118,6 +129,28 @@ int cmadx_segment_sum(const cmadx_segment_plan_t* p, const double* vals, double*
     else
         segment_sum_kernel<int32_t><<<nblk, 256, 0, s>>>(p->offsets, (const int32_t*)p->items, vals, out,
                                                          p->n_segments, accumulate);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return CMADX_OK;
+}
+
+// Interface pack / unpack of the halo exchange (the element partition's shared dofs): the two
+// index kernels around the NCCL all-reduce, so the step path launches no framework kernels.
+int cmadx_index_gather(const int64_t* index, int64_t n, const double* src, double* packed, void* stream) {
+    if (n < 0 || (n > 0 && (!index || !src || !packed))) return CMADX_EINVAL;
+    if (n == 0) return CMADX_OK;
+    index_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(index, n, src, packed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return CMADX_OK;
+}
+
+int cmadx_index_scatter(const int64_t* index, int64_t n, const double* packed, double* dst, void* stream) {
+    if (n < 0 || (n > 0 && (!index || !packed || !dst))) return CMADX_EINVAL;
+    if (n == 0) return CMADX_OK;
+    index_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(index, n, packed, dst);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e);
     g_launches.fetch_add(1, std::memory_order_relaxed);

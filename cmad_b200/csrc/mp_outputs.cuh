@@ -193,6 +193,40 @@ CMADX_DEV void write_point_outputs(const MpArgs& A, const int64_t i, const doubl
             nee = fma(mult(a) * pt.n[a], ee[a], nee);
         }
         write_dC_dp(A, i, pl, pt.yf, pt.n, pt.f, pt.eD, x[6], dg, Mee, nee, sig);
+        // rotation-matrix leaves (the reference's jacrev treats the 9 entries of Q as independent,
+        // cmad/parameters/parameters.py:368-377): C sees Q only through e_m = Q^T eps Q
+        // (small_elastic_plastic.py:44-62), so dC/dQ_ij = dC/de_m : d e_m/dQ_ij with
+        // d(e_m)_kl/dQ_ij = delta_jk W_il + delta_jl W_ik, W = eps Q (= Q e_m for the orthonormal Q
+        // the reference builds), and dC/de_m = -(dC/dx[:, :6] - [I6; 0]) in material axes.
+        for (int c = 0; c < A.n_active; ++c) {
+            const int q = A.pid[c] - CMADX_P_Q00;
+            if (q < 0) continue;
+            double col[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            if (pl) {
+                const int qi = q / 3, qj = q % 3;
+                const double E3[3][3] = {{em[0], em[1], em[2]}, {em[1], em[3], em[4]}, {em[2], em[4], em[5]}};
+                double W[3];                            // row qi of W = Q e_m
+#pragma unroll
+                for (int l = 0; l < 3; ++l) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) s = fma(m.Q[3 * qi + k], E3[k][l], s);
+                    W[l] = s;
+                }
+                const int ck[6] = {0, 0, 0, 1, 1, 2}, cl[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+                for (int b = 0; b < 6; ++b) {
+                    const double D = ((ck[b] == qj) ? W[cl[b]] : 0.0) + ((cl[b] == qj) ? W[ck[b]] : 0.0);
+#pragma unroll
+                    for (int r = 0; r < 7; ++r) {
+                        const double dCde = ((r == b) ? 1.0 : 0.0) - full_jacobian_entry(m, pt, dg, r, b);
+                        col[r] = fma(dCde, D, col[r]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 7; ++r) st(A.b.dC_dp, (int64_t)r * A.n_active + c, ld, i, col[r]);
+        }
     }
 
     const bool want_ift = A.b.dsig_deps || A.b.dxi_deps;

@@ -28,7 +28,7 @@ struct DevMat {
     double lam, mu, two_mu, inv_two_mu;
     double Y, S, D, K;
     double hill[6];
-    double a;
+    double a, inv_a;          // Hosford exponent and 1 / a (host-computed: the same correctly rounded quotient)
     double Q[9];
     double yield_tol;
     double dlam[2], dmu[2];   // d(lambda, mu)/d(elastic[0..1])
@@ -196,7 +196,7 @@ template <> struct YieldFn<CMADX_YIELD_HOSFORD> {
 #pragma unroll
         for (int i = 0; i < 3; ++i) { q[i] = hosford_pow(fabs(dl[i] * ivm), a, m.a_int); sq += q[i]; }
         sq *= 0.5;
-        phi = vm * pow(sq, 1.0 / a);
+        phi = vm * pow(sq, m.inv_a);
         iphi = 1.0 / phi;
         am1 = a - 1.0;
         const double isq = 1.0 / sq;
@@ -227,8 +227,29 @@ template <> struct YieldFn<CMADX_YIELD_HOSFORD> {
         const int pa = ia, ma = (ia + 2) % 3, pb = ib, mb = (ib + 2) % 3;
         return Gd(pa, pb) - Gd(pa, mb) - Gd(ma, pb) + Gd(ma, mb);
     }
-    CMADX_DEV bool dparam(const DevMat&, int, const double (&)[6], double&, double (&)[6]) const {
-        return false;   // d/d(hosford a) is not provided by the closed-form kernels
+    // d(phi, n)/d(exponent a) at the last evaluated state (cmad/models/effective_stress.py:168-177
+    // differentiated by jacrev over the `a` leaf, cmad/models/model.py:126-133).  With
+    // r_i = |Delta_i| / phi (so 1/2 sum r_i^a = 1) and L = 1/2 sum r_i^a ln r_i:
+    //   d phi / da = phi L / a,    d g_i / da = g_i (ln r_i - (a - 1) L / a),   g_i = 1/2 t_i r_i^(a-1)
+    // (the vm scaling of the reference's formula cancels analytically; terms with r_i = 0 vanish).
+    CMADX_DEV bool dparam(const DevMat& m, int pid, const double (&sig)[6], double& dphi, double (&dn)[6]) const {
+        if (pid != CMADX_P_HOSFORD_A) return false;
+        const double dl[3] = {sig[0] - sig[3], sig[3] - sig[5], sig[5] - sig[0]};
+        double lr[3], L = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double r = fabs(dl[i]) * iphi;
+            lr[i] = (r > 0.0) ? log(r) : 0.0;
+            L = fma(fabs(g[i]) * r, lr[i], L);          // 1/2 r^a ln r = |g| r ln r
+        }
+        const double a = m.a;
+        dphi = L / (a * iphi);
+        double dgi[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) dgi[i] = g[i] * (lr[i] - am1 * L / a);
+        dn[0] = dgi[0] - dgi[2]; dn[3] = dgi[1] - dgi[0]; dn[5] = dgi[2] - dgi[1];
+        dn[1] = 0.0; dn[2] = 0.0; dn[4] = 0.0;
+        return true;
     }
 };
 
@@ -537,7 +558,7 @@ template <int N> CMADX_DEV double normN(const double (&v)[N]) {
     double s = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) s = fma(v[i], v[i], s);
-    return sqrt(s);
+    return (s == 0.0) ? 0.0 : sqrt(s);       // sqrt(0) = 0 without the special-case subroutine (elastic lanes)
 }
 template <int N> CMADX_DEV double dotN(const double (&u)[N], const double (&v)[N]) {
     double s = 0.0;
@@ -666,7 +687,10 @@ struct NewtonLane {
             if (!live || nw.max_iters <= 0) {
                 active = false;
             } else {
-                const double rel = traced ? nc / n0 : 1.0;   // 0/0 -> NaN: test is false
+                // nc == n0 here: n0 / n0 is 1 for finite non-zero n0 and NaN otherwise (0/0, inf/inf:
+                // the test is then false) - spelled out so elastic lanes (n0 = 0) skip the
+                // division's special-case subroutine
+                const double rel = !traced ? 1.0 : ((n0 > 0.0 && n0 < CUDART_INF) ? 1.0 : CUDART_NAN);
                 if (rel < nw.rel_tol || nc < nw.abs_tol) active = false; else need_dir = true;
             }
         } else {

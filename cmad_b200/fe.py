@@ -535,7 +535,16 @@ class InterfaceExchange:
         if not self._active or self.n_interface == 0:
             return R
         import torch.distributed as dist
-        torch.index_select(R, 0, self.index, out=self._buf)
+        if R.is_cuda:       # pack / unpack with the library's own index kernels (no framework kernels on the step path)
+            s = C.c_void_p(torch.cuda.current_stream(R.device).cuda_stream)
+            with torch.cuda.device(R.device):
+                L.check(L.lib().cmadx_index_gather(self.index.data_ptr(), self.n_interface, R.data_ptr(),
+                                                   self._buf.data_ptr(), s), "cmadx_index_gather")
+                dist.all_reduce(self._buf, op=dist.ReduceOp.SUM, group=self._group)
+                L.check(L.lib().cmadx_index_scatter(self.index.data_ptr(), self.n_interface, self._buf.data_ptr(),
+                                                    R.data_ptr(), s), "cmadx_index_scatter")
+            return R
+        torch.index_select(R, 0, self.index, out=self._buf)           # CPU tensors (gloo tests of the host logic)
         dist.all_reduce(self._buf, op=dist.ReduceOp.SUM, group=self._group)
         R.index_copy_(0, self.index, self._buf)
         return R

@@ -469,6 +469,14 @@ int cmadx_segment_plan_destroy(cmadx_segment_plan_t* plan);
 int cmadx_segment_sum(const cmadx_segment_plan_t* plan, const double* vals_dev,
                       double* out_dev, int accumulate, void* stream);
 
+/* Pack / unpack of a sorted dof subset (the interface dofs of an element partition) around the
+ * halo all-reduce of the assembled residual: packed[i] = src[index[i]] / dst[index[i]] = packed[i].
+ * `index` is a device array of n distinct positions.                                        */
+int cmadx_index_gather(const int64_t* index_dev, int64_t n, const double* src_dev, double* packed_dev,
+                       void* stream);
+int cmadx_index_scatter(const int64_t* index_dev, int64_t n, const double* packed_dev, double* dst_dev,
+                        void* stream);
+
 /* debugging aid: how many points the last J2 radial-return launch on `stream`
  * handed back to the generic kernel (synchronises the stream); -1 if none ran */
 int64_t cmadx_debug_bail_count(void* stream);

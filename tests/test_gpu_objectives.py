@@ -19,9 +19,11 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("kind", ["J2", "hill", "hosford"])
 def test_batched_objective_matches_oracle(cuda_device, kind):
     hill = (0.45, 0.6, 0.55, 1.4, 1.6, 1.5) if kind == "hill" else None
-    active = ("E", "nu", "D", "S", "Y") + (tuple("FGHLMN") if kind == "hill" else ())
+    # Hosford: the exponent a is an active parameter too (d/da of |x|^a and of the outer 1/a root)
+    active = ("E", "nu", "D", "S", "Y") + (tuple("FGHLMN") if kind == "hill" else ()) + (("a",) if kind == "hosford" else ())
     values, act, tr = param_tree(kind, ("voce",), hill=hill, active=active)
     P = Parameters(values, act, tr)
+    assert len(P.active_idx) == len(active)
     sh, data, w = _problem(n=3000, N=12, seed=1, kind=kind)
     Jr, gr, Jp, gp, xi_ref, it_ref = mo.objective(values, P.active_idx, sh, data, w, "adjoint")
     model = SmallElasticPlastic(P)

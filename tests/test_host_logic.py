@@ -103,8 +103,13 @@ def test_argument_validation_without_gpu(built_lib):
     assert built_lib.cmadx_mp_update(C.byref(m), C.byref(nw), None, 0, C.byref(b), None) == _lib.EINVAL
     b.ld = 4; b.strain_comps = 7
     assert built_lib.cmadx_mp_update(C.byref(m), C.byref(nw), None, 0, C.byref(b), None) == _lib.EINVAL
-    pid = (C.c_int32 * 1)(_lib.P_HOSFORD_A); b.strain_comps = 6
+    # the Hosford exponent is differentiated in FULL_3D only; rotation-matrix entries not in the def-type kernels
+    pid = (C.c_int32 * 1)(_lib.P_HOSFORD_A); b.strain_comps = 3; b.def_type = _lib.DEF_PLANE_STRESS
     assert built_lib.cmadx_mp_update(C.byref(m), C.byref(nw), pid, 1, C.byref(b), None) == _lib.EUNSUPPORTED
+    pid = (C.c_int32 * 1)(_lib.P_Q00 + 4)
+    assert built_lib.cmadx_mp_update(C.byref(m), C.byref(nw), pid, 1, C.byref(b), None) == _lib.EUNSUPPORTED
+    b.strain_comps = 6; b.def_type = _lib.DEF_FULL_3D
+    assert built_lib.cmadx_mp_update(C.byref(m), C.byref(nw), pid, 1, C.byref(b), None) == _lib.EINVAL   # no buffers
     nw.ls_max_evals = 0
     assert built_lib.cmadx_mp_update(C.byref(m), C.byref(nw), None, 0, C.byref(b), None) == _lib.EINVAL
     b.n = 0; nw.ls_max_evals = 4                                         # empty batch is a no-op

@@ -238,3 +238,59 @@ def test_cuda_objectives_vs_reference(cuda_device, case):
         r = obj.evaluate(OB[f"{case}.x_canonical"])
         assert abs(r.J - OB[f"{case}.J_{strategy}"]) < 1e-11 * abs(r.J)
         assert rel_err(r.grad, OB[f"{case}.grad_{strategy}"]) < 1e-9
+
+
+def _leaf_parameters(kind):
+    """Only the leaves the closed-form kernels did not differentiate in round 1 active: the 9
+    rotation-matrix entries and (Hosford) the exponent a."""
+    values = material(kind)
+    act = const_like(values, False)
+    act["rotation matrix"] = True
+    if kind.startswith("hosford"):
+        act["plastic"]["effective stress"]["hosford"]["a"] = True
+    return values, Parameters(values, act, const_like(values, None))
+
+
+def _check_leaf_columns(case, run_update):
+    kind, key = case.split(".")
+    values, P = _leaf_parameters(kind)
+    aidx = np.asarray(P.active_idx)
+    assert len(aidx) == 9 + (1 if kind.startswith("hosford") else 0)
+    g = {k: TR[f"{case}.{k}"] for k in ("grad_u", "xi_prev", "iters", "flags", "dC_dp")}
+    n_plastic = 0
+    for s in range(g["grad_u"].shape[0]):
+        out = run_update(values, P, _newton_kw(key), g["xi_prev"][s].T.copy(), g["grad_u"][s].T.copy())
+        same = (np.asarray(out["iters"]) == g["iters"][s]) & (np.asarray(out["flags"]) == g["flags"][s])
+        assert same.all(), (case, s)
+        n = same.size
+        ref = g["dC_dp"][s][:, :, aidx]                                  # (n, 7, P_a): the reference's jacrev columns
+        got = np.asarray(out["dC_dp"]).T.reshape(n, 7, len(aidx))
+        assert rel_err(got, ref) < 1e-9, (case, s, rel_err(got, ref))
+        n_plastic += int((g["flags"][s] & 2).astype(bool).sum())
+        assert np.abs(ref).max() > 0 or n_plastic == 0
+    assert n_plastic > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["J2.mp", "hill_rot.fe", "hosford.mp"])
+def test_cuda_dC_dp_rotation_and_exponent_leaves_vs_reference(cuda_device, case):
+    """dC/dp columns of the `rotation matrix` entries and of `hosford a` (the reference's jacrev over
+    ALL leaves, cmad/models/model.py:126-133) from K1, against the reference's own run."""
+    import torch
+    from cmad_b200 import NewtonSettings, active_param_ids, material_from_values, mp
+
+    def run(values, P, kw, xi_prev, grad_u):
+        out = mp.mp_update(material_from_values(values), NewtonSettings(mode="traced", **kw), active_param_ids(P),
+                           torch.from_numpy(xi_prev).to(cuda_device), torch.from_numpy(grad_u).to(cuda_device),
+                           outputs=("xi", "iters", "flags", "dC_dp"))
+        torch.cuda.synchronize()
+        return {k: v.cpu().numpy() for k, v in out.items()}
+    _check_leaf_columns(case, run)
+
+
+@pytest.mark.parametrize("case", ["J2.mp", "hill_rot.fe", "hosford.mp"])
+def test_c_oracle_dC_dp_rotation_and_exponent_leaves_vs_reference(case):
+    def run(values, P, kw, xi_prev, grad_u):
+        prob = oc.describe(values, P.active_idx, newton_mode="traced", strain_comps=9, **kw)
+        return oc.mp_update(prob, xi_prev, grad_u, want=("xi", "iters", "flags", "dC_dp"))
+    _check_leaf_columns(case, run)
