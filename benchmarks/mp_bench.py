@@ -70,6 +70,8 @@ def main():
     ap.add_argument("--generic", action="store_true")
     ap.add_argument("--one-pass", action="store_true", help="(default) one-pass generic kernels")
     ap.add_argument("--queue", action="store_true", help="warp-level parking kernel instead of the one-pass generic kernels")
+    ap.add_argument("--cta", action="store_true", help="block-level hand-off kernel instead of the one-pass generic kernels")
+    ap.add_argument("--defer", type=int, default=None, help="defer_after K (None: library default)")
     ap.add_argument("--stream", action="store_true", help="lane-refill streaming kernel instead of the one-pass generic kernels")
     ap.add_argument("--tag", default=None)
     ap.add_argument("--max-iters", type=int, default=10)
@@ -92,7 +94,7 @@ def main():
             "fp64_peak_tflops": mp.fp64_peak_tflops()}
 
     if args.what == "k1":
-        nw = NewtonSettings(force_generic=args.generic, one_pass=args.one_pass, stream=args.stream, queue=args.queue, max_iters=args.max_iters,
+        nw = NewtonSettings(force_generic=args.generic, one_pass=args.one_pass, stream=args.stream, queue=args.queue, cta=args.cta, defer_after=args.defer, max_iters=args.max_iters,
                             ls_max_evals=args.ls_evals)
         outs = ("xi", "sigma", "dsig_deps", "dC_dp", "iters", "flags")
         xi = torch.zeros((7, n), dtype=torch.float64, device=dev)
@@ -105,7 +107,7 @@ def main():
         b = 784
         print(json.dumps({**base, "kernel": "K1 mp_update (xi, sigma, tangent, dC/dp)",
                           "solver": ("generic" if (args.generic or args.kind != "J2") else "j2-radial")
-                          + ("" if (args.kind == "J2" and not args.generic) else (" queue" if args.queue else (" lane-refill" if args.stream else " one-pass"))),
+                          + ("" if (args.kind == "J2" and not args.generic) else (" cta" if args.cta else " queue" if args.queue else (" lane-refill" if args.stream else " one-pass"))),
                           "newton": [args.max_iters, args.ls_evals], "tag": args.tag,
                           "checksum": [float(out[k].double().sum()) for k in outs],
                           "ms_per_step": ms, "ms_min": ms_min, "updates_per_s": n / ms * 1e3,

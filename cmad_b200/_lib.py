@@ -15,7 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "lib", "libcmad_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
-SOURCES = ["api.cu", "mp_update.cu", "mp_update_stream.cu", "mp_update_queue.cu", "mp_update_j2.cu", "mp_update_dt.cu", "mp_update_rate.cu", "elastic_update.cu", "mp_sens.cu", "mp_sens_dt.cu", "mp_hess.cu", "mp_history.cu",
+SOURCES = ["api.cu", "mp_update.cu", "mp_update_stream.cu", "mp_update_queue.cu", "mp_update_cta.cu", "mp_update_j2.cu", "mp_update_dt.cu", "mp_update_rate.cu", "elastic_update.cu", "mp_sens.cu", "mp_sens_dt.cu", "mp_hess.cu", "mp_history.cu",
            "fe_block.cu", "fe_tet4.cu", "fe_hex8.cu", "fe_generic.cu", "fe_tet4x4.cu", "fe_mixed.cu", "fe_post.cu", "fe_vjp.cu", "fe_scatter.cu"]
 
 # ---- enums (mirror include/cmad_b200.h) ---------------------------------
@@ -36,6 +36,7 @@ NEWTON_F_GENERIC = 1
 NEWTON_F_ONE_PASS = 2
 NEWTON_F_STREAM = 4
 NEWTON_F_QUEUE = 8
+NEWTON_F_CTA = 16
 
 
 class Material(C.Structure):

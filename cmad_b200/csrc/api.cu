@@ -169,6 +169,7 @@ int make_dev_newton(const cmadx_newton_t* nw, DevNewton* o) {
     const int k = (nw->flags & CMADX_NEWTON_DEFER_MASK) >> CMADX_NEWTON_DEFER_SHIFT;
     o->defer_request = (k == 0) ? -1 : (k == 255 ? 0 : k);   // -1: library default, see default_defer()
     o->defer_after = 0;
+    o->defer_min = -1;
     return CMADX_OK;
 }
 
@@ -292,6 +293,9 @@ static int launch(const MpArgs& A, cudaStream_t s) {
         if (e != cudaSuccess) return cuda_fail(e);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         e = launch_mp_update_sep_list(B, s);
+    } else if ((A.nw.flags & CMADX_NEWTON_F_CTA) && mp_update_cta_supported(A)) {
+        // generic Newton, one block per tile of 512 points, hard points handed over inside the block
+        e = launch_mp_update_cta(A, A.nw.defer_request > 0 ? A.nw.defer_request : 0, s);
     } else if ((A.nw.flags & CMADX_NEWTON_F_QUEUE) && mp_update_queue_supported(A)) {
         // generic Newton with warp-level parking: a persistent grid takes chunks of tiles from a counter
         BailScratch bs;

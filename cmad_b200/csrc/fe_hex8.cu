@@ -31,8 +31,6 @@
 // fall in complementary banks.  The tile keeps the three rows of node a 74 doubles
 // apart (37 x 16 B, odd) so the block-wise 64-bit writes are conflict-free (simulated:
 // 162 wavefronts per warp, the minimum).
-#include <cstdlib>
-
 #include "fe_common.cuh"
 
 namespace cmadx {
@@ -308,30 +306,10 @@ CMADX_DEV void hex8_point(const FeArgs& A, const int64_t e, const bool live, dou
     }
 }
 
-// L2 prefetch of the element-major inputs of a later block: blocks are dispatched in index
-// order, so the block `dist` places ahead starts about one block lifetime from now and finds
-// its grad_N / xi_prev / det / elem_eq runs in L2 (phase A then waits an L2 round trip instead
-// of a DRAM one; ncu on the unprefetched kernel: 13.7 % of the stall samples in phase A's loads).
-CMADX_DEV void hex8_prefetch_block(const cmadx_fe_block_t& b, int64_t blk, int n_per_block) {
-    const int64_t e0 = blk * n_per_block;
-    if (e0 >= b.n_elems) return;
-    const int64_t ne = min((int64_t)n_per_block, b.n_elems - e0);
-    const int t = threadIdx.x;
-    const char* g = reinterpret_cast<const char*>(b.grad_N + e0 * 192);
-    for (int64_t o = (int64_t)t * 128; o < ne * 1536; o += (int64_t)FE_BLOCK * 128)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(g + o));
-    const char* x = reinterpret_cast<const char*>(b.xi_prev + e0 * 56);
-    for (int64_t o = (int64_t)t * 128; o < ne * 448; o += (int64_t)FE_BLOCK * 128)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(x + o));
-    if (t < 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(b.det + e0 * 8) + t * 128));
-    else if (t < 20) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(b.elem_eq + e0 * 24) + (t - 8) * 128));
-}
-
 template <int SOLVER, bool ROT, bool WANT_K, bool LIST>
-__global__ void __launch_bounds__(FE_BLOCK, (SOLVER == 0) ? (WANT_K ? 3 : 4) : 1) fe_hex8_kernel(const __grid_constant__ FeArgs A, const int pf_dist) {
+__global__ void __launch_bounds__(FE_BLOCK, (SOLVER == 0) ? (WANT_K ? 3 : 4) : 1) fe_hex8_kernel(const __grid_constant__ FeArgs A) {
     extern __shared__ __align__(16) double smem[];
     if (!LIST) {
-        if (pf_dist > 0) hex8_prefetch_block(A.b, (int64_t)blockIdx.x + pf_dist, HEX_EPB);
         const int64_t e = (int64_t)blockIdx.x * HEX_EPB + (threadIdx.x >> 3);
         hex8_point<SOLVER, ROT, WANT_K>(A, e, e < A.b.n_elems, smem, A.bail_count != nullptr);
     } else {
@@ -358,11 +336,7 @@ struct Hex8Launcher {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         const int64_t nblk = LIST ? 2 * sms : (A.b.n_elems + HEX_EPB - 1) / HEX_EPB;
-        static const int pf_env = [] { const char* s = std::getenv("CMADX_HEX8_PREFETCH"); return s ? atoi(s) : -1; }();
-        int resident = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, FE_BLOCK, smem);
-        const int pf_dist = LIST ? 0 : (pf_env >= 0 ? pf_env * sms : resident * sms);
-        kern<<<(unsigned)nblk, FE_BLOCK, smem, stream>>>(A, pf_dist);
+        kern<<<(unsigned)nblk, FE_BLOCK, smem, stream>>>(A);
         return cudaGetLastError();
     }
 };

@@ -36,6 +36,9 @@ cudaError_t launch_mp_update_stream(const MpArgs& A, unsigned* counter, cudaStre
 // tiles handed out in chunks from `counter` (one zeroed unsigned in device memory)
 bool mp_update_queue_supported(const MpArgs& A);
 cudaError_t launch_mp_update_queue(const MpArgs& A, unsigned* counter, cudaStream_t stream);
+// generic Newton with block-level hand-off of the points that still iterate (mp_update_cta.cu)
+bool mp_update_cta_supported(const MpArgs& A);
+cudaError_t launch_mp_update_cta(const MpArgs& A, int defer_min, cudaStream_t stream);
 cudaError_t launch_mp_update_elastic(const MpArgs& A, cudaStream_t stream);
 // SmallRateElasticPlastic (rate form; `strain` = strain increment)
 cudaError_t launch_mp_update_rate(const MpArgs& A, cudaStream_t stream);

@@ -43,6 +43,8 @@ struct DevNewton {
                        // handed to the second (compacted) pass; 0: off.  Only kernels that own a
                        // second pass set it (from defer_request); everywhere else it stays 0
     int defer_request; // what the caller asked for (cmadx_newton_t flags bits 8..15)
+    int defer_min;     // >= 0: a lane that needs a Newton direction after this many updates stops with its
+                       // state intact (block-level hand-off, mp_update_cta.cu); -1: off
     double abs_tol, rel_tol, c1, bmin, bmax;
 };
 
@@ -101,6 +103,18 @@ template <> struct YieldFn<CMADX_YIELD_J2> {
     CMADX_DEV bool dparam(const DevMat&, int, const double (&)[6], double&, double (&)[6]) const {
         return false;
     }
+    // state of the last evaluation as NS doubles (stride apart), and back - with the normal it implies
+    static constexpr int NS = 8;
+    CMADX_DEV void save(double* p, int st) const {
+        p[0] = c; p[st] = sn;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) p[(2 + a) * st] = sh[a];
+    }
+    CMADX_DEV void load(const DevMat&, const double* p, int st, double (&n)[6]) {
+        c = p[0]; sn = p[st];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) { sh[a] = p[(2 + a) * st]; n[a] = 1.2247448713915890491 * sh[a]; }
+    }
 };
 
 template <> struct YieldFn<CMADX_YIELD_HILL> {
@@ -156,6 +170,18 @@ template <> struct YieldFn<CMADX_YIELD_HILL> {
 #pragma unroll
         for (int a = 0; a < 6; ++a) dn[a] = (0.5 * dg[a] - nn[a] * dphi) * iphi;
         return true;
+    }
+    static constexpr int NS = 10;
+    CMADX_DEV void save(double* p, int st) const {
+        p[0] = iphi; p[st] = d12; p[2 * st] = d20; p[3 * st] = d01;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) p[(4 + a) * st] = nn[a];
+    }
+    CMADX_DEV void load(const DevMat& m, const double* p, int st, double (&n)[6]) {
+        F = m.hill[0]; G = m.hill[1]; H = m.hill[2]; L = m.hill[3]; Mm = m.hill[4]; N = m.hill[5];
+        iphi = p[0]; d12 = p[st]; d20 = p[2 * st]; d01 = p[3 * st];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) { nn[a] = p[(4 + a) * st]; n[a] = nn[a]; }
     }
 };
 
@@ -250,6 +276,20 @@ template <> struct YieldFn<CMADX_YIELD_HOSFORD> {
         dn[0] = dgi[0] - dgi[2]; dn[3] = dgi[1] - dgi[0]; dn[5] = dgi[2] - dgi[1];
         dn[1] = 0.0; dn[2] = 0.0; dn[4] = 0.0;
         return true;
+    }
+    static constexpr int NS = 7;
+    CMADX_DEV void save(double* p, int st) const {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { p[i * st] = g[i]; p[(3 + i) * st] = w[i]; }
+        p[6 * st] = iphi;
+    }
+    CMADX_DEV void load(const DevMat& m, const double* p, int st, double (&n)[6]) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { g[i] = p[i * st]; w[i] = p[(3 + i) * st]; }
+        iphi = p[6 * st];
+        am1 = m.a - 1.0;
+        n[0] = g[0] - g[2]; n[3] = g[1] - g[0]; n[5] = g[2] - g[1];
+        n[1] = 0.0; n[2] = 0.0; n[4] = 0.0;
     }
 };
 
@@ -460,6 +500,22 @@ struct SepPoint {
     }
 };
 
+// the yield-surface state of a point (what the Jacobian and the derivative outputs read after a
+// residual evaluation) as NS doubles `st` apart: lets another thread continue or finish the point
+template <class Pt>
+CMADX_DEV void save_point_state(const Pt& pt, double* p, int st) {
+    pt.yf.save(p, st);
+    p[decltype(pt.yf)::NS * st] = pt.f;
+    p[(decltype(pt.yf)::NS + 1) * st] = pt.eD;
+}
+template <class Pt>
+CMADX_DEV void load_point_state(const DevMat& m, Pt& pt, const double* p, int st, bool plastic) {
+    pt.yf.load(m, p, st, pt.n);
+    pt.f = p[decltype(pt.yf)::NS * st];
+    pt.eD = p[(decltype(pt.yf)::NS + 1) * st];
+    pt.plastic = plastic;
+}
+
 // position in the full 7-vector [ep(6), alpha] of local unknown k
 template <int YK> struct SepPointTraits {
     CMADX_DEV static constexpr int full(int k) { return k; }
@@ -649,7 +705,7 @@ CMADX_DEV void list_append(bool want, unsigned* count, int* list, unsigned cap, 
 // Pt provides residual(m, x, xp, em, C), jacobian(m, dgamma, J) and `plastic`.
 template <class Pt, int N>
 struct NewtonLane {
-    enum { PH_INIT = 0, PH_PROBE = 1, PH_EVAL = 2 };
+    enum { PH_INIT = 0, PH_PROBE = 1, PH_EVAL = 2, PH_DIR = 3 };   // PH_DIR: resume at "take a direction"
     double x[N];                 // current iterate
     double dx[N];                // Newton direction of the running line search / last step
     double n0, nc;               // ||C|| at x0 and at the last convergence test
@@ -673,14 +729,15 @@ struct NewtonLane {
     CMADX_DEV void trip(const DevMat& m, const DevNewton& nw, Pt& pt, const double (&xp)[N],
                         const double (&em)[6], bool live, double (&Ct)[N]) {
         const bool traced = (nw.mode == CMADX_NEWTON_TRACED);
-        {
+        if (phase != PH_DIR) {   // PH_DIR: (Ct, pt) at x were restored by the caller, nothing to evaluate
             double xt[N];
 #pragma unroll
             for (int i = 0; i < N; ++i) xt[i] = (phase == PH_PROBE) ? fma(-al, dx[i], x[i]) : x[i];
             pt.residual(m, xt, xp, em, Ct);                // the only call site
         }
-        bool need_dir = false;   // (x, Ct) current and pt fresh at x: take a Newton step
-        if (phase == PH_INIT) {
+        bool need_dir = (phase == PH_DIR);   // (x, Ct) current and pt fresh at x: take a Newton step
+        if (phase == PH_DIR) {
+        } else if (phase == PH_INIT) {
             flag_entry = pt.plastic ? 1 : 0;
             n0 = normN<N>(Ct);
             nc = n0;
@@ -738,7 +795,8 @@ struct NewtonLane {
         // Two-pass divergence control of the one-pass kernels: a lane that still needs a
         // direction after `defer_after` updates stops here; the kernel appends it to a list and
         // a second pass re-solves those points in warps made of hard points only.
-        if (need_dir && nw.defer_after > 0 && ii >= nw.defer_after) {
+        if (need_dir && phase != PH_DIR &&
+            ((nw.defer_after > 0 && ii >= nw.defer_after) || (nw.defer_min >= 0 && ii >= nw.defer_min))) {
             need_dir = false;
             active = false;
             deferred = true;

@@ -173,19 +173,36 @@ def displacement_l2_step(N: np.ndarray, wdet: np.ndarray, elem_eq: np.ndarray, U
     return float(((u_ip * u_ip).sum(axis=-1) * wdet).sum())
 
 
+def _step_state(qoi, assemble, U, xi_prev, t, t_prev, k):
+    """StepState of a converged load step; QoIs that read reactions get the assembled (un-embedded)
+    residual and tangent at the converged state from one more assembly (as the reference's
+    FELoadMatch._reaction_at re-runs the residual assembly, cmad/qois/fe_load_match.py:179-196)."""
+    from .fe_qoi import StepState
+    s = StepState(U=U, t=t, t_prev=t_prev, step=k)
+    K_data = None
+    if qoi is not None and qoi.needs_residual:
+        R, K_data, _ = assemble(U, xi_prev)
+        s.R = np.asarray(R, dtype=np.float64)
+    return s, K_data
+
+
 def fe_quasistatic_drive(assemble, pattern: SparsePattern, bcs: DirichletBCs, U0: np.ndarray, xi0,
                          t_schedule: Sequence[float], settings: dict | None = None,
-                         step_qoi: Callable[[np.ndarray, float, float], float] | None = None):
+                         step_qoi: Callable[[np.ndarray, float, float], float] | None = None, qoi=None):
     """Load-step loop (driver.py:103-146): returns ``(U_steps, xi_last, J, logs)``;
-    ``step_qoi(U, t, t_prev)`` is summed into ``J`` after every converged step."""
+    ``step_qoi(U, t, t_prev)`` - or a :class:`cmad_b200.fe_qoi.FEQoI` object ``qoi`` - is summed into
+    ``J`` after every converged step."""
     U, xi = np.array(U0, dtype=np.float64), xi0
     U_steps, logs, J = [], [], 0.0
     for k in range(1, len(t_schedule)):
         t, t_prev = float(t_schedule[k]), float(t_schedule[k - 1])
-        U, xi, log = fe_newton_solve(assemble, pattern, bcs, U, xi, t, settings)
+        xi_prev = xi
+        U, xi, log = fe_newton_solve(assemble, pattern, bcs, U, xi_prev, t, settings)
         U_steps.append(U.copy())
         logs.append(log)
-        if step_qoi is not None:
+        if qoi is not None:
+            J += qoi.value(_step_state(qoi, assemble, U, xi_prev, t, t_prev, k)[0])
+        elif step_qoi is not None:
             J += step_qoi(U, t, t_prev)
     return np.array(U_steps), xi, J, logs
 
@@ -202,7 +219,7 @@ def displacement_l2_step_dU(N: np.ndarray, wdet: np.ndarray, elem_eq: np.ndarray
 
 def fe_direct_gradient(assemble, jvp, pattern: SparsePattern, bcs: DirichletBCs, U0, xi0, dxi0,
                        t_schedule: Sequence[float], n_active: int, settings: dict | None,
-                       step_qoi, step_qoi_dU):
+                       step_qoi=None, step_qoi_dU=None, qoi=None):
     """``(J, dJ/dp)`` in native parameter values by forward (direct) sensitivities through
     the load steps - the discrete equivalent of differentiating the trajectory of
     cmad/fem/driver.py:103-146 through the IFT rule of the FE Newton
@@ -221,21 +238,29 @@ def fe_direct_gradient(assemble, jvp, pattern: SparsePattern, bcs: DirichletBCs,
         xi_prev = xi
         U, xi, log = fe_newton_solve(assemble, pattern, bcs, U, xi_prev, t, settings)
         lu = spla.splu(log.K_emb)
-        dq = step_qoi_dU(U, t, t_prev)
-        J += step_qoi(U, t, t_prev)
+        sbar = None
+        if qoi is not None:
+            st, _ = _step_state(qoi, assemble, U, xi_prev, t, t_prev, k)
+            dq, sbar = qoi.dU(st), qoi.dR(st)
+            J += qoi.value(st)
+        else:
+            dq = step_qoi_dU(U, t, t_prev)
+            J += step_qoi(U, t, t_prev)
         for c in range(n_active):
             dR, _ = jvp(U, xi_prev, xi, c, dX[c], None)
             rhs = -np.asarray(dR)
             rhs[bcs.indices] = 0.0                     # prescribed values do not depend on p
             dU = lu.solve(rhs)
-            _, dX[c] = jvp(U, xi_prev, xi, c, dX[c], dU)
+            dR_total, dX[c] = jvp(U, xi_prev, xi, c, dX[c], dU)      # dR/dp + dR/dxi_prev dxi_prev + K dU
             grad[c] += float(dq @ dU)
+            if sbar is not None:
+                grad[c] += float(sbar @ np.asarray(dR_total))
     return J, grad
 
 
 def fe_adjoint_gradient(assemble, vjp, vjp_disp, pattern: SparsePattern, bcs: DirichletBCs, U0, xi0,
                         t_schedule: Sequence[float], n_active: int, settings: dict | None,
-                        step_qoi, step_qoi_dU):
+                        step_qoi=None, step_qoi_dU=None, qoi=None):
     """``(J, dJ/dp)`` in native parameter values by the DISCRETE ADJOINT through the load
     steps - what ``jax.grad`` of the trajectory of cmad/fem/driver.py:103-146 computes through
     the IFT rules of the FE Newton (cmad/fem/nonlinear_solver.py:450-542) and of the local
@@ -255,18 +280,31 @@ def fe_adjoint_gradient(assemble, vjp, vjp_disp, pattern: SparsePattern, bcs: Di
         t, t_prev = float(t_schedule[k]), float(t_schedule[k - 1])
         xi_prev = xi
         U, xi, log = fe_newton_solve(assemble, pattern, bcs, U, xi_prev, t, settings)
-        J += step_qoi(U, t, t_prev)
-        steps.append((U.copy(), xi_prev, xi, log.K_emb, step_qoi_dU(U, t, t_prev)))
+        sbar, Kt_sbar = None, None
+        if qoi is not None:
+            st, K_data = _step_state(qoi, assemble, U, xi_prev, t, t_prev, k)
+            J += qoi.value(st)
+            dq, sbar = qoi.dU(st), qoi.dR(st)
+            if sbar is not None:                        # a QoI of the reactions: dJ_n/dU gets K^T sbar
+                Kt_sbar = pattern.csr(np.asarray(K_data)).T @ sbar
+        else:
+            J += step_qoi(U, t, t_prev)
+            dq = step_qoi_dU(U, t, t_prev)
+        steps.append((U.copy(), xi_prev, xi, log.K_emb, dq, sbar, Kt_sbar))
     grad = np.zeros(n_active)
     xbar = None
-    for U, xi_prev, xi, K_emb, dq in reversed(steps):
+    for U, xi_prev, xi, K_emb, dq, sbar, Kt_sbar in reversed(steps):
         rhs = np.asarray(dq, dtype=np.float64).copy()
+        if Kt_sbar is not None:
+            rhs += Kt_sbar
         if xbar is not None:
             rhs += np.asarray(vjp_disp(U, xi_prev, xi, xbar))
         rhs[bcs.indices] = 0.0                          # prescribed values do not depend on p
         lam = spla.splu(sp.csc_matrix(K_emb.T)).solve(-rhs)
         lam[bcs.indices] = 0.0
-        pbar, xbar = vjp(U, xi_prev, xi, lam, xbar)
+        # the residual's direct dependence on (p, xi_prev) is weighted by lam (equilibrium) and by
+        # sbar (the QoI reads reactions): one VJP with Rbar = lam + sbar
+        pbar, xbar = vjp(U, xi_prev, xi, lam if sbar is None else lam + sbar, xbar)
         grad += np.asarray(pbar)
     return J, grad
 

@@ -36,6 +36,7 @@ class NewtonSettings:
     stream: bool = False            # material-point batches: the streaming (lane-refill) kernel instead of the
                                     # one-pass generic kernels - A/B testing, identical results
     queue: bool = False             # material-point batches: generic kernel with warp-level parking (mp_update_queue.cu)
+    cta: bool = False               # material-point batches: generic kernel with block-level hand-off (mp_update_cta.cu)
     defer_after: int | None = None  # generic kernels' two-pass scheme: None = library default (K = 2 for Hosford a > 8, else off),
                                     # 0 = single pass, K = defer points needing more than K updates
 
@@ -44,7 +45,7 @@ class NewtonSettings:
             raise ValueError(f"unknown newton mode {self.mode!r}")
         return L.Newton(L.NEWTON_TRACED if self.mode == "traced" else L.NEWTON_IMPERATIVE,
                         int(self.max_iters), int(self.ls_max_evals),
-                        (L.NEWTON_F_GENERIC if self.force_generic else 0) | (L.NEWTON_F_ONE_PASS if self.one_pass else 0) | (L.NEWTON_F_STREAM if self.stream else 0) | (L.NEWTON_F_QUEUE if self.queue else 0)
+                        (L.NEWTON_F_GENERIC if self.force_generic else 0) | (L.NEWTON_F_ONE_PASS if self.one_pass else 0) | (L.NEWTON_F_STREAM if self.stream else 0) | (L.NEWTON_F_QUEUE if self.queue else 0) | (L.NEWTON_F_CTA if self.cta else 0)
                         | ((0 if self.defer_after is None else (255 if self.defer_after == 0 else
                                                                min(int(self.defer_after), 254))) << 8),
                         float(self.abs_tol), float(self.rel_tol),

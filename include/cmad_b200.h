@@ -99,7 +99,11 @@ enum {
     /* material-point batches: generic kernel with warp-level parking (mp_update_queue.cu): lanes
      * that still iterate when most of their warp is done are parked in shared memory and resumed
      * in full warps; results equal the one-pass kernels' bit for bit */
-    CMADX_NEWTON_F_QUEUE = 8
+    CMADX_NEWTON_F_QUEUE = 8,
+    /* material-point batches: generic kernel with block-level hand-off (mp_update_cta.cu): a block
+     * owns 512 points, the points that still iterate after `defer_after` updates (0: all plastic
+     * points) are resumed by full warps from records in shared memory, every store is a full row */
+    CMADX_NEWTON_F_CTA = 16
 };
 #define CMADX_NEWTON_DEFER_SHIFT 8
 #define CMADX_NEWTON_DEFER_MASK 0xff00

@@ -442,7 +442,7 @@ def test_two_pass_deferral_keeps_iterates_and_counts(cuda_device, kind, a):
 # ----------------------------------------------------------------- streaming (lane-refill) kernel
 @pytest.mark.parametrize("case", ["J2", "hill", "hill-rot", "hosford4", "hosford100", "hosford4-rot", "hosford-generic"])
 @pytest.mark.parametrize("mode", ["traced", "imperative"])
-@pytest.mark.parametrize("variant", ["stream", "queue", "default"])
+@pytest.mark.parametrize("variant", ["stream", "queue", "default", "cta", "cta-k2"])
 def test_streaming_kernel_equals_one_pass_kernel(cuda_device, case, mode, variant):
     """The warp-parking kernel (mp_update_queue.cu) and the lane-refill kernel (mp_update_stream.cu) hand
     points to lanes in a different order and computes the outputs in a separate drain step, but every
@@ -463,8 +463,8 @@ def test_streaming_kernel_equals_one_pass_kernel(cuda_device, case, mode, varian
         dict(max_iters=20, abs_tol=1e-12, rel_tol=1e-12)
     generic = case.endswith("-generic")
     nws = NewtonSettings(mode=mode, force_generic=True if kind == "J2" or generic else False,
-                         stream=(variant == "stream"), queue=(variant == "queue"),
-                         defer_after=0 if variant == "default" else None, **kw)   # "default": lock-step blocks for reduced Hosford
+                         stream=(variant == "stream"), queue=(variant == "queue"), cta=variant.startswith("cta"),
+                         defer_after=0 if variant in ("default", "cta") else (2 if variant == "cta-k2" else None), **kw)   # "default": lock-step blocks for reduced Hosford
     nwo = NewtonSettings(mode=mode, force_generic=True if kind == "J2" or generic else False, one_pass=True,
                          defer_after=0, **kw)
     for n, comps, pad in ((1, 6, 0), (31, 6, 0), (33, 9, 3), (4099, 6, 5), (70001, 9, 0)):
