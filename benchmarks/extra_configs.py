@@ -34,8 +34,13 @@ if ROOT not in sys.path:
 # FP64 flops per unit (2 x DFMA + DMUL + DADD thread instructions, predicated on) from ncu
 # captures of these exact workloads; the source file is named next to each number.
 FP64_FLOPS = {
-    # filled from profiles/r2_*_flops.txt (see profiles/tools/ncu_flops.py)
+    # (flops per unit, source): ncu counts of the timed region of these exact workloads
+    # (benchmarks/count_flops.sh -> profiles/r2_flops_<name>.csv, reduced by profiles/tools/ncu_region_flops.py)
 }
+_flops_file = os.path.join(ROOT, "profiles", "r2_fp64_flops.json")
+if os.path.exists(_flops_file):
+    import json as _json
+    FP64_FLOPS.update({k: (v["flops_per_unit"], v["source"]) for k, v in _json.load(open(_flops_file)).items()})
 
 
 def _const(t, c):
@@ -78,11 +83,13 @@ class Ctx:
             dist.barrier()
         torch.cuda.synchronize(self.dev)
         sampler.start()
+        torch.cuda.nvtx.range_push("cmadx_timed")      # lets `ncu --nvtx --nvtx-include "cmadx_timed/"` count this region only
         ev0[0].record()
         for k in range(K):
             fn(lambda name, k=k: evm[name][k].record())
             ev0[k + 1].record()
         torch.cuda.synchronize(self.dev)
+        torch.cuda.nvtx.range_pop()
         if self.world > 1:
             dist.barrier()
         clocks = sampler.stop()
@@ -282,6 +289,11 @@ def fe_adjoint_mixed(ctx: Ctx, family: str, div: int):
            "launches_per_step": int(launches), "clocks": clocks, "setup_s": round(setup_s, 1),
            "grad": [float(x) for x in state["pbar"].cpu()]}
     res.update(ctx.fracs(n_e, seg["assemble"], alg, f"fe_mixed_{family}"))
+    key = f"fe_adjoint_mixed_{family}"
+    if key in FP64_FLOPS:                                # FP64 rate of the WHOLE adjoint step (all its kernels)
+        fl, src = FP64_FLOPS[key]
+        res.update({"fp64_flops_per_unit_step": fl, "fp64_flops_source": src,
+                    "fp64_tflops_step": n_e * fl / ms / 1e9, "frac_fp64_step": n_e * fl / ms / 1e9 / ctx.fp64})
     return res
 
 

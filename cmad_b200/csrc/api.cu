@@ -267,6 +267,16 @@ int get_bail_scratch(cudaStream_t s, BailScratch* out, unsigned min_cap = BAIL_C
 }
 }  // namespace
 
+// Measured on B200 (2^23 points, profiles/r2n_k1_cta.jsonl): the block-level hand-off kernel beats
+// the one-pass / two-pass kernels for near-Tresca Hosford exponents (K = 2: 4.87 -> 4.11 ms) and for
+// J2 through the generic kernel (4.44 -> 3.48 ms); it ties for Hosford a = 4 (1.79 -> 1.75 ms, the
+// lock-step kernel stays) and loses for Hill (3.27 -> 3.75 ms).
+static bool cta_by_default(const MpArgs& A) {
+    if (A.nw.flags & (CMADX_NEWTON_F_ONE_PASS | CMADX_NEWTON_F_STREAM | CMADX_NEWTON_F_QUEUE)) return false;
+    if (A.m.yield == CMADX_YIELD_HOSFORD) return A.nw.defer_request > 0;
+    return A.m.yield == CMADX_YIELD_J2;
+}
+
 static int launch(const MpArgs& A, cudaStream_t s) {
     if (A.b.n == 0) return CMADX_OK;
     cudaError_t e;
@@ -293,7 +303,7 @@ static int launch(const MpArgs& A, cudaStream_t s) {
         if (e != cudaSuccess) return cuda_fail(e);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         e = launch_mp_update_sep_list(B, s);
-    } else if ((A.nw.flags & CMADX_NEWTON_F_CTA) && mp_update_cta_supported(A)) {
+    } else if (((A.nw.flags & CMADX_NEWTON_F_CTA) || cta_by_default(A)) && mp_update_cta_supported(A)) {
         // generic Newton, one block per tile of 512 points, hard points handed over inside the block
         e = launch_mp_update_cta(A, A.nw.defer_request > 0 ? A.nw.defer_request : 0, s);
     } else if ((A.nw.flags & CMADX_NEWTON_F_QUEUE) && mp_update_queue_supported(A)) {

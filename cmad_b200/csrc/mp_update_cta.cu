@@ -134,7 +134,9 @@ mp_update_cta_kernel(const __grid_constant__ MpArgs A, const int defer_min) {
         }
         if (!live) L.active = false;
         nw.defer_min = fresh ? defer_min : -1;
-        while (__syncthreads_or(L.active ? 1 : 0) != 0) {
+        // phase 1 votes block-wide (lock-step: instruction-cache locality); the hard rounds vote per
+        // warp - their lanes' counts differ widely and no warp reads another's records before phase 3
+        while (fresh ? (__syncthreads_or(L.active ? 1 : 0) != 0) : (__any_sync(0xffffffffu, L.active) != 0)) {
             if (L.active) L.trip(m, nw, pt, yp, em, true, Ct);     // the finishing trip leaves Ct at x, pt fresh there
         }
         if (live) {

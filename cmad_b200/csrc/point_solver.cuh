@@ -105,6 +105,7 @@ template <> struct YieldFn<CMADX_YIELD_J2> {
     }
     // state of the last evaluation as NS doubles (stride apart), and back - with the normal it implies
     static constexpr int NS = 8;
+    CMADX_DEV void save_n(double*, int, const double (&)[6]) const {}
     CMADX_DEV void save(double* p, int st) const {
         p[0] = c; p[st] = sn;
 #pragma unroll
@@ -172,6 +173,7 @@ template <> struct YieldFn<CMADX_YIELD_HILL> {
         return true;
     }
     static constexpr int NS = 10;
+    CMADX_DEV void save_n(double*, int, const double (&)[6]) const {}
     CMADX_DEV void save(double* p, int st) const {
         p[0] = iphi; p[st] = d12; p[2 * st] = d20; p[3 * st] = d01;
 #pragma unroll
@@ -233,7 +235,10 @@ template <> struct YieldFn<CMADX_YIELD_HOSFORD> {
             const double t = (dl[i] > 0.0) - (dl[i] < 0.0); // sign, 0 at 0
             const double ir = (r > 0.0) ? 1.0 / r : 0.0;
             g[i] = 0.5 * t * ra * ir;                       // 1/2 t r^(a-1)
-            w[i] = 0.5 * ra * ir * ir;                      // 1/2 r^(a-2)
+            // 1/2 r^(a-2).  Rounded here once and for all (__dmul_rn is never contracted into the
+            // adds of Gd()): the value is part of the state another thread may restore from shared
+            // memory (mp_update_cta.cu), and both flows must see the same bits
+            w[i] = __dmul_rn(0.5 * ra * ir, ir);
         }
         n[0] = g[0] - g[2]; n[3] = g[1] - g[0]; n[5] = g[2] - g[1];
         n[1] = 0.0; n[2] = 0.0; n[4] = 0.0;
@@ -277,7 +282,12 @@ template <> struct YieldFn<CMADX_YIELD_HOSFORD> {
         dn[1] = 0.0; dn[2] = 0.0; dn[4] = 0.0;
         return true;
     }
-    static constexpr int NS = 7;
+    // the normal is saved as evaluated (n = g_i - g_j may have been contracted with the product
+    // that defines g_i: recomputing it from the rounded g would differ in the last bit)
+    static constexpr int NS = 10;
+    CMADX_DEV void save_n(double* p, int st, const double (&n)[6]) const {
+        p[7 * st] = n[0]; p[8 * st] = n[3]; p[9 * st] = n[5];
+    }
     CMADX_DEV void save(double* p, int st) const {
 #pragma unroll
         for (int i = 0; i < 3; ++i) { p[i * st] = g[i]; p[(3 + i) * st] = w[i]; }
@@ -288,7 +298,7 @@ template <> struct YieldFn<CMADX_YIELD_HOSFORD> {
         for (int i = 0; i < 3; ++i) { g[i] = p[i * st]; w[i] = p[(3 + i) * st]; }
         iphi = p[6 * st];
         am1 = m.a - 1.0;
-        n[0] = g[0] - g[2]; n[3] = g[1] - g[0]; n[5] = g[2] - g[1];
+        n[0] = p[7 * st]; n[3] = p[8 * st]; n[5] = p[9 * st];
         n[1] = 0.0; n[2] = 0.0; n[4] = 0.0;
     }
 };
@@ -505,6 +515,7 @@ struct SepPoint {
 template <class Pt>
 CMADX_DEV void save_point_state(const Pt& pt, double* p, int st) {
     pt.yf.save(p, st);
+    pt.yf.save_n(p, st, pt.n);
     p[decltype(pt.yf)::NS * st] = pt.f;
     p[(decltype(pt.yf)::NS + 1) * st] = pt.eD;
 }

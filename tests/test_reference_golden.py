@@ -37,9 +37,11 @@ OB = np.load(os.path.join(G, "ref_mp_objectives.npz"))
 TRACED = sorted({k.rsplit(".", 1)[0] for k in TR.files})
 IMPER = sorted({k.rsplit(".", 1)[0] for k in IM.files})
 OBJ = sorted({k.rsplit(".", 1)[0] for k in OB.files})
-# knife-edge material (a = 100: |f| of the converged state sits at rounding level of the
-# 1e-14 plastic band); counts compared statistically, values on the agreeing points
-LOOSE = {"hosford_notch.notch"}
+# Round 1 compared the notch material (Hosford a = 100, 500 iterations, 100 probes) statistically.
+# Both the C++ oracle and the CUDA kernels reproduce the reference's counts and flags on every
+# point of that fixture, and the reference's own answers do not move under a one-ulp change of
+# its inputs (tests/golden/ref_knife_edge.npz): the comparison is exact for every case now.
+LOOSE: set = set()
 
 _ROW9 = [3 * i + j for i, j in UP]                                   # packed component -> row-major 3x3 entry
 _COLS = [((3 * k + l,) if k == l else (3 * k + l, 3 * l + k)) for k, l in UP]
@@ -294,3 +296,14 @@ def test_c_oracle_dC_dp_rotation_and_exponent_leaves_vs_reference(case):
         prob = oc.describe(values, P.active_idx, newton_mode="traced", strain_comps=9, **kw)
         return oc.mp_update(prob, xi_prev, grad_u, want=("xi", "iters", "flags", "dC_dp"))
     _check_leaf_columns(case, run)
+
+
+def test_reference_counts_of_the_notch_material_are_stable_under_one_ulp():
+    """tests/golden/make_knife_edge_golden.py: the reference's own make_newton_solve on the
+    hosford_notch.notch inputs, re-run with every strain entry moved by +-1 ulp - same counts, same
+    flags.  So "bit-exact counts" is a well-defined target for this material too."""
+    K = np.load(os.path.join(G, "ref_knife_edge.npz"))
+    assert K["iters"].shape == (2, 16) and int(K["iters"].max()) >= 10
+    for tag in ("base", "up", "down"):
+        assert np.array_equal(K[f"iters_{tag}"], K["iters"]) and np.array_equal(K[f"flags_{tag}"], K["flags"])
+    assert np.array_equal(K["iters"], TR["hosford_notch.notch.iters"])
