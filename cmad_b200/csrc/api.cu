@@ -170,6 +170,12 @@ int make_dev_newton(const cmadx_newton_t* nw, DevNewton* o) {
     o->defer_request = (k == 0) ? -1 : (k == 255 ? 0 : k);   // -1: library default, see default_defer()
     o->defer_after = 0;
     o->defer_min = -1;
+    // imperative flavour with newton_solve's legacy line search (ls_max_evals = its max_ls_evals):
+    // only the generic Newton kernels carry it
+    if (nw->mode == CMADX_NEWTON_IMPERATIVE) {
+        if (nw->ls_max_evals < 0) return CMADX_EINVAL;
+        if (nw->ls_max_evals > 0) o->flags |= CMADX_NEWTON_F_GENERIC;
+    }
     return CMADX_OK;
 }
 
@@ -611,6 +617,8 @@ int cmadx_mp_forward_history(const cmadx_material_t* mat, const cmadx_newton_t* 
     // fused one-launch path: J2 (radial-return first pass, HBM / latency-bound: 1.3x faster than the
     // per-step launches at scale), and any surface for small batches (launch-bound regime); large
     // generic batches keep the per-step kernels (higher occupancy, measured faster)
+    if (newton && newton->mode == CMADX_NEWTON_IMPERATIVE && newton->ls_max_evals > 0)
+        return CMADX_EUNSUPPORTED;       // the legacy line search lives in cmadx_mp_update only
     const bool j2_radial = dm.yield == CMADX_YIELD_J2 && newton && !(newton->flags & CMADX_NEWTON_F_GENERIC);
     if (history_def_type(hist) == CMADX_DEF_FULL_3D && !dm.rot && hist->n < (int64_t)0x7fffffff &&
         (j2_radial || hist->n <= 32768) && !std::getenv("CMADX_HISTORY_PER_STEP")) {
@@ -763,6 +771,7 @@ static int fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* 
     FeArgs A;
     if (int rc = check_fe_block(mat, blk, &A)) return rc;
     if (int rc = make_dev_newton(newton, &A.nw)) return rc;
+    if (A.nw.mode == CMADX_NEWTON_IMPERATIVE && A.nw.ls_max > 0) return CMADX_EUNSUPPORTED;
     default_defer(A.m, &A.nw);
     if (mix) {
         if (blk->n_elems > 0) {

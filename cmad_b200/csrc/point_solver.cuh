@@ -716,7 +716,9 @@ CMADX_DEV void list_append(bool want, unsigned* count, int* list, unsigned cap, 
 // Pt provides residual(m, x, xp, em, C), jacobian(m, dgamma, J) and `plastic`.
 template <class Pt, int N>
 struct NewtonLane {
-    enum { PH_INIT = 0, PH_PROBE = 1, PH_EVAL = 2, PH_DIR = 3 };   // PH_DIR: resume at "take a direction"
+    // PH_DIR: resume at "take a direction"; PH_LEGACY: a probe of the imperative flavour's legacy
+    // line search (newton_solve(max_ls_evals > 0), cmad/models/nonlinear_solver.py:55-81)
+    enum { PH_INIT = 0, PH_PROBE = 1, PH_EVAL = 2, PH_DIR = 3, PH_LEGACY = 4 };
     double x[N];                 // current iterate
     double dx[N];                // Newton direction of the running line search / last step
     double n0, nc;               // ||C|| at x0 and at the last convergence test
@@ -763,6 +765,30 @@ struct NewtonLane {
             }
         } else {
             bool test = (phase == PH_EVAL);                  // x is where Ct was evaluated
+            if (phase == PH_LEGACY) {
+                // x already sits at x_k + al dx.  psi_j >= (1 - 2 beta al) psi_0 (false for NaN):
+                // next al = max(eta al, -al^2 psi_0' / (2 (psi_j - psi_0 - al psi_0'))), psi_0' = -2 psi_0,
+                // beta = 1e-4, eta = 0.5; at jj == max_ls_evals the loop breaks WITHOUT moving x.
+                // The accepted (or last) evaluation is the one the next convergence test would
+                // repeat at the same x, so it is reused (identical values).
+                const double psi0 = 0.5 * CC, dpsi0 = -2.0 * psi0;          // CC = ||C(x_k)||^2 via the norm
+                const double cj = normN<N>(Ct);
+                const double psij = 0.5 * cj * cj;
+                if (psij >= (1.0 - 2.0 * 1e-4 * al) * psi0) {
+                    const double an = fmax(0.5 * al, -(al * al * dpsi0) / (2.0 * (psij - psi0 - al * dpsi0)));
+                    if (ne == nw.ls_max) {
+                        test = true;                                         // "reached max ls evals"
+                    } else {
+                        ++ne;
+                        const double da = an - al;
+#pragma unroll
+                        for (int i = 0; i < N; ++i) x[i] = fma(da, dx[i], x[i]);
+                        al = an;
+                    }
+                } else {
+                    test = true;
+                }
+            }
             if (phase == PH_PROBE) {
                 // ---- line search (quadratic model), line_search.py:125-181
                 const double phi0 = 0.5 * CC, dphi0 = -CC, armijo = nw.c1 * dphi0;
@@ -792,6 +818,7 @@ struct NewtonLane {
                 }
             }
             if (test) {
+                if (phase == PH_LEGACY) phase = PH_EVAL;
                 const bool by_iters = ii >= nw.max_iters;
                 // imperative flavour at max_iters: newton_solve returns the norm of its last test
                 if (traced || !by_iters) nc = normN<N>(Ct);
@@ -828,7 +855,13 @@ struct NewtonLane {
 #pragma unroll
                 for (int i = 0; i < N; ++i) x[i] += dx[i];
                 ++ii;
-                phase = PH_EVAL;
+                if (nw.ls_max > 0) {          // legacy line search: probes start at the full step
+                    CC = nc * nc;
+                    al = 1.0; ne = 1;
+                    phase = PH_LEGACY;
+                } else {
+                    phase = PH_EVAL;
+                }
             }
         }
     }

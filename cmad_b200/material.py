@@ -27,7 +27,8 @@ class NewtonSettings:
     max_iters: int = 10
     abs_tol: float = 1e-14
     rel_tol: float = 1e-14
-    ls_max_evals: int = 4
+    ls_max_evals: int = 4           # traced flavour: probes of the quadratic line search
+    max_ls_evals: int = 0           # imperative flavour: newton_solve's legacy line search (0 = none, the default)
     ls_sufficient_decrease: float = 1.0e-4
     ls_min_backtrack: float = 0.5
     ls_max_backtrack: float = 0.9
@@ -44,7 +45,7 @@ class NewtonSettings:
         if self.mode not in ("traced", "imperative"):
             raise ValueError(f"unknown newton mode {self.mode!r}")
         return L.Newton(L.NEWTON_TRACED if self.mode == "traced" else L.NEWTON_IMPERATIVE,
-                        int(self.max_iters), int(self.ls_max_evals),
+                        int(self.max_iters), int(self.ls_max_evals if self.mode == "traced" else self.max_ls_evals),
                         (L.NEWTON_F_GENERIC if self.force_generic else 0) | (L.NEWTON_F_ONE_PASS if self.one_pass else 0) | (L.NEWTON_F_STREAM if self.stream else 0) | (L.NEWTON_F_QUEUE if self.queue else 0) | (L.NEWTON_F_CTA if self.cta else 0)
                         | ((0 if self.defer_after is None else (255 if self.defer_after == 0 else
                                                                min(int(self.defer_after), 254))) << 8),

@@ -59,9 +59,8 @@ def run_primal_pass(model: SmallElasticPlastic, F: np.ndarray, num_steps: int,
     device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     kw = dict(newton_kwargs or {})
     newton = NewtonSettings(mode="imperative", max_iters=kw.pop("max_iters", 10),
-                            abs_tol=kw.pop("abs_tol", 1e-14), rel_tol=kw.pop("rel_tol", 1e-14))
-    if kw.pop("max_ls_evals", 0):
-        raise NotImplementedError("the legacy line search of newton_solve (max_ls_evals > 0) is not on the B200 path")
+                            abs_tol=kw.pop("abs_tol", 1e-14), rel_tol=kw.pop("rel_tol", 1e-14),
+                            max_ls_evals=int(kw.pop("max_ls_evals", 0)))     # legacy line search of newton_solve
     if kw:
         raise ValueError(f"unknown newton_kwargs {sorted(kw)}")
     B, n_xi, dt = Fb.shape[0], model.num_dofs, _LIB_DEF_TYPE[model._def_type]

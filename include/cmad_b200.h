@@ -131,7 +131,10 @@ typedef struct cmadx_material {
 typedef struct cmadx_newton {
     int32_t mode;           /* CMADX_NEWTON_*                                  */
     int32_t max_iters;
-    int32_t ls_max_evals;   /* traced mode only; >= 1                          */
+    int32_t ls_max_evals;   /* traced: probes of the quadratic line search, >= 1;
+                               imperative: max_ls_evals of newton_solve's legacy line
+                               search (cmad/models/nonlinear_solver.py:55-81), 0 = none
+                               (the reference's default; cmadx_mp_update only)        */
     int32_t flags;          /* CMADX_NEWTON_F_* bits                           */
     double abs_tol, rel_tol;
     double ls_c1, ls_bmin, ls_bmax;

@@ -29,6 +29,8 @@ static inline unsigned __shfl_sync(unsigned, unsigned v, int) { return v; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline double __ldg(const double* p) { return *p; }
 static inline void __stcs(double* p, double v) { *p = v; }
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }   // one rounding, never fused
+static inline int __syncthreads_or(int p) { return p; }
 static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, sizeof d); return d; }
 static const struct { unsigned x, y, z; } threadIdx = {0u, 0u, 0u};
 

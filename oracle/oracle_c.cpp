@@ -478,7 +478,7 @@ inline void solve_point(const double* mat, const int* cfg, const double* sol,
         }
         nc = norm2(n, C);
     } else {
-        // imperative newton_solve, nonlinear_solver.py:14-85 (max_ls_evals = 0)
+        // imperative newton_solve, nonlinear_solver.py:14-85 (ls_max = its max_ls_evals, 0 = none)
         while (ii < max_iters && !converged) {
             residual(model, m, x, xp, gu, C);
             nc = norm2(n, C);
@@ -490,6 +490,26 @@ inline void solve_point(const double* mat, const int* cfg, const double* sol,
             for (int i = 0; i < n; ++i) delta[i] = -C[i];
             lu_solve(n, J, delta, 1);
             for (int i = 0; i < n; ++i) x[i] += delta[i];
+            if (ls_max > 0) {
+                // legacy line search, nonlinear_solver.py:55-81 (beta = 1e-4, eta = 0.5)
+                double Cj[7] = {0};
+                residual(model, m, x, xp, gu, Cj);
+                const double psi0 = 0.5 * nc * nc, dpsi0 = -2.0 * psi0;
+                int jj = 1;
+                double aj = 1.0, cj = norm2(n, Cj), psij = 0.5 * cj * cj;
+                while (psij >= (1.0 - 2.0 * 1e-4 * aj) * psi0) {
+                    const double ap = aj;
+                    aj = std::fmax(0.5 * aj, -(aj * aj * dpsi0) / (2.0 * (psij - psi0 - aj * dpsi0)));
+                    if (jj == ls_max) break;
+                    ++jj;
+                    const double da = aj - ap;
+                    for (int i = 0; i < n; ++i) x[i] += da * delta[i];
+                    residual(model, m, x, xp, gu, Cj);
+                    cj = norm2(n, Cj);
+                    psij = 0.5 * cj * cj;
+                    ++out.ls_evals;
+                }
+            }
             ++ii;
         }
     }

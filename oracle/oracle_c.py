@@ -86,7 +86,7 @@ def _leaf_path_to_pid(path: tuple, pair: tuple) -> int | None:
 
 def describe(values: dict, active_idx=None, model: str = "small_elastic_plastic",
              newton_mode: str = "traced", max_iters: int = 10, abs_tol: float = 1e-14,
-             rel_tol: float = 1e-14, ls_max_evals: int = 4, c1: float = 1e-4,
+             rel_tol: float = 1e-14, ls_max_evals: int = 4, max_ls_evals: int = 0, c1: float = 1e-4,
              bmin: float = 0.5, bmax: float = 0.9, strain_comps: int = 6,
              yield_tol: float = 1e-14) -> OracleProblem:
     """Build the flat problem description from a reference-style parameter pytree
@@ -121,7 +121,8 @@ def describe(values: dict, active_idx=None, model: str = "small_elastic_plastic"
             mat[PID["LIN_K"]] = float(hd["linear"]["K"])
     mat[NUM_PID] = yield_tol
     cfg[4] = {"traced": 0, "imperative": 1}[newton_mode]
-    cfg[5], cfg[6], cfg[7] = max_iters, ls_max_evals, strain_comps
+    # traced: probes of the quadratic line search; imperative: newton_solve's legacy max_ls_evals (0 = none)
+    cfg[5], cfg[6], cfg[7] = max_iters, (ls_max_evals if newton_mode == "traced" else max_ls_evals), strain_comps
     sol = np.array([abs_tol, rel_tol, c1, bmin, bmax])
     # flat index -> pid
     pids = []

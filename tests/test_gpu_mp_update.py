@@ -149,14 +149,12 @@ def test_parity_hosford_a100_long_line_search(cuda_device):
     out = mp.mp_update(mat, nw, [], torch.zeros((7, n), dtype=torch.float64, device=cuda_device),
                        torch.from_numpy(e).to(cuda_device), outputs=("xi", "sigma", "dsig_deps", "iters", "flags", "cnorm"))
     ref = oc.mp_update(prob, np.zeros((7, n)), e, want=("xi", "sigma", "dsig_deps", "iters", "flags", "cnorm"))
-    it = out["iters"].cpu().numpy()
-    # a=100 is ill-conditioned: iteration paths amplify 1-ulp differences, so counts are
-    # compared statistically and values on the converged points only
-    conv = (ref["cnorm"] < 1e-12) & (out["cnorm"].cpu().numpy() < 1e-12)
-    assert conv.mean() > 0.9
-    assert np.mean(it == ref["iters"]) > 0.9
-    assert np.array_equal(out["flags"].cpu().numpy()[conv], ref["flags"][conv])
-    assert rel_err(out["sigma"].cpu().numpy()[:, conv], ref["sigma"][:, conv]) < 1e-8
+    # round 1 compared this batch statistically; counts and flags are in fact equal on every point
+    assert np.array_equal(out["iters"].cpu().numpy(), ref["iters"])
+    assert np.array_equal(out["flags"].cpu().numpy(), ref["flags"])
+    assert int(ref["iters"].max()) >= 8 and float(np.mean(ref["cnorm"] < 1e-12)) > 0.99
+    assert rel_err(out["xi"].cpu().numpy(), ref["xi"]) < 1e-9
+    assert rel_err(out["sigma"].cpu().numpy(), ref["sigma"]) < 1e-8
 
 
 def test_parity_elastic_model(cuda_device):
