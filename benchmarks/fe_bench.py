@@ -108,7 +108,11 @@ def main():
         ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
         return float(np.mean(ms)), float(np.min(ms))
 
-    base = {"family": args.family, "n_elems": n_e, "n_ips": n_e * n_ip, "yield": args.kind,
+    # algorithmic bytes of the block's actual rule (the table above holds the default rules)
+    n_b = arr.n_basis
+    rd = 24 * n_b + n_ip * n_b * 24 + n_ip * 8 + n_ip * 56
+    ALG_BYTES[args.family] = {"K3": rd + (3 * n_b) ** 2 * 8 + 24 * n_b + n_ip * 56, "K4": rd + 24 * n_b + n_ip * 56}
+    base = {"family": args.family, "n_ip": n_ip, "n_elems": n_e, "n_ips": n_e * n_ip, "yield": args.kind,
             "solver": "generic" if args.generic or args.kind != "J2" else "j2-radial",
             "steps": args.steps, "warmup": args.warmup, "setup_s": round(setup_s, 1), "hbm_peak_gbs": hbm}
     variants = args.variants.split(",")

@@ -20,6 +20,7 @@ SOURCES = ["api.cu", "mp_update.cu", "mp_update_stream.cu", "mp_update_queue.cu"
 
 # ---- enums (mirror include/cmad_b200.h) ---------------------------------
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(5)
+VERSION = 100        # CMADX_VERSION of include/cmad_b200.h this binding was written against
 MODEL_SMALL_ELASTIC_PLASTIC, MODEL_ELASTIC, MODEL_SMALL_RATE_ELASTIC_PLASTIC = 0, 1, 2
 YIELD_J2, YIELD_HILL, YIELD_HOSFORD = 0, 1, 2
 DEF_FULL_3D, DEF_PLANE_STRESS, DEF_UNIAXIAL_STRESS = 0, 1, 2
@@ -194,6 +195,16 @@ def lib() -> C.CDLL:
     L.cmadx_segment_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.cmadx_index_gather.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.cmadx_index_scatter.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    # a stale library (the .so is git-ignored and rebuilt by mtime) with a drifted struct layout
+    # would be driven with mis-laid-out structs: refuse it here instead of corrupting memory
+    if L.cmadx_version() != VERSION:
+        raise CmadxError(f"{LIB_PATH}: library version {L.cmadx_version()} != binding version {VERSION}; rebuild")
+    sizes = (C.c_int64 * 5)()
+    L.cmadx_struct_sizes(sizes)
+    want = [C.sizeof(t) for t in (Material, Newton, MpBuffers, MpHistory, FeBlock)]
+    if list(sizes) != want:
+        raise CmadxError(f"{LIB_PATH}: struct sizes {list(sizes)} != ctypes layout {want}; rebuild "
+                         "(`python -c 'import __graft_entry__ as g; g.build()'`)")
     _lib = L
     return L
 

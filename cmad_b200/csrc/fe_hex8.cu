@@ -36,7 +36,19 @@
 namespace cmadx {
 namespace {
 
+// K_e leaves the SM as ONE bulk copy per element (cp.async.bulk shared -> global, 4608 B, issued
+// by the element's first lane; SASS: UBLKCP): the tile is dense (node blocks 72 doubles apart -
+// the block-wise 64-bit writes are conflict-free at this stride too, 162 wavefronts per warp;
+// it was the 128-bit READ-BACK of the register path that needed the 74-double padding) and the
+// 36 LDS.128 + 18 STG.256 per thread of the read-back loop, with their staging registers, are
+// gone.  -DCMADX_HEX8_NO_BULK_STORE restores the register path (A/B measurements).
+#ifdef CMADX_HEX8_NO_BULK_STORE
+constexpr bool HEX_BULK_STORE = false;
 constexpr int HEX_TILE_STRIDE = 74;               // 72 + 2: 37 x 16 B, odd
+#else
+constexpr bool HEX_BULK_STORE = true;
+constexpr int HEX_TILE_STRIDE = 72;
+#endif
 constexpr int HEX_EPB = FE_BLOCK / 8;             // elements per block
 
 // Layout constants.  K3 (WANT_K): as described above, 76 KB per block -> 3 blocks / SM.
@@ -278,6 +290,18 @@ CMADX_DEV void hex8_point(const FeArgs& A, const int64_t e, const bool live, dou
                     }
             }
         }
+        if constexpr (HEX_BULK_STORE) {
+            // generic-proxy writes of the tile -> visible to the async proxy, then one bulk copy
+            // per element; the group is waited for (source read) before the region is reused
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (emit && ip == 0) {
+                const unsigned src = (unsigned)__cvta_generic_to_shared(tile);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(b.K_elem + e * 576), "r"(src), "n"(576 * 8) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
         __syncwarp();
         if (emit) {
             // K_e = 144 chunks of 32 B; lane t stores chunk c*8 + t.  Chunk s lives in node
@@ -293,6 +317,7 @@ CMADX_DEV void hex8_point(const FeArgs& A, const int64_t e, const bool live, dou
                 st256(Ke + 4 * s, hi ? v.x : u.x, hi ? v.y : u.y, hi ? u.x : v.x, hi ? u.y : v.y);
             }
         }
+        }
     }
     if (emit && want_R) {
         if (b.R_elem) {
@@ -303,6 +328,11 @@ CMADX_DEV void hex8_point(const FeArgs& A, const int64_t e, const bool live, dou
 #pragma unroll
             for (int i = 0; i < 3; ++i) atomicAdd(b.R_global + eq3[i], Racc[i]);
         }
+    }
+    if constexpr (WANT_K && HEX_BULK_STORE) {
+        // the tile must stay intact until the copy engine has read it (block exit / next list item)
+        if (emit && ip == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
     }
 }
 

@@ -8,6 +8,8 @@
 // element).  Row r of K_e ends up on lane r mod 4, so after every group of four rows each lane
 // streams one 96-byte row out as three 256-bit stores: K_e is written exactly once (the
 // any-rule kernel of fe_generic.cu makes n_ip passes over it).
+#include <cstdlib>
+
 #include "fe_common.cuh"
 
 namespace cmadx {
@@ -19,8 +21,24 @@ CMADX_DEV double quad_sum(double v) {          // sum over the 4 lanes of an ele
     return v;
 }
 
-template <int SOLVER, bool ROT, bool WANT_K>
-__global__ void __launch_bounds__(FE_BLOCK, (SOLVER == 0) ? 3 : 1) fe_tet4x4_kernel(const __grid_constant__ FeArgs A) {
+// Reduce-scatter over the 4 lanes of an element: every lane contributes v[0..3], lane l returns
+// sum over the lanes of v[l] - 3 shuffles for 4 sums (the butterfly all-reduce of each value takes
+// 8), with the butterfly's association ((v_l + v_{l^1}) + (v_{l^2} + v_{l^3})): bit-identical.
+CMADX_DEV double quad_reduce_scatter(const double (&v)[4], const int ip) {
+    const bool b0 = ip & 1, b1 = ip & 2;
+    double ka = b0 ? v[1] : v[0], kb = b0 ? v[3] : v[2];
+    ka += __shfl_xor_sync(0xffffffffu, b0 ? v[0] : v[1], 1);
+    kb += __shfl_xor_sync(0xffffffffu, b0 ? v[2] : v[3], 1);
+    const double keep = b1 ? kb : ka;
+    return keep + __shfl_xor_sync(0xffffffffu, b1 ? ka : kb, 2);
+}
+
+// FLAT: the three row groups unrolled (D and grad_N stay in registers - the rolled loop indexes
+// them dynamically, i.e. through local memory) at 254 registers, 2 blocks / SM.  Measured (3.07 M
+// tets, B200, profiles/r2p_fe.jsonl): rolled 2.93 ms, flat 2.69 ms -> flat is the J2 default
+// (CMADX_TET4X4_ROLLED=1 selects the rolled kernel).
+template <int SOLVER, bool ROT, bool WANT_K, bool FLAT = false>
+__global__ void __launch_bounds__(FE_BLOCK, (SOLVER == 0) ? (FLAT ? 2 : 3) : 1) fe_tet4x4_kernel(const __grid_constant__ FeArgs A) {
     const cmadx_fe_block_t& b = A.b;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t e = t >> 2;
@@ -86,17 +104,19 @@ __global__ void __launch_bounds__(FE_BLOCK, (SOLVER == 0) ? 3 : 1) fe_tet4x4_ker
     }
     // ---- R_e: this point's contribution, summed over the element's 4 lanes; lane a keeps node a
     if (b.R_elem || b.R_global) {
-        double mine[3] = {0.0, 0.0, 0.0};
+        double mine[3];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int i = 0; i < 3; ++i) {
+            double v[4];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
+            for (int a = 0; a < 4; ++a) {
                 double s = 0.0;
 #pragma unroll
                 for (int j = 0; j < 3; ++j) s = fma(gN[a][j], o.sg[vix(j, i)], s);
-                s = quad_sum(s * wdv);
-                if (a == ip) mine[i] = s;
+                v[a] = s * wdv;
             }
+            mine[i] = quad_reduce_scatter(v, ip);
+        }
         if (emit) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
@@ -111,31 +131,34 @@ __global__ void __launch_bounds__(FE_BLOCK, (SOLVER == 0) ? 3 : 1) fe_tet4x4_ker
 #pragma unroll
             for (int be = 0; be < 6; ++be) D[al][be] *= is_diag(be) ? wdv : 0.5 * wdv;
         double* Ke = b.K_elem + el * 144;
-#pragma unroll 1
+#pragma unroll (FLAT ? 3 : 1)
         for (int g4 = 0; g4 < 3; ++g4) {             // rows 4 g4 .. 4 g4 + 3
-            double keep[12];
+            double keep[12], P[4][6];
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
                 const int r = 4 * g4 + rr, a = r / 3, i = r - 3 * a;
-                double P[6];
 #pragma unroll
                 for (int be = 0; be < 6; ++be) {
                     double s = 0.0;
 #pragma unroll
                     for (int j = 0; j < 3; ++j) s = fma(gN[a][j], D[vix(j, i)][be], s);
-                    P[be] = s;
+                    P[rr][be] = s;
                 }
+            }
 #pragma unroll
-                for (int bb = 0; bb < 4; ++bb)
+            for (int bb = 0; bb < 4; ++bb)
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
+                for (int k = 0; k < 3; ++k) {
+                    double v[4];
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
                         double s = 0.0;
 #pragma unroll
-                        for (int l = 0; l < 3; ++l) s = fma(P[vix(k, l)], gN[bb][l], s);
-                        s = quad_sum(s);
-                        if (rr == ip) keep[3 * bb + k] = s;
+                        for (int l = 0; l < 3; ++l) s = fma(P[rr][vix(k, l)], gN[bb][l], s);
+                        v[rr] = s;
                     }
-            }
+                    keep[3 * bb + k] = quad_reduce_scatter(v, ip);
+                }
             if (emit) {
                 double* r = Ke + (4 * g4 + ip) * 12;
                 st256(r, keep[0], keep[1], keep[2], keep[3]);
@@ -154,7 +177,9 @@ struct Tet4x4Launcher {
         } else {
             const int64_t nthr = A.b.n_elems * 4;
             const int64_t nblk = (nthr + FE_BLOCK - 1) / FE_BLOCK;
-            fe_tet4x4_kernel<SOLVER, ROT, WANT_K><<<(unsigned)nblk, FE_BLOCK, 0, stream>>>(A);
+            static const bool flat = std::getenv("CMADX_TET4X4_ROLLED") == nullptr;
+            if (SOLVER == 0 && !ROT && WANT_K && flat) fe_tet4x4_kernel<SOLVER, ROT, WANT_K, SOLVER == 0 && !ROT && WANT_K><<<(unsigned)nblk, FE_BLOCK, 0, stream>>>(A);
+            else fe_tet4x4_kernel<SOLVER, ROT, WANT_K><<<(unsigned)nblk, FE_BLOCK, 0, stream>>>(A);
             return cudaGetLastError();
         }
     }

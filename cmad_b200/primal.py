@@ -132,8 +132,11 @@ def write_xi(out_dir, prefix: str, xi_trajectory: Sequence[Sequence[np.ndarray]]
 
 
 def write_solver_log(out_dir, prefix: str, solver_log) -> None:
+    # batched runs carry arrays per step (one entry per experiment): lists in the JSON
+    plain = [{k: (np.asarray(v).tolist() if isinstance(v, (np.ndarray, np.generic)) else v) for k, v in s.items()}
+             for s in solver_log]
     with (Path(out_dir) / f"{prefix}solver.json").open("w") as f:
-        json.dump(solver_log, f, indent=2)
+        json.dump(plain, f, indent=2)
 
 
 def write_J(out_dir, prefix: str, J: float) -> None:

@@ -516,8 +516,8 @@ def test_fe_two_pass_deferral_keeps_iterates_and_counts(cuda_device, family):
     for K in (1, None, 4):
         o = fe.fe_block_launch(mat, fe.fe_newton_settings(defer_after=K, **kw), arr, U, xi0, outs)
         torch.cuda.synchronize()
-        for k in outs:      # same iterates / counts / flags; K_e of the two launches agrees to rounding
-            if k in ("xi", "iters", "flags"):
+        for k in outs:      # same counts / flags; iterates, R_e, K_e of the two launches agree to rounding
+            if k in ("iters", "flags"):     # (separately compiled instantiations: FMA contraction may differ)
                 assert torch.equal(o[k], base[k]), (family, K, k)
             else:
                 assert rel_err(o[k].cpu().numpy(), base[k].cpu().numpy()) < 1e-12, (family, K, k)
