@@ -15,8 +15,8 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "lib", "libcmad_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
-SOURCES = ["api.cu", "mp_update.cu", "mp_update_stream.cu", "mp_update_queue.cu", "mp_update_cta.cu", "mp_update_j2.cu", "mp_update_dt.cu", "mp_update_rate.cu", "elastic_update.cu", "mp_sens.cu", "mp_sens_dt.cu", "mp_hess.cu", "mp_history.cu",
-           "fe_block.cu", "fe_tet4.cu", "fe_hex8.cu", "fe_generic.cu", "fe_tet4x4.cu", "fe_mixed.cu", "fe_post.cu", "fe_vjp.cu", "fe_scatter.cu"]
+SOURCES = ["api.cu", "mp_update.cu", "mp_update_stream.cu", "mp_update_queue.cu", "mp_update_cta.cu", "mp_update_j2.cu", "mp_update_dt.cu", "mp_update_rate.cu", "elastic_update.cu", "mp_sens.cu", "mp_sens_dt.cu", "mp_sens_rate.cu", "mp_hess.cu", "mp_history.cu",
+           "fe_block.cu", "fe_tet4.cu", "fe_hex8.cu", "fe_generic.cu", "fe_tet4x4.cu", "fe_rate.cu", "fe_mixed.cu", "fe_post.cu", "fe_vjp.cu", "fe_scatter.cu"]
 
 # ---- enums (mirror include/cmad_b200.h) ---------------------------------
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(5)
@@ -60,7 +60,7 @@ class MpBuffers(C.Structure):
                 ("xi", C.c_void_p), ("sigma", C.c_void_p), ("dsig_deps", C.c_void_p),
                 ("dxi_deps", C.c_void_p), ("dC_dp", C.c_void_p), ("dC_dxi", C.c_void_p),
                 ("dC_dxi_prev", C.c_void_p), ("iters", C.c_void_p), ("flags", C.c_void_p),
-                ("cnorm", C.c_void_p), ("C", C.c_void_p)]
+                ("cnorm", C.c_void_p), ("C", C.c_void_p), ("strain_prev", C.c_void_p)]
 
 
 class MpHistory(C.Structure):
@@ -76,7 +76,7 @@ class FeBlock(C.Structure):
                 ("xi_prev", C.c_void_p), ("grad_N", C.c_void_p), ("det", C.c_void_p),
                 ("quad_w", C.c_void_p), ("xi", C.c_void_p), ("R_elem", C.c_void_p),
                 ("K_elem", C.c_void_p), ("R_global", C.c_void_p), ("sigma", C.c_void_p),
-                ("iters", C.c_void_p), ("flags", C.c_void_p)]
+                ("iters", C.c_void_p), ("flags", C.c_void_p), ("U_prev", C.c_void_p)]
 
 
 class FeMixed(C.Structure):

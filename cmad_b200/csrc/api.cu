@@ -42,6 +42,8 @@ struct HistArgs {
 cudaError_t launch_mp_history(const HistArgs& A, bool radial, cudaStream_t s);
 cudaError_t launch_mp_sens(const SensArgs& A, bool adjoint, cudaStream_t stream);
 cudaError_t launch_mp_sens_dt(const SensArgs& A, int def_type, bool adjoint, cudaStream_t stream);
+cudaError_t launch_mp_sens_rate(const SensArgs& A, bool adjoint, cudaStream_t stream);
+cudaError_t launch_fe_rate(const FeArgs& A, cudaStream_t stream);
 int64_t sens_blocks(int64_t n);
 int64_t hess_blocks(int64_t n);
 cudaError_t launch_mp_hess(const SensArgs& A, int def_type, double* pair_sums, double* H_out, cudaStream_t stream);
@@ -601,10 +603,13 @@ static int history_n_xi(const cmadx_mp_history_t* h) { return 7 + history_def_ty
 static int check_history(const cmadx_material_t* mat, const cmadx_mp_history_t* h, DevMat* dm) {
     if (!h) return CMADX_EINVAL;
     if (int rc = make_dev_mat(mat, dm)) return rc;
-    if (dm->model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC) return CMADX_EUNSUPPORTED;
+    const bool rate = dm->model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC;
+    if (dm->model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC && !rate) return CMADX_EUNSUPPORTED;
     if (h->n < 0 || h->ld < h->n || h->nsteps < 0) return CMADX_EINVAL;
     const int sc = h->strain_comps;
     if (sc != 6 && sc != 9 && sc != 3 && sc != 4 && sc != 1) return CMADX_EINVAL;
+    // the rate model: FULL_3D with identity material axes (mp_update_rate.cu, mp_sens_rate.cu)
+    if (rate && ((sc != 6 && sc != 9) || dm->rot)) return CMADX_EUNSUPPORTED;
     if (history_def_type(h) != CMADX_DEF_FULL_3D && dm->rot) return CMADX_EUNSUPPORTED;
     if (h->n > 0 && (!h->strain || !h->xi_hist)) return CMADX_EINVAL;
     return CMADX_OK;
@@ -620,7 +625,8 @@ int cmadx_mp_forward_history(const cmadx_material_t* mat, const cmadx_newton_t* 
     if (newton && newton->mode == CMADX_NEWTON_IMPERATIVE && newton->ls_max_evals > 0)
         return CMADX_EUNSUPPORTED;       // the legacy line search lives in cmadx_mp_update only
     const bool j2_radial = dm.yield == CMADX_YIELD_J2 && newton && !(newton->flags & CMADX_NEWTON_F_GENERIC);
-    if (history_def_type(hist) == CMADX_DEF_FULL_3D && !dm.rot && hist->n < (int64_t)0x7fffffff &&
+    const bool rate = dm.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC;
+    if (!rate && history_def_type(hist) == CMADX_DEF_FULL_3D && !dm.rot && hist->n < (int64_t)0x7fffffff &&
         (j2_radial || hist->n <= 32768) && !std::getenv("CMADX_HISTORY_PER_STEP")) {
         // fused path: one launch for the whole history (mp_history.cu)
         HistArgs A;
@@ -654,6 +660,8 @@ int cmadx_mp_forward_history(const cmadx_material_t* mat, const cmadx_newton_t* 
         b.xi_prev = hist->xi_hist + (int64_t)(t - 1) * nxi * hist->ld;
         b.xi = hist->xi_hist + (int64_t)t * nxi * hist->ld;
         b.strain = hist->strain + (int64_t)t * hist->strain_comps * hist->ld;
+        // the rate model's residual sees eps_t - eps_{t-1}: the history carries total strains
+        if (rate) b.strain_prev = hist->strain + (int64_t)(t - 1) * hist->strain_comps * hist->ld;
         b.iters = hist->iters_hist ? hist->iters_hist + (int64_t)t * hist->ld : nullptr;
         if (int rc = cmadx_mp_update(mat, newton, nullptr, 0, &b, stream)) return rc;
     }
@@ -679,8 +687,9 @@ static int objective(const cmadx_material_t* mat, const int32_t* active_pid, int
     A.phi_hist = nullptr;
     A.hess_flags = 0;
     const int dt = history_def_type(hist);
-    cudaError_t e = (dt == CMADX_DEF_FULL_3D) ? launch_mp_sens(A, adjoint, (cudaStream_t)stream)
-                                              : launch_mp_sens_dt(A, dt, adjoint, (cudaStream_t)stream);
+    cudaError_t e = (A.m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC) ? launch_mp_sens_rate(A, adjoint, (cudaStream_t)stream)
+                    : (dt == CMADX_DEF_FULL_3D) ? launch_mp_sens(A, adjoint, (cudaStream_t)stream)
+                                                : launch_mp_sens_dt(A, dt, adjoint, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     g_launches.fetch_add(2, std::memory_order_relaxed);
     return CMADX_OK;
@@ -717,7 +726,7 @@ int cmadx_mp_objective_hessian(const cmadx_material_t* mat, const int32_t* activ
     if (flags & ~CMADX_HESS_F_REFERENCE_QOI_CROSS) return CMADX_EINVAL;
     A.hess_flags = flags;
     if (int rc = check_history(mat, hist, &A.m)) return rc;
-    if (A.m.rot) return CMADX_EUNSUPPORTED;
+    if (A.m.rot || A.m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC) return CMADX_EUNSUPPORTED;
     const int dt = history_def_type(hist);
     if (n_active < 0 || n_active > CMADX_MAX_ACTIVE || (n_active > 0 && !active_pid)) return CMADX_EINVAL;
     if (!hist->result || !hist->workspace || (hist->n > 0 && !hist->data)) return CMADX_EINVAL;
@@ -742,10 +751,15 @@ int cmadx_mp_objective_hessian(const cmadx_material_t* mat, const int32_t* activ
     return CMADX_OK;
 }
 
-static int check_fe_block(const cmadx_material_t* mat, const cmadx_fe_block_t* blk, FeArgs* A) {
+static int check_fe_block(const cmadx_material_t* mat, const cmadx_fe_block_t* blk, FeArgs* A,
+                          bool allow_rate = false) {
     if (!blk) return CMADX_EINVAL;
     if (int rc = make_dev_mat(mat, &A->m)) return rc;
-    if (A->m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC) return CMADX_EUNSUPPORTED;
+    if (A->m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC) {
+        // K3 / K4 only (fe_rate.cu), identity material axes; needs the previous displacement vector
+        if (!allow_rate || A->m.rot) return CMADX_EUNSUPPORTED;
+        if (blk->n_elems > 0 && !blk->U_prev) return CMADX_EINVAL;
+    } else if (A->m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC) return CMADX_EUNSUPPORTED;
     const cmadx_fe_block_t& b = *blk;
     if (b.n_elems < 0 || b.n_dofs < 0) return CMADX_EINVAL;
     // tet4 / hex8 with any volume rule (cmad/cli/common.py:497-540: up to 24 / 64 points); the
@@ -769,7 +783,7 @@ static int check_fe_block(const cmadx_material_t* mat, const cmadx_fe_block_t* b
 static int fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* newton,
                              const cmadx_fe_block_t* blk, const cmadx_fe_mixed_t* mix, void* stream) {
     FeArgs A;
-    if (int rc = check_fe_block(mat, blk, &A)) return rc;
+    if (int rc = check_fe_block(mat, blk, &A, true)) return rc;
     if (int rc = make_dev_newton(newton, &A.nw)) return rc;
     if (A.nw.mode == CMADX_NEWTON_IMPERATIVE && A.nw.ls_max > 0) return CMADX_EUNSUPPORTED;
     default_defer(A.m, &A.nw);
@@ -788,6 +802,16 @@ static int fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* 
     if (b.n_elems == 0) return CMADX_OK;
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e;
+    if (A.m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC) {
+        // the rate form: one kernel for every rule (fe_rate.cu).  Its mixed u-p form is not carried:
+        // hydro_cauchy is tr(cauchy(xi)) / 3 there (small_rate_elastic_plastic.py:369-376), so the
+        // pressure rows depend on the local state - not the state-free pressure block of fe_mixed.cu
+        if (mix) return CMADX_EUNSUPPORTED;
+        e = launch_fe_rate(A, s);
+        if (e != cudaSuccess) return cuda_fail(e);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return CMADX_OK;
+    }
     const bool default_rule = (b.n_basis == 4 && b.n_ip == 1) || (b.n_basis == 8 && b.n_ip == 8);
     const bool tuned = default_rule || (b.n_basis == 4 && b.n_ip == 4);       // + fe_tet4x4.cu
     const bool radial = tuned && A.m.yield == CMADX_YIELD_J2 && !A.m.rot &&

@@ -33,12 +33,13 @@ CMADX_DEV double quad_reduce_scatter(const double (&v)[4], const int ip) {
     return keep + __shfl_xor_sync(0xffffffffu, b1 ? ka : kb, 2);
 }
 
-// FLAT: the three row groups unrolled (D and grad_N stay in registers - the rolled loop indexes
-// them dynamically, i.e. through local memory) at 254 registers, 2 blocks / SM.  Measured (3.07 M
-// tets, B200, profiles/r2p_fe.jsonl): rolled 2.93 ms, flat 2.69 ms -> flat is the J2 default
-// (CMADX_TET4X4_ROLLED=1 selects the rolled kernel).
-template <int SOLVER, bool ROT, bool WANT_K, bool FLAT = false>
-__global__ void __launch_bounds__(FE_BLOCK, (SOLVER == 0) ? (FLAT ? 2 : 3) : 1) fe_tet4x4_kernel(const __grid_constant__ FeArgs A) {
+// FACTORED (the J2 radial kernel, which always runs with the element hand-back list): only the
+// factored path below is compiled in - an element whose grad_N is not the same at its 4 points is
+// handed to the any-rule kernel like a radial-return bail - so the kernel stays lean.  Measured
+// (3.07 M tets, B200): per-point products, rolled row groups 2.93 ms, unrolled 2.69 ms
+// (profiles/r2p_fe.jsonl); factored: see DESIGN.md.  CMADX_TET4X4_GENERAL=1 selects the per-point kernel.
+template <int SOLVER, bool ROT, bool WANT_K, bool FACTORED = false>
+__global__ void __launch_bounds__(FE_BLOCK, (SOLVER == 0) ? (FACTORED ? 4 : 3) : 1) fe_tet4x4_kernel(const __grid_constant__ FeArgs A) {
     const cmadx_fe_block_t& b = A.b;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t e = t >> 2;
@@ -77,9 +78,16 @@ __global__ void __launch_bounds__(FE_BLOCK, (SOLVER == 0) ? (FLAT ? 2 : 3) : 1) 
     solve_point<SOLVER, ROT, WANT_K>(A.m, nw, xp, eps, live, o, D);
 
     // an element is handed to the generic second pass as a whole
+    // one grad_N per element?  (bit-equal across the element's 4 points)
+    bool uniform = true;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            uniform = uniform && (gN[a][k] == __shfl_sync(0xffffffffu, gN[a][k], (threadIdx.x & 31) & ~3));
     bool ebail = false;
     if (SOLVER == 0) {
-        const unsigned bal = __ballot_sync(0xffffffffu, live && o.bail);
+        const unsigned bal = __ballot_sync(0xffffffffu, live && (o.bail || (FACTORED && !uniform)));
         ebail = ((bal >> ((threadIdx.x & 31) & ~3)) & 0xfu) != 0u;
         if (ebail && live && ip == 0 && A.bail_count) append_bail(A, e);
     }
@@ -102,6 +110,58 @@ __global__ void __launch_bounds__(FE_BLOCK, (SOLVER == 0) ? (FLAT ? 2 : 3) : 1) 
                                   fma(__ldg(Np + 1), __ldg(b.U + qp.y), __ldg(Np) * __ldg(b.U + qp.x))));
         mixed_momentum_stress<WANT_K>(pr, o.sg, D);
     }
+    // ---- Linear tets have ONE grad_N per element (constant Jacobian): the per-point sums then factor,
+    //   R_e = B^T (sum_ip sigma w dv),   K_e = B^T (sum_ip Dh w dv) B,
+    // so the 4 lanes all-reduce sigma w dv (6 values) and Dh w dv (36 values) and lane a forms rows
+    // 3a..3a+2 of R_e / K_e from the sums: a quarter of the FP64 work of the per-point products and
+    // no reduction of the 144 K_e entries (ncu on the per-point version: 3072 instructions per warp,
+    // 38 % of the issue slots at 8 warps / SM - latency-bound).  The kernel checks the premise on the
+    // data it was given (bit-equal grad_N across the 4 points of every element of the warp) and keeps
+    // the general per-point path otherwise.
+    if (FACTORED || __all_sync(0xffffffffu, uniform || !live)) {
+        double ga[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) ga[j] = (ip == 0) ? gN[0][j] : ((ip == 1) ? gN[1][j] : ((ip == 2) ? gN[2][j] : gN[3][j]));
+        if (b.R_elem || b.R_global) {
+            double sw[6];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) sw[a] = quad_sum(o.sg[a] * wdv);
+            if (emit) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const double r = fma(ga[2], sw[vix(2, i)], fma(ga[1], sw[vix(1, i)], ga[0] * sw[vix(0, i)]));
+                    if (b.R_elem) b.R_elem[e * 12 + 3 * ip + i] = r;
+                    if (b.R_global) atomicAdd(b.R_global + eq[3 * ip + i], r);
+                }
+            }
+        }
+        if constexpr (WANT_K) {
+#pragma unroll
+            for (int al = 0; al < 6; ++al)
+#pragma unroll
+                for (int be = 0; be < 6; ++be) D[al][be] = quad_sum(D[al][be] * (is_diag(be) ? wdv : 0.5 * wdv));
+            double* Ke = b.K_elem + el * 144 + 36 * ip;          // rows 3 ip .. 3 ip + 2
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                double P[6], row[12];
+#pragma unroll
+                for (int be = 0; be < 6; ++be)
+                    P[be] = fma(ga[2], D[vix(2, i)][be], fma(ga[1], D[vix(1, i)][be], ga[0] * D[vix(0, i)][be]));
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        row[3 * bb + k] = fma(P[vix(k, 2)], gN[bb][2], fma(P[vix(k, 1)], gN[bb][1], P[vix(k, 0)] * gN[bb][0]));
+                if (emit) {
+                    st256(Ke + 12 * i, row[0], row[1], row[2], row[3]);
+                    st256(Ke + 12 * i + 4, row[4], row[5], row[6], row[7]);
+                    st256(Ke + 12 * i + 8, row[8], row[9], row[10], row[11]);
+                }
+            }
+        }
+        return;
+    }
+    if constexpr (!FACTORED) {
     // ---- R_e: this point's contribution, summed over the element's 4 lanes; lane a keeps node a
     if (b.R_elem || b.R_global) {
         double mine[3];
@@ -131,7 +191,7 @@ __global__ void __launch_bounds__(FE_BLOCK, (SOLVER == 0) ? (FLAT ? 2 : 3) : 1) 
 #pragma unroll
             for (int be = 0; be < 6; ++be) D[al][be] *= is_diag(be) ? wdv : 0.5 * wdv;
         double* Ke = b.K_elem + el * 144;
-#pragma unroll (FLAT ? 3 : 1)
+#pragma unroll 1
         for (int g4 = 0; g4 < 3; ++g4) {             // rows 4 g4 .. 4 g4 + 3
             double keep[12], P[4][6];
 #pragma unroll
@@ -167,6 +227,7 @@ __global__ void __launch_bounds__(FE_BLOCK, (SOLVER == 0) ? (FLAT ? 2 : 3) : 1) 
             }
         }
     }
+    }   // !FACTORED
 }
 
 template <int SOLVER, bool ROT, bool WANT_K, bool LIST>
@@ -177,8 +238,8 @@ struct Tet4x4Launcher {
         } else {
             const int64_t nthr = A.b.n_elems * 4;
             const int64_t nblk = (nthr + FE_BLOCK - 1) / FE_BLOCK;
-            static const bool flat = std::getenv("CMADX_TET4X4_ROLLED") == nullptr;
-            if (SOLVER == 0 && !ROT && WANT_K && flat) fe_tet4x4_kernel<SOLVER, ROT, WANT_K, SOLVER == 0 && !ROT && WANT_K><<<(unsigned)nblk, FE_BLOCK, 0, stream>>>(A);
+            static const bool factored = std::getenv("CMADX_TET4X4_GENERAL") == nullptr;
+            if (SOLVER == 0 && !ROT && factored && A.bail_count) fe_tet4x4_kernel<SOLVER, ROT, WANT_K, SOLVER == 0 && !ROT><<<(unsigned)nblk, FE_BLOCK, 0, stream>>>(A);
             else fe_tet4x4_kernel<SOLVER, ROT, WANT_K><<<(unsigned)nblk, FE_BLOCK, 0, stream>>>(A);
             return cudaGetLastError();
         }

@@ -200,6 +200,19 @@ CMADX_DEV double hosford_pow(double r, double a, int a_int) {
     return res;
 }
 
+// s^(1/a) for s > 0, the outer root of the Hosford norm.  libm's pow was 13 % of all instructions
+// of the a = 4 kernel (ncu, profiles/r2g_k1_hosford_4_flops.txt): two correctly rounded square
+// roots for a = 4, one for a = 2, exp(log(s) / a) for the other integer exponents (|log s| < 15 and
+// 1/a <= 1/3: the argument error is far below one ulp of the result, which then carries exp's own
+// rounding), libm pow otherwise.  Same value as pow to an ulp or two; iteration counts of every
+// parity fixture unchanged.
+CMADX_DEV double hosford_root(double s, double inv_a, int a_int) {
+    if (a_int == 4) return sqrt(sqrt(s));
+    if (a_int == 2) return sqrt(s);
+    if (a_int > 2) return exp(inv_a * log(s));
+    return pow(s, inv_a);
+}
+
 // Hosford: phi = vm * (1/2 sum_i |Delta_i/vm|^a)^(1/a) on the *diagonal* stress
 // entries only (the reference's documented limitation).  The vm scaling cancels
 // analytically (phi is the plain a-norm of the differences); it is kept for the
@@ -224,7 +237,7 @@ template <> struct YieldFn<CMADX_YIELD_HOSFORD> {
 #pragma unroll
         for (int i = 0; i < 3; ++i) { q[i] = hosford_pow(fabs(dl[i] * ivm), a, m.a_int); sq += q[i]; }
         sq *= 0.5;
-        phi = vm * pow(sq, m.inv_a);
+        phi = vm * hosford_root(sq, m.inv_a, m.a_int);
         iphi = 1.0 / phi;
         am1 = a - 1.0;
         const double isq = 1.0 / sq;

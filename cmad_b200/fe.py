@@ -101,8 +101,9 @@ class SegmentPlan:
             pass
 
 
-def _fe_struct(arrays: FEBlockArrays, U, xi_prev, out: dict) -> L.FeBlock:
+def _fe_struct(arrays: FEBlockArrays, U, xi_prev, out: dict, U_prev=None) -> L.FeBlock:
     b = L.FeBlock()
+    b.U_prev = U_prev.data_ptr() if U_prev is not None else None
     b.n_elems, b.n_dofs = arrays.n_elems, arrays.n_dofs
     b.n_basis, b.n_ip = arrays.n_basis, arrays.n_ip
     b.elem_eq, b.U, b.xi_prev = arrays.elem_eq.data_ptr(), U.data_ptr(), xi_prev.data_ptr()
@@ -114,10 +115,13 @@ def _fe_struct(arrays: FEBlockArrays, U, xi_prev, out: dict) -> L.FeBlock:
 
 def fe_block_launch(material: L.Material, newton: NewtonSettings, arrays: FEBlockArrays,
                     U_global: torch.Tensor, xi_prev: torch.Tensor, outputs=("xi", "R_elem", "K_elem"),
-                    out: dict | None = None, stream: torch.cuda.Stream | None = None) -> dict:
+                    out: dict | None = None, stream: torch.cuda.Stream | None = None,
+                    U_prev: torch.Tensor | None = None) -> dict:
     """One K3/K4 launch over an element block (asynchronous on ``stream``).
     ``outputs`` ⊆ {xi, R_elem, K_elem, R_global, sigma, iters, flags}; ``R_global``
-    (atomic scatter-add) is zero-initialised here unless passed in through ``out``."""
+    (atomic scatter-add) is zero-initialised here unless passed in through ``out``.
+    ``U_prev``: the previous step's displacement vector, required by
+    ``small_rate_elastic_plastic`` blocks (their residual sees eps(U) - eps(U_prev))."""
     n_e, n_b, n_ip = arrays.n_elems, arrays.n_basis, arrays.n_ip
     dev = arrays.grad_N.device
     if dev.type != "cuda":
@@ -142,7 +146,10 @@ def fe_block_launch(material: L.Material, newton: NewtonSettings, arrays: FEBloc
             shape, dt = shapes[name]
             alloc = torch.zeros if name == "R_global" else torch.empty
             out[name] = alloc(shape, dtype=dt, device=dev)
-    b = _fe_struct(arrays, U_global, xi_prev, out)
+    if U_prev is not None and (U_prev.dtype != torch.float64 or U_prev.numel() != arrays.n_dofs
+                               or not U_prev.is_contiguous() or U_prev.device != dev):
+        raise ValueError(f"U_prev: expected contiguous float64 ({arrays.n_dofs},) on {dev}")
+    b = _fe_struct(arrays, U_global, xi_prev, out, U_prev)
     nw = newton.to_struct()
     s = stream if stream is not None else torch.cuda.current_stream(dev)
     with torch.cuda.device(dev):
@@ -155,14 +162,14 @@ def fe_block_launch(material: L.Material, newton: NewtonSettings, arrays: FEBloc
 def assemble_element_block(material: L.Material, newton: NewtonSettings, arrays: FEBlockArrays,
                            U_global: torch.Tensor, xi_prev_per_block: torch.Tensor,
                            r_plan: SegmentPlan | None = None, out: dict | None = None,
-                           stream: torch.cuda.Stream | None = None):
+                           stream: torch.cuda.Stream | None = None, U_prev: torch.Tensor | None = None):
     """``(R_block, vals, xi_solved_per_block)`` of a COUPLED block, as the
     reference's ``assemble_element_block`` returns them: ``R_block (n_dofs,)``,
     ``vals`` = flattened ``(elem, row dof, col dof)`` COO data,
     ``xi_solved (n_e, n_ip, n_xi)``.  With ``r_plan`` (a :class:`SegmentPlan` over
     ``elem_eq.ravel()``) R is summed deterministically; otherwise by atomics."""
     outs = ("xi", "R_elem", "K_elem") if r_plan is not None else ("xi", "K_elem", "R_global")
-    o = fe_block_launch(material, newton, arrays, U_global, xi_prev_per_block, outs, out, stream)
+    o = fe_block_launch(material, newton, arrays, U_global, xi_prev_per_block, outs, out, stream, U_prev=U_prev)
     R = r_plan.sum(o["R_elem"].reshape(-1), stream=stream) if r_plan is not None else o["R_global"]
     return R, o["K_elem"].reshape(-1), o["xi"]
 

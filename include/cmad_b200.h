@@ -176,6 +176,12 @@ typedef struct cmadx_mp_buffers {
     int32_t* flags;         /* [n] bit0: plastic branch at x0, bit1: at x*     */
     double* cnorm;          /* [n] final ||C||_2                               */
     double* C;              /* [n_xi][ld]   residual at the returned xi        */
+    const double* strain_prev; /* [strain_comps][ld] or NULL.  small_rate_elastic_plastic only
+                               (its residual sees eps(U) - eps(U_prev),
+                               cmad/models/small_rate_elastic_plastic.py:41-51): NULL => the
+                               `strain` rows already carry the increment; non-NULL => `strain`
+                               and `strain_prev` are the total strains of this and the previous
+                               step and the increment is formed on the device        */
 } cmadx_mp_buffers_t;
 
 int cmadx_version(void);
@@ -333,6 +339,9 @@ typedef struct cmadx_fe_block {
                                 (evaluate_cauchy_at_ips, cmad/fem/postprocess.py:35-185) */
     int32_t* iters;          /* [n_elems][n_ip] or NULL                          */
     int32_t* flags;          /* [n_elems][n_ip] or NULL (bit0 entry, bit1 exit)  */
+    const double* U_prev;    /* [n_dofs] displacement vector of the previous step: required by
+                                small_rate_elastic_plastic blocks (their residual sees
+                                eps(U) - eps(U_prev)), ignored (may be NULL) otherwise */
 } cmadx_fe_block_t;
 
 int cmadx_fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* newton,

@@ -197,10 +197,14 @@ def _imperative_job(job):
 #  C. MP adjoint / direct objectives with the Calibration QoI                 #
 # --------------------------------------------------------------------------- #
 def _objective_job(job):
-    kind, scaled, F, weight = job
+    kind, scaled, F, weight = job[:4]
     values, act, tr = objective_trees(kind, scaled)
     P = Parameters(values, act, tr)
-    model = SmallElasticPlastic(P)
+    if len(job) > 4 and job[4] == "rate":       # the rate form under the same objectives
+        from cmad.models.small_rate_elastic_plastic import SmallRateElasticPlastic
+        model = SmallRateElasticPlastic(P)
+    else:
+        model = SmallElasticPlastic(P)
     N = F.shape[2] - 1
     # data: the stress history at the "true" parameters (test_J2_fd_checks.py:21-47)
     data = np.zeros((3, 3, N + 1))
@@ -219,6 +223,13 @@ def _objective_job(job):
     res = {}
     for name, ctor in (("adjoint", MPAdjointObjective), ("direct", MPDirectObjective)):
         P.set_active_values_from_flat(offset, False)
+        if len(job) > 4 and job[4] == "rate":
+            # MPObjective.__init__ (mp_objective.py:46) stores the model's CURRENT xi as the step-0
+            # state of the adjoint pass.  After the data run above that is the final state of the
+            # data history, not the initial one the forward pass starts from; harmless for
+            # SmallElasticPlastic with an elastic first step (nothing there depends on xi_prev), but
+            # the rate form's dC/dp reads sig_prev: build the objective on a model at its initial state.
+            model.set_xi_to_init_vals()
         J, g = ctor(qoi, F).evaluate(x)
         res[f"J_{name}"], res[f"grad_{name}"] = float(J), np.asarray(g, float)
     res.update(F=F, data=data, weight=weight, x_canonical=x, active_native=offset,
@@ -306,11 +317,16 @@ def _fe_job(job):
     from cmad.global_residuals.small_disp_equilibrium import SmallDispEquilibrium
     from jax.flatten_util import ravel_pytree
 
-    family, kind, mixed, seed, n_elems = job
+    family, kind, mixed, seed, n_elems = job[:5]
+    rate = len(job) > 5 and job[5] == "rate"
     rng = np.random.default_rng(seed)
     values = material(kind)
     P = parameters(values)
-    model = SmallElasticPlastic(P)
+    if rate:
+        from cmad.models.small_rate_elastic_plastic import SmallRateElasticPlastic
+        model = SmallRateElasticPlastic(P)
+    else:
+        model = SmallElasticPlastic(P)
     gr = SmallDispEquilibrium(ndims=3, mixed=mixed, stabilization_multiplier=1.0)
     ev = gr.for_model(model, GlobalResidualMode.COUPLED)            # local Newton 20 / 1e-12 / 1e-12
     unravel_xi = ravel_pytree(model._init_xi)[1]
@@ -329,7 +345,7 @@ def _fe_job(job):
     block_shapes = [(n_b, 3), (n_b, 1)] if mixed else [(n_b, 3)]
     shared = BlockIPGeometryShared(quad_w=np.asarray(rule.w),
                                    field_N_per_block=tuple(N for _ in block_shapes))
-    rec = {k: [] for k in ("X", "U", "p", "xi_prev", "grad_N", "det", "h", "xi", "R_u", "R_p",
+    rec = {k: [] for k in ("X", "U", "U_prev", "p", "xi_prev", "grad_N", "det", "h", "xi", "R_u", "R_p",
                            "K_uu", "K_up", "K_pu", "K_pp", "R_only_u", "R_only_p")}
     for e in range(n_elems):
         X = Xref + rng.normal(size=Xref.shape) * 0.06               # distorted element
@@ -342,6 +358,7 @@ def _fe_job(job):
                                       field_grad_N_phys_per_block=tuple(gN for _ in block_shapes),
                                       element_size=h)
         xi_prev = np.zeros((n_ip, 7))
+        U_last = np.zeros_like(X)
         for step in range(2):
             ramp = np.array([0.004, -0.001, 0.0015]) if step == 0 else np.array([0.003, 0.004, -0.002])
             U = X * ramp[None, :] * (1.0 + step) + rng.normal(size=X.shape) * 4e-4
@@ -350,6 +367,9 @@ def _fe_job(job):
                 pe = rng.normal(size=(n_b, 1)) * 40.0 - 100.0
                 Ue = [U, pe]
             Uprev = [np.zeros_like(u) for u in Ue]
+            if rate:                   # the rate form sees eps(U) - eps(U_prev): carry the real previous step
+                Uprev = [U_last.copy()]
+            rec["U_prev"].append(Uprev[0].copy())
             Rb, Kb, xi = per_element_R_and_K_coupled(
                 Ue, Uprev, P.values, xi_prev, geom, shared, ev["R_and_dR_dU_and_xi"], unravel_xi,
                 {}, block_shapes, 0.0)
@@ -367,6 +387,7 @@ def _fe_job(job):
                 rec["K_pu"].append(np.asarray(Kb[1][0]).reshape(n_b, 3 * n_b))
                 rec["K_pp"].append(np.asarray(Kb[1][1]).reshape(n_b, n_b))
             xi_prev = np.asarray(xi)
+            U_last = U
     out = {k: np.array(v) for k, v in rec.items() if v}
     out["quad_w"], out["N"] = np.asarray(rule.w), N
     return out
@@ -653,6 +674,32 @@ def main():
             print("rate", kind, "iters", np.bincount(r["iters"]), "traced", np.bincount(r["traced_iters"]),
                   "alpha", r["xi"][-1, 6])
         np.savez_compressed(os.path.join(HERE, "ref_rate_model.npz"), **out)
+
+    if only is None or "rate_objective" in only:
+        # MPAdjointObjective / MPDirectObjective + Calibration over SmallRateElasticPlastic
+        w = np.array([[1.0, 0.5, 0.0], [0.5, 1.0, 0.0], [0.0, 0.0, 0.25]])
+        jobs, names = [], []
+        for kind in ("J2", "hill", "hosford"):
+            for scaled in (True, False):
+                jobs.append((kind, scaled, two_leg_F(11, 24, scale=1.5, diag_only=kind == "hosford"), w, "rate"))
+                names.append(f"{kind}.{'scaled' if scaled else 'native'}")
+        out = {}
+        for nm, r in zip(names, pool.map(_objective_job, jobs)):
+            for k, v in r.items():
+                out[f"{nm}.{k}"] = v
+            print("rate objective", nm, r["J_adjoint"], r["grad_adjoint"], r["grad_direct"])
+        np.savez_compressed(os.path.join(HERE, "ref_rate_objectives.npz"), **out)
+
+    if only is None or "rate_fe" in only:
+        # per_element_R_and_K_coupled over the rate form's per-IP COUPLED evaluator (displacement form)
+        jobs = [(fam, kind, False, 31 + i, 3, "rate")
+                for i, (fam, kind) in enumerate((("tet4", "J2"), ("hex8", "J2"), ("tet4", "hill"), ("hex8", "hosford")))]
+        out = {}
+        for job, r in zip(jobs, pool.map(_fe_job, jobs, chunksize=1)):
+            for k, v in r.items():
+                out[f"{job[0]}.{job[1]}.{k}"] = v
+            print("rate fe", job[:2], "alpha max", r["xi"][..., 6].max(), "|K|", np.abs(r["K_uu"]).max())
+        np.savez_compressed(os.path.join(HERE, "ref_rate_fe_elements.npz"), **out)
 
 
 if __name__ == "__main__":

@@ -704,7 +704,8 @@ def test_block_parity_other_quadrature_rules(cuda_device, family, degree, n_ip, 
             assert rel_err(out[k].cpu().numpy(), ref[k]) < TOL, (k, s, rel_err(out[k].cpu().numpy(), ref[k]))
         # residual-only variant and the atomic global scatter
         o4 = fe.fe_block_launch(mat, nw, arr, Ud, xi, outputs=("xi", "R_elem", "R_global"))
-        assert torch.equal(o4["R_elem"], out["R_elem"])
+        # K3 and K4 are separately compiled instantiations (FMA contraction may differ): rounding level
+        assert rel_err(o4["R_elem"].cpu().numpy(), out["R_elem"].cpu().numpy()) < 1e-13
         Rg = np.zeros(arr.n_dofs); np.add.at(Rg, eq.reshape(-1), ref["R_elem"].reshape(-1))
         assert rel_err(o4["R_global"].cpu().numpy(), Rg) < 1e-9
         xi, xi_ref = out["xi"], ref["xi"]

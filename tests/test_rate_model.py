@@ -73,3 +73,135 @@ def test_cuda_vs_reference_rate_model(cuda_device, kind):
         assert rel_err(o["dC_dp"][:, 0].cpu().numpy().reshape(7, len(aidx)),
                        RT[f"{kind}.dC_dp"][t - 1][:, aidx]) < 1e-9, (kind, t, "dC_dp")
         xi = o["xi"]
+
+
+# ------------------------------------------------------------------------------------------ #
+#  Calibration objectives over the rate form: MPAdjointObjective / MPDirectObjective          #
+#  (mp_objective.py:92-215) run by the reference on SmallRateElasticPlastic                    #
+#  (make_reference_golden.py, `rate_objective`; fixture ref_rate_objectives.npz)               #
+# ------------------------------------------------------------------------------------------ #
+RO = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_rate_objectives.npz"))
+RO_CASES = sorted({k.rsplit(".", 1)[0] for k in RO.files})
+
+
+def _rate_objective_parameters(case):
+    from tests.golden.materials import objective_trees
+    kind, mode = case.split(".")
+    values, act, tr = objective_trees(kind, mode == "scaled")
+    return values, act, tr
+
+
+def test_reference_adjoint_equals_direct_for_the_rate_form():
+    for case in RO_CASES:
+        assert abs(RO[f"{case}.J_adjoint"] - RO[f"{case}.J_direct"]) < 1e-12 * abs(RO[f"{case}.J_direct"])
+        assert rel_err(RO[f"{case}.grad_adjoint"], RO[f"{case}.grad_direct"]) < 1e-9, case
+
+
+@pytest.mark.parametrize("case", ["J2.native", "hosford.scaled"])
+def test_torch_oracle_rate_objective_vs_reference(case):
+    from oracle import cmad_oracle as co
+    values, act, tr = _rate_objective_parameters(case)
+    P = co.OracleParameters(values, act, tr)
+    spec = co.ModelSpec(kind="small_rate_elastic_plastic")
+    J, g = co.mp_objective_adjoint(P, RO[f"{case}.F"], RO[f"{case}.data"], RO[f"{case}.weight"], spec,
+                                   RO[f"{case}.x_canonical"], True)
+    assert abs(J - RO[f"{case}.J_adjoint"]) < 1e-11 * abs(J)
+    assert rel_err(g, RO[f"{case}.grad_adjoint"]) < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", RO_CASES)
+def test_cuda_rate_objectives_vs_reference(cuda_device, case):
+    """K1-rate per step (the history carries total strains, the increment is formed on the device)
+    + K2-rate (mp_sens_rate.cu), through the reference's constructor signatures."""
+    from cmad_b200.objectives import Calibration, MPAdjointObjective, MPDirectObjective, SmallRateElasticPlastic
+    values, act, tr = _rate_objective_parameters(case)
+    for strategy, ctor in (("adjoint", MPAdjointObjective), ("direct", MPDirectObjective)):
+        P = Parameters(values, act, tr)
+        assert np.array_equal(P.active_idx, RO[f"{case}.active_idx"])
+        obj = ctor(Calibration(SmallRateElasticPlastic(P), RO[f"{case}.data"], RO[f"{case}.weight"]),
+                   RO[f"{case}.F"], device=cuda_device)
+        r = obj.evaluate(RO[f"{case}.x_canonical"])
+        assert abs(r.J - RO[f"{case}.J_{strategy}"]) < 1e-11 * abs(r.J), (case, strategy)
+        assert rel_err(r.grad, RO[f"{case}.grad_{strategy}"]) < 1e-9, (case, strategy, r.grad)
+
+
+@pytest.mark.gpu
+def test_cuda_rate_objective_hessian_is_refused(cuda_device):
+    from cmad_b200.objectives import Calibration, MPDirectAdjointObjective, SmallRateElasticPlastic
+    case = "J2.scaled"
+    values, act, tr = _rate_objective_parameters(case)
+    obj = MPDirectAdjointObjective(Calibration(SmallRateElasticPlastic(Parameters(values, act, tr)),
+                                               RO[f"{case}.data"], RO[f"{case}.weight"]), RO[f"{case}.F"], device=cuda_device)
+    with pytest.raises(NotImplementedError):
+        obj.evaluate(RO[f"{case}.x_canonical"])
+
+
+# ------------------------------------------------------------------------------------------ #
+#  FE element blocks of the rate form: per_element_R_and_K_coupled over the rate model's        #
+#  per-IP COUPLED evaluator, with the real previous displacement (fixture ref_rate_fe_elements) #
+# ------------------------------------------------------------------------------------------ #
+RF = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_rate_fe_elements.npz"))
+RF_CASES = sorted({k.rsplit(".", 1)[0] for k in RF.files})
+FE_NEWTON = dict(max_iters=20, abs_tol=1e-12, rel_tol=1e-12)          # for_model's COUPLED defaults
+
+
+def _rate_fe_arrays(case):
+    g = {k: RF[f"{case}.{k}"] for k in ("U", "U_prev", "xi_prev", "grad_N", "det", "xi", "R_u", "K_uu", "R_only_u")}
+    n_e, n_b = g["U"].shape[0], g["U"].shape[1]
+    conn = np.arange(n_e * n_b).reshape(n_e, n_b)
+    eq_u = (conn[:, :, None] * 3 + np.arange(3)[None, None, :]).reshape(n_e, 3 * n_b)
+    return g, eq_u, RF[f"{case}.quad_w"], RF[f"{case}.N"]
+
+
+def test_rate_fe_fixture_is_plastic_and_history_dependent():
+    for case in RF_CASES:
+        g, *_ = _rate_fe_arrays(case)
+        assert g["xi"][..., 6].max() > 0 and np.abs(g["U_prev"]).max() > 0
+        assert rel_err(g["R_only_u"], g["R_u"]) < 1e-12
+
+
+@pytest.mark.parametrize("case", ["tet4.J2", "hex8.hosford"])
+def test_torch_oracle_rate_elements_vs_reference(case):
+    import torch
+    from oracle import cmad_oracle as co
+    family, kind = case.split(".")
+    g, eq_u, quad_w, N = _rate_fe_arrays(case)
+    spec = co.ModelSpec(kind="small_rate_elastic_plastic")
+    tv = co.to_torch_tree(material(kind))
+    for e in range(0, g["U"].shape[0], 3):                      # every third record: torch AD per element is slow
+        R, K, xi, _ = co.coupled_element(tv, torch.from_numpy(g["U"][e]), torch.from_numpy(g["U_prev"][e]),
+                                      torch.from_numpy(g["xi_prev"][e]), torch.from_numpy(g["grad_N"][e]),
+                                      torch.from_numpy(g["det"][e]), torch.from_numpy(quad_w), spec,
+                                      newton_settings=FE_NEWTON)
+        n_b = g["U"].shape[1]
+        assert rel_err(np.asarray(xi), g["xi"][e]) < 1e-10, (case, e)
+        assert rel_err(np.asarray(R).reshape(-1), g["R_u"][e].reshape(-1)) < 1e-9
+        assert rel_err(np.asarray(K).reshape(3 * n_b, 3 * n_b), g["K_uu"][e]) < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", RF_CASES)
+def test_cuda_rate_fe_blocks_vs_reference(cuda_device, case):
+    import torch
+    from cmad_b200 import fe, material_from_values
+    from cmad_b200.fe_mesh import FEBlockArrays
+    family, kind = case.split(".")
+    g, eq_u, quad_w, N = _rate_fe_arrays(case)
+    n_e, n_b = eq_u.shape[0], eq_u.shape[1] // 3
+    t = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a)).to(dt).to(cuda_device)  # noqa: E731
+    arr = FEBlockArrays(t(eq_u, torch.int32), t(g["grad_N"]), t(g["det"]), t(quad_w), t(N), int(g["U"].size), None, None)
+    mat = material_from_values(material(kind), model="small_rate_elastic_plastic")
+    nw = fe.fe_newton_settings(**FE_NEWTON)
+    U, Up, xp = t(g["U"].reshape(-1)), t(g["U_prev"].reshape(-1)), t(g["xi_prev"])
+    plan = fe.SegmentPlan(eq_u.reshape(-1), int(g["U"].size), device=cuda_device)
+    R, vals, xi = fe.assemble_element_block(mat, nw, arr, U, xp, r_plan=plan, U_prev=Up)
+    torch.cuda.synchronize()
+    assert rel_err(xi.cpu().numpy(), g["xi"]) < 1e-10, (case, "xi")
+    assert rel_err(R.cpu().numpy()[eq_u], g["R_u"].reshape(n_e, -1)) < 1e-9, (case, "R")
+    assert rel_err(vals.cpu().numpy().reshape(n_e, 3 * n_b, 3 * n_b), g["K_uu"]) < 1e-9, (case, "K")
+    # residual-only launch (K4) and the missing-U_prev error
+    o = fe.fe_block_launch(mat, nw, arr, U, xp, ("xi", "R_elem"), U_prev=Up)
+    assert rel_err(o["R_elem"].cpu().numpy(), g["R_u"].reshape(n_e, -1)) < 1e-9
+    with pytest.raises(ValueError):
+        fe.fe_block_launch(mat, nw, arr, U, xp, ("xi", "R_elem"))
