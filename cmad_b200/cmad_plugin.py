@@ -43,7 +43,7 @@ from . import _lib as L
 from .material import NewtonSettings, material_from_values
 
 _MODEL_KINDS = {"SmallElasticPlastic": "small_elastic_plastic"}
-_LOCAL_NEWTON: dict[int, dict] = {}       # id(fe_problem) -> local_newton_settings given to build_fe_problem
+_LOCAL_NEWTON: dict[int, tuple] = {}      # id(fe_problem) -> (weakref, local_newton_settings given to build_fe_problem)
 _installed: dict[str, Any] = {}
 
 
@@ -99,7 +99,11 @@ def newton_of(fe_problem) -> NewtonSettings:
     """Local Newton settings of the problem's COUPLED blocks: what build_fe_problem was given
     (captured by :func:`install`), else the reference default 20 / 1e-12 / 1e-12 with the default
     line search (cmad/global_residuals/global_residual.py:292-297)."""
-    s = _LOCAL_NEWTON.get(id(fe_problem)) or {"abs_tol": 1e-12, "rel_tol": 1e-12, "max_iters": 20}
+    s = getattr(fe_problem, "_b200_local_newton", None)
+    if s is None:
+        hit = _LOCAL_NEWTON.get(id(fe_problem))
+        s = hit[1] if hit is not None and hit[0]() is fe_problem else None     # ids are reused after collection
+    s = s or {"abs_tol": 1e-12, "rel_tol": 1e-12, "max_iters": 20}
     return NewtonSettings.from_reference_kwargs(**s)
 
 
@@ -322,7 +326,12 @@ def install(backend=None, env: str = "CMAD_B200") -> bool:
     def build_fe_problem(*args, **kwargs):
         fp = original_build(*args, **kwargs)
         if kwargs.get("local_newton_settings") is not None:
-            _LOCAL_NEWTON[id(fp)] = dict(kwargs["local_newton_settings"])
+            settings = dict(kwargs["local_newton_settings"])
+            try:
+                object.__setattr__(fp, "_b200_local_newton", settings)
+            except (AttributeError, TypeError):                  # slotted / frozen problem objects
+                import weakref
+                _LOCAL_NEWTON[id(fp)] = (weakref.ref(fp), settings)
         return fp
 
     assembly.assemble_element_block = assemble_element_block

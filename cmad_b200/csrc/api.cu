@@ -149,6 +149,8 @@ int make_dev_mat(const cmadx_material_t* mat, DevMat* o) {
         if (mat->yield == CMADX_YIELD_HOSFORD && mat->hosford_a >= 1.0 && mat->hosford_a <= 1024.0 &&
             mat->hosford_a == std::floor(mat->hosford_a))
             o->a_int = (int)mat->hosford_a;
+        static const bool libm_root = std::getenv("CMADX_HOSFORD_LIBM_ROOT") != nullptr;      // A/B measurements
+        o->root_int = libm_root ? 0 : o->a_int;
         o->yield_tol = mat->yield_tol;
     }
     bool ident = true;

@@ -35,6 +35,7 @@ struct DevMat {
     double d2lam[3], d2mu[3]; // second derivatives (00, 01, 11): Hessian path only
     int hmask, rot, model, yield;
     int a_int;                // Hosford exponent when it is a small positive integer, else 0
+    int root_int;             // = a_int when the outer root may skip libm pow (hosford_root), else 0
 };
 
 struct DevNewton {
@@ -237,7 +238,7 @@ template <> struct YieldFn<CMADX_YIELD_HOSFORD> {
 #pragma unroll
         for (int i = 0; i < 3; ++i) { q[i] = hosford_pow(fabs(dl[i] * ivm), a, m.a_int); sq += q[i]; }
         sq *= 0.5;
-        phi = vm * hosford_root(sq, m.inv_a, m.a_int);
+        phi = vm * hosford_root(sq, m.inv_a, m.root_int);
         iphi = 1.0 / phi;
         am1 = a - 1.0;
         const double isq = 1.0 / sq;

@@ -232,10 +232,11 @@ def fe_problem_from_deck(path: str) -> DeckProblem:
         raise ValueError(f"residuals.global residual: mixed requires volume quadrature degree >= 2; got {quad}")
     volume_degree = int(quad) if quad is not None else (2 if mixed else None)      # cli/common.py:379-391
     lls = {**_LS_DEFAULT, **(loc.get("line search") or {})}
-    local_newton = NewtonSettings("traced", int(loc["nonlinear max iters"]), float(loc["nonlinear absolute tol"]),
-                                  float(loc["nonlinear relative tol"]), int(lls["max evals"]),
-                                  float(lls["sufficient decrease"]), float(lls["min backtrack factor"]),
-                                  float(lls["max backtrack factor"]))
+    local_newton = NewtonSettings(mode="traced", max_iters=int(loc["nonlinear max iters"]),
+                                  abs_tol=float(loc["nonlinear absolute tol"]), rel_tol=float(loc["nonlinear relative tol"]),
+                                  ls_max_evals=int(lls["max evals"]), ls_sufficient_decrease=float(lls["sufficient decrease"]),
+                                  ls_min_backtrack=float(lls["min backtrack factor"]),
+                                  ls_max_backtrack=float(lls["max backtrack factor"]))
     gls = {**_LS_DEFAULT, **{k: v for k, v in (gr.get("line search") or {}).items() if k != "print"}}
     nonlinear = {"max iters": int(gr["nonlinear max iters"]), "abs tol": float(gr["nonlinear absolute tol"]),
                  "rel tol": float(gr["nonlinear relative tol"]), "line search": gls}

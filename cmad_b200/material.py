@@ -28,7 +28,6 @@ class NewtonSettings:
     abs_tol: float = 1e-14
     rel_tol: float = 1e-14
     ls_max_evals: int = 4           # traced flavour: probes of the quadratic line search
-    max_ls_evals: int = 0           # imperative flavour: newton_solve's legacy line search (0 = none, the default)
     ls_sufficient_decrease: float = 1.0e-4
     ls_min_backtrack: float = 0.5
     ls_max_backtrack: float = 0.9
@@ -40,6 +39,7 @@ class NewtonSettings:
     cta: bool = False               # material-point batches: generic kernel with block-level hand-off (mp_update_cta.cu)
     defer_after: int | None = None  # generic kernels' two-pass scheme: None = library default (K = 2 for Hosford a > 8, else off),
                                     # 0 = single pass, K = defer points needing more than K updates
+    max_ls_evals: int = 0           # imperative flavour: newton_solve's legacy line search (0 = none, the default)
 
     def to_struct(self) -> L.Newton:
         if self.mode not in ("traced", "imperative"):
@@ -58,9 +58,9 @@ class NewtonSettings:
                               line_search_settings=None, **_ignored) -> "NewtonSettings":
         ls = {"max evals": 4, "sufficient decrease": 1e-4, "min backtrack factor": 0.5,
               "max backtrack factor": 0.9, **(line_search_settings or {})}
-        return cls("traced", max_iters, abs_tol, rel_tol, ls["max evals"],
-                   ls["sufficient decrease"], ls["min backtrack factor"],
-                   ls["max backtrack factor"])
+        return cls(mode="traced", max_iters=max_iters, abs_tol=abs_tol, rel_tol=rel_tol,
+                   ls_max_evals=ls["max evals"], ls_sufficient_decrease=ls["sufficient decrease"],
+                   ls_min_backtrack=ls["min backtrack factor"], ls_max_backtrack=ls["max backtrack factor"])
 
 
 def _pid_of(path: tuple, k: int, pair: tuple) -> int | None:

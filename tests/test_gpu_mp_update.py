@@ -430,9 +430,11 @@ def test_two_pass_deferral_keeps_iterates_and_counts(cuda_device, kind, a):
     for K in (1, None, 5):
         out = mp.mp_update(mat, NewtonSettings(defer_after=K), pid, xi, e, outputs=keys)
         torch.cuda.synchronize()
-        for k in keys:      # same iterates / counts / flags; derivative outputs of the two launches agree to rounding
-            if k in ("xi", "sigma", "iters", "flags", "cnorm"):
+        for k in keys:      # same counts / flags; iterates and derivative outputs of the two launches agree to rounding
+            if k in ("iters", "flags"):
                 assert torch.equal(out[k], base[k]), (kind, K, k)
+            elif k == "cnorm":
+                assert float((out[k] - base[k]).abs().max()) < 1e-13, (kind, K, k)
             else:
                 assert rel_err(out[k].cpu().numpy(), base[k].cpu().numpy()) < 1e-12, (kind, K, k)
 
@@ -485,8 +487,16 @@ def test_streaming_kernel_equals_one_pass_kernel(cuda_device, case, mode, varian
                 return mp.mp_update(mat, nw, pid, xi[:, :n], gd[:, :n], out=view)
             a_, b_ = run(nws), run(nwo)
             torch.cuda.synchronize()
-            for k in ("xi", "iters", "flags", "cnorm", "C"):
+            # every lane runs the same evaluation sequence: counts and flags are identical; the
+            # iterates agree to an ulp or two (the kernels are separately compiled instantiations
+            # of the same point routine and nvcc's FMA contraction is not identical across them:
+            # measured 1e-16 relative on < 0.1 % of the points, profiles/r2s_kernel_bits.txt); the
+            # residual at the solution is rounding noise and is compared at the tolerance's scale
+            for k in ("iters", "flags"):
                 assert torch.equal(a_[k], b_[k]), (case, mode, n, s, k)
+            assert rel_err(a_["xi"].cpu().numpy(), b_["xi"].cpu().numpy()) < 1e-13, (case, mode, n, s)
+            for k in ("cnorm", "C"):
+                assert float((a_[k] - b_[k]).abs().max()) < 1e-13, (case, mode, n, s, k)
             for k in ("sigma", "dsig_deps", "dxi_deps", "dC_dp", "dC_dxi", "dC_dxi_prev"):
                 ra, rb = a_[k].cpu().numpy(), b_[k].cpu().numpy()
                 assert rel_err(ra, rb) < 1e-12, (case, mode, n, s, k, rel_err(ra, rb))

@@ -114,3 +114,18 @@ def test_argument_validation_without_gpu(built_lib):
     assert built_lib.cmadx_mp_update(C.byref(m), C.byref(nw), None, 0, C.byref(b), None) == _lib.EINVAL
     b.n = 0; nw.ls_max_evals = 4                                         # empty batch is a no-op
     assert built_lib.cmadx_mp_update(C.byref(m), C.byref(nw), None, 0, C.byref(b), None) == _lib.OK
+
+
+def test_newton_settings_from_reference_kwargs_maps_every_line_search_field():
+    """Regression: the fields are passed by keyword (a field inserted into the dataclass once
+    shifted the positional line-search settings by one)."""
+    from cmad_b200 import NewtonSettings
+    nw = NewtonSettings.from_reference_kwargs(max_iters=7, abs_tol=1e-9, rel_tol=1e-8, line_search_settings={
+        "max evals": 11, "sufficient decrease": 3e-4, "min backtrack factor": 0.25, "max backtrack factor": 0.75})
+    assert (nw.mode, nw.max_iters, nw.abs_tol, nw.rel_tol) == ("traced", 7, 1e-9, 1e-8)
+    assert (nw.ls_max_evals, nw.ls_sufficient_decrease, nw.ls_min_backtrack, nw.ls_max_backtrack) == (11, 3e-4, 0.25, 0.75)
+    assert nw.max_ls_evals == 0
+    s = nw.to_struct()
+    assert (s.max_iters, s.ls_max_evals, s.ls_c1, s.ls_bmin, s.ls_bmax) == (7, 11, 3e-4, 0.25, 0.75)
+    d = NewtonSettings.from_reference_kwargs()
+    assert (d.ls_max_evals, d.ls_sufficient_decrease, d.ls_min_backtrack, d.ls_max_backtrack) == (4, 1e-4, 0.5, 0.9)
