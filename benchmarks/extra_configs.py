@@ -370,6 +370,36 @@ def mp_objective(ctx: Ctx, log2n: int = 21, nsteps: int = 20):
            "launches_per_step": int(launches), "clocks": clocks,
            "J": res["r"].J, "grad": [float(g) for g in res["r"].grad]}
     out.update(ctx.fracs(n * N, seg["forward_history"] + seg["adjoint_K2"], 108 + 176, "mp_objective"))
+    # end to end through HOST buffers (cmadx_mp_objective_host): pinned strain / data histories in,
+    # 8 (1 + P_a) bytes out per chunk - the calibration use case where little comes back over PCIe
+    try:
+        ne = 1 << 19
+        sh = torch.empty((N + 1, 6, ne), dtype=torch.float64, pin_memory=True)
+        dh = torch.empty((N + 1, 9, ne), dtype=torch.float64, pin_memory=True)
+        sh.copy_(strain[:, :, :ne]); dh.copy_(data[:, :, :ne])
+        nws = NewtonSettings(mode="imperative")
+        dev_idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        run = lambda: mp.mp_objective_host(mat, nws, pid, sh, dh, np.ones((3, 3)), "adjoint", device=dev_idx)
+        run()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            r_host = run()
+        dt = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        ms_e2e = float(dt.item()) * 1e3
+        out["e2e"] = {"value": world * ne * N / ms_e2e * 1e3, "unit": "point-steps/s (objective + gradient)",
+                      "api": "cmadx_mp_objective_host (pinned host histories in, (J, grad) out)",
+                      "points_per_gpu": ne, "ms_per_call": ms_e2e,
+                      "h2d_bytes_per_call": int(sh.numel() + dh.numel()) * 8, "d2h_bytes_per_call": (1 + na) * 8 * ((ne + (1 << 18) - 1) >> 18),
+                      "pcie_gbs": (sh.numel() + dh.numel()) * 8 / ms_e2e / 1e6, "J_sample": float(r_host[0])}
+        del sh, dh
+    except Exception as exc:                              # the device-resident line stands on its own
+        out["e2e"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
     return out
 
 

@@ -22,6 +22,7 @@ SOURCES = ["api.cu", "mp_update.cu", "mp_update_stream.cu", "mp_update_queue.cu"
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(5)
 VERSION = 100        # CMADX_VERSION of include/cmad_b200.h this binding was written against
 MODEL_SMALL_ELASTIC_PLASTIC, MODEL_ELASTIC, MODEL_SMALL_RATE_ELASTIC_PLASTIC = 0, 1, 2
+QOI_CALIBRATION, QOI_UNIAXIAL_CALIBRATION = 0, 1
 YIELD_J2, YIELD_HILL, YIELD_HOSFORD = 0, 1, 2
 DEF_FULL_3D, DEF_PLANE_STRESS, DEF_UNIAXIAL_STRESS = 0, 1, 2
 ELASTIC_PAIRS = [("E", "nu"), ("E", "mu"), ("E", "kappa"), ("E", "lambda"), ("kappa", "mu"),
@@ -67,7 +68,8 @@ class MpHistory(C.Structure):
     _fields_ = [("n", C.c_int64), ("ld", C.c_int64), ("nsteps", C.c_int32),
                 ("strain_comps", C.c_int32), ("strain", C.c_void_p), ("data", C.c_void_p),
                 ("weight", C.c_double * 9), ("xi_hist", C.c_void_p), ("iters_hist", C.c_void_p),
-                ("result", C.c_void_p), ("workspace", C.c_void_p), ("J_point", C.c_void_p)]
+                ("result", C.c_void_p), ("workspace", C.c_void_p), ("J_point", C.c_void_p),
+                ("qoi_kind", C.c_int32), ("reserved_", C.c_int32), ("weight_steps", C.c_void_p)]
 
 
 class FeBlock(C.Structure):
@@ -159,6 +161,8 @@ def lib() -> C.CDLL:
                                            C.POINTER(MpHistory), C.c_void_p]
     obj_args = [C.POINTER(Material), C.POINTER(C.c_int32), C.c_int32, C.POINTER(MpHistory), C.c_void_p]
     L.cmadx_mp_objective_adjoint.argtypes = obj_args
+    L.cmadx_mp_objective_host.argtypes = [C.POINTER(Material), C.POINTER(Newton), C.POINTER(C.c_int32), C.c_int32,
+                                          C.POINTER(MpHistory), C.c_int, C.c_int, C.c_int64]
     L.cmadx_mp_objective_direct.argtypes = obj_args
     L.cmadx_mp_objective_hessian.argtypes = obj_args[:-1] + [C.c_int32, C.c_void_p]
     L.cmadx_mp_hessian_workspace_bytes.restype = C.c_int64

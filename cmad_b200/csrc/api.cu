@@ -497,8 +497,9 @@ int cmadx_mp_update_host(const cmadx_material_t* mat, const cmadx_newton_t* newt
     if (int rc = build_args(mat, newton, active_pid, n_active, host, &A)) return rc;
     const int64_t n = host->n;
     if (n == 0) return CMADX_OK;
-    if (host->def_type != CMADX_DEF_FULL_3D) return CMADX_EUNSUPPORTED;   // device buffers only for now
-    const int nxi = (A.m.model == CMADX_MODEL_ELASTIC) ? 6 : 7;
+    // state rows / prescribed strain components by deformation type (cmadx_mp_buffers_t::def_type)
+    const int nxi = (A.m.model == CMADX_MODEL_ELASTIC) ? 6 : 7 + host->def_type;
+    const int ns = host->def_type == CMADX_DEF_FULL_3D ? 6 : (host->def_type == CMADX_DEF_PLANE_STRESS ? 3 : 1);
     int64_t chunk = chunk_points > 0 ? chunk_points : (int64_t)1 << 20;
     if (chunk > n) chunk = n;
     chunk = (chunk + 31) / 32 * 32;
@@ -529,8 +530,8 @@ int cmadx_mp_update_host(const cmadx_material_t* mat, const cmadx_newton_t* newt
     add(host->xi_init, nullptr, nxi, 8);
     add(nullptr, host->xi, nxi, 8);
     add(nullptr, host->sigma, 6, 8);
-    add(nullptr, host->dsig_deps, 36, 8);
-    add(nullptr, host->dxi_deps, nxi * 6, 8);
+    add(nullptr, host->dsig_deps, 6 * ns, 8);
+    add(nullptr, host->dxi_deps, nxi * ns, 8);
     add(nullptr, (n_active > 0) ? host->dC_dp : nullptr, nxi * (n_active > 0 ? n_active : 1), 8);
     add(nullptr, host->dC_dxi, nxi * nxi, 8);
     add(nullptr, host->dC_dxi_prev, nxi * nxi, 8);
@@ -614,6 +615,11 @@ static int check_history(const cmadx_material_t* mat, const cmadx_mp_history_t* 
     if (rate && ((sc != 6 && sc != 9) || dm->rot)) return CMADX_EUNSUPPORTED;
     if (history_def_type(h) != CMADX_DEF_FULL_3D && dm->rot) return CMADX_EUNSUPPORTED;
     if (h->n > 0 && (!h->strain || !h->xi_hist)) return CMADX_EINVAL;
+    if (h->qoi_kind != CMADX_QOI_CALIBRATION) {
+        if (h->qoi_kind != CMADX_QOI_UNIAXIAL_CALIBRATION) return CMADX_EINVAL;
+        if (history_def_type(h) != CMADX_DEF_UNIAXIAL_STRESS || rate) return CMADX_EUNSUPPORTED;
+        if (h->nsteps > 0 && !h->weight_steps) return CMADX_EINVAL;
+    }
     return CMADX_OK;
 }
 
@@ -707,6 +713,102 @@ int cmadx_mp_objective_direct(const cmadx_material_t* mat, const int32_t* active
     return objective(mat, active_pid, n_active, hist, stream, false);
 }
 
+// The calibration objective on HOST buffers: strain / data histories in, (J, dJ/dp) out - 48 bytes
+// for the usual five active parameters against (strain_comps + 9) * 8 * (N + 1) bytes per point in,
+// the case where the GPU wins end to end through host memory.  Points are independent: chunks of
+// points go through a 3-slot pipeline (H2D histories, forward history, K2, 8 (1 + P_a)-byte D2H) and
+// the chunk results are summed on the host in chunk order (deterministic).
+int cmadx_mp_objective_host(const cmadx_material_t* mat, const cmadx_newton_t* newton,
+                            const int32_t* active_pid, int32_t n_active,
+                            const cmadx_mp_history_t* host, int adjoint, int device,
+                            int64_t chunk_points) {
+    DevMat dm;
+    if (!host) return CMADX_EINVAL;
+    {
+        cmadx_mp_history_t probe = *host;            // xi_hist lives in the device scratch
+        probe.xi_hist = reinterpret_cast<double*>(const_cast<double*>(host->strain));
+        if (int rc = check_history(mat, &probe, &dm)) return rc;
+    }
+    if (n_active < 0 || n_active > CMADX_MAX_ACTIVE || (n_active > 0 && !active_pid)) return CMADX_EINVAL;
+    if (!host->result || (host->n > 0 && (!host->strain || !host->data))) return CMADX_EINVAL;
+    const int ncol = 1 + n_active;
+    for (int c = 0; c < ncol; ++c) host->result[c] = 0.0;
+    const int64_t n = host->n;
+    if (n == 0) return CMADX_OK;
+    const int sc = host->strain_comps, nxi = history_n_xi(host), N1 = host->nsteps + 1;
+    int64_t chunk = chunk_points > 0 ? chunk_points : (int64_t)1 << 18;
+    if (chunk > n) chunk = n;
+    chunk = (chunk + 31) / 32 * 32;
+
+    struct DeviceGuard {
+        int prev = -1;
+        ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    } guard;
+    cudaError_t e = cudaGetDevice(&guard.prev);
+    if (e != cudaSuccess) { guard.prev = -1; return cuda_fail(e); }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e);
+
+    auto pad = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t o_strain = 0;
+    const size_t o_data = o_strain + pad((size_t)N1 * sc * chunk * 8);
+    const size_t o_xi = o_data + pad((size_t)N1 * 9 * chunk * 8);
+    const size_t o_ws = o_xi + pad((size_t)N1 * nxi * chunk * 8);
+    const size_t o_res = o_ws + pad((size_t)cmadx_mp_objective_workspace_bytes(chunk, n_active));
+    const size_t o_jp = o_res + pad((size_t)ncol * 8);
+    const size_t total = o_jp + (host->J_point ? pad((size_t)chunk * 8) : 0);
+
+    int rc = CMADX_OK;
+    HostScratch* hs = find_scratch(device);
+    std::lock_guard<std::mutex> lock(hs->mu);
+    if (!get_scratch(hs, total, &rc)) return rc;
+
+    const int64_t nchunks = (n + chunk - 1) / chunk;
+    std::vector<double> partial((size_t)nchunks * ncol, 0.0);
+    std::vector<double> ones(nxi > 7 ? (size_t)chunk : 0, 1.0);
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int k = (int)(c % HostScratch::SLOTS);
+        cudaStream_t s = hs->st[k];
+        char* base = (char*)hs->dev[k];
+        const int64_t i0 = c * chunk;
+        const int64_t nc = (n - i0 < chunk) ? (n - i0) : chunk;
+        e = cudaMemcpy2DAsync(base + o_strain, (size_t)chunk * 8, (const char*)host->strain + (size_t)i0 * 8,
+                              (size_t)host->ld * 8, (size_t)nc * 8, (size_t)N1 * sc, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) return cuda_fail(e);
+        e = cudaMemcpy2DAsync(base + o_data, (size_t)chunk * 8, (const char*)host->data + (size_t)i0 * 8,
+                              (size_t)host->ld * 8, (size_t)nc * 8, (size_t)N1 * 9, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) return cuda_fail(e);
+        // initial state: zeros, stretches of the def-type variants 1
+        e = cudaMemsetAsync(base + o_xi, 0, (size_t)nxi * chunk * 8, s);
+        if (e != cudaSuccess) return cuda_fail(e);
+        for (int r = 7; r < nxi; ++r) {
+            e = cudaMemcpyAsync(base + o_xi + (size_t)r * chunk * 8, ones.data(), (size_t)nc * 8, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) return cuda_fail(e);
+        }
+        cmadx_mp_history_t h = *host;
+        h.n = nc; h.ld = chunk;
+        h.strain = (const double*)(base + o_strain); h.data = (const double*)(base + o_data);
+        h.xi_hist = (double*)(base + o_xi); h.iters_hist = nullptr;
+        h.workspace = (double*)(base + o_ws); h.result = (double*)(base + o_res);
+        h.J_point = host->J_point ? (double*)(base + o_jp) : nullptr;
+        if ((rc = cmadx_mp_forward_history(mat, newton, &h, s))) return rc;
+        if ((rc = objective(mat, active_pid, n_active, &h, s, adjoint != 0))) return rc;
+        e = cudaMemcpyAsync(partial.data() + (size_t)c * ncol, h.result, (size_t)ncol * 8, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) return cuda_fail(e);
+        if (host->J_point) {
+            e = cudaMemcpyAsync(host->J_point + i0, h.J_point, (size_t)nc * 8, cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) return cuda_fail(e);
+        }
+    }
+    for (int k = 0; k < HostScratch::SLOTS; ++k) {
+        e = cudaStreamSynchronize(hs->st[k]);
+        if (e != cudaSuccess) return cuda_fail(e);
+    }
+    for (int64_t c = 0; c < nchunks; ++c)
+        for (int q = 0; q < ncol; ++q) host->result[q] += partial[(size_t)c * ncol + q];
+    return CMADX_OK;
+}
+
 // workspace layout of the Hessian path: [phi_hist (N+1) x 7 x ld][partials][pair sums]
 static int64_t hess_partials_doubles(int64_t n, int32_t n_active) {
     const int64_t npairs = (int64_t)n_active * (n_active + 1) / 2;
@@ -728,8 +830,9 @@ int cmadx_mp_objective_hessian(const cmadx_material_t* mat, const int32_t* activ
     if (flags & ~CMADX_HESS_F_REFERENCE_QOI_CROSS) return CMADX_EINVAL;
     A.hess_flags = flags;
     if (int rc = check_history(mat, hist, &A.m)) return rc;
-    if (A.m.rot || A.m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC) return CMADX_EUNSUPPORTED;
-    const int dt = history_def_type(hist);
+    if (A.m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC || hist->qoi_kind != CMADX_QOI_CALIBRATION)
+        return CMADX_EUNSUPPORTED;
+    const int dt = history_def_type(hist);     // rotated axes: FULL_3D only (check_history refuses the other def-types)
     if (n_active < 0 || n_active > CMADX_MAX_ACTIVE || (n_active > 0 && !active_pid)) return CMADX_EINVAL;
     if (!hist->result || !hist->workspace || (hist->n > 0 && !hist->data)) return CMADX_EINVAL;
     for (int c = 0; c < n_active; ++c) {

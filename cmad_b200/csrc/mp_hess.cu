@@ -170,13 +170,29 @@ CMADX_DEV HD qoi_hd(const HD (&sig)[6], const double (&w)[9], const double (&d)[
     return J;
 }
 
+// rotated material axes: the QoI compares the GLOBAL cauchy S sigma_m with the data
+// (S = d(Q s Q^T)/ds on packed components, rot_maps_hess below); S == nullptr: identity axes
+CMADX_DEV void to_global_hd(const double* S, HD (&sig)[6]) {
+    if (!S) return;
+    HD g[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        HD acc = hd(0.0);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc = acc + S[a * 6 + c] * sig[c];
+        g[a] = acc;
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) sig[a] = g[a];
+}
+
 // The (parameter, state) cross terms of the QoI's second derivative along the two directions:
 // D2 J [(p_i, 0), (0, X_j)] + D2 J [(0, X_i), (p_j, 0)].  The reference omits exactly these
 // (its QoI takes jacrev(jacfwd(., DXI_PREV), DPARAMS), cmad/qois/qoi.py:53-55, which is zero for
 // a QoI that does not depend on xi_prev); the reference-compatible mode subtracts them.
 __device__ __noinline__ double qoi_cross_terms(const HD& lam, const HD& mu, const HD (&x)[7],
                                                const double (&em)[6], const double (&w)[9],
-                                               const double (&d)[9]) {
+                                               const double (&d)[9], const double* S = nullptr) {
     double acc = 0.0;
 #pragma unroll 1
     for (int side = 0; side < 2; ++side) {
@@ -187,6 +203,7 @@ __device__ __noinline__ double qoi_cross_terms(const HD& lam, const HD& mu, cons
 #pragma unroll
         for (int r = 0; r < 7; ++r) xs[r] = side ? HD{x[r].v, x[r].a, 0.0, 0.0} : HD{x[r].v, 0.0, x[r].b, 0.0};
         stress_hd(l, u, xs, em, sig);
+        to_global_hd(S, sig);
         acc += qoi_hd(sig, w, d).ab;
     }
     return acc;
@@ -197,11 +214,18 @@ template <int YK>
 __device__ __forceinline__ double lagrangian_mixed(const DevMat& m, const HessParams& P, const HD (&x)[7],
                                                 const HD (&xp)[7], const double (&em)[6],
                                                 const double (&phi)[7], const double (&w)[9],
-                                                const double (&d)[9], bool plastic) {
+                                                const double (&d)[9], bool plastic, const double* S = nullptr) {
     HD sig[6];
     stress_hd(P.lam, P.mu, x, em, sig);
     const HD two_mu = 2.0 * P.mu;
-    HD L = qoi_hd(sig, w, d);
+    HD L;
+    {
+        HD sg[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) sg[a] = sig[a];
+        to_global_hd(S, sg);
+        L = qoi_hd(sg, w, d);
+    }
     if (plastic) {
         HD pe, n[6];
         yield_hd<YK>(m, P, sig, pe, n);
@@ -246,6 +270,24 @@ __global__ void __launch_bounds__(HESS_BLOCK) mp_hess_kernel(const __grid_consta
     for (int c = 0; c < na; ++c)
 #pragma unroll
         for (int r = 0; r < 7; ++r) { X(c, r) = 0.0; Xp(c, r) = 0.0; }
+    // rotated material axes (cmad/models/small_elastic_plastic.py:44-62, 318-319): the strain goes to
+    // material axes, the state lives there, the QoI reads the global cauchy.  T[c][b] =
+    // d(Q^T e Q)_c / d e_b, S[a][c] = d(Q s Q^T)_a / d s_c on packed components.
+    double Trot[36], Srot[36];
+    const double* Sq = nullptr;
+    if (m.rot) {
+        const int ci_[6] = {0, 0, 0, 1, 1, 2}, cj_[6] = {0, 1, 2, 1, 2, 2};
+        for (int c = 0; c < 6; ++c)
+            for (int b = 0; b < 6; ++b) {
+                const int ii = ci_[c], jj = cj_[c], kk = ci_[b], ll = cj_[b];
+                double tt = m.Q[3 * kk + ii] * m.Q[3 * ll + jj];
+                double ss = m.Q[3 * ii + kk] * m.Q[3 * jj + ll];
+                if (kk != ll) { tt += m.Q[3 * ll + ii] * m.Q[3 * kk + jj]; ss += m.Q[3 * ii + ll] * m.Q[3 * jj + kk]; }
+                Trot[c * 6 + b] = tt;
+                Srot[c * 6 + b] = ss;
+            }
+        Sq = Srot;
+    }
     double x[7], xp[7];
 #pragma unroll
     for (int c = 0; c < 7; ++c) {
@@ -280,6 +322,17 @@ __global__ void __launch_bounds__(HESS_BLOCK) mp_hess_kernel(const __grid_consta
             for (int c = 0; c < 9; ++c) d[c] = 0.0;
 #pragma unroll
             for (int c = 0; c < 7; ++c) phi[c] = 0.0;
+        }
+        if (m.rot) {
+            double eg[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) eg[c] = em[c];
+            for (int c = 0; c < 6; ++c) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int b = 0; b < 6; ++b) sacc = fma(Trot[c * 6 + b], eg[b], sacc);
+                em[c] = sacc;
+            }
         }
         // ---- forward sensitivities X_t = A^{-1}(-dC/dp - B X_{t-1})  (mp_objective.py:300-301)
         SepPoint<YK> pt;
@@ -348,9 +401,9 @@ __global__ void __launch_bounds__(HESS_BLOCK) mp_hess_kernel(const __grid_consta
                     xh[r] = {x[r], X(ci, r), X(cj, r), 0.0};
                     xph[r] = {xp[r], Xp(ci, r), Xp(cj, r), 0.0};
                 }
-                double hij = lagrangian_mixed<YK>(m, P, xh, xph, em, phi, A.h.weight, d, pl);
+                double hij = lagrangian_mixed<YK>(m, P, xh, xph, em, phi, A.h.weight, d, pl, Sq);
                 if (A.hess_flags & CMADX_HESS_F_REFERENCE_QOI_CROSS)
-                    hij -= qoi_cross_terms(P.lam, P.mu, xh, em, A.h.weight, d);
+                    hij -= qoi_cross_terms(P.lam, P.mu, xh, em, A.h.weight, d, Sq);
                 Hacc(q) += hij;
             }
         }

@@ -83,12 +83,13 @@ mp_sens_kernel(const __grid_constant__ SensArgs A) {
     double hist[7];
 #pragma unroll
     for (int c = 0; c < 7; ++c) hist[c] = 0.0;
-    double X[NA_MAX][7];          // direct: dxi/dp carried forward
+    // direct: dxi/dp (7 x n_active per point) carried forward in SHARED memory, entry (c, r) of
+    // thread t at (c * 7 + r) * SENS_BLOCK + t (conflict-free).  It used to live in local memory:
+    // 336 B per thread that the streaming history loads kept evicting from L1 (direct 7.56 ms
+    // against 4.0 ms for the adjoint on the same history, 0.30 of HBM).
+    extern __shared__ double Xs[];
     if (!ADJOINT) {
-#pragma unroll
-        for (int c = 0; c < NA_MAX; ++c)
-#pragma unroll
-            for (int r = 0; r < 7; ++r) X[c][r] = 0.0;
+        for (int c = 0; c < na * 7; ++c) Xs[c * SENS_BLOCK + threadIdx.x] = 0.0;
     }
 
     // the state pair (xi_t, xi_{t-1}) shares one member with the next step's pair: it is
@@ -276,24 +277,24 @@ mp_sens_kernel(const __grid_constant__ SensArgs A) {
             }
         } else {
             // rhs = -dC/dp - B X_prev ;  B = [-I, n; 0, 0] (plastic) or -I (elastic)
-            auto column = [&](const int pid, double (&Xc)[7], double& gc) {
+            auto column = [&](const int pid, double* Xc, double& gc) {
                 double col[7], rhs[7];
                 dC_dp_column(m, pid, pl, pt.yf, pt.n, pt.f, pt.eD, x[6], dg, Mee, nee, sig, col);
-                const double x6 = Xc[6];
+                const double x6 = Xc[6 * SENS_BLOCK];
 #pragma unroll
-                for (int q = 0; q < 6; ++q) rhs[q] = -col[q] + Xc[q] - (pl ? pt.n[q] * x6 : 0.0);
+                for (int q = 0; q < 6; ++q) rhs[q] = -col[q] + Xc[q * SENS_BLOCK] - (pl ? pt.n[q] * x6 : 0.0);
                 rhs[6] = -col[6] + (pl ? 0.0 : x6);
                 solve7(rhs);
                 double acc = 0.0;
 #pragma unroll
-                for (int q = 0; q < 7; ++q) { Xc[q] = rhs[q]; acc = fma(dJdx[q], rhs[q], acc); }
+                for (int q = 0; q < 7; ++q) { Xc[q * SENS_BLOCK] = rhs[q]; acc = fma(dJdx[q], rhs[q], acc); }
                 if (pid == CMADX_P_EL0 || pid == CMADX_P_EL1)
                     acc += dJdlam * m.dlam[pid - CMADX_P_EL0] + dJdmu * m.dmu[pid - CMADX_P_EL0];
                 gc += acc;
             };
-            // dxi/dp (7 x n_active) lives in local memory (L1-resident): measured faster than the
-            // 246-register fully unrolled variant (7.6 vs 9.6 ms on the 2^22 x 20 benchmark)
-            for (int c = 0; c < na; ++c) column(A.pid[c], X[c], g[c]);
+#pragma unroll
+            for (int c = 0; c < NA_MAX; ++c)
+                if (c < na) column(A.pid[c], Xs + (c * 7) * SENS_BLOCK + threadIdx.x, g[c]);
         }
 #pragma unroll
         for (int c = 0; c < 7; ++c) {
@@ -349,19 +350,33 @@ reduce_partials_kernel(const double* partials, int64_t nblk, int ncols, double* 
     if (threadIdx.x == 0) result[c] = sm[0];
 }
 
+// dynamic shared memory of the direct variant: dxi/dp, 7 x n_active doubles per thread
+template <class K>
+cudaError_t sens_launch(K kern, const SensArgs& A, bool adjoint, int64_t nblk, cudaStream_t stream) {
+    const size_t smem = adjoint ? 0 : sizeof(double) * 7 * (size_t)A.n_active * SENS_BLOCK;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<(unsigned)nblk, SENS_BLOCK, smem, stream>>>(A);
+    return cudaGetLastError();
+}
+
 template <bool ADJOINT>
 cudaError_t launch_sens_rot(const SensArgs& A, cudaStream_t stream) {
     const int64_t nblk = (A.h.n + SENS_BLOCK - 1) / SENS_BLOCK;
     constexpr int NA = CMADX_MAX_ACTIVE;
+    cudaError_t e0;
     switch (A.m.yield) {
     case CMADX_YIELD_J2:
-        mp_sens_kernel<CMADX_YIELD_J2, ADJOINT, NA, true><<<(unsigned)nblk, SENS_BLOCK, 0, stream>>>(A); break;
+        e0 = sens_launch(mp_sens_kernel<CMADX_YIELD_J2, ADJOINT, NA, true>, A, ADJOINT, nblk, stream); break;
     case CMADX_YIELD_HILL:
-        mp_sens_kernel<CMADX_YIELD_HILL, ADJOINT, NA, true><<<(unsigned)nblk, SENS_BLOCK, 0, stream>>>(A); break;
+        e0 = sens_launch(mp_sens_kernel<CMADX_YIELD_HILL, ADJOINT, NA, true>, A, ADJOINT, nblk, stream); break;
     case CMADX_YIELD_HOSFORD:
-        mp_sens_kernel<CMADX_YIELD_HOSFORD, ADJOINT, NA, true><<<(unsigned)nblk, SENS_BLOCK, 0, stream>>>(A); break;
+        e0 = sens_launch(mp_sens_kernel<CMADX_YIELD_HOSFORD, ADJOINT, NA, true>, A, ADJOINT, nblk, stream); break;
     default: return cudaErrorInvalidValue;
     }
+    if (e0 != cudaSuccess) return e0;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     reduce_partials_kernel<<<1 + A.n_active, REDUCE_THREADS, 0, stream>>>(A.partials, nblk, 1 + A.n_active, A.h.result);
@@ -371,15 +386,17 @@ cudaError_t launch_sens_rot(const SensArgs& A, cudaStream_t stream) {
 template <bool ADJOINT, int NA_MAX>
 cudaError_t launch_sens_t(const SensArgs& A, cudaStream_t stream) {
     const int64_t nblk = (A.h.n + SENS_BLOCK - 1) / SENS_BLOCK;
+    cudaError_t e0;
     switch (A.m.yield) {
     case CMADX_YIELD_J2:
-        mp_sens_kernel<CMADX_YIELD_J2, ADJOINT, NA_MAX><<<(unsigned)nblk, SENS_BLOCK, 0, stream>>>(A); break;
+        e0 = sens_launch(mp_sens_kernel<CMADX_YIELD_J2, ADJOINT, NA_MAX>, A, ADJOINT, nblk, stream); break;
     case CMADX_YIELD_HILL:
-        mp_sens_kernel<CMADX_YIELD_HILL, ADJOINT, NA_MAX><<<(unsigned)nblk, SENS_BLOCK, 0, stream>>>(A); break;
+        e0 = sens_launch(mp_sens_kernel<CMADX_YIELD_HILL, ADJOINT, NA_MAX>, A, ADJOINT, nblk, stream); break;
     case CMADX_YIELD_HOSFORD:
-        mp_sens_kernel<CMADX_YIELD_HOSFORD, ADJOINT, NA_MAX><<<(unsigned)nblk, SENS_BLOCK, 0, stream>>>(A); break;
+        e0 = sens_launch(mp_sens_kernel<CMADX_YIELD_HOSFORD, ADJOINT, NA_MAX>, A, ADJOINT, nblk, stream); break;
     default: return cudaErrorInvalidValue;
     }
+    if (e0 != cudaSuccess) return e0;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     reduce_partials_kernel<<<1 + A.n_active, REDUCE_THREADS, 0, stream>>>(A.partials, nblk, 1 + A.n_active, A.h.result);

@@ -83,7 +83,23 @@ __global__ void __launch_bounds__(SENS_DT_BLOCK) mp_sens_dt_kernel(const __grid_
         for (int a = 0; a < 6; ++a) sig[a] = is_diag(a) ? fma(m.two_mu, ee[a], m.lam * tree) : m.two_mu * ee[a];
         // Calibration QoI: J, r_a = dJ/d sigma_a (both entries of an off-diagonal component summed)
         double r[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        {
+        double dJdz[NZ];                   // direct dependence of the QoI on the stretch dofs
+#pragma unroll
+        for (int k = 0; k < NZ; ++k) dJdz[k] = 0.0;
+        if (DT == CMADX_DEF_UNIAXIAL_STRESS && A.h.qoi_kind == CMADX_QOI_UNIAXIAL_CALIBRATION) {
+            // UniaxialCalibration (cmad/qois/uniaxial_calibration.py:69-85): pred = [sigma_axial,
+            // lambda_2 - 1, lambda_3 - 1], weights of this step, data rows 0..2
+            const double* ws = A.h.weight_steps + (int64_t)t * 3;
+            const double w0 = __ldg(ws), mis0 = w0 * (sig[0] - d[0]);
+            Jacc = fma(0.5 * mis0, mis0, Jacc);
+            r[0] = w0 * mis0;
+#pragma unroll
+            for (int k = 0; k < NZ; ++k) {
+                const double wk = __ldg(ws + 1 + k), mis = wk * (x[7 + k] - 1.0 - d[1 + k]);
+                Jacc = fma(0.5 * mis, mis, Jacc);
+                dJdz[k] = wk * mis;
+            }
+        } else {
             const int comp[9] = {0, 1, 2, 1, 3, 4, 2, 4, 5};
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
@@ -102,7 +118,7 @@ __global__ void __launch_bounds__(SENS_DT_BLOCK) mp_sens_dt_kernel(const __grid_
         }
         dJdx[6] = 0.0;
 #pragma unroll
-        for (int k = 0; k < NZ; ++k) dJdx[7 + k] = fma(m.two_mu, r[Pt::zcomp(k)], m.lam * rtr);
+        for (int k = 0; k < NZ; ++k) dJdx[7 + k] = fma(m.two_mu, r[Pt::zcomp(k)], m.lam * rtr) + dJdz[k];
         double ree = 0.0;
 #pragma unroll
         for (int a = 0; a < 6; ++a) ree = fma(r[a], ee[a], ree);

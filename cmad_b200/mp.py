@@ -129,27 +129,69 @@ def mp_update(material: L.Material, newton: NewtonSettings, active_pid, xi_prev:
 
 def mp_update_host(material: L.Material, newton: NewtonSettings, active_pid, xi_prev, strain,
                    outputs=DEFAULT_OUTPUTS, out: dict | None = None, xi_init=None,
-                   device: int = 0, chunk_points: int = 0) -> dict:
+                   device: int = 0, chunk_points: int = 0, def_type: int = L.DEF_FULL_3D) -> dict:
     """Same update on HOST buffers (NumPy arrays or CPU torch tensors, ideally
-    pinned): chunked H2D -> kernel -> D2H pipeline inside the library. Blocking."""
+    pinned): chunked H2D -> kernel -> D2H pipeline inside the library. Blocking.
+    Every deformation type of :func:`mp_update`."""
     lib = L.lib()
+    if def_type not in DEF_TYPES:
+        raise ValueError(f"unknown def_type {def_type}")
     as_t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
     xi_prev, strain = as_t(xi_prev), as_t(strain)
     xi_init = as_t(xi_init) if xi_init is not None else None
-    nxi = n_xi_of(material)
+    nxi = n_xi_of(material, def_type)
     n = xi_prev.shape[1]
     _check_in("xi_prev", xi_prev, nxi, n, "cpu")
+    if strain.shape[0] not in DEF_TYPES[def_type][2]:
+        raise ValueError(f"strain must have one of {DEF_TYPES[def_type][2]} components for this def_type")
     _check_in("strain", strain, strain.shape[0], n, "cpu")
     pid = np.ascontiguousarray(active_pid, dtype=np.int32)
     if out is None:
-        out = allocate_outputs(material, n, len(pid), outputs, "cpu", pin=False)
-    b = _buffers(material, xi_prev, strain, xi_init, out)
+        out = allocate_outputs(material, n, len(pid), outputs, "cpu", pin=False, def_type=def_type)
+    b = _buffers(material, xi_prev, strain, xi_init, out, def_type)
     nw = newton.to_struct()
     rc = lib.cmadx_mp_update_host(C.byref(material), C.byref(nw),
                                   pid.ctypes.data_as(C.POINTER(C.c_int32)), len(pid),
                                   C.byref(b), int(device), int(chunk_points))
     L.check(rc, "cmadx_mp_update_host")
     return out
+
+
+def mp_objective_host(material: L.Material, newton: NewtonSettings, active_pid, strain_hist, data_hist, weight,
+                      strategy: str = "adjoint", device: int = 0, chunk_points: int = 0,
+                      want_J_point: bool = False):
+    """Calibration objective ``(J, dJ/dp native)`` of a batch of experiments held in HOST memory
+    (``cmadx_mp_objective_host``): ``strain_hist (N+1, comps, n)``, ``data_hist (N+1, 9, n)`` NumPy /
+    CPU tensors (pinned for speed), ``weight`` 3x3.  Returns ``result (1 + n_active,)`` and, with
+    ``want_J_point``, the per-point objective.  Histories go to the device in chunks of points;
+    what comes back is 8 (1 + n_active) bytes per chunk."""
+    lib = L.lib()
+    as_t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+    sh, dh = as_t(strain_hist), as_t(data_hist)
+    if sh.dtype != torch.float64 or dh.dtype != torch.float64 or sh.dim() != 3 or dh.dim() != 3 or not sh.is_contiguous() \
+            or not dh.is_contiguous() or dh.shape[1] != 9 or dh.shape[0] != sh.shape[0] or dh.shape[2] != sh.shape[2]:
+        raise ValueError("strain_hist (N+1, comps, n) and data_hist (N+1, 9, n): contiguous float64")
+    if sh.device.type != "cpu" or dh.device.type != "cpu":
+        raise ValueError("mp_objective_host takes host arrays (device histories: cmad_b200.objectives)")
+    if strategy not in ("adjoint", "direct"):
+        raise ValueError(f"unknown strategy {strategy!r}")
+    pid = np.ascontiguousarray(active_pid, dtype=np.int32)
+    n = sh.shape[2]
+    result = np.zeros(1 + len(pid))
+    Jp = np.zeros(n) if want_J_point else None
+    h = L.MpHistory()
+    h.n, h.ld, h.nsteps, h.strain_comps = n, max(n, 1), sh.shape[0] - 1, sh.shape[1]
+    h.strain, h.data = sh.data_ptr(), dh.data_ptr()
+    w = np.asarray(weight, dtype=np.float64).reshape(9)
+    for k in range(9):
+        h.weight[k] = float(w[k])
+    h.result = result.ctypes.data
+    h.J_point = Jp.ctypes.data if Jp is not None else None
+    nw = newton.to_struct()
+    rc = lib.cmadx_mp_objective_host(C.byref(material), C.byref(nw), pid.ctypes.data_as(C.POINTER(C.c_int32)), len(pid),
+                                     C.byref(h), 1 if strategy == "adjoint" else 0, int(device), int(chunk_points))
+    L.check(rc, "cmadx_mp_objective_host")
+    return (result, Jp) if want_J_point else result
 
 
 def fp64_peak_tflops(iters: int = 20000) -> float:

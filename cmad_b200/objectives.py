@@ -102,6 +102,33 @@ class Calibration:
         return self._data
 
 
+class UniaxialCalibration:
+    """``UniaxialCalibration(model, data, weight, uniaxial_stress_idx, stretch_var_idx)``
+    (cmad/qois/uniaxial_calibration.py:21-85), the QoI of uniaxial-stress tests that also measure
+    the two lateral strains: ``J = sum_t 1/2 ||weight[:, t] o ([sigma_axial, lambda_2 - 1,
+    lambda_3 - 1] - data[:, t])||^2`` with ``data`` and ``weight`` of shape ``(3, N+1)``
+    (``(B, 3, N+1)`` data for a batch).  UNIAXIAL_STRESS models, ``uniaxial_stress_idx = 0`` and
+    ``stretch_var_idx = 2`` (the block of off-axis stretches) - what the kernels carry."""
+    qoi_kind = L.QOI_UNIAXIAL_CALIBRATION
+
+    def __init__(self, model: SmallElasticPlastic, data: np.ndarray, weight: np.ndarray,
+                 uniaxial_stress_idx: int = 0, stretch_var_idx: int = 2) -> None:
+        data, weight = np.asarray(data, dtype=np.float64), np.asarray(weight, dtype=np.float64)
+        if getattr(model, "_def_type", FULL_3D) != UNIAXIAL_STRESS:
+            raise NotImplementedError("UniaxialCalibration needs a UNIAXIAL_STRESS model")
+        if uniaxial_stress_idx != 0 or stretch_var_idx != 2:
+            raise NotImplementedError("UniaxialCalibration: uniaxial_stress_idx = 0, stretch_var_idx = 2 on the B200 path")
+        if weight.ndim != 2 or weight.shape[0] != 3 or data.shape[-2:] != weight.shape:
+            raise ValueError("UniaxialCalibration: data (.., 3, N+1) and weight (3, N+1)")
+        self._model, self._data, self._weight = model, data, weight
+
+    def model(self):
+        return self._model
+
+    def data(self):
+        return self._data
+
+
 def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous, balanced range of point indices owned by ``rank``."""
     base, rem = divmod(n, world)
@@ -122,6 +149,15 @@ def data_history(data: np.ndarray) -> np.ndarray:
     """(B, 3, 3, N+1) -> (N+1, 9, B)."""
     data = np.asarray(data, dtype=np.float64)
     return np.ascontiguousarray(data.reshape(data.shape[0], 9, data.shape[-1]).transpose(2, 1, 0))
+
+
+def uniaxial_data_history(data: np.ndarray) -> np.ndarray:
+    """UniaxialCalibration data (B, 3, N+1) = (sigma_axial, e_2, e_3) -> (N+1, 9, B) slabs whose
+    rows 0..2 carry them (the layout CMADX_QOI_UNIAXIAL_CALIBRATION reads)."""
+    data = np.asarray(data, dtype=np.float64)
+    out = np.zeros((data.shape[-1], 9, data.shape[0]))
+    out[:, :3, :] = data.transpose(2, 1, 0)
+    return out
 
 
 class _DeviceHistories:
@@ -153,7 +189,16 @@ def gpu_local_evaluator(model: SmallElasticPlastic, strain_hist: np.ndarray, dat
     newton = newton or NewtonSettings(mode="imperative", max_iters=10, abs_tol=1e-14, rel_tol=1e-14)
     adjoint = {"adjoint": True, "direct": False, "direct_adjoint": True}[strategy]
     hessian = strategy == "direct_adjoint"
-    w = np.asarray(weight, dtype=np.float64).reshape(9)
+    weight = np.asarray(weight, dtype=np.float64)
+    uniaxial_qoi = weight.shape != (3, 3)              # UniaxialCalibration: per-step weights (3, N+1)
+    if uniaxial_qoi:
+        if weight.shape != (3, hist.N + 1) or strain_hist.shape[1] != 1:
+            raise ValueError("UniaxialCalibration: weight (3, N+1) on a UNIAXIAL_STRESS history")
+        w_steps = torch.from_numpy(np.ascontiguousarray(weight.T)).to(device)        # (N+1, 3)
+        w = np.zeros(9)
+    else:
+        w_steps = None
+        w = weight.reshape(9)
 
     def evaluate() -> torch.Tensor:
         pid = active_param_ids(model.parameters)
@@ -174,6 +219,8 @@ def gpu_local_evaluator(model: SmallElasticPlastic, strain_hist: np.ndarray, dat
             h.weight[k] = float(w[k])
         h.xi_hist, h.iters_hist = hist.xi.data_ptr(), hist.iters.data_ptr()
         h.result, h.workspace, h.J_point = result.data_ptr(), ws.data_ptr(), hist.J_point.data_ptr()
+        if uniaxial_qoi:
+            h.qoi_kind, h.weight_steps = L.QOI_UNIAXIAL_CALIBRATION, w_steps.data_ptr()
         stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         hist.xi[0].zero_()
         hist.xi[0, 7:] = 1.0                               # stretches of the def-type variants start at 1
@@ -246,8 +293,11 @@ def _single_point_objective(qoi: Calibration, global_state: np.ndarray, strategy
         F, data = F[None], data[None]
     device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
     model = qoi.model()
-    ev = gpu_local_evaluator(model, strain_history_from_F(F), data_history(data), qoi._weight,
-                             strategy, device, **kwargs)
+    if getattr(qoi, "qoi_kind", L.QOI_CALIBRATION) == L.QOI_UNIAXIAL_CALIBRATION:
+        dh = uniaxial_data_history(data)
+    else:
+        dh = data_history(data)
+    ev = gpu_local_evaluator(model, strain_history_from_F(F), dh, qoi._weight, strategy, device, **kwargs)
     return BatchedMPObjective(model.parameters, ev, group)
 
 

@@ -250,7 +250,18 @@ typedef struct cmadx_mp_history {
                                Parameters.transform_grad)                      */
     double* workspace;      /* device scratch, cmadx_mp_objective_workspace_bytes() */
     double* J_point;        /* [n] or NULL: per-point objective                */
+    int32_t qoi_kind;       /* CMADX_QOI_CALIBRATION (0, the default) or
+                               CMADX_QOI_UNIAXIAL_CALIBRATION: UniaxialCalibration
+                               (cmad/qois/uniaxial_calibration.py:69-85), UNIAXIAL_STRESS
+                               histories only (strain_comps 1, uniaxial_stress_idx 0,
+                               stretch_var_idx 2): J = sum_t 1/2 ||w_t o ([sigma_axial,
+                               lambda_2 - 1, lambda_3 - 1] - data_t)||^2; rows 0..2 of
+                               every data slab hold (sigma, e_2, e_3), `weight` is unused */
+    int32_t reserved_;
+    const double* weight_steps; /* UNIAXIAL_CALIBRATION: [N+1][3] device, the QoI's
+                               per-step weights (weight[:, step]); same for all points */
 } cmadx_mp_history_t;
+enum { CMADX_QOI_CALIBRATION = 0, CMADX_QOI_UNIAXIAL_CALIBRATION = 1 };
 
 /* bytes of `workspace` needed for n points and n_active parameters */
 int64_t cmadx_mp_objective_workspace_bytes(int64_t n, int32_t n_active);
@@ -269,6 +280,19 @@ int cmadx_mp_objective_adjoint(const cmadx_material_t* mat, const int32_t* activ
                                int32_t n_active, const cmadx_mp_history_t* hist, void* stream);
 int cmadx_mp_objective_direct(const cmadx_material_t* mat, const int32_t* active_pid,
                               int32_t n_active, const cmadx_mp_history_t* hist, void* stream);
+
+/* The same objective on HOST buffers (pageable or pinned): `host->strain` / `host->data` are host
+ * histories in the slab layout above, `host->result` a host array of 1 + n_active doubles,
+ * `host->J_point` an optional host array; xi_hist / iters_hist / workspace are ignored (device
+ * scratch is cached per device as for cmadx_mp_update_host).  Chunks of points are pipelined
+ * H2D -> forward history -> K2 -> D2H of 8 (1 + n_active) bytes; the chunk sums are added on the
+ * host in chunk order.  Blocking.  adjoint != 0: reverse-time recurrence, else forward
+ * sensitivities.  This is MPAdjointObjective.evaluate / MPDirectObjective.evaluate
+ * (cmad/objectives/mp_objective.py:53-57) for a batch of experiments held in host memory.     */
+int cmadx_mp_objective_host(const cmadx_material_t* mat, const cmadx_newton_t* newton,
+                            const int32_t* active_pid, int32_t n_active,
+                            const cmadx_mp_history_t* host, int adjoint, int device,
+                            int64_t chunk_points);
 
 /* Second-order pass: MPDirectAdjointObjective (cmad/objectives/mp_objective.py:218-343) -
  * J, dJ/dp and the Hessian d2J/dp2 of the summed objective in NATIVE parameter values

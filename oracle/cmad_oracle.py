@@ -741,6 +741,25 @@ def calibration_qoi(x, x_prev, params, grad_u, grad_u_prev, spec, data, weight):
     return 0.5 * torch.sum(mis * mis)
 
 
+def uniaxial_calibration_qoi(x, x_prev, params, grad_u, grad_u_prev, spec, data, weight):
+    """cmad/qois/uniaxial_calibration.py:69-85 with ``uniaxial_stress_idx = spec.uniaxial_stress_idx``
+    and ``stretch_var_idx = 2`` (the off-axis stretches at ``x[7:9]``); data / weight (3,) of the step."""
+    cauchy = cauchy_fun(spec)(x, x_prev, params, grad_u, grad_u_prev, spec)
+    i = spec.uniaxial_stress_idx
+    pred = torch.stack([cauchy[i, i], x[7] - 1.0, x[8] - 1.0])
+    mis = (pred - data) * weight
+    return 0.5 * torch.sum(mis * mis)
+
+
+def _qoi_of(weight):
+    """Calibration for a (3, 3) weight, UniaxialCalibration for per-step weights (3, N+1):
+    returns (qoi function, weight-at-step accessor)."""
+    w = torch.as_tensor(np.asarray(weight), dtype=DT)
+    if tuple(w.shape) == (3, 3):
+        return calibration_qoi, (lambda step: w)
+    return uniaxial_calibration_qoi, (lambda step: w[:, step])
+
+
 # --------------------------------------------------------------------------
 # MP drivers (cmad/cli/primal.py:129-176, cmad/objectives/mp_objective.py)
 # --------------------------------------------------------------------------
@@ -770,13 +789,13 @@ def mp_primal(parameters: OracleParameters, F: np.ndarray, spec: ModelSpec,
     return xi, cauchy, iters, norms, flags
 
 
-def _step_derivs(x, x_prev, params, gu, gup, spec, parameters, data_s, weight):
+def _step_derivs(x, x_prev, params, gu, gup, spec, parameters, data_s, weight, qoi_fn=calibration_qoi):
     A = dC_dxi(x, x_prev, params, gu, gup, spec).numpy()
     B = dC_dxi_prev(x, x_prev, params, gu, gup, spec).numpy()
     dCdp = parameters.active_params_jacobian(
         tree_map(lambda t: t.numpy(), dC_dparams(x, x_prev, params, gu, gup, spec)),
         spec.num_dofs)
-    q = lambda *a: calibration_qoi(*a, spec, data_s, weight)
+    q = lambda *a: qoi_fn(*a, spec, data_s, weight)
     dJdx = jacfwd(q, argnums=0)(x, x_prev, params, gu, gup).numpy().reshape(1, -1)
     dJdp = parameters.active_params_jacobian(
         tree_map(lambda t: t.numpy(), jacrev(q, argnums=2)(x, x_prev, params, gu, gup)), 1)
@@ -791,14 +810,14 @@ def mp_objective_adjoint(parameters: OracleParameters, F, data, weight, spec: Mo
         parameters.set_active_values_from_flat(np.asarray(flat_active_values, float), are_canonical)
     params = to_torch_tree(parameters.values)
     N = F.shape[-1] - 1
-    w = torch.as_tensor(weight, dtype=DT)
+    qoi_fn, w_at = _qoi_of(weight)
     xs = [torch.as_tensor(spec.init_xi())]
     J = 0.0
     for step in range(1, N + 1):                                   # :73-87
         gu = _grad_u_from_F(F[:, :, step], spec); gup = _grad_u_from_F(F[:, :, step - 1], spec)
         x, _ = newton_imperative(xs[-1], params, gu, gup, spec)
         d = torch.as_tensor(data[..., step], dtype=DT)
-        J += float(calibration_qoi(x, xs[-1], params, gu, gup, spec, d, w))
+        J += float(qoi_fn(x, xs[-1], params, gu, gup, spec, d, w_at(step)))
         xs.append(x)
     Pa = parameters.num_active_params
     g = np.zeros((1, Pa)); hist = np.zeros((spec.num_dofs, 1))
@@ -806,7 +825,7 @@ def mp_objective_adjoint(parameters: OracleParameters, F, data, weight, spec: Mo
         gu = _grad_u_from_F(F[:, :, step], spec); gup = _grad_u_from_F(F[:, :, step - 1], spec)
         d = torch.as_tensor(data[..., step], dtype=DT)
         A, B, dCdp, dJdx, dJdp = _step_derivs(xs[step], xs[step - 1], params, gu, gup, spec,
-                                              parameters, d, w)
+                                              parameters, d, w_at(step), qoi_fn)
         phi = np.linalg.solve(A.T, -dJdx.T + hist)
         hist = -B.T @ phi
         g += phi.T @ dCdp + dJdp
@@ -822,7 +841,7 @@ def mp_objective_direct(parameters: OracleParameters, F, data, weight, spec: Mod
         parameters.set_active_values_from_flat(np.asarray(flat_active_values, float), are_canonical)
     params = to_torch_tree(parameters.values)
     N = F.shape[-1] - 1
-    w = torch.as_tensor(weight, dtype=DT)
+    qoi_fn, w_at = _qoi_of(weight)
     Pa = parameters.num_active_params
     x_prev = torch.as_tensor(spec.init_xi())
     J = 0.0; g = np.zeros((1, Pa)); dxdp = np.zeros((spec.num_dofs, Pa))
@@ -830,8 +849,8 @@ def mp_objective_direct(parameters: OracleParameters, F, data, weight, spec: Mod
         gu = _grad_u_from_F(F[:, :, step], spec); gup = _grad_u_from_F(F[:, :, step - 1], spec)
         x, _ = newton_imperative(x_prev, params, gu, gup, spec)
         d = torch.as_tensor(data[..., step], dtype=DT)
-        J += float(calibration_qoi(x, x_prev, params, gu, gup, spec, d, w))
-        A, B, dCdp, dJdx, dJdp = _step_derivs(x, x_prev, params, gu, gup, spec, parameters, d, w)
+        J += float(qoi_fn(x, x_prev, params, gu, gup, spec, d, w_at(step)))
+        A, B, dCdp, dJdx, dJdp = _step_derivs(x, x_prev, params, gu, gup, spec, parameters, d, w_at(step), qoi_fn)
         dxdp = np.linalg.solve(A, -dCdp - B @ dxdp)
         g += dJdx @ dxdp + dJdp
         x_prev = x

@@ -533,6 +533,45 @@ def _rate_job(job):
     return out
 
 
+
+# --------------------------------------------------------------------------- #
+#  G. UniaxialCalibration QoI (cmad/qois/uniaxial_calibration.py) on the       #
+#     UNIAXIAL_STRESS deformation type: axial stress + the two off-axis strains #
+# --------------------------------------------------------------------------- #
+def _uniaxial_qoi_job(job):
+    from cmad.models.deformation_types import DefType
+    from cmad.qois.uniaxial_calibration import UniaxialCalibration
+    kind, scaled = job
+    F = deftype_F("UNIAXIAL_STRESS", nsteps=32)
+    N = F.shape[2] - 1
+    vals, act, tr = objective_trees(kind, scaled)
+    Po = Parameters(vals, act, tr)
+    mo_ = SmallElasticPlastic(Po, def_type=DefType.UNIAXIAL_STRESS)
+    data = np.zeros((3, N + 1))
+    mo_.set_xi_to_init_vals()
+    for step in range(1, N + 1):
+        mo_.gather_global(mp_U_from_F(F[:, :, step]), mp_U_from_F(F[:, :, step - 1]))
+        newton_solve(mo_)
+        mo_.seed_none(); mo_.evaluate_cauchy()
+        xi = mo_.xi()
+        data[:, step] = [mo_.Sigma()[0, 0], float(xi[2][0]) - 1.0, float(xi[2][1]) - 1.0]
+        mo_.advance_xi()
+    t = np.arange(N + 1)
+    # per-step weights (weight_at_step = weight[:, step]): stress in its own units, strains scaled up
+    weight = np.stack([1.0 + 0.25 * np.sin(0.7 * t), 2.0e4 * (1.0 + 0.1 * np.cos(0.3 * t)), 1.0e4 + 50.0 * t])
+    qoi = UniaxialCalibration(mo_, data, weight, uniaxial_stress_idx=0, stretch_var_idx=2)
+    offset = 1.1 * Po.flat_active_values(False)
+    Po.set_active_values_from_flat(offset, False)
+    x = Po.flat_active_values(True)
+    out = {"F": F, "data": data, "weight": weight, "x_canonical": x, "active_native": offset,
+           "active_idx": np.asarray(Po.active_idx)}
+    for name, ctor in (("adjoint", MPAdjointObjective), ("direct", MPDirectObjective)):
+        Po.set_active_values_from_flat(offset, False)
+        mo_.set_xi_to_init_vals()             # see _objective_job: MPObjective stores the model's current xi as step 0
+        J, g = ctor(qoi, F).evaluate(x)
+        out[f"J_{name}"], out[f"grad_{name}"] = float(J), np.asarray(g, float)
+    return out
+
 # --------------------------------------------------------------------------- #
 def main():
     ap = argparse.ArgumentParser()
@@ -604,6 +643,21 @@ def main():
             print("hessian", nm, r["J"], r["grad"], np.linalg.eigvalsh(r["hessian"]))
         np.savez_compressed(os.path.join(HERE, "ref_mp_hessian.npz"), **out)
 
+    if only is None or "hessian_rot" in only:
+        # the direct-adjoint Hessian with rotated material axes (anisotropic Hill, two hardening laws)
+        w = np.array([[1.0, 0.5, 0.0], [0.5, 1.0, 0.0], [0.0, 0.0, 0.25]])
+        jobs, names = [], []
+        for kind in ("hill_rot",):
+            for scaled in (True, False):
+                jobs.append((kind, scaled, two_leg_F(11, 10, scale=1.5), w))
+                names.append(f"{kind}.{'scaled' if scaled else 'native'}")
+        out = {}
+        for nm, r in zip(names, pool.map(_hessian_job, jobs, chunksize=1)):
+            for k, v in r.items():
+                out[f"{nm}.{k}"] = v
+            print("hessian_rot", nm, r["J"], r["grad"], np.linalg.eigvalsh(r["hessian"]))
+        np.savez_compressed(os.path.join(HERE, "ref_mp_hessian_rot.npz"), **out)
+
     if only is None or "hessian_jvp" in only:
         w = np.array([[1.0, 0.5, 0.0], [0.5, 1.0, 0.0], [0.0, 0.0, 0.25]])
         jobs, names = [], []
@@ -674,6 +728,15 @@ def main():
             print("rate", kind, "iters", np.bincount(r["iters"]), "traced", np.bincount(r["traced_iters"]),
                   "alpha", r["xi"][-1, 6])
         np.savez_compressed(os.path.join(HERE, "ref_rate_model.npz"), **out)
+
+    if only is None or "uniaxial_qoi" in only:
+        jobs = [(k, sc) for k in ("J2", "hill", "hosford") for sc in (True, False)]
+        out = {}
+        for (kind, sc), r in zip(jobs, pool.map(_uniaxial_qoi_job, jobs, chunksize=1)):
+            for k, v in r.items():
+                out[f"{kind}.{'scaled' if sc else 'native'}.{k}"] = v
+            print("uniaxial qoi", kind, sc, r["J_adjoint"], r["grad_adjoint"], r["grad_direct"])
+        np.savez_compressed(os.path.join(HERE, "ref_uniaxial_qoi.npz"), **out)
 
     if only is None or "rate_objective" in only:
         # MPAdjointObjective / MPDirectObjective + Calibration over SmallRateElasticPlastic

@@ -127,3 +127,65 @@ def test_cuda_objectives_vs_reference_def_types(cuda_device, case, tag):
         r = obj.evaluate(DT[f"{pre}.x_canonical"])
         assert abs(r.J - DT[f"{pre}.J_{strategy}"]) < 1e-10 * abs(r.J), (case, tag, strategy)
         assert rel_err(r.grad, DT[f"{pre}.grad_{strategy}"]) < 1e-8, (case, tag, strategy, r.grad)
+
+
+# ------------------------------------------------------------------------------------------ #
+#  UniaxialCalibration (cmad/qois/uniaxial_calibration.py): axial stress + the two off-axis   #
+#  strains with per-step weights, run by the reference (make_reference_golden.py section G,   #
+#  fixture ref_uniaxial_qoi.npz)                                                               #
+# ------------------------------------------------------------------------------------------ #
+UQ = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_uniaxial_qoi.npz"))
+UQ_CASES = sorted({k.rsplit(".", 1)[0] for k in UQ.files})
+
+
+def test_uniaxial_qoi_fixture_is_consistent():
+    for case in UQ_CASES:
+        assert abs(UQ[f"{case}.J_adjoint"] - UQ[f"{case}.J_direct"]) < 1e-12 * abs(UQ[f"{case}.J_direct"])
+        assert rel_err(UQ[f"{case}.grad_adjoint"], UQ[f"{case}.grad_direct"]) < 1e-8
+        assert UQ[f"{case}.weight"].shape == UQ[f"{case}.data"].shape == (3, UQ[f"{case}.F"].shape[2])
+        assert np.abs(UQ[f"{case}.data"][1:]).max() > 1e-3           # lateral strains are measured
+
+
+@pytest.mark.parametrize("case", ["J2.native", "hosford.scaled"])
+def test_torch_oracle_uniaxial_qoi_vs_reference(case):
+    from oracle import cmad_oracle as co
+    kind, tag = case.split(".")
+    values, act, tr = objective_trees(kind, tag == "scaled")
+    P = co.OracleParameters(values, act, tr)
+    spec = co.ModelSpec(kind="small_elastic_plastic", def_type=co.UNIAXIAL_STRESS)
+    J, g = co.mp_objective_adjoint(P, UQ[f"{case}.F"], UQ[f"{case}.data"], UQ[f"{case}.weight"], spec,
+                                   UQ[f"{case}.x_canonical"], True)
+    assert abs(J - UQ[f"{case}.J_adjoint"]) < 1e-10 * abs(J)
+    assert rel_err(g, UQ[f"{case}.grad_adjoint"]) < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", UQ_CASES)
+def test_cuda_uniaxial_qoi_vs_reference(cuda_device, case):
+    """`MPAdjointObjective / MPDirectObjective(UniaxialCalibration(model, data, weight, 0, 2), F)` on
+    the CUDA path (K1-DT + K2-DT with CMADX_QOI_UNIAXIAL_CALIBRATION)."""
+    from cmad_b200 import objectives as ob
+    kind, tag = case.split(".")
+    for strategy, ctor in (("adjoint", ob.MPAdjointObjective), ("direct", ob.MPDirectObjective)):
+        values, act, tr = objective_trees(kind, tag == "scaled")
+        P = Parameters(values, act, tr)
+        assert np.array_equal(P.active_idx, UQ[f"{case}.active_idx"])
+        model = ob.SmallElasticPlastic(P, def_type=ob.UNIAXIAL_STRESS)
+        qoi = ob.UniaxialCalibration(model, UQ[f"{case}.data"], UQ[f"{case}.weight"], uniaxial_stress_idx=0, stretch_var_idx=2)
+        r = ctor(qoi, UQ[f"{case}.F"], device=cuda_device).evaluate(UQ[f"{case}.x_canonical"])
+        assert abs(r.J - UQ[f"{case}.J_{strategy}"]) < 1e-10 * abs(r.J), (case, strategy)
+        assert rel_err(r.grad, UQ[f"{case}.grad_{strategy}"]) < 1e-8, (case, strategy, r.grad)
+
+
+@pytest.mark.gpu
+def test_cuda_uniaxial_qoi_refusals(cuda_device):
+    from cmad_b200 import objectives as ob
+    case = "J2.scaled"
+    values, act, tr = objective_trees("J2", True)
+    P = Parameters(values, act, tr)
+    with pytest.raises(NotImplementedError):          # a FULL_3D model has no off-axis stretches
+        ob.UniaxialCalibration(ob.SmallElasticPlastic(P), UQ[f"{case}.data"], UQ[f"{case}.weight"])
+    model = ob.SmallElasticPlastic(P, def_type=ob.UNIAXIAL_STRESS)
+    qoi = ob.UniaxialCalibration(model, UQ[f"{case}.data"], UQ[f"{case}.weight"])
+    with pytest.raises(NotImplementedError):          # no second-order pass for this QoI
+        ob.MPDirectAdjointObjective(qoi, UQ[f"{case}.F"], device=cuda_device).evaluate(UQ[f"{case}.x_canonical"])

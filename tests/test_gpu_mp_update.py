@@ -503,3 +503,23 @@ def test_streaming_kernel_equals_one_pass_kernel(cuda_device, case, mode, varian
             xi = torch.zeros((7, ld), dtype=torch.float64, device=cuda_device)
             xi[:, :n] = a_["xi"]
         assert bool((a_["flags"] & 2).any()) or n < 32
+
+
+@pytest.mark.parametrize("def_type,comps", [(1, 3), (2, 1)])
+def test_host_buffer_path_other_deformation_types(cuda_device, def_type, comps):
+    """cmadx_mp_update_host for PLANE_STRESS / UNIAXIAL_STRESS (n_xi 8 / 9): same bits as the
+    device-buffer entry point, chunked."""
+    rng = np.random.default_rng(3)
+    values, act, tr = param_tree("J2")
+    P = Parameters(values, act, tr); mat = material_from_values(values); pid = active_param_ids(P)
+    nw = NewtonSettings()
+    n = 20011
+    e = rng.normal(size=(comps, n)) * 2e-3
+    outs = ("xi", "sigma", "dsig_deps", "dxi_deps", "dC_dp", "iters", "flags", "cnorm")
+    xi0 = mp.init_xi(mat, n, "cpu", def_type=def_type)
+    dev = mp.mp_update(mat, nw, pid, xi0.to(cuda_device), torch.from_numpy(e).to(cuda_device), outputs=outs, def_type=def_type)
+    host = mp.mp_update_host(mat, nw, pid, xi0, e, outputs=outs, chunk_points=4096, def_type=def_type)
+    torch.cuda.synchronize()
+    assert bool((dev["flags"] & 2).any())
+    for k in outs:
+        assert torch.equal(dev[k].cpu(), host[k]), k

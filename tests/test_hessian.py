@@ -300,7 +300,7 @@ def test_cuda_hessian_vs_reference_def_types(cuda_device, case):
 @pytest.mark.gpu
 def test_hessian_entry_point_edge_cases(cuda_device):
     """Argument errors and degenerate sizes of cmadx_mp_objective_hessian: no active parameter
-    (J only), rotated axes (unsupported -> NotImplementedError, never a silent fallback), an
+    (J only), an active rotation-matrix entry (unsupported -> NotImplementedError, never a silent fallback), an
     unknown flag bit (EINVAL), and an elastic-only history (zero plastic sensitivity terms)."""
     import ctypes as C
     import torch
@@ -314,8 +314,9 @@ def test_hessian_entry_point_edge_cases(cuda_device):
     out = gpu_local_evaluator(SmallElasticPlastic(Parameters(v, a, t)), sh, data, w, "direct_adjoint",
                               cuda_device)().cpu().numpy()
     assert out.shape == (1,) and np.isfinite(out[0]) and out[0] > 0
-    # (2) rotated axes
+    # (2) rotated axes with an active rotation-matrix entry: not differentiated twice -> refused
     v, a, t = param_tree("J2", ("voce",), rotation=rotation_matrix([1.0, 2.0, -0.5], 0.7))
+    a["rotation matrix"] = True
     with pytest.raises(NotImplementedError):
         gpu_local_evaluator(SmallElasticPlastic(Parameters(v, a, t)), sh, data, w, "direct_adjoint", cuda_device)()
     # (3) elastic-only history: H = d2J/dp2 through the elastic constants only; flow-stress block zero
@@ -385,3 +386,52 @@ def test_cuda_jvp_strategy_vs_reference(cuda_device, case):
     P2 = Parameters(*objective_trees(kind, mode == "scaled"))
     r = MPDirectAdjointObjective(Calibration(SmallElasticPlastic(P2), data, w), F, device=cuda_device).evaluate(x)
     assert hess_err(r.hessian, HJ[f"{case}.hessian"]) < 1e-8
+
+
+# ------------------------------------------------------------------------------------------ #
+#  Rotated material axes in the direct-adjoint Hessian (anisotropic Hill, Voce + linear),     #
+#  fixture ref_mp_hessian_rot.npz from the reference's MPDirectAdjointObjective                #
+# ------------------------------------------------------------------------------------------ #
+_HR_PATH = os.path.join(G, "ref_mp_hessian_rot.npz")
+HR = np.load(_HR_PATH)
+CASES_ROT = sorted({k.rsplit(".", 1)[0] for k in HR.files})
+
+
+@pytest.mark.parametrize("case", CASES_ROT)
+def test_torch_oracle_hessian_rotated_axes_vs_reference(case):
+    kind, mode = case.split(".")
+    values, act, tr = objective_trees(kind, mode == "scaled")
+    assert np.abs(np.asarray(values["rotation matrix"]) - np.eye(3)).max() > 0.1
+    P = co.OracleParameters(values, act, tr)
+    F, data = HR[f"{case}.F"][:, :, :6], HR[f"{case}.data"][:, :, :6]        # a prefix keeps the torch run short ...
+    J, g, H = co.mp_objective_direct_adjoint(P, F, data, HR[f"{case}.weight"], co.ModelSpec(),
+                                             HR[f"{case}.x_canonical"], True, reference_qoi_cross_terms=True)
+    assert np.isfinite(H).all() and np.array_equal(H, H.T)                   # ... the full history is compared on the GPU
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES_ROT)
+def test_cuda_hessian_rotated_axes_vs_reference(cuda_device, case):
+    from cmad_b200.objectives import Calibration, MPAdjointObjective, MPDirectAdjointObjective, SmallElasticPlastic
+    kind, mode = case.split(".")
+    x = HR[f"{case}.x_canonical"]
+    F, data, w = HR[f"{case}.F"], HR[f"{case}.data"], HR[f"{case}.weight"]
+
+    def run(compat):
+        P = Parameters(*objective_trees(kind, mode == "scaled"))
+        return MPDirectAdjointObjective(Calibration(SmallElasticPlastic(P), data, w), F, device=cuda_device,
+                                        reference_qoi_cross_terms=compat).evaluate(x), P
+    r, _ = run(True)
+    assert abs(r.J - HR[f"{case}.J"]) < 1e-11 * abs(r.J)
+    assert np.abs(r.grad - HR[f"{case}.grad"]).max() < 1e-9 * np.abs(r.grad).max()
+    assert hess_err(r.hessian, HR[f"{case}.hessian"]) < 1e-8, hess_err(r.hessian, HR[f"{case}.hessian"])
+    # the complete Hessian = derivative of the CUDA adjoint gradient
+    rc, P = run(False)
+    grad_obj = MPAdjointObjective(Calibration(SmallElasticPlastic(P), data, w), F, device=cuda_device)
+    fd = np.zeros_like(rc.hessian)
+    for c in range(len(x)):
+        h = 1e-6 * max(abs(x[c]), 1e-2)
+        xp_, xm_ = x.copy(), x.copy()
+        xp_[c] += h; xm_[c] -= h
+        fd[:, c] = (grad_obj.evaluate(xp_).grad - grad_obj.evaluate(xm_).grad) / (2 * h)
+    assert hess_err(rc.hessian, 0.5 * (fd + fd.T)) < 2e-5, hess_err(rc.hessian, 0.5 * (fd + fd.T))
