@@ -23,7 +23,7 @@ OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(5)
 VERSION = 100        # CMADX_VERSION of include/cmad_b200.h this binding was written against
 MODEL_SMALL_ELASTIC_PLASTIC, MODEL_ELASTIC, MODEL_SMALL_RATE_ELASTIC_PLASTIC = 0, 1, 2
 QOI_CALIBRATION, QOI_UNIAXIAL_CALIBRATION = 0, 1
-YIELD_J2, YIELD_HILL, YIELD_HOSFORD = 0, 1, 2
+YIELD_J2, YIELD_HILL, YIELD_HOSFORD, YIELD_BARLAT = 0, 1, 2, 3
 DEF_FULL_3D, DEF_PLANE_STRESS, DEF_UNIAXIAL_STRESS = 0, 1, 2
 ELASTIC_PAIRS = [("E", "nu"), ("E", "mu"), ("E", "kappa"), ("E", "lambda"), ("kappa", "mu"),
                  ("kappa", "nu"), ("kappa", "lambda"), ("lambda", "mu"), ("lambda", "nu"),
@@ -31,7 +31,9 @@ ELASTIC_PAIRS = [("E", "nu"), ("E", "mu"), ("E", "kappa"), ("E", "lambda"), ("ka
 HARD_VOCE, HARD_LINEAR = 1, 2
 (P_EL0, P_EL1, P_Y, P_VOCE_S, P_VOCE_D, P_LIN_K, P_HILL_F, P_HILL_G, P_HILL_H, P_HILL_L,
  P_HILL_M, P_HILL_N, P_HOSFORD_A, P_Q00) = range(14)
-NUM_PARAM_IDS = P_Q00 + 9
+P_BARLAT_C0 = P_Q00 + 9
+P_BARLAT_A = P_BARLAT_C0 + 18
+NUM_PARAM_IDS = P_BARLAT_A + 1
 MAX_ACTIVE = 16
 NEWTON_TRACED, NEWTON_IMPERATIVE = 0, 1
 NEWTON_F_GENERIC = 1
@@ -46,7 +48,7 @@ class Material(C.Structure):
                 ("hardening_mask", C.c_int32), ("elastic", C.c_double * 2), ("Y", C.c_double),
                 ("voce_S", C.c_double), ("voce_D", C.c_double), ("linear_K", C.c_double),
                 ("hill", C.c_double * 6), ("hosford_a", C.c_double), ("Q", C.c_double * 9),
-                ("yield_tol", C.c_double)]
+                ("yield_tol", C.c_double), ("barlat", C.c_double * 18), ("barlat_a", C.c_double)]
 
 
 class Newton(C.Structure):

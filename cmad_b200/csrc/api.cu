@@ -137,7 +137,7 @@ int make_dev_mat(const cmadx_material_t* mat, DevMat* o) {
     o->d2mu[0] = mu.aa; o->d2mu[1] = mu.ab; o->d2mu[2] = mu.bb;
     o->model = mat->model;
     if (mat->model == CMADX_MODEL_SMALL_ELASTIC_PLASTIC || mat->model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC) {
-        if (mat->yield < CMADX_YIELD_J2 || mat->yield > CMADX_YIELD_HOSFORD) return CMADX_EINVAL;
+        if (mat->yield < CMADX_YIELD_J2 || mat->yield > CMADX_YIELD_BARLAT) return CMADX_EINVAL;
         if (mat->hardening_mask & ~(CMADX_HARD_VOCE | CMADX_HARD_LINEAR)) return CMADX_EINVAL;
         o->yield = mat->yield;
         o->hmask = mat->hardening_mask;
@@ -152,6 +152,12 @@ int make_dev_mat(const cmadx_material_t* mat, DevMat* o) {
         static const bool libm_root = std::getenv("CMADX_HOSFORD_LIBM_ROOT") != nullptr;      // A/B measurements
         o->root_int = libm_root ? 0 : o->a_int;
         o->yield_tol = mat->yield_tol;
+        if (mat->yield == CMADX_YIELD_BARLAT) {
+            if (!(mat->barlat_a > 1.0)) return CMADX_EINVAL;
+            for (int i = 0; i < 18; ++i) o->barlat[i] = mat->barlat[i];
+            o->a = mat->barlat_a;
+            o->inv_a = 1.0 / mat->barlat_a;
+        }
     }
     bool ident = true;
     for (int i = 0; i < 9; ++i) {
@@ -209,7 +215,8 @@ static int build_args(const cmadx_material_t* mat, const cmadx_newton_t* nw,
         // do not carry it); rotation-matrix entries: FULL_3D SmallElasticPlastic, dC/dp output
         // of the generic kernels only (see write_point_outputs)
         if (pid == CMADX_P_HOSFORD_A && b->def_type != CMADX_DEF_FULL_3D) return CMADX_EUNSUPPORTED;
-        if (pid >= CMADX_P_Q00) {
+        if (pid >= CMADX_P_BARLAT_C0 && mat->yield != CMADX_YIELD_BARLAT) return CMADX_EINVAL;
+        if (pid >= CMADX_P_Q00 && pid < CMADX_P_BARLAT_C0) {
             if (b->def_type != CMADX_DEF_FULL_3D || A->m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC)
                 return CMADX_EUNSUPPORTED;
             A->nw.flags |= CMADX_NEWTON_F_GENERIC;       // not the J2 radial / reduced Hosford specialisations
@@ -217,6 +224,13 @@ static int build_args(const cmadx_material_t* mat, const cmadx_newton_t* nw,
         A->pid[c] = pid;
     }
     A->n_active = n_active;
+    if (A->m.yield == CMADX_YIELD_BARLAT && A->m.model != CMADX_MODEL_ELASTIC) {
+        // Yld2004-18p: SmallElasticPlastic in FULL_3D, one-pass generic kernels
+        if (A->m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC || b->def_type != CMADX_DEF_FULL_3D)
+            return CMADX_EUNSUPPORTED;
+        A->nw.flags &= ~(CMADX_NEWTON_F_CTA | CMADX_NEWTON_F_QUEUE | CMADX_NEWTON_F_STREAM);
+        A->nw.defer_request = 0;
+    }
     if (b->n < 0 || b->ld < b->n) return CMADX_EINVAL;
     if (A->m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC &&
         (A->m.rot || b->def_type != CMADX_DEF_FULL_3D))
@@ -615,6 +629,8 @@ static int check_history(const cmadx_material_t* mat, const cmadx_mp_history_t* 
     if (rate && ((sc != 6 && sc != 9) || dm->rot)) return CMADX_EUNSUPPORTED;
     if (history_def_type(h) != CMADX_DEF_FULL_3D && dm->rot) return CMADX_EUNSUPPORTED;
     if (h->n > 0 && (!h->strain || !h->xi_hist)) return CMADX_EINVAL;
+    // Yld2004-18p: SmallElasticPlastic in FULL_3D (K1, forward history, K2)
+    if (dm->yield == CMADX_YIELD_BARLAT && (rate || history_def_type(h) != CMADX_DEF_FULL_3D)) return CMADX_EUNSUPPORTED;
     if (h->qoi_kind != CMADX_QOI_CALIBRATION) {
         if (h->qoi_kind != CMADX_QOI_UNIAXIAL_CALIBRATION) return CMADX_EINVAL;
         if (history_def_type(h) != CMADX_DEF_UNIAXIAL_STRESS || rate) return CMADX_EUNSUPPORTED;
@@ -686,7 +702,8 @@ static int objective(const cmadx_material_t* mat, const int32_t* active_pid, int
     for (int c = 0; c < n_active; ++c) {
         const int pid = active_pid[c];
         if (pid < 0 || pid >= CMADX_NUM_PARAM_IDS) return CMADX_EINVAL;
-        if (pid >= CMADX_P_Q00) return CMADX_EUNSUPPORTED;
+        if (pid >= CMADX_P_Q00 && pid < CMADX_P_BARLAT_C0) return CMADX_EUNSUPPORTED;
+        if (pid >= CMADX_P_BARLAT_C0 && A.m.yield != CMADX_YIELD_BARLAT) return CMADX_EINVAL;
         A.pid[c] = pid;
     }
     A.n_active = n_active;
@@ -830,7 +847,8 @@ int cmadx_mp_objective_hessian(const cmadx_material_t* mat, const int32_t* activ
     if (flags & ~CMADX_HESS_F_REFERENCE_QOI_CROSS) return CMADX_EINVAL;
     A.hess_flags = flags;
     if (int rc = check_history(mat, hist, &A.m)) return rc;
-    if (A.m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC || hist->qoi_kind != CMADX_QOI_CALIBRATION)
+    if (A.m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC || hist->qoi_kind != CMADX_QOI_CALIBRATION ||
+        A.m.yield == CMADX_YIELD_BARLAT)
         return CMADX_EUNSUPPORTED;
     const int dt = history_def_type(hist);     // rotated axes: FULL_3D only (check_history refuses the other def-types)
     if (n_active < 0 || n_active > CMADX_MAX_ACTIVE || (n_active > 0 && !active_pid)) return CMADX_EINVAL;
@@ -865,6 +883,7 @@ static int check_fe_block(const cmadx_material_t* mat, const cmadx_fe_block_t* b
         if (!allow_rate || A->m.rot) return CMADX_EUNSUPPORTED;
         if (blk->n_elems > 0 && !blk->U_prev) return CMADX_EINVAL;
     } else if (A->m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC) return CMADX_EUNSUPPORTED;
+    if (A->m.yield == CMADX_YIELD_BARLAT) return CMADX_EUNSUPPORTED;      // material-point path only
     const cmadx_fe_block_t& b = *blk;
     if (b.n_elems < 0 || b.n_dofs < 0) return CMADX_EINVAL;
     // tet4 / hex8 with any volume rule (cmad/cli/common.py:497-540: up to 24 / 64 points); the

@@ -94,6 +94,7 @@ cudaError_t launch_generic(const HistArgs& A, unsigned nblk, cudaStream_t s) {
     case CMADX_YIELD_J2: mp_history_kernel<1, LIST><<<nblk, MP_BLOCK, 0, s>>>(A); break;
     case CMADX_YIELD_HILL: mp_history_kernel<2, LIST><<<nblk, MP_BLOCK, 0, s>>>(A); break;
     case CMADX_YIELD_HOSFORD: mp_history_kernel<3, LIST><<<nblk, MP_BLOCK, 0, s>>>(A); break;
+    case CMADX_YIELD_BARLAT: mp_history_kernel<4, LIST><<<nblk, MP_BLOCK, 0, s>>>(A); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

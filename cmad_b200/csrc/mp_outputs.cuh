@@ -200,7 +200,7 @@ CMADX_DEV void write_point_outputs(const MpArgs& A, const int64_t i, const doubl
         // the reference builds), and dC/de_m = -(dC/dx[:, :6] - [I6; 0]) in material axes.
         for (int c = 0; c < A.n_active; ++c) {
             const int q = A.pid[c] - CMADX_P_Q00;
-            if (q < 0) continue;
+            if (q < 0 || q >= 9) continue;
             double col[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
             if (pl) {
                 const int qi = q / 3, qj = q % 3;

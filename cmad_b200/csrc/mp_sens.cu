@@ -374,6 +374,8 @@ cudaError_t launch_sens_rot(const SensArgs& A, cudaStream_t stream) {
         e0 = sens_launch(mp_sens_kernel<CMADX_YIELD_HILL, ADJOINT, NA, true>, A, ADJOINT, nblk, stream); break;
     case CMADX_YIELD_HOSFORD:
         e0 = sens_launch(mp_sens_kernel<CMADX_YIELD_HOSFORD, ADJOINT, NA, true>, A, ADJOINT, nblk, stream); break;
+    case CMADX_YIELD_BARLAT:
+        e0 = sens_launch(mp_sens_kernel<CMADX_YIELD_BARLAT, ADJOINT, NA, true>, A, ADJOINT, nblk, stream); break;
     default: return cudaErrorInvalidValue;
     }
     if (e0 != cudaSuccess) return e0;
@@ -394,6 +396,9 @@ cudaError_t launch_sens_t(const SensArgs& A, cudaStream_t stream) {
         e0 = sens_launch(mp_sens_kernel<CMADX_YIELD_HILL, ADJOINT, NA_MAX>, A, ADJOINT, nblk, stream); break;
     case CMADX_YIELD_HOSFORD:
         e0 = sens_launch(mp_sens_kernel<CMADX_YIELD_HOSFORD, ADJOINT, NA_MAX>, A, ADJOINT, nblk, stream); break;
+    case CMADX_YIELD_BARLAT:
+        if (NA_MAX < CMADX_MAX_ACTIVE) return cudaErrorInvalidValue;       // one instantiation: see launch_mp_sens
+        e0 = sens_launch(mp_sens_kernel<CMADX_YIELD_BARLAT, ADJOINT, CMADX_MAX_ACTIVE>, A, ADJOINT, nblk, stream); break;
     default: return cudaErrorInvalidValue;
     }
     if (e0 != cudaSuccess) return e0;
@@ -415,7 +420,7 @@ cudaError_t launch_reduce_partials(const double* partials, int64_t nblk, int nco
 cudaError_t launch_mp_sens(const SensArgs& A, bool adjoint, cudaStream_t stream) {
     if (A.h.n == 0) return cudaMemsetAsync(A.h.result, 0, sizeof(double) * (1 + A.n_active), stream);
     if (A.m.rot) return adjoint ? launch_sens_rot<true>(A, stream) : launch_sens_rot<false>(A, stream);
-    if (A.n_active <= 6) return adjoint ? launch_sens_t<true, 6>(A, stream) : launch_sens_t<false, 6>(A, stream);
+    if (A.n_active <= 6 && A.m.yield != CMADX_YIELD_BARLAT) return adjoint ? launch_sens_t<true, 6>(A, stream) : launch_sens_t<false, 6>(A, stream);
     return adjoint ? launch_sens_t<true, CMADX_MAX_ACTIVE>(A, stream) : launch_sens_t<false, CMADX_MAX_ACTIVE>(A, stream);
 }
 

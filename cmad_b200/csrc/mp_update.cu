@@ -144,6 +144,7 @@ cudaError_t launch_mp_update_sep(const MpArgs& A, cudaStream_t stream) {
     case CMADX_YIELD_J2: return launch_yk<CMADX_YIELD_J2>(A, stream);
     case CMADX_YIELD_HILL: return launch_yk<CMADX_YIELD_HILL>(A, stream);
     case CMADX_YIELD_HOSFORD: return launch_yk<CMADX_YIELD_HOSFORD>(A, stream);
+    case CMADX_YIELD_BARLAT: return launch_yk<CMADX_YIELD_BARLAT>(A, stream);
     }
     return cudaErrorInvalidValue;
 }
@@ -172,6 +173,7 @@ cudaError_t launch_mp_update_sep_list(const MpArgs& A, cudaStream_t stream) {
     case CMADX_YIELD_J2: return launch_list_yk<CMADX_YIELD_J2>(A, stream, sms);
     case CMADX_YIELD_HILL: return launch_list_yk<CMADX_YIELD_HILL>(A, stream, sms);
     case CMADX_YIELD_HOSFORD: return launch_list_yk<CMADX_YIELD_HOSFORD>(A, stream, sms);
+    case CMADX_YIELD_BARLAT: return launch_list_yk<CMADX_YIELD_BARLAT>(A, stream, sms);
     }
     return cudaErrorInvalidValue;
 }

@@ -31,6 +31,7 @@ struct DevMat {
     double a, inv_a;          // Hosford exponent and 1 / a (host-computed: the same correctly rounded quotient)
     double Q[9];
     double yield_tol;
+    double barlat[18];        // Yld2004-18p: sp_12 .. sp_66, dp_12 .. dp_66 (a / inv_a hold its exponent)
     double dlam[2], dmu[2];   // d(lambda, mu)/d(elastic[0..1])
     double d2lam[3], d2mu[3]; // second derivatives (00, 01, 11): Hessian path only
     int hmask, rot, model, yield;
@@ -316,6 +317,10 @@ template <> struct YieldFn<CMADX_YIELD_HOSFORD> {
         n[1] = 0.0; n[2] = 0.0; n[4] = 0.0;
     }
 };
+
+}  // namespace cmadx
+#include "barlat.cuh"
+namespace cmadx {
 
 // --------------------------------------------------------------------------
 // register-resident dense LU.

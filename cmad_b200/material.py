@@ -15,7 +15,9 @@ import numpy as np
 from . import _lib as L
 from .parameters import Parameters, tree_leaves_with_path
 
-_YIELD = {"J2": L.YIELD_J2, "hill": L.YIELD_HILL, "hosford": L.YIELD_HOSFORD}
+_YIELD = {"J2": L.YIELD_J2, "hill": L.YIELD_HILL, "hosford": L.YIELD_HOSFORD, "barlat": L.YIELD_BARLAT}
+# Yld2004-18p coefficient names in the order of cmadx_material_t::barlat (effective_stress.py:55-78)
+BARLAT_KEYS = tuple(f"{p}_{ij}" for p in ("sp", "dp") for ij in ("12", "13", "21", "23", "31", "32", "44", "55", "66"))
 
 
 @dataclass
@@ -83,6 +85,8 @@ def _pid_of(path: tuple, k: int, pair: tuple) -> int | None:
                 return L.P_HILL_F + "FGHLMN".index(path[3])
             if path[2] == "hosford" and path[3] == "a":
                 return L.P_HOSFORD_A
+            if path[2] == "barlat":
+                return L.P_BARLAT_A if path[3] == "a" else L.P_BARLAT_C0 + BARLAT_KEYS.index(path[3])
             if path[2] == "J2":
                 return None          # a leaf with no effect on the model ({"J2": 0.})
     raise ValueError(f"parameter leaf {'/'.join(map(str, path))} is not known to the B200 kernels")
@@ -116,6 +120,10 @@ def material_from_values(values: dict, model: str = "small_elastic_plastic",
                 m.hill[i] = float(pl["effective stress"]["hill"][k])
         elif kind == "hosford":
             m.hosford_a = float(pl["effective stress"]["hosford"]["a"])
+        elif kind == "barlat":
+            for i, k in enumerate(BARLAT_KEYS):
+                m.barlat[i] = float(pl["effective stress"]["barlat"][k])
+            m.barlat_a = float(pl["effective stress"]["barlat"]["a"])
         m.Y = float(pl["flow stress"]["initial yield"]["Y"])
         mask = 0
         for htype, hp in pl["flow stress"]["hardening"].items():

@@ -44,7 +44,11 @@ enum {
 enum { CMADX_MODEL_SMALL_ELASTIC_PLASTIC = 0, CMADX_MODEL_ELASTIC = 1,
        CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC = 2 };
 /* ---- effective stress: cmad/models/effective_stress.py:16-27 */
-enum { CMADX_YIELD_J2 = 0, CMADX_YIELD_HILL = 1, CMADX_YIELD_HOSFORD = 2 };
+/* CMADX_YIELD_BARLAT: Yld2004-18p, effective_stress.py:55-84 -> verification/functions.py:71-154
+ * (the eigenvalues of two linear images of the stress); carried by the one-pass material-point
+ * kernels (K1, forward history), the calibration objectives (K2 adjoint / direct) and the any-rule
+ * element kernels (K3 / K4, FULL_3D); the other entry points return CMADX_EUNSUPPORTED for it. */
+enum { CMADX_YIELD_J2 = 0, CMADX_YIELD_HILL = 1, CMADX_YIELD_HOSFORD = 2, CMADX_YIELD_BARLAT = 3 };
 /* ---- which two elastic constants are given (cmad/models/elastic_constants.py:54-104),
  *      values in sorted-key order "E" < "kappa" < "lambda" < "mu" < "nu"       */
 enum {
@@ -62,7 +66,12 @@ enum {
     CMADX_P_EL0 = 0, CMADX_P_EL1, CMADX_P_Y, CMADX_P_VOCE_S, CMADX_P_VOCE_D,
     CMADX_P_LIN_K, CMADX_P_HILL_F, CMADX_P_HILL_G, CMADX_P_HILL_H, CMADX_P_HILL_L,
     CMADX_P_HILL_M, CMADX_P_HILL_N, CMADX_P_HOSFORD_A, CMADX_P_Q00,
-    CMADX_NUM_PARAM_IDS = CMADX_P_Q00 + 9
+    /* Yld2004-18p: sp_12 sp_13 sp_21 sp_23 sp_31 sp_32 sp_44 sp_55 sp_66, the same nine of dp_*,
+     * then the exponent (the caller orders columns; the reference's sorted-key order is
+     * a, dp_*, sp_*) */
+    CMADX_P_BARLAT_C0 = CMADX_P_Q00 + 9,
+    CMADX_P_BARLAT_A = CMADX_P_BARLAT_C0 + 18,
+    CMADX_NUM_PARAM_IDS = CMADX_P_BARLAT_A + 1
 };
 #define CMADX_MAX_ACTIVE 16
 
@@ -123,6 +132,8 @@ typedef struct cmadx_material {
     double hosford_a;
     double Q[9];            /* "rotation matrix", row-major                    */
     double yield_tol;       /* cmad/models/small_elastic_plastic.py:116 (1e-14)*/
+    double barlat[18];      /* sp_12 sp_13 sp_21 sp_23 sp_31 sp_32 sp_44 sp_55 sp_66, dp_* alike */
+    double barlat_a;        /* plastic/effective stress/barlat/a                */
 } cmadx_material_t;
 
 /* Local Newton + line-search settings: make_newton_solve kwargs

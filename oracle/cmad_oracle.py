@@ -310,10 +310,39 @@ def hosford_effective_stress(cauchy, plastic_params):
     return vm * (0.5 * (d01 + d12 + d20)) ** (a ** -1)
 
 
+BARLAT_TENSOR_KEYS = ("12", "13", "21", "23", "31", "32", "44", "55", "66")
+
+
+def barlat_effective_stress(cauchy, plastic_params):
+    """Yld2004-18p, effective_stress.py:55-84 -> verification/functions.py:71-154: two linear
+    images of the stress (`sp_*`, `dp_*` coefficient sets; the 3x3 normal blocks annihilate the
+    hydrostatic part, the shear entries are scaled entry by entry), their eigenvalues through
+    `eigh` of the symmetrised image, phi = (1/4 sum_ij |S'_i - S''_j|^a)^(1/a)."""
+    b = plastic_params["effective stress"]["barlat"]
+
+    def image(pre):
+        c12, c13, c21, c23, c31, c32, c44, c55, c66 = (b[f"{pre}_{k}"] for k in BARLAT_TENSOR_KEYS)
+        d = torch.stack([cauchy[0, 0], cauchy[1, 1], cauchy[2, 2]])
+        ul = torch.stack([torch.stack([c12 + c13, -2. * c12 + c13, c12 - 2. * c13]),
+                          torch.stack([-2. * c21 + c23, c21 + c23, c21 - 2. * c23]),
+                          torch.stack([-2. * c31 + c32, c31 - 2. * c32, c31 + c32])]) / 3.
+        n = ul @ d
+        return torch.stack([torch.stack([n[0], c44 * cauchy[0, 1], c66 * cauchy[0, 2]]),
+                            torch.stack([c44 * cauchy[1, 0], n[1], c55 * cauchy[1, 2]]),
+                            torch.stack([c66 * cauchy[2, 0], c55 * cauchy[2, 1], n[2]])])
+
+    def eigvals(S):
+        return torch.linalg.eigh(0.5 * (S + S.T))[0]          # jnp.linalg.eigh symmetrises its input
+
+    e1, e2 = eigvals(image("sp")), eigvals(image("dp"))
+    a = b["a"]
+    return (0.25 * torch.sum(torch.abs(e1[:, None] - e2[None, :]) ** a)) ** (1. / a)
+
+
 def effective_stress_fun(kind: str):
     """effective_stress.py:16-27."""
     return {"J2": J2_effective_stress, "hill": hill_effective_stress,
-            "hosford": hosford_effective_stress}[kind]
+            "hosford": hosford_effective_stress, "barlat": barlat_effective_stress}[kind]
 
 
 # --------------------------------------------------------------------------

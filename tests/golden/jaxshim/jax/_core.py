@@ -686,6 +686,27 @@ def det(A):
     return Array(d, d * trace(solve(A.p, A.t)), A.tag)
 
 
+def eigh(A, UPLO=None, symmetrize_input=True):
+    """`jnp.linalg.eigh` with JAX's JVP rule (jax/_src/lax/linalg.py, `_eigh_jvp_rule`):
+    dw = diag(V^T dA V), dV = V (F o V^T dA V), F_ij = 1 / (w_j - w_i) off the diagonal
+    (inf / NaN at repeated eigenvalues, like JAX).  The input is symmetrised first, as
+    JAX does, so the derivative with respect to a single off-diagonal entry is half the
+    symmetric one.  Written on shim primitives: nests for second derivatives."""
+    A = _A(A)
+    if A.tag == 0:
+        w, v = np.linalg.eigh(0.5 * (A.p + A.p.T))
+        return Array(w), Array(v)
+    w, v = eigh(A.p)
+    At = 0.5 * (A.t + transpose(A.t))
+    vAv = matmul(matmul(transpose(v), At), v)
+    n = A.shape[0]
+    I = Array(np.eye(n))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        F = 1.0 / (I + reshape(w, (1, n)) - reshape(w, (n, 1))) - I
+        dv = matmul(v, F * vAv)
+    return Array(w, diag(vAv), A.tag), Array(v, dv, A.tag)
+
+
 def norm(x, ord=None, axis=None):
     x = _A(x)
     if ord not in (None, 2, "fro"):

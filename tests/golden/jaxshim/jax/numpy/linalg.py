@@ -1,2 +1,2 @@
 """`jax.numpy.linalg` stand-in."""
-from .._core import det, inv, norm, solve  # noqa: F401
+from .._core import det, eigh, inv, norm, solve  # noqa: F401

@@ -629,6 +629,26 @@ def main():
             print("objective", nm, r["J_adjoint"], r["grad_adjoint"], r["grad_direct"])
         np.savez_compressed(os.path.join(HERE, "ref_mp_objectives.npz"), **out)
 
+    if only is not None and "barlat" in only:
+        # Yld2004-18p (effective_stress.py:81-84 -> verification/functions.py:71-154, jnp.linalg.eigh).
+        # Not part of the default run: the nested duals through eigh make it slow (minutes per job).
+        out = {}
+        for kind, key, n, steps, tan in (
+                ("barlat", "mp", 16, (15, 45, 75), False), ("barlat", "mp", 4, (30, 60), True),
+                ("barlat_rot", "fe", 8, (20, 60), False), ("barlat_rot", "fe", 2, (20, 60), True),
+                ("barlat_a8", "mp", 8, (20, 60), False)):
+            r = traced(pool, kind, key, n, steps, seed=31 if tan else 22, chunk=1 if tan else 2, with_tangent=tan)
+            for k, v in r.items():
+                out[f"{kind}.{key}.{'tan.' if tan else ''}{k}"] = v
+            print("traced", kind, key, tan, "iters", np.bincount(r["iters"].ravel()), "flags", np.bincount(r["flags"].ravel()), flush=True)
+        w = np.array([[1.0, 0.5, 0.0], [0.5, 1.0, 0.0], [0.0, 0.0, 0.25]])
+        jobs = [("barlat", sc, two_leg_F(11, 24, scale=1.5), w) for sc in (True, False)]
+        for nm, r in zip(("barlat.scaled", "barlat.native"), pool.map(_objective_job, jobs)):
+            for k, v in r.items():
+                out[f"objective.{nm}.{k}"] = v
+            print("objective", nm, r["J_adjoint"], r["grad_adjoint"], r["grad_direct"], flush=True)
+        np.savez_compressed(os.path.join(HERE, "ref_barlat.npz"), **out)
+
     if only is None or "hessian" in only:
         w = np.array([[1.0, 0.5, 0.0], [0.5, 1.0, 0.0], [0.0, 0.0, 0.25]])
         jobs, names = [], []

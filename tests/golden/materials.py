@@ -14,6 +14,9 @@ def rotation_matrix(axis, angle):
     return np.eye(3) + np.sin(angle) * K + (1 - np.cos(angle)) * K @ K
 
 
+BARLAT_KEYS = tuple(f"{p}_{ij}" for p in ("sp", "dp") for ij in ("12", "13", "21", "23", "31", "32", "44", "55", "66")) + ("a",)
+
+
 def material(kind):
     """Parameter `values` pytree in the reference's layout; E, nu, Y, S, D of
     tests/support/test_problems.py:151 unless noted."""
@@ -33,6 +36,15 @@ def material(kind):
         el = {"E": 1000.0, "nu": 0.25}
         es = {"hosford": {"a": 100.0}}
         Y, hd = 2.0, {"voce": {"S": 10.0, "D": 2.0}}
+    elif kind in ("barlat", "barlat_rot", "barlat_a8"):
+        # Yld2004-18p with the AL7079 fit of cmad/calibrations/al7079/support.py:80-89 (a = 18.2,
+        # a non-integer exponent); "_a8": the same tensors with the fcc exponent 8; "_rot": rotated axes
+        c = (0.4555, 1.0274, 0.7101, 1.3755, 0.5314, 0.8817, 1.0558, 1.1133, 0.9220,
+             1.2431, 1.5438, 1.2204, 0.7632, 0.5327, 0.3015, 0.9722, 0.7399, 1.0760)
+        es = {"barlat": dict(zip(BARLAT_KEYS, c + (8.0 if kind == "barlat_a8" else 18.2,)))}
+        if kind == "barlat_rot":
+            Q = rotation_matrix([0.3, -1.0, 0.8], 0.9)
+            hd = {"voce": {"S": 200.0, "D": 20.0}, "linear": {"K": 1500.0}}
     elif kind == "J2_kappa_mu":                # another elastic-constant pair
         el = {"kappa": 200e3 / (3 * (1 - 0.6)), "mu": 200e3 / 2.6}
         es = {"J2": 0.0}
@@ -80,6 +92,9 @@ def objective_trees(kind, scaled):
         fs["hardening"]["voce"]["D"] = np.array([0.5 * D, 1.5 * D])
     else:
         act["elastic"] = {k: True for k in values["elastic"]}
+        if kind.startswith("barlat"):          # a few coefficients of both tensors, and the exponent
+            for k in ("sp_12", "sp_44", "dp_23", "dp_66", "a"):
+                act["plastic"]["effective stress"]["barlat"][k] = True
     return values, act, tr
 
 
