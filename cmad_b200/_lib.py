@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcmad_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
 SOURCES = ["api.cu", "mp_update.cu", "mp_update_stream.cu", "mp_update_queue.cu", "mp_update_cta.cu", "mp_update_j2.cu", "mp_update_dt.cu", "mp_update_rate.cu", "elastic_update.cu", "mp_sens.cu", "mp_sens_dt.cu", "mp_sens_rate.cu", "mp_hess.cu", "mp_history.cu",
-           "fe_block.cu", "fe_tet4.cu", "fe_hex8.cu", "fe_generic.cu", "fe_tet4x4.cu", "fe_rate.cu", "fe_mixed.cu", "fe_post.cu", "fe_vjp.cu", "fe_scatter.cu"]
+           "fe_block.cu", "fe_tet4.cu", "fe_hex8.cu", "fe_generic.cu", "fe_tet4x4.cu", "fe_rate.cu", "fe_mixed.cu", "fe_post.cu", "fe_vjp.cu", "fe_scatter.cu", "sym3_eigh.cu", "mp_partials.cu"]
 
 # ---- enums (mirror include/cmad_b200.h) ---------------------------------
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(5)
@@ -49,6 +49,12 @@ class Material(C.Structure):
                 ("voce_S", C.c_double), ("voce_D", C.c_double), ("linear_K", C.c_double),
                 ("hill", C.c_double * 6), ("hosford_a", C.c_double), ("Q", C.c_double * 9),
                 ("yield_tol", C.c_double), ("barlat", C.c_double * 18), ("barlat_a", C.c_double)]
+
+
+class MpPartials(C.Structure):
+    _fields_ = [("n", C.c_int64), ("ld", C.c_int64), ("strain_comps", C.c_int32), ("reserved", C.c_int32),
+                ("xi", C.c_void_p), ("xi_prev", C.c_void_p), ("strain", C.c_void_p), ("dC_deps", C.c_void_p),
+                ("dsig_dxi", C.c_void_p), ("dsig_deps", C.c_void_p), ("dsig_dp", C.c_void_p)]
 
 
 class Newton(C.Structure):
@@ -199,6 +205,9 @@ def lib() -> C.CDLL:
                                             C.POINTER(C.c_void_p)]
     L.cmadx_segment_plan_destroy.argtypes = [C.c_void_p]
     L.cmadx_segment_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.cmadx_mp_model_partials.argtypes = [C.POINTER(Material), C.POINTER(C.c_int32), C.c_int32,
+                                          C.POINTER(MpPartials), C.c_void_p]
+    L.cmadx_sym3_eigh.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.cmadx_index_gather.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.cmadx_index_scatter.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     # a stale library (the .so is git-ignored and rebuilt by mtime) with a drifted struct layout

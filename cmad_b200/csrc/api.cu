@@ -875,7 +875,7 @@ int cmadx_mp_objective_hessian(const cmadx_material_t* mat, const int32_t* activ
 }
 
 static int check_fe_block(const cmadx_material_t* mat, const cmadx_fe_block_t* blk, FeArgs* A,
-                          bool allow_rate = false) {
+                          bool allow_rate = false, bool allow_barlat = false) {
     if (!blk) return CMADX_EINVAL;
     if (int rc = make_dev_mat(mat, &A->m)) return rc;
     if (A->m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC) {
@@ -883,7 +883,9 @@ static int check_fe_block(const cmadx_material_t* mat, const cmadx_fe_block_t* b
         if (!allow_rate || A->m.rot) return CMADX_EUNSUPPORTED;
         if (blk->n_elems > 0 && !blk->U_prev) return CMADX_EINVAL;
     } else if (A->m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC) return CMADX_EUNSUPPORTED;
-    if (A->m.yield == CMADX_YIELD_BARLAT) return CMADX_EUNSUPPORTED;      // material-point path only
+    // Yld2004-18p: K3 / K4 (fe_generic.cu) and the stress recovery; K6 does not carry it
+    if (A->m.yield == CMADX_YIELD_BARLAT &&
+        (!allow_barlat || A->m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC)) return CMADX_EUNSUPPORTED;
     const cmadx_fe_block_t& b = *blk;
     if (b.n_elems < 0 || b.n_dofs < 0) return CMADX_EINVAL;
     // tet4 / hex8 with any volume rule (cmad/cli/common.py:497-540: up to 24 / 64 points); the
@@ -907,10 +909,11 @@ static int check_fe_block(const cmadx_material_t* mat, const cmadx_fe_block_t* b
 static int fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* newton,
                              const cmadx_fe_block_t* blk, const cmadx_fe_mixed_t* mix, void* stream) {
     FeArgs A;
-    if (int rc = check_fe_block(mat, blk, &A, true)) return rc;
+    if (int rc = check_fe_block(mat, blk, &A, true, true)) return rc;
     if (int rc = make_dev_newton(newton, &A.nw)) return rc;
     if (A.nw.mode == CMADX_NEWTON_IMPERATIVE && A.nw.ls_max > 0) return CMADX_EUNSUPPORTED;
     default_defer(A.m, &A.nw);
+    if (A.m.yield == CMADX_YIELD_BARLAT) A.nw.defer_request = 0;       // one pass of the any-rule kernel
     if (mix) {
         if (blk->n_elems > 0) {
             if (!mix->elem_eq_p || !mix->N || !mix->h) return CMADX_EINVAL;
@@ -1001,7 +1004,7 @@ int cmadx_fe_cauchy_at_ips(const cmadx_material_t* mat, const cmadx_fe_block_t* 
     if (!b.xi_prev) b.xi_prev = xi_state;       // not used by this entry point
     if (!b.xi) b.xi = sigma;
     FeArgs A;
-    if (int rc = check_fe_block(mat, &b, &A)) return rc;
+    if (int rc = check_fe_block(mat, &b, &A, false, true)) return rc;
     cudaError_t e = cmadx::launch_fe_cauchy(A.m, A.b, xi_state, sigma, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     g_launches.fetch_add(1, std::memory_order_relaxed);

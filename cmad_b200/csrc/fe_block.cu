@@ -30,6 +30,7 @@ cudaError_t launch_fe_tet4(const FeArgs& A, int solver, bool list, cudaStream_t 
 cudaError_t launch_fe_hex8(const FeArgs& A, int solver, bool list, cudaStream_t stream, int sms);
 cudaError_t launch_fe_generic(const FeArgs& A, int solver, cudaStream_t stream);
 cudaError_t launch_fe_generic_list(const FeArgs& A, cudaStream_t stream);
+cudaError_t launch_fe_generic_barlat(const FeArgs& A, cudaStream_t stream);
 cudaError_t launch_fe_tet4x4(const FeArgs& A, int solver, cudaStream_t stream);
 static bool tet4x4(const FeArgs& A) { return A.b.n_basis == 4 && A.b.n_ip == 4; }
 
@@ -41,6 +42,7 @@ static bool default_rule(const FeArgs& A) {
 // main launch: J2 radial kernel where it applies, else the generic kernel
 cudaError_t launch_fe_block(const FeArgs& A, bool j2_radial, cudaStream_t stream) {
     if (A.b.n_elems == 0) return cudaSuccess;
+    if (A.m.yield == CMADX_YIELD_BARLAT) return launch_fe_generic_barlat(A, stream);
     if (tet4x4(A)) return launch_fe_tet4x4(A, j2_radial ? 0 : 1 + A.m.yield, stream);
     if (!default_rule(A)) return launch_fe_generic(A, 1 + A.m.yield, stream);
     const int solver = j2_radial ? 0 : 1 + A.m.yield;

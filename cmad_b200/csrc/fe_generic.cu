@@ -17,7 +17,9 @@ namespace cmadx {
 namespace {
 
 // LIST: the elements a tuned first pass handed back (bail list), one thread per list entry
-template <int SOLVER, bool ROT, bool WANT_K, int NB, bool LIST = false>
+// YKX >= 0: primal solve with the generic Newton of yield surface YKX, for surfaces outside the
+// SOLVER numbering shared with the tuned kernels (Yld2004-18p: this kernel is its only element kernel)
+template <int SOLVER, bool ROT, bool WANT_K, int NB, bool LIST = false, int YKX = -1>
 __global__ void __launch_bounds__(FE_BLOCK) fe_generic_kernel(const __grid_constant__ FeArgs A) {
     const cmadx_fe_block_t& b = A.b;
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -73,7 +75,8 @@ __global__ void __launch_bounds__(FE_BLOCK) fe_generic_kernel(const __grid_const
         } else {
             DevNewton nw = A.nw;
             nw.defer_after = 0;
-            solve_point<SOLVER, ROT, WANT_K>(A.m, nw, xp, eps, true, o, D);
+            if constexpr (YKX >= 0) point_generic<YKX, ROT, WANT_K>(A.m, nw, xp, eps, true, o, D);
+            else solve_point<SOLVER, ROT, WANT_K>(A.m, nw, xp, eps, true, o, D);
         }
 #pragma unroll
         for (int c = 0; c < 7; ++c) b.xi[p * 7 + c] = o.x[c];
@@ -192,6 +195,26 @@ cudaError_t launch_fe_generic_list(const FeArgs& A, cudaStream_t stream) {
     const int solver = 1 + A.m.yield;
     if (A.b.n_basis == 4) return dispatch_fe_list<GenericListLauncher<4>::L>(A, solver, stream, 0);
     return dispatch_fe_list<GenericListLauncher<8>::L>(A, solver, stream, 0);
+}
+
+// K3 / K4 of a Yld2004-18p block, any rule (the default rules included)
+template <int NB>
+static cudaError_t launch_barlat_nb(const FeArgs& A, cudaStream_t stream) {
+    constexpr int B = CMADX_YIELD_BARLAT;
+    const unsigned nblk = (unsigned)((A.b.n_elems + FE_BLOCK - 1) / FE_BLOCK);
+    const bool k = A.b.K_elem != nullptr;
+    if (A.m.rot) {
+        if (k) fe_generic_kernel<1, true, true, NB, false, B><<<nblk, FE_BLOCK, 0, stream>>>(A);
+        else fe_generic_kernel<1, true, false, NB, false, B><<<nblk, FE_BLOCK, 0, stream>>>(A);
+    } else {
+        if (k) fe_generic_kernel<1, false, true, NB, false, B><<<nblk, FE_BLOCK, 0, stream>>>(A);
+        else fe_generic_kernel<1, false, false, NB, false, B><<<nblk, FE_BLOCK, 0, stream>>>(A);
+    }
+    return cudaGetLastError();
+}
+cudaError_t launch_fe_generic_barlat(const FeArgs& A, cudaStream_t stream) {
+    if (A.b.n_elems == 0) return cudaSuccess;
+    return (A.b.n_basis == 4) ? launch_barlat_nb<4>(A, stream) : launch_barlat_nb<8>(A, stream);
 }
 
 // solver: 1 + yield (primal, generic Newton) or 4 + yield (JVP)

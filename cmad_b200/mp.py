@@ -194,6 +194,52 @@ def mp_objective_host(material: L.Material, newton: NewtonSettings, active_pid, 
     return (result, Jp) if want_J_point else result
 
 
+def model_partials(material: L.Material, active_pid, xi: torch.Tensor, xi_prev: torch.Tensor, strain: torch.Tensor,
+                   stream: torch.cuda.Stream | None = None) -> dict:
+    """The raw AD products of the reference's ``Model`` at given states (``model.py:121-160``):
+    ``dC_deps (42, n)``, ``dsig_dxi (42, n)``, ``dsig_deps (36, n)`` and ``dsig_dp (6 P_a, n)`` - see
+    ``cmadx_mp_model_partials``.  ``dC/dU_prev`` and ``dcauchy/dxi_prev`` are identically zero."""
+    n = xi.shape[1]
+    _check_in("xi", xi, 7, n, "cuda"); _check_in("xi_prev", xi_prev, 7, n, "cuda")
+    if strain.shape[0] not in (6, 9):
+        raise ValueError("strain must have 6 or 9 components")
+    _check_in("strain", strain, strain.shape[0], n, "cuda")
+    pid = np.ascontiguousarray(active_pid, dtype=np.int32)
+    mk = lambda rows: torch.empty((rows, n), dtype=torch.float64, device=xi.device)  # noqa: E731
+    out = {"dC_deps": mk(42), "dsig_dxi": mk(42), "dsig_deps": mk(36)}
+    if len(pid):
+        out["dsig_dp"] = mk(6 * len(pid))
+    p = L.MpPartials()
+    p.n, p.ld, p.strain_comps = n, n, strain.shape[0]
+    xi, xi_prev, strain = xi.contiguous(), xi_prev.contiguous(), strain.contiguous()
+    p.xi, p.xi_prev, p.strain = xi.data_ptr(), xi_prev.data_ptr(), strain.data_ptr()
+    for k, v in out.items():
+        setattr(p, k, v.data_ptr())
+    s = stream if stream is not None else torch.cuda.current_stream(xi.device)
+    with torch.cuda.device(xi.device):
+        rc = L.lib().cmadx_mp_model_partials(C.byref(material), pid.ctypes.data_as(C.POINTER(C.c_int32)), len(pid),
+                                             C.byref(p), s.cuda_stream)
+    L.check(rc, "cmadx_mp_model_partials")
+    return out
+
+
+def sym3_eigh(A6: torch.Tensor, vectors: bool = True, stream: torch.cuda.Stream | None = None):
+    """Eigen-decomposition of a batch of symmetric 3x3 tensors on the GPU: the drop-in for
+    ``sorted_eigen_decomposition`` (cmad/util/jax_eigen_decomposition.py:167-171).  ``A6`` is
+    ``(6, n)`` component-major (xx, xy, xz, yy, yz, zz).  Returns ``(w (3, n) ascending, V (3, 3, n))``
+    with ``V[:, k, i]`` the k-th eigenvector of tensor i (``None`` when ``vectors`` is false)."""
+    A6 = A6.contiguous()
+    _check_in("A6", A6, 6, A6.shape[1], "cuda")
+    n = A6.shape[1]
+    w = torch.empty((3, n), dtype=torch.float64, device=A6.device)
+    V = torch.empty((9, n), dtype=torch.float64, device=A6.device) if vectors else None
+    s = stream if stream is not None else torch.cuda.current_stream(A6.device)
+    with torch.cuda.device(A6.device):
+        rc = L.lib().cmadx_sym3_eigh(n, n, A6.data_ptr(), w.data_ptr(), V.data_ptr() if vectors else None, s.cuda_stream)
+    L.check(rc, "cmadx_sym3_eigh")
+    return w, (V.view(3, 3, n) if vectors else None)
+
+
 def fp64_peak_tflops(iters: int = 20000) -> float:
     v = C.c_double(0.0)
     s = torch.cuda.current_stream()

@@ -528,6 +528,36 @@ int cmadx_index_gather(const int64_t* index_dev, int64_t n, const double* src_de
 int cmadx_index_scatter(const int64_t* index_dev, int64_t n, const double* packed_dev, double* dst_dev,
                         void* stream);
 
+/* Raw AD products of the reference's Model object at GIVEN states (Model.evaluate semantics,
+ * cmad/models/model.py:121-160,168-193): dC/dU (jacfwd over U), dcauchy/dxi, dcauchy/dU and
+ * dcauchy/dparams.  SmallElasticPlastic, FULL_3D, every effective stress, rotated axes included.
+ * Component-major device arrays, leading dimension ld >= n; a NULL output is skipped.  U-derivatives
+ * are with respect to the SYMMETRIC strain components (both entries moving; the reference's
+ * single-entry columns are half of them off the diagonal).  dC/dU_prev and dcauchy/dxi_prev vanish
+ * identically for this model and have no output.  dsig_dp carries the elastic constants (zero
+ * columns for the flow-stress / yield-surface leaves, which cauchy does not see); rotation-matrix
+ * leaves there: CMADX_EUNSUPPORTED.                                                           */
+typedef struct cmadx_mp_partials {
+    int64_t n, ld;
+    int32_t strain_comps;   /* 6 = symmetric strain, 9 = grad_u row-major       */
+    int32_t reserved;
+    const double* xi;       /* [7][ld] state the products are evaluated at      */
+    const double* xi_prev;  /* [7][ld]                                          */
+    const double* strain;   /* [strain_comps][ld]                               */
+    double* dC_deps;        /* [7*6][ld]  (r*6+b)                               */
+    double* dsig_dxi;       /* [6*7][ld]  (a*7+c), global cauchy                */
+    double* dsig_deps;      /* [36][ld]   (a*6+b), partial (xi held fixed)      */
+    double* dsig_dp;        /* [6*n_active][ld] (a*n_active+c), partial         */
+} cmadx_mp_partials_t;
+int cmadx_mp_model_partials(const cmadx_material_t* mat, const int32_t* active_pid, int32_t n_active,
+                            const cmadx_mp_partials_t* p, void* stream);
+
+/* Batched eigen-decomposition of symmetric 3x3 tensors: replaces `sorted_eigen_decomposition`
+ * (cmad/util/jax_eigen_decomposition.py:86-171).  Component-major device arrays with leading
+ * dimension ld >= n: A6 rows xx,xy,xz,yy,yz,zz; w rows = eigenvalues in ascending order; V rows
+ * 3 m + k = component m of the k-th eigenvector (NULL: eigenvalues only).                     */
+int cmadx_sym3_eigh(int64_t n, int64_t ld, const double* A6_dev, double* w_dev, double* V_dev, void* stream);
+
 /* debugging aid: how many points the last J2 radial-return launch on `stream`
  * handed back to the generic kernel (synchronises the stream); -1 if none ran */
 int64_t cmadx_debug_bail_count(void* stream);

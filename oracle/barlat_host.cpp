@@ -16,6 +16,24 @@
 using namespace cmadx;
 
 extern "C" {
+// the Jacobi eigen-solver of the kernels (barlat.cuh, sym3_eigh.cu) on n packed tensors (row-major
+// n x 6: xx,xy,xz,yy,yz,zz): eigenvalues in ascending order (n x 3), vectors as columns (n x 3 x 3)
+void eig3_host(int64_t n, const double* A6, double* w, double* V) {
+    for (int64_t i = 0; i < n; ++i) {
+        double S[6], ww[3], VV[3][3];
+        for (int c = 0; c < 6; ++c) S[c] = A6[6 * i + c];
+        eig3_jacobi(S, ww, VV);
+        int ord[3] = {0, 1, 2};
+        for (int a = 0; a < 3; ++a)
+            for (int b = a + 1; b < 3; ++b)
+                if (ww[ord[b]] < ww[ord[a]]) { int t = ord[a]; ord[a] = ord[b]; ord[b] = t; }
+        for (int k = 0; k < 3; ++k) {
+            w[3 * i + k] = ww[ord[k]];
+            for (int m = 0; m < 3; ++m) V[9 * i + 3 * m + k] = VV[m][ord[k]];
+        }
+    }
+}
+
 // coeffs: 18 tensor coefficients + exponent; sig: xx,xy,xz,yy,yz,zz.
 // out: phi, n[6], M[36] (row-major a,b), then per parameter (19, header order): dphi, dn[6]
 int barlat_host_eval(const double* coeffs, const double* sig, double* out) {

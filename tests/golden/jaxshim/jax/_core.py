@@ -462,6 +462,7 @@ sin = _unary(np.sin, lambda x, o: cos(x))
 cos = _unary(np.cos, lambda x, o: -sin(x))
 tanh = _unary(np.tanh, lambda x, o: 1.0 - o * o)
 arccos = _unary(np.arccos, lambda x, o: -1.0 / sqrt(1.0 - x * x))
+arctan = _unary(np.arctan, lambda x, o: 1.0 / (1.0 + x * x))
 sign = lambda x: Array(np.sign(_raw(x)))  # noqa: E731
 
 

@@ -2,7 +2,7 @@
 import numpy as _np
 
 from .._core import (Array as ndarray, abs_ as abs, add, all_ as all, allclose, any_ as any, arange,  # noqa: F401
-                     arccos, argmax, argmin, argsort, array, asarray, atleast_1d, atleast_2d, broadcast_to,
+                     arccos, arctan, argmax, argmin, argsort, array, asarray, atleast_1d, atleast_2d, broadcast_to,
                      c_, cbrt, clip, concatenate, cos, cross, cumsum, diag, dot, einsum, exp,
                      expand_dims, eye, flip, floor, full, hstack, isclose, isfinite, isnan, linspace, log,
                      logical_and, logical_not, logical_or, matmul, maximum, mean, minimum, moveaxis,

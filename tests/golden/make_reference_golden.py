@@ -150,6 +150,47 @@ def _traced_chunk(job):
     return {k: np.array(v) for k, v in out.items() if v}, nP       # each (steps, n, ...)
 
 
+def _partials_job(job):
+    """The raw AD products of `Model.__init__` (cmad/models/model.py:121-160) that the traced fixture
+    does not hold: dC/dU, dC/dU_prev (jacfwd over the GlobalFieldsAtPoint argument) and the partial
+    derivatives of `cauchy` with respect to xi, xi_prev and the parameters, at converged states."""
+    kind, newton_key, n, steps, seed = job
+    values = material(kind)
+    P = parameters(values)
+    model = SmallElasticPlastic(P)
+    solve = make_newton_solve(model._residual, **NEWTON[newton_key])
+    d, d2, a = synthetic.path_params(seed, 0, n, diag_only=kind.startswith("hosford"))
+    out = {k: [] for k in ("grad_u", "xi_prev", "xi", "flags", "dC_dU", "dC_dU_prev", "dsig_dxi", "dsig_dxi_prev",
+                           "dsig_dp", "dsig_dU")}
+    yf = yield_fun_of(model, values)
+    xi_prev = [[np.zeros(6), np.zeros(1)] for _ in range(n)]
+    for t in steps:
+        e6 = synthetic.strain_at_step(d, d2, a, t)
+        for i in range(n):
+            e = e6[:, i]
+            gu = np.array([[e[0], e[1], e[2]], [e[1], e[3], e[4]], [e[2], e[4], e[5]]])
+            U = mp_U_from_F(np.eye(3) + gu)
+            xp, params = xi_prev[i], P.values
+            xi = [np.asarray(x) for x in solve(xp, params, U, U)]
+            _, f1, _ = yf(xi, xp, params, U, U)
+            out["flags"].append(2 if (float(f1) > 1e-14 or abs(float(f1)) < 1e-14) else 0)
+            jac = model._jacobian
+            out["grad_u"].append(gu.reshape(9)); out["xi_prev"].append(np.concatenate(xp)); out["xi"].append(np.concatenate(xi))
+            out["dC_dU"].append(np.asarray(jac[DerivType.DU](xi, xp, params, U, U).grad_fields["u"]).reshape(7, 9))
+            out["dC_dU_prev"].append(np.asarray(jac[DerivType.DU_PREV](xi, xp, params, U, U).grad_fields["u"]).reshape(7, 9))
+            out["dsig_dxi"].append(np.hstack([np.asarray(b).reshape(9, -1) for b in model.dcauchy[0](xi, xp, params, U, U)]))
+            out["dsig_dxi_prev"].append(np.hstack([np.asarray(b).reshape(9, -1) for b in model.dcauchy[1](xi, xp, params, U, U)]))
+            out["dsig_dp"].append(np.hstack([np.asarray(x).reshape(9, -1)
+                                             for x in jax.tree_util.tree_leaves(model.dcauchy[2](xi, xp, params, U, U))]))
+            dsdU = jax.jacfwd(model.cauchy, argnums=DerivType.DU)(xi, xp, params, U, U)
+            out["dsig_dU"].append(np.asarray(dsdU.grad_fields["u"]).reshape(9, 9))
+            xi_prev[i] = xi
+    res = {k: np.array(v) for k, v in out.items()}
+    res["param_names"] = np.array(P._names)
+    res["param_sizes"] = np.array(P.flat_param_sizes)
+    return res
+
+
 def traced(pool, kind, newton_key, n, steps, seed=22, scale=1.0, chunk=4, with_tangent=True):
     jobs = [(kind, newton_key, lo, min(lo + chunk, n), steps, seed, scale, with_tangent)
             for lo in range(0, n, chunk)]
@@ -728,6 +769,28 @@ def main():
                 out[f"{nm}.{k}"] = v
             print("fe", nm, "alpha max", r["xi"][..., 6].max())
         np.savez_compressed(os.path.join(HERE, "ref_fe_elements.npz"), **out)
+
+    if only is not None and "partials" in only:
+        jobs = [("J2", "mp", 6, (20, 60), 5), ("hill_rot", "fe", 6, (20, 60), 6), ("hosford", "mp", 6, (20, 60), 7),
+                ("barlat_rot", "fe", 3, (20, 60), 8)]
+        out = {}
+        for job, r in zip(jobs, pool.map(_partials_job, jobs, chunksize=1)):
+            for k, v in r.items():
+                out[f"{job[0]}.{k}"] = v
+            print("partials", job[0], "plastic", int((r["flags"] > 0).sum()), "of", r["flags"].size, flush=True)
+        np.savez_compressed(os.path.join(HERE, "ref_model_partials.npz"), **out)
+
+    if only is not None and "barlat_fe" in only:
+        # element blocks with the Yld2004-18p surface (slow: eigh under nested duals at every point)
+        jobs = [("tet4", "barlat_rot", False, 41, 2), ("tet4", "barlat", True, 42, 2),
+                ("hex8", "barlat", False, 43, 1), ("hex8", "barlat_rot", True, 44, 1)]
+        names = [f"{f}.{k}.{'mixed' if m else 'disp'}" for f, k, m, _, _ in jobs]
+        out = {}
+        for nm, r in zip(names, pool.map(_fe_job, jobs, chunksize=1)):
+            for k, v in r.items():
+                out[f"{nm}.{k}"] = v
+            print("fe", nm, "alpha max", r["xi"][..., 6].max(), flush=True)
+        np.savez_compressed(os.path.join(HERE, "ref_barlat_fe.npz"), **out)
 
     if only is None or "deftypes" in only:
         jobs = [(kind, dt) for dt in ("PLANE_STRESS", "UNIAXIAL_STRESS") for kind in ("J2", "hill", "hosford")]

@@ -279,6 +279,30 @@ def test_cuda_objectives_vs_reference(cuda_device, mode):
         assert rel_err(r.grad, BR[f"{case}.grad_{strategy}"]) < 1e-9
 
 
+BFE_PATH = os.path.join(G, "ref_barlat_fe.npz")
+BFE = np.load(BFE_PATH) if os.path.exists(BFE_PATH) else None
+FE_CASES = sorted({k.rsplit(".", 1)[0] for k in BFE.files}) if BFE is not None else []
+
+
+def test_fe_fixture_is_plastic_and_complete():
+    """`per_element_R_and_K_coupled` of the reference on distorted tet4 / hex8 elements with the
+    Yld2004-18p surface, displacement and mixed u-p, rotated axes included."""
+    assert FE_CASES == ["hex8.barlat.disp", "hex8.barlat_rot.mixed", "tet4.barlat.mixed", "tet4.barlat_rot.disp"]
+    for case in FE_CASES:
+        assert BFE[f"{case}.xi"][..., 6].max() > 0
+        assert rel_err(BFE[f"{case}.R_only_u"], BFE[f"{case}.R_u"]) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", FE_CASES)
+@pytest.mark.parametrize("deterministic", [True, False])
+def test_cuda_fe_vs_reference_elements(cuda_device, case, deterministic):
+    """K3 / K4 (the any-rule element kernel with the Barlat point routine) against the reference's
+    own element residuals, tangent blocks and states."""
+    from tests.test_fe_reference_golden import _cuda_fe_vs_fixture
+    _cuda_fe_vs_fixture(cuda_device, case, deterministic, BFE)
+
+
 @pytest.mark.gpu
 def test_cuda_barlat_unsupported_entries_say_so(cuda_device):
     """Entry points that do not carry the surface return CMADX_EUNSUPPORTED, never a wrong answer."""

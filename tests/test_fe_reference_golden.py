@@ -25,7 +25,7 @@ CASES = sorted({k.rsplit(".", 1)[0] for k in FE.files})
 NEWTON = dict(max_iters=20, abs_tol=1e-12, rel_tol=1e-12)          # for_model's COUPLED defaults
 
 
-def _case_arrays(case):
+def _case_arrays(case, FE=FE):
     """Every (element, step) record of the fixture as one independent element of a block
     with private nodes: dofs block-major (u: 3*n_nodes, then p)."""
     family, kind, form = case.split(".")
@@ -102,10 +102,14 @@ def test_mixed_oracle_tangent_blocks_vs_finite_differences(family):
 @pytest.mark.parametrize("case", CASES)
 @pytest.mark.parametrize("deterministic", [True, False])
 def test_cuda_fe_vs_reference_elements(cuda_device, case, deterministic):
+    _cuda_fe_vs_fixture(cuda_device, case, deterministic, FE)
+
+
+def _cuda_fe_vs_fixture(cuda_device, case, deterministic, FE):
     import torch
     from cmad_b200 import fe, material_from_values
     from cmad_b200.fe_mesh import FEBlockArrays
-    family, kind, mixed, g, eq_u, eq_p, U, quad_w, N = _case_arrays(case)
+    family, kind, mixed, g, eq_u, eq_p, U, quad_w, N = _case_arrays(case, FE)
     n_e, n_b = eq_u.shape[0], eq_u.shape[1] // 3
     t = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a)).to(dt).to(cuda_device)  # noqa: E731
     arr = FEBlockArrays(t(eq_u, torch.int32), t(g["grad_N"]), t(g["det"]), t(quad_w), t(N), int(U.size),

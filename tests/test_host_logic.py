@@ -53,7 +53,7 @@ def test_material_mapping_and_errors():
     assert list(m.hill) == [.4, .5, .6, 1.1, 1.2, 1.3] and m.linear_K == 1500.0
     assert _lib.ELASTIC_PAIRS[m.elastic_pair] == ("E", "nu")
     with pytest.raises(NotImplementedError):
-        bad = {**values, "plastic": {**values["plastic"], "effective stress": {"barlat": {}}}}
+        bad = {**values, "plastic": {**values["plastic"], "effective stress": {"hybrid_hill": {}}}}
         material_from_values(bad)
     with pytest.raises(ValueError):
         material_from_values({"elastic": {"E": 1.0}}, model="elastic")
