@@ -77,7 +77,7 @@ def material_of(model, params) -> L.Material:
 
 def supports(model, gr=None, params=None) -> bool:
     """True when the COUPLED element block of ``model`` (under global residual ``gr``) is served:
-    SmallElasticPlastic, FULL_3D, effective stress in {J2, Hill, Hosford}, hardening within
+    SmallElasticPlastic, FULL_3D, effective stress in {J2, Hill, Hosford, Barlat (K3 / K4 only: no K6 rule)}, hardening within
     {Voce, linear}, ``SmallDispEquilibrium`` displacement or mixed u-p."""
     kind = _kind_of(model)
     if kind is None:
