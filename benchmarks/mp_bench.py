@@ -30,6 +30,11 @@ def tree(kind):
         es = {"hill": dict(zip("FGHLMN", (0.45, 0.55, 0.5, 1.4, 1.5, 1.6)))}
     elif kind.startswith("hosford"):
         es = {"hosford": {"a": float(kind.split(":")[1]) if ":" in kind else 4.0}}
+    elif kind.startswith("barlat"):        # Yld2004-18p, AL7079 fit of the reference (calibrations/al7079/support.py)
+        c = (0.4555, 1.0274, 0.7101, 1.3755, 0.5314, 0.8817, 1.0558, 1.1133, 0.9220,
+             1.2431, 1.5438, 1.2204, 0.7632, 0.5327, 0.3015, 0.9722, 0.7399, 1.0760)
+        keys = [f"{p}_{ij}" for p in ("sp", "dp") for ij in ("12", "13", "21", "23", "31", "32", "44", "55", "66")]
+        es = {"barlat": {**dict(zip(keys, c)), "a": float(kind.split(":")[1]) if ":" in kind else 8.0}}
     else:
         raise ValueError(kind)
     values = {"rotation matrix": np.eye(3), "elastic": {"E": 200e3, "nu": 0.3},

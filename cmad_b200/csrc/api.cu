@@ -43,7 +43,7 @@ cudaError_t launch_mp_history(const HistArgs& A, bool radial, cudaStream_t s);
 cudaError_t launch_mp_sens(const SensArgs& A, bool adjoint, cudaStream_t stream);
 cudaError_t launch_mp_sens_dt(const SensArgs& A, int def_type, bool adjoint, cudaStream_t stream);
 cudaError_t launch_mp_sens_rate(const SensArgs& A, bool adjoint, cudaStream_t stream);
-cudaError_t launch_fe_rate(const FeArgs& A, cudaStream_t stream);
+cudaError_t launch_fe_rate(const FeArgs& A, const cmadx_fe_mixed_t* mix, cudaStream_t stream);
 int64_t sens_blocks(int64_t n);
 int64_t hess_blocks(int64_t n);
 cudaError_t launch_mp_hess(const SensArgs& A, int def_type, double* pair_sums, double* H_out, cudaStream_t stream);
@@ -232,16 +232,15 @@ static int build_args(const cmadx_material_t* mat, const cmadx_newton_t* nw,
         A->nw.defer_request = 0;
     }
     if (b->n < 0 || b->ld < b->n) return CMADX_EINVAL;
-    if (A->m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC &&
-        (A->m.rot || b->def_type != CMADX_DEF_FULL_3D))
+    if (A->m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC && b->def_type != CMADX_DEF_FULL_3D)
         return CMADX_EUNSUPPORTED;
     if (b->def_type == CMADX_DEF_FULL_3D) {
         if (b->strain_comps != 6 && b->strain_comps != 9) return CMADX_EINVAL;
     } else if (b->def_type == CMADX_DEF_PLANE_STRESS || b->def_type == CMADX_DEF_UNIAXIAL_STRESS) {
         const bool ps = b->def_type == CMADX_DEF_PLANE_STRESS;
         if (ps ? (b->strain_comps != 3 && b->strain_comps != 4) : (b->strain_comps != 1)) return CMADX_EINVAL;
-        // identity material axes, SmallElasticPlastic only
-        if (A->m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC || A->m.rot) return CMADX_EUNSUPPORTED;
+        // SmallElasticPlastic only (rotated material axes: SepPointDTRot)
+        if (A->m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC) return CMADX_EUNSUPPORTED;
     } else {
         return CMADX_EINVAL;
     }
@@ -625,9 +624,8 @@ static int check_history(const cmadx_material_t* mat, const cmadx_mp_history_t* 
     if (h->n < 0 || h->ld < h->n || h->nsteps < 0) return CMADX_EINVAL;
     const int sc = h->strain_comps;
     if (sc != 6 && sc != 9 && sc != 3 && sc != 4 && sc != 1) return CMADX_EINVAL;
-    // the rate model: FULL_3D with identity material axes (mp_update_rate.cu, mp_sens_rate.cu)
-    if (rate && ((sc != 6 && sc != 9) || dm->rot)) return CMADX_EUNSUPPORTED;
-    if (history_def_type(h) != CMADX_DEF_FULL_3D && dm->rot) return CMADX_EUNSUPPORTED;
+    // the rate model: FULL_3D (mp_update_rate.cu, mp_sens_rate.cu)
+    if (rate && (sc != 6 && sc != 9)) return CMADX_EUNSUPPORTED;
     if (h->n > 0 && (!h->strain || !h->xi_hist)) return CMADX_EINVAL;
     // Yld2004-18p: SmallElasticPlastic in FULL_3D (K1, forward history, K2)
     if (dm->yield == CMADX_YIELD_BARLAT && (rate || history_def_type(h) != CMADX_DEF_FULL_3D)) return CMADX_EUNSUPPORTED;
@@ -850,7 +848,8 @@ int cmadx_mp_objective_hessian(const cmadx_material_t* mat, const int32_t* activ
     if (A.m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC || hist->qoi_kind != CMADX_QOI_CALIBRATION ||
         A.m.yield == CMADX_YIELD_BARLAT)
         return CMADX_EUNSUPPORTED;
-    const int dt = history_def_type(hist);     // rotated axes: FULL_3D only (check_history refuses the other def-types)
+    const int dt = history_def_type(hist);
+    if (dt != CMADX_DEF_FULL_3D && A.m.rot) return CMADX_EUNSUPPORTED;      // rotated axes: FULL_3D only in this pass
     if (n_active < 0 || n_active > CMADX_MAX_ACTIVE || (n_active > 0 && !active_pid)) return CMADX_EINVAL;
     if (!hist->result || !hist->workspace || (hist->n > 0 && !hist->data)) return CMADX_EINVAL;
     for (int c = 0; c < n_active; ++c) {
@@ -879,8 +878,8 @@ static int check_fe_block(const cmadx_material_t* mat, const cmadx_fe_block_t* b
     if (!blk) return CMADX_EINVAL;
     if (int rc = make_dev_mat(mat, &A->m)) return rc;
     if (A->m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC) {
-        // K3 / K4 only (fe_rate.cu), identity material axes; needs the previous displacement vector
-        if (!allow_rate || A->m.rot) return CMADX_EUNSUPPORTED;
+        // K3 / K4 only (fe_rate.cu); needs the previous displacement vector
+        if (!allow_rate) return CMADX_EUNSUPPORTED;
         if (blk->n_elems > 0 && !blk->U_prev) return CMADX_EINVAL;
     } else if (A->m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC) return CMADX_EUNSUPPORTED;
     // Yld2004-18p: K3 / K4 (fe_generic.cu) and the stress recovery; K6 does not carry it
@@ -930,11 +929,11 @@ static int fe_block_assemble(const cmadx_material_t* mat, const cmadx_newton_t* 
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e;
     if (A.m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC) {
-        // the rate form: one kernel for every rule (fe_rate.cu).  Its mixed u-p form is not carried:
-        // hydro_cauchy is tr(cauchy(xi)) / 3 there (small_rate_elastic_plastic.py:369-376), so the
-        // pressure rows depend on the local state - not the state-free pressure block of fe_mixed.cu
-        if (mix) return CMADX_EUNSUPPORTED;
-        e = launch_fe_rate(A, s);
+        // the rate form: one kernel for every rule (fe_rate.cu), which also forms the pressure rows
+        // of the mixed u-p form: hydro_cauchy is tr(cauchy(xi)) / 3 there
+        // (small_rate_elastic_plastic.py:369-376), i.e. state-dependent - not the state-free
+        // pressure block of fe_mixed.cu
+        e = launch_fe_rate(A, mix, s);
         if (e != cudaSuccess) return cuda_fail(e);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return CMADX_OK;

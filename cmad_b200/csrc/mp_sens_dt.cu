@@ -19,9 +19,9 @@ namespace {
 
 constexpr int SENS_DT_BLOCK = 128;
 
-template <int YK, int DT, bool ADJOINT>
+template <int YK, int DT, bool ADJOINT, bool ROT = false>
 __global__ void __launch_bounds__(SENS_DT_BLOCK) mp_sens_dt_kernel(const __grid_constant__ SensArgs A) {
-    using Pt = SepPointDT<YK, DT>;
+    using Pt = typename std::conditional<ROT, SepPointDTRot<YK, DT>, SepPointDT<YK, DT>>::type;
     constexpr int N = Pt::N, NZ = Pt::NZ;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < A.h.n;
@@ -74,13 +74,14 @@ __global__ void __launch_bounds__(SENS_DT_BLOCK) mp_sens_dt_kernel(const __grid_
         pt.residual(m, x, xp, em, C);
         const bool pl = pt.plastic;
         const double dg = x[6] - xp[6];
-        double et[6], ee[6], sig[6];
-        pt.total_strain(x, em, et);
+        double et[6], ee[6], sig[6], sgl[6];      // sig: material-frame stress, sgl: global (what the QoI reads)
+        pt.material_strain(x, em, et);
 #pragma unroll
         for (int a = 0; a < 6; ++a) ee[a] = et[a] - x[a];
         const double tree = ee[0] + ee[3] + ee[5];
 #pragma unroll
         for (int a = 0; a < 6; ++a) sig[a] = is_diag(a) ? fma(m.two_mu, ee[a], m.lam * tree) : m.two_mu * ee[a];
+        pt.to_global(sig, sgl);
         // Calibration QoI: J, r_a = dJ/d sigma_a (both entries of an off-diagonal component summed)
         double r[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         double dJdz[NZ];                   // direct dependence of the QoI on the stretch dofs
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(SENS_DT_BLOCK) mp_sens_dt_kernel(const __grid_
             // UniaxialCalibration (cmad/qois/uniaxial_calibration.py:69-85): pred = [sigma_axial,
             // lambda_2 - 1, lambda_3 - 1], weights of this step, data rows 0..2
             const double* ws = A.h.weight_steps + (int64_t)t * 3;
-            const double w0 = __ldg(ws), mis0 = w0 * (sig[0] - d[0]);
+            const double w0 = __ldg(ws), mis0 = w0 * (sgl[0] - d[0]);
             Jacc = fma(0.5 * mis0, mis0, Jacc);
             r[0] = w0 * mis0;
 #pragma unroll
@@ -103,25 +104,20 @@ __global__ void __launch_bounds__(SENS_DT_BLOCK) mp_sens_dt_kernel(const __grid_
             const int comp[9] = {0, 1, 2, 1, 3, 4, 2, 4, 5};
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
-                const double mis = A.h.weight[k] * (sig[comp[k]] - d[k]);
+                const double mis = A.h.weight[k] * (sgl[comp[k]] - d[k]);
                 Jacc = fma(0.5 * mis, mis, Jacc);
                 r[comp[k]] = fma(A.h.weight[k], mis, r[comp[k]]);
             }
         }
-        const double rtr = r[0] + r[3] + r[5];
-        double dJdx[N];
+        // cotangent of the stress in material axes, and dJ/dx through the stress (sep_point_dt.cuh)
+        double rm[6], dJdx[N];
+        pt.stress_cotangent(m, r, rm, dJdx);
 #pragma unroll
-        for (int b = 0; b < 6; ++b) {
-            double v = is_diag(b) ? fma(-m.two_mu, r[b], -m.lam * rtr) : -m.two_mu * r[b];
-            if (DT == CMADX_DEF_UNIAXIAL_STRESS && !is_diag(b)) v = 0.0;   // sigma independent of ep_shear
-            dJdx[b] = v;
-        }
-        dJdx[6] = 0.0;
-#pragma unroll
-        for (int k = 0; k < NZ; ++k) dJdx[7 + k] = fma(m.two_mu, r[Pt::zcomp(k)], m.lam * rtr) + dJdz[k];
+        for (int k = 0; k < NZ; ++k) dJdx[7 + k] += dJdz[k];
+        const double rtr = rm[0] + rm[3] + rm[5];
         double ree = 0.0;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) ree = fma(r[a], ee[a], ree);
+        for (int a = 0; a < 6; ++a) ree = fma(rm[a], ee[a], ree);
         const double dJdlam = tree * rtr, dJdmu = 2.0 * ree;
         double Mee[6], nee = 0.0;
 #pragma unroll
@@ -247,6 +243,21 @@ __global__ void __launch_bounds__(SENS_DT_BLOCK) mp_sens_dt_kernel(const __grid_
 template <int DT, bool ADJOINT>
 cudaError_t launch_t(const SensArgs& A, cudaStream_t stream) {
     const int64_t nblk = (A.h.n + SENS_DT_BLOCK - 1) / SENS_DT_BLOCK;
+    if (A.m.rot) {
+        if (A.phi_hist) return cudaErrorInvalidValue;       // the Hessian pass keeps identity axes
+        switch (A.m.yield) {
+        case CMADX_YIELD_J2:
+            mp_sens_dt_kernel<CMADX_YIELD_J2, DT, ADJOINT, true><<<(unsigned)nblk, SENS_DT_BLOCK, 0, stream>>>(A); break;
+        case CMADX_YIELD_HILL:
+            mp_sens_dt_kernel<CMADX_YIELD_HILL, DT, ADJOINT, true><<<(unsigned)nblk, SENS_DT_BLOCK, 0, stream>>>(A); break;
+        case CMADX_YIELD_HOSFORD:
+            mp_sens_dt_kernel<CMADX_YIELD_HOSFORD, DT, ADJOINT, true><<<(unsigned)nblk, SENS_DT_BLOCK, 0, stream>>>(A); break;
+        default: return cudaErrorInvalidValue;
+        }
+        cudaError_t er = cudaGetLastError();
+        if (er != cudaSuccess) return er;
+        return launch_reduce_partials(A.partials, nblk, 1 + A.n_active, A.h.result, stream);
+    }
     switch (A.m.yield) {
     case CMADX_YIELD_J2:
         mp_sens_dt_kernel<CMADX_YIELD_J2, DT, ADJOINT><<<(unsigned)nblk, SENS_DT_BLOCK, 0, stream>>>(A); break;

@@ -38,6 +38,10 @@ __global__ void __launch_bounds__(SENS_BLOCK) mp_sens_rate_kernel(const __grid_c
         for (int r = 0; r < 7; ++r) X[c][r] = 0.0;
     }
     double Jacc = 0.0, hist[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    // rotated material axes: de_m = T de, the QoI reads the global stress S sig (rate_point.cuh)
+    const bool rot = m.rot != 0;
+    double T[6][6], S[6][6];
+    if (rot) rot_maps(m.Q, T, S);
     for (int s = 0; s < N; ++s) {
         const int t = ADJOINT ? N - s : s + 1;
         double x[7], xp[7], de[6], d[9];
@@ -50,6 +54,18 @@ __global__ void __launch_bounds__(SENS_BLOCK) mp_sens_rate_kernel(const __grid_c
             rate_load_strain(A.h.strain + (int64_t)(t - 1) * sc * ld, sc, ld, i, ep);
 #pragma unroll
             for (int c = 0; c < 6; ++c) de[c] -= ep[c];
+            if (rot) {
+                double dm[6];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int b = 0; b < 6; ++b) s = fma(T[c][b], de[b], s);
+                    dm[c] = s;
+                }
+#pragma unroll
+                for (int c = 0; c < 6; ++c) de[c] = dm[c];
+            }
             const double* ds = A.h.data + (int64_t)t * 9 * ld + i;
 #pragma unroll
             for (int c = 0; c < 9; ++c) d[c] = __ldg(ds + c * ld);
@@ -68,11 +84,33 @@ __global__ void __launch_bounds__(SENS_BLOCK) mp_sens_rate_kernel(const __grid_c
         const double dg = x[6] - xp[6];
         // Calibration QoI on the state's stress
         double r[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        double sgl[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            sgl[a] = x[a];
+            if (rot) {
+                sgl[a] = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) sgl[a] = fma(S[a][c], x[c], sgl[a]);
+            }
+        }
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
-            const double mis = A.h.weight[k] * (x[comp[k]] - d[k]);
+            const double mis = A.h.weight[k] * (sgl[comp[k]] - d[k]);
             Jacc = fma(0.5 * mis, mis, Jacc);
             r[comp[k]] = fma(A.h.weight[k], mis, r[comp[k]]);
+        }
+        if (rot) {               // dJ/dsig_m = S^T dJ/dsig_g
+            double rm[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                double s = 0.0;
+#pragma unroll
+                for (int a = 0; a < 6; ++a) s = fma(S[a][c], r[a], s);
+                rm[c] = s;
+            }
+#pragma unroll
+            for (int c = 0; c < 6; ++c) r[c] = rm[c];
         }
         RegLU<7> lu;
         auto load = [&]() {

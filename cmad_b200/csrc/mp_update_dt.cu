@@ -10,7 +10,9 @@
 // SepPoint<YK> bordered by the stretch columns and the stress rows, the register LU with
 // threshold pivoting (N = 8 / 9), the reference-identical Newton state machine
 // (local_newton), IFT outputs by one solve per prescribed strain component.
-// Restrictions (CMADX_EUNSUPPORTED otherwise): identity material axes, uniaxial_stress_idx 0.
+// Rotated material axes: SepPointDTRot (sep_point_dt.cuh) - the constraints live in global axes,
+// the update in material axes; the identity path keeps its own point type (same bits as before).
+// Restriction (CMADX_EUNSUPPORTED otherwise): uniaxial_stress_idx 0.
 //
 // State x = [ep(6), alpha, z...], z = stretches (initialised to 1 by the model).  Total
 // strain in material (= global) axes, packed xx,xy,xz,yy,yz,zz:
@@ -24,9 +26,9 @@
 namespace cmadx {
 namespace {
 
-template <int YK, int DT>
+template <int YK, int DT, bool ROT = false>
 __global__ void __launch_bounds__(MP_BLOCK) mp_update_dt_kernel(const __grid_constant__ MpArgs A) {
-    using Pt = SepPointDT<YK, DT>;
+    using Pt = typename std::conditional<ROT, SepPointDTRot<YK, DT>, SepPointDT<YK, DT>>::type;
     constexpr int N = Pt::N, NZ = Pt::NZ;
     constexpr int NS = (DT == CMADX_DEF_PLANE_STRESS) ? 3 : 1;           // prescribed symmetric components
     const int scomp[3] = {0, (DT == CMADX_DEF_PLANE_STRESS) ? 1 : 0, 3};
@@ -68,15 +70,17 @@ __global__ void __launch_bounds__(MP_BLOCK) mp_update_dt_kernel(const __grid_con
         for (int c = 0; c < N; ++c) st(A.b.C, c, ld, i, C[c]);
     }
     double et[6], ee[6], sig[6];
-    pt.total_strain(x, em, et);
+    pt.material_strain(x, em, et);
 #pragma unroll
     for (int a = 0; a < 6; ++a) ee[a] = et[a] - x[a];
     const double tre = ee[0] + ee[3] + ee[5];
 #pragma unroll
     for (int a = 0; a < 6; ++a) sig[a] = is_diag(a) ? fma(m.two_mu, ee[a], m.lam * tre) : m.two_mu * ee[a];
     if (A.b.sigma) {
+        double sg[6];
+        pt.to_global(sig, sg);
 #pragma unroll
-        for (int a = 0; a < 6; ++a) st(A.b.sigma, a, ld, i, sig[a]);
+        for (int a = 0; a < 6; ++a) st(A.b.sigma, a, ld, i, sg[a]);
     }
     const double dg = x[6] - xp[6];
     const bool pl = pt.plastic;
@@ -158,18 +162,16 @@ __global__ void __launch_bounds__(MP_BLOCK) mp_update_dt_kernel(const __grid_con
         }
         if (A.b.dsig_deps) {
             double de[6];
-#pragma unroll
-            for (int a = 0; a < 6; ++a) de[a] = (a == bc) ? 1.0 : 0.0;
-#pragma unroll
-            for (int k = 0; k < NZ; ++k) de[Pt::zcomp(k)] += dx[7 + k];
-            if (DT == CMADX_DEF_UNIAXIAL_STRESS) { de[1] = dx[1]; de[2] = dx[2]; de[4] = dx[4]; }
-            double dee[6];
+            pt.dmaterial_strain(bc, dx, de);
+            double dee[6], dsm[6], dsg[6];
 #pragma unroll
             for (int a = 0; a < 6; ++a) dee[a] = de[a] - dx[a];
             const double ltr = m.lam * (dee[0] + dee[3] + dee[5]);
 #pragma unroll
-            for (int a = 0; a < 6; ++a)
-                st(A.b.dsig_deps, a * NS + bb, ld, i, is_diag(a) ? fma(m.two_mu, dee[a], ltr) : m.two_mu * dee[a]);
+            for (int a = 0; a < 6; ++a) dsm[a] = is_diag(a) ? fma(m.two_mu, dee[a], ltr) : m.two_mu * dee[a];
+            pt.to_global(dsm, dsg);
+#pragma unroll
+            for (int a = 0; a < 6; ++a) st(A.b.dsig_deps, a * NS + bb, ld, i, dsg[a]);
         }
     }
 }
@@ -177,6 +179,15 @@ __global__ void __launch_bounds__(MP_BLOCK) mp_update_dt_kernel(const __grid_con
 template <int DT>
 cudaError_t launch_dt(const MpArgs& A, cudaStream_t stream) {
     const unsigned nblk = (unsigned)((A.b.n + MP_BLOCK - 1) / MP_BLOCK);
+    if (A.m.rot) {
+        switch (A.m.yield) {
+        case CMADX_YIELD_J2: mp_update_dt_kernel<CMADX_YIELD_J2, DT, true><<<nblk, MP_BLOCK, 0, stream>>>(A); break;
+        case CMADX_YIELD_HILL: mp_update_dt_kernel<CMADX_YIELD_HILL, DT, true><<<nblk, MP_BLOCK, 0, stream>>>(A); break;
+        case CMADX_YIELD_HOSFORD: mp_update_dt_kernel<CMADX_YIELD_HOSFORD, DT, true><<<nblk, MP_BLOCK, 0, stream>>>(A); break;
+        default: return cudaErrorInvalidValue;
+        }
+        return cudaGetLastError();
+    }
     switch (A.m.yield) {
     case CMADX_YIELD_J2: mp_update_dt_kernel<CMADX_YIELD_J2, DT><<<nblk, MP_BLOCK, 0, stream>>>(A); break;
     case CMADX_YIELD_HILL: mp_update_dt_kernel<CMADX_YIELD_HILL, DT><<<nblk, MP_BLOCK, 0, stream>>>(A); break;

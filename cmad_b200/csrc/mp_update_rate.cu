@@ -20,6 +20,23 @@ __global__ void __launch_bounds__(MP_BLOCK) mp_update_rate_kernel(const __grid_c
         for (int c = 0; c < 6; ++c) de[c] -= ep[c];
     }
     if (!live) de[0] = 1e-3;
+    // rotated material axes (compute_delta_strain :53-72, _cauchy_fn :351-359): the state is the
+    // MATERIAL-frame stress; the increment enters as Q^T de Q, the stress leaves as Q sig Q^T
+    const bool rot = m.rot != 0;
+    double T[6][6], S[6][6];
+    if (rot) {
+        rot_maps(m.Q, T, S);
+        double dm[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) s = fma(T[c][b], de[b], s);
+            dm[c] = s;
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) de[c] = dm[c];
+    }
 #pragma unroll
     for (int c = 0; c < 7; ++c) x[c] = xp[c];
     if (live && A.b.xi_init) {
@@ -43,7 +60,15 @@ __global__ void __launch_bounds__(MP_BLOCK) mp_update_rate_kernel(const __grid_c
     }
     if (A.b.sigma) {
 #pragma unroll
-        for (int a = 0; a < 6; ++a) st(A.b.sigma, a, ld, i, x[a]);
+        for (int a = 0; a < 6; ++a) {
+            double v = x[a];
+            if (rot) {
+                v = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) v = fma(S[a][c], x[c], v);
+            }
+            st(A.b.sigma, a, ld, i, v);
+        }
     }
     const double dg = x[6] - xp[6];
     const bool pl = pt.plastic;
@@ -82,6 +107,7 @@ __global__ void __launch_bounds__(MP_BLOCK) mp_update_rate_kernel(const __grid_c
     const bool trouble = lu.factor_natural();
     const bool slow = __any_sync(__activemask(), trouble);
     if (slow && trouble) { pt.jacobian(m, dg, lu.a); lu.factor_pivot(); }
+    double Xm[7][6];         // dxi / d(material strain increment component b)
 #pragma unroll
     for (int b = 0; b < 6; ++b) {
         // dC/d(de_b) = -(delta_ab + (lam/2mu) [a diag][b diag]) on the stress rows, both branches
@@ -90,14 +116,44 @@ __global__ void __launch_bounds__(MP_BLOCK) mp_update_rate_kernel(const __grid_c
         for (int a = 0; a < 6; ++a) col[a] = ((a == b) ? 1.0 : 0.0) + ((is_diag(a) && is_diag(b)) ? lr : 0.0);
         col[6] = 0.0;
         if (slow && trouble) lu.solve_pivot(col); else lu.solve_natural(col);     // = -dxi/d(de_b)... sign folded
-        if (A.b.dxi_deps) {
 #pragma unroll
-            for (int r = 0; r < 7; ++r) st(A.b.dxi_deps, r * 6 + b, ld, i, col[r]);
-        }
-        if (A.b.dsig_deps) {
+        for (int r = 0; r < 7; ++r) Xm[r][b] = col[r];
+    }
+    if (rot) {               // global strain components: columns through T, stress rows through S
+        double Xg[7][6];
 #pragma unroll
-            for (int a = 0; a < 6; ++a) st(A.b.dsig_deps, a * 6 + b, ld, i, col[a]);
-        }
+        for (int r = 0; r < 7; ++r)
+#pragma unroll
+            for (int b = 0; b < 6; ++b) {
+                double s = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) s = fma(Xm[r][c], T[c][b], s);
+                Xg[r][b] = s;
+            }
+#pragma unroll
+        for (int r = 0; r < 7; ++r)
+#pragma unroll
+            for (int b = 0; b < 6; ++b) Xm[r][b] = Xg[r][b];
+    }
+    if (A.b.dxi_deps) {
+#pragma unroll
+        for (int r = 0; r < 7; ++r)
+#pragma unroll
+            for (int b = 0; b < 6; ++b) st(A.b.dxi_deps, r * 6 + b, ld, i, Xm[r][b]);
+    }
+    if (A.b.dsig_deps) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = 0; b < 6; ++b) {
+                double v = Xm[a][b];
+                if (rot) {
+                    v = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) v = fma(S[a][c], Xm[c][b], v);
+                }
+                st(A.b.dsig_deps, a * 6 + b, ld, i, v);
+            }
     }
 }
 

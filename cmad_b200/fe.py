@@ -187,14 +187,18 @@ def assemble_element_block_residual(material, newton, arrays, U_global, xi_prev_
 def assemble_element_block_mixed(material: L.Material, newton: NewtonSettings, arrays: FEBlockArrays,
                                  U_global: torch.Tensor, xi_prev_per_block: torch.Tensor,
                                  stab_mult: float = 1.0, r_plan: SegmentPlan | None = None,
-                                 want_K: bool = True, stream: torch.cuda.Stream | None = None):
+                                 want_K: bool = True, stream: torch.cuda.Stream | None = None,
+                                 U_prev: torch.Tensor | None = None):
     """Mixed u-p (``SmallDispEquilibrium(mixed=True)``, small_disp_equilibrium.py:87-111)
     counterpart of :func:`assemble_element_block`: returns ``(R_block, vals, xi_solved)``
     with ``R_block (n_dofs,)`` over the block-major (u, p) dofs and ``vals`` the
     concatenated COO streams in the reference's (r, s) emit order - (u,u), (u,p), (p,u),
     (p,p), each flattened ``(elem, row dof, col dof)`` (cmad/fem/assembly.py:722-732).
     ``r_plan``: a :class:`SegmentPlan` over ``cat(elem_eq.ravel(), elem_eq_p.ravel())``
-    (deterministic R); otherwise atomics.  ``want_K=False``: residual only (vals is None)."""
+    (deterministic R); otherwise atomics.  ``want_K=False``: residual only (vals is None).
+    ``U_prev``: the previous step's (u, p) vector, required by ``small_rate_elastic_plastic`` blocks -
+    their pressure rows depend on the local state (``hydro_cauchy = tr(cauchy(xi)) / 3``) and are
+    formed by the element kernel itself."""
     if not arrays.mixed:
         raise ValueError("block arrays were built without mixed=True")
     n_e, n_b, n_ip = arrays.n_elems, arrays.n_basis, arrays.n_ip
@@ -218,7 +222,10 @@ def assemble_element_block_mixed(material: L.Material, newton: NewtonSettings, a
     if r_plan is None:
         R = torch.zeros(arrays.n_dofs, dtype=torch.float64, device=dev)
         out["R_global"] = R
-    b = _fe_struct(arrays, U_global, xi_prev_per_block, out)
+    if U_prev is not None and (U_prev.dtype != torch.float64 or U_prev.numel() != arrays.n_dofs
+                               or not U_prev.is_contiguous() or U_prev.device != dev):
+        raise ValueError(f"U_prev: expected contiguous float64 ({arrays.n_dofs},) on {dev}")
+    b = _fe_struct(arrays, U_global, xi_prev_per_block, out, U_prev)
     mx = L.FeMixed()
     mx.elem_eq_p, mx.N, mx.h = arrays.elem_eq_p.data_ptr(), arrays.N.data_ptr(), arrays.h.data_ptr()
     mx.stab_mult = float(stab_mult)

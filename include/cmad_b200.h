@@ -40,7 +40,9 @@ enum {
 /* ---- models: cmad/models/small_elastic_plastic.py:95, cmad/models/elastic.py:29 */
 /* CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC (cmad/models/small_rate_elastic_plastic.py): state =
  * [cauchy(6), alpha]; the `strain` rows of a batch carry the strain INCREMENT eps - eps_prev
- * (the reference forms it from U and U_prev); K1 only, FULL_3D, identity material axes. */
+ * (the reference forms it from U and U_prev); FULL_3D, rotated material axes included: K1, the
+ * forward history, K2 adjoint / direct, element blocks of any rule in the displacement and the
+ * mixed u-p form (fe_rate.cu).  Not carried: the def-type kernels, the Hessian path, K6. */
 enum { CMADX_MODEL_SMALL_ELASTIC_PLASTIC = 0, CMADX_MODEL_ELASTIC = 1,
        CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC = 2 };
 /* ---- effective stress: cmad/models/effective_stress.py:16-27 */

@@ -1036,6 +1036,48 @@ def coupled_ip(params, U_e, U_e_prev, x_prev, grad_N, w, dv, spec: ModelSpec,
     return R, dR, x, info
 
 
+def coupled_ip_mixed(params, U_e, p_e, U_e_prev, x_prev, grad_N, N, w, dv, h, spec: ModelSpec,
+                     stab_mult: float = 1.0, newton_settings: dict | None = None):
+    """``R_and_dR_dU_and_xi`` of the MIXED u-p formulation at one integration point
+    (small_disp_equilibrium.py:87-111) for a model whose ``dev_cauchy`` / ``hydro_cauchy`` read the
+    LOCAL STATE (SmallRateElasticPlastic, small_rate_elastic_plastic.py:361-376):
+    ``sigma = dev(cauchy(xi)) - p I``, ``R_p = (-(p + hydro)/kappa N - tau gradN.grad p) w dv``,
+    ``tau = stab h^2 / (2 mu)``.  Total derivatives through the IFT rule: dxi/dU from
+    ``ift_dxi_dgrad_u`` (C does not see p).  Returns ``(R_u, R_p, K_uu, K_up, K_pu, K_pp, xi)``."""
+    settings = newton_settings or {"abs_tol": 1e-12, "rel_tol": 1e-12, "max_iters": 20}
+    U_e = torch.as_tensor(U_e, dtype=DT); U_e_prev = torch.as_tensor(U_e_prev, dtype=DT)
+    p_e = torch.as_tensor(p_e, dtype=DT).reshape(-1)
+    grad_N = torch.as_tensor(grad_N, dtype=DT); N = torch.as_tensor(N, dtype=DT)
+    n_b = U_e.shape[0]
+    gu = interpolate_grad_u(U_e, grad_N); gup = interpolate_grad_u(U_e_prev, grad_N)
+    x, _ = newton_traced(x_prev, params, gu, gup, spec, **settings)
+    xp = torch.as_tensor(x_prev, dtype=DT)
+    lam, mu = lame_from_params(params["elastic"])
+    kappa = lam + 2. * mu / 3.
+    tau = stab_mult * 0.5 * h ** 2 / mu
+
+    def res(U, p, xx):
+        g = interpolate_grad_u(U, grad_N)
+        cauchy = cauchy_fun(spec)(xx, xp, params, g, gup, spec)
+        hydro = torch.trace(cauchy) / 3.
+        pr = N @ p
+        sigma = cauchy - hydro * torch.eye(3, dtype=DT) - pr * torch.eye(3, dtype=DT)
+        Ru = (grad_N @ sigma) * w * dv
+        Rp = (-(pr + hydro) / kappa * N - tau * (grad_N @ (grad_N.T @ p))) * w * dv
+        return torch.cat([Ru.reshape(-1), Rp])
+
+    R = res(U_e, p_e, x)
+    dR_dU = jacfwd(res, argnums=0)(U_e, p_e, x).reshape(4 * n_b, n_b, 3)
+    dR_dp = jacfwd(res, argnums=1)(U_e, p_e, x)
+    dR_dx = jacfwd(res, argnums=2)(U_e, p_e, x)                                   # (4 n_b, n_xi)
+    dx_dgu = ift_dxi_dgrad_u(x, xp, params, gu, gup, spec)                        # (n_xi, 3, 3) [., k, l]
+    dx_dU = torch.einsum("xkl,bl->xbk", dx_dgu, grad_N)                           # grad_u[k,l] = U[b,k] gradN[b,l]
+    K = dR_dU + torch.einsum("rx,xbk->rbk", dR_dx, dx_dU)
+    nu = 3 * n_b
+    return (R[:nu].reshape(n_b, 3), R[nu:], K[:nu].reshape(nu, nu), dR_dp[:nu], K[nu:].reshape(n_b, nu),
+            dR_dp[nu:], x)
+
+
 def coupled_element(params, U_e, U_e_prev, xi_prev_ips, grad_N_ips, dets, quad_w,
                     spec: ModelSpec, newton_settings=None, want_tangent=True):
     """``per_element_R_and_K_coupled`` (fem/assembly.py:416-535): scan over IPs,

@@ -409,7 +409,7 @@ def _fe_job(job):
                 Ue = [U, pe]
             Uprev = [np.zeros_like(u) for u in Ue]
             if rate:                   # the rate form sees eps(U) - eps(U_prev): carry the real previous step
-                Uprev = [U_last.copy()]
+                Uprev = [U_last.copy()] + ([np.zeros((n_b, 1))] if mixed else [])
             rec["U_prev"].append(Uprev[0].copy())
             Rb, Kb, xi = per_element_R_and_K_coupled(
                 Ue, Uprev, P.values, xi_prev, geom, shared, ev["R_and_dR_dU_and_xi"], unravel_xi,
@@ -523,6 +523,11 @@ def _deftype_job(job):
         tag = "scaled" if scaled else "native"
         for name, ctor in (("adjoint", MPAdjointObjective), ("direct", MPDirectObjective)):
             Po.set_active_values_from_flat(offset, False)
+            # MPObjective.__init__ (mp_objective.py:46) stores the model's CURRENT xi as the step-0 state
+            # of the adjoint pass; after the data run above that is the END state.  Harmless while the
+            # first load step is elastic (the identity-axes fixtures), wrong when it is plastic (the
+            # rotated ones: adjoint != direct by 50 %): build the objective on a model at its initial state.
+            mo_.set_xi_to_init_vals()
             J, g = ctor(qoi, F).evaluate(x)
             out[f"obj_{tag}.J_{name}"], out[f"obj_{tag}.grad_{name}"] = float(J), np.asarray(g, float)
         out[f"obj_{tag}.data"], out[f"obj_{tag}.weight"], out[f"obj_{tag}.x_canonical"] = data, w, x
@@ -846,6 +851,42 @@ def main():
                 out[f"{job[0]}.{job[1]}.{k}"] = v
             print("rate fe", job[:2], "alpha max", r["xi"][..., 6].max(), "|K|", np.abs(r["K_uu"]).max())
         np.savez_compressed(os.path.join(HERE, "ref_rate_fe_elements.npz"), **out)
+
+
+    if only is not None and "deftypes_rot" in only:
+        # PLANE_STRESS / UNIAXIAL_STRESS with rotated material axes (small_elastic_plastic.py:44-62:
+        # the uniaxial constraint is imposed on the GLOBAL off-diagonal strains, Q ep Q^T)
+        jobs = [("hill_rot", dt) for dt in ("PLANE_STRESS", "UNIAXIAL_STRESS")]
+        out = {}
+        for (kind, dt), r in zip(jobs, pool.map(_deftype_job, jobs, chunksize=1)):
+            for k, v in r.items():
+                out[f"{kind}.{dt}.{k}"] = v
+            print("deftypes_rot", kind, dt, "iters", np.bincount(r["iters"]), "traced", np.bincount(r["traced_iters"]),
+                  "alpha", r["xi"][-1, 6], "J", r["obj_scaled.J_adjoint"], flush=True)
+        np.savez_compressed(os.path.join(HERE, "ref_def_types_rot.npz"), **out)
+
+    if only is not None and "rate_rot" in only:
+        # SmallRateElasticPlastic with rotated material axes (the case tests/models/
+        # test_hill_material_rotations.py runs) and in the mixed u-p formulation (tests/fem/
+        # test_mixed_up_plastic.py): K1 / Model AD products, calibration objectives, element blocks
+        out = {}
+        (r,) = pool.map(_rate_job, [("hill_rot",)], chunksize=1)
+        for k, v in r.items():
+            out[f"model.hill_rot.{k}"] = v
+        print("rate_rot model iters", np.bincount(r["iters"]), "alpha", r["xi"][-1, 6], flush=True)
+        w = np.array([[1.0, 0.5, 0.0], [0.5, 1.0, 0.0], [0.0, 0.0, 0.25]])
+        jobs = [("hill_rot", sc, two_leg_F(11, 24, scale=1.5), w, "rate") for sc in (True, False)]
+        for nm, r in zip(("scaled", "native"), pool.map(_objective_job, jobs, chunksize=1)):
+            for k, v in r.items():
+                out[f"objective.hill_rot.{nm}.{k}"] = v
+            print("rate_rot objective", nm, r["J_adjoint"], r["grad_adjoint"], r["grad_direct"], flush=True)
+        jobs = [("tet4", "hill_rot", False, 51, 3, "rate"), ("hex8", "hill_rot", True, 52, 2, "rate"),
+                ("tet4", "J2", True, 53, 3, "rate"), ("hex8", "hosford", True, 54, 2, "rate")]
+        for job, r in zip(jobs, pool.map(_fe_job, jobs, chunksize=1)):
+            for k, v in r.items():
+                out[f"fe.{job[0]}.{job[1]}.{'mixed' if job[2] else 'disp'}.{k}"] = v
+            print("rate_rot fe", job[:3], "alpha max", r["xi"][..., 6].max(), "|K|", np.abs(r["K_uu"]).max(), flush=True)
+        np.savez_compressed(os.path.join(HERE, "ref_rate_rot.npz"), **out)
 
 
 if __name__ == "__main__":

@@ -19,7 +19,23 @@ from cmad_b200 import Parameters
 from tests.golden.materials import active_all_scalars, const_like, material, objective_trees
 from tests.helpers import UP, rel_err
 
-DT = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_def_types.npz"))
+class _Fixtures:
+    """Several .npz fixtures behind one lookup (keys are disjoint: `<kind>.<def type>.<array>`)."""
+
+    def __init__(self, *names):
+        self._z = [np.load(os.path.join(os.path.dirname(__file__), "golden", n)) for n in names]
+        self.files = [k for z in self._z for k in z.files]
+
+    def __getitem__(self, key):
+        for z in self._z:
+            if key in z.files:
+                return z[key]
+        raise KeyError(key)
+
+
+# ref_def_types_rot.npz: the same jobs on the rotated anisotropic Hill material (`--only deftypes_rot`):
+# constraints in global axes, update in material axes (small_elastic_plastic.py:44-62, 287-302)
+DT = _Fixtures("ref_def_types.npz", "ref_def_types_rot.npz")
 CASES = sorted({".".join(k.split(".")[:2]) for k in DT.files})
 DEF = {"PLANE_STRESS": 1, "UNIAXIAL_STRESS": 2}            # CMADX_DEF_*
 
