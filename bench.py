@@ -38,7 +38,7 @@ N_POINTS = 1 << 24
 HISTORY_STEPS = 100
 SEED = 22
 ALG_BYTES_PER_UPDATE = 784      # in 56+48, out 56+48+288+280+4+4
-# ncu --set full capture of mp_update_j2_kernel at the bench size (profiles/r1_final_k1_j2_raw.txt):
+# ncu --set full capture of mp_update_j2_kernel at the bench size (profiles/r1_final_k1_j2_raw.txt; re-captured on the round-2 binary: 13.098 GB, profiles/r2z_k1_j2_keys.txt):
 # dram__bytes_read 1.745326 GB + dram__bytes_write 11.350847 GB for one 16 777 216-point launch
 NCU_DRAM_BYTES_PER_UPDATE = (1.745326e9 + 11.350847e9) / 16777216
 OUTPUTS = ("xi", "sigma", "dsig_deps", "dC_dp", "iters", "flags")
@@ -294,7 +294,7 @@ def run_b200(args):
                 "alg_bytes_per_update": ALG_BYTES_PER_UPDATE, "avg_launch_ms": avg_kernel_ms,
                 "traffic_note": "bytes per launch of this size, from the ncu --set full capture of a 2^24-point "
                                 "launch (780.6 B/update measured vs 784 algorithmic: no re-reads), "
-                                "profiles/r1_final_k1_j2_raw.txt",
+                                "profiles/r1_final_k1_j2_raw.txt; re-captured on the round-2 binary: 13.098 GB, profiles/r2z_k1_j2_keys.txt",
                 "fp64": {"peak_tflops_measured": fp64_peak,
                          "note": "DFMA micro-benchmark (cmadx_fp64_peak); FP64 pipe ~28% busy in the "
                                  "J2 kernel (ncu), i.e. HBM binds"}}
@@ -344,7 +344,7 @@ def run_b200(args):
                 line["cpu_baseline_handderived"] = hd
     del strains, xi_a, xi_b, outs, out_a, out_b, scratch
     torch.cuda.empty_cache()
-    if not args.no_extra:
+    if not args.no_extra and args.extra_steps > 0:          # --extra-steps 0 = skip (profiling runs)
         from benchmarks import extra_configs as xc
         ctx = xc.Ctx(dev, rank, world, local, hbm_peak, fp64_peak, ClockSampler, args.extra_steps, W)
         which = set(args.extra.split(",")) if args.extra else None

@@ -211,10 +211,8 @@ static int build_args(const cmadx_material_t* mat, const cmadx_newton_t* nw,
     for (int c = 0; c < n_active; ++c) {
         const int pid = active_pid[c];
         if (pid < 0 || pid >= CMADX_NUM_PARAM_IDS) return CMADX_EINVAL;
-        // the Hosford exponent: SmallElasticPlastic / rate model in FULL_3D (the def-type kernels
-        // do not carry it); rotation-matrix entries: FULL_3D SmallElasticPlastic, dC/dp output
-        // of the generic kernels only (see write_point_outputs)
-        if (pid == CMADX_P_HOSFORD_A && b->def_type != CMADX_DEF_FULL_3D) return CMADX_EUNSUPPORTED;
+        // rotation-matrix entries: FULL_3D SmallElasticPlastic, dC/dp output of the generic kernels
+        // only (see write_point_outputs)
         if (pid >= CMADX_P_BARLAT_C0 && mat->yield != CMADX_YIELD_BARLAT) return CMADX_EINVAL;
         if (pid >= CMADX_P_Q00 && pid < CMADX_P_BARLAT_C0) {
             if (b->def_type != CMADX_DEF_FULL_3D || A->m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC)
@@ -225,9 +223,7 @@ static int build_args(const cmadx_material_t* mat, const cmadx_newton_t* nw,
     }
     A->n_active = n_active;
     if (A->m.yield == CMADX_YIELD_BARLAT && A->m.model != CMADX_MODEL_ELASTIC) {
-        // Yld2004-18p: SmallElasticPlastic in FULL_3D, one-pass generic kernels
-        if (A->m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC || b->def_type != CMADX_DEF_FULL_3D)
-            return CMADX_EUNSUPPORTED;
+        // Yld2004-18p: the one-pass generic kernels (FULL_3D, def-type and rate kernels)
         A->nw.flags &= ~(CMADX_NEWTON_F_CTA | CMADX_NEWTON_F_QUEUE | CMADX_NEWTON_F_STREAM);
         A->nw.defer_request = 0;
     }
@@ -627,8 +623,6 @@ static int check_history(const cmadx_material_t* mat, const cmadx_mp_history_t* 
     // the rate model: FULL_3D (mp_update_rate.cu, mp_sens_rate.cu)
     if (rate && (sc != 6 && sc != 9)) return CMADX_EUNSUPPORTED;
     if (h->n > 0 && (!h->strain || !h->xi_hist)) return CMADX_EINVAL;
-    // Yld2004-18p: SmallElasticPlastic in FULL_3D (K1, forward history, K2)
-    if (dm->yield == CMADX_YIELD_BARLAT && (rate || history_def_type(h) != CMADX_DEF_FULL_3D)) return CMADX_EUNSUPPORTED;
     if (h->qoi_kind != CMADX_QOI_CALIBRATION) {
         if (h->qoi_kind != CMADX_QOI_UNIAXIAL_CALIBRATION) return CMADX_EINVAL;
         if (history_def_type(h) != CMADX_DEF_UNIAXIAL_STRESS || rate) return CMADX_EUNSUPPORTED;

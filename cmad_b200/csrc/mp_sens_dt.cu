@@ -252,6 +252,8 @@ cudaError_t launch_t(const SensArgs& A, cudaStream_t stream) {
             mp_sens_dt_kernel<CMADX_YIELD_HILL, DT, ADJOINT, true><<<(unsigned)nblk, SENS_DT_BLOCK, 0, stream>>>(A); break;
         case CMADX_YIELD_HOSFORD:
             mp_sens_dt_kernel<CMADX_YIELD_HOSFORD, DT, ADJOINT, true><<<(unsigned)nblk, SENS_DT_BLOCK, 0, stream>>>(A); break;
+        case CMADX_YIELD_BARLAT:
+            mp_sens_dt_kernel<CMADX_YIELD_BARLAT, DT, ADJOINT, true><<<(unsigned)nblk, SENS_DT_BLOCK, 0, stream>>>(A); break;
         default: return cudaErrorInvalidValue;
         }
         cudaError_t er = cudaGetLastError();
@@ -265,6 +267,8 @@ cudaError_t launch_t(const SensArgs& A, cudaStream_t stream) {
         mp_sens_dt_kernel<CMADX_YIELD_HILL, DT, ADJOINT><<<(unsigned)nblk, SENS_DT_BLOCK, 0, stream>>>(A); break;
     case CMADX_YIELD_HOSFORD:
         mp_sens_dt_kernel<CMADX_YIELD_HOSFORD, DT, ADJOINT><<<(unsigned)nblk, SENS_DT_BLOCK, 0, stream>>>(A); break;
+    case CMADX_YIELD_BARLAT:
+        mp_sens_dt_kernel<CMADX_YIELD_BARLAT, DT, ADJOINT><<<(unsigned)nblk, SENS_DT_BLOCK, 0, stream>>>(A); break;
     default: return cudaErrorInvalidValue;
     }
     cudaError_t e = cudaGetLastError();

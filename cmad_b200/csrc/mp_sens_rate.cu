@@ -195,6 +195,7 @@ cudaError_t launch_t(const SensArgs& A, cudaStream_t stream) {
     case CMADX_YIELD_J2: mp_sens_rate_kernel<CMADX_YIELD_J2, ADJOINT><<<nblk, SENS_BLOCK, 0, stream>>>(A); break;
     case CMADX_YIELD_HILL: mp_sens_rate_kernel<CMADX_YIELD_HILL, ADJOINT><<<nblk, SENS_BLOCK, 0, stream>>>(A); break;
     case CMADX_YIELD_HOSFORD: mp_sens_rate_kernel<CMADX_YIELD_HOSFORD, ADJOINT><<<nblk, SENS_BLOCK, 0, stream>>>(A); break;
+    case CMADX_YIELD_BARLAT: mp_sens_rate_kernel<CMADX_YIELD_BARLAT, ADJOINT><<<nblk, SENS_BLOCK, 0, stream>>>(A); break;
     default: return cudaErrorInvalidValue;
     }
     cudaError_t e = cudaGetLastError();

@@ -165,6 +165,7 @@ cudaError_t launch_mp_update_rate(const MpArgs& A, cudaStream_t stream) {
     case CMADX_YIELD_J2: mp_update_rate_kernel<CMADX_YIELD_J2><<<nblk, MP_BLOCK, 0, stream>>>(A); break;
     case CMADX_YIELD_HILL: mp_update_rate_kernel<CMADX_YIELD_HILL><<<nblk, MP_BLOCK, 0, stream>>>(A); break;
     case CMADX_YIELD_HOSFORD: mp_update_rate_kernel<CMADX_YIELD_HOSFORD><<<nblk, MP_BLOCK, 0, stream>>>(A); break;
+    case CMADX_YIELD_BARLAT: mp_update_rate_kernel<CMADX_YIELD_BARLAT><<<nblk, MP_BLOCK, 0, stream>>>(A); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

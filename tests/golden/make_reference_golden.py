@@ -865,6 +865,33 @@ def main():
                   "alpha", r["xi"][-1, 6], "J", r["obj_scaled.J_adjoint"], flush=True)
         np.savez_compressed(os.path.join(HERE, "ref_def_types_rot.npz"), **out)
 
+    if only is not None and "barlat_more" in only:
+        # Yld2004-18p in the def-type kernels and in the rate form (material point): slow jobs, own files
+        dt_jobs = [("barlat", dt) for dt in ("PLANE_STRESS", "UNIAXIAL_STRESS")]
+        w = np.array([[1.0, 0.5, 0.0], [0.5, 1.0, 0.0], [0.0, 0.0, 0.25]])
+        ob_jobs = [("barlat", sc, two_leg_F(11, 24, scale=1.5), w, "rate") for sc in (True, False)]
+        r_dt = pool.map_async(_deftype_job, dt_jobs, chunksize=1)
+        r_rm = pool.map_async(_rate_job, [("barlat",)], chunksize=1)
+        r_ob = pool.map_async(_objective_job, ob_jobs, chunksize=1)
+        out = {}
+        for (kind, dt), r in zip(dt_jobs, r_dt.get()):
+            for k, v in r.items():
+                out[f"{kind}.{dt}.{k}"] = v
+            print("barlat deftypes", dt, "iters", np.bincount(r["iters"]), "alpha", r["xi"][-1, 6], flush=True)
+        np.savez_compressed(os.path.join(HERE, "ref_def_types_barlat.npz"), **out)
+        out = {}
+        (r,) = r_rm.get()
+        for k, v in r.items():
+            out[f"barlat.{k}"] = v
+        print("barlat rate iters", np.bincount(r["iters"]), "alpha", r["xi"][-1, 6], flush=True)
+        np.savez_compressed(os.path.join(HERE, "ref_rate_model_barlat.npz"), **out)
+        out = {}
+        for nm, r in zip(("barlat.scaled", "barlat.native"), r_ob.get()):
+            for k, v in r.items():
+                out[f"{nm}.{k}"] = v
+            print("barlat rate objective", nm, r["J_adjoint"], r["grad_adjoint"], r["grad_direct"], flush=True)
+        np.savez_compressed(os.path.join(HERE, "ref_rate_objectives_barlat.npz"), **out)
+
     if only is not None and "rate_rot" in only:
         # SmallRateElasticPlastic with rotated material axes (the case tests/models/
         # test_hill_material_rotations.py runs) and in the mixed u-p formulation (tests/fem/

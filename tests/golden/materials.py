@@ -73,6 +73,19 @@ def active_all_scalars(values):
     return act
 
 
+def active_kernel_set(values):
+    """`active_all_scalars`, within the kernels' limit of CMADX_MAX_ACTIVE = 16 columns: a Barlat
+    material (23 differentiable scalar leaves) keeps the elastic / flow-stress leaves and the nine
+    `sp_*` coefficients (the `dp_*` columns and the exponent are covered by tests/test_barlat.py)."""
+    act = active_all_scalars(values)
+    b = act["plastic"]["effective stress"].get("barlat")
+    if b is not None:
+        for k in b:
+            if k.startswith("dp_"):
+                b[k] = False
+    return act
+
+
 def objective_trees(kind, scaled):
     """(values, active, transforms) of the objective fixtures: flow-stress
     parameters active with log / bounds transforms (test_problems.py:27-48), or

@@ -16,7 +16,7 @@ import numpy as np
 import pytest
 
 from cmad_b200 import Parameters
-from tests.golden.materials import active_all_scalars, const_like, material, objective_trees
+from tests.golden.materials import active_all_scalars, active_kernel_set, const_like, material, objective_trees
 from tests.helpers import UP, rel_err
 
 class _Fixtures:
@@ -35,7 +35,8 @@ class _Fixtures:
 
 # ref_def_types_rot.npz: the same jobs on the rotated anisotropic Hill material (`--only deftypes_rot`):
 # constraints in global axes, update in material axes (small_elastic_plastic.py:44-62, 287-302)
-DT = _Fixtures("ref_def_types.npz", "ref_def_types_rot.npz")
+# ref_def_types_barlat.npz: the Yld2004-18p surface in both def-types (`--only barlat_more`)
+DT = _Fixtures("ref_def_types.npz", "ref_def_types_rot.npz", "ref_def_types_barlat.npz")
 CASES = sorted({".".join(k.split(".")[:2]) for k in DT.files})
 DEF = {"PLANE_STRESS": 1, "UNIAXIAL_STRESS": 2}            # CMADX_DEF_*
 
@@ -86,7 +87,7 @@ def test_cuda_vs_reference_def_types(cuda_device, case):
     kind, dtn = case.split(".")
     dt = DEF[dtn]
     values = material(kind)
-    P = Parameters(values, active_all_scalars(values), const_like(values, None))
+    P = Parameters(values, active_kernel_set(values), const_like(values, None))
     mat, pid = material_from_values(values), active_param_ids(P)
     aidx = np.asarray(P.active_idx)
     F = DT[f"{case}.F"]
@@ -121,6 +122,36 @@ def test_cuda_vs_reference_def_types(cuda_device, case):
     # stress constraint of the def-type at the end state
     s = o["sigma"][:, 0].cpu().numpy()
     assert abs(s[5]) < 1e-8 and (dt == 1 or abs(s[3]) < 1e-8)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtn", ["PLANE_STRESS", "UNIAXIAL_STRESS"])
+def test_cuda_dC_dp_hosford_exponent_def_types(cuda_device, dtn):
+    """The `hosford a` column of dC/dp (the reference's jacrev over ALL leaves, model.py:126-133) from
+    the def-type kernel, at the reference's own states (Model.evaluate semantics: max_iters = 0)."""
+    import torch
+    from cmad_b200 import NewtonSettings, active_param_ids, material_from_values, mp
+    case, dt = f"hosford.{dtn}", DEF[dtn]
+    values = material("hosford")
+    act = const_like(values, False)
+    act["plastic"]["effective stress"]["hosford"]["a"] = True
+    P = Parameters(values, act, const_like(values, None))
+    aidx = np.asarray(P.active_idx)
+    F = DT[f"{case}.F"]
+    rows, nxi = _strain_rows(case, F), (8 if dt == 1 else 9)
+    mat = material_from_values(values)
+    xi_hist = np.vstack([mp.init_xi(mat, 1, "cpu", def_type=dt).numpy().T, DT[f"{case}.xi"]])     # (N+1, nxi)
+    n_plastic = 0
+    for t in range(1, F.shape[2]):
+        xp = torch.from_numpy(xi_hist[t - 1:t].T.copy()).to(cuda_device)
+        x = torch.from_numpy(xi_hist[t:t + 1].T.copy()).to(cuda_device)
+        e = torch.from_numpy(rows[:, t:t + 1].copy()).to(cuda_device)
+        o = mp.mp_update(mat, NewtonSettings(mode="imperative", max_iters=0), active_param_ids(P), xp, e,
+                         outputs=("xi", "dC_dp", "flags"), xi_init=x, def_type=dt)
+        ref = DT[f"{case}.dC_dp"][t - 1][:, aidx]
+        assert rel_err(o["dC_dp"][:, 0].cpu().numpy().reshape(nxi, 1), ref) < 1e-9 or np.abs(ref).max() == 0.0, (case, t)
+        n_plastic += int(np.abs(ref).max() > 0)
+    assert n_plastic > 5
 
 
 @pytest.mark.gpu

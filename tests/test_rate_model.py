@@ -15,10 +15,14 @@ import numpy as np
 import pytest
 
 from cmad_b200 import Parameters
-from tests.golden.materials import active_all_scalars, const_like, material
+from tests.golden.materials import active_all_scalars, active_kernel_set, const_like, material
 from tests.helpers import UP, rel_err
 
-RT = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_rate_model.npz"))
+from tests.test_def_types import _Fixtures  # noqa: E402
+
+# ref_rate_model_barlat.npz / ref_rate_objectives_barlat.npz: the same jobs with the Yld2004-18p surface
+# (`make_reference_golden.py --only barlat_more`)
+RT = _Fixtures("ref_rate_model.npz", "ref_rate_model_barlat.npz")
 KINDS = sorted({k.split(".")[0] for k in RT.files})
 
 
@@ -46,7 +50,7 @@ def test_cuda_vs_reference_rate_model(cuda_device, kind):
     import torch
     from cmad_b200 import NewtonSettings, active_param_ids, material_from_values, mp
     values = material(kind)
-    P = Parameters(values, active_all_scalars(values), const_like(values, None))
+    P = Parameters(values, active_kernel_set(values), const_like(values, None))
     mat = material_from_values(values, model="small_rate_elastic_plastic")
     pid, aidx = active_param_ids(P), np.asarray(P.active_idx)
     F = RT[f"{kind}.F"]
@@ -80,7 +84,7 @@ def test_cuda_vs_reference_rate_model(cuda_device, kind):
 #  (mp_objective.py:92-215) run by the reference on SmallRateElasticPlastic                    #
 #  (make_reference_golden.py, `rate_objective`; fixture ref_rate_objectives.npz)               #
 # ------------------------------------------------------------------------------------------ #
-RO = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_rate_objectives.npz"))
+RO = _Fixtures("ref_rate_objectives.npz", "ref_rate_objectives_barlat.npz")
 RO_CASES = sorted({k.rsplit(".", 1)[0] for k in RO.files})
 
 
