@@ -23,7 +23,10 @@ class _Fixtures:
     """Several .npz fixtures behind one lookup (keys are disjoint: `<kind>.<def type>.<array>`)."""
 
     def __init__(self, *names):
-        self._z = [np.load(os.path.join(os.path.dirname(__file__), "golden", n)) for n in names]
+        paths = [os.path.join(os.path.dirname(__file__), "golden", n) for n in names]
+        assert os.path.exists(paths[0]), paths[0]
+        # later files extend the first with more cases; one that has not been generated adds none
+        self._z = [np.load(p) for p in paths if os.path.exists(p)]
         self.files = [k for z in self._z for k in z.files]
 
     def __getitem__(self, key):
