@@ -31,6 +31,8 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libcmad_b200_xla.so")
 TARGETS = {
     "cmadx_mp_update": "CmadxMpUpdate",
     "cmadx_mp_update_full": "CmadxMpUpdateFull",
+    "cmadx_mp_model_partials": "CmadxMpModelPartials",
+    "cmadx_sym3_eigh": "CmadxSym3Eigh",
     "cmadx_fe_block": "CmadxFeBlock",
     "cmadx_fe_block_residual": "CmadxFeBlockResidual",
     "cmadx_fe_block_mixed": "CmadxFeBlockMixed",

@@ -116,6 +116,40 @@ ffi::Error MpUpdateFullImpl(cudaStream_t stream, F64 xi_prev, F64 strain, Bytes 
     return status(cmadx_mp_update(&mat, &nw, active_pid.data(), (int32_t)active_pid.size(), &b, stream));
 }
 
+// Model._jacobian[DU], Model.dcauchy[DXI | DPARAMS] and jacfwd(cauchy, DU) at given states
+// (cmad/models/model.py:121-160), component-major [comps][n]
+ffi::Error MpModelPartialsImpl(cudaStream_t stream, F64 xi, F64 xi_prev, F64 strain, Bytes material,
+                               ffi::Span<const int32_t> active_pid, RF64 dC_deps, RF64 dsig_dxi, RF64 dsig_deps,
+                               RF64 dsig_dp) {
+    CMADX_UNPACK(cmadx_material_t, mat, material);
+    auto d = xi.dimensions();
+    auto dp = xi_prev.dimensions();
+    auto e = strain.dimensions();
+    if (d.size() != 2 || dp.size() != 2 || e.size() != 2 || d[0] != 7 || dp[0] != 7 || d[1] != e[1] || dp[1] != d[1])
+        return ffi::Error::InvalidArgument("xi / xi_prev / strain: expected [7][n], [7][n], [6|9][n]");
+    cmadx_mp_partials_t p;
+    std::memset(&p, 0, sizeof p);
+    p.n = d[1];
+    p.ld = d[1];
+    p.strain_comps = (int32_t)e[0];
+    p.xi = xi.typed_data();
+    p.xi_prev = xi_prev.typed_data();
+    p.strain = strain.typed_data();
+    p.dC_deps = dC_deps->typed_data();
+    p.dsig_dxi = dsig_dxi->typed_data();
+    p.dsig_deps = dsig_deps->typed_data();
+    p.dsig_dp = active_pid.size() ? dsig_dp->typed_data() : nullptr;
+    return status(cmadx_mp_model_partials(&mat, active_pid.data(), (int32_t)active_pid.size(), &p, stream));
+}
+
+// sorted_eigen_decomposition (cmad/util/jax_eigen_decomposition.py:86-171) over a batch: A6 [6][n] ->
+// eigenvalues [3][n] ascending, eigenvectors [9][n] (row 3 m + k = component m of vector k)
+ffi::Error Sym3EighImpl(cudaStream_t stream, F64 A6, RF64 w, RF64 V) {
+    auto d = A6.dimensions();
+    if (d.size() != 2 || d[0] != 6) return ffi::Error::InvalidArgument("A6: expected [6][n]");
+    return status(cmadx_sym3_eigh(d[1], d[1], A6.typed_data(), w->typed_data(), V->typed_data(), stream));
+}
+
 // ------------------------------------------------------------------------------------
 // FE element block.  The arrays are the reference's own, unchanged: u_gather_eq (int32),
 // grad_N_phys (n_e, n_ip, n_b, 3), iso_jac_det (n_e, n_ip), quad_w, xi (n_e, n_ip, n_xi)
@@ -306,6 +340,14 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(CmadxMpUpdateFull, MpUpdateFullImpl,
         .Attr<Bytes>("material").Attr<Bytes>("newton").Attr<ffi::Span<const int32_t>>("active_pid").Attr<int32_t>("def_type")
         .Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>()
         .Ret<S32>().Ret<S32>());
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(CmadxMpModelPartials, MpModelPartialsImpl,
+    CMADX_STREAM.Arg<F64>().Arg<F64>().Arg<F64>()
+        .Attr<Bytes>("material").Attr<ffi::Span<const int32_t>>("active_pid")
+        .Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>());
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(CmadxSym3Eigh, Sym3EighImpl,
+    CMADX_STREAM.Arg<F64>().Ret<F64>().Ret<F64>());
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(CmadxFeBlock, FeBlockImpl,
     CMADX_STREAM.Arg<S32>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>()
