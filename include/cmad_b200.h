@@ -48,8 +48,9 @@ enum { CMADX_MODEL_SMALL_ELASTIC_PLASTIC = 0, CMADX_MODEL_ELASTIC = 1,
 /* ---- effective stress: cmad/models/effective_stress.py:16-27 */
 /* CMADX_YIELD_BARLAT: Yld2004-18p, effective_stress.py:55-84 -> verification/functions.py:71-154
  * (the eigenvalues of two linear images of the stress); carried by the one-pass material-point
- * kernels (K1, forward history), the calibration objectives (K2 adjoint / direct) and the any-rule
- * element kernels (K3 / K4, FULL_3D); the other entry points return CMADX_EUNSUPPORTED for it. */
+ * kernels (K1, forward history; the three def-types; the rate model), the calibration objectives
+ * (K2 adjoint / direct) and the any-rule element kernels (K3 / K4 of SmallElasticPlastic); the
+ * other entry points (Hessian, K6, rate-model element blocks) return CMADX_EUNSUPPORTED for it. */
 enum { CMADX_YIELD_J2 = 0, CMADX_YIELD_HILL = 1, CMADX_YIELD_HOSFORD = 2, CMADX_YIELD_BARLAT = 3 };
 /* ---- which two elastic constants are given (cmad/models/elastic_constants.py:54-104),
  *      values in sorted-key order "E" < "kappa" < "lambda" < "mu" < "nu"       */

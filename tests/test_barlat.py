@@ -305,13 +305,10 @@ def test_cuda_fe_vs_reference_elements(cuda_device, case, deterministic):
 
 @pytest.mark.gpu
 def test_cuda_barlat_unsupported_entries_say_so(cuda_device):
-    """Entry points that do not carry the surface return CMADX_EUNSUPPORTED, never a wrong answer."""
-    import torch
-    from cmad_b200 import NewtonSettings, material_from_values, mp
-    from cmad_b200._lib import DEF_PLANE_STRESS
-    values = material("barlat")
-    xi = torch.zeros((8, 4), dtype=torch.float64, device=cuda_device)
-    e = torch.zeros((3, 4), dtype=torch.float64, device=cuda_device)
+    """Entry points that do not carry the surface return CMADX_EUNSUPPORTED, never a wrong answer:
+    the Hessian pass of the calibration objective."""
+    from cmad_b200.objectives import Calibration, MPDirectAdjointObjective, SmallElasticPlastic
+    P, F, data, w = _objective_inputs("objective.barlat.scaled")
+    obj = MPDirectAdjointObjective(Calibration(SmallElasticPlastic(P), data, w), F, device=cuda_device)
     with pytest.raises(NotImplementedError):
-        mp.mp_update(material_from_values(values), NewtonSettings(mode="traced"), np.zeros(0, np.int32), xi, e,
-                     outputs=("xi",), def_type=DEF_PLANE_STRESS)
+        obj.evaluate(BR["objective.barlat.scaled.x_canonical"])

@@ -152,9 +152,12 @@ def test_cuda_dC_dp_hosford_exponent_def_types(cuda_device, dtn):
         o = mp.mp_update(mat, NewtonSettings(mode="imperative", max_iters=0), active_param_ids(P), xp, e,
                          outputs=("xi", "dC_dp", "flags"), xi_init=x, def_type=dt)
         ref = DT[f"{case}.dC_dp"][t - 1][:, aidx]
-        assert rel_err(o["dC_dp"][:, 0].cpu().numpy().reshape(nxi, 1), ref) < 1e-9 or np.abs(ref).max() == 0.0, (case, t)
-        n_plastic += int(np.abs(ref).max() > 0)
-    assert n_plastic > 5
+        got = o["dC_dp"][:, 0].cpu().numpy().reshape(nxi, 1)
+        # uniaxial stress: phi = |sigma_axial| for every exponent, the column is zero up to rounding
+        # (1e-35 in the reference's AD, 1e-20 in the closed form): absolute floor at the columns' scale
+        assert np.abs(got - ref).max() < 1e-9 * max(np.abs(ref).max(), 1e-6), (case, t)
+        n_plastic += int(np.abs(ref).max() > 1e-12)
+    assert n_plastic > 5 or dtn == "UNIAXIAL_STRESS"
 
 
 @pytest.mark.gpu
