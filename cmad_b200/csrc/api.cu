@@ -228,15 +228,17 @@ static int build_args(const cmadx_material_t* mat, const cmadx_newton_t* nw,
         A->nw.defer_request = 0;
     }
     if (b->n < 0 || b->ld < b->n) return CMADX_EINVAL;
-    if (A->m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC && b->def_type != CMADX_DEF_FULL_3D)
+    // the rate form under the def-types: mp_update_rate_dt.cu (n_xi 8 / 12), J2 / Hill / Hosford
+    if (A->m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC && b->def_type != CMADX_DEF_FULL_3D &&
+        A->m.yield == CMADX_YIELD_BARLAT)
         return CMADX_EUNSUPPORTED;
     if (b->def_type == CMADX_DEF_FULL_3D) {
         if (b->strain_comps != 6 && b->strain_comps != 9) return CMADX_EINVAL;
     } else if (b->def_type == CMADX_DEF_PLANE_STRESS || b->def_type == CMADX_DEF_UNIAXIAL_STRESS) {
         const bool ps = b->def_type == CMADX_DEF_PLANE_STRESS;
         if (ps ? (b->strain_comps != 3 && b->strain_comps != 4) : (b->strain_comps != 1)) return CMADX_EINVAL;
-        // SmallElasticPlastic only (rotated material axes: SepPointDTRot)
-        if (A->m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC) return CMADX_EUNSUPPORTED;
+        // SmallElasticPlastic (rotated material axes: SepPointDTRot) and SmallRateElasticPlastic
+        if (A->m.model == CMADX_MODEL_ELASTIC) return CMADX_EUNSUPPORTED;
     } else {
         return CMADX_EINVAL;
     }
@@ -300,7 +302,8 @@ static int launch(const MpArgs& A, cudaStream_t s) {
     if (A.b.n == 0) return CMADX_OK;
     cudaError_t e;
     if (A.b.def_type != CMADX_DEF_FULL_3D) {
-        e = launch_mp_update_dt(A, s);
+        e = (A.m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC) ? launch_mp_update_rate_dt(A, s)
+                                                                  : launch_mp_update_dt(A, s);
     } else if (A.m.model == CMADX_MODEL_ELASTIC) {
         e = launch_mp_update_elastic(A, s);
     } else if (A.m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC) {
@@ -507,7 +510,10 @@ int cmadx_mp_update_host(const cmadx_material_t* mat, const cmadx_newton_t* newt
     const int64_t n = host->n;
     if (n == 0) return CMADX_OK;
     // state rows / prescribed strain components by deformation type (cmadx_mp_buffers_t::def_type)
-    const int nxi = (A.m.model == CMADX_MODEL_ELASTIC) ? 6 : 7 + host->def_type;
+    // + the three off-axis delta strains of the rate form under uniaxial stress (n_xi = 12)
+    const int nxi = (A.m.model == CMADX_MODEL_ELASTIC) ? 6
+                    : 7 + host->def_type + ((A.m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC &&
+                                             host->def_type == CMADX_DEF_UNIAXIAL_STRESS) ? 3 : 0);
     const int ns = host->def_type == CMADX_DEF_FULL_3D ? 6 : (host->def_type == CMADX_DEF_PLANE_STRESS ? 3 : 1);
     int64_t chunk = chunk_points > 0 ? chunk_points : (int64_t)1 << 20;
     if (chunk > n) chunk = n;

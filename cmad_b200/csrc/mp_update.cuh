@@ -23,6 +23,8 @@ struct MpArgs {
 int make_dev_mat(const cmadx_material_t* mat, DevMat* out);
 int make_dev_newton(const cmadx_newton_t* nw, DevNewton* out);
 
+// SmallRateElasticPlastic under PLANE_STRESS / UNIAXIAL_STRESS (mp_update_rate_dt.cu)
+cudaError_t launch_mp_update_rate_dt(const MpArgs& A, cudaStream_t stream);
 cudaError_t launch_mp_update_sep(const MpArgs& A, cudaStream_t stream);
 // J2 radial-return kernel (valid for yield J2, no rotation, no xi_init)
 cudaError_t launch_mp_update_j2(const MpArgs& A, cudaStream_t stream);

@@ -30,7 +30,10 @@ DEFAULT_OUTPUTS = ("xi", "sigma", "dsig_deps", "dC_dp", "iters", "flags")
 
 def n_xi_of(material: L.Material, def_type: int = L.DEF_FULL_3D) -> int:
     if def_type != L.DEF_FULL_3D:
-        return DEF_TYPES[def_type][0]
+        # the rate form under uniaxial stress carries three off-axis delta strains more
+        # (small_rate_elastic_plastic.py:189-199)
+        extra = 3 if (material.model == L.MODEL_SMALL_RATE_ELASTIC_PLASTIC and def_type == L.DEF_UNIAXIAL_STRESS) else 0
+        return DEF_TYPES[def_type][0] + extra
     return 6 if material.model == L.MODEL_ELASTIC else 7
 
 
@@ -39,7 +42,7 @@ def init_xi(material: L.Material, n: int, device, def_type: int = L.DEF_FULL_3D)
     nxi = n_xi_of(material, def_type)
     x = torch.zeros((nxi, n), dtype=torch.float64, device=device)
     if def_type != L.DEF_FULL_3D:
-        x[7:] = 1.0
+        x[7:DEF_TYPES[def_type][0]] = 1.0          # the stretches; the rate form's delta strains stay 0
     return x
 
 

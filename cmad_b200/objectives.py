@@ -76,14 +76,17 @@ class SmallElasticPlastic:
 
 class SmallRateElasticPlastic(SmallElasticPlastic):
     """Stand-in for the rate form (cmad/models/small_rate_elastic_plastic.py): state =
-    [cauchy(6), alpha], FULL_3D; on the B200 path for the material-point update and the
-    ``cmad primal`` loop (:mod:`cmad_b200.primal`)."""
+    [cauchy(6), alpha] (+ the out-of-plane stretch under PLANE_STRESS, + two stretches and three
+    off-axis delta strains under UNIAXIAL_STRESS: n_xi 8 / 12, :176-199); on the B200 path for the
+    material-point update and the ``cmad primal`` loop (:mod:`cmad_b200.primal`) in the three
+    def-types, and for the calibration objectives in FULL_3D."""
     model_name = "small_rate_elastic_plastic"
 
     def __init__(self, parameters: Parameters, def_type: int = FULL_3D, yield_tol: float = 1e-14, **unsupported):
-        if def_type != FULL_3D:
-            raise NotImplementedError("SmallRateElasticPlastic: FULL_3D only on the B200 path")
-        super().__init__(parameters, FULL_3D, yield_tol, **unsupported)
+        super().__init__(parameters, def_type, yield_tol, **unsupported)
+        if def_type == UNIAXIAL_STRESS:
+            self.num_dofs += 3
+            self.num_residuals = 4
 
 
 class Calibration:

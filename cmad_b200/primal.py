@@ -41,6 +41,8 @@ def block_sizes(model: SmallElasticPlastic) -> list[int]:
     block of the PLANE_STRESS (1) / UNIAXIAL_STRESS (2) def-types
     (cmad/models/small_elastic_plastic.py:126-180)."""
     extra = model.num_dofs - 7
+    if extra == 5:          # the rate form under UNIAXIAL_STRESS: stretches (2) + off-axis delta strains (3)
+        return [6, 1, 2, 3]
     return [6, 1] + ([extra] if extra else [])
 
 
@@ -66,8 +68,8 @@ def run_primal_pass(model: SmallElasticPlastic, F: np.ndarray, num_steps: int,
     B, n_xi, dt = Fb.shape[0], model.num_dofs, _LIB_DEF_TYPE[model._def_type]
     strain = torch.from_numpy(strain_history_from_F(Fb)).to(device)           # (N+1, comps, B)
     mat = model.material()
-    xi = torch.zeros((n_xi, B), dtype=torch.float64, device=device)
-    xi[7:] = 1.0                                                               # stretches start at 1
+    xi = mp.init_xi(mat, B, device, def_type=dt)                               # stretches start at 1
+    assert xi.shape[0] == n_xi
     sizes = block_sizes(model)
     offs = np.concatenate([[0], np.cumsum(sizes)])
     split = lambda x: [x[:, offs[k]:offs[k + 1]].copy() for k in range(len(sizes))]

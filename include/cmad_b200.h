@@ -40,9 +40,11 @@ enum {
 /* ---- models: cmad/models/small_elastic_plastic.py:95, cmad/models/elastic.py:29 */
 /* CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC (cmad/models/small_rate_elastic_plastic.py): state =
  * [cauchy(6), alpha]; the `strain` rows of a batch carry the strain INCREMENT eps - eps_prev
- * (the reference forms it from U and U_prev); FULL_3D, rotated material axes included: K1, the
+ * (the reference forms it from U and U_prev); rotated material axes included.  FULL_3D: K1, the
  * forward history, K2 adjoint / direct, element blocks of any rule in the displacement and the
- * mixed u-p form (fe_rate.cu).  Not carried: the def-type kernels, the Hessian path, K6. */
+ * mixed u-p form (fe_rate.cu).  PLANE_STRESS / UNIAXIAL_STRESS (cmadx_mp_update only): n_xi = 8 /
+ * 12 = [cauchy(6), alpha, stretches (1 | 2), off-axis delta strains (uniaxial: 3)].
+ * Not carried: histories / objectives of the def-types, the Hessian path, K6. */
 enum { CMADX_MODEL_SMALL_ELASTIC_PLASTIC = 0, CMADX_MODEL_ELASTIC = 1,
        CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC = 2 };
 /* ---- effective stress: cmad/models/effective_stress.py:16-27 */
@@ -166,7 +168,8 @@ typedef struct cmadx_mp_buffers {
                                UNIAXIAL_STRESS: 1 = axial strain                 */
     int32_t def_type;       /* CMADX_DEF_* (cmad/models/deformation_types.py): 0 FULL_3D
                                (n_xi 7), PLANE_STRESS (n_xi 8: + out-of-plane stretch),
-                               UNIAXIAL_STRESS (n_xi 9: + two off-axis stretches).  For the
+                               UNIAXIAL_STRESS (n_xi 9: + two off-axis stretches; 12 for the
+                               rate model: + three off-axis delta strains).  For the
                                latter two the derivative outputs are w.r.t. the prescribed
                                symmetric components only: dsig_deps [6*ns], dxi_deps
                                [n_xi*ns] with ns = 3 (xx, xy, yy) or 1                  */

@@ -385,6 +385,8 @@ class ModelSpec:
             b.append(1)
         elif self.def_type == UNIAXIAL_STRESS:
             b.append(2)
+            if self.kind == "small_rate_elastic_plastic":      # + off-axis delta strains, small_rate_elastic_plastic.py:189-199
+                b.append(3)
         elif self.def_type != FULL_3D:
             raise NotImplementedError
         return b
@@ -400,6 +402,8 @@ class ModelSpec:
         x = np.zeros(sum(b))
         n0 = 6 if self.kind == "elastic" else 7
         x[n0:] = 1.0
+        if self.kind == "small_rate_elastic_plastic" and self.def_type == UNIAXIAL_STRESS:
+            x[n0 + 2:] = 0.0                                   # the off-axis delta strains start at zero
         return x
 
 
@@ -527,12 +531,21 @@ def rate_residual(x, x_prev, params, grad_u, grad_u_prev, spec: ModelSpec):
     """small_rate_elastic_plastic.py:250-346 (FULL_3D): state = [cauchy(6), alpha]; the trial
     stress increment comes from eps(U) - eps(U_prev) (:34-77), the yield function and its
     normal are evaluated at the state's own stress (:80-100)."""
-    assert spec.def_type == FULL_3D
     cauchy = sym_tensor_from_vector(x[0:6])
     cauchy_prev = sym_tensor_from_vector(x_prev[0:6])
     alpha, alpha_prev = x[6], x_prev[6]
     Q = params["rotation matrix"]
-    de = 0.5 * (grad_u + grad_u.T) - 0.5 * (grad_u_prev + grad_u_prev.T)
+    I3 = torch.eye(3, dtype=DT)
+    if spec.def_type == FULL_3D:
+        gu, gup = grad_u, grad_u_prev
+    else:                                                      # :41-51 (the def-types' stretches enter F)
+        gu = _gather_F(x, grad_u, spec, 7) - I3
+        gup = _gather_F(x_prev, grad_u_prev, spec, 7) - I3
+    de = 0.5 * (gu + gu.T) - 0.5 * (gup + gup.T)
+    if spec.def_type == UNIAXIAL_STRESS:                       # :57-70: off-diagonals = the fourth state block
+        d = x[9:12]
+        de = torch.stack([torch.stack([de[0, 0], d[0], d[1]]), torch.stack([d[0], de[1, 1], d[2]]),
+                          torch.stack([d[1], d[2], de[2, 2]])])
     trial = isotropic_linear_elastic_stress(Q.T @ de @ Q, params)
     dgamma = alpha - alpha_prev
     sc = two_mu_scale_factor(params)
@@ -544,6 +557,14 @@ def rate_residual(x, x_prev, params, grad_u, grad_u_prev, spec: ModelSpec):
     Ce = torch.cat([vector_from_sym_tensor(cauchy - cauchy_prev - trial) / sc, dgamma.reshape(1)])
     dc = trial - isotropic_linear_elastic_stress(dgamma * n, params)
     Cp = torch.cat([vector_from_sym_tensor(cauchy - cauchy_prev - dc) / sc, f.reshape(1)])
+    if spec.def_type != FULL_3D:                               # :296-345: constraints on the GLOBAL stress increment
+        gt, gd = Q @ trial @ Q.T, Q @ dc @ Q.T
+        if spec.def_type == PLANE_STRESS:
+            Ce = torch.cat([Ce, (gt[2, 2] / sc).reshape(1)]); Cp = torch.cat([Cp, (gd[2, 2] / sc).reshape(1)])
+        else:
+            assert spec.uniaxial_stress_idx == 0
+            rows = lambda g: torch.stack([g[1, 1], g[2, 2], g[0, 1], g[0, 2], g[1, 2]]) / sc  # noqa: E731
+            Ce = torch.cat([Ce, rows(gt)]); Cp = torch.cat([Cp, rows(gd)])
     return torch.where(sep_is_plastic(f, spec.yield_tol), Cp, Ce)
 
 

@@ -457,11 +457,16 @@ def deftype_F(def_type_name, nsteps=40):
 
 def _deftype_job(job):
     from cmad.models.deformation_types import DefType
-    kind, dt_name = job
+    kind, dt_name = job[:2]
+    rate = len(job) > 2 and job[2] == "rate"
     dt = DefType[dt_name]
     values = material(kind)
     P = parameters(values)
-    model = SmallElasticPlastic(P, def_type=dt)
+    if rate:          # the rate form under the def-types (small_rate_elastic_plastic.py:34-77, 296-345): n_xi 8 / 12
+        from cmad.models.small_rate_elastic_plastic import SmallRateElasticPlastic
+        model = SmallRateElasticPlastic(P, def_type=dt)
+    else:
+        model = SmallElasticPlastic(P, def_type=dt)
     nxi = model.num_dofs
     F = deftype_F(dt_name)
     N = F.shape[2] - 1
@@ -500,6 +505,8 @@ def _deftype_job(job):
         model.advance_xi()
     out = {k: np.array(v) for k, v in rec.items()}
     out["F"] = F
+    if rate:
+        return out
     # objectives (KA5): Calibration on the in-plane / axial stresses, offset parameters
     for scaled in (True, False):
         vals, act, tr = objective_trees(kind, scaled)
@@ -891,6 +898,16 @@ def main():
                 out[f"{nm}.{k}"] = v
             print("barlat rate objective", nm, r["J_adjoint"], r["grad_adjoint"], r["grad_direct"], flush=True)
         np.savez_compressed(os.path.join(HERE, "ref_rate_objectives_barlat.npz"), **out)
+
+    if only is not None and "rate_deftypes" in only:
+        jobs = [(kind, dt, "rate") for dt in ("PLANE_STRESS", "UNIAXIAL_STRESS") for kind in ("J2", "hill_rot", "hosford")]
+        out = {}
+        for (kind, dt, _), r in zip(jobs, pool.map(_deftype_job, jobs, chunksize=1)):
+            for k, v in r.items():
+                out[f"{kind}.{dt}.{k}"] = v
+            print("rate deftypes", kind, dt, "iters", np.bincount(r["iters"]), "traced", np.bincount(r["traced_iters"]),
+                  "alpha", r["xi"][-1, 6], flush=True)
+        np.savez_compressed(os.path.join(HERE, "ref_def_types_rate.npz"), **out)
 
     if only is not None and "rate_rot" in only:
         # SmallRateElasticPlastic with rotated material axes (the case tests/models/
