@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcmad_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
 SOURCES = ["api.cu", "mp_update.cu", "mp_update_stream.cu", "mp_update_queue.cu", "mp_update_cta.cu", "mp_update_j2.cu", "mp_update_dt.cu", "mp_update_rate.cu", "elastic_update.cu", "mp_sens.cu", "mp_sens_dt.cu", "mp_sens_rate.cu", "mp_hess.cu", "mp_history.cu",
-           "fe_block.cu", "fe_tet4.cu", "fe_hex8.cu", "fe_generic.cu", "fe_tet4x4.cu", "fe_rate.cu", "fe_mixed.cu", "fe_post.cu", "fe_vjp.cu", "fe_scatter.cu", "sym3_eigh.cu", "mp_partials.cu", "mp_update_rate_dt.cu"]
+           "fe_block.cu", "fe_tet4.cu", "fe_hex8.cu", "fe_generic.cu", "fe_tet4x4.cu", "fe_rate.cu", "fe_mixed.cu", "fe_post.cu", "fe_vjp.cu", "fe_scatter.cu", "sym3_eigh.cu", "mp_partials.cu", "mp_update_rate_dt.cu", "mp_sens_rate_dt.cu"]
 
 # ---- enums (mirror include/cmad_b200.h) ---------------------------------
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(5)

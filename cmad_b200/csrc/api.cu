@@ -43,6 +43,7 @@ cudaError_t launch_mp_history(const HistArgs& A, bool radial, cudaStream_t s);
 cudaError_t launch_mp_sens(const SensArgs& A, bool adjoint, cudaStream_t stream);
 cudaError_t launch_mp_sens_dt(const SensArgs& A, int def_type, bool adjoint, cudaStream_t stream);
 cudaError_t launch_mp_sens_rate(const SensArgs& A, bool adjoint, cudaStream_t stream);
+cudaError_t launch_mp_sens_rate_dt(const SensArgs& A, int def_type, bool adjoint, cudaStream_t stream);
 cudaError_t launch_fe_rate(const FeArgs& A, const cmadx_fe_mixed_t* mix, cudaStream_t stream);
 int64_t sens_blocks(int64_t n);
 int64_t hess_blocks(int64_t n);
@@ -616,7 +617,11 @@ static int history_def_type(const cmadx_mp_history_t* h) {
     return (h->strain_comps == 6 || h->strain_comps == 9) ? CMADX_DEF_FULL_3D
            : (h->strain_comps == 1 ? CMADX_DEF_UNIAXIAL_STRESS : CMADX_DEF_PLANE_STRESS);
 }
-static int history_n_xi(const cmadx_mp_history_t* h) { return 7 + history_def_type(h); }
+// + the three off-axis delta strains of the rate form under uniaxial stress (n_xi = 12)
+static int history_n_xi(const cmadx_mp_history_t* h, int model) {
+    const int dt = history_def_type(h);
+    return 7 + dt + ((model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC && dt == CMADX_DEF_UNIAXIAL_STRESS) ? 3 : 0);
+}
 
 static int check_history(const cmadx_material_t* mat, const cmadx_mp_history_t* h, DevMat* dm) {
     if (!h) return CMADX_EINVAL;
@@ -626,8 +631,8 @@ static int check_history(const cmadx_material_t* mat, const cmadx_mp_history_t* 
     if (h->n < 0 || h->ld < h->n || h->nsteps < 0) return CMADX_EINVAL;
     const int sc = h->strain_comps;
     if (sc != 6 && sc != 9 && sc != 3 && sc != 4 && sc != 1) return CMADX_EINVAL;
-    // the rate model: FULL_3D (mp_update_rate.cu, mp_sens_rate.cu)
-    if (rate && (sc != 6 && sc != 9)) return CMADX_EUNSUPPORTED;
+    // the rate model under the def-types (mp_update_rate_dt.cu, mp_sens_rate_dt.cu): J2 / Hill / Hosford
+    if (rate && sc != 6 && sc != 9 && dm->yield == CMADX_YIELD_BARLAT) return CMADX_EUNSUPPORTED;
     if (h->n > 0 && (!h->strain || !h->xi_hist)) return CMADX_EINVAL;
     if (h->qoi_kind != CMADX_QOI_CALIBRATION) {
         if (h->qoi_kind != CMADX_QOI_UNIAXIAL_CALIBRATION) return CMADX_EINVAL;
@@ -677,7 +682,7 @@ int cmadx_mp_forward_history(const cmadx_material_t* mat, const cmadx_newton_t* 
     std::memset(&b, 0, sizeof(b));
     b.n = hist->n; b.ld = hist->ld; b.strain_comps = hist->strain_comps;
     b.def_type = history_def_type(hist);
-    const int nxi = history_n_xi(hist);
+    const int nxi = history_n_xi(hist, dm.model);
     for (int t = 1; t <= hist->nsteps; ++t) {
         b.xi_prev = hist->xi_hist + (int64_t)(t - 1) * nxi * hist->ld;
         b.xi = hist->xi_hist + (int64_t)t * nxi * hist->ld;
@@ -710,7 +715,9 @@ static int objective(const cmadx_material_t* mat, const int32_t* active_pid, int
     A.phi_hist = nullptr;
     A.hess_flags = 0;
     const int dt = history_def_type(hist);
-    cudaError_t e = (A.m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC) ? launch_mp_sens_rate(A, adjoint, (cudaStream_t)stream)
+    const bool rate = A.m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC;
+    cudaError_t e = rate ? (dt == CMADX_DEF_FULL_3D ? launch_mp_sens_rate(A, adjoint, (cudaStream_t)stream)
+                                                    : launch_mp_sens_rate_dt(A, dt, adjoint, (cudaStream_t)stream))
                     : (dt == CMADX_DEF_FULL_3D) ? launch_mp_sens(A, adjoint, (cudaStream_t)stream)
                                                 : launch_mp_sens_dt(A, dt, adjoint, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
@@ -750,7 +757,8 @@ int cmadx_mp_objective_host(const cmadx_material_t* mat, const cmadx_newton_t* n
     for (int c = 0; c < ncol; ++c) host->result[c] = 0.0;
     const int64_t n = host->n;
     if (n == 0) return CMADX_OK;
-    const int sc = host->strain_comps, nxi = history_n_xi(host), N1 = host->nsteps + 1;
+    const int sc = host->strain_comps, nxi = history_n_xi(host, dm.model), N1 = host->nsteps + 1;
+    const int nz = history_def_type(host);           // stretch rows (start at 1); the rate form's delta strains start at 0
     int64_t chunk = chunk_points > 0 ? chunk_points : (int64_t)1 << 18;
     if (chunk > n) chunk = n;
     chunk = (chunk + 31) / 32 * 32;
@@ -796,7 +804,7 @@ int cmadx_mp_objective_host(const cmadx_material_t* mat, const cmadx_newton_t* n
         // initial state: zeros, stretches of the def-type variants 1
         e = cudaMemsetAsync(base + o_xi, 0, (size_t)nxi * chunk * 8, s);
         if (e != cudaSuccess) return cuda_fail(e);
-        for (int r = 7; r < nxi; ++r) {
+        for (int r = 7; r < 7 + nz; ++r) {
             e = cudaMemcpyAsync(base + o_xi + (size_t)r * chunk * 8, ones.data(), (size_t)nc * 8, cudaMemcpyHostToDevice, s);
             if (e != cudaSuccess) return cuda_fail(e);
         }

@@ -15,152 +15,15 @@
 // unknowns): rows a < 6 gain -(I + (lam / 2mu) 1 1^T) G, the constraint rows are
 // q_r^T (G - dgamma M [sigma cols] - n [alpha col]) with q_r = S[c_r, :] + (lam / 2mu) tr-part.
 // Same Newton state machine, register LU (N = 8 | 12) and output conventions as the other K1 kernels.
-#include "rate_point.cuh"
-#include "sep_point_dt.cuh"
+#include "rate_point_dt.cuh"
 
 namespace cmadx {
 namespace {
 
 template <int YK, int DT>
-struct RatePointDT {
-    static constexpr int NZ = (DT == CMADX_DEF_PLANE_STRESS) ? 1 : 2;
-    static constexpr int ND = (DT == CMADX_DEF_PLANE_STRESS) ? 0 : 3;
-    static constexpr int NR = NZ + ND;                  // constraint rows
-    static constexpr int N = 7 + NR, ALPHA = 6;
-    RatePoint<YK> b;
-    bool plastic;
-    double T[6][6], S[6][6];
-    double dem[6];                                      // material strain increment of the last evaluation
-
-    // global component moved by unknown 7 + r / constrained by row 7 + r
-    CMADX_DEV static constexpr int ccomp(int r) {
-        return (DT == CMADX_DEF_PLANE_STRESS) ? 5 : (r == 0 ? 3 : (r == 1 ? 5 : (r == 2 ? 1 : (r == 3 ? 2 : 4))));
-    }
-
-    CMADX_DEV void maps(const DevMat& m) {
-        if (m.rot) {
-            rot_maps(m.Q, T, S);
-        } else {
-#pragma unroll
-            for (int a = 0; a < 6; ++a)
-#pragma unroll
-                for (int c = 0; c < 6; ++c) { T[a][c] = (a == c) ? 1.0 : 0.0; S[a][c] = T[a][c]; }
-        }
-    }
-    CMADX_DEV void qrow(const DevMat& m, int r, double (&q)[6]) const {
-        const int c = ccomp(r);
-        const double t = m.lam * m.inv_two_mu * (S[c][0] + S[c][3] + S[c][5]);
-#pragma unroll
-        for (int a = 0; a < 6; ++a) q[a] = S[c][a] + (is_diag(a) ? t : 0.0);
-    }
-
-    CMADX_DEV void residual(const DevMat& m, const double (&x)[N], const double (&xp)[N],
-                            const double (&em)[6], double (&C)[N]) {
-        maps(m);
-        double deg[6];
-        if (DT == CMADX_DEF_PLANE_STRESS) {
-            deg[0] = em[0]; deg[1] = em[1]; deg[2] = 0.0; deg[3] = em[3]; deg[4] = 0.0; deg[5] = x[7] - xp[7];
-        } else {
-            deg[0] = em[0]; deg[1] = x[9]; deg[2] = x[10]; deg[3] = x[7] - xp[7]; deg[4] = x[11]; deg[5] = x[8] - xp[8];
-        }
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            double s = 0.0;
-#pragma unroll
-            for (int c = 0; c < 6; ++c) s = fma(T[a][c], deg[c], s);
-            dem[a] = s;
-        }
-        double x7[7], xp7[7], C7[7];
-#pragma unroll
-        for (int c = 0; c < 7; ++c) { x7[c] = x[c]; xp7[c] = xp[c]; }
-        b.residual(m, x7, xp7, dem, C7);
-        plastic = b.plastic;
-#pragma unroll
-        for (int c = 0; c < 7; ++c) C[c] = C7[c];
-        const double dg = x[6] - xp[6];
-        double w[6];
-#pragma unroll
-        for (int a = 0; a < 6; ++a) w[a] = plastic ? fma(-dg, b.n[a], dem[a]) : dem[a];
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            double q[6], s = 0.0;
-            qrow(m, r, q);
-#pragma unroll
-            for (int a = 0; a < 6; ++a) s = fma(q[a], w[a], s);
-            C[7 + r] = s;
-        }
-    }
-
-    CMADX_DEV void jacobian(const DevMat& m, double dg, double (&J)[N][N]) const {
-        double J7[7][7];
-        b.jacobian(m, dg, J7);
-        const double lr = m.lam * m.inv_two_mu;
-#pragma unroll
-        for (int a = 0; a < 7; ++a) {
-#pragma unroll
-            for (int c = 0; c < 7; ++c) J[a][c] = J7[a][c];
-#pragma unroll
-            for (int r = 0; r < NR; ++r) {
-                // d C_a / d dem_b = -(delta_ab + lr [a diag][b diag]) on the stress rows, 0 on the yield row
-                double v = 0.0;
-                if (a < 6) {
-                    const int g = ccomp(r);
-                    v = -T[a][g];
-                    if (is_diag(a)) v -= lr * (T[0][g] + T[3][g] + T[5][g]);
-                }
-                J[a][7 + r] = v;
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            double q[6];
-            qrow(m, r, q);
-#pragma unroll
-            for (int c = 0; c < 6; ++c) {
-                double v = 0.0;
-                if (plastic) {
-#pragma unroll
-                    for (int a = 0; a < 6; ++a) v = fma(q[a], b.yf.M(a, c), v);
-                    v *= -dg;
-                }
-                J[7 + r][c] = v;
-            }
-            double qn = 0.0;
-#pragma unroll
-            for (int a = 0; a < 6; ++a) qn = fma(q[a], b.n[a], qn);
-            J[7 + r][6] = plastic ? -qn : 0.0;
-#pragma unroll
-            for (int r2 = 0; r2 < NR; ++r2) {
-                double v = 0.0;
-#pragma unroll
-                for (int a = 0; a < 6; ++a) v = fma(q[a], T[a][ccomp(r2)], v);
-                J[7 + r][7 + r2] = v;
-            }
-        }
-    }
-
-    // dC / d(prescribed increment component bc)
-    CMADX_DEV void dC_deps(const DevMat& m, int bc, double (&col)[N]) const {
-        const double lr = m.lam * m.inv_two_mu;
-        const double tr = T[0][bc] + T[3][bc] + T[5][bc];
-#pragma unroll
-        for (int a = 0; a < 6; ++a) col[a] = -T[a][bc] - (is_diag(a) ? lr * tr : 0.0);
-        col[6] = 0.0;
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            double q[6], v = 0.0;
-            qrow(m, r, q);
-#pragma unroll
-            for (int a = 0; a < 6; ++a) v = fma(q[a], T[a][bc], v);
-            col[7 + r] = v;
-        }
-    }
-};
-
-template <int YK, int DT>
 __global__ void __launch_bounds__(MP_BLOCK) mp_update_rate_dt_kernel(const __grid_constant__ MpArgs A) {
     using Pt = RatePointDT<YK, DT>;
-    constexpr int N = Pt::N, NZ = Pt::NZ, NR = Pt::NR;
+    constexpr int N = Pt::N, NZ = Pt::NZ;
     constexpr int NS = (DT == CMADX_DEF_PLANE_STRESS) ? 3 : 1;
     const int scomp[3] = {0, (DT == CMADX_DEF_PLANE_STRESS) ? 1 : 0, 3};
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -232,57 +95,18 @@ __global__ void __launch_bounds__(MP_BLOCK) mp_update_rate_dt_kernel(const __gri
             for (int c = 0; c < N; ++c) st(A.b.dC_dxi, r * N + c, ld, i, lu.a[r][c]);
     }
     if (A.b.dC_dxi_prev) {
-        // sigma_prev / alpha_prev as in the FULL_3D form; the stretches enter as z - z_prev (the columns
-        // are minus the current ones), the delta strains have no previous value
 #pragma unroll
         for (int r = 0; r < N; ++r)
 #pragma unroll
-            for (int c = 0; c < N; ++c) {
-                double v = 0.0;
-                if (c < 6) v = (r == c) ? -m.inv_two_mu : 0.0;
-                else if (c == 6) v = (r < 6) ? (pl ? -pt.b.n[r] : 0.0) : (r == 6 ? (pl ? 0.0 : -1.0) : -lu.a[r][6]);
-                else if (c < 7 + NZ) v = -lu.a[r][c];
-                st(A.b.dC_dxi_prev, r * N + c, ld, i, v);
-            }
+            for (int c = 0; c < N; ++c) st(A.b.dC_dxi_prev, r * N + c, ld, i, rate_dt_B(m, pt, lu.a, r, c));
     }
     if (A.b.dC_dp && A.n_active > 0) {
         const int na = A.n_active;
-        double x7[7], xp7[7], w[6];
-#pragma unroll
-        for (int c = 0; c < 7; ++c) { x7[c] = x[c]; xp7[c] = xp[c]; }
-        double trw = 0.0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) { w[a] = pl ? fma(-dg, pt.b.n[a], pt.dem[a]) : pt.dem[a]; if (is_diag(a)) trw += w[a]; }
         for (int c = 0; c < na; ++c) {
-            const int pid = A.pid[c];
-            double col[7];
-            rate_dC_dp_column<YK>(m, pid, pt.b, x7, xp7, pt.dem, col);
+            double col[N];
+            rate_dt_dC_dp_column<YK, DT>(m, A.pid[c], pt, x, xp, col);
 #pragma unroll
-            for (int r = 0; r < 7; ++r) st(A.b.dC_dp, (int64_t)r * na + c, ld, i, col[r]);
-            // constraint rows: the elastic constants through lam / 2mu, the yield-surface leaves through n
-            double dlr = 0.0, dn[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            bool has_dn = false;
-            if (pid == CMADX_P_EL0 || pid == CMADX_P_EL1) {
-                const int k = pid - CMADX_P_EL0;
-                dlr = (m.dlam[k] * m.two_mu - m.lam * 2.0 * m.dmu[k]) * m.inv_two_mu * m.inv_two_mu;
-            } else if (pl && pid > CMADX_P_LIN_K) {
-                double sig[6], dphi;
-#pragma unroll
-                for (int a = 0; a < 6; ++a) sig[a] = x[a];
-                has_dn = pt.b.yf.dparam(m, pid, sig, dphi, dn);
-            }
-#pragma unroll
-            for (int r = 0; r < NR; ++r) {
-                const int g = Pt::ccomp(r);
-                double v = dlr * trw * (pt.S[g][0] + pt.S[g][3] + pt.S[g][5]);
-                if (has_dn) {
-                    double q[6];
-                    pt.qrow(m, r, q);
-#pragma unroll
-                    for (int a = 0; a < 6; ++a) v = fma(-dg * q[a], dn[a], v);
-                }
-                st(A.b.dC_dp, (int64_t)(7 + r) * na + c, ld, i, v);
-            }
+            for (int r = 0; r < N; ++r) st(A.b.dC_dp, (int64_t)r * na + c, ld, i, col[r]);
         }
     }
     if (!A.b.dsig_deps && !A.b.dxi_deps) return;

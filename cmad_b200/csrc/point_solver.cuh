@@ -342,8 +342,11 @@ namespace cmadx {
 // --------------------------------------------------------------------------
 // partial-pivoting LU of an n x n matrix in (local) memory; returns the swap bits in
 // the order RegLU::solve_pivot replays them; a[k][k] holds 1/pivot afterwards
-static __device__ __noinline__ unsigned long long lu_factor_pivot_mem(double* a, int n) {
+// (n <= 11: 55 decisions fit one word; n = 12 - the rate form under uniaxial stress - has 66: the
+// decisions past bit 63 go to *hi)
+static __device__ __noinline__ unsigned long long lu_factor_pivot_mem(double* a, int n, unsigned long long* hi = nullptr) {
     unsigned long long swaps = 0ull;
+    if (hi) *hi = 0ull;
     int bit = 0;
     for (int k = 0; k < n; ++k) {
         for (int i = k + 1; i < n; ++i) {
@@ -355,7 +358,8 @@ static __device__ __noinline__ unsigned long long lu_factor_pivot_mem(double* a,
                     a[i * n + j] = u;
                 }
             }
-            swaps |= (sw ? 1ull : 0ull) << bit;
+            if (bit < 64) swaps |= (sw ? 1ull : 0ull) << bit;
+            else if (hi) *hi |= (sw ? 1ull : 0ull) << (bit - 64);
             ++bit;
         }
         const double rp = 1.0 / a[k * n + k];
@@ -373,6 +377,8 @@ template <int N>
 struct RegLU {
     double a[N][N];
     unsigned long long swaps;   // N (N - 1) / 2 row-exchange decisions (36 for N = 9)
+    unsigned long long swaps_hi;   // decisions 64.. (N = 12: 66 in all); unused for N <= 11
+    static_assert(N * (N - 1) / 2 <= 128, "RegLU: swap record holds 128 decisions");
 
     // natural-order elimination; returns true when this lane needs pivoting
     CMADX_DEV bool factor_natural() {
@@ -419,7 +425,8 @@ struct RegLU {
         for (int i = 0; i < N; ++i)
 #pragma unroll
             for (int j = 0; j < N; ++j) t[i * N + j] = a[i][j];
-        swaps = lu_factor_pivot_mem(t, N);
+        swaps_hi = 0ull;
+        swaps = (N * (N - 1) / 2 > 64) ? lu_factor_pivot_mem(t, N, &swaps_hi) : lu_factor_pivot_mem(t, N);
 #pragma unroll
         for (int i = 0; i < N; ++i)
 #pragma unroll
@@ -431,7 +438,7 @@ struct RegLU {
         for (int k = 0; k < N; ++k) {
 #pragma unroll
             for (int i = k + 1; i < N; ++i) {
-                const bool sw = (swaps >> bit) & 1ull;
+                const bool sw = (bit < 64) ? ((swaps >> bit) & 1ull) : ((swaps_hi >> (bit - 64)) & 1ull);
                 const double u = b[k], v = b[i];
                 b[k] = sw ? v : u;
                 b[i] = sw ? u : v;

@@ -166,12 +166,14 @@ def uniaxial_data_history(data: np.ndarray) -> np.ndarray:
 class _DeviceHistories:
     """Device-resident histories of this rank's shard."""
 
-    def __init__(self, strain_hist: np.ndarray, data_hist: np.ndarray, device: torch.device):
+    def __init__(self, strain_hist: np.ndarray, data_hist: np.ndarray, device: torch.device, n_xi: int | None = None):
         self.N = strain_hist.shape[0] - 1
         self.n = strain_hist.shape[2]
         self.strain = torch.from_numpy(np.ascontiguousarray(strain_hist)).to(device)
         self.data = torch.from_numpy(np.ascontiguousarray(data_hist)).to(device)
-        self.n_xi = {9: 7, 6: 7, 4: 8, 3: 8, 1: 9}[strain_hist.shape[1]]
+        self.n_stretch = {9: 0, 6: 0, 4: 1, 3: 1, 1: 2}[strain_hist.shape[1]]
+        # (the rate form under uniaxial stress: 12 = 9 + three off-axis delta strains)
+        self.n_xi = n_xi if n_xi is not None else 7 + self.n_stretch
         self.xi = torch.zeros((self.N + 1, self.n_xi, self.n), dtype=torch.float64, device=device)
         self.iters = torch.zeros((self.N + 1, self.n), dtype=torch.int32, device=device)
         self.J_point = torch.zeros((self.n,), dtype=torch.float64, device=device)
@@ -188,7 +190,7 @@ def gpu_local_evaluator(model: SmallElasticPlastic, strain_hist: np.ndarray, dat
     nd = _NDIMS[getattr(model, "_def_type", FULL_3D)]
     if strain_hist.shape[1] not in ((6, 9) if nd == 3 else (nd * nd, 3) if nd == 2 else (1,)):
         raise ValueError(f"strain history with {strain_hist.shape[1]} rows does not fit the model's def_type")
-    hist = _DeviceHistories(strain_hist, data_hist, device)
+    hist = _DeviceHistories(strain_hist, data_hist, device, getattr(model, "num_dofs", None))
     newton = newton or NewtonSettings(mode="imperative", max_iters=10, abs_tol=1e-14, rel_tol=1e-14)
     adjoint = {"adjoint": True, "direct": False, "direct_adjoint": True}[strategy]
     hessian = strategy == "direct_adjoint"
@@ -226,7 +228,7 @@ def gpu_local_evaluator(model: SmallElasticPlastic, strain_hist: np.ndarray, dat
             h.qoi_kind, h.weight_steps = L.QOI_UNIAXIAL_CALIBRATION, w_steps.data_ptr()
         stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         hist.xi[0].zero_()
-        hist.xi[0, 7:] = 1.0                               # stretches of the def-type variants start at 1
+        hist.xi[0, 7:7 + hist.n_stretch] = 1.0             # stretches of the def-type variants start at 1
         with torch.cuda.device(device):
             L.check(lib.cmadx_mp_forward_history(C.byref(mat), C.byref(nw), C.byref(h), stream),
                     "cmadx_mp_forward_history")

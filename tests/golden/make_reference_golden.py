@@ -505,13 +505,11 @@ def _deftype_job(job):
         model.advance_xi()
     out = {k: np.array(v) for k, v in rec.items()}
     out["F"] = F
-    if rate:
-        return out
     # objectives (KA5): Calibration on the in-plane / axial stresses, offset parameters
     for scaled in (True, False):
         vals, act, tr = objective_trees(kind, scaled)
         Po = Parameters(vals, act, tr)
-        mo_ = SmallElasticPlastic(Po, def_type=dt)
+        mo_ = SmallRateElasticPlastic(Po, def_type=dt) if rate else SmallElasticPlastic(Po, def_type=dt)
         data = np.zeros((3, 3, N + 1))
         mo_.set_xi_to_init_vals()
         for step in range(1, N + 1):

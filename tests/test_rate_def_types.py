@@ -111,8 +111,7 @@ def test_cuda_rate_def_type_batch(cuda_device):
 @pytest.mark.parametrize("case", ["J2.UNIAXIAL_STRESS", "hill_rot.PLANE_STRESS"])
 def test_cuda_primal_loop_rate_def_types(cuda_device, case):
     """`cmad primal` on the rate form under a def-type: the Python stand-in + run_primal_pass reproduce
-    the reference's trajectory (block layout [6, 1, 1] / [6, 1, 2, 3]); the calibration objectives of
-    this combination are refused, not approximated."""
+    the reference's trajectory (block layout [6, 1, 1] / [6, 1, 2, 3])."""
     from cmad_b200 import objectives as ob
     from cmad_b200.primal import block_sizes, run_primal_pass
     kind, dtn = case.split(".")
@@ -128,6 +127,48 @@ def test_cuda_primal_loop_rate_def_types(cuda_device, case):
     assert rel_err(xi_end, RD[f"{case}.xi"][-1]) < 1e-9
     sig = np.array([cauchy[i, j, -1] for i, j in UP])
     assert rel_err(sig, RD[f"{case}.sigma"][-1]) < 1e-9
-    data = np.zeros((3, 3, N + 1)); w = np.zeros((3, 3)); w[0, 0] = 1.0
-    with pytest.raises(NotImplementedError):
-        ob.MPAdjointObjective(ob.Calibration(model, data, w), F, device=cuda_device).evaluate(np.zeros(0))
+
+
+def test_reference_adjoint_equals_direct():
+    for case in CASES:
+        for tag in ("scaled", "native"):
+            a, d = RD[f"{case}.obj_{tag}.grad_adjoint"], RD[f"{case}.obj_{tag}.grad_direct"]
+            assert rel_err(a, d) < 1e-9, (case, tag)
+
+
+@pytest.mark.parametrize("case", ["J2.PLANE_STRESS", "hill_rot.UNIAXIAL_STRESS"])
+def test_torch_oracle_rate_def_type_objective_vs_reference(case):
+    from oracle import cmad_oracle as co
+    from tests.golden.materials import objective_trees
+    kind, dtn = case.split(".")
+    pre = f"{case}.obj_native"
+    values, act, tr = objective_trees(kind, False)
+    P = co.OracleParameters(values, act, tr)
+    spec = co.ModelSpec(kind="small_rate_elastic_plastic", def_type=getattr(co, dtn))
+    J, g = co.mp_objective_adjoint(P, RD[f"{case}.F"], RD[f"{pre}.data"], RD[f"{pre}.weight"], spec,
+                                   RD[f"{pre}.x_canonical"], True)
+    assert abs(J - RD[f"{pre}.J_adjoint"]) < 1e-10 * abs(J)
+    assert rel_err(np.asarray(g), RD[f"{pre}.grad_adjoint"]) < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("tag", ["scaled", "native"])
+def test_cuda_objectives_vs_reference_rate_def_types(cuda_device, case, tag):
+    """The KA5 setting on the rate form (tests/objectives/test_J2_fd_checks.py runs its plane-stress
+    gradient checks on both small-strain models): forward history (K1 per step, increments formed on
+    the device) + K2 adjoint / direct on the bordered systems, reference constructor signatures."""
+    from cmad_b200 import objectives as ob
+    from tests.golden.materials import objective_trees
+    kind, dtn = case.split(".")
+    F = RD[f"{case}.F"]
+    pre = f"{case}.obj_{tag}"
+    for strategy, ctor in (("adjoint", ob.MPAdjointObjective), ("direct", ob.MPDirectObjective)):
+        values, act, tr = objective_trees(kind, tag == "scaled")
+        P = Parameters(values, act, tr)
+        assert np.array_equal(P.active_idx, RD[f"{pre}.active_idx"])
+        model = ob.SmallRateElasticPlastic(P, def_type=getattr(ob, dtn))
+        obj = ctor(ob.Calibration(model, RD[f"{pre}.data"], RD[f"{pre}.weight"]), F, device=cuda_device)
+        r = obj.evaluate(RD[f"{pre}.x_canonical"])
+        assert abs(r.J - RD[f"{pre}.J_{strategy}"]) < 1e-10 * abs(r.J), (case, tag, strategy)
+        assert rel_err(r.grad, RD[f"{pre}.grad_{strategy}"]) < 1e-8, (case, tag, strategy, r.grad)
