@@ -853,10 +853,12 @@ int cmadx_mp_objective_hessian(const cmadx_material_t* mat, const int32_t* activ
     if (flags & ~CMADX_HESS_F_REFERENCE_QOI_CROSS) return CMADX_EINVAL;
     A.hess_flags = flags;
     if (int rc = check_history(mat, hist, &A.m)) return rc;
-    if (A.m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC || hist->qoi_kind != CMADX_QOI_CALIBRATION ||
+    const bool rate = A.m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC;
+    if ((A.m.model != CMADX_MODEL_SMALL_ELASTIC_PLASTIC && !rate) || hist->qoi_kind != CMADX_QOI_CALIBRATION ||
         A.m.yield == CMADX_YIELD_BARLAT)
         return CMADX_EUNSUPPORTED;
     const int dt = history_def_type(hist);
+    if (rate && dt != CMADX_DEF_FULL_3D) return CMADX_EUNSUPPORTED;         // the rate form: FULL_3D (mp_hess_rate_kernel)
     if (dt != CMADX_DEF_FULL_3D && A.m.rot) return CMADX_EUNSUPPORTED;      // rotated axes: FULL_3D only in this pass
     if (n_active < 0 || n_active > CMADX_MAX_ACTIVE || (n_active > 0 && !active_pid)) return CMADX_EINVAL;
     if (!hist->result || !hist->workspace || (hist->n > 0 && !hist->data)) return CMADX_EINVAL;
@@ -873,7 +875,8 @@ int cmadx_mp_objective_hessian(const cmadx_material_t* mat, const int32_t* activ
     double* pair_sums = A.partials + hess_partials_doubles(hist->n, n_active);
     cudaStream_t s = (cudaStream_t)stream;
     // J, dJ/dp, and phi_t for every step
-    cudaError_t e = (dt == CMADX_DEF_FULL_3D) ? launch_mp_sens(A, true, s) : launch_mp_sens_dt(A, dt, true, s);
+    cudaError_t e = rate ? launch_mp_sens_rate(A, true, s)
+                    : (dt == CMADX_DEF_FULL_3D) ? launch_mp_sens(A, true, s) : launch_mp_sens_dt(A, dt, true, s);
     if (e != cudaSuccess) return cuda_fail(e);
     e = launch_mp_hess(A, dt, pair_sums, hist->result + 1 + n_active, s);
     if (e != cudaSuccess) return cuda_fail(e);

@@ -24,6 +24,7 @@
 #include "mp_outputs.cuh"
 #include "mp_sens.cuh"
 #include "sep_point_dt.cuh"
+#include "rate_point.cuh"
 
 namespace cmadx {
 cudaError_t launch_reduce_partials(const double* partials, int64_t nblk, int ncols, double* result,
@@ -433,6 +434,209 @@ __global__ void __launch_bounds__(HESS_BLOCK) mp_hess_kernel(const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------
+// SmallRateElasticPlastic, FULL_3D (cmad/models/small_rate_elastic_plastic.py:250-346): state
+// x = [cauchy(6), alpha] in material axes, de = T (eps_t - eps_{t-1}); the QoI reads the state's own
+// stress (S x for rotated axes), so J_t has no parameter dependence and the reference's Hessian
+// (qoi.py:53-55) is complete for this model.  Same scheme as mp_hess_kernel: X_t from the K2 direct
+// recurrence of mp_sens_rate.cu, one hyper-dual evaluation of J_t + phi_t . C per pair.
+template <int YK>
+__device__ __forceinline__ double lagrangian_mixed_rate(const DevMat& m, const HessParams& P, const HD (&x)[7],
+                                                     const HD (&xp)[7], const double (&de)[6],
+                                                     const double (&phi)[7], const double (&w)[9],
+                                                     const double (&d)[9], bool plastic, const double* S) {
+    HD sig[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) sig[a] = x[a];
+    HD L;
+    {
+        HD sg[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) sg[a] = sig[a];
+        to_global_hd(S, sg);
+        L = qoi_hd(sg, w, d);
+    }
+    const HD two_mu = 2.0 * P.mu;
+    const HD i2mu = inv(two_mu);
+    const HD dg = x[6] - xp[6];
+    HD wv[6];                        // the strain the elastic operator acts on: de (- dgamma n)
+#pragma unroll
+    for (int a = 0; a < 6; ++a) wv[a] = hd(de[a]);
+    if (plastic) {
+        HD pe, n[6];
+        yield_hd<YK>(m, P, sig, pe, n);
+        HD hard = P.Y;
+        if (m.hmask & CMADX_HARD_VOCE) hard = hard + P.S * (1.0 - hexp(-(P.D * x[6])));
+        if (m.hmask & CMADX_HARD_LINEAR) hard = hard + P.K * x[6];
+        L = L + phi[6] * ((pe - hard) * i2mu);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) wv[a] = wv[a] - dg * n[a];
+    } else {
+        L = L + phi[6] * dg;
+    }
+    const HD ltr = P.lam * (wv[0] + wv[3] + wv[5]);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        const HD inc = is_diag(a) ? two_mu * wv[a] + ltr : two_mu * wv[a];
+        L = L + phi[a] * ((x[a] - xp[a] - inc) * i2mu);
+    }
+    return L.ab;
+}
+
+template <int YK>
+__global__ void __launch_bounds__(HESS_BLOCK) mp_hess_rate_kernel(const __grid_constant__ SensArgs A) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < A.h.n;
+    const int64_t ld = A.h.ld;
+    const DevMat& m = A.m;
+    const int N = A.h.nsteps, na = A.n_active, sc = A.h.strain_comps;
+    const int npairs = na * (na + 1) / 2;
+    extern __shared__ double hs[];
+    constexpr int NX = 7;
+    auto X = [&](int c, int r) -> double& { return hs[(c * NX + r) * HESS_BLOCK + threadIdx.x]; };
+    auto Xp = [&](int c, int r) -> double& { return hs[((na + c) * NX + r) * HESS_BLOCK + threadIdx.x]; };
+    auto Hacc = [&](int q) -> double& { return hs[(2 * na * NX + q) * HESS_BLOCK + threadIdx.x]; };
+    for (int q = 0; q < npairs; ++q) Hacc(q) = 0.0;
+    for (int c = 0; c < na; ++c)
+#pragma unroll
+        for (int r = 0; r < 7; ++r) { X(c, r) = 0.0; Xp(c, r) = 0.0; }
+    double Trot[36], Srot[36];
+    const double* Sq = nullptr;
+    if (m.rot) {
+        const int ci_[6] = {0, 0, 0, 1, 1, 2}, cj_[6] = {0, 1, 2, 1, 2, 2};
+        for (int c = 0; c < 6; ++c)
+            for (int b = 0; b < 6; ++b) {
+                const int ii = ci_[c], jj = cj_[c], kk = ci_[b], ll = cj_[b];
+                double tt = m.Q[3 * kk + ii] * m.Q[3 * ll + jj];
+                double ss = m.Q[3 * ii + kk] * m.Q[3 * jj + ll];
+                if (kk != ll) { tt += m.Q[3 * ll + ii] * m.Q[3 * kk + jj]; ss += m.Q[3 * ii + ll] * m.Q[3 * jj + kk]; }
+                Trot[c * 6 + b] = tt;
+                Srot[c * 6 + b] = ss;
+            }
+        Sq = Srot;
+    }
+    double x[7], xp[7], ep[6];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+        const double v = live ? __ldg(A.h.xi_hist + c * ld + i) : 0.0;
+        x[c] = v; xp[c] = v;
+    }
+    if (live) rate_load_strain(A.h.strain, sc, ld, i, ep);
+    else {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) ep[c] = 0.0;
+    }
+    for (int t = 1; t <= N; ++t) {
+        double de[6], et[6], d[9], phi[7];
+        if (live) {
+            const double* xs = A.h.xi_hist + (int64_t)t * 7 * ld + i;
+            const double* ph = A.phi_hist + (int64_t)t * 7 * ld + i;
+#pragma unroll
+            for (int c = 0; c < 7; ++c) { x[c] = __ldg(xs + c * ld); phi[c] = ph[c * ld]; }
+            rate_load_strain(A.h.strain + (int64_t)t * sc * ld, sc, ld, i, et);
+            const double* ds = A.h.data + (int64_t)t * 9 * ld + i;
+#pragma unroll
+            for (int c = 0; c < 9; ++c) d[c] = __ldg(ds + c * ld);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 7; ++c) { x[c] = (c == 0) ? 1.0 : 0.0; phi[c] = 0.0; }
+#pragma unroll
+            for (int c = 0; c < 6; ++c) et[c] = ep[c] + 1e-3 * (c == 0);
+#pragma unroll
+            for (int c = 0; c < 9; ++c) d[c] = 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { de[c] = et[c] - ep[c]; ep[c] = et[c]; }
+        if (m.rot) {
+            double dgl[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) dgl[c] = de[c];
+            for (int c = 0; c < 6; ++c) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int b = 0; b < 6; ++b) sacc = fma(Trot[c * 6 + b], dgl[b], sacc);
+                de[c] = sacc;
+            }
+        }
+        // ---- forward sensitivities X_t = A^{-1}(-dC/dp - B X_{t-1}),  B = [-I/2mu, -n; 0, -1]
+        RatePoint<YK> pt;
+        double C[7];
+        pt.residual(m, x, xp, de, C);
+        const bool pl = pt.plastic;
+        const double dg = x[6] - xp[6];
+        RegLU<7> lu;
+        pt.jacobian(m, dg, lu.a);
+        const bool trouble = lu.factor_natural();
+        const bool slow = __any_sync(__activemask(), trouble);
+        if (slow && trouble) {
+            pt.jacobian(m, dg, lu.a);
+            lu.factor_pivot();
+        }
+        for (int c = 0; c < na; ++c) {
+            double col[7], rhs[7];
+            rate_dC_dp_column<YK>(m, A.pid[c], pt, x, xp, de, col);
+            const double x6 = Xp(c, 6);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) rhs[q] = -col[q] + m.inv_two_mu * Xp(c, q) + (pl ? pt.n[q] * x6 : 0.0);
+            rhs[6] = -col[6] + (pl ? 0.0 : x6);
+            if (slow && trouble) lu.solve_pivot(rhs); else lu.solve_natural(rhs);
+#pragma unroll
+            for (int q = 0; q < 7; ++q) X(c, q) = rhs[q];
+        }
+        // ---- H_ij += D2 L_t [Z_i, Z_j]
+        int q = 0;
+#pragma unroll 1
+        for (int ci = 0; ci < na; ++ci) {
+#pragma unroll 1
+            for (int cj = ci; cj < na; ++cj, ++q) {
+                const int pi = A.pid[ci], pj = A.pid[cj];
+                HessParams P;
+                {
+                    const int ki = pi - CMADX_P_EL0, kj = pj - CMADX_P_EL0;
+                    const bool ei = (ki == 0 || ki == 1), ej = (kj == 0 || kj == 1);
+                    const int k2 = ki + kj;
+                    P.lam = {m.lam, ei ? m.dlam[ki] : 0.0, ej ? m.dlam[kj] : 0.0, (ei && ej) ? m.d2lam[k2] : 0.0};
+                    P.mu = {m.mu, ei ? m.dmu[ki] : 0.0, ej ? m.dmu[kj] : 0.0, (ei && ej) ? m.d2mu[k2] : 0.0};
+                }
+                P.Y = seed(m.Y, CMADX_P_Y, pi, pj);
+                P.S = seed(m.S, CMADX_P_VOCE_S, pi, pj);
+                P.D = seed(m.D, CMADX_P_VOCE_D, pi, pj);
+                P.K = seed(m.K, CMADX_P_LIN_K, pi, pj);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) P.hill[k] = seed(m.hill[k], CMADX_P_HILL_F + k, pi, pj);
+                HD xh[7], xph[7];
+#pragma unroll
+                for (int r = 0; r < 7; ++r) {
+                    xh[r] = {x[r], X(ci, r), X(cj, r), 0.0};
+                    xph[r] = {xp[r], Xp(ci, r), Xp(cj, r), 0.0};
+                }
+                Hacc(q) += lagrangian_mixed_rate<YK>(m, P, xh, xph, de, phi, A.h.weight, d, pl, Sq);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 7; ++c) xp[c] = x[c];
+        for (int c = 0; c < na; ++c)
+#pragma unroll
+            for (int r = 0; r < 7; ++r) Xp(c, r) = X(c, r);
+    }
+    __shared__ double sm[HESS_BLOCK / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = 0; q < npairs; ++q) {
+        double v = live ? Hacc(q) : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) sm[warp] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+#pragma unroll
+            for (int wq = 0; wq < HESS_BLOCK / 32; ++wq) s += sm[wq];
+            A.partials[(int64_t)blockIdx.x * npairs + q] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // PLANE_STRESS / UNIAXIAL_STRESS (n_xi = 8 / 9): the reference's Hessian known answer (KA5,
 // tests/objectives/test_jvp_vs_original.py:75-97) lives in plane stress.  Same scheme; the
 // bordered residual (sep_point_dt.cuh: stretch unknowns, stress-constraint rows cauchy_cc/2mu)
@@ -696,6 +900,13 @@ cudaError_t launch_mp_hess(const SensArgs& A, int def_type, double* pair_sums, d
         e = launch_hess_dt<CMADX_DEF_PLANE_STRESS>(A, (unsigned)nblk, stream);
     } else if (def_type == CMADX_DEF_UNIAXIAL_STRESS) {
         e = launch_hess_dt<CMADX_DEF_UNIAXIAL_STRESS>(A, (unsigned)nblk, stream);
+    } else if (A.m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC) {
+        switch (A.m.yield) {
+        case CMADX_YIELD_J2: e = launch_hess_kernel(mp_hess_rate_kernel<CMADX_YIELD_J2>, A, 7, (unsigned)nblk, stream); break;
+        case CMADX_YIELD_HILL: e = launch_hess_kernel(mp_hess_rate_kernel<CMADX_YIELD_HILL>, A, 7, (unsigned)nblk, stream); break;
+        case CMADX_YIELD_HOSFORD: e = launch_hess_kernel(mp_hess_rate_kernel<CMADX_YIELD_HOSFORD>, A, 7, (unsigned)nblk, stream); break;
+        default: return cudaErrorInvalidValue;
+        }
     } else {
         switch (A.m.yield) {
         case CMADX_YIELD_J2: e = launch_hess_kernel(mp_hess_kernel<CMADX_YIELD_J2>, A, 7, (unsigned)nblk, stream); break;

@@ -136,6 +136,11 @@ __global__ void __launch_bounds__(SENS_BLOCK) mp_sens_rate_kernel(const __grid_c
             for (int c = 0; c < 6; ++c) phi[c] = hist[c] - r[c];
             phi[6] = hist[6];
             solve7(phi);
+            if (A.phi_hist && live) {      // kept for the direct-adjoint Hessian pass (mp_hess.cu)
+                double* ph = A.phi_hist + (int64_t)t * 7 * ld + i;
+#pragma unroll
+                for (int c = 0; c < 7; ++c) ph[c * ld] = phi[c];
+            }
             // h <- -B^T phi
             double nphi = 0.0;
 #pragma unroll

@@ -285,9 +285,12 @@ def _hessian_job(job):
     kind, scaled, F, weight = job[:4]
     dt_name = job[4] if len(job) > 4 else "FULL_3D"
     from cmad.models.deformation_types import DefType
+    Model_ = SmallElasticPlastic
+    if len(job) > 5 and job[5] == "rate":       # the rate form (small_rate_elastic_plastic.py)
+        from cmad.models.small_rate_elastic_plastic import SmallRateElasticPlastic as Model_
     values, act, tr = objective_trees(kind, scaled)
     P = Parameters(values, act, tr)
-    model = SmallElasticPlastic(P, def_type=DefType[dt_name])
+    model = Model_(P, def_type=DefType[dt_name])
     N = F.shape[2] - 1
     data = np.zeros((3, 3, N + 1))
     model.set_xi_to_init_vals()
@@ -302,7 +305,7 @@ def _hessian_job(job):
     # a FRESH parameters / model pair for the objective, as a run that reads its data from file
     # has (the data-generation model above is not reused)
     P = Parameters(*objective_trees(kind, scaled))
-    model = SmallElasticPlastic(P, def_type=DefType[dt_name])
+    model = Model_(P, def_type=DefType[dt_name])
     qoi = Calibration(model, data, weight)
     P.set_active_values_from_flat(offset, False)
     x = P.flat_active_values(True)
@@ -728,6 +731,22 @@ def main():
                 out[f"{nm}.{k}"] = v
             print("hessian_rot", nm, r["J"], r["grad"], np.linalg.eigvalsh(r["hessian"]))
         np.savez_compressed(os.path.join(HERE, "ref_mp_hessian_rot.npz"), **out)
+
+    if only is None or "hessian_rate" in only:
+        # the direct-adjoint Hessian of the rate form (FULL_3D; identity and rotated material axes)
+        w = np.array([[1.0, 0.5, 0.0], [0.5, 1.0, 0.0], [0.0, 0.0, 0.25]])
+        jobs, names = [], []
+        for kind in ("J2", "hill", "hosford", "hill_rot"):
+            for scaled in (True, False):
+                jobs.append((kind, scaled, two_leg_F(11, 10, scale=1.5, diag_only=kind == "hosford"), w,
+                             "FULL_3D", "rate"))
+                names.append(f"{kind}.{'scaled' if scaled else 'native'}")
+        out = {}
+        for nm, r in zip(names, pool.map(_hessian_job, jobs, chunksize=1)):
+            for k, v in r.items():
+                out[f"{nm}.{k}"] = v
+            print("hessian_rate", nm, r["J"], r["grad"], np.linalg.eigvalsh(r["hessian"]), flush=True)
+        np.savez_compressed(os.path.join(HERE, "ref_mp_hessian_rate.npz"), **out)
 
     if only is None or "hessian_jvp" in only:
         w = np.array([[1.0, 0.5, 0.0], [0.5, 1.0, 0.0], [0.0, 0.0, 0.25]])
