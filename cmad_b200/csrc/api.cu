@@ -842,8 +842,8 @@ static int64_t hess_partials_doubles(int64_t n, int32_t n_active) {
 int64_t cmadx_mp_hessian_workspace_bytes(int64_t n, int64_t ld, int32_t nsteps, int32_t n_active) {
     if (n < 0 || ld < n || nsteps < 0 || n_active < 0 || n_active > CMADX_MAX_ACTIVE) return -1;
     const int64_t npairs = (int64_t)n_active * (n_active + 1) / 2;
-    // phi_hist is sized for the largest local system (n_xi = 9, UNIAXIAL_STRESS)
-    return (int64_t)sizeof(double) * ((int64_t)(nsteps + 1) * 9 * ld + hess_partials_doubles(n, n_active) + npairs + 1);
+    // phi_hist is sized for the largest local system (n_xi = 12, the rate form under UNIAXIAL_STRESS)
+    return (int64_t)sizeof(double) * ((int64_t)(nsteps + 1) * 12 * ld + hess_partials_doubles(n, n_active) + npairs + 1);
 }
 
 int cmadx_mp_objective_hessian(const cmadx_material_t* mat, const int32_t* active_pid,
@@ -858,8 +858,8 @@ int cmadx_mp_objective_hessian(const cmadx_material_t* mat, const int32_t* activ
         A.m.yield == CMADX_YIELD_BARLAT)
         return CMADX_EUNSUPPORTED;
     const int dt = history_def_type(hist);
-    if (rate && dt != CMADX_DEF_FULL_3D) return CMADX_EUNSUPPORTED;         // the rate form: FULL_3D (mp_hess_rate_kernel)
-    if (dt != CMADX_DEF_FULL_3D && A.m.rot) return CMADX_EUNSUPPORTED;      // rotated axes: FULL_3D only in this pass
+    // rotated axes: FULL_3D, and the rate form in every def-type (mp_hess_rate_dt_kernel)
+    if (dt != CMADX_DEF_FULL_3D && A.m.rot && !rate) return CMADX_EUNSUPPORTED;
     if (n_active < 0 || n_active > CMADX_MAX_ACTIVE || (n_active > 0 && !active_pid)) return CMADX_EINVAL;
     if (!hist->result || !hist->workspace || (hist->n > 0 && !hist->data)) return CMADX_EINVAL;
     for (int c = 0; c < n_active; ++c) {
@@ -871,11 +871,11 @@ int cmadx_mp_objective_hessian(const cmadx_material_t* mat, const int32_t* activ
     A.n_active = n_active;
     A.h = *hist;
     A.phi_hist = hist->workspace;
-    A.partials = hist->workspace + (int64_t)(hist->nsteps + 1) * 9 * hist->ld;
+    A.partials = hist->workspace + (int64_t)(hist->nsteps + 1) * 12 * hist->ld;
     double* pair_sums = A.partials + hess_partials_doubles(hist->n, n_active);
     cudaStream_t s = (cudaStream_t)stream;
     // J, dJ/dp, and phi_t for every step
-    cudaError_t e = rate ? launch_mp_sens_rate(A, true, s)
+    cudaError_t e = rate ? (dt == CMADX_DEF_FULL_3D ? launch_mp_sens_rate(A, true, s) : launch_mp_sens_rate_dt(A, dt, true, s))
                     : (dt == CMADX_DEF_FULL_3D) ? launch_mp_sens(A, true, s) : launch_mp_sens_dt(A, dt, true, s);
     if (e != cudaSuccess) return cuda_fail(e);
     e = launch_mp_hess(A, dt, pair_sums, hist->result + 1 + n_active, s);

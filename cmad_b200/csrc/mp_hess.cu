@@ -24,7 +24,7 @@
 #include "mp_outputs.cuh"
 #include "mp_sens.cuh"
 #include "sep_point_dt.cuh"
-#include "rate_point.cuh"
+#include "rate_point_dt.cuh"
 
 namespace cmadx {
 cudaError_t launch_reduce_partials(const double* partials, int64_t nblk, int ncols, double* result,
@@ -852,6 +852,209 @@ __global__ void __launch_bounds__(HESS_BLOCK) mp_hess_dt_kernel(const __grid_con
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// SmallRateElasticPlastic under PLANE_STRESS / UNIAXIAL_STRESS (n_xi 8 / 12; rate_point_dt.cuh,
+// small_rate_elastic_plastic.py:189-199, 312-343): the stretch unknowns enter the global strain
+// increment as z - z_prev, the off-axis delta strains directly; the constraint rows act on the GLOBAL
+// stress increment S Cel (dem - dgamma n) / 2mu.  Identity and rotated axes share the code path
+// (T = S = I).  X_t as in mp_sens_rate_dt.cu's direct recurrence.
+template <int YK, int DT, int N>
+__device__ __forceinline__ double lagrangian_mixed_rate_dt(const DevMat& m, const HessParams& P, const HD (&x)[N],
+                                                        const HD (&xp)[N], const double (&em)[6],
+                                                        const double (&phi)[N], const double (&w)[9],
+                                                        const double (&d)[9], bool plastic,
+                                                        const double (&T)[6][6], const double (&S)[6][6]) {
+    using Pt = RatePointDT<YK, DT>;
+    HD deg[6];
+    if (DT == CMADX_DEF_PLANE_STRESS) {
+        deg[0] = hd(em[0]); deg[1] = hd(em[1]); deg[2] = hd(0.0); deg[3] = hd(em[3]); deg[4] = hd(0.0);
+        deg[5] = x[7] - xp[7];
+    } else {
+        deg[0] = hd(em[0]); deg[1] = x[N > 9 ? 9 : 0]; deg[2] = x[N > 10 ? 10 : 0]; deg[3] = x[7] - xp[7];
+        deg[4] = x[N > 11 ? 11 : 0]; deg[5] = x[N > 8 ? 8 : 0] - xp[N > 8 ? 8 : 0];
+    }
+    HD wv[6], sig[6], sg[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        HD acc = hd(0.0), gl = hd(0.0);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { acc = acc + T[a][c] * deg[c]; gl = gl + S[a][c] * x[c]; }
+        wv[a] = acc;
+        sig[a] = x[a];
+        sg[a] = gl;
+    }
+    HD L = qoi_hd(sg, w, d);
+    const HD two_mu = 2.0 * P.mu;
+    const HD i2mu = inv(two_mu);
+    const HD dg = x[6] - xp[6];
+    if (plastic) {
+        HD pe, n[6];
+        yield_hd<YK>(m, P, sig, pe, n);
+        HD hard = P.Y;
+        if (m.hmask & CMADX_HARD_VOCE) hard = hard + P.S * (1.0 - hexp(-(P.D * x[6])));
+        if (m.hmask & CMADX_HARD_LINEAR) hard = hard + P.K * x[6];
+        L = L + phi[6] * ((pe - hard) * i2mu);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) wv[a] = wv[a] - dg * n[a];
+    } else {
+        L = L + phi[6] * dg;
+    }
+    const HD ltr = P.lam * (wv[0] + wv[3] + wv[5]);
+    HD inc[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        inc[a] = is_diag(a) ? two_mu * wv[a] + ltr : two_mu * wv[a];
+        L = L + phi[a] * ((x[a] - xp[a] - inc[a]) * i2mu);
+    }
+#pragma unroll
+    for (int r = 0; r < Pt::NR; ++r) {
+        const int c = Pt::ccomp(r);
+        HD gi = hd(0.0);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) gi = gi + S[c][a] * inc[a];
+        L = L + phi[7 + r] * (gi * i2mu);
+    }
+    return L.ab;
+}
+
+template <int YK, int DT>
+__global__ void __launch_bounds__(HESS_BLOCK) mp_hess_rate_dt_kernel(const __grid_constant__ SensArgs A) {
+    using Pt = RatePointDT<YK, DT>;
+    constexpr int N = Pt::N, NZ = Pt::NZ;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < A.h.n;
+    const int64_t ld = A.h.ld;
+    const DevMat& m = A.m;
+    const int NT = A.h.nsteps, na = A.n_active, sc = A.h.strain_comps;
+    const int npairs = na * (na + 1) / 2;
+    extern __shared__ double hs[];
+    auto X = [&](int c, int r) -> double& { return hs[(c * N + r) * HESS_BLOCK + threadIdx.x]; };
+    auto Xp = [&](int c, int r) -> double& { return hs[((na + c) * N + r) * HESS_BLOCK + threadIdx.x]; };
+    auto Hacc = [&](int q) -> double& { return hs[(2 * na * N + q) * HESS_BLOCK + threadIdx.x]; };
+    for (int q = 0; q < npairs; ++q) Hacc(q) = 0.0;
+    for (int c = 0; c < na; ++c)
+#pragma unroll
+        for (int r = 0; r < N; ++r) { X(c, r) = 0.0; Xp(c, r) = 0.0; }
+    double x[N], xp[N], ep[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        const double v = live ? __ldg(A.h.xi_hist + c * ld + i) : ((c >= 7 && c < 7 + NZ) ? 1.0 : 0.0);
+        x[c] = v; xp[c] = v;
+    }
+    if (live) load_dt_strain<DT>(A.h.strain, sc, ld, i, ep);
+    for (int t = 1; t <= NT; ++t) {
+        double em[6] = {1e-3, 0.0, 0.0, 0.0, 0.0, 0.0}, d[9], phi[N];
+        if (live) {
+            const double* xs = A.h.xi_hist + (int64_t)t * N * ld + i;
+            const double* ph = A.phi_hist + (int64_t)t * N * ld + i;
+#pragma unroll
+            for (int c = 0; c < N; ++c) { x[c] = __ldg(xs + c * ld); phi[c] = ph[c * ld]; }
+            double et[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            load_dt_strain<DT>(A.h.strain + (int64_t)t * sc * ld, sc, ld, i, et);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { em[c] = et[c] - ep[c]; ep[c] = et[c]; }
+            const double* ds = A.h.data + (int64_t)t * 9 * ld + i;
+#pragma unroll
+            for (int c = 0; c < 9; ++c) d[c] = __ldg(ds + c * ld);
+        } else {
+            x[0] = 1.0;
+#pragma unroll
+            for (int c = 0; c < 9; ++c) d[c] = 0.0;
+#pragma unroll
+            for (int c = 0; c < N; ++c) phi[c] = 0.0;
+        }
+        Pt pt;
+        double C[N];
+        pt.residual(m, x, xp, em, C);
+        const bool pl = pt.plastic;
+        const double dg = x[6] - xp[6];
+        {
+            double Am[N][N];
+            pt.jacobian(m, dg, Am);
+            RegLU<N> lu;
+#pragma unroll
+            for (int a = 0; a < N; ++a)
+#pragma unroll
+                for (int b = 0; b < N; ++b) lu.a[a][b] = Am[a][b];
+            const bool trouble = lu.factor_natural();
+            const bool slow = __any_sync(__activemask(), trouble);
+            if (slow && trouble) {
+#pragma unroll
+                for (int a = 0; a < N; ++a)
+#pragma unroll
+                    for (int b = 0; b < N; ++b) lu.a[a][b] = Am[a][b];
+                lu.factor_pivot();
+            }
+            for (int c = 0; c < na; ++c) {
+                double col[N], rhs[N], xpv[N];
+                rate_dt_dC_dp_column<YK, DT>(m, A.pid[c], pt, x, xp, col);
+#pragma unroll
+                for (int k = 0; k < N; ++k) xpv[k] = Xp(c, k);
+#pragma unroll
+                for (int q = 0; q < N; ++q) {
+                    double v = -col[q];
+#pragma unroll
+                    for (int k = 0; k < N; ++k) v = fma(-rate_dt_B(m, pt, Am, q, k), xpv[k], v);
+                    rhs[q] = v;
+                }
+                if (slow && trouble) lu.solve_pivot(rhs); else lu.solve_natural(rhs);
+#pragma unroll
+                for (int q = 0; q < N; ++q) X(c, q) = rhs[q];
+            }
+        }
+        int q = 0;
+#pragma unroll 1
+        for (int ci = 0; ci < na; ++ci) {
+#pragma unroll 1
+            for (int cj = ci; cj < na; ++cj, ++q) {
+                const int pi = A.pid[ci], pj = A.pid[cj];
+                HessParams P;
+                {
+                    const int ki = pi - CMADX_P_EL0, kj = pj - CMADX_P_EL0;
+                    const bool ei = (ki == 0 || ki == 1), ej = (kj == 0 || kj == 1);
+                    const int k2 = ki + kj;
+                    P.lam = {m.lam, ei ? m.dlam[ki] : 0.0, ej ? m.dlam[kj] : 0.0, (ei && ej) ? m.d2lam[k2] : 0.0};
+                    P.mu = {m.mu, ei ? m.dmu[ki] : 0.0, ej ? m.dmu[kj] : 0.0, (ei && ej) ? m.d2mu[k2] : 0.0};
+                }
+                P.Y = seed(m.Y, CMADX_P_Y, pi, pj);
+                P.S = seed(m.S, CMADX_P_VOCE_S, pi, pj);
+                P.D = seed(m.D, CMADX_P_VOCE_D, pi, pj);
+                P.K = seed(m.K, CMADX_P_LIN_K, pi, pj);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) P.hill[k] = seed(m.hill[k], CMADX_P_HILL_F + k, pi, pj);
+                HD xh[N], xph[N];
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    xh[r] = {x[r], X(ci, r), X(cj, r), 0.0};
+                    xph[r] = {xp[r], Xp(ci, r), Xp(cj, r), 0.0};
+                }
+                Hacc(q) += lagrangian_mixed_rate_dt<YK, DT, N>(m, P, xh, xph, em, phi, A.h.weight, d, pl, pt.T, pt.S);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < N; ++c) xp[c] = x[c];
+        for (int c = 0; c < na; ++c)
+#pragma unroll
+            for (int r = 0; r < N; ++r) Xp(c, r) = X(c, r);
+    }
+    __shared__ double sm[HESS_BLOCK / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = 0; q < npairs; ++q) {
+        double v = live ? Hacc(q) : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) sm[warp] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+#pragma unroll
+            for (int wq = 0; wq < HESS_BLOCK / 32; ++wq) s += sm[wq];
+            A.partials[(int64_t)blockIdx.x * npairs + q] = s;
+        }
+        __syncthreads();
+    }
+}
+
 // dynamic shared memory of a block: (2 na n_xi + npairs) doubles per thread
 template <class K>
 cudaError_t launch_hess_kernel(K kernel, const SensArgs& A, int n_xi, unsigned nblk, cudaStream_t stream) {
@@ -868,6 +1071,15 @@ cudaError_t launch_hess_kernel(K kernel, const SensArgs& A, int n_xi, unsigned n
 template <int DT>
 cudaError_t launch_hess_dt(const SensArgs& A, unsigned nblk, cudaStream_t stream) {
     constexpr int NX = (DT == CMADX_DEF_PLANE_STRESS) ? 8 : 9;
+    if (A.m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC) {
+        constexpr int NR = (DT == CMADX_DEF_PLANE_STRESS) ? 8 : 12;
+        switch (A.m.yield) {
+        case CMADX_YIELD_J2: return launch_hess_kernel(mp_hess_rate_dt_kernel<CMADX_YIELD_J2, DT>, A, NR, nblk, stream);
+        case CMADX_YIELD_HILL: return launch_hess_kernel(mp_hess_rate_dt_kernel<CMADX_YIELD_HILL, DT>, A, NR, nblk, stream);
+        case CMADX_YIELD_HOSFORD: return launch_hess_kernel(mp_hess_rate_dt_kernel<CMADX_YIELD_HOSFORD, DT>, A, NR, nblk, stream);
+        default: return cudaErrorInvalidValue;
+        }
+    }
     switch (A.m.yield) {
     case CMADX_YIELD_J2: return launch_hess_kernel(mp_hess_dt_kernel<CMADX_YIELD_J2, DT>, A, NX, nblk, stream);
     case CMADX_YIELD_HILL: return launch_hess_kernel(mp_hess_dt_kernel<CMADX_YIELD_HILL, DT>, A, NX, nblk, stream);

@@ -113,6 +113,11 @@ __global__ void __launch_bounds__(SENS_BLOCK) mp_sens_rate_dt_kernel(const __gri
 #pragma unroll
             for (int c = 0; c < N; ++c) phi[c] = hist[c] - dJdx[c];
             solveN(phi);
+            if (A.phi_hist && live) {      // kept for the direct-adjoint Hessian pass (mp_hess.cu)
+                double* ph = A.phi_hist + (int64_t)t * N * ld + i;
+#pragma unroll
+                for (int c = 0; c < N; ++c) ph[c * ld] = phi[c];
+            }
             // h <- -B^T phi
 #pragma unroll
             for (int c = 0; c < N; ++c) {

@@ -320,7 +320,10 @@ int cmadx_mp_objective_host(const cmadx_material_t* mat, const cmadx_newton_t* n
  * QoI.evaluate_hessians (cmad/models/model.py:134-148, 245-270).  `result` holds
  * 1 + n_active + n_active^2 doubles: J, grad, H row-major (symmetric).  `workspace` needs
  * cmadx_mp_hessian_workspace_bytes().  FULL_3D, PLANE_STRESS and UNIAXIAL_STRESS (by
- * strain_comps, as for the gradient entry points), identity material axes; deterministic.
+ * strain_comps, as for the gradient entry points); deterministic.  SmallElasticPlastic: rotated
+ * material axes in FULL_3D.  SmallRateElasticPlastic (small_rate_elastic_plastic.py:250-346): the
+ * three def-types, identity and rotated axes; its QoI reads the state's stress, so both flag
+ * settings give the same Hessian.
  * flags: 0 = the complete Hessian (equals the derivative of the gradient).
  * CMADX_HESS_F_REFERENCE_QOI_CROSS reproduces the reference entry for entry: its QoI builds
  * the mixed block d2J/dxi dparams by differentiating w.r.t. xi_PREV (cmad/qois/qoi.py:53-55),

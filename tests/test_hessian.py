@@ -435,3 +435,140 @@ def test_cuda_hessian_rotated_axes_vs_reference(cuda_device, case):
         xp_[c] += h; xm_[c] -= h
         fd[:, c] = (grad_obj.evaluate(xp_).grad - grad_obj.evaluate(xm_).grad) / (2 * h)
     assert hess_err(rc.hessian, 0.5 * (fd + fd.T)) < 2e-5, hess_err(rc.hessian, 0.5 * (fd + fd.T))
+
+
+# ------------------------------------------------------------------------------------------ #
+#  SmallRateElasticPlastic (FULL_3D, identity and rotated material axes): the reference's own   #
+#  MPDirectAdjointObjective on the rate form (ref_mp_hessian_rate.npz).  The QoI reads the      #
+#  state's stress, so the reference's Hessian is complete for this model.                       #
+# ------------------------------------------------------------------------------------------ #
+HRT = np.load(os.path.join(G, "ref_mp_hessian_rate.npz"))
+CASES_RATE = sorted({k.rsplit(".", 1)[0] for k in HRT.files})
+
+
+def test_rate_hessian_fixture_set():
+    assert {c.split(".")[0] for c in CASES_RATE} == {"J2", "hill", "hosford", "hill_rot"}
+    for case in CASES_RATE:
+        H = HRT[f"{case}.hessian"]
+        assert np.isfinite(H).all() and np.abs(H - H.T).max() < 1e-8 * np.abs(H).max()
+
+
+@pytest.mark.parametrize("case", ["J2.scaled", "hill_rot.native"])
+def test_torch_oracle_rate_hessian_vs_reference(case):
+    kind, mode = case.split(".")
+    values, act, tr = objective_trees(kind, mode == "scaled")
+    P = co.OracleParameters(values, act, tr)
+    spec = co.ModelSpec(kind="small_rate_elastic_plastic")
+    J, g, H = co.mp_objective_direct_adjoint(P, HRT[f"{case}.F"], HRT[f"{case}.data"], HRT[f"{case}.weight"], spec,
+                                             HRT[f"{case}.x_canonical"], True, reference_qoi_cross_terms=True)
+    assert abs(J - HRT[f"{case}.J"]) < 1e-11 * abs(J)
+    assert np.abs(g - HRT[f"{case}.grad"]).max() < 1e-9 * np.abs(g).max()
+    assert hess_err(H, HRT[f"{case}.hessian"]) < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES_RATE)
+def test_cuda_rate_hessian_vs_reference(cuda_device, case):
+    from cmad_b200.objectives import Calibration, MPAdjointObjective, MPDirectAdjointObjective, SmallRateElasticPlastic
+    kind, mode = case.split(".")
+    x = HRT[f"{case}.x_canonical"]
+    F, data, w = HRT[f"{case}.F"], HRT[f"{case}.data"], HRT[f"{case}.weight"]
+
+    def run(compat):
+        P = Parameters(*objective_trees(kind, mode == "scaled"))
+        assert np.array_equal(P.active_idx, HRT[f"{case}.active_idx"])
+        return MPDirectAdjointObjective(Calibration(SmallRateElasticPlastic(P), data, w), F, device=cuda_device,
+                                        reference_qoi_cross_terms=compat).evaluate(x), P
+    r, _ = run(True)
+    assert abs(r.J - HRT[f"{case}.J"]) < 1e-11 * abs(r.J)
+    assert np.abs(r.grad - HRT[f"{case}.grad"]).max() < 1e-9 * np.abs(r.grad).max()
+    assert hess_err(r.hessian, HRT[f"{case}.hessian"]) < 1e-8, hess_err(r.hessian, HRT[f"{case}.hessian"])
+    assert np.array_equal(r.hessian, r.hessian.T)
+    # complete = reference-compatible for this model (no parameter enters the QoI)
+    rc, P = run(False)
+    assert np.array_equal(rc.hessian, r.hessian)
+    # ... and it is the derivative of the CUDA adjoint gradient once every step's Newton solve has
+    # converged: the reference's 10 imperative iterations leave step 6 of `hill.native` unconverged (it
+    # needs 13; the fixture - and the comparison above - carry that state), so the check runs with 60
+    from cmad_b200 import NewtonSettings
+    from cmad_b200.objectives import _single_point_objective
+    nw = NewtonSettings(mode="imperative", max_iters=60, abs_tol=1e-14, rel_tol=1e-14)
+    qoi = Calibration(SmallRateElasticPlastic(P), data, w)
+    Hc = _single_point_objective(qoi, F, "direct_adjoint", cuda_device, newton=nw).evaluate(x).hessian
+    grad_obj = _single_point_objective(qoi, F, "adjoint", cuda_device, newton=nw)
+    fd = np.zeros_like(Hc)
+    for c in range(len(x)):
+        h = 1e-6 * max(abs(x[c]), 1e-2)
+        xp_, xm_ = x.copy(), x.copy()
+        xp_[c] += h; xm_[c] -= h
+        fd[:, c] = (grad_obj.evaluate(xp_).grad - grad_obj.evaluate(xm_).grad) / (2 * h)
+    assert hess_err(Hc, 0.5 * (fd + fd.T)) < 2e-5, hess_err(Hc, 0.5 * (fd + fd.T))
+
+
+# ------------------------------------------------------------------------------------------ #
+#  The rate form under PLANE_STRESS / UNIAXIAL_STRESS (n_xi 8 / 12), identity and rotated axes  #
+#  (ref_mp_hessian_rate_dt.npz, the reference's own MPDirectAdjointObjective)                   #
+# ------------------------------------------------------------------------------------------ #
+HRD = np.load(os.path.join(G, "ref_mp_hessian_rate_dt.npz"))
+CASES_RATE_DT = sorted({k.rsplit(".", 1)[0] for k in HRD.files})
+
+
+def hess_err_sensitive(H, Href, grad, x):
+    """`hess_err` over the parameters the objective depends on.  Under uniaxial stress J does not see
+    nu (the reference's own gradient entry is 1e-10 of the others, its Hessian row rounding noise):
+    such rows are required to vanish on the scale of the others instead of being compared entry by
+    entry against noise."""
+    s = np.abs(grad * x)
+    keep = s > 1e-9 * s.max()
+    scale = np.abs(np.diag(Href) * x * x)[keep].max()
+    for i in np.nonzero(~keep)[0]:
+        assert (np.abs(H[i] * x[i] * x).max() < 1e-8 * scale) and (np.abs(Href[i] * x[i] * x).max() < 1e-8 * scale)
+    return hess_err(H[np.ix_(keep, keep)], Href[np.ix_(keep, keep)])
+
+
+def test_rate_def_type_hessian_fixture_set():
+    assert {c.rsplit(".", 1)[1] for c in CASES_RATE_DT} == {"PLANE_STRESS", "UNIAXIAL_STRESS"}
+    assert any(c.startswith("hill_rot") for c in CASES_RATE_DT)
+
+
+@pytest.mark.parametrize("case", [c for c in CASES_RATE_DT if c.startswith(("J2.scaled.PLANE", "hill_rot.native.UNIAXIAL"))])
+def test_torch_oracle_rate_hessian_vs_reference_def_types(case):
+    kind, mode, dtn = case.split(".")
+    values, act, tr = objective_trees(kind, mode == "scaled")
+    P = co.OracleParameters(values, act, tr)
+    spec = co.ModelSpec(kind="small_rate_elastic_plastic", def_type=getattr(co, dtn))
+    J, g, H = co.mp_objective_direct_adjoint(P, HRD[f"{case}.F"], HRD[f"{case}.data"], HRD[f"{case}.weight"], spec,
+                                             HRD[f"{case}.x_canonical"], True, reference_qoi_cross_terms=True)
+    assert abs(J - HRD[f"{case}.J"]) < 1e-10 * abs(J)
+    assert np.abs(g - HRD[f"{case}.grad"]).max() < 1e-8 * np.abs(g).max()
+    xn = HRD[f"{case}.active_native"] if mode == "native" else np.ones_like(g)
+    assert hess_err_sensitive(H, HRD[f"{case}.hessian"], HRD[f"{case}.grad"], xn) < 1e-7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES_RATE_DT)
+def test_cuda_rate_hessian_vs_reference_def_types(cuda_device, case):
+    from cmad_b200 import NewtonSettings
+    from cmad_b200 import objectives as ob
+    kind, mode, dtn = case.split(".")
+    x = HRD[f"{case}.x_canonical"]
+    F, data, w = HRD[f"{case}.F"], HRD[f"{case}.data"], HRD[f"{case}.weight"]
+    P = Parameters(*objective_trees(kind, mode == "scaled"))
+    assert np.array_equal(P.active_idx, HRD[f"{case}.active_idx"])
+    qoi = ob.Calibration(ob.SmallRateElasticPlastic(P, def_type=getattr(ob, dtn)), data, w)
+    r = ob.MPDirectAdjointObjective(qoi, F, device=cuda_device, reference_qoi_cross_terms=True).evaluate(x)
+    assert abs(r.J - HRD[f"{case}.J"]) < 1e-10 * abs(r.J)
+    assert np.abs(r.grad - HRD[f"{case}.grad"]).max() < 1e-8 * np.abs(r.grad).max()
+    xn = HRD[f"{case}.active_native"] if mode == "native" else np.ones_like(x)
+    assert hess_err_sensitive(r.hessian, HRD[f"{case}.hessian"], HRD[f"{case}.grad"], xn) < 1e-7
+    # with every Newton solve converged: the derivative of the CUDA adjoint gradient
+    nw = NewtonSettings(mode="imperative", max_iters=60, abs_tol=1e-14, rel_tol=1e-14)
+    Hc = ob._single_point_objective(qoi, F, "direct_adjoint", cuda_device, newton=nw).evaluate(x).hessian
+    grad_obj = ob._single_point_objective(qoi, F, "adjoint", cuda_device, newton=nw)
+    fd = np.zeros_like(Hc)
+    for c in range(len(x)):
+        h = 1e-6 * max(abs(x[c]), 1e-2)
+        xp_, xm_ = x.copy(), x.copy()
+        xp_[c] += h; xm_[c] -= h
+        fd[:, c] = (grad_obj.evaluate(xp_).grad - grad_obj.evaluate(xm_).grad) / (2 * h)
+    assert hess_err_sensitive(Hc, 0.5 * (fd + fd.T), HRD[f"{case}.grad"], xn) < 2e-5

@@ -130,17 +130,6 @@ def test_cuda_rate_objectives_vs_reference(cuda_device, case):
         assert rel_err(r.grad, RO[f"{case}.grad_{strategy}"]) < 1e-9, (case, strategy, r.grad)
 
 
-@pytest.mark.gpu
-def test_cuda_rate_objective_hessian_is_refused(cuda_device):
-    from cmad_b200.objectives import Calibration, MPDirectAdjointObjective, SmallRateElasticPlastic
-    case = "J2.scaled"
-    values, act, tr = _rate_objective_parameters(case)
-    obj = MPDirectAdjointObjective(Calibration(SmallRateElasticPlastic(Parameters(values, act, tr)),
-                                               RO[f"{case}.data"], RO[f"{case}.weight"]), RO[f"{case}.F"], device=cuda_device)
-    with pytest.raises(NotImplementedError):
-        obj.evaluate(RO[f"{case}.x_canonical"])
-
-
 # ------------------------------------------------------------------------------------------ #
 #  FE element blocks of the rate form: per_element_R_and_K_coupled over the rate model's        #
 #  per-IP COUPLED evaluator, with the real previous displacement (fixture ref_rate_fe_elements) #
