@@ -858,8 +858,6 @@ int cmadx_mp_objective_hessian(const cmadx_material_t* mat, const int32_t* activ
         A.m.yield == CMADX_YIELD_BARLAT)
         return CMADX_EUNSUPPORTED;
     const int dt = history_def_type(hist);
-    // rotated axes: FULL_3D, and the rate form in every def-type (mp_hess_rate_dt_kernel)
-    if (dt != CMADX_DEF_FULL_3D && A.m.rot && !rate) return CMADX_EUNSUPPORTED;
     if (n_active < 0 || n_active > CMADX_MAX_ACTIVE || (n_active > 0 && !active_pid)) return CMADX_EINVAL;
     if (!hist->result || !hist->workspace || (hist->n > 0 && !hist->data)) return CMADX_EINVAL;
     for (int c = 0; c < n_active; ++c) {

@@ -658,6 +658,66 @@ CMADX_DEV void stress_hd_dt(const HD& lam, const HD& mu, const HD (&x)[N], const
     for (int a = 0; a < 6; ++a) sig[a] = is_diag(a) ? two_mu * ee[a] + ltr : two_mu * ee[a];
 }
 
+// rotated material axes (SepPointDTRot): the kinematic constraints live in GLOBAL axes
+// (uniaxial stress: the off-diagonal global strains are those of S ep), the update in material axes;
+// sig = material-frame stress, sg = S sig = what the QoI and the constraint rows read
+template <int DT, int N>
+__device__ __noinline__ void stress_hd_dt_rot(const HD& lam, const HD& mu, const HD (&x)[N], const double (&em)[6],
+                                const double (&T)[6][6], const double (&S)[6][6], HD (&sig)[6], HD (&sg)[6]) {
+    HD eg[6];
+    if (DT == CMADX_DEF_PLANE_STRESS) {
+        eg[0] = hd(em[0]); eg[1] = hd(em[1]); eg[2] = hd(0.0); eg[3] = hd(em[3]); eg[4] = hd(0.0); eg[5] = x[7] - 1.0;
+    } else {
+        HD og[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            HD acc = hd(0.0);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) acc = acc + S[a][c] * x[c];
+            og[a] = acc;
+        }
+        eg[0] = hd(em[0]); eg[1] = og[1]; eg[2] = og[2]; eg[3] = x[7] - 1.0; eg[4] = og[4]; eg[5] = x[N > 8 ? 8 : 7] - 1.0;
+    }
+    HD ee[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        HD acc = hd(0.0);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc = acc + T[a][c] * eg[c];
+        ee[a] = acc - x[a];
+    }
+    const HD ltr = lam * (ee[0] + ee[3] + ee[5]);
+    const HD two_mu = 2.0 * mu;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) sig[a] = is_diag(a) ? two_mu * ee[a] + ltr : two_mu * ee[a];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        HD acc = hd(0.0);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc = acc + S[a][c] * sig[c];
+        sg[a] = acc;
+    }
+}
+
+template <int DT, int N>
+__device__ __noinline__ double qoi_cross_terms_dt_rot(const HD& lam, const HD& mu, const HD (&x)[N],
+                                                      const double (&em)[6], const double (&w)[9],
+                                                      const double (&d)[9], const double (&T)[6][6],
+                                                      const double (&S)[6][6]) {
+    double acc = 0.0;
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+        const HD l = side ? HD{lam.v, 0.0, lam.b, 0.0} : HD{lam.v, lam.a, 0.0, 0.0};
+        const HD u = side ? HD{mu.v, 0.0, mu.b, 0.0} : HD{mu.v, mu.a, 0.0, 0.0};
+        HD xs[N], sig[6], sg[6];
+#pragma unroll
+        for (int r = 0; r < N; ++r) xs[r] = side ? HD{x[r].v, x[r].a, 0.0, 0.0} : HD{x[r].v, 0.0, x[r].b, 0.0};
+        stress_hd_dt_rot<DT, N>(l, u, xs, em, T, S, sig, sg);
+        acc += qoi_hd(sg, w, d).ab;
+    }
+    return acc;
+}
+
 template <int DT, int N>
 __device__ __noinline__ double qoi_cross_terms_dt(const HD& lam, const HD& mu, const HD (&x)[N],
                                                   const double (&em)[6], const double (&w)[9],
@@ -676,17 +736,26 @@ __device__ __noinline__ double qoi_cross_terms_dt(const HD& lam, const HD& mu, c
     return acc;
 }
 
-template <int YK, int DT, int N>
+template <int YK, int DT, int N, bool ROT = false>
 __device__ __forceinline__ double lagrangian_mixed_dt(const DevMat& m, const HessParams& P, const HD (&x)[N],
                                                    const HD (&xp)[N], const double (&em)[6],
                                                    const double (&phi)[N], const double (&w)[9],
-                                                   const double (&d)[9], bool plastic) {
+                                                   const double (&d)[9], bool plastic,
+                                                   const double (*T)[6] = nullptr, const double (*S)[6] = nullptr) {
     constexpr int NZ = N - 7;
-    HD ee[6], sig[6];
-    stress_hd_dt<DT, N>(P.lam, P.mu, x, em, ee, sig);
+    HD sig[6], sg[6];
+    if constexpr (ROT) {
+        stress_hd_dt_rot<DT, N>(P.lam, P.mu, x, em, *reinterpret_cast<const double (*)[6][6]>(T),
+                                *reinterpret_cast<const double (*)[6][6]>(S), sig, sg);
+    } else {
+        HD ee[6];
+        stress_hd_dt<DT, N>(P.lam, P.mu, x, em, ee, sig);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) sg[a] = sig[a];
+    }
     const HD two_mu = 2.0 * P.mu;
     const HD i2m = inv(two_mu);
-    HD L = qoi_hd(sig, w, d);
+    HD L = qoi_hd(sg, w, d);
     if (plastic) {
         HD pe, n[6];
         yield_hd<YK>(m, P, sig, pe, n);
@@ -704,13 +773,13 @@ __device__ __forceinline__ double lagrangian_mixed_dt(const DevMat& m, const Hes
     }
     // stress-constraint rows (both branches): cauchy_cc / 2mu for the stretch-driven components
 #pragma unroll
-    for (int k = 0; k < NZ; ++k) L = L + phi[7 + k] * (sig[SepPointDT<YK, DT>::zcomp(k)] * i2m);
+    for (int k = 0; k < NZ; ++k) L = L + phi[7 + k] * (sg[SepPointDT<YK, DT>::zcomp(k)] * i2m);
     return L.ab;
 }
 
-template <int YK, int DT>
+template <int YK, int DT, bool ROT = false>
 __global__ void __launch_bounds__(HESS_BLOCK) mp_hess_dt_kernel(const __grid_constant__ SensArgs A) {
-    using Pt = SepPointDT<YK, DT>;
+    using Pt = typename std::conditional<ROT, SepPointDTRot<YK, DT>, SepPointDT<YK, DT>>::type;
     constexpr int N = Pt::N, NZ = Pt::NZ;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < A.h.n;
@@ -757,7 +826,7 @@ __global__ void __launch_bounds__(HESS_BLOCK) mp_hess_dt_kernel(const __grid_con
         const bool pl = pt.plastic;
         const double dg = x[6] - xp[6];
         double et[6], ee[6], sig[6];
-        pt.total_strain(x, em, et);
+        pt.material_strain(x, em, et);
 #pragma unroll
         for (int a = 0; a < 6; ++a) ee[a] = et[a] - x[a];
         const double tree = ee[0] + ee[3] + ee[5];
@@ -822,9 +891,16 @@ __global__ void __launch_bounds__(HESS_BLOCK) mp_hess_dt_kernel(const __grid_con
                     xh[r] = {x[r], X(ci, r), X(cj, r), 0.0};
                     xph[r] = {xp[r], Xp(ci, r), Xp(cj, r), 0.0};
                 }
-                double hij = lagrangian_mixed_dt<YK, DT, N>(m, P, xh, xph, em, phi, A.h.weight, d, pl);
-                if (A.hess_flags & CMADX_HESS_F_REFERENCE_QOI_CROSS)
-                    hij -= qoi_cross_terms_dt<DT, N>(P.lam, P.mu, xh, em, A.h.weight, d);
+                double hij;
+                if constexpr (ROT) {
+                    hij = lagrangian_mixed_dt<YK, DT, N, true>(m, P, xh, xph, em, phi, A.h.weight, d, pl, pt.T, pt.S);
+                    if (A.hess_flags & CMADX_HESS_F_REFERENCE_QOI_CROSS)
+                        hij -= qoi_cross_terms_dt_rot<DT, N>(P.lam, P.mu, xh, em, A.h.weight, d, pt.T, pt.S);
+                } else {
+                    hij = lagrangian_mixed_dt<YK, DT, N>(m, P, xh, xph, em, phi, A.h.weight, d, pl);
+                    if (A.hess_flags & CMADX_HESS_F_REFERENCE_QOI_CROSS)
+                        hij -= qoi_cross_terms_dt<DT, N>(P.lam, P.mu, xh, em, A.h.weight, d);
+                }
                 Hacc(q) += hij;
             }
         }
@@ -1077,6 +1153,14 @@ cudaError_t launch_hess_dt(const SensArgs& A, unsigned nblk, cudaStream_t stream
         case CMADX_YIELD_J2: return launch_hess_kernel(mp_hess_rate_dt_kernel<CMADX_YIELD_J2, DT>, A, NR, nblk, stream);
         case CMADX_YIELD_HILL: return launch_hess_kernel(mp_hess_rate_dt_kernel<CMADX_YIELD_HILL, DT>, A, NR, nblk, stream);
         case CMADX_YIELD_HOSFORD: return launch_hess_kernel(mp_hess_rate_dt_kernel<CMADX_YIELD_HOSFORD, DT>, A, NR, nblk, stream);
+        default: return cudaErrorInvalidValue;
+        }
+    }
+    if (A.m.rot) {
+        switch (A.m.yield) {
+        case CMADX_YIELD_J2: return launch_hess_kernel(mp_hess_dt_kernel<CMADX_YIELD_J2, DT, true>, A, NX, nblk, stream);
+        case CMADX_YIELD_HILL: return launch_hess_kernel(mp_hess_dt_kernel<CMADX_YIELD_HILL, DT, true>, A, NX, nblk, stream);
+        case CMADX_YIELD_HOSFORD: return launch_hess_kernel(mp_hess_dt_kernel<CMADX_YIELD_HOSFORD, DT, true>, A, NX, nblk, stream);
         default: return cudaErrorInvalidValue;
         }
     }

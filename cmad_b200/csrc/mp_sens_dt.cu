@@ -244,7 +244,6 @@ template <int DT, bool ADJOINT>
 cudaError_t launch_t(const SensArgs& A, cudaStream_t stream) {
     const int64_t nblk = (A.h.n + SENS_DT_BLOCK - 1) / SENS_DT_BLOCK;
     if (A.m.rot) {
-        if (A.phi_hist) return cudaErrorInvalidValue;       // the Hessian pass keeps identity axes
         switch (A.m.yield) {
         case CMADX_YIELD_J2:
             mp_sens_dt_kernel<CMADX_YIELD_J2, DT, ADJOINT, true><<<(unsigned)nblk, SENS_DT_BLOCK, 0, stream>>>(A); break;

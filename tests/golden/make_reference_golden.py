@@ -806,6 +806,26 @@ def main():
             print("hessian_rate_dt", nm, r["J"], r["grad"], np.linalg.eigvalsh(r["hessian"]), flush=True)
         np.savez_compressed(os.path.join(HERE, "ref_mp_hessian_rate_dt.npz"), **out)
 
+    if only is None or "hessian_dt_rot" in only:
+        # SmallElasticPlastic's Hessian in PLANE_STRESS / UNIAXIAL_STRESS with rotated material axes
+        jobs, names = [], []
+        for kind, scaled, dt_name in (("hill_rot", True, "PLANE_STRESS"), ("hill_rot", False, "PLANE_STRESS"),
+                                      ("hill_rot", True, "UNIAXIAL_STRESS"), ("hill_rot", False, "UNIAXIAL_STRESS")):
+            w = np.zeros((3, 3)); w[0, 0] = 1.0
+            if dt_name == "PLANE_STRESS":
+                w[1, 1] = 1.0; w[0, 1] = w[1, 0] = 0.5
+            jobs.append((kind, scaled, deftype_F(dt_name, nsteps=10), w, dt_name))
+            names.append(f"{kind}.{'scaled' if scaled else 'native'}.{dt_name}")
+        out = {}
+        for nm, r in zip(names, pool.map(_hessian_job, jobs, chunksize=1)):
+            if not np.all(np.isfinite(r["hessian"])):
+                print("hessian_dt_rot", nm, "NON-FINITE Hessian - case dropped")
+                continue
+            for k, v in r.items():
+                out[f"{nm}.{k}"] = v
+            print("hessian_dt_rot", nm, r["J"], r["grad"], np.linalg.eigvalsh(r["hessian"]), flush=True)
+        np.savez_compressed(os.path.join(HERE, "ref_mp_hessian_dt_rot.npz"), **out)
+
     if only is None or "fe" in only:
         jobs, names = [], []
         for family in ("tet4", "hex8"):
