@@ -229,10 +229,6 @@ static int build_args(const cmadx_material_t* mat, const cmadx_newton_t* nw,
         A->nw.defer_request = 0;
     }
     if (b->n < 0 || b->ld < b->n) return CMADX_EINVAL;
-    // the rate form under the def-types: mp_update_rate_dt.cu (n_xi 8 / 12), J2 / Hill / Hosford
-    if (A->m.model == CMADX_MODEL_SMALL_RATE_ELASTIC_PLASTIC && b->def_type != CMADX_DEF_FULL_3D &&
-        A->m.yield == CMADX_YIELD_BARLAT)
-        return CMADX_EUNSUPPORTED;
     if (b->def_type == CMADX_DEF_FULL_3D) {
         if (b->strain_comps != 6 && b->strain_comps != 9) return CMADX_EINVAL;
     } else if (b->def_type == CMADX_DEF_PLANE_STRESS || b->def_type == CMADX_DEF_UNIAXIAL_STRESS) {
@@ -631,8 +627,6 @@ static int check_history(const cmadx_material_t* mat, const cmadx_mp_history_t* 
     if (h->n < 0 || h->ld < h->n || h->nsteps < 0) return CMADX_EINVAL;
     const int sc = h->strain_comps;
     if (sc != 6 && sc != 9 && sc != 3 && sc != 4 && sc != 1) return CMADX_EINVAL;
-    // the rate model under the def-types (mp_update_rate_dt.cu, mp_sens_rate_dt.cu): J2 / Hill / Hosford
-    if (rate && sc != 6 && sc != 9 && dm->yield == CMADX_YIELD_BARLAT) return CMADX_EUNSUPPORTED;
     if (h->n > 0 && (!h->strain || !h->xi_hist)) return CMADX_EINVAL;
     if (h->qoi_kind != CMADX_QOI_CALIBRATION) {
         if (h->qoi_kind != CMADX_QOI_UNIAXIAL_CALIBRATION) return CMADX_EINVAL;

@@ -183,6 +183,7 @@ cudaError_t launch_t(const SensArgs& A, cudaStream_t stream) {
     case CMADX_YIELD_J2: mp_sens_rate_dt_kernel<CMADX_YIELD_J2, DT, ADJOINT><<<nblk, SENS_BLOCK, 0, stream>>>(A); break;
     case CMADX_YIELD_HILL: mp_sens_rate_dt_kernel<CMADX_YIELD_HILL, DT, ADJOINT><<<nblk, SENS_BLOCK, 0, stream>>>(A); break;
     case CMADX_YIELD_HOSFORD: mp_sens_rate_dt_kernel<CMADX_YIELD_HOSFORD, DT, ADJOINT><<<nblk, SENS_BLOCK, 0, stream>>>(A); break;
+    case CMADX_YIELD_BARLAT: mp_sens_rate_dt_kernel<CMADX_YIELD_BARLAT, DT, ADJOINT><<<nblk, SENS_BLOCK, 0, stream>>>(A); break;
     default: return cudaErrorInvalidValue;
     }
     cudaError_t e = cudaGetLastError();

@@ -139,6 +139,7 @@ cudaError_t launch_dt(const MpArgs& A, cudaStream_t stream) {
     case CMADX_YIELD_J2: mp_update_rate_dt_kernel<CMADX_YIELD_J2, DT><<<nblk, MP_BLOCK, 0, stream>>>(A); break;
     case CMADX_YIELD_HILL: mp_update_rate_dt_kernel<CMADX_YIELD_HILL, DT><<<nblk, MP_BLOCK, 0, stream>>>(A); break;
     case CMADX_YIELD_HOSFORD: mp_update_rate_dt_kernel<CMADX_YIELD_HOSFORD, DT><<<nblk, MP_BLOCK, 0, stream>>>(A); break;
+    case CMADX_YIELD_BARLAT: mp_update_rate_dt_kernel<CMADX_YIELD_BARLAT, DT><<<nblk, MP_BLOCK, 0, stream>>>(A); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

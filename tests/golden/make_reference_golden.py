@@ -967,6 +967,17 @@ def main():
                   "alpha", r["xi"][-1, 6], flush=True)
         np.savez_compressed(os.path.join(HERE, "ref_def_types_rate.npz"), **out)
 
+    if only is not None and "rate_deftypes_barlat" in only:
+        # Yld2004-18p in the rate form under the def-types (slow jobs, own file)
+        jobs = [("barlat", dt, "rate") for dt in ("PLANE_STRESS", "UNIAXIAL_STRESS")]
+        out = {}
+        for (kind, dt, _), r in zip(jobs, pool.map(_deftype_job, jobs, chunksize=1)):
+            for k, v in r.items():
+                out[f"{kind}.{dt}.{k}"] = v
+            print("rate deftypes", kind, dt, "iters", np.bincount(r["iters"]), "traced", np.bincount(r["traced_iters"]),
+                  "alpha", r["xi"][-1, 6], flush=True)
+        np.savez_compressed(os.path.join(HERE, "ref_def_types_rate_barlat.npz"), **out)
+
     if only is not None and "rate_rot" in only:
         # SmallRateElasticPlastic with rotated material axes (the case tests/models/
         # test_hill_material_rotations.py runs) and in the mixed u-p formulation (tests/fem/

@@ -16,9 +16,10 @@ import pytest
 from cmad_b200 import Parameters
 from tests.golden.materials import active_kernel_set, const_like, material
 from tests.helpers import UP, rel_err
-from tests.test_def_types import DEF, _strain_rows, _sym_cols_2d
+from tests.test_def_types import DEF, _Fixtures, _strain_rows, _sym_cols_2d
 
-RD = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_def_types_rate.npz"))
+# ref_def_types_rate_barlat.npz: the same jobs with the Yld2004-18p surface (`--only rate_deftypes_barlat`)
+RD = _Fixtures("ref_def_types_rate.npz", "ref_def_types_rate_barlat.npz")
 CASES = sorted({".".join(k.split(".")[:2]) for k in RD.files})
 
 
