@@ -630,7 +630,7 @@ static int check_history(const cmadx_material_t* mat, const cmadx_mp_history_t* 
     if (h->n > 0 && (!h->strain || !h->xi_hist)) return CMADX_EINVAL;
     if (h->qoi_kind != CMADX_QOI_CALIBRATION) {
         if (h->qoi_kind != CMADX_QOI_UNIAXIAL_CALIBRATION) return CMADX_EINVAL;
-        if (history_def_type(h) != CMADX_DEF_UNIAXIAL_STRESS || rate) return CMADX_EUNSUPPORTED;
+        if (history_def_type(h) != CMADX_DEF_UNIAXIAL_STRESS) return CMADX_EUNSUPPORTED;
         if (h->nsteps > 0 && !h->weight_steps) return CMADX_EINVAL;
     }
     return CMADX_OK;

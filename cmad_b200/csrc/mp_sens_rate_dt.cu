@@ -79,11 +79,29 @@ __global__ void __launch_bounds__(SENS_BLOCK) mp_sens_rate_dt_kernel(const __gri
             for (int c = 0; c < 6; ++c) v = fma(pt.S[a][c], x[c], v);
             sgl[a] = v;
         }
+        double dJdz[NZ];                   // direct dependence of the QoI on the stretch dofs
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const double mis = A.h.weight[k] * (sgl[comp[k]] - d[k]);
-            Jacc = fma(0.5 * mis, mis, Jacc);
-            r[comp[k]] = fma(A.h.weight[k], mis, r[comp[k]]);
+        for (int k = 0; k < NZ; ++k) dJdz[k] = 0.0;
+        if (DT == CMADX_DEF_UNIAXIAL_STRESS && A.h.qoi_kind == CMADX_QOI_UNIAXIAL_CALIBRATION) {
+            // UniaxialCalibration (cmad/qois/uniaxial_calibration.py:69-85): pred = [sigma_axial,
+            // lambda_2 - 1, lambda_3 - 1], weights of this step, data rows 0..2 (as in mp_sens_dt.cu)
+            const double* ws = A.h.weight_steps + (int64_t)t * 3;
+            const double w0 = __ldg(ws), mis0 = w0 * (sgl[0] - d[0]);
+            Jacc = fma(0.5 * mis0, mis0, Jacc);
+            r[0] = w0 * mis0;
+#pragma unroll
+            for (int k = 0; k < NZ; ++k) {
+                const double wk = __ldg(ws + 1 + k), mis = wk * (x[7 + k] - 1.0 - d[1 + k]);
+                Jacc = fma(0.5 * mis, mis, Jacc);
+                dJdz[k] = wk * mis;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const double mis = A.h.weight[k] * (sgl[comp[k]] - d[k]);
+                Jacc = fma(0.5 * mis, mis, Jacc);
+                r[comp[k]] = fma(A.h.weight[k], mis, r[comp[k]]);
+            }
         }
 #pragma unroll
         for (int c = 0; c < N; ++c) {
@@ -91,6 +109,8 @@ __global__ void __launch_bounds__(SENS_BLOCK) mp_sens_rate_dt_kernel(const __gri
             if (c < 6) {
 #pragma unroll
                 for (int a = 0; a < 6; ++a) v = fma(pt.S[a][c], r[a], v);
+            } else if (c >= 7 && c < 7 + NZ) {
+                v = dJdz[c - 7];
             }
             dJdx[c] = v;
         }

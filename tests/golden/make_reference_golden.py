@@ -595,12 +595,16 @@ def _rate_job(job):
 def _uniaxial_qoi_job(job):
     from cmad.models.deformation_types import DefType
     from cmad.qois.uniaxial_calibration import UniaxialCalibration
-    kind, scaled = job
+    kind, scaled = job[:2]
     F = deftype_F("UNIAXIAL_STRESS", nsteps=32)
     N = F.shape[2] - 1
     vals, act, tr = objective_trees(kind, scaled)
     Po = Parameters(vals, act, tr)
-    mo_ = SmallElasticPlastic(Po, def_type=DefType.UNIAXIAL_STRESS)
+    if len(job) > 2 and job[2] == "rate":
+        from cmad.models.small_rate_elastic_plastic import SmallRateElasticPlastic
+        mo_ = SmallRateElasticPlastic(Po, def_type=DefType.UNIAXIAL_STRESS)
+    else:
+        mo_ = SmallElasticPlastic(Po, def_type=DefType.UNIAXIAL_STRESS)
     data = np.zeros((3, N + 1))
     mo_.set_xi_to_init_vals()
     for step in range(1, N + 1):
@@ -890,6 +894,16 @@ def main():
                 out[f"{kind}.{'scaled' if sc else 'native'}.{k}"] = v
             print("uniaxial qoi", kind, sc, r["J_adjoint"], r["grad_adjoint"], r["grad_direct"])
         np.savez_compressed(os.path.join(HERE, "ref_uniaxial_qoi.npz"), **out)
+
+    if only is None or "uniaxial_qoi_rate" in only:
+        # UniaxialCalibration on the rate form (stretch block 2 as well), identity and rotated axes
+        jobs = [(k, sc, "rate") for k in ("J2", "hill_rot", "hosford") for sc in (True, False)]
+        out = {}
+        for (kind, sc, _), r in zip(jobs, pool.map(_uniaxial_qoi_job, jobs, chunksize=1)):
+            for k, v in r.items():
+                out[f"{kind}.{'scaled' if sc else 'native'}.{k}"] = v
+            print("uniaxial qoi rate", kind, sc, r["J_adjoint"], r["grad_adjoint"], r["grad_direct"], flush=True)
+        np.savez_compressed(os.path.join(HERE, "ref_uniaxial_qoi_rate.npz"), **out)
 
     if only is None or "rate_objective" in only:
         # MPAdjointObjective / MPDirectObjective + Calibration over SmallRateElasticPlastic

@@ -173,3 +173,49 @@ def test_cuda_objectives_vs_reference_rate_def_types(cuda_device, case, tag):
         r = obj.evaluate(RD[f"{pre}.x_canonical"])
         assert abs(r.J - RD[f"{pre}.J_{strategy}"]) < 1e-10 * abs(r.J), (case, tag, strategy)
         assert rel_err(r.grad, RD[f"{pre}.grad_{strategy}"]) < 1e-8, (case, tag, strategy, r.grad)
+
+
+# ------------------------------------------------------------------------------------------ #
+#  UniaxialCalibration on the rate form (axial stress + the two off-axis stretches, per-step    #
+#  weights; stretch block 2 of the rate model as well): ref_uniaxial_qoi_rate.npz               #
+# ------------------------------------------------------------------------------------------ #
+_UQR = os.path.join(os.path.dirname(__file__), "golden", "ref_uniaxial_qoi_rate.npz")
+UQR = np.load(_UQR)
+UQR_CASES = sorted({k.rsplit(".", 1)[0] for k in UQR.files})
+
+
+def test_uniaxial_qoi_rate_fixture_is_consistent():
+    assert {c.split(".")[0] for c in UQR_CASES} == {"J2", "hill_rot", "hosford"}
+    for case in UQR_CASES:
+        assert abs(UQR[f"{case}.J_adjoint"] - UQR[f"{case}.J_direct"]) < 1e-12 * abs(UQR[f"{case}.J_direct"])
+        assert rel_err(UQR[f"{case}.grad_adjoint"], UQR[f"{case}.grad_direct"]) < 1e-8
+        assert np.abs(UQR[f"{case}.data"][1:]).max() > 1e-3           # lateral strains are measured
+
+
+@pytest.mark.parametrize("case", ["J2.native", "hill_rot.scaled"])
+def test_torch_oracle_uniaxial_qoi_rate_vs_reference(case):
+    from oracle import cmad_oracle as co
+    from tests.golden.materials import objective_trees
+    kind, tag = case.split(".")
+    P = co.OracleParameters(*objective_trees(kind, tag == "scaled"))
+    spec = co.ModelSpec(kind="small_rate_elastic_plastic", def_type=co.UNIAXIAL_STRESS)
+    J, g = co.mp_objective_adjoint(P, UQR[f"{case}.F"], UQR[f"{case}.data"], UQR[f"{case}.weight"], spec,
+                                   UQR[f"{case}.x_canonical"], True)
+    assert abs(J - UQR[f"{case}.J_adjoint"]) < 1e-10 * abs(J)
+    assert rel_err(np.asarray(g), UQR[f"{case}.grad_adjoint"]) < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", UQR_CASES)
+def test_cuda_uniaxial_qoi_rate_vs_reference(cuda_device, case):
+    from cmad_b200 import objectives as ob
+    from tests.golden.materials import objective_trees
+    kind, tag = case.split(".")
+    for strategy, ctor in (("adjoint", ob.MPAdjointObjective), ("direct", ob.MPDirectObjective)):
+        P = Parameters(*objective_trees(kind, tag == "scaled"))
+        assert np.array_equal(P.active_idx, UQR[f"{case}.active_idx"])
+        model = ob.SmallRateElasticPlastic(P, def_type=ob.UNIAXIAL_STRESS)
+        qoi = ob.UniaxialCalibration(model, UQR[f"{case}.data"], UQR[f"{case}.weight"], uniaxial_stress_idx=0, stretch_var_idx=2)
+        r = ctor(qoi, UQR[f"{case}.F"], device=cuda_device).evaluate(UQR[f"{case}.x_canonical"])
+        assert abs(r.J - UQR[f"{case}.J_{strategy}"]) < 1e-10 * abs(r.J), (case, strategy)
+        assert rel_err(r.grad, UQR[f"{case}.grad_{strategy}"]) < 1e-8, (case, strategy, r.grad)
